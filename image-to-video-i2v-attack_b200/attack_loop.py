@@ -1,0 +1,205 @@
+"""The per-step attack loop shared by I2V, ENS-I2V and adaptive ENS-I2V.
+
+One function, `run_image_guided`, restates the common skeleton of reference
+image_attacks.py:294-364 (I2V), 426-496 (ENS-I2V) and TPAMI_attack.py:223-320 (AENS-I2V) around this
+repo's kernels:
+
+    setup    x = denorm(frames)                       K3  i2v_denorm_f32          (308)
+             modifier = 0.01/255, Adam m = v = 0                                   (304-306)
+             clean features of every hooked layer     engine.features             (318-323)
+             true_image = compose_norm(x, modifier)   K3  i2v_compose_norm_f32    (331-332)
+    step     [AENS] coeffs <- softmax(softmax(prev)+momentum*coeffs)   K2         (TPAMI 265)
+             features of true_image                   engine.features             (334)
+             per layer: cos[n], dcos/dfeat * w_l      K1  i2v_cosine_loss_grad    (341-347 + autograd)
+             dcost/dtrue_image                        engine.input_grad           (352)
+             cost / layer sums / prev                 K2  i2v_layer_sums_f32      (347; TPAMI 289-297)
+             Adam + next true_image                   K3a i2v_adam_compose_table  (351-353, 331-332)
+    finish   the last true_image IS the returned adversarial clip                  (360-364)
+
+Nothing in the loop synchronises with the host: the cost of every step and (AENS) the coefficient
+vectors go to device logs that are copied once after the loop (the reference syncs 2-5 times per
+step: print(cost), .cpu(), .item()).
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import capi
+
+INIT_MODIFIER = 0.01 / 255   # image_attacks.py:304
+BETA1, BETA2, ADAM_EPS = 0.9, 0.999, 1e-8   # torch.optim.Adam defaults (image_attacks.py:306)
+
+
+class LoopResult:
+    __slots__ = ("adv", "cost", "weights", "elapsed_ms")
+
+    def __init__(self, adv, cost, weights, elapsed_ms):
+        self.adv = adv
+        self.cost = cost
+        self.weights = weights
+        self.elapsed_ms = elapsed_ms
+
+
+def frames_of(videos):
+    """[b,c,f,h,w] -> contiguous [b*f,c,h,w] (image_attacks.py:300-301)."""
+    b, c, f, h, w = videos.shape
+    return videos.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w).contiguous()
+
+
+def clip_of(frames, b, f):
+    """[b*f,c,h,w] -> the reference's returned view [b,c,f,h,w] (image_attacks.py:362-363)."""
+    n, c, h, w = frames.shape
+    return frames.reshape(b, f, c, h, w).permute(0, 2, 1, 3, 4)
+
+
+def _chunk_frames(engines, N, chunk):
+    if chunk is None:
+        chunk = int(os.environ.get("I2V_CHUNK", "0")) or min(getattr(e, "preferred_chunk", 128) for e in engines)
+    return max(1, min(int(chunk), N))
+
+
+class ImageGuidedRun:
+    """One attack call, split into setup() / step() / finish() so that a benchmark can time exactly K
+    steps; `run_image_guided` is the plain composition the attack classes use.
+
+    adaptive=False: cost = sum of all cosines (I2V / ENS-I2V).
+    adaptive=True : AENS-I2V; `coeffs` is the persistent [L] device tensor (updated in place).
+    chunk      : frames per forward/backward sub-batch (bounds activation memory and keeps one
+                 chunk's activations L2-resident); frames are independent, so the result does not
+                 depend on it.  Default: $I2V_CHUNK or the engines' preferred size.
+    reduce_hook: optional object with .cos_rows(cos) / .grad(g) for multi-GPU runs (dist.py).
+    tap        : optional callable(step, dict) for tests — forces a host sync per step when given.
+    """
+
+    def __init__(self, engines, epsilon, steps, step_size, adaptive=False, coeffs=None, momentum=0.0,
+                 coef_CE=False, chunk=None, reduce_hook=None, tap=None):
+        self.engines = list(engines)
+        self.epsilon = float(epsilon)
+        self.steps = int(steps)
+        self.step_size = float(step_size)
+        self.adaptive = adaptive
+        self.coeffs = coeffs
+        self.momentum = float(momentum)
+        self.coef_CE = bool(coef_CE)
+        self.chunk_request = chunk
+        self.reduce_hook = reduce_hook
+        self.tap = tap
+        self.n_layers = sum(e.num_layers for e in self.engines)
+        if adaptive and (coeffs is None or coeffs.numel() != self.n_layers):
+            raise ValueError("adaptive mode needs a coeffs tensor with one entry per hooked layer (%d)" % self.n_layers)
+        self.step_no = 0
+
+    def setup(self, videos):
+        if videos.dim() != 5 or videos.shape[1] != 3:
+            raise ValueError("videos must be [b,3,f,h,w], got %s" % (tuple(videos.shape),))
+        device = torch.device("cuda", torch.cuda.current_device())
+        capi.device_check(device)
+        b, c, f, h, w = videos.shape
+        self.b, self.f = b, f
+        frames = frames_of(videos.to(device=device, dtype=torch.float32, non_blocking=True))
+        N = self.N = b * f
+        inner = self.inner = h * w
+        chunk = self.chunk = _chunk_frames(self.engines, N, self.chunk_request)
+        self.spans = [(s, min(s + chunk, N)) for s in range(0, N, chunk)]
+        steps = self.steps
+
+        self.x = torch.empty_like(frames)
+        capi.denorm(frames, self.x, inner)                                      # image_attacks.py:308
+        self.mod = torch.empty_like(frames)
+        capi.fill(self.mod, INIT_MODIFIER)                                      # image_attacks.py:304
+        self.m = torch.zeros_like(frames)
+        self.v = torch.zeros_like(frames)
+        self.true_img = torch.empty_like(frames)
+        self.g_total = torch.empty_like(frames)
+
+        # clean features (image_attacks.py:318-323; TPAMI_attack.py:241-253), kept for all N frames
+        self.init_feats = []
+        for e in self.engines:
+            per_layer = None
+            for (s0, s1) in self.spans:
+                fe = e.features(frames[s0:s1], need_grad=False)
+                if per_layer is None:
+                    per_layer = [torch.empty((N,) + tuple(t.shape[1:]), device=device, dtype=torch.float32) for t in fe]
+                for dst, t in zip(per_layer, fe):
+                    dst[s0:s1].copy_(t)
+            self.init_feats.append(per_layer)
+        self.grads = [[torch.empty((chunk,) + tuple(t.shape[1:]), device=device, dtype=torch.float32) for t in fe]
+                      for fe in self.init_feats]
+
+        self.cos = torch.zeros(self.n_layers, N, device=device, dtype=torch.float32)
+        self.step_idx = torch.zeros(1, device=device, dtype=torch.int32)
+        self.cost_log = torch.zeros(max(steps, 1), device=device, dtype=torch.float32)
+        self.table = capi.adam_step_table(steps, self.step_size, BETA1, BETA2).to(device)
+        if self.adaptive:
+            self.prev = torch.ones(self.n_layers, device=device, dtype=torch.float32)   # TPAMI_attack.py:257
+            self.w_out = torch.empty(self.n_layers, device=device, dtype=torch.float32)
+            self.weights_log = torch.zeros(max(steps, 1), self.n_layers, device=device, dtype=torch.float32)
+        else:
+            self.prev = self.w_out = self.weights_log = None
+        capi.compose_norm(self.x, self.mod, self.true_img, self.epsilon, inner)   # image_attacks.py:331-332
+        self.step_no = 0
+        return self
+
+    def step(self):
+        if self.step_no >= self.steps:
+            raise RuntimeError("all %d steps of this run are done" % self.steps)
+        adaptive = self.adaptive
+        if adaptive:
+            capi.layer_reweight(self.coeffs, self.prev, self.momentum, self.w_out, self.weights_log, self.step_idx)
+        for (s0, s1) in self.spans:
+            layer = 0
+            for ei, (e, f0, gr) in enumerate(zip(self.engines, self.init_feats, self.grads)):
+                feats = e.features(self.true_img[s0:s1], need_grad=True)
+                gviews = []
+                for a, a0, ga in zip(feats, f0, gr):
+                    gv = ga[:s1 - s0]
+                    capi.cosine_loss_grad(a, a0[s0:s1], gv, self.cos[layer, s0:s1],
+                                          w_dev=self.w_out[layer:layer + 1] if adaptive else None, w_host=1.0,
+                                          relu_mask=e.relu_masked_grads)
+                    gviews.append(gv)
+                    layer += 1
+                g = e.input_grad(gviews)
+                if ei == 0:
+                    self.g_total[s0:s1].copy_(g)
+                else:
+                    self.g_total[s0:s1].add_(g)
+        if self.reduce_hook is not None:
+            self.reduce_hook.grad(self.g_total)
+            self.reduce_hook.cos_rows(self.cos)
+        capi.layer_sums(self.cos, self.coeffs if adaptive else None, self.prev, self.cost_log, self.step_idx,
+                        mode=1 if adaptive else 0, coef_CE=self.coef_CE)
+        if self.tap is not None:
+            self.tap(self.step_no, dict(g=self.g_total.clone(), cos=self.cos.clone(), mod_before=self.mod.clone(),
+                                        m_before=self.m.clone(), v_before=self.v.clone(),
+                                        true_image=self.true_img.clone()))
+        capi.adam_compose_table(self.g_total, self.m, self.v, self.mod, self.x, self.true_img, self.epsilon, self.inner,
+                                self.table, self.step_idx, BETA1, BETA2, ADAM_EPS)
+        capi.step_advance(self.step_idx)
+        self.step_no += 1
+
+    def finish(self):
+        # `true_img` holds (clamp(x + clamp(mod, ±eps), 0, 1) - mean)/std for the final modifier, which is
+        # exactly image_attacks.py:360-361.
+        adv = clip_of(self.true_img, self.b, self.f)
+        n = self.step_no
+        cost_host = self.cost_log[:n].cpu().numpy() if n > 0 else np.zeros(0, dtype=np.float32)
+        weights_host = self.weights_log[:n].cpu().numpy() if self.adaptive and n > 0 else None
+        return LoopResult(adv, cost_host, weights_host, None)
+
+
+def run_image_guided(engines, videos, epsilon, steps, step_size, adaptive=False, coeffs=None, momentum=0.0,
+                     coef_CE=False, chunk=None, reduce_hook=None, tap=None):
+    run = ImageGuidedRun(engines, epsilon, steps, step_size, adaptive, coeffs, momentum, coef_CE, chunk, reduce_hook, tap)
+    run.setup(videos)
+    for _ in range(run.steps):
+        run.step()
+    return run.finish()
+
+
+def record_loss_info(loss_info, video_names, cost):
+    """image_attacks.py:355-358: the batch-total cost of every step under every video name."""
+    for i, cval in enumerate(cost):
+        text = str(np.float32(cval))
+        for name in video_names:
+            loss_info.setdefault(name, {})[i] = {"cost": text}

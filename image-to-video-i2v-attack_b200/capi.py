@@ -1,0 +1,230 @@
+"""ctypes binding of the C ABI declared in include/i2v_b200.h.
+
+Host code stays Python/PyTorch (as the reference is); torch is used for device memory and streams
+only — every function here hands raw device pointers and the current CUDA stream to
+libi2v_b200.so.  There is no fallback: a missing library or a non-CUDA tensor raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("I2V_B200_LIB", os.path.join(_HERE, "libi2v_b200.so"))
+
+_c_i64 = ctypes.c_int64
+_c_int = ctypes.c_int
+_c_f = ctypes.c_float
+_c_d = ctypes.c_double
+_c_p = ctypes.c_void_p
+
+# name -> argtypes; must list every function include/i2v_b200.h declares (tests/test_capi_symbols.py)
+SIGNATURES = {
+    "i2v_version": ([], _c_int),
+    "i2v_last_error": ([], ctypes.c_char_p),
+    "i2v_device_check": ([_c_int], _c_int),
+    "i2v_denorm_f32": ([_c_p, _c_p, _c_i64, _c_i64, _c_int, _c_p], _c_int),
+    "i2v_normalize_f32": ([_c_p, _c_p, _c_i64, _c_i64, _c_int, _c_p], _c_int),
+    "i2v_compose_norm_f32": ([_c_p, _c_p, _c_p, _c_i64, _c_i64, _c_int, _c_f, _c_p], _c_int),
+    "i2v_fill_f32": ([_c_p, _c_f, _c_i64, _c_p], _c_int),
+    "i2v_adam_compose_f32": ([_c_p] * 6 + [_c_i64, _c_i64, _c_int, _c_f, _c_d, _c_d, _c_d, _c_d, _c_int, _c_p], _c_int),
+    "i2v_adam_step_table": ([_c_p, _c_int, _c_d, _c_d, _c_d], _c_int),
+    "i2v_adam_compose_table_f32": ([_c_p] * 6 + [_c_i64, _c_i64, _c_int, _c_f, _c_f, _c_f, _c_f, _c_f, _c_p, _c_p, _c_p], _c_int),
+    "i2v_step_advance": ([_c_p, _c_p], _c_int),
+    "i2v_sign_step_project_f32": ([_c_p, _c_p, _c_p, _c_i64, _c_i64, _c_int, _c_f, _c_f, _c_int, _c_p], _c_int),
+    "i2v_frame_absmean_f32": ([_c_p, _c_p, _c_int, _c_int, _c_int, _c_i64, _c_int, _c_p], _c_int),
+    "i2v_mi_sign_step_project_f32": ([_c_p] * 5 + [_c_int, _c_int, _c_int, _c_i64, _c_int, _c_f, _c_f, _c_f, _c_p], _c_int),
+    "i2v_cosine_loss_grad_f32": ([_c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_p, _c_f, _c_int, _c_p], _c_int),
+    "i2v_layer_reweight_f32": ([_c_p, _c_p, _c_int, _c_f, _c_p, _c_p, _c_p, _c_p], _c_int),
+    "i2v_layer_sums_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_i64, _c_int, _c_int, _c_p], _c_int),
+}
+
+_lib = None
+
+
+class I2VError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen libi2v_b200.so (no CUDA call is made) and attach the signatures."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise I2VError(
+            "libi2v_b200.so not found at %s — build it with `python -m i2v_b200.build` "
+            "(there is no CPU or PyTorch fallback for these kernels)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (argtypes, restype) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = lib
+    return lib
+
+
+# Launch accounting for bench.py: every successful kernel-launching call bumps LAUNCHES[name]; with
+# PROFILE_EVENTS set to a list, (name, start_event, end_event, bytes) tuples are appended so the
+# benchmark can time each kernel on the launching stream with CUDA events.
+LAUNCHES = {}
+PROFILE_EVENTS = None
+_NO_KERNEL = ("i2v_device_check", "i2v_adam_step_table")
+
+
+class _Timed:
+    __slots__ = ("name", "nbytes", "ev")
+
+    def __init__(self, name, nbytes=0):
+        self.name = name
+        self.nbytes = nbytes
+        self.ev = None
+
+    def __enter__(self):
+        if PROFILE_EVENTS is not None:
+            self.ev = torch.cuda.Event(enable_timing=True)
+            self.ev.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ev is not None and exc[0] is None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            PROFILE_EVENTS.append((self.name, self.ev, end, self.nbytes))
+        return False
+
+
+def _check(rc, what):
+    if rc == 0 and what not in _NO_KERNEL:
+        LAUNCHES[what] = LAUNCHES.get(what, 0) + 1
+    if rc != 0:
+        msg = load().i2v_last_error()
+        raise I2VError("%s failed (%d): %s" % (what, rc, msg.decode(errors="replace") if msg else "?"))
+
+
+def _dev(t, dtype=torch.float32, name="tensor"):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise I2VError("%s must live on a CUDA device (no CPU path exists)" % name)
+    if t.dtype != dtype:
+        raise I2VError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise I2VError("%s must be contiguous" % name)
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+_checked_devices = set()
+
+
+def device_check(device=None):
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    if idx not in _checked_devices:
+        _check(load().i2v_device_check(idx), "i2v_device_check")
+        _checked_devices.add(idx)
+
+
+def version():
+    return load().i2v_version()
+
+
+# ------------------------------------------------------------------------------- K3 family
+def denorm(inp, out, inner, channels=3):
+    _check(load().i2v_denorm_f32(_dev(inp), _dev(out), inp.numel(), inner, channels, _stream()), "i2v_denorm_f32")
+    return out
+
+
+def normalize(x, out, inner, channels=3):
+    _check(load().i2v_normalize_f32(_dev(x), _dev(out), x.numel(), inner, channels, _stream()), "i2v_normalize_f32")
+    return out
+
+
+def compose_norm(x, mod, out, eps, inner, channels=3):
+    _check(load().i2v_compose_norm_f32(_dev(x), _dev(mod), _dev(out), x.numel(), inner, channels, eps, _stream()),
+           "i2v_compose_norm_f32")
+    return out
+
+
+def fill(t, value):
+    _check(load().i2v_fill_f32(_dev(t), value, t.numel(), _stream()), "i2v_fill_f32")
+    return t
+
+
+def adam_compose(g, m, v, mod, x, next_img, eps, inner, step, lr, beta1=0.9, beta2=0.999, adam_eps=1e-8, channels=3):
+    _check(load().i2v_adam_compose_f32(_dev(g), _dev(m), _dev(v), _dev(mod), _dev(x), _dev(next_img), g.numel(), inner,
+                                       channels, eps, lr, beta1, beta2, adam_eps, step, _stream()),
+           "i2v_adam_compose_f32")
+
+
+def adam_step_table(steps, lr, beta1=0.9, beta2=0.999):
+    """Host float32 tensor [steps, 2] of (sqrt(1-beta2^t), -lr/(1-beta1^t)) for t = 1..steps."""
+    table = torch.empty(max(steps, 1), 2, dtype=torch.float32)
+    _check(load().i2v_adam_step_table(table.data_ptr(), steps, lr, beta1, beta2), "i2v_adam_step_table")
+    return table
+
+
+def adam_compose_table(g, m, v, mod, x, next_img, eps, inner, step_table, step_idx, beta1=0.9, beta2=0.999,
+                       adam_eps=1e-8, channels=3):
+    import numpy as np
+    w1 = float(np.float32(1.0 - beta1))
+    b2 = float(np.float32(beta2))
+    a2 = float(np.float32(1.0 - beta2))
+    ae = float(np.float32(adam_eps))
+    with _Timed("i2v_adam_compose_table_f32", 36 * g.numel()):
+        _check(load().i2v_adam_compose_table_f32(_dev(g), _dev(m), _dev(v), _dev(mod), _dev(x), _dev(next_img),
+                                                 g.numel(), inner, channels, eps, w1, b2, a2, ae, _dev(step_table),
+                                                 _dev(step_idx, torch.int32), _stream()),
+               "i2v_adam_compose_table_f32")
+
+
+def step_advance(step_idx):
+    _check(load().i2v_step_advance(_dev(step_idx, torch.int32), _stream()), "i2v_step_advance")
+
+
+def sign_step_project(adv, g, x, step_size, eps, inner, project=True, channels=3):
+    _check(load().i2v_sign_step_project_f32(_dev(adv), _dev(g), _dev(x), adv.numel(), inner, channels, step_size, eps,
+                                            1 if project else 0, _stream()), "i2v_sign_step_project_f32")
+    return adv
+
+
+def frame_absmean(g, norm, clip_level=False):
+    B, C, T, H, W = g.shape
+    _check(load().i2v_frame_absmean_f32(_dev(g), _dev(norm), B, C, T, H * W, int(clip_level), _stream()),
+           "i2v_frame_absmean_f32")
+    return norm
+
+
+def mi_sign_step_project(adv, g, momentum, norm, x, decay, step_size, eps, clip_level=False):
+    B, C, T, H, W = g.shape
+    _check(load().i2v_mi_sign_step_project_f32(_dev(adv), _dev(g), _dev(momentum), _dev(norm), _dev(x), B, C, T, H * W,
+                                               int(clip_level), decay, step_size, eps, _stream()),
+           "i2v_mi_sign_step_project_f32")
+    return adv
+
+
+# ------------------------------------------------------------------------------- K1 / K2
+def cosine_loss_grad(a, b, grad_a, cos_out, w_dev=None, w_host=1.0, relu_mask=False):
+    """a, b: [N, ...] feature maps (flattened per frame); grad_a may be None (loss only)."""
+    N = a.shape[0]
+    D = a.numel() // max(N, 1)
+    if b.numel() != a.numel():
+        raise I2VError("feature maps differ in size")
+    with _Timed("i2v_cosine_loss_grad_f32", (12 if grad_a is not None else 8) * a.numel()):
+        _check(load().i2v_cosine_loss_grad_f32(_dev(a), _dev(b), _dev(grad_a), _dev(cos_out), N, D, _dev(w_dev), w_host,
+                                               int(relu_mask), _stream()), "i2v_cosine_loss_grad_f32")
+
+
+def layer_reweight(coeffs, prev, momentum, w_out=None, weights_log=None, step_idx=None):
+    _check(load().i2v_layer_reweight_f32(_dev(coeffs), _dev(prev), coeffs.numel(), momentum, _dev(w_out),
+                                         _dev(weights_log), _dev(step_idx, torch.int32), _stream()),
+           "i2v_layer_reweight_f32")
+
+
+def layer_sums(cos, coeffs=None, prev=None, cost_log=None, step_idx=None, mode=0, coef_CE=False):
+    L, N = cos.shape
+    _check(load().i2v_layer_sums_f32(_dev(cos), _dev(coeffs), _dev(prev), _dev(cost_log), _dev(step_idx, torch.int32),
+                                     L, N, mode, int(coef_CE), _stream()), "i2v_layer_sums_f32")

@@ -1,0 +1,321 @@
+// K1: per-frame cosine feature loss + analytic gradient; K2: adaptive layer re-weighting.
+//
+// K1 maps one thread-block CLUSTER to one frame (reference image_attacks.py:341-343 computes
+// F.cosine_similarity over the flattened [N, D] feature map, one cosine per frame).  Every CTA of the
+// cluster streams its slice of a and b once from HBM accumulating <a,b>, <a,a>, <b,b> in FP64, the
+// three partials are exchanged through distributed shared memory (no global atomics, fixed order =>
+// bit-reproducible), and the gradient is written in a second pass that never goes back to HBM:
+// while streaming, each CTA stashes as much of its slice as fits in its ~200 KB of shared memory
+// (with a 16-CTA cluster a whole ResNet layer2 frame, 2 x 1.6 MB, lives on-chip); what does not fit
+// is the TAIL of the slice, which is walked backwards so the most recently read lines are still in
+// the 126 MB L2 (one CTA per SM => at most 148/CLUSTER frames in flight).
+// Algorithmic HBM bytes: 12*D per frame (read a, read b, write grad).
+//
+// Numerics (SURVEY.md 7.3 "step-1 numerics"): at step 1 cos ~ 1 and the gradient
+//     g = b/(|a||b|) - cos * a/|a|^2
+// is a catastrophic cancellation (|g| ~ 1e-8 of its terms).  Sums are FP64, the two scalars stay in
+// FP64 and each gradient element is formed in FP64 and rounded once, so the result is the correctly
+// rounded analytic gradient, i.e. at least as close to the float64 reference as torch-f32 autograd is.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace i2v {
+
+constexpr int kCosThreads = 512;
+constexpr int kUnroll = 4;
+constexpr double kCosEps = 1e-8;   // F.cosine_similarity default eps (image_attacks.py:343)
+
+struct CosPartial { double dot, aa, bb; };
+
+template <bool VEC>
+__global__ void __launch_bounds__(kCosThreads, 1)
+cosine_loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ grad,
+                        float* __restrict__ cos_out, int64_t D, const float* __restrict__ w_dev, float w_host,
+                        int relu_mask, int64_t cap) {
+    extern __shared__ float4 stash[];   // [2][cap]: this CTA's slice of a and of b (as much as fits)
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned S = cluster.num_blocks();
+    const unsigned rank = cluster.block_rank();
+    const int64_t frame = blockIdx.x / S;
+    const float* af = a + frame * D;
+    const float* bf = b + frame * D;
+
+    // slice of this CTA, in units of float4 (VEC) or float
+    const int64_t units = VEC ? D / 4 : D;
+    const int64_t lo = units * rank / S;
+    const int64_t hi = units * (rank + 1) / S;
+
+    double dot = 0.0, aa = 0.0, bb = 0.0;
+    if (VEC) {
+        const float4* a4 = reinterpret_cast<const float4*>(af);
+        const float4* b4 = reinterpret_cast<const float4*>(bf);
+        float4* sa = stash;
+        float4* sb = stash + cap;
+        int64_t i = lo + threadIdx.x;
+        // kUnroll independent 16-byte loads per tensor in flight per thread
+        for (; i + (int64_t)(kUnroll - 1) * kCosThreads < hi; i += (int64_t)kUnroll * kCosThreads) {
+            float4 av[kUnroll], bv[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) { av[u] = ld_stream(a4 + i + u * kCosThreads); bv[u] = ld_stream(b4 + i + u * kCosThreads); }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int64_t k = i + u * kCosThreads - lo;
+                if (grad != nullptr && k < cap) { sa[k] = av[u]; sb[k] = bv[u]; }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    double x = (double)(&av[u].x)[j], y = (double)(&bv[u].x)[j];
+                    dot = fma(x, y, dot); aa = fma(x, x, aa); bb = fma(y, y, bb);
+                }
+            }
+        }
+        for (; i < hi; i += kCosThreads) {
+            float4 av = ld_stream(a4 + i), bv = ld_stream(b4 + i);
+            const int64_t k = i - lo;
+            if (grad != nullptr && k < cap) { sa[k] = av; sb[k] = bv; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double x = (double)(&av.x)[j], y = (double)(&bv.x)[j];
+                dot = fma(x, y, dot); aa = fma(x, x, aa); bb = fma(y, y, bb);
+            }
+        }
+    } else {
+        for (int64_t i = lo + threadIdx.x; i < hi; i += kCosThreads) {
+            double x = (double)af[i], y = (double)bf[i];
+            dot = fma(x, y, dot); aa = fma(x, x, aa); bb = fma(y, y, bb);
+        }
+    }
+
+    // CTA reduction: warp shuffles, then 16 warps through shared memory in fixed order
+    __shared__ CosPartial warp_part[kCosThreads / 32];
+    __shared__ CosPartial cta_part;
+    __shared__ double coef[2];
+    dot = warp_sum(dot); aa = warp_sum(aa); bb = warp_sum(bb);
+    if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = CosPartial{dot, aa, bb};
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        CosPartial s{0.0, 0.0, 0.0};
+        for (int w = 0; w < kCosThreads / 32; ++w) { s.dot += warp_part[w].dot; s.aa += warp_part[w].aa; s.bb += warp_part[w].bb; }
+        cta_part = s;
+    }
+    cluster.sync();   // every CTA's partial is visible cluster-wide
+
+    if (threadIdx.x == 0) {
+        CosPartial t{0.0, 0.0, 0.0};
+        for (unsigned r = 0; r < S; ++r) {   // rank order: identical result in every CTA
+            const CosPartial* p = cluster.map_shared_rank(&cta_part, r);
+            t.dot += p->dot; t.aa += p->aa; t.bb += p->bb;
+        }
+        const double na_raw = sqrt(t.aa), nb_raw = sqrt(t.bb);
+        const double na = fmax(na_raw, kCosEps), nb = fmax(nb_raw, kCosEps);
+        const double inv = 1.0 / (na * nb);
+        const double cosv = t.dot * inv;
+        const double w = (double)(w_dev ? *w_dev : w_host);
+        coef[0] = w * inv;                                        // alpha: multiplies b
+        coef[1] = (na_raw > kCosEps) ? w * cosv / (na * na) : 0.0; // beta:  multiplies a (0 when |a| is clamped)
+        if (rank == 0 && cos_out) cos_out[frame] = (float)cosv;
+    }
+    cluster.sync();   // remote reads done before any CTA may exit; also publishes coef[] to the CTA
+    if (grad == nullptr) return;
+
+    const double alpha = coef[0], beta = coef[1];
+    float* gf = grad + frame * D;
+    if (VEC) {
+        const float4* a4 = reinterpret_cast<const float4*>(af);
+        const float4* b4 = reinterpret_cast<const float4*>(bf);
+        float4* g4 = reinterpret_cast<float4*>(gf);
+        const float4* sa = stash;
+        const float4* sb = stash + cap;
+        // backwards: the un-stashed tail of the slice was read last in pass 1 and is the hottest in L2;
+        // each thread revisits exactly the vectors it stashed itself (same i mod 512), so the stash
+        // needs no barrier of its own.
+        const int64_t last = lo + ((hi - 1 - lo - threadIdx.x) / kCosThreads) * kCosThreads + threadIdx.x;
+#pragma unroll 4
+        for (int64_t i = (hi - lo > (int64_t)threadIdx.x) ? last : lo - 1; i >= lo; i -= kCosThreads) {
+            const int64_t k = i - lo;
+            float4 av, bv, r;
+            if (k < cap) { av = sa[k]; bv = sb[k]; } else { av = ld_plain(a4 + i); bv = ld_plain(b4 + i); }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float x = (&av.x)[j];
+                float gval = (float)fma(alpha, (double)(&bv.x)[j], -(beta * (double)x));
+                (&r.x)[j] = (relu_mask && !(x > 0.0f)) ? 0.0f : gval;
+            }
+            st_stream(g4 + i, r);
+        }
+    } else {
+        for (int64_t i = hi - 1 - threadIdx.x; i >= lo; i -= kCosThreads) {
+            float x = af[i];
+            float gval = (float)fma(alpha, (double)bf[i], -(beta * (double)x));
+            gf[i] = (relu_mask && !(x > 0.0f)) ? 0.0f : gval;
+        }
+    }
+}
+
+// K2: one warp.  coeffs <- softmax(softmax(prev) + momentum*coeffs)   (TPAMI_attack.py:265)
+__global__ void layer_reweight_kernel(float* __restrict__ coeffs, const float* __restrict__ prev, int L,
+                                      float momentum, float* __restrict__ w_out, float* __restrict__ weights_log,
+                                      const int* __restrict__ step_idx) {
+    const int l = threadIdx.x;
+    const bool on = l < L;
+    // inner softmax over prev
+    double p = on ? (double)prev[l] : -INFINITY;
+    double mx = p;
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    double e = on ? exp(p - mx) : 0.0;
+    double s1 = (float)(e / warp_sum(e));          // torch materialises the inner softmax as f32
+    // outer softmax over s1 + momentum*coeffs  (momentum*coeffs and the add are f32 ops in torch)
+    float mc = on ? __fmul_rn(momentum, coeffs[l]) : 0.0f;
+    double q = on ? (double)__fadd_rn((float)s1, mc) : -INFINITY;
+    double mx2 = q;
+    for (int o = 16; o > 0; o >>= 1) mx2 = fmax(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
+    double e2 = on ? exp(q - mx2) : 0.0;
+    float c = (float)(e2 / warp_sum(e2));
+    if (on) {
+        coeffs[l] = c;
+        if (w_out) w_out[l] = __fmul_rn(__fdiv_rn(1.0f, (float)L), c);   // d mean_l / d each_l = 1/L, times coeffs[l]
+        if (weights_log) weights_log[(int64_t)(step_idx ? *step_idx : 0) * L + l] = c;
+    }
+}
+
+// Layer sums / cost / prev update.  One CTA; row sums in FP64 in a fixed order.
+__global__ void __launch_bounds__(256)
+layer_sums_kernel(const float* __restrict__ cosv, const float* __restrict__ coeffs, float* __restrict__ prev,
+                  float* __restrict__ cost_log, const int* __restrict__ step_idx, int L, int64_t N, int mode, int coef_CE) {
+    __shared__ double part[8];
+    __shared__ double rows[32];
+    for (int l = 0; l < L; ++l) {
+        double acc = 0.0;
+        for (int64_t n = threadIdx.x; n < N; n += blockDim.x) acc += (double)cosv[(int64_t)l * N + n];
+        acc = warp_sum(acc);
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int w = 0; w < 8; ++w) s += part[w];
+            rows[l] = s;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double cost = 0.0;
+        for (int l = 0; l < L; ++l) {
+            float s = (float)rows[l];
+            if (mode == 0) {
+                cost += (double)s;
+            } else {
+                float weighted = __fmul_rn(coeffs[l], s);   // each_features_loss[l] (TPAMI_attack.py:290)
+                cost += (double)weighted;
+                if (prev) prev[l] = coef_CE ? weighted : s;  // TPAMI_attack.py:293-297
+            }
+        }
+        if (mode == 1) cost /= (double)L;
+        if (cost_log) cost_log[step_idx ? *step_idx : 0] = (float)cost;
+    }
+}
+
+}  // namespace i2v
+
+using namespace i2v;
+
+// Cluster size / stash policy (host).  I2V_COS_CLUSTER=<1|2|4|8|16> overrides for experiments.
+static int pick_cluster(int64_t N, int64_t units, int64_t cap_max) {
+    if (const char* e = getenv("I2V_COS_CLUSTER")) {
+        int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) return v;
+    }
+    int s_fit = 1;
+    while (s_fit < 16 && (units + s_fit - 1) / s_fit > cap_max) s_fit <<= 1;   // whole slice on-chip if possible
+    int s_fill = 1;
+    while (s_fill < 16 && N * s_fill < (int64_t)sm_count()) s_fill <<= 1;       // at least one CTA per SM
+    int S = s_fit > s_fill ? s_fit : s_fill;
+    while (S > 1 && units / S < 1024) S >>= 1;                                  // keep >= 4K elements per CTA
+    return S;
+}
+
+template <bool VEC>
+static int cosine_launch(const float* a, const float* b, float* grad_a, float* cos_out, int64_t N, int64_t D,
+                         const float* w_dev, float w_host, int relu_mask, cudaStream_t st) {
+    static int smem_optin = -1;
+    static bool attr_done = false;
+    auto kern = cosine_loss_grad_kernel<VEC>;
+    if (smem_optin < 0) {
+        int dev = 0, v = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || v <= 0) v = 48 * 1024;
+        smem_optin = v;
+    }
+    const int64_t units = VEC ? D / 4 : D;
+    const int64_t cap_max = VEC ? (smem_optin - 2048) / 32 : 0;   // float4 pairs that fit beside the static smem
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 2048);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return cuda_fail(e, "i2v_cosine_loss_grad_f32 (attributes)");
+        attr_done = true;
+    }
+    int S = pick_cluster(N, units, cap_max > 0 ? cap_max : 1);
+
+    for (;;) {
+        const int64_t slice = (units + S - 1) / S;
+        // Fully stashed slices may share an SM; partially stashed ones take the whole SM so that at most
+        // 148/S frames are in flight and the un-stashed tails stay L2-resident.
+        const int64_t cap = !VEC || grad_a == nullptr ? 0 : (slice <= cap_max ? slice : cap_max);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(N * S));
+        cfg.blockDim = dim3(kCosThreads);
+        cfg.dynamicSmemBytes = (size_t)cap * 32;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)S;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (S > 8) {   // non-portable size: make sure this device can co-schedule such a cluster
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess || nclusters < 1) {
+                cudaGetLastError();
+                S = 8;
+                continue;
+            }
+        }
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, b, grad_a, cos_out, D, w_dev, w_host, relu_mask, cap);
+        if (e != cudaSuccess) return cuda_fail(e, "i2v_cosine_loss_grad_f32");
+        return I2V_OK;
+    }
+}
+
+extern "C" int i2v_cosine_loss_grad_f32(const float* a, const float* b, float* grad_a, float* cos_out, int64_t N,
+                                        int64_t D, const float* w_dev, float w_host, int relu_mask,
+                                        i2v_stream_t stream) {
+    I2V_REQUIRE(a && b, "null feature pointer");
+    I2V_REQUIRE(N >= 0 && D >= 1, "bad sizes N=%lld D=%lld", (long long)N, (long long)D);
+    I2V_REQUIRE(N <= 0x7fffffff / 16, "too many frames in one call");
+    if (N == 0) return I2V_OK;
+    const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
+                                       reinterpret_cast<uintptr_t>(grad_a)) & 15) == 0;
+    if (vec) return cosine_launch<true>(a, b, grad_a, cos_out, N, D, w_dev, w_host, relu_mask, as_stream(stream));
+    return cosine_launch<false>(a, b, grad_a, cos_out, N, D, w_dev, w_host, relu_mask, as_stream(stream));
+}
+
+extern "C" int i2v_layer_reweight_f32(float* coeffs, const float* prev, int L, float momentum, float* w_out,
+                                      float* weights_log, const int* step_idx, i2v_stream_t stream) {
+    I2V_REQUIRE(coeffs && prev, "null pointer");
+    I2V_REQUIRE(L >= 1 && L <= 32, "L must be in [1,32] (got %d)", L);
+    layer_reweight_kernel<<<1, 32, 0, as_stream(stream)>>>(coeffs, prev, L, momentum, w_out, weights_log, step_idx);
+    I2V_LAUNCH_CHECK("i2v_layer_reweight_f32");
+    return I2V_OK;
+}
+
+extern "C" int i2v_layer_sums_f32(const float* cosv, const float* coeffs, float* prev, float* cost_log,
+                                  const int* step_idx, int L, int64_t N, int mode, int coef_CE, i2v_stream_t stream) {
+    I2V_REQUIRE(cosv, "null pointer");
+    I2V_REQUIRE(L >= 1 && L <= 32 && N >= 0, "bad sizes L=%d N=%lld", L, (long long)N);
+    I2V_REQUIRE(mode == 0 || (mode == 1 && coeffs), "mode 1 needs coeffs");
+    layer_sums_kernel<<<1, 256, 0, as_stream(stream)>>>(cosv, coeffs, prev, cost_log, step_idx, L, N, mode, coef_CE);
+    I2V_LAUNCH_CHECK("i2v_layer_sums_f32");
+    return I2V_OK;
+}

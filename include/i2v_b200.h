@@ -1,0 +1,153 @@
+/* i2v_b200 — C ABI of the B200-native I2V / ENS-I2V / AENS-I2V per-step attack loop.
+ *
+ * The reference (zhipeng-wei/Image-to-Video-I2V-attack) is pure Python over PyTorch; it has no FFI of
+ * its own.  Each entry point below therefore cites the reference *Python* lines whose arithmetic it
+ * replaces (paths relative to the reference root).  The host side (Python, `i2v_b200/capi.py`) binds
+ * these through ctypes, passing `tensor.data_ptr()` and `torch.cuda.current_stream().cuda_stream`.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers owned by the caller (torch allocations) unless stated otherwise.
+ *  - Kernels are asynchronous on `stream` (a cudaStream_t passed as void*). No hidden allocation.
+ *  - Return value: 0 on success, negative I2V_E* code on failure; i2v_last_error() gives the text.
+ *  - sm_100a only.  There is no CPU fallback and no other-arch fallback: on a different device the
+ *    launch fails and the error is reported.
+ *  - "channel layout": element i of a tensor belongs to channel ((i / inner) % channels).
+ *        [N,3,H,W] planar  -> inner = H*W,   channels = 3   (image_attacks.py:59  [3,1,1] broadcast)
+ *        [B,3,T,H,W]       -> inner = T*H*W, channels = 3   (base_attacks.py:154 [3,1,1,1] broadcast)
+ *        [N,H,W,4] NHWC4   -> inner = 1,     channels = 4   (native engine; channel 3 is padding and is
+ *                                                            kept at exactly 0 by every kernel)
+ *    mean = {0.485,0.456,0.406}, std = {0.229,0.224,0.225} rounded to f32 (image_attacks.py:33-34).
+ */
+#ifndef I2V_B200_H_
+#define I2V_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define I2V_VERSION 100
+
+#define I2V_OK            0
+#define I2V_EINVAL       -1   /* bad argument (null pointer, bad layout, unsupported size)          */
+#define I2V_ECUDA        -2   /* CUDA runtime error (launch failure, wrong architecture, ...)      */
+#define I2V_EUNSUPPORTED -3   /* shape not supported by the tensor-core path (caller must not hide) */
+
+typedef void* i2v_stream_t;
+
+int         i2v_version(void);
+const char* i2v_last_error(void);
+/* Verifies that `device` is compute capability 10.x and makes it current. */
+int         i2v_device_check(int device);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3 family — fused per-pixel update kernels (HBM-bound, float4 streaming)
+ * ------------------------------------------------------------------------------------------- */
+
+/* x = inp * std_c + mean_c          (mul then add, two roundings, no FMA)
+ * replaces `_transform_video(video, 'back')`: image_attacks.py:60-62, base_attacks.py:155-157.   */
+int i2v_denorm_f32(const float* inp, float* x, int64_t n, int64_t inner, int channels, i2v_stream_t stream);
+
+/* out = (x - mean_c) / std_c          (sub then true division, two roundings)
+ * replaces `_transform_video(video, 'forward')`: image_attacks.py:57-59, base_attacks.py:152-154. */
+int i2v_normalize_f32(const float* x, float* out, int64_t n, int64_t inner, int channels, i2v_stream_t stream);
+
+/* out = (clamp(x + clamp(mod,-eps,eps), 0, 1) - mean_c) / std_c
+ * replaces image_attacks.py:331-332 / 360-361 (also 465-466, TPAMI_attack.py:268-269, 316-317).  */
+int i2v_compose_norm_f32(const float* x, const float* mod, float* out, int64_t n, int64_t inner,
+                         int channels, float eps, i2v_stream_t stream);
+
+int i2v_fill_f32(float* p, float value, int64_t n, i2v_stream_t stream);
+
+/* K3a: one Adam step on the unconstrained modifier, fused with the backward of the compose/normalise
+ * block in front of it and with the compose/normalise of the NEXT step behind it.
+ *   g        : dcost/d(true_image), normalised space                     (read)
+ *   m, v     : Adam exp_avg / exp_avg_sq                                  (read+write)
+ *   mod      : modifier                                                   (read+write)
+ *   x        : clean frames in [0,1]                                      (read)
+ *   next_img : (clamp(x + clamp(mod',±eps),0,1) - mean_c)/std_c           (write)
+ * Arithmetic (every op one f32 rounding; `fma` = fused):
+ *   gm   = (g / std_c) * 1[0 <= x+clamp(mod) <= 1] * 1[-eps <= mod <= eps]   autograd of 331-332
+ *   m    = fma(f32(1-beta1), gm - m, m)                                      torch.optim.Adam lerp_
+ *   v    = fma(f32(1-beta2)*gm, gm, v*f32(beta2))                            mul_ + addcmul_
+ *   den  = sqrt(v) / f32(sqrt(1-beta2^step)) + f32(adam_eps)
+ *   mod  = mod + (f32(-lr/(1-beta1^step)) * m) / den                         addcdiv_
+ * replaces image_attacks.py:351-353 (+331-332 of the next iteration); `step` is 1-based.          */
+int i2v_adam_compose_f32(const float* g, float* m, float* v, float* mod, const float* x,
+                         float* next_img, int64_t n, int64_t inner, int channels, float eps,
+                         double lr, double beta1, double beta2, double adam_eps, int step,
+                         i2v_stream_t stream);
+
+/* CUDA-graph friendly form of K3a: the two step-dependent scalars come from a device table
+ * step_table[2*k+0] = f32(sqrt(1-beta2^(k+1))), step_table[2*k+1] = f32(-lr/(1-beta1^(k+1)))
+ * indexed by the device counter *step_idx (0-based; advanced by i2v_step_advance).
+ * i2v_adam_step_table fills a HOST table with exactly the scalars i2v_adam_compose_f32 would use. */
+int i2v_adam_step_table(float* host_table, int steps, double lr, double beta1, double beta2);
+int i2v_adam_compose_table_f32(const float* g, float* m, float* v, float* mod, const float* x,
+                               float* next_img, int64_t n, int64_t inner, int channels, float eps,
+                               float w1, float beta2, float a2, float adam_eps,
+                               const float* step_table, const int* step_idx, i2v_stream_t stream);
+int i2v_step_advance(int* step_idx, i2v_stream_t stream);
+
+/* K3b: BIM update block.  adv is normalised on entry and exit.
+ *   a = adv*std_c; a = a + mean_c; a = a + step_size*sign(g); d = clamp(a - x, ±eps);
+ *   a = clamp(x + d, 0, 1); adv = (a - mean_c)/std_c        — every op one f32 rounding, sign(0)=0.
+ * replaces base_attacks.py:289-293 (same block at 334-338, 405-409, 473-477, 546-550, 605-609,
+ * 677-681, 806-810, video_attacks.py:224-228).  `project`=0 gives FGSM's block (254-257: no
+ * eps-projection, x unused and may be NULL).                                                       */
+int i2v_sign_step_project_f32(float* adv, const float* g, const float* x, int64_t n, int64_t inner,
+                              int channels, float step_size, float eps, int project,
+                              i2v_stream_t stream);
+
+/* K3c: MI-FGSM.  g is [B,C,T,HW] (C = 3).
+ *   i2v_frame_absmean_f32: norm[b,t] = mean_{c,h,w} |g|            utils.py:63 (frame_level=True)
+ *                          or, clip_level!=0, norm[b] = mean_{c,t,h,w}|g|   utils.py:65
+ *   i2v_mi_sign_step_project_f32: gn = g / norm; gn = gn + momentum*decay; momentum = gn;
+ *                          then the K3b block with sign(gn)          base_attacks.py:328-338       */
+int i2v_frame_absmean_f32(const float* g, float* norm, int B, int C, int T, int64_t HW,
+                          int clip_level, i2v_stream_t stream);
+int i2v_mi_sign_step_project_f32(float* adv, const float* g, float* momentum, const float* norm,
+                                 const float* x, int B, int C, int T, int64_t HW, int clip_level,
+                                 float decay, float step_size, float eps, i2v_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1 — per-frame cosine feature loss and its analytic gradient (HBM-bound, two passes, the second
+ *      served from L2; one 8-CTA cluster per frame with a DSMEM reduction)
+ * ------------------------------------------------------------------------------------------- */
+
+/*   cos[n]    = sum_i (a/max(|a|,1e-8))*(b/max(|b|,1e-8))             F.cosine_similarity, dim=1
+ *   grad_a[n] = w * ( b/(|a||b|) - cos*a/|a|^2 )  [* 1[a>0] if relu_mask]   autograd of the above
+ * a, b, grad_a: [N, D] contiguous (any permutation of the D axis gives the same cos — the reduction
+ * is over the whole frame — so NCHW and NHWC feature maps are both accepted).
+ * w = *w_dev if w_dev != NULL else w_host (ENS-I2V: 1; AENS: coeffs[l]/L, TPAMI_attack.py:289-291).
+ * Sums are accumulated in FP64; the gradient is formed in FP64 and rounded once.
+ * grad_a may be NULL (loss only: the init-feature pass never needs it).
+ * replaces image_attacks.py:341-347 + autograd (also 475-480; TPAMI_attack.py:282-286).           */
+int i2v_cosine_loss_grad_f32(const float* a, const float* b, float* grad_a, float* cos_out,
+                             int64_t N, int64_t D, const float* w_dev, float w_host, int relu_mask,
+                             i2v_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2 — adaptive layer re-weighting (latency-bound, one warp)
+ * ------------------------------------------------------------------------------------------- */
+
+/* coeffs <- softmax(softmax(prev) + momentum*coeffs)      TPAMI_attack.py:265      (L <= 32)
+ * w_out[l] = coeffs[l] / L  (the upstream dcost/dcos of `mean_l(coeffs[l]*sum_n cos[l,n])`, 289-291)
+ * weights_log (nullable): row *step_idx of a [steps, L] device log — `self.weights`, 266.         */
+int i2v_layer_reweight_f32(float* coeffs, const float* prev, int L, float momentum, float* w_out,
+                           float* weights_log, const int* step_idx, i2v_stream_t stream);
+
+/* From cos[L,N]:  s[l] = sum_n cos[l,n] (fixed order);
+ *   mode 0 (I2V / ENS-I2V): cost = sum_l s[l]                         image_attacks.py:347, 480
+ *   mode 1 (AENS):          cost = mean_l(coeffs[l]*s[l]);            TPAMI_attack.py:290-291
+ *                           prev[l] = coef_CE ? coeffs[l]*s[l] : s[l] TPAMI_attack.py:293-297
+ * cost_log[*step_idx] = cost (device log; `loss_info` / `cost_saved`, one D2H after the loop).     */
+int i2v_layer_sums_f32(const float* cos, const float* coeffs, float* prev, float* cost_log,
+                       const int* step_idx, int L, int64_t N, int mode, int coef_CE,
+                       i2v_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* I2V_B200_H_ */

@@ -1,0 +1,197 @@
+"""TEST INFRASTRUCTURE ONLY — full-loop CPU restatements of the reference attack classes.
+
+Every function follows the cited reference lines statement by statement; the per-pixel arithmetic goes
+through the C oracle (oracle/i2v_oracle.c via oracle/oracle.py), the image / video model runs on the
+CPU under torch autograd exactly as the reference runs it (full forward, hooks on the target layers).
+Pinned against the unmodified reference classes by tests/test_oracle_golden.py.
+
+Nothing here imports the product package.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import oracle as O
+
+INIT_MODIFIER = 0.01 / 255   # image_attacks.py:304
+
+
+# --------------------------------------------------------------------------------------------------
+# reference `_find_target_layer` restated (image_attacks.py:260-271; TPAMI_attack.py:176-200)
+# --------------------------------------------------------------------------------------------------
+def target_layers(model, family, depth):
+    is_list = isinstance(depth, (list, tuple))
+    ds = list(depth) if is_list else [depth]
+    if family == "resnet":
+        return [getattr(model, "layer{}".format(d))[-1] for d in ds]
+    if family == "alexnet":
+        table = {1: 1, 2: 4, 3: 7, 4: 11}
+        return [model.features[table[d]] for d in ds]
+    if family == "vgg":
+        table = {1: 1, 2: 11, 3: 20, 4: 29}
+        return [model.features[table[d]] for d in ds]
+    if family == "squeezenet":
+        table = {1: 3, 2: 6, 3: 9, 4: 12}
+        if is_list:
+            return [model.features[table[d]] for d in ds]
+        return [model.features[table[ds[0]]].expand3x3_activation]
+    raise ValueError(family)
+
+
+class HookedModel:
+    """model.train() + BN eval (image_attacks.py:253-256) and forward hooks that append the target
+    layers' outputs in execution order (273-292)."""
+
+    def __init__(self, model, family, depth):
+        self.model = model
+        model.train()
+        for m in model.modules():
+            if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.BatchNorm1d)):
+                m.eval()
+        self.acts = []
+        self.handles = [t.register_forward_hook(lambda mod, inp, out: self.acts.append(out))
+                        for t in target_layers(model, family, depth)]
+
+    def run(self, img):
+        self.acts = []
+        self.model(img)
+        acts, self.acts = self.acts, []
+        return acts
+
+    def close(self):
+        for h in self.handles:
+            h.remove()
+
+
+def _frames(videos):
+    b, c, f, h, w = videos.shape
+    return videos.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w).contiguous()
+
+
+def image_guided_loop(hooked, videos, epsilon, steps, step_size, adaptive=False, coeffs=None, momentum=0.0,
+                      coef_CE=False, cos_mode="torch", tap=None):
+    """image_attacks.py:294-364 / 426-496 (adaptive=False) and TPAMI_attack.py:223-320 (adaptive=True).
+
+    hooked  : list of HookedModel (one per image model, reference order)
+    cos_mode: 'torch' — F.cosine_similarity + autograd in f32, the reference's own arithmetic
+              'f64'   — the float64 analytic cosine gradient of the C oracle (the accuracy arbiter)
+    tap     : optional callable(step, dict) receiving per-step state (g, m, v, mod, true_image, cos)
+    Returns (adv [b,3,f,h,w] float32 ndarray, cost [steps] float32, weights [steps, L] or None, coeffs)
+    """
+    videos = torch.as_tensor(videos, dtype=torch.float32)
+    b, c, f, h, w = videos.shape
+    N, inner = b * f, h * w
+    frames = _frames(videos)                                                   # 300-301
+    x = O.denorm(frames.numpy(), inner)                                        # 308
+    mod = np.full_like(x, np.float32(INIT_MODIFIER))                           # 304
+    m = np.zeros_like(x)                                                       # Adam state (306)
+    v = np.zeros_like(x)
+
+    with torch.no_grad():
+        init = [[a.detach().clone() for a in hm.run(frames)] for hm in hooked]  # 318-323
+    L = sum(len(i) for i in init)
+
+    cost_log = np.zeros(steps, dtype=np.float32)
+    weights = [] if adaptive else None
+    if adaptive:
+        coeffs = np.asarray(coeffs, dtype=np.float32).copy()
+        prev = np.ones(L, dtype=np.float32)                                    # TPAMI_attack.py:257
+    true_np = O.compose_norm(x, mod, epsilon, inner)                           # 331-332
+
+    for i in range(steps):
+        if adaptive:
+            coeffs, w_up = O.layer_reweight(coeffs, prev, momentum)            # TPAMI_attack.py:265
+            weights.append(coeffs.copy())                                      # 266
+        true_image = torch.from_numpy(true_np.copy()).requires_grad_(True)
+        cos_rows, feats, ups = [], [], []
+        layer = 0
+        for hm, init_feats in zip(hooked, init):                               # 334 / 469-470
+            acts = hm.run(true_image)
+            for a, a0 in zip(acts, init_feats):
+                if cos_mode == "torch":
+                    cs = F.cosine_similarity(a.view(N, -1), a0.view(N, -1))    # 341-343
+                    cos_rows.append(cs)
+                else:
+                    cs, gr = O.cosine_loss_grad_f64(a.detach().numpy().reshape(N, -1), a0.numpy().reshape(N, -1),
+                                                    w=float(w_up[layer]) if adaptive else 1.0)
+                    cos_rows.append(torch.from_numpy(cs.astype(np.float32)))
+                    feats.append(a)
+                    ups.append(torch.from_numpy(gr.astype(np.float32)).view_as(a))
+                layer += 1
+        if cos_mode == "torch":
+            stacked = torch.stack(cos_rows)                                    # [L, N]
+            if adaptive:
+                used = torch.from_numpy(coeffs).unsqueeze(1)                   # 289
+                each = torch.sum(used * stacked, dim=1)                        # 290
+                cost = torch.mean(each)                                        # 291
+                prev = (each if coef_CE else torch.sum(stacked.detach(), dim=1)).detach().numpy().copy()  # 293-297
+            else:
+                cost = torch.sum(stacked)                                      # 347
+            (g,) = torch.autograd.grad(cost, true_image)                       # 352
+            cost_val = np.float32(cost.detach().numpy())
+            cos_np = stacked.detach().numpy()
+        else:
+            (g,) = torch.autograd.grad(feats, true_image, ups)
+            cos_np = torch.stack(cos_rows).numpy()
+            cost_val, prev_new = O.layer_sums(cos_np, coeffs if adaptive else None, mode=1 if adaptive else 0,
+                                              coef_CE=coef_CE)
+            if adaptive:
+                prev = prev_new
+        cost_log[i] = cost_val
+        g_np = g.numpy()
+        m, v, mod, true_np = O.adam_compose(g_np, m, v, mod, x, epsilon, inner, i + 1, step_size)   # 351-353, 331-332
+        if tap is not None:
+            tap(i, dict(g=g_np, m=m, v=v, mod=mod, true_image=true_np, cos=cos_np))
+
+    adv = true_np.reshape(b, f, c, h, w).transpose(0, 2, 1, 3, 4)              # 360-363
+    return adv, cost_log, (np.stack(weights) if adaptive and steps else None), coeffs
+
+
+# --------------------------------------------------------------------------------------------------
+# base_attacks.py:242-340
+# --------------------------------------------------------------------------------------------------
+def _ce_grad(model, adv, labels, targeted):
+    adv_t = torch.from_numpy(adv.copy()).requires_grad_(True)
+    out = model(adv_t)
+    cost = targeted * torch.nn.CrossEntropyLoss()(out, labels)                 # 285
+    (g,) = torch.autograd.grad(cost, adv_t)                                    # 286-287
+    return g.numpy()
+
+
+def fgsm(model, videos, labels, epsilon=16 / 255, targeted=1):
+    """base_attacks.py:242-259"""
+    model.eval()
+    videos = np.ascontiguousarray(videos, dtype=np.float32)
+    inner = videos.shape[2] * videos.shape[3] * videos.shape[4]
+    g = _ce_grad(model, videos, labels, targeted)
+    return O.sign_step_project(videos, g, None, epsilon, epsilon, inner, project=False)
+
+
+def bim(model, videos, labels, epsilon=16 / 255, steps=10, targeted=1):
+    """base_attacks.py:272-295"""
+    model.eval()
+    videos = np.ascontiguousarray(videos, dtype=np.float32)
+    inner = videos.shape[2] * videos.shape[3] * videos.shape[4]
+    step_size = epsilon / steps                                                # 270
+    x = O.denorm(videos, inner)                                                # 279
+    adv = videos.copy()                                                        # 280
+    for _ in range(steps):
+        g = _ce_grad(model, adv, labels, targeted)                             # 283-287
+        adv = O.sign_step_project(adv, g, x, step_size, epsilon, inner)        # 289-293
+    return adv
+
+
+def mifgsm(model, videos, labels, epsilon=16 / 255, steps=10, decay=1.0, targeted=1):
+    """base_attacks.py:309-340 with utils.py:58-67 (frame-level norm)"""
+    model.eval()
+    videos = np.ascontiguousarray(videos, dtype=np.float32)
+    inner = videos.shape[2] * videos.shape[3] * videos.shape[4]
+    step_size = epsilon / steps                                                # 306
+    momentum = np.zeros_like(videos)                                           # 316
+    x = O.denorm(videos, inner)                                                # 317
+    adv = videos.copy()                                                        # 318
+    for _ in range(steps):
+        g = _ce_grad(model, adv, labels, targeted)                             # 321-326
+        norm = O.frame_absmean(g)                                              # 328 -> utils.py:63
+        adv, momentum = O.mi_sign_step_project(adv, g, momentum, norm, x, decay, step_size, epsilon)   # 328-338
+    return adv

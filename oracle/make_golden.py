@@ -1,0 +1,121 @@
+"""TEST INFRASTRUCTURE ONLY — generate tests/golden/*.npz by running the UNMODIFIED reference classes
+(/root/reference, loaded through oracle/load_reference.py) on seeded synthetic inputs, CPU, float32.
+
+Run in the build container (the reference is not present on the GPU box):
+    python -m oracle.make_golden
+The fixtures pin the oracle (tests/test_oracle_golden.py) and, on the GPU box, the CUDA path
+(tests/test_gpu_attacks.py).  Weights are torchvision random init under torch.manual_seed(0); a
+checksum of the first conv weight is stored so a torch version that initialises differently is detected.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import load_reference as LR   # noqa: E402
+import i2v_b200.synth as synth            # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+THREADS = 4
+
+
+def weight_checksum(model):
+    p = next(model.parameters()).detach().double()
+    return np.array([p.sum().item(), p.abs().sum().item(), float(p.flatten()[0])])
+
+
+def run_image_guided(ref, kind, names, depths, shape, steps, step_size, **kw):
+    b, f, h, w = shape
+    videos, labels = synth.clip(0, b=b, f=f, h=h, w=w)
+    with LR.quiet():
+        if kind == "i2v":
+            atk = ref.image_attacks.ImageGuidedFMDirection_Adam(names, depth=depths, step_size=step_size, steps=steps)
+            models = [atk.model]
+        elif kind == "ens":
+            atk = ref.image_attacks.ImageGuidedFML2_Adam_MultiModels(names, depths, steps=steps)
+            models = atk.models
+        else:
+            atk = ref.TPAMI_attack.AENS_I2V_MF(names, depths, step_size, steps=steps, **kw)
+            models = atk.models
+    vids = ["clip0"] * b
+    with LR.AdamSpy(keep=("grad", "param", "param_before", "exp_avg", "exp_avg_sq")) as spy, LR.quiet():
+        out = atk(videos.clone(), labels, vids)
+    rec = {"videos": videos.numpy(), "steps": steps, "step_size": step_size, "epsilon": 16 / 255,
+           "weight_checksums": np.stack([weight_checksum(m) for m in models])}
+    if kind == "aens":
+        adv, _, cost_saved = out
+        rec["cost_saved"] = cost_saved
+        rec["weights"] = np.stack(atk.weights)
+        rec["coeffs_after"] = atk.coeffs.numpy()
+    else:
+        adv = out
+    rec["adv"] = adv.detach().contiguous().numpy()
+    rec["cost"] = np.array([float(atk.loss_info["clip0"][i]["cost"]) for i in range(steps)], dtype=np.float32)
+    # teacher-forcing taps: gradient w.r.t. the modifier and the Adam state of the first and last step
+    # (ensemble fixtures keep only the first gradient: the Adam arithmetic is pinned by the i2v ones)
+    for tag, r in (("first", spy.records[0]), ("last", spy.records[-1])):
+        rec["g_mod_" + tag] = r["grad"].numpy()
+        if kind != "i2v":
+            break
+        rec["mod_" + tag] = r["param"].numpy()
+        rec["m_" + tag] = r["exp_avg"].numpy()
+        rec["v_" + tag] = r["exp_avg_sq"].numpy()
+        if tag == "last":   # state before the last step: the last step can be teacher-forced on its own
+            rec["mod_before_last"] = r["param_before"].numpy()
+            rec["m_before_last"] = r["exp_avg_before"].numpy()
+            rec["v_before_last"] = r["exp_avg_sq_before"].numpy()
+    return rec
+
+
+def run_base(ref):
+    torch.manual_seed(0)
+    model = synth.TinyVideoNet()
+    videos, _ = synth.clip(3, b=1, f=32, h=12, w=12)
+    labels = torch.tensor([3])
+    rec = {"videos": videos.numpy(), "labels": labels.numpy(), "weight_checksums": weight_checksum(model)[None]}
+    rec["fgsm"] = ref.base_attacks.FGSM(model)(videos.clone(), labels).numpy()
+    rec["bim3"] = ref.base_attacks.BIM(model, steps=3)(videos.clone(), labels).numpy()
+    rec["mifgsm3"] = ref.base_attacks.MIFGSM(model, steps=3)(videos.clone(), labels).numpy()
+    tgt = ref.base_attacks.BIM(model, steps=2)
+    tgt.set_attack_mode("targeted", lambda images, labels: (labels + 1) % 10)
+    rec["bim2_targeted"] = tgt(videos.clone(), labels).numpy()
+    g = torch.randn(2, 3, 32, 6, 6, generator=torch.Generator().manual_seed(5))
+    rec["norm_grads_in"] = g.numpy()
+    rec["norm_grads_frame"] = ref.utils.norm_grads(g.clone(), True).numpy()
+    rec["norm_grads_clip"] = ref.utils.norm_grads(g.clone(), False).numpy()
+    return rec
+
+
+def main():
+    torch.set_num_threads(THREADS)
+    os.makedirs(OUT, exist_ok=True)
+    ref = LR.load()
+    ens_names = ["resnet", "vgg", "squeezenet", "alexnet"]
+    jobs = {
+        "i2v_resnet50_d2_32": lambda: run_image_guided(ref, "i2v", ["resnet"], 2, (1, 2, 32, 32), 3, 0.005),
+        "i2v_vgg_d3_32": lambda: run_image_guided(ref, "i2v", ["vgg"], 3, (1, 2, 32, 32), 2, 0.005),
+        "ens_4models_64": lambda: run_image_guided(
+            ref, "ens", ens_names, {"resnet": 2, "vgg": 3, "squeezenet": 2, "alexnet": 3}, (1, 2, 64, 64), 3, 0.005),
+        "aens_4models_64": lambda: run_image_guided(
+            ref, "aens", ens_names, {n: [2, 3] for n in ens_names}, (1, 2, 64, 64), 3, 0.005, momentum=0.5),
+        "aens_ce_2models_64": lambda: run_image_guided(
+            ref, "aens", ["resnet", "squeezenet"], {"resnet": [1, 2], "squeezenet": [2, 3]}, (1, 2, 64, 64), 2, 0.005,
+            coef_CE=True),
+        "base_tiny3d": lambda: run_base(ref),
+    }
+    only = sys.argv[1:]
+    for name, job in jobs.items():
+        if only and name not in only:
+            continue
+        rec = job()
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **rec)
+        print("%-24s %8.1f KB" % (name, os.path.getsize(path) / 1024))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,59 @@
+"""The C-ABI library builds, loads on a CPU-only box and exports every symbol include/i2v_b200.h
+declares (no compute call is made here)."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "i2v_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(i2v_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from i2v_b200 import build, capi
+    build.build()
+    return capi.load()
+
+
+def test_header_functions_are_exported(lib):
+    names = _declared()
+    assert len(names) >= 15
+    out = subprocess.check_output(["nm", "-D", "--defined-only", lib._name]).decode()
+    exported = set(re.findall(r" T (i2v_\w+)", out))
+    missing = [n for n in names if n not in exported]
+    assert not missing, "declared in the header but not exported: %s" % missing
+
+
+def test_binding_covers_header(lib):
+    from i2v_b200 import capi
+    assert sorted(capi.SIGNATURES) == _declared()
+    assert capi.version() == 100
+
+
+def test_no_cpu_fallback():
+    """CPU tensors are refused: the product path has no CPU implementation."""
+    import torch
+    from i2v_b200 import capi
+    with pytest.raises(capi.I2VError):
+        capi.denorm(torch.zeros(1, 3, 4, 4), torch.zeros(1, 3, 4, 4), 16)
+
+
+def test_product_never_imports_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's baseline legs may touch oracle/."""
+    pkg = os.path.join(ROOT, "image-to-video-i2v-attack_b200")
+    files = [os.path.join(pkg, f) for f in os.listdir(pkg) if f.endswith(".py")]
+    files += [os.path.join(ROOT, f) for f in ("image_attacks.py", "TPAMI_attack.py", "base_attacks.py", "utils.py", "i2v_b200.py")]
+    for f in files:
+        src = open(f).read()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+        assert "/root/reference" not in src, f
+    for f in os.listdir(os.path.join(pkg, "csrc")):
+        src = open(os.path.join(pkg, "csrc", f)).read()
+        assert not re.search(r"#include\s*[\"<][^\">]*oracle", src), f

@@ -1,0 +1,291 @@
+"""GPU parity of the memory-bound kernels (K1, K2, K3a/b/c) against the CPU oracle, through the C ABI.
+
+Bars (BASELINE.json north_star):
+  * K3 update kernels: BIT-EXACT vs oracle/i2v_oracle.c on identical inputs.
+  * K1 cosine: cos within 1e-5 relative of the float64 arbiter (we get ~1e-7); gradient closer to the
+    float64 arbiter than torch-f32 autograd is.
+  * K2: within 1 ulp of the oracle (device exp() vs libm exp() in float64, rounded to f32).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ulp_diff
+from i2v_b200 import capi
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+EPS = 16 / 255
+DEV = "cuda"
+
+
+def bits_equal(a, b):
+    a = np.ascontiguousarray(a, dtype=np.float32).view(np.int32)
+    b = np.ascontiguousarray(b, dtype=np.float32).view(np.int32)
+    return np.array_equal(a, b)
+
+
+def gpu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+LAYOUTS = [
+    # shape, inner, channels
+    ((5, 3, 16, 20), 320, 3),          # [N,3,H,W] planar, inner % 4 == 0
+    ((3, 3, 7, 5), 35, 3),             # planar, inner % 4 != 0 and n % 4 != 0 (scalar tail)
+    ((2, 3, 4, 6, 6), 144, 3),         # [B,3,T,H,W]
+    ((4, 9, 9, 3), 1, 3),              # NHWC, 3 channels interleaved
+    ((4, 8, 8, 4), 1, 4),              # NHWC4 (padded channel stays 0)
+    ((0, 3, 8, 8), 64, 3),             # empty
+]
+
+
+def _rand01(shape, seed):
+    return np.random.default_rng(seed).random(shape, dtype=np.float32)
+
+
+@pytest.mark.parametrize("shape,inner,channels", LAYOUTS)
+def test_denorm_normalize_compose_bit_exact(shape, inner, channels):
+    rng = np.random.default_rng(1)
+    inp = (rng.standard_normal(shape) * 2).astype(np.float32)
+    x = torch.empty(shape, device=DEV)
+    capi.denorm(gpu(inp), x, inner, channels)
+    want = O.denorm(inp, inner, channels)
+    assert bits_equal(x.cpu().numpy(), want)
+    out = torch.empty(shape, device=DEV)
+    capi.normalize(gpu(want), out, inner, channels)
+    assert bits_equal(out.cpu().numpy(), O.normalize(want, inner, channels))
+    x01 = _rand01(shape, 2)
+    mod = ((rng.random(shape) - 0.5) * 0.3).astype(np.float32)      # exceeds ±eps on ~60 % of elements
+    capi.compose_norm(gpu(x01), gpu(mod), out, EPS, inner, channels)
+    assert bits_equal(out.cpu().numpy(), O.compose_norm(x01, mod, EPS, inner, channels))
+
+
+@pytest.mark.parametrize("shape,inner,channels", LAYOUTS)
+def test_adam_compose_bit_exact_over_steps(shape, inner, channels):
+    """Five Adam steps with gradients spanning 1e-9..1e-2 (step-1 gradients are ~1e-8),
+    pixels at the [0,1] borders and modifiers crossing ±eps so that both clamp masks are exercised."""
+    rng = np.random.default_rng(3)
+    x01 = _rand01(shape, 4)
+    x01[x01 < 0.05] = 0.0
+    x01[x01 > 0.95] = 1.0
+    if channels == 4:
+        x01[..., 3] = 0
+    mod = np.full(shape, np.float32(0.01 / 255))
+    m = np.zeros(shape, np.float32)
+    v = np.zeros(shape, np.float32)
+    d = dict(g=None, m=gpu(m), v=gpu(v), mod=gpu(mod), x=gpu(x01), out=torch.empty(shape, device=DEV))
+    table = capi.adam_step_table(5, 0.02).to(DEV)
+    step_idx = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for step in range(1, 6):
+        g = (rng.standard_normal(shape) * 10.0 ** rng.uniform(-9, -2, size=shape)).astype(np.float32)
+        g[rng.random(shape) < 0.05] = 0.0
+        m, v, mod, want = O.adam_compose(g, m, v, mod, x01, EPS, inner, step, 0.02, channels=channels)
+        if step % 2:   # alternate the two entry points: scalars by value / device table
+            capi.adam_compose(gpu(g), d["m"], d["v"], d["mod"], d["x"], d["out"], EPS, inner, step, 0.02, channels=channels)
+        else:
+            capi.adam_compose_table(gpu(g), d["m"], d["v"], d["mod"], d["x"], d["out"], EPS, inner, table, step_idx,
+                                    channels=channels)
+        capi.step_advance(step_idx)
+        if channels == 4:   # padded lanes: state untouched, output forced to 0 on both sides
+            sel = np.ones(shape, bool); sel[..., 3] = False
+        else:
+            sel = np.ones(shape, bool)
+        for name, ref in (("m", m), ("v", v), ("mod", mod), ("out", want)):
+            got = d[name].cpu().numpy()
+            assert bits_equal(got[sel], ref[sel]), (name, step)
+    assert int(step_idx.item()) == 5
+    if mod.size:
+        assert (np.abs(mod) > EPS).any(), "test should drive some modifiers outside the eps ball"
+
+
+@pytest.mark.parametrize("shape,inner", [((2, 3, 4, 6, 6), 144), ((1, 3, 3, 5, 7), 105), ((3, 3, 8, 8), 64)])
+@pytest.mark.parametrize("project", [True, False])
+def test_sign_step_project_bit_exact(shape, inner, project):
+    rng = np.random.default_rng(5)
+    x01 = _rand01(shape, 6)
+    adv = O.normalize(np.clip(x01 + (rng.random(shape).astype(np.float32) - 0.5) * 0.2, 0, 1), inner)
+    g = rng.standard_normal(shape).astype(np.float32)
+    g[rng.random(shape) < 0.1] = 0.0          # sign(0) = 0
+    a = gpu(adv)
+    capi.sign_step_project(a, gpu(g), gpu(x01) if project else None, EPS / 10, EPS, inner, project=project)
+    want = O.sign_step_project(adv, g, x01 if project else None, EPS / 10, EPS, inner, project=project)
+    assert bits_equal(a.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 32, 12, 12), (1, 3, 16, 7, 5), (3, 3, 4, 28, 28)])
+@pytest.mark.parametrize("clip_level", [False, True])
+def test_mi_update_bit_exact(shape, clip_level):
+    rng = np.random.default_rng(7)
+    inner = shape[2] * shape[3] * shape[4]
+    x01 = _rand01(shape, 8)
+    adv = O.normalize(x01, inner)
+    g = (rng.standard_normal(shape) * 1e-3).astype(np.float32)
+    mom = rng.standard_normal(shape).astype(np.float32)
+    norm = torch.empty((shape[0],) if clip_level else (shape[0], shape[2]), device=DEV)
+    capi.frame_absmean(gpu(g), norm, clip_level=clip_level)
+    want_norm = O.frame_absmean(g, clip_level)
+    assert ulp_diff(norm.cpu().numpy(), want_norm).max() <= 1       # tree vs sequential float64 sum
+    a, mo = gpu(adv), gpu(mom)
+    capi.mi_sign_step_project(a, gpu(g), mo, gpu(want_norm), gpu(x01), 1.0, EPS / 10, EPS, clip_level=clip_level)
+    want_adv, want_mom = O.mi_sign_step_project(adv, g, mom, want_norm, x01, 1.0, EPS / 10, EPS, clip_level)
+    assert bits_equal(mo.cpu().numpy(), want_mom)
+    assert bits_equal(a.cpu().numpy(), want_adv)
+
+
+def test_update_kernels_full_size_bit_exact():
+    """Config-2 frame size (224x224) on 48 frames: 7.2 M elements through K3a and K3b."""
+    shape = (48, 3, 224, 224)
+    inner = 224 * 224
+    rng = np.random.default_rng(9)
+    x01 = _rand01(shape, 10)
+    g = (rng.standard_normal(shape) * 1e-6).astype(np.float32)
+    mod = ((rng.random(shape) - 0.5) * 0.2).astype(np.float32)
+    m = (rng.standard_normal(shape) * 1e-6).astype(np.float32)
+    v = (rng.random(shape) * 1e-12).astype(np.float32)
+    dm, dv, dmod, out = gpu(m), gpu(v), gpu(mod), torch.empty(shape, device=DEV)
+    capi.adam_compose(gpu(g), dm, dv, dmod, gpu(x01), out, EPS, inner, 17, 0.005)
+    m2, v2, mod2, want = O.adam_compose(g, m, v, mod, x01, EPS, inner, 17, 0.005)
+    assert bits_equal(dm.cpu().numpy(), m2) and bits_equal(dv.cpu().numpy(), v2)
+    assert bits_equal(dmod.cpu().numpy(), mod2) and bits_equal(out.cpu().numpy(), want)
+    shape5 = (2, 3, 24, 224, 224)
+    adv = want.reshape(2, 24, 3, 224, 224).transpose(0, 2, 1, 3, 4).copy()
+    x5 = x01.reshape(2, 24, 3, 224, 224).transpose(0, 2, 1, 3, 4).copy()
+    g5 = g.reshape(shape5)
+    a = gpu(adv)
+    capi.sign_step_project(a, gpu(g5), gpu(x5), EPS / 10, EPS, 24 * inner)
+    assert bits_equal(a.cpu().numpy(), O.sign_step_project(adv, g5, x5, EPS / 10, EPS, 24 * inner))
+
+
+# ------------------------------------------------------------------------------------- K1
+def _torch_cos(a, b, dtype):
+    at = torch.tensor(a, dtype=dtype, requires_grad=True)
+    bt = torch.tensor(b, dtype=dtype)
+    c = torch.nn.functional.cosine_similarity(at.view(at.shape[0], -1), bt.view(bt.shape[0], -1))
+    c.sum().backward()
+    return c.detach().numpy(), at.grad.numpy()
+
+
+def _k1(a, b, w=1.0, relu_mask=False, w_dev=None, want_grad=True):
+    da, db = gpu(a), gpu(b)
+    grad = torch.empty_like(da) if want_grad else None
+    cos = torch.empty(a.shape[0], device=DEV)
+    capi.cosine_loss_grad(da, db, grad, cos, w_dev=w_dev, w_host=w, relu_mask=relu_mask)
+    return cos.cpu().numpy(), (grad.cpu().numpy() if want_grad else None)
+
+
+@pytest.mark.parametrize("N,D", [(3, 512 * 28 * 28), (5, 128 * 27 * 27), (2, 4099), (7, 384 * 13 * 13), (1, 12)])
+@pytest.mark.parametrize("near", [False, True])
+def test_cosine_loss_grad_vs_float64(N, D, near):
+    """near=True is the step-1 regime: a = b + 1e-4 noise, cos ~ 1 - 5e-9, gradient ~1e-8 of its terms."""
+    rng = np.random.default_rng(11)
+    b = np.maximum(rng.standard_normal((N, D)), 0).astype(np.float32)        # post-ReLU-like
+    if near:
+        a = (b * (1 + 1e-4 * rng.standard_normal((N, D)))).astype(np.float32)
+    else:
+        a = np.maximum(rng.standard_normal((N, D)), 0).astype(np.float32)
+    cos64, grad64 = O.cosine_loss_grad_f64(a, b)
+    cos, grad = _k1(a, b)
+    assert np.abs(cos - cos64).max() <= 1e-5 * np.abs(cos64).max()           # north-star tolerance
+    assert np.abs(cos - cos64).max() <= 1.2e-7                               # what we actually get
+    scale = np.abs(grad64).max(axis=1, keepdims=True)
+    err = (np.abs(grad - grad64) / scale).max()
+    assert err <= 1e-6, err                                                  # correctly rounded => ~6e-8
+    # torch-f32 autograd (the reference's arithmetic) is no closer to float64 than we are
+    _, g32 = _torch_cos(a, b, torch.float32)
+    err32 = (np.abs(g32 - grad64) / scale).max()
+    assert err <= err32 * 1.0001 + 1e-7, (err, err32)
+    # and torch-f64 autograd agrees with the analytic float64 gradient of the oracle
+    c64t, g64t = _torch_cos(a, b, torch.float64)
+    assert np.allclose(c64t, cos64, rtol=1e-12) and (np.abs(g64t - grad64) / scale).max() < 1e-9
+
+
+def test_cosine_weights_mask_and_loss_only():
+    rng = np.random.default_rng(12)
+    N, D = 4, 256 * 14 * 14
+    a = rng.standard_normal((N, D)).astype(np.float32)          # signed, so the ReLU mask bites
+    b = rng.standard_normal((N, D)).astype(np.float32)
+    cos64, grad64 = O.cosine_loss_grad_f64(a, b, w=0.125, relu_mask=True)
+    w_dev = torch.tensor([0.125], device=DEV)
+    cos, grad = _k1(a, b, w=99.0, relu_mask=True, w_dev=w_dev)   # w_dev wins over w_host
+    assert np.abs(cos - cos64).max() <= 1.2e-7
+    assert (grad[a <= 0] == 0).all()
+    assert (np.abs(grad - grad64) / np.abs(grad64).max()).max() <= 1e-6
+    cos2, none = _k1(a, b, want_grad=False)
+    assert none is None and bits_equal(cos2, cos)
+
+
+def test_cosine_zero_features_and_empty():
+    """All-zero frame: |a| is clamped to 1e-8, cos = 0, no NaN (torch 2.x cosine_similarity semantics)."""
+    N, D = 3, 4096
+    rng = np.random.default_rng(13)
+    a = rng.standard_normal((N, D)).astype(np.float32)
+    b = rng.standard_normal((N, D)).astype(np.float32)
+    a[1] = 0
+    b[2] = 0
+    cos, grad = _k1(a, b)
+    cos64, grad64 = O.cosine_loss_grad_f64(a, b)
+    assert np.isfinite(cos).all() and np.isfinite(grad).all()
+    assert cos[1] == 0 and cos[2] == 0
+    assert np.allclose(grad, grad64, rtol=1e-6, atol=1e-30)
+    ct, gt = _torch_cos(a, b, torch.float64)
+    assert np.allclose(grad64, gt, rtol=1e-9, atol=1e-30)       # the oracle follows torch's clamping
+    e = torch.empty(0, 16, device=DEV)
+    capi.cosine_loss_grad(e, e, torch.empty_like(e), torch.empty(0, device=DEV))
+
+
+@pytest.mark.parametrize("cluster", ["1", "2", "4", "8", "16"])
+def test_cosine_cluster_sizes_agree(cluster):
+    """Every cluster size (DSMEM reduction width, shared-memory stash coverage) gives the same answer;
+    full ResNet layer2 feature size, N not a multiple of anything."""
+    rng = np.random.default_rng(14)
+    N, D = 5, 512 * 28 * 28
+    a = np.maximum(rng.standard_normal((N, D)), 0).astype(np.float32)
+    b = np.maximum(rng.standard_normal((N, D)), 0).astype(np.float32)
+    cos64, grad64 = O.cosine_loss_grad_f64(a, b)
+    old = os.environ.get("I2V_COS_CLUSTER")
+    os.environ["I2V_COS_CLUSTER"] = cluster
+    try:
+        cos, grad = _k1(a, b)
+    finally:
+        if old is None:
+            os.environ.pop("I2V_COS_CLUSTER")
+        else:
+            os.environ["I2V_COS_CLUSTER"] = old
+    assert np.abs(cos - cos64).max() <= 1.2e-7
+    assert (np.abs(grad - grad64) / np.abs(grad64).max()).max() <= 1e-6
+
+
+# ------------------------------------------------------------------------------------- K2
+@pytest.mark.parametrize("L", [1, 2, 8, 16, 32])
+@pytest.mark.parametrize("momentum", [0.0, 0.5])
+def test_layer_reweight_and_sums(L, momentum):
+    rng = np.random.default_rng(15)
+    N = 37
+    coeffs = np.ones(L, np.float32)
+    prev = np.ones(L, np.float32)
+    dc, dp = gpu(coeffs), gpu(prev)
+    w_out = torch.empty(L, device=DEV)
+    log = torch.zeros(3, L, device=DEV)
+    cost_log = torch.zeros(3, device=DEV)
+    step_idx = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for step in range(3):
+        coeffs, w = O.layer_reweight(coeffs, prev, momentum)
+        capi.layer_reweight(dc, dp, momentum, w_out, log, step_idx)
+        assert ulp_diff(dc.cpu().numpy(), coeffs).max() <= 1
+        assert ulp_diff(w_out.cpu().numpy(), w).max() <= 1
+        assert bits_equal(log[step].cpu().numpy(), dc.cpu().numpy())
+        coeffs = dc.cpu().numpy().copy()           # teacher-force so 1-ulp differences do not accumulate
+        cosv = rng.uniform(0.2, 1.0, size=(L, N)).astype(np.float32)
+        for mode, ce in ((0, False), (1, False), (1, True)):
+            cost, prev_o = O.layer_sums(cosv, coeffs, mode, ce)
+            dprev = torch.zeros(L, device=DEV)
+            capi.layer_sums(gpu(cosv), dc, dprev, cost_log, step_idx, mode=mode, coef_CE=ce)
+            assert ulp_diff(cost_log[step].cpu().numpy(), np.float32(cost)).max() <= 1
+            if mode == 1:
+                assert ulp_diff(dprev.cpu().numpy(), prev_o).max() <= 1
+        prev = prev_o
+        dp.copy_(gpu(prev))
+        capi.step_advance(step_idx)

@@ -1,0 +1,93 @@
+"""Host-side logic that needs no GPU: depth -> layer mapping, name handling, sharding, step scalars."""
+import numpy as np
+import pytest
+import torch
+
+from i2v_b200 import backbones, capi, dist as D
+from oracle import oracle as O
+
+
+def test_depth_to_layer_mapping_matches_reference_tables():
+    m = backbones.seeded_random_init("resnet50")
+    assert backbones.find_target_layers(m, "resnet", 2) == [m.layer2[-1]]
+    assert backbones.find_target_layers(m, "resnet", [2, 3]) == [m.layer2[-1], m.layer3[-1]]
+    v = backbones.seeded_random_init("vgg16")
+    assert backbones.find_target_layers(v, "vgg", 3) == [v.features[20]]
+    a = backbones.seeded_random_init("alexnet")
+    assert backbones.find_target_layers(a, "alexnet", [2, 3]) == [a.features[4], a.features[7]]
+    s = backbones.seeded_random_init("squeezenet1_1")
+    assert backbones.find_target_layers(s, "squeezenet", 2) == [s.features[6].expand3x3_activation]
+    # list of depths hooks the whole Fire module (TPAMI_attack.py:195-198)
+    assert backbones.find_target_layers(s, "squeezenet", [2, 3]) == [s.features[6], s.features[9]]
+
+
+def test_unknown_model_and_depth_raise_value_error():
+    with pytest.raises(ValueError):
+        backbones.arch_of("inception")
+    m = backbones.seeded_random_init("alexnet")
+    with pytest.raises(ValueError):
+        backbones.find_target_layers(m, "alexnet", 5)
+
+
+def test_reference_names_keep_reference_archs():
+    saved = dict(backbones.ARCH_OVERRIDE)
+    backbones.ARCH_OVERRIDE.clear()
+    try:
+        assert backbones.arch_of("resnet") == "resnet101"      # image_attacks.py:95
+        assert backbones.arch_of("densenet") == "densenet161"  # image_attacks.py:97
+        assert backbones.arch_of("vgg") == "vgg16"
+        assert backbones.arch_of("resnet50") == "resnet50"
+    finally:
+        backbones.ARCH_OVERRIDE.update(saved)
+
+
+def test_seeded_init_is_reproducible_and_leaves_rng_alone():
+    torch.manual_seed(123)
+    before = torch.rand(1)
+    torch.manual_seed(123)
+    a = backbones.seeded_random_init("squeezenet1_1", 0)
+    after = torch.rand(1)
+    b = backbones.seeded_random_init("squeezenet1_1", 0)
+    assert torch.equal(before, after)
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert torch.equal(pa, pb)
+
+
+def test_adam_step_table_matches_oracle_scalars():
+    table = capi.adam_step_table(60, 0.005).numpy()
+    for k in (0, 1, 9, 59):
+        bc2, nss = O.adam_step_scalars(0.005, 0.9, 0.999, k + 1)
+        assert table[k, 0] == np.float32(bc2) and table[k, 1] == np.float32(nss)
+    # and the python-double recipe of torch/optim/adam.py
+    t = 7
+    assert table[t - 1, 0] == np.float32((1 - 0.999 ** t) ** 0.5)
+    assert table[t - 1, 1] == np.float32(-(0.005 / (1 - 0.9 ** t)))
+
+
+def test_contiguous_shard_partitions_exactly():
+    for n in (0, 1, 7, 400, 401):
+        for world in (1, 2, 3, 8):
+            spans = [D.contiguous_shard(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    # the reference's own split: 400 loader steps, --batch_nums 8 (image_main.py:61-63)
+    assert D.contiguous_shard(400, 3, 8) == (150, 200)
+
+
+def test_round_robin_shard_and_ensemble_placement():
+    got = sorted(i for r in range(4) for i in D.clip_shard(10, r, 4))
+    assert got == list(range(10))
+    names = ["resnet", "vgg", "densenet", "squeezenet"]
+    assert D.ensemble_placement(names, 2, 4) == ([2], 0)
+    assert D.ensemble_placement(names, 6, 8) == ([2], 1)
+    assert D.ensemble_placement(names, 1, 2) == ([1, 3], 0)
+    assert D.ensemble_placement(names, 4, 5) == ([], None)
+
+
+def test_loss_info_format():
+    from i2v_b200 import attack_loop
+    info = {}
+    attack_loop.record_loss_info(info, ["a", "b"], np.array([1.9999996, 1.5], dtype=np.float32))
+    assert info["a"][0] == {"cost": "1.9999996"} and info["b"][1] == {"cost": "1.5"}
