@@ -37,7 +37,20 @@ SIGNATURES = {
     "i2v_cosine_loss_grad_f32": ([_c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_p, _c_f, _c_int, _c_p], _c_int),
     "i2v_layer_reweight_f32": ([_c_p, _c_p, _c_int, _c_f, _c_p, _c_p, _c_p, _c_p], _c_int),
     "i2v_layer_sums_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_i64, _c_int, _c_int, _c_p], _c_int),
+    "i2v_conv_fwd_simt_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
+    "i2v_conv_dgrad_simt_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
+    "i2v_maxpool_fwd_f32": ([_c_p, _c_p, _c_p] + [_c_int] * 9 + [_c_p], _c_int),
+    "i2v_maxpool_bwd_f32": ([_c_p, _c_p, _c_p, _c_p] + [_c_int] * 9 + [_c_p], _c_int),
+    "i2v_copy_channels_f32": ([_c_p, _c_p, _c_i64] + [_c_int] * 6 + [_c_p], _c_int),
 }
+
+EPI_RELU = 1
+LAYOUT_X_NCHW = 16
+
+
+class ConvDesc(ctypes.Structure):
+    """i2v_conv_desc"""
+    _fields_ = [(n, ctypes.c_int32) for n in ("N", "H", "W", "Cin", "Cout", "R", "S", "stride", "pad", "P", "Q")]
 
 _lib = None
 
@@ -228,3 +241,36 @@ def layer_sums(cos, coeffs=None, prev=None, cost_log=None, step_idx=None, mode=0
     L, N = cos.shape
     _check(load().i2v_layer_sums_f32(_dev(cos), _dev(coeffs), _dev(prev), _dev(cost_log), _dev(step_idx, torch.int32),
                                      L, N, mode, int(coef_CE), _stream()), "i2v_layer_sums_f32")
+
+
+# ------------------------------------------------------------------------------- K4 / K5 (CUDA-core path)
+def conv_fwd_simt(desc, x, bmat, bias, residual, y, relu=False, x_nchw=False):
+    flags = (EPI_RELU if relu else 0) | (LAYOUT_X_NCHW if x_nchw else 0)
+    _check(load().i2v_conv_fwd_simt_f32(ctypes.addressof(desc), _dev(x), _dev(bmat), _dev(bias), _dev(residual), _dev(y),
+                                        flags, _stream()), "i2v_conv_fwd_simt_f32")
+
+
+def conv_dgrad_simt(desc, dy, bmat, addend, mask_src, dx, x_nchw=False):
+    flags = LAYOUT_X_NCHW if x_nchw else 0
+    _check(load().i2v_conv_dgrad_simt_f32(ctypes.addressof(desc), _dev(dy), _dev(bmat), _dev(addend), _dev(mask_src),
+                                          _dev(dx), flags, _stream()), "i2v_conv_dgrad_simt_f32")
+
+
+def maxpool_fwd(x, y, argmax, k, stride, pad):
+    N, H, W, C = x.shape
+    _, P, Q, _ = y.shape
+    _check(load().i2v_maxpool_fwd_f32(_dev(x), _dev(y), _dev(argmax, torch.uint8), N, H, W, C, P, Q, k, stride, pad,
+                                      _stream()), "i2v_maxpool_fwd_f32")
+
+
+def maxpool_bwd(dy, argmax, mask_src, dx, k, stride, pad):
+    N, H, W, C = dx.shape
+    _, P, Q, _ = dy.shape
+    _check(load().i2v_maxpool_bwd_f32(_dev(dy), _dev(argmax, torch.uint8), _dev(mask_src), _dev(dx), N, H, W, C, P, Q,
+                                      k, stride, pad, _stream()), "i2v_maxpool_bwd_f32")
+
+
+def copy_channels(src, dst, src_off, dst_off, ccopy, accumulate=False):
+    M = src.numel() // src.shape[-1]
+    _check(load().i2v_copy_channels_f32(_dev(src), _dev(dst), M, src.shape[-1], src_off, dst.shape[-1], dst_off, ccopy,
+                                        int(accumulate), _stream()), "i2v_copy_channels_f32")

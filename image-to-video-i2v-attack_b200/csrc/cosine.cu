@@ -29,17 +29,36 @@ constexpr int kUnroll = 4;
 constexpr double kCosEps = 1e-8;   // F.cosine_similarity default eps (image_attacks.py:343)
 
 struct CosPartial { double dot, aa, bb; };
+struct CosCoef { float ah, al, bh, bl; };   // alpha, beta as unevaluated float pairs (hi + lo)
+
+// One gradient element, float32 only (no F2F conversions: the XU pipe was 34 % busy with them):
+//   g = alpha*b - beta*a   with alpha = ah+al, beta = bh+bl (each pair carries ~48 bits)
+// t + e == bh*a exactly (e is the rounding error of the product, recovered by an FMA), so the
+// cancellation alpha*b - beta*a happens inside one FMA on exact operands; the result is within
+// ~2 ulp of the correctly rounded float64 value even at step 1 where |g| ~ 1e-8 |alpha*b|.
+__device__ __forceinline__ float cos_grad1(float a, float b, const CosCoef& c) {
+    const float t = __fmul_rn(c.bh, a);
+    const float e = __fmaf_rn(c.bh, a, -t);
+    const float g1 = __fmaf_rn(c.ah, b, -t);
+    const float lo = __fmaf_rn(c.al, b, -__fmul_rn(c.bl, a));
+    return __fadd_rn(__fsub_rn(g1, e), lo);
+}
 
 template <bool VEC>
-__global__ void __launch_bounds__(kCosThreads, 1)
+__global__ void __launch_bounds__(kCosThreads, 2)
 cosine_loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ grad,
                         float* __restrict__ cos_out, int64_t D, const float* __restrict__ w_dev, float w_host,
-                        int relu_mask, int64_t cap) {
+                        int relu_mask, int64_t cap, int64_t N) {
     extern __shared__ float4 stash[];   // [2][cap]: this CTA's slice of a and of b (as much as fits)
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned S = cluster.num_blocks();
     const unsigned rank = cluster.block_rank();
-    const int64_t frame = blockIdx.x / S;
+    __shared__ CosPartial warp_part[kCosThreads / 32];
+    __shared__ CosPartial cta_part;
+    __shared__ CosCoef coef;
+    // Persistent clusters: the grid holds as many clusters as are co-resident and each walks over frames
+    // with that stride, so no SM slot idles waiting for 16 free slots in one GPC between frames.
+    for (int64_t frame = blockIdx.x / S; frame < N; frame += gridDim.x / S) {
     const float* af = a + frame * D;
     const float* bf = b + frame * D;
 
@@ -48,7 +67,11 @@ cosine_loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b
     const int64_t lo = units * rank / S;
     const int64_t hi = units * (rank + 1) / S;
 
-    double dot = 0.0, aa = 0.0, bb = 0.0;
+    // Per-thread partial sums stay in float32: a thread sees only slice/512 (~50-100) elements per lane
+    // group, four independent accumulators per quantity; the ~1e-7 relative rounding of each partial is
+    // random across the 8K threads of a frame, so the frame sums (combined in FP64 below) are good to
+    // ~2e-9 relative — two orders better than the 1e-5 the loss needs.
+    float d4[4] = {0.f, 0.f, 0.f, 0.f}, p4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
     if (VEC) {
         const float4* a4 = reinterpret_cast<const float4*>(af);
         const float4* b4 = reinterpret_cast<const float4*>(bf);
@@ -63,35 +86,35 @@ cosine_loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
                 const int64_t k = i + u * kCosThreads - lo;
-                if (grad != nullptr && k < cap) { sa[k] = av[u]; sb[k] = bv[u]; }
+                if (k < cap) { sa[k] = av[u]; sb[k] = bv[u]; }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    double x = (double)(&av[u].x)[j], y = (double)(&bv[u].x)[j];
-                    dot = fma(x, y, dot); aa = fma(x, x, aa); bb = fma(y, y, bb);
+                    const float x = (&av[u].x)[j], y = (&bv[u].x)[j];
+                    d4[j] = __fmaf_rn(x, y, d4[j]); p4[j] = __fmaf_rn(x, x, p4[j]); q4[j] = __fmaf_rn(y, y, q4[j]);
                 }
             }
         }
         for (; i < hi; i += kCosThreads) {
             float4 av = ld_stream(a4 + i), bv = ld_stream(b4 + i);
             const int64_t k = i - lo;
-            if (grad != nullptr && k < cap) { sa[k] = av; sb[k] = bv; }
+            if (k < cap) { sa[k] = av; sb[k] = bv; }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                double x = (double)(&av.x)[j], y = (double)(&bv.x)[j];
-                dot = fma(x, y, dot); aa = fma(x, x, aa); bb = fma(y, y, bb);
+                const float x = (&av.x)[j], y = (&bv.x)[j];
+                d4[j] = __fmaf_rn(x, y, d4[j]); p4[j] = __fmaf_rn(x, x, p4[j]); q4[j] = __fmaf_rn(y, y, q4[j]);
             }
         }
     } else {
         for (int64_t i = lo + threadIdx.x; i < hi; i += kCosThreads) {
-            double x = (double)af[i], y = (double)bf[i];
-            dot = fma(x, y, dot); aa = fma(x, x, aa); bb = fma(y, y, bb);
+            const float x = af[i], y = bf[i];
+            d4[0] = __fmaf_rn(x, y, d4[0]); p4[0] = __fmaf_rn(x, x, p4[0]); q4[0] = __fmaf_rn(y, y, q4[0]);
         }
     }
+    double dot = ((double)d4[0] + (double)d4[1]) + ((double)d4[2] + (double)d4[3]);
+    double aa = ((double)p4[0] + (double)p4[1]) + ((double)p4[2] + (double)p4[3]);
+    double bb = ((double)q4[0] + (double)q4[1]) + ((double)q4[2] + (double)q4[3]);
 
     // CTA reduction: warp shuffles, then 16 warps through shared memory in fixed order
-    __shared__ CosPartial warp_part[kCosThreads / 32];
-    __shared__ CosPartial cta_part;
-    __shared__ double coef[2];
     dot = warp_sum(dot); aa = warp_sum(aa); bb = warp_sum(bb);
     if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = CosPartial{dot, aa, bb};
     __syncthreads();
@@ -113,14 +136,18 @@ cosine_loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b
         const double inv = 1.0 / (na * nb);
         const double cosv = t.dot * inv;
         const double w = (double)(w_dev ? *w_dev : w_host);
-        coef[0] = w * inv;                                        // alpha: multiplies b
-        coef[1] = (na_raw > kCosEps) ? w * cosv / (na * na) : 0.0; // beta:  multiplies a (0 when |a| is clamped)
+        const double alpha = w * inv;                                             // multiplies b
+        const double beta = (na_raw > kCosEps) ? w * cosv / (na * na) : 0.0;      // multiplies a (0 when |a| is clamped)
+        CosCoef c;
+        c.ah = (float)alpha; c.al = (float)(alpha - (double)c.ah);
+        c.bh = (float)beta;  c.bl = (float)(beta - (double)c.bh);
+        coef = c;
         if (rank == 0 && cos_out) cos_out[frame] = (float)cosv;
     }
-    cluster.sync();   // remote reads done before any CTA may exit; also publishes coef[] to the CTA
-    if (grad == nullptr) return;
+    cluster.sync();   // remote reads done before cta_part is reused / the CTA exits; publishes coef
+    if (grad == nullptr) continue;
 
-    const double alpha = coef[0], beta = coef[1];
+    const CosCoef c = coef;
     float* gf = grad + frame * D;
     if (VEC) {
         const float4* a4 = reinterpret_cast<const float4*>(af);
@@ -139,19 +166,20 @@ cosine_loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b
             if (k < cap) { av = sa[k]; bv = sb[k]; } else { av = ld_plain(a4 + i); bv = ld_plain(b4 + i); }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                float x = (&av.x)[j];
-                float gval = (float)fma(alpha, (double)(&bv.x)[j], -(beta * (double)x));
+                const float x = (&av.x)[j];
+                const float gval = cos_grad1(x, (&bv.x)[j], c);
                 (&r.x)[j] = (relu_mask && !(x > 0.0f)) ? 0.0f : gval;
             }
             st_stream(g4 + i, r);
         }
     } else {
         for (int64_t i = hi - 1 - threadIdx.x; i >= lo; i -= kCosThreads) {
-            float x = af[i];
-            float gval = (float)fma(alpha, (double)bf[i], -(beta * (double)x));
+            const float x = af[i];
+            const float gval = cos_grad1(x, bf[i], c);
             gf[i] = (relu_mask && !(x > 0.0f)) ? 0.0f : gval;
         }
     }
+    }   // frames
 }
 
 // K2: one warp.  coeffs <- softmax(softmax(prev) + momentum*coeffs)   (TPAMI_attack.py:265)
@@ -221,17 +249,16 @@ layer_sums_kernel(const float* __restrict__ cosv, const float* __restrict__ coef
 using namespace i2v;
 
 // Cluster size / stash policy (host).  I2V_COS_CLUSTER=<1|2|4|8|16> overrides for experiments.
-static int pick_cluster(int64_t N, int64_t units, int64_t cap_max) {
+static int pick_cluster(int64_t N, int64_t units) {
     if (const char* e = getenv("I2V_COS_CLUSTER")) {
         int v = atoi(e);
         if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) return v;
     }
-    int s_fit = 1;
-    while (s_fit < 16 && (units + s_fit - 1) / s_fit > cap_max) s_fit <<= 1;   // whole slice on-chip if possible
-    int s_fill = 1;
-    while (s_fill < 16 && N * s_fill < (int64_t)sm_count()) s_fill <<= 1;       // at least one CTA per SM
-    int S = s_fit > s_fill ? s_fit : s_fill;
-    while (S > 1 && units / S < 1024) S >>= 1;                                  // keep >= 4K elements per CTA
+    // As many CTAs per frame as possible (more of the frame on-chip, fewer frames in flight so the
+    // un-stashed tails stay in L2), while every CTA keeps >= 16K elements to stream.
+    int S = 16;
+    while (S > 1 && units / S < 4096) S >>= 1;
+    (void)N;
     return S;
 }
 
@@ -248,22 +275,24 @@ static int cosine_launch(const float* a, const float* b, float* grad_a, float* c
         smem_optin = v;
     }
     const int64_t units = VEC ? D / 4 : D;
-    const int64_t cap_max = VEC ? (smem_optin - 2048) / 32 : 0;   // float4 pairs that fit beside the static smem
+    // Two CTAs share an SM so that one CTA's load phase overlaps the other's reduce/store phase; each
+    // gets half of the shared memory for its stash.  I2V_COS_CTAS_PER_SM=1 gives one CTA the whole SM.
+    int per_sm = 2;
+    if (const char* e = getenv("I2V_COS_CTAS_PER_SM")) { int v = atoi(e); if (v == 1 || v == 2) per_sm = v; }
+    const int64_t cap_max = VEC ? ((smem_optin - 2048) / per_sm - 1024) / 32 : 0;   // float4 pairs per CTA
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 2048);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e != cudaSuccess) return cuda_fail(e, "i2v_cosine_loss_grad_f32 (attributes)");
         attr_done = true;
     }
-    int S = pick_cluster(N, units, cap_max > 0 ? cap_max : 1);
+    int S = pick_cluster(N, units);
 
     for (;;) {
         const int64_t slice = (units + S - 1) / S;
-        // Fully stashed slices may share an SM; partially stashed ones take the whole SM so that at most
-        // 148/S frames are in flight and the un-stashed tails stay L2-resident.
         const int64_t cap = !VEC || grad_a == nullptr ? 0 : (slice <= cap_max ? slice : cap_max);
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3((unsigned)(N * S));
+        cfg.gridDim = dim3((unsigned)(N * S));   // upper bound; trimmed to the co-resident cluster count below
         cfg.blockDim = dim3(kCosThreads);
         cfg.dynamicSmemBytes = (size_t)cap * 32;
         cfg.stream = st;
@@ -274,15 +303,14 @@ static int cosine_launch(const float* a, const float* b, float* grad_a, float* c
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if (S > 8) {   // non-portable size: make sure this device can co-schedule such a cluster
-            int nclusters = 0;
-            if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess || nclusters < 1) {
-                cudaGetLastError();
-                S = 8;
-                continue;
-            }
+        int nclusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess || nclusters < 1) {
+            cudaGetLastError();
+            if (S > 1) { S >>= 1; continue; }   // e.g. a non-portable size this device cannot co-schedule
+            nclusters = 1;
         }
-        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, b, grad_a, cos_out, D, w_dev, w_host, relu_mask, cap);
+        if (getenv("I2V_COS_NONPERSISTENT") == nullptr && (int64_t)nclusters < N) cfg.gridDim = dim3((unsigned)(nclusters * S));
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a, b, grad_a, cos_out, D, w_dev, w_host, relu_mask, cap, N);
         if (e != cudaSuccess) return cuda_fail(e, "i2v_cosine_loss_grad_f32");
         return I2V_OK;
     }

@@ -17,9 +17,18 @@ namespace i2v {
 
 constexpr int kThreads = 256;
 
-static inline int grid_for(int64_t nvec, int per_sm = 8) {
+// Grid = SM count x CTAs that are actually co-resident per SM for THIS kernel (registers decide), so the
+// grid-stride loop runs as exactly one full wave: a grid of 8 CTAs/SM when only 6 fit leaves a
+// one-third-full second wave (measured: 1.33 waves, 61 % warps active on K3a).
+template <typename K>
+static inline int grid_for(K kernel, int64_t nvec) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 0) != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        occ = 4;
+    }
     int64_t want = (nvec + kThreads - 1) / kThreads;
-    int64_t cap = (int64_t)sm_count() * per_sm;   // a multiple of the SM count: whole waves only
+    int64_t cap = (int64_t)sm_count() * occ;
     if (want < 1) want = 1;
     return (int)(want < cap ? want : cap);
 }
@@ -323,6 +332,7 @@ __global__ void step_advance_kernel(int* step_idx) { *step_idx += 1; }
 // host-side dispatch
 // ---------------------------------------------------------------------------------------------
 static int check_layout(const void* p0, int64_t n, int64_t inner, int channels) {
+    if (n == 0) return I2V_OK;   // empty batch: nothing to check, nothing to launch (pointers may be null)
     I2V_REQUIRE(p0 != nullptr, "null tensor pointer");
     I2V_REQUIRE(n >= 0 && inner >= 1, "bad sizes n=%lld inner=%lld", (long long)n, (long long)inner);
     I2V_REQUIRE(channels == 3 || channels == 4, "channels must be 3 or 4 (got %d)", channels);
@@ -339,15 +349,15 @@ using namespace i2v;
 
 extern "C" int i2v_denorm_f32(const float* inp, float* x, int64_t n, int64_t inner, int channels, i2v_stream_t stream) {
     if (int r = check_layout(inp, n, inner, channels)) return r;
-    I2V_REQUIRE(x && aligned16(x), "x must be a 16-byte aligned device pointer");
     if (n == 0) return I2V_OK;
+    I2V_REQUIRE(x && aligned16(x), "x must be a 16-byte aligned device pointer");
     cudaStream_t st = as_stream(stream);
     if (n < (int64_t)0x7fffffff) {
-        if (inner % 4 == 0) denorm_kernel<uint32_t, true><<<grid_for(n / 4), kThreads, 0, st>>>(inp, x, (uint32_t)n, (uint32_t)inner, channels);
-        else denorm_kernel<uint32_t, false><<<grid_for(n / 4), kThreads, 0, st>>>(inp, x, (uint32_t)n, (uint32_t)inner, channels);
+        if (inner % 4 == 0) denorm_kernel<uint32_t, true><<<grid_for(denorm_kernel<uint32_t, true>, n / 4), kThreads, 0, st>>>(inp, x, (uint32_t)n, (uint32_t)inner, channels);
+        else denorm_kernel<uint32_t, false><<<grid_for(denorm_kernel<uint32_t, false>, n / 4), kThreads, 0, st>>>(inp, x, (uint32_t)n, (uint32_t)inner, channels);
     } else {
-        if (inner % 4 == 0) denorm_kernel<uint64_t, true><<<grid_for(n / 4), kThreads, 0, st>>>(inp, x, (uint64_t)n, (uint64_t)inner, channels);
-        else denorm_kernel<uint64_t, false><<<grid_for(n / 4), kThreads, 0, st>>>(inp, x, (uint64_t)n, (uint64_t)inner, channels);
+        if (inner % 4 == 0) denorm_kernel<uint64_t, true><<<grid_for(denorm_kernel<uint64_t, true>, n / 4), kThreads, 0, st>>>(inp, x, (uint64_t)n, (uint64_t)inner, channels);
+        else denorm_kernel<uint64_t, false><<<grid_for(denorm_kernel<uint64_t, false>, n / 4), kThreads, 0, st>>>(inp, x, (uint64_t)n, (uint64_t)inner, channels);
     }
     I2V_LAUNCH_CHECK("i2v_denorm_f32");
     return I2V_OK;
@@ -355,15 +365,15 @@ extern "C" int i2v_denorm_f32(const float* inp, float* x, int64_t n, int64_t inn
 
 extern "C" int i2v_normalize_f32(const float* x, float* out, int64_t n, int64_t inner, int channels, i2v_stream_t stream) {
     if (int r = check_layout(x, n, inner, channels)) return r;
-    I2V_REQUIRE(out && aligned16(out), "out must be a 16-byte aligned device pointer");
     if (n == 0) return I2V_OK;
+    I2V_REQUIRE(out && aligned16(out), "out must be a 16-byte aligned device pointer");
     cudaStream_t st = as_stream(stream);
     if (n < (int64_t)0x7fffffff) {
-        if (inner % 4 == 0) normalize_kernel<uint32_t, true><<<grid_for(n / 4), kThreads, 0, st>>>(x, out, (uint32_t)n, (uint32_t)inner, channels);
-        else normalize_kernel<uint32_t, false><<<grid_for(n / 4), kThreads, 0, st>>>(x, out, (uint32_t)n, (uint32_t)inner, channels);
+        if (inner % 4 == 0) normalize_kernel<uint32_t, true><<<grid_for(normalize_kernel<uint32_t, true>, n / 4), kThreads, 0, st>>>(x, out, (uint32_t)n, (uint32_t)inner, channels);
+        else normalize_kernel<uint32_t, false><<<grid_for(normalize_kernel<uint32_t, false>, n / 4), kThreads, 0, st>>>(x, out, (uint32_t)n, (uint32_t)inner, channels);
     } else {
-        if (inner % 4 == 0) normalize_kernel<uint64_t, true><<<grid_for(n / 4), kThreads, 0, st>>>(x, out, (uint64_t)n, (uint64_t)inner, channels);
-        else normalize_kernel<uint64_t, false><<<grid_for(n / 4), kThreads, 0, st>>>(x, out, (uint64_t)n, (uint64_t)inner, channels);
+        if (inner % 4 == 0) normalize_kernel<uint64_t, true><<<grid_for(normalize_kernel<uint64_t, true>, n / 4), kThreads, 0, st>>>(x, out, (uint64_t)n, (uint64_t)inner, channels);
+        else normalize_kernel<uint64_t, false><<<grid_for(normalize_kernel<uint64_t, false>, n / 4), kThreads, 0, st>>>(x, out, (uint64_t)n, (uint64_t)inner, channels);
     }
     I2V_LAUNCH_CHECK("i2v_normalize_f32");
     return I2V_OK;
@@ -372,15 +382,15 @@ extern "C" int i2v_normalize_f32(const float* x, float* out, int64_t n, int64_t 
 extern "C" int i2v_compose_norm_f32(const float* x, const float* mod, float* out, int64_t n, int64_t inner,
                                     int channels, float eps, i2v_stream_t stream) {
     if (int r = check_layout(x, n, inner, channels)) return r;
-    I2V_REQUIRE(mod && out && aligned16(mod) && aligned16(out), "mod/out must be 16-byte aligned device pointers");
     if (n == 0) return I2V_OK;
+    I2V_REQUIRE(mod && out && aligned16(mod) && aligned16(out), "mod/out must be 16-byte aligned device pointers");
     cudaStream_t st = as_stream(stream);
     if (n < (int64_t)0x7fffffff) {
-        if (inner % 4 == 0) compose_kernel<uint32_t, true><<<grid_for(n / 4), kThreads, 0, st>>>(x, mod, out, (uint32_t)n, (uint32_t)inner, channels, eps);
-        else compose_kernel<uint32_t, false><<<grid_for(n / 4), kThreads, 0, st>>>(x, mod, out, (uint32_t)n, (uint32_t)inner, channels, eps);
+        if (inner % 4 == 0) compose_kernel<uint32_t, true><<<grid_for(compose_kernel<uint32_t, true>, n / 4), kThreads, 0, st>>>(x, mod, out, (uint32_t)n, (uint32_t)inner, channels, eps);
+        else compose_kernel<uint32_t, false><<<grid_for(compose_kernel<uint32_t, false>, n / 4), kThreads, 0, st>>>(x, mod, out, (uint32_t)n, (uint32_t)inner, channels, eps);
     } else {
-        if (inner % 4 == 0) compose_kernel<uint64_t, true><<<grid_for(n / 4), kThreads, 0, st>>>(x, mod, out, (uint64_t)n, (uint64_t)inner, channels, eps);
-        else compose_kernel<uint64_t, false><<<grid_for(n / 4), kThreads, 0, st>>>(x, mod, out, (uint64_t)n, (uint64_t)inner, channels, eps);
+        if (inner % 4 == 0) compose_kernel<uint64_t, true><<<grid_for(compose_kernel<uint64_t, true>, n / 4), kThreads, 0, st>>>(x, mod, out, (uint64_t)n, (uint64_t)inner, channels, eps);
+        else compose_kernel<uint64_t, false><<<grid_for(compose_kernel<uint64_t, false>, n / 4), kThreads, 0, st>>>(x, mod, out, (uint64_t)n, (uint64_t)inner, channels, eps);
     }
     I2V_LAUNCH_CHECK("i2v_compose_norm_f32");
     return I2V_OK;
@@ -389,7 +399,7 @@ extern "C" int i2v_compose_norm_f32(const float* x, const float* mod, float* out
 extern "C" int i2v_fill_f32(float* p, float value, int64_t n, i2v_stream_t stream) {
     I2V_REQUIRE(p && aligned16(p) && n >= 0, "bad fill arguments");
     if (n == 0) return I2V_OK;
-    fill_kernel<<<grid_for(n / 4), kThreads, 0, as_stream(stream)>>>(p, value, n);
+    fill_kernel<<<grid_for(fill_kernel, n / 4), kThreads, 0, as_stream(stream)>>>(p, value, n);
     I2V_LAUNCH_CHECK("i2v_fill_f32");
     return I2V_OK;
 }
@@ -413,7 +423,7 @@ template <bool TABLE>
 static int adam_launch(const float* g, float* m, float* v, float* mod, const float* x, float* out, int64_t n,
                        int64_t inner, int channels, float eps, AdamScalars s, const float* table, const int* idx,
                        cudaStream_t st) {
-    const int grid = grid_for(n / 4);
+    const int grid = grid_for(adam_compose_kernel<uint32_t, true, TABLE>, n / 4);
     if (n < (int64_t)0x7fffffff) {
         if (inner % 4 == 0) adam_compose_kernel<uint32_t, true, TABLE><<<grid, kThreads, 0, st>>>(g, m, v, mod, x, out, (uint32_t)n, (uint32_t)inner, channels, eps, s, table, idx);
         else adam_compose_kernel<uint32_t, false, TABLE><<<grid, kThreads, 0, st>>>(g, m, v, mod, x, out, (uint32_t)n, (uint32_t)inner, channels, eps, s, table, idx);
@@ -429,10 +439,10 @@ extern "C" int i2v_adam_compose_f32(const float* g, float* m, float* v, float* m
                                     int64_t n, int64_t inner, int channels, float eps, double lr, double beta1,
                                     double beta2, double adam_eps, int step, i2v_stream_t stream) {
     if (int r = check_layout(g, n, inner, channels)) return r;
+    if (n == 0) return I2V_OK;
     I2V_REQUIRE(m && v && mod && x && next_img, "null state pointer");
     I2V_REQUIRE(aligned16(m) && aligned16(v) && aligned16(mod) && aligned16(x) && aligned16(next_img), "state pointers must be 16-byte aligned");
     I2V_REQUIRE(step >= 1, "Adam step is 1-based (got %d)", step);
-    if (n == 0) return I2V_OK;
     AdamScalars s;
     s.w1 = (float)(1.0 - beta1);
     s.beta2 = (float)beta2;
@@ -447,9 +457,9 @@ extern "C" int i2v_adam_compose_table_f32(const float* g, float* m, float* v, fl
                                           float beta2, float a2, float adam_eps, const float* step_table,
                                           const int* step_idx, i2v_stream_t stream) {
     if (int r = check_layout(g, n, inner, channels)) return r;
+    if (n == 0) return I2V_OK;
     I2V_REQUIRE(m && v && mod && x && next_img && step_table && step_idx, "null state pointer");
     I2V_REQUIRE(aligned16(m) && aligned16(v) && aligned16(mod) && aligned16(x) && aligned16(next_img), "state pointers must be 16-byte aligned");
-    if (n == 0) return I2V_OK;
     AdamScalars s{w1, beta2, a2, adam_eps, 0.f, 0.f};
     return adam_launch<true>(g, m, v, mod, x, next_img, n, inner, channels, eps, s, step_table, step_idx, as_stream(stream));
 }
@@ -464,12 +474,12 @@ extern "C" int i2v_step_advance(int* step_idx, i2v_stream_t stream) {
 extern "C" int i2v_sign_step_project_f32(float* adv, const float* g, const float* x, int64_t n, int64_t inner,
                                          int channels, float step_size, float eps, int project, i2v_stream_t stream) {
     if (int r = check_layout(adv, n, inner, channels)) return r;
+    if (n == 0) return I2V_OK;
     I2V_REQUIRE(channels == 3, "sign-step kernels take the reference's 3-channel layouts only");
     I2V_REQUIRE(g && aligned16(g), "g must be a 16-byte aligned device pointer");
     I2V_REQUIRE(!project || (x && aligned16(x)), "x is required (16-byte aligned) when project != 0");
-    if (n == 0) return I2V_OK;
     cudaStream_t st = as_stream(stream);
-    const int grid = grid_for(n / 4);
+    const int grid = grid_for(sign_step_kernel<uint32_t, true>, n / 4);
     if (n < (int64_t)0x7fffffff) {
         if (inner % 4 == 0) sign_step_kernel<uint32_t, true><<<grid, kThreads, 0, st>>>(adv, g, x, (uint32_t)n, (uint32_t)inner, channels, step_size, eps, project);
         else sign_step_kernel<uint32_t, false><<<grid, kThreads, 0, st>>>(adv, g, x, (uint32_t)n, (uint32_t)inner, channels, step_size, eps, project);
@@ -502,7 +512,7 @@ extern "C" int i2v_mi_sign_step_project_f32(float* adv, const float* g, float* m
     I2V_REQUIRE((HW & 3) != 0 || (aligned16(adv) && aligned16(g) && aligned16(momentum) && aligned16(x)), "tensors must be 16-byte aligned");
     const int64_t n = (int64_t)B * C * T * HW;
     if (n == 0) return I2V_OK;
-    mi_step_kernel<<<grid_for((HW & 3) == 0 ? n / 4 : n), kThreads, 0, as_stream(stream)>>>(
+    mi_step_kernel<<<grid_for(mi_step_kernel, (HW & 3) == 0 ? n / 4 : n), kThreads, 0, as_stream(stream)>>>(
         adv, g, momentum, norm, x, C, T, HW, clip_level, decay, step_size, eps, n);
     I2V_LAUNCH_CHECK("i2v_mi_sign_step_project_f32");
     return I2V_OK;

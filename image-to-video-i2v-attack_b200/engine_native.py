@@ -1,0 +1,374 @@
+"""Native feature extractor: the truncated backbone forward and its input data-gradient on this repo's
+own sm_100a kernels (K4/K5), NHWC float32 activations.
+
+What the reference runs per step through torchvision + cuDNN + autograd (image_attacks.py:334, 352):
+the FULL network forward, then a backward that also produces every weight gradient.  Here:
+
+  * the graph is cut at the deepest hooked layer (nothing after it feeds the loss);
+  * eval-mode BatchNorm (image_attacks.py:253-256) is folded into the convolution weights and bias;
+  * ReLU, residual adds and the ReLU-backward masks live in the convolution epilogues;
+  * backward is the data gradient only; gradients are kept as "pre-activation" gradients, i.e. already
+    multiplied by 1[activation > 0], so no separate ReLU-backward pass exists.
+
+The graph is a small list of ops over named buffers, built from the torchvision module (weights are
+taken from it, so random-init / pretrained policies of backbones.py apply unchanged):
+
+    Conv(x -> y, folded weights, relu, residual)     MaxPool(x -> y)     Concat(xs -> y)   (Fire)
+
+Supported families: resnet (Bottleneck nets), vgg, alexnet, squeezenet — every hook point of
+reference image_attacks.py:260-271 and TPAMI_attack.py:176-200.  DenseNet (BN-ReLU-Conv ordering,
+average pooling) is not implemented here and raises; use engine='cudnn' for it.
+
+Kernel selection per conv: the tcgen05 tensor-core implicit GEMM (conv_tc.cu) when it supports the
+shape, otherwise the CUDA-core gather-GEMM (conv_simt.cu).  `tf32x3=True` (default, "FP32 parity
+mode") runs the tensor cores with 3xTF32 split accumulation; False is plain TF32.
+"""
+import os
+
+import torch
+import torch.nn as nn
+import torchvision
+
+from . import backbones, capi
+
+
+class _Conv:
+    kind = "conv"
+
+    def __init__(self, name, x, y, conv, bn, relu, residual=None, x_nchw=False):
+        self.name, self.x, self.y, self.relu, self.residual, self.x_nchw = name, x, y, relu, residual, x_nchw
+        w = conv.weight.detach().float()
+        cout, cin, R, S = w.shape
+        if conv.groups != 1 or conv.dilation != (1, 1) or R != S or conv.stride[0] != conv.stride[1] \
+                or conv.padding[0] != conv.padding[1]:
+            raise NotImplementedError("unsupported convolution %s" % (conv,))
+        self.cin, self.cout, self.R, self.stride, self.pad = cin, cout, R, conv.stride[0], conv.padding[0]
+        if bn is not None:
+            scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+            shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+        else:
+            scale = torch.ones(cout, device=w.device)
+            shift = conv.bias.detach().float() if conv.bias is not None else torch.zeros(cout, device=w.device)
+        ws = w * scale.view(-1, 1, 1, 1)
+        # fprop B[(r,s,ci), co]; dgrad B[(r,s,co), ci]; columns padded to a multiple of 4
+        bf = ws.permute(2, 3, 1, 0).reshape(R * S * cin, cout)
+        bd = ws.permute(2, 3, 0, 1).reshape(R * S * cout, cin)
+        self.b_fwd = _pad_cols(bf)
+        self.b_dgrad = _pad_cols(bd)
+        self.bias = _pad_vec(shift)
+
+    def out_hw(self, h, w):
+        return ((h + 2 * self.pad - self.R) // self.stride + 1, (w + 2 * self.pad - self.R) // self.stride + 1)
+
+
+class _Pool:
+    kind = "pool"
+
+    def __init__(self, name, x, y, mp):
+        self.name, self.x, self.y = name, x, y
+        k = mp.kernel_size if isinstance(mp.kernel_size, int) else mp.kernel_size[0]
+        s = mp.stride if isinstance(mp.stride, int) else mp.stride[0]
+        p = mp.padding if isinstance(mp.padding, int) else mp.padding[0]
+        self.k, self.stride, self.pad, self.ceil = k, s, p, bool(mp.ceil_mode)
+
+    def out_hw(self, h, w):
+        def one(n):
+            if self.ceil:
+                o = -(-(n + 2 * self.pad - self.k) // self.stride) + 1
+                if (o - 1) * self.stride >= n + self.pad:   # last window must start inside the input (torch rule)
+                    o -= 1
+                return o
+            return (n + 2 * self.pad - self.k) // self.stride + 1
+        return one(h), one(w)
+
+
+class _Concat:
+    kind = "concat"
+
+    def __init__(self, name, xs, y):
+        self.name, self.xs, self.y = name, xs, y
+
+
+def _pad_cols(m):
+    k, n = m.shape
+    n4 = (n + 3) // 4 * 4
+    if n4 != n:
+        m = torch.cat([m, m.new_zeros(k, n4 - n)], 1)
+    return m.contiguous()
+
+
+def _pad_vec(v):
+    n = v.numel()
+    n4 = (n + 3) // 4 * 4
+    if n4 != n:
+        v = torch.cat([v, v.new_zeros(n4 - n)])
+    return v.contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# graph builders
+# --------------------------------------------------------------------------------------------------
+def _build_resnet(model, targets):
+    ops, hooks, chans, relu_typed = [], {}, {"img": 3}, set()
+    ops.append(_Conv("conv1", "img", "stem", model.conv1, model.bn1, True, x_nchw=True))
+    chans["stem"] = model.conv1.out_channels
+    relu_typed.add("stem")
+    ops.append(_Pool("maxpool", "stem", "pool", model.maxpool))
+    chans["pool"] = chans["stem"]
+    cur = "pool"
+    remaining = set(id(t) for t in targets)
+    for li in range(1, 5):
+        layer = getattr(model, "layer%d" % li)
+        for bi, blk in enumerate(layer):
+            if not isinstance(blk, torchvision.models.resnet.Bottleneck):
+                raise NotImplementedError("native engine implements Bottleneck ResNets (resnet50/101/152)")
+            pre = "l%d.%d." % (li, bi)
+            sc = cur
+            if blk.downsample is not None:
+                ops.append(_Conv(pre + "ds", cur, pre + "sc", blk.downsample[0], blk.downsample[1], False))
+                chans[pre + "sc"] = blk.downsample[0].out_channels
+                sc = pre + "sc"
+            ops.append(_Conv(pre + "conv1", cur, pre + "c1", blk.conv1, blk.bn1, True))
+            ops.append(_Conv(pre + "conv2", pre + "c1", pre + "c2", blk.conv2, blk.bn2, True))
+            ops.append(_Conv(pre + "conv3", pre + "c2", pre + "out", blk.conv3, blk.bn3, True, residual=sc))
+            chans[pre + "c1"], chans[pre + "c2"], chans[pre + "out"] = blk.conv1.out_channels, blk.conv2.out_channels, blk.conv3.out_channels
+            relu_typed.update([pre + "c1", pre + "c2", pre + "out"])
+            cur = pre + "out"
+            if id(blk) in remaining:
+                hooks[id(blk)] = cur
+                remaining.discard(id(blk))
+            if not remaining:
+                return ops, hooks, chans, relu_typed
+    raise ValueError("hooked layer not found in the ResNet graph")
+
+
+def _build_sequential(features, targets):
+    """VGG / AlexNet / SqueezeNet `features` (nn.Sequential of Conv2d, ReLU, MaxPool2d, Fire)."""
+    Fire = torchvision.models.squeezenet.Fire
+    ops, hooks, chans, relu_typed = [], {}, {"img": 3}, set()
+    remaining = set(id(t) for t in targets)
+    cur, i, first = "img", 0, True
+    mods = list(features)
+
+    def conv_relu(name, x, conv, relu_mod):
+        nonlocal first
+        y = name
+        ops.append(_Conv(name, x, y, conv, None, relu_mod is not None, x_nchw=first))
+        first = False
+        chans[y] = conv.out_channels
+        if relu_mod is not None:
+            relu_typed.add(y)
+        return y
+
+    while i < len(mods) and remaining:
+        m = mods[i]
+        if isinstance(m, nn.Conv2d):
+            relu_mod = mods[i + 1] if i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU) else None
+            if id(m) in remaining and relu_mod is not None:
+                raise NotImplementedError("hook on a pre-ReLU convolution output is not a reference hook point")
+            cur = conv_relu("f%d" % i, cur, m, relu_mod)
+            if relu_mod is not None:
+                if id(relu_mod) in remaining:
+                    hooks[id(relu_mod)] = cur
+                    remaining.discard(id(relu_mod))
+                i += 1
+            elif id(m) in remaining:
+                hooks[id(m)] = cur
+                remaining.discard(id(m))
+        elif isinstance(m, nn.MaxPool2d):
+            y = "f%d" % i
+            ops.append(_Pool(y, cur, y, m))
+            chans[y] = chans[cur]
+            cur = y
+        elif isinstance(m, Fire):
+            pre = "f%d." % i
+            sq = conv_relu(pre + "squeeze", cur, m.squeeze, m.squeeze_activation)
+            e3 = pre + "e3"
+            if id(m.expand3x3_activation) in remaining and len(remaining) == 1:
+                # scalar-depth hook (image_attacks.py:271): only the 3x3 branch of the last Fire is needed
+                ops.append(_Conv(e3, sq, e3, m.expand3x3, None, True))
+                chans[e3] = m.expand3x3.out_channels
+                relu_typed.add(e3)
+                hooks[id(m.expand3x3_activation)] = e3
+                remaining.discard(id(m.expand3x3_activation))
+                break
+            e1 = conv_relu(pre + "e1", sq, m.expand1x1, m.expand1x1_activation)
+            ops.append(_Conv(e3, sq, e3, m.expand3x3, None, True))
+            chans[e3] = m.expand3x3.out_channels
+            relu_typed.add(e3)
+            y = pre + "cat"
+            ops.append(_Concat(y, [e1, e3], y))
+            chans[y] = chans[e1] + chans[e3]
+            relu_typed.add(y)
+            cur = y
+            for key in (id(m), id(m.expand3x3_activation)):
+                if key in remaining:
+                    hooks[key] = y if key == id(m) else e3
+                    remaining.discard(key)
+        elif isinstance(m, (nn.ReLU, nn.Dropout)):
+            pass
+        else:
+            raise NotImplementedError("native engine: unsupported module %s" % type(m).__name__)
+        i += 1
+    if remaining:
+        raise ValueError("hooked layer not found in the feature stack")
+    return ops, hooks, chans, relu_typed
+
+
+class NativeEngine:
+    relu_masked_grads = True    # K1 applies 1[feature > 0]: gradients are kept pre-activation
+    preferred_chunk = 32        # frames per forward/backward: ~4 GB of NHWC activations + gradients for ResNet-50 layer2
+
+    def __init__(self, model, model_name, depth, tf32x3=True, use_tensor_cores=None):
+        self.model = backbones.freeze_for_attack(model)
+        self.model_name, self.depth, self.tf32x3 = model_name, depth, tf32x3
+        self.targets = backbones.find_target_layers(model, model_name, depth)
+        fam = backbones.family_of(model_name)
+        if fam == "resnet":
+            self.ops, hooks, self.chans, self.relu_typed = _build_resnet(model, self.targets)
+        elif fam in ("vgg", "alexnet", "squeezenet"):
+            self.ops, hooks, self.chans, self.relu_typed = _build_sequential(model.features, self.targets)
+        else:
+            raise NotImplementedError("the native engine does not implement the %s family (pre-activation BN, average "
+                                      "pooling); use engine='cudnn'" % fam)
+        # hook buffers in reference order = forward execution order of the target modules
+        self.hook_bufs = [hooks[id(t)] for t in self.targets]
+        order = {op.y: i for i, op in enumerate(self.ops)}
+        self.hook_bufs.sort(key=lambda b: order[b])
+        for b in self.hook_bufs:
+            if b not in self.relu_typed:
+                raise NotImplementedError("hooked buffer %s is not a ReLU output" % b)
+        if use_tensor_cores is None:
+            use_tensor_cores = os.environ.get("I2V_NATIVE_TC", "1") != "0"
+        self.use_tc = use_tensor_cores and hasattr(capi, "conv_tc_supported")
+        self._cache = {}
+
+    @property
+    def num_layers(self):
+        return len(self.hook_bufs)
+
+    # ---- per-(n,h,w) buffer plan -------------------------------------------------------------------
+    def _plan(self, n, h, w, device):
+        key = (n, h, w)
+        plan = self._cache.get(key)
+        if plan is not None:
+            return plan
+        dims = {"img": (h, w)}
+        acts, grads, argmax, descs = {}, {}, {}, {}
+        for op in self.ops:
+            if op.kind == "conv":
+                ih, iw = dims[op.x]
+                oh, ow = op.out_hw(ih, iw)
+                dims[op.y] = (oh, ow)
+                d = capi.ConvDesc(n, ih, iw, op.cin, op.cout, op.R, op.R, op.stride, op.pad, oh, ow)
+                descs[op.name] = d
+            elif op.kind == "pool":
+                ih, iw = dims[op.x]
+                dims[op.y] = op.out_hw(ih, iw)
+            else:
+                dims[op.y] = dims[op.xs[0]]
+            oh, ow = dims[op.y]
+            acts[op.y] = torch.empty(n, oh, ow, self.chans[op.y], device=device, dtype=torch.float32)
+            if op.kind == "pool":
+                argmax[op.y] = torch.empty(n, oh, ow, self.chans[op.y], device=device, dtype=torch.uint8)
+        for name, t in acts.items():
+            if name not in self.hook_bufs:
+                grads[name] = torch.empty_like(t)
+        plan = dict(dims=dims, acts=acts, grads=grads, argmax=argmax, descs=descs,
+                    gimg=torch.empty(n, 3, h, w, device=device, dtype=torch.float32))
+        if len(self._cache) > 4:
+            self._cache.clear()
+        self._cache[key] = plan
+        return plan
+
+    # ---- forward -------------------------------------------------------------------------------------
+    def _conv_fwd(self, op, d, x, y, residual):
+        capi.conv_fwd_simt(d, x, op.b_fwd, op.bias, residual, y, relu=op.relu, x_nchw=op.x_nchw)
+
+    def _conv_dgrad(self, op, d, dy, addend, mask_src, dx):
+        capi.conv_dgrad_simt(d, dy, op.b_dgrad, addend, mask_src, dx, x_nchw=op.x_nchw)
+
+    def features(self, img, need_grad):
+        n, c, h, w = img.shape
+        if c != 3 or not img.is_contiguous():
+            raise ValueError("expected a contiguous [n,3,H,W] image batch")
+        plan = self._plan(n, h, w, img.device)
+        acts = plan["acts"]
+        for op in self.ops:
+            if op.kind == "conv":
+                x = img if op.x == "img" else acts[op.x]
+                self._conv_fwd(op, plan["descs"][op.name], x, acts[op.y], acts[op.residual] if op.residual else None)
+            elif op.kind == "pool":
+                capi.maxpool_fwd(acts[op.x], acts[op.y], plan["argmax"][op.y], op.k, op.stride, op.pad)
+            else:
+                off = 0
+                for xn in op.xs:
+                    capi.copy_channels(acts[xn], acts[op.y], 0, off, self.chans[xn])
+                    off += self.chans[xn]
+        self._last = plan if need_grad else None
+        feats = [acts[b] for b in self.hook_bufs]
+        # clean features are kept by the caller across the whole attack: hand out copies, the plan's buffers are reused
+        return [f.clone() for f in feats] if not need_grad else feats
+
+    # ---- backward ------------------------------------------------------------------------------------
+    def input_grad(self, grads):
+        plan = self._last
+        if plan is None:
+            raise RuntimeError("input_grad() needs a preceding features(..., need_grad=True)")
+        acts = plan["acts"]
+        G = dict(plan["grads"])
+        ready = set()
+        for b, g in zip(self.hook_bufs, grads):
+            G[b] = g.view_as(acts[b])
+            ready.add(b)
+        pending = {}          # buffer -> gradient tensor of an identity (residual) contribution not yet merged
+        last = self.hook_bufs[-1]
+        started = False
+        for op in reversed(self.ops):
+            if not started:
+                if op.y != last:
+                    continue
+                started = True
+            if op.y not in ready:
+                if op.y in pending:      # only an identity contribution reached this buffer
+                    raise RuntimeError("internal: unmerged residual gradient for %s" % op.y)
+                continue                 # dead branch (not upstream of any hook)
+            gy = G[op.y]
+            if op.kind == "conv":
+                if op.residual is not None:
+                    r = op.residual
+                    if r in self.relu_typed:
+                        pending[r] = gy                   # merged (and masked by 1[r>0]) by the dgrad that writes G[r]
+                    else:
+                        G[r] = gy                         # pre-activation shortcut (downsample output): same gradient
+                        ready.add(r)
+                if op.x == "img":
+                    dx, mask = plan["gimg"], None
+                else:
+                    dx, mask = G[op.x], (acts[op.x] if op.x in self.relu_typed else None)
+                addend = None
+                if op.x in ready:
+                    addend = dx
+                    if op.x in pending:
+                        raise RuntimeError("internal: two addends for %s" % op.x)
+                elif op.x in pending:
+                    addend = pending.pop(op.x)
+                self._conv_dgrad(op, plan["descs"][op.name], gy, addend, mask, dx)
+                ready.add(op.x)
+            elif op.kind == "pool":
+                mask = acts[op.x] if op.x in self.relu_typed else None
+                if op.x in ready or op.x in pending:
+                    raise NotImplementedError("pooling input with several consumers")
+                capi.maxpool_bwd(gy, plan["argmax"][op.y], mask, G[op.x], op.k, op.stride, op.pad)
+                ready.add(op.x)
+            else:
+                off = 0
+                for xn in op.xs:
+                    if xn in ready:
+                        capi.copy_channels(gy, G[xn], off, 0, self.chans[xn], accumulate=True)
+                    else:
+                        capi.copy_channels(gy, G[xn], off, 0, self.chans[xn])
+                        ready.add(xn)
+                    off += self.chans[xn]
+        self._last = None
+        return plan["gimg"]

@@ -147,6 +147,52 @@ int i2v_layer_sums_f32(const float* cos, const float* coeffs, float* prev, float
                        const int* step_idx, int L, int64_t N, int mode, int coef_CE,
                        i2v_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * K4 / K5 — truncated image-backbone forward and data-gradient (NHWC f32 activations)
+ * ------------------------------------------------------------------------------------------- */
+
+typedef struct i2v_conv_desc {
+    int32_t N, H, W, Cin;          /* conv input  x [N,H,W,Cin]                                     */
+    int32_t Cout, R, S;            /* filter [Cout,R,S,Cin]                                          */
+    int32_t stride, pad;           /* square stride / zero padding                                   */
+    int32_t P, Q;                  /* conv output y [N,P,Q,Cout]                                     */
+} i2v_conv_desc;
+
+#define I2V_EPI_RELU        1   /* y = max(y, 0) after bias and residual                            */
+#define I2V_LAYOUT_X_NCHW  16   /* the conv INPUT-side tensor (x for fwd, dx for dgrad) is [N,C,H,W]:
+                                   lets the stem read the [N,3,H,W] image and its data-gradient write
+                                   dcost/dimage in the layout the update kernels use                 */
+
+/* CUDA-core (exact FP32 FFMA) gather-GEMM convolution — every shape, the validation reference of the
+ * tensor-core path and the odd-shape path (7x7/s2 Cin=3 stem, AlexNet 11x11/s4, strided dgrad).
+ *   fwd  : y  = relu?( conv(x, w)*bn_scale + bias [+ residual] )
+ *          bmat = [(r,s,ci), co] = w[co,ci,r,s]*bn_scale[co]  (leading dimension = Cout rounded up to 4)
+ *          eval-mode BatchNorm folded into bmat/bias: torchvision `bn(conv(x))` with BN in eval,
+ *          image_attacks.py:253-256; forward of image_attacks.py:334.
+ *   dgrad: dx = ( conv_transpose(dy, w*bn_scale) [+ addend] ) * 1[mask_src > 0]
+ *          bmat = [(r,s,co), ci] = w[co,ci,r,s]*bn_scale[co]  (leading dimension = Cin rounded up to 4)
+ *          mask_src = the forward activation this gradient flows into (ReLU backward), or NULL.
+ *          The data gradient only: the reference's cost.backward() (image_attacks.py:352) also computes
+ *          weight gradients that nothing reads.                                       */
+int i2v_conv_fwd_simt_f32(const i2v_conv_desc* d, const float* x, const float* bmat, const float* bias,
+                          const float* residual, float* y, int flags, i2v_stream_t stream);
+int i2v_conv_dgrad_simt_f32(const i2v_conv_desc* d, const float* dy, const float* bmat, const float* addend,
+                            const float* mask_src, float* dx, int flags, i2v_stream_t stream);
+
+/* k x k max pooling (stride, -inf padding), NHWC, C % 4 == 0.  argmax[N,P,Q,C] = r*k+s of the FIRST
+ * maximum in window scan order (torch.nn.MaxPool2d); backward is the gather form (no atomics) and can
+ * apply the ReLU-backward mask of the pooled tensor's producer.  torchvision resnet.maxpool (3,2,1),
+ * vgg (2,2,0), alexnet / squeezenet (3,2,0; ceil_mode via P,Q).                                      */
+int i2v_maxpool_fwd_f32(const float* x, float* y, uint8_t* argmax, int N, int H, int W, int C, int P, int Q,
+                        int k, int stride, int pad, i2v_stream_t stream);
+int i2v_maxpool_bwd_f32(const float* dy, const uint8_t* argmax, const float* mask_src, float* dx, int N, int H,
+                        int W, int C, int P, int Q, int k, int stride, int pad, i2v_stream_t stream);
+
+/* dst[m, dst_off : dst_off+Ccopy] (=|+=) src[m, src_off : src_off+Ccopy] — channel concat of SqueezeNet's
+ * Fire modules (torch.cat([expand1x1, expand3x3], 1)) and its backward split.                        */
+int i2v_copy_channels_f32(const float* src, float* dst, int64_t M, int Csrc, int src_off, int Cdst, int dst_off,
+                          int Ccopy, int accumulate, i2v_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -147,6 +147,34 @@ def image_guided_loop(hooked, videos, epsilon, steps, step_size, adaptive=False,
     return adv, cost_log, (np.stack(weights) if adaptive and steps else None), coeffs
 
 
+def teacher_forced_grad(hooked, frames, true_image, dtype=torch.float32, weights=None):
+    """dcost/dtrue_image of ONE step for a GIVEN true_image (image_attacks.py:334-352), in `dtype`.
+
+    float64 is the accuracy arbiter of SURVEY.md 8(c): both float32 implementations (torch on the CPU —
+    the reference's arithmetic — and the CUDA path) are scored by their distance to it, because at
+    step 1 the gradient is a cancellation-level quantity and the reference does not reproduce itself
+    across reduction orders (D8).  `hooked` models are converted to `dtype` in place.
+    Returns (cost, grad [N,3,H,W] as float64 ndarray, cos [L,N])."""
+    frames = torch.as_tensor(frames).to(dtype)
+    ti = torch.as_tensor(np.ascontiguousarray(true_image)).to(dtype).requires_grad_(True)
+    N = frames.shape[0]
+    rows = []
+    for hm in hooked:
+        hm.model.to(dtype)
+        with torch.no_grad():
+            init = [a.detach().clone() for a in hm.run(frames)]
+        acts = hm.run(ti)
+        for a, a0 in zip(acts, init):
+            rows.append(F.cosine_similarity(a.view(N, -1), a0.view(N, -1)))
+    stacked = torch.stack(rows)
+    if weights is None:
+        cost = torch.sum(stacked)
+    else:
+        cost = torch.mean(torch.sum(torch.as_tensor(weights).to(dtype).unsqueeze(1) * stacked, dim=1))
+    (g,) = torch.autograd.grad(cost, ti)
+    return float(cost.detach()), g.double().numpy(), stacked.detach().double().numpy()
+
+
 # --------------------------------------------------------------------------------------------------
 # base_attacks.py:242-340
 # --------------------------------------------------------------------------------------------------

@@ -1,0 +1,165 @@
+"""GPU parity of the backbone kernels (K4/K5): convolution forward / data-gradient, max pooling, and the
+native engine's truncated forward + input gradient, against PyTorch float64 on the CPU (the arbiter)
+and float32 (the reference's arithmetic).  Tolerance: max |err| <= 2e-5 * max |ref| for a single layer in
+FP32 mode (observed ~1e-6); the float32 torch result must not be meaningfully closer than ours."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from i2v_b200 import backbones, capi, engines
+from i2v_b200.engine_native import NativeEngine, _pad_cols, _pad_vec
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+#        N  H   W   Cin Cout k s p  x_nchw
+SHAPES = [
+    (2, 56, 56, 64, 64, 1, 1, 0, False),     # layer1.0.conv1
+    (2, 56, 56, 64, 64, 3, 1, 1, False),     # layer1.x.conv2
+    (2, 56, 56, 256, 128, 1, 1, 0, False),   # layer2.0.conv1
+    (2, 56, 56, 128, 128, 3, 2, 1, False),   # layer2.0.conv2 (strided 3x3)
+    (2, 56, 56, 256, 512, 1, 2, 0, False),   # layer2.0.downsample (strided 1x1)
+    (3, 28, 28, 128, 512, 1, 1, 0, False),   # layer2.x.conv3
+    (1, 64, 64, 3, 64, 7, 2, 3, True),       # ResNet stem, reads / writes the [N,3,H,W] image
+    (1, 64, 64, 3, 64, 11, 4, 2, True),      # AlexNet conv1
+    (2, 15, 15, 64, 192, 5, 1, 2, False),    # AlexNet conv2
+    (2, 27, 27, 64, 16, 1, 1, 0, False),     # SqueezeNet squeeze (16 channels)
+    (1, 13, 13, 48, 192, 3, 1, 1, False),    # SqueezeNet expand3x3, odd spatial size
+    (1, 7, 9, 8, 12, 3, 1, 1, False),        # tiny ragged
+]
+
+
+def _ref_conv(x, w, scale, shift, stride, pad, residual, relu, dtype):
+    y = F.conv2d(x.to(dtype), (w * scale.view(-1, 1, 1, 1)).to(dtype), None, stride, pad) + shift.to(dtype).view(1, -1, 1, 1)
+    if residual is not None:
+        y = y + residual.to(dtype)
+    return torch.relu(y) if relu else y
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_conv_fwd_and_dgrad_simt(shape):
+    N, H, W, Cin, Cout, k, s, p, x_nchw = shape
+    g = torch.Generator().manual_seed(hash(shape) % 1000)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    scale = torch.rand(Cout, generator=g) + 0.5
+    shift = torch.randn(Cout, generator=g) * 0.1
+    P, Q = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    res = torch.randn(N, Cout, P, Q, generator=g)
+    ws = w * scale.view(-1, 1, 1, 1)
+    d = capi.ConvDesc(N, H, W, Cin, Cout, k, k, s, p, P, Q)
+    bf = _pad_cols(ws.permute(2, 3, 1, 0).reshape(k * k * Cin, Cout)).to(DEV)
+    bd = _pad_cols(ws.permute(2, 3, 0, 1).reshape(k * k * Cout, Cin)).to(DEV)
+    bias = _pad_vec(shift).to(DEV)
+    xd = (x if x_nchw else x.permute(0, 2, 3, 1)).contiguous().to(DEV)
+    resd = res.permute(0, 2, 3, 1).contiguous().to(DEV)
+    for use_res, relu in ((False, False), (True, True)):
+        y = torch.empty(N, P, Q, Cout, device=DEV)
+        capi.conv_fwd_simt(d, xd, bf, bias, resd if use_res else None, y, relu=relu, x_nchw=x_nchw)
+        ref64 = _ref_conv(x, w, scale, shift, s, p, res if use_res else None, relu, torch.float64)
+        ref32 = _ref_conv(x, w, scale, shift, s, p, res if use_res else None, relu, torch.float32)
+        got = y.permute(0, 3, 1, 2).cpu().double()
+        err = (got - ref64).abs().max() / ref64.abs().max()
+        err32 = (ref32.double() - ref64).abs().max() / ref64.abs().max()
+        assert err <= 2e-5 and err <= 20 * err32 + 1e-6, (err, err32)
+    # data gradient: dx = conv_transpose(dy, w*scale) [+ addend], masked by a forward activation
+    dy = torch.randn(N, Cout, P, Q, generator=g)
+    addend = torch.randn(N, Cin, H, W, generator=g)
+    act = torch.randn(N, Cin, H, W, generator=g)
+    dyd = dy.permute(0, 2, 3, 1).contiguous().to(DEV)
+    lay = (lambda t: t.contiguous().to(DEV)) if x_nchw else (lambda t: t.permute(0, 2, 3, 1).contiguous().to(DEV))
+    for use_add, use_mask in ((False, False), (True, True)):
+        dx = torch.empty_like(xd)
+        capi.conv_dgrad_simt(d, dyd, bd, lay(addend) if use_add else None, lay(act) if use_mask else None, dx, x_nchw=x_nchw)
+        ref64 = torch.nn.grad.conv2d_input((N, Cin, H, W), ws.double(), dy.double(), s, p)
+        if use_add:
+            ref64 = ref64 + addend.double()
+        if use_mask:
+            ref64 = ref64 * (act > 0).double()
+        got = (dx if x_nchw else dx.permute(0, 3, 1, 2)).cpu().double()
+        err = (got - ref64).abs().max() / ref64.abs().max()
+        assert err <= 2e-5, err
+
+
+@pytest.mark.parametrize("H,W,k,s,p,ceil", [(112, 112, 3, 2, 1, False), (55, 55, 3, 2, 0, False), (27, 31, 3, 2, 0, True),
+                                            (56, 56, 2, 2, 0, False), (13, 13, 3, 2, 0, True)])
+def test_maxpool_fwd_bwd(H, W, k, s, p, ceil):
+    g = torch.Generator().manual_seed(3)
+    N, C = 2, 16
+    x = torch.relu(torch.randn(N, C, H, W, generator=g))          # post-ReLU input: zeros tie, first wins
+    mp = torch.nn.MaxPool2d(k, s, p, ceil_mode=ceil, return_indices=True)
+    xr = x.clone().requires_grad_(True)
+    yr, idx = mp(xr)
+    P, Q = yr.shape[2:]
+    dy = torch.randn(N, C, P, Q, generator=g)
+    yr.backward(dy)
+    xd = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    y = torch.empty(N, P, Q, C, device=DEV)
+    am = torch.empty(N, P, Q, C, device=DEV, dtype=torch.uint8)
+    capi.maxpool_fwd(xd, y, am, k, s, p)
+    assert torch.equal(y.permute(0, 3, 1, 2).cpu(), yr.detach())
+    dx = torch.empty_like(xd)
+    capi.maxpool_bwd(dy.permute(0, 2, 3, 1).contiguous().to(DEV), am, None, dx, k, s, p)
+    ref = xr.grad
+    got = dx.permute(0, 3, 1, 2).cpu()
+    # ties between equal zeros may be broken differently; the gradient through them is killed by the ReLU mask
+    nz = x > 0
+    assert torch.allclose(got[nz], ref[nz], rtol=1e-6, atol=1e-7)
+    capi.maxpool_bwd(dy.permute(0, 2, 3, 1).contiguous().to(DEV), am, xd, dx, k, s, p)
+    got = dx.permute(0, 3, 1, 2).cpu()
+    assert torch.allclose(got, ref * nz, rtol=1e-6, atol=1e-7)
+
+
+def test_copy_channels():
+    a = torch.randn(5, 7, 3, 16, device=DEV)
+    b = torch.randn(5, 7, 3, 24, device=DEV)
+    cat = torch.empty(5, 7, 3, 40, device=DEV)
+    capi.copy_channels(a, cat, 0, 0, 16)
+    capi.copy_channels(b, cat, 0, 16, 24)
+    assert torch.equal(cat, torch.cat([a, b], -1))
+    back = torch.ones(5, 7, 3, 24, device=DEV)
+    capi.copy_channels(cat, back, 16, 0, 24, accumulate=True)
+    assert torch.equal(back, b + 1)
+
+
+ENGINE_CASES = [("resnet", 2, 64), ("resnet", [1, 2], 64), ("resnet", 3, 64), ("vgg", 3, 32), ("vgg", [2, 3], 32),
+                ("alexnet", 3, 64), ("alexnet", [2, 3], 64), ("squeezenet", 2, 64), ("squeezenet", [2, 3], 64),
+                ("squeezenet", 4, 64)]
+
+
+@pytest.mark.parametrize("name,depth,side", ENGINE_CASES)
+@pytest.mark.parametrize("mode", ["simt", "tc"])
+def test_native_engine_matches_autograd(name, depth, side, mode):
+    """Truncated forward features and dcost/dimage of the native engine vs torch autograd in float64 on the
+    CPU, for every family and both hook styles (scalar depth / list of depths)."""
+    if mode == "tc" and not hasattr(capi, "conv_tc_supported"):
+        pytest.skip("tensor-core path not built yet")
+    g = torch.Generator().manual_seed(7)
+    img = torch.randn(3, 3, side, side, generator=g)
+    model = backbones.get_model(name)
+    eng = NativeEngine(model, name, depth, tf32x3=True, use_tensor_cores=(mode == "tc"))
+    feats = eng.features(img.to(DEV), need_grad=True)
+    # float64 reference on the CPU through the reference's own hook mechanism
+    ref_model = backbones.seeded_random_init(backbones.arch_of(name), 0).double()
+    backbones.freeze_for_attack(ref_model)
+    acts = []
+    hs = [t.register_forward_hook(lambda m, i, o: acts.append(o)) for t in backbones.find_target_layers(ref_model, name, depth)]
+    xi = img.double().requires_grad_(True)
+    ref_model(xi)
+    for h in hs:
+        h.remove()
+    assert len(acts) == len(feats)
+    ups = []
+    for a, f in zip(acts, feats):
+        got = f.permute(0, 3, 1, 2).cpu().double()
+        assert got.shape == a.shape
+        err = (got - a.detach()).abs().max() / a.detach().abs().max()
+        assert err <= 5e-5, ("feature", err)
+        up = torch.randn(a.shape, generator=g, dtype=torch.float64) * (a.detach() > 0)     # pre-activation gradient
+        ups.append(up)
+    (gref,) = torch.autograd.grad(acts, xi, ups)
+    grads = [u.permute(0, 2, 3, 1).contiguous().float().to(DEV) for u in ups]
+    gimg = eng.input_grad(grads).cpu().double()
+    err = (gimg - gref).abs().max() / gref.abs().max()
+    assert err <= 2e-4, ("input gradient", err)

@@ -192,7 +192,10 @@ def test_cosine_loss_grad_vs_float64(N, D, near):
     assert np.abs(cos - cos64).max() <= 1.2e-7                               # what we actually get
     scale = np.abs(grad64).max(axis=1, keepdims=True)
     err = (np.abs(grad - grad64) / scale).max()
-    assert err <= 1e-6, err                                                  # correctly rounded => ~6e-8
+    # far from cancellation the gradient is correctly rounded (~1e-7).  In the step-1 regime |g| is ~1e-4 of
+    # its two terms, so the ~1e-9..1e-7 relative error of the float32-partial frame sums is amplified 1e4x;
+    # torch-f32 autograd (checked below) is another 10-1000x further from float64 there.
+    assert err <= (1e-3 if near else 1e-6), err
     # torch-f32 autograd (the reference's arithmetic) is no closer to float64 than we are
     _, g32 = _torch_cos(a, b, torch.float32)
     err32 = (np.abs(g32 - grad64) / scale).max()
@@ -229,7 +232,9 @@ def test_cosine_zero_features_and_empty():
     cos64, grad64 = O.cosine_loss_grad_f64(a, b)
     assert np.isfinite(cos).all() and np.isfinite(grad).all()
     assert cos[1] == 0 and cos[2] == 0
-    assert np.allclose(grad, grad64, rtol=1e-6, atol=1e-30)
+    scale = np.abs(grad64).max(axis=1, keepdims=True) + 1e-300
+    assert (np.abs(grad - grad64) / scale).max() <= 1e-6
+    assert (grad[2] == 0).all()                                 # b = 0: alpha*b - beta*a with cos = 0
     ct, gt = _torch_cos(a, b, torch.float64)
     assert np.allclose(grad64, gt, rtol=1e-9, atol=1e-30)       # the oracle follows torch's clamping
     e = torch.empty(0, 16, device=DEV)
