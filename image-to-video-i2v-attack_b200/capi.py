@@ -39,8 +39,10 @@ SIGNATURES = {
     "i2v_layer_sums_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_i64, _c_int, _c_int, _c_p], _c_int),
     "i2v_conv_fwd_simt_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_dgrad_simt_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
+    "i2v_conv_tc_supported": ([_c_p, _c_int], _c_int),
+    "i2v_conv_tc_f32": ([_c_p, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_maxpool_fwd_f32": ([_c_p, _c_p, _c_p] + [_c_int] * 9 + [_c_p], _c_int),
-    "i2v_maxpool_bwd_f32": ([_c_p, _c_p, _c_p, _c_p] + [_c_int] * 9 + [_c_p], _c_int),
+    "i2v_maxpool_bwd_f32": ([_c_p, _c_p, _c_p, _c_p] + [_c_int] * 10 + [_c_p], _c_int),
     "i2v_copy_channels_f32": ([_c_p, _c_p, _c_i64] + [_c_int] * 6 + [_c_p], _c_int),
 }
 
@@ -82,7 +84,7 @@ def load():
 # benchmark can time each kernel on the launching stream with CUDA events.
 LAUNCHES = {}
 PROFILE_EVENTS = None
-_NO_KERNEL = ("i2v_device_check", "i2v_adam_step_table")
+_NO_KERNEL = ("i2v_device_check", "i2v_adam_step_table", "i2v_conv_tc_supported")
 
 
 class _Timed:
@@ -256,6 +258,17 @@ def conv_dgrad_simt(desc, dy, bmat, addend, mask_src, dx, x_nchw=False):
                                           _dev(dx), flags, _stream()), "i2v_conv_dgrad_simt_f32")
 
 
+def conv_tc_supported(desc, dgrad):
+    return bool(load().i2v_conv_tc_supported(ctypes.addressof(desc), int(dgrad)))
+
+
+def conv_tc(desc, dgrad, src, w_hi, w_lo, bias, residual, mask_src, dst, relu=False):
+    """Tensor-core implicit GEMM (tcgen05/TMEM/TMA).  w_lo=None -> plain TF32, else 3xTF32 FP32-parity mode."""
+    _check(load().i2v_conv_tc_f32(ctypes.addressof(desc), int(dgrad), _dev(src), _dev(w_hi), _dev(w_lo), _dev(bias),
+                                  _dev(residual), _dev(mask_src), _dev(dst), EPI_RELU if relu else 0, _stream()),
+           "i2v_conv_tc_f32")
+
+
 def maxpool_fwd(x, y, argmax, k, stride, pad):
     N, H, W, C = x.shape
     _, P, Q, _ = y.shape
@@ -263,11 +276,11 @@ def maxpool_fwd(x, y, argmax, k, stride, pad):
                                       _stream()), "i2v_maxpool_fwd_f32")
 
 
-def maxpool_bwd(dy, argmax, mask_src, dx, k, stride, pad):
+def maxpool_bwd(dy, argmax, mask_src, dx, k, stride, pad, accumulate=False):
     N, H, W, C = dx.shape
     _, P, Q, _ = dy.shape
     _check(load().i2v_maxpool_bwd_f32(_dev(dy), _dev(argmax, torch.uint8), _dev(mask_src), _dev(dx), N, H, W, C, P, Q,
-                                      k, stride, pad, _stream()), "i2v_maxpool_bwd_f32")
+                                      k, stride, pad, int(accumulate), _stream()), "i2v_maxpool_bwd_f32")
 
 
 def copy_channels(src, dst, src_off, dst_off, ccopy, accumulate=False):

@@ -247,7 +247,7 @@ maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* 
 // multiplied by the ReLU-backward mask of the pooled tensor's producer (mask_src = that forward activation).
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ argmax, const float* __restrict__ mask_src,
-                   float* __restrict__ dx, int N, int H, int W, int C, int P, int Q, int k, int stride, int pad) {
+                   float* __restrict__ dx, int N, int H, int W, int C, int P, int Q, int k, int stride, int pad, int accumulate) {
     const int C4 = C >> 2;
     const int64_t total = (int64_t)N * H * W * C4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -279,6 +279,10 @@ maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ arg
         if (mask_src) {
             const float4 mk = __ldg(reinterpret_cast<const float4*>(mask_src) + i);
             if (!(mk.x > 0.f)) g[0] = 0.f; if (!(mk.y > 0.f)) g[1] = 0.f; if (!(mk.z > 0.f)) g[2] = 0.f; if (!(mk.w > 0.f)) g[3] = 0.f;
+        }
+        if (accumulate) {   // the pooled tensor's input has another consumer (a hooked layer: K1 wrote its gradient first)
+            const float4 o = reinterpret_cast<const float4*>(dx)[i];
+            g[0] += o.x; g[1] += o.y; g[2] += o.z; g[3] += o.w;
         }
         reinterpret_cast<float4*>(dx)[i] = make_float4(g[0], g[1], g[2], g[3]);
     }
@@ -369,12 +373,13 @@ extern "C" int i2v_maxpool_fwd_f32(const float* x, float* y, uint8_t* argmax, in
 }
 
 extern "C" int i2v_maxpool_bwd_f32(const float* dy, const uint8_t* argmax, const float* mask_src, float* dx, int N, int H,
-                                   int W, int C, int P, int Q, int k, int stride, int pad, i2v_stream_t stream) {
+                                   int W, int C, int P, int Q, int k, int stride, int pad, int accumulate,
+                                   i2v_stream_t stream) {
     I2V_REQUIRE(dy && argmax && dx, "null pointer");
     I2V_REQUIRE(C % 4 == 0 && k >= 1 && k <= 15 && stride >= 1 && pad >= 0 && pad < k, "unsupported pooling shape");
     if (N == 0) return I2V_OK;
     const int64_t total = (int64_t)N * H * W * (C / 4);
-    maxpool_bwd_kernel<<<grid1d(total), 256, 0, as_stream(stream)>>>(dy, argmax, mask_src, dx, N, H, W, C, P, Q, k, stride, pad);
+    maxpool_bwd_kernel<<<grid1d(total), 256, 0, as_stream(stream)>>>(dy, argmax, mask_src, dx, N, H, W, C, P, Q, k, stride, pad, accumulate);
     I2V_LAUNCH_CHECK("i2v_maxpool_bwd_f32");
     return I2V_OK;
 }

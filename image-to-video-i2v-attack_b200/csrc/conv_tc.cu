@@ -1,0 +1,484 @@
+// K4/K5 (tensor-core path): NHWC convolution forward / stride-1 data-gradient as an implicit GEMM on the
+// 5th-generation tensor cores — tcgen05.mma.kind::tf32 with the accumulator in TMEM, operands staged in
+// shared memory by TMA (tiled 2-D loads for 1x1/s1, im2col-mode loads for everything else), mbarrier
+// producer/consumer pipeline, one output tile of 128 pixels x BN channels per CTA.
+//
+//     D[m, n] = sum_{tap=(r,s)} sum_{c} A[pixel(m) + tap, c] * B[n, (tap, c)]
+//       A : activations [N,H,W,C] f32 (C % 32 == 0); one pipeline stage = one tap x 32 channels
+//           = a 128-row x 128-byte tile, SWIZZLE_128B, written by ONE TMA instruction
+//       B : weights [Cout, R*S*C] f32, K-major, eval-mode BatchNorm scale folded in (host)
+//       D : TMEM, 128 lanes x BN f32 columns
+//
+// FP32-parity mode (X3 = true): the tensor core reads f32 bit patterns as TF32, i.e. it ignores the low
+// 13 mantissa bits.  Each operand is split exactly into hi = trunc_tf32(v) and lo = v - hi, and
+//     a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo          (the dropped a_lo*b_lo term is < 2^-22 |a*b|)
+// is accumulated in FP32 in TMEM: three MMAs per K-slice.  B_hi/B_lo are precomputed once per model;
+// A_hi is the raw tile (hardware truncation), A_lo is produced on the fly by four "split" warps that
+// rewrite each landed A tile into a second shared-memory buffer (element-wise, so the swizzle pattern is
+// preserved).  X3 = false is plain TF32 (one MMA per K-slice), the mode cuDNN uses with allow_tf32.
+//
+// Epilogue (same four warps, after the main loop): TMEM -> registers (tcgen05.ld 32x32b.x32: one
+// pixel-row per thread), + bias, + residual, ReLU, ReLU-backward mask, 128-bit stores to NHWC.
+//
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator,
+// warps 4..7 = A-split during the main loop, then epilogue (warp w owns TMEM lanes 32*(w%4)..+31).
+// Every mbarrier wait has a clock-based watchdog that traps instead of hanging the GPU.
+#include <cuda.h>
+#include <stdlib.h>
+#include <mutex>
+#include <unordered_map>
+#include "common.cuh"
+
+namespace i2v {
+
+constexpr int TC_BM = 128;        // pixels per tile (UMMA M)
+constexpr int TC_BK = 32;         // f32 per stage row = 128 bytes = one swizzle span
+constexpr int TC_THREADS = 256;
+constexpr uint32_t TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
+
+struct TcArgs {
+    const float* bias;       // [Cout] or null
+    const float* residual;   // [M, Cout] or null
+    const float* mask_src;   // [M, Cout] or null
+    float* dst;              // [M, Cout]
+    int64_t M;               // N*P*Q output pixels
+    int Cout;
+    int P, Q;                // output spatial dims
+    int stride, pad, R, S;
+    int cblocks;             // C / 32
+    int relu;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Watchdog: ~4 s at 2 GHz.  A protocol bug traps (CUDA error on the host) instead of hanging the box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 8000000000LL) { printf("i2v conv_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c, int w, int h,
+                                                   int n, uint16_t off_w, uint16_t off_h) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+                 " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+                 : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
+// LBO = 1 (ignored for swizzled K-major), SBO = 1024 B (8 rows x 128 B), version 1 (Blackwell), layout 2.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major, M = 128, N = BN.
+__device__ __forceinline__ constexpr uint32_t umma_idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN, bool X3>
+struct TcSmem {
+    static constexpr uint32_t B_BYTES = BN * TC_BK * 4;
+    static constexpr uint32_t STAGE_BYTES = TC_A_BYTES * (X3 ? 2 : 1) + B_BYTES * (X3 ? 2 : 1);
+};
+
+// ---------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------
+template <int BN, bool X3, bool IM2COL>
+__global__ void __launch_bounds__(TC_THREADS)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+               const __grid_constant__ CUtensorMap tmBlo, const TcArgs args, const int stages) {
+    using L = TcSmem<BN, X3>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment is required by SWIZZLE_128B (TMA destination and UMMA descriptors)
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* tiles = smem;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * L::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + stages;
+    uint64_t* split_bar = empty_bar + stages;
+    uint64_t* accum_bar = split_bar + stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    float* bias_s = reinterpret_cast<float*>(tmem_slot + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m0 = (int64_t)blockIdx.x * TC_BM;
+    const int n0 = blockIdx.y * BN;
+    const int kiters = args.R * args.S * args.cblocks;
+
+    auto stage_a = [&](int s) { return tiles + (size_t)s * L::STAGE_BYTES; };
+    auto stage_alo = [&](int s) { return tiles + (size_t)s * L::STAGE_BYTES + TC_A_BYTES; };
+    auto stage_bhi = [&](int s) { return tiles + (size_t)s * L::STAGE_BYTES + TC_A_BYTES * (X3 ? 2 : 1); };
+    auto stage_blo = [&](int s) { return tiles + (size_t)s * L::STAGE_BYTES + TC_A_BYTES * 2 + L::B_BYTES; };
+
+    // ---- one-time setup ----------------------------------------------------------------------
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA); prefetch_tmap(&tmBhi);
+        if (X3) prefetch_tmap(&tmBlo);
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+            mbar_init(&split_bar[s], 128);
+        }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {   // TMEM: BN f32 columns x 128 lanes for the accumulator
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x >= 128 && threadIdx.x - 128 < BN)
+        bias_s[threadIdx.x - 128] = args.bias ? args.bias[n0 + threadIdx.x - 128] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====================================================================
+        if (lane == 0) {
+            int img = 0, base_h = 0, base_w = 0;
+            if (IM2COL) {
+                const int64_t pq = (int64_t)args.P * args.Q;
+                img = (int)(m0 / pq);
+                const int rem = (int)(m0 - (int64_t)img * pq);
+                const int p = rem / args.Q, q = rem - p * args.Q;
+                base_h = p * args.stride - args.pad;      // coordinate of the filter window's corner (tap 0,0)
+                base_w = q * args.stride - args.pad;
+            }
+            int it = 0;
+            for (int r = 0; r < args.R; ++r)
+                for (int s = 0; s < args.S; ++s)
+                    for (int cb = 0; cb < args.cblocks; ++cb, ++it) {
+                        const int st = it % stages;
+                        const uint32_t ph = (uint32_t)(it / stages) & 1;
+                        mbar_wait(&empty_bar[st], ph ^ 1);
+                        mbar_arrive_expect_tx(&full_bar[st], TC_A_BYTES + L::B_BYTES * (X3 ? 2 : 1));
+                        if (IM2COL) tma_load_im2col_4d(&tmA, &full_bar[st], stage_a(st), cb * TC_BK, base_w, base_h, img, (uint16_t)s, (uint16_t)r);
+                        else        tma_load_2d(&tmA, &full_bar[st], stage_a(st), cb * TC_BK, (int)m0);
+                        const int kcol = ((r * args.S + s) * args.cblocks + cb) * TC_BK;
+                        tma_load_2d(&tmBhi, &full_bar[st], stage_bhi(st), kcol, n0);
+                        if (X3) tma_load_2d(&tmBlo, &full_bar[st], stage_blo(st), kcol, n0);
+                    }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =======================================================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(BN);
+            for (int it = 0; it < kiters; ++it) {
+                const int st = it % stages;
+                const uint32_t ph = (uint32_t)(it / stages) & 1;
+                mbar_wait(&full_bar[st], ph);
+                if (X3) mbar_wait(&split_bar[st], ph);
+                tc_fence_after();
+                const uint64_t da = umma_desc_sw128(smem_u32(stage_a(st)));
+                const uint64_t dbh = umma_desc_sw128(smem_u32(stage_bhi(st)));
+                uint64_t dal = 0, dbl = 0;
+                if (X3) { dal = umma_desc_sw128(smem_u32(stage_alo(st))); dbl = umma_desc_sw128(smem_u32(stage_blo(st))); }
+#pragma unroll
+                for (int kk = 0; kk < TC_BK / 8; ++kk) {              // UMMA K = 8 tf32 = 32 bytes: +2 in the >>4 address field
+                    umma_tf32(tmem_base, da + 2 * kk, dbh + 2 * kk, idesc, (it | kk) ? 1u : 0u);
+                    if (X3) {
+                        umma_tf32(tmem_base, dal + 2 * kk, dbh + 2 * kk, idesc, 1u);
+                        umma_tf32(tmem_base, da + 2 * kk, dbl + 2 * kk, idesc, 1u);
+                    }
+                }
+                umma_commit(&empty_bar[st]);       // frees the stage when these MMAs have read it
+            }
+            umma_commit(accum_bar);                // accumulator complete
+        }
+    } else if (warp >= 4) {
+        const int t = threadIdx.x - 128;           // 0..127
+        if (X3) {
+            // ===== A split: A_lo = a - trunc_tf32(a), element-wise on the swizzled tile ==============
+            for (int it = 0; it < kiters; ++it) {
+                const int st = it % stages;
+                const uint32_t ph = (uint32_t)(it / stages) & 1;
+                mbar_wait(&full_bar[st], ph);
+                const float4* src = reinterpret_cast<const float4*>(stage_a(st));
+                float4* dst = reinterpret_cast<float4*>(stage_alo(st));
+#pragma unroll
+                for (int j = 0; j < (int)(TC_A_BYTES / 16 / 128); ++j) {
+                    float4 v = src[t + 128 * j], o;
+                    o.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                    o.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                    o.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                    o.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                    dst[t + 128 * j] = o;
+                }
+                fence_proxy_async();               // generic-proxy stores -> visible to the tensor core (async proxy)
+                mbar_arrive(&split_bar[st]);
+            }
+        }
+        // ===== epilogue ===========================================================================
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int64_t m = m0 + t;                  // thread t owns TMEM lane t = output pixel m
+        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32(lane_base + (uint32_t)c0, r);   // warp-collective: every lane participates
+            if (m < args.M) {
+                const int64_t off = m * args.Cout + n0 + c0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 v = make_float4(__uint_as_float(r[j]) + bias_s[c0 + j], __uint_as_float(r[j + 1]) + bias_s[c0 + j + 1],
+                                           __uint_as_float(r[j + 2]) + bias_s[c0 + j + 2], __uint_as_float(r[j + 3]) + bias_s[c0 + j + 3]);
+                    if (args.residual) {
+                        const float4 q = __ldg(reinterpret_cast<const float4*>(args.residual + off + j));
+                        v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+                    }
+                    if (args.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    if (args.mask_src) {
+                        const float4 q = __ldg(reinterpret_cast<const float4*>(args.mask_src + off + j));
+                        if (!(q.x > 0.f)) v.x = 0.f; if (!(q.y > 0.f)) v.y = 0.f; if (!(q.z > 0.f)) v.z = 0.f; if (!(q.w > 0.f)) v.w = 0.f;
+                    }
+                    *reinterpret_cast<float4*>(args.dst + off + j) = v;
+                }
+            }
+        }
+    }
+
+    // ---- teardown --------------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(BN) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: tensor maps (driver entry points resolved at run time: no link-time libcuda dependency)
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode_tiled = nullptr;
+static EncodeIm2colFn g_encode_im2col = nullptr;
+
+static int resolve_driver() {
+    if (g_encode_tiled && g_encode_im2col) return I2V_OK;
+    cudaDriverEntryPointQueryResult q;
+    void* f = nullptr;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q);
+    if (e != cudaSuccess || !f) return cuda_fail(e == cudaSuccess ? cudaErrorUnknown : e, "cuTensorMapEncodeTiled entry point");
+    g_encode_tiled = (EncodeTiledFn)f;
+    f = nullptr;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &q);
+    if (e != cudaSuccess || !f) return cuda_fail(e == cudaSuccess ? cudaErrorUnknown : e, "cuTensorMapEncodeIm2col entry point");
+    g_encode_im2col = (EncodeIm2colFn)f;
+    return I2V_OK;
+}
+
+// 2-D row-major [rows, cols] f32, box [box_rows, 32], SWIZZLE_128B
+static int make_map_2d(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * sizeof(float)};
+    cuuint32_t box[2] = {TC_BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu", (int)r, (unsigned long long)rows, (unsigned long long)cols); return I2V_ECUDA; }
+    return I2V_OK;
+}
+
+// im2col-mode map over an NHWC activation tensor: 32 channels x 128 pixels per load
+static int make_map_im2col(CUtensorMap* map, const float* base, int N, int H, int W, int C, int R, int S, int stride, int pad) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    // bounding box of the filter-window corner: lower = -pad, upper = pad - (filter - 1)   (dilation 1),
+    // cutlass/conv/collective/detail.hpp compute_{lower,upper}_corner_whd for fprop
+    int lower[2] = {-pad, -pad};
+    int upper[2] = {pad - (S - 1), pad - (R - 1)};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    CUresult r = g_encode_im2col(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, lower, upper,
+                                 TC_BK, TC_BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeIm2col failed (%d) N=%d H=%d W=%d C=%d R=%d stride=%d pad=%d", (int)r, N, H, W, C, R, stride, pad); return I2V_ECUDA; }
+    return I2V_OK;
+}
+
+// Tensor maps are keyed by (pointer, geometry): the engine reuses its activation buffers every step, so
+// after the first step no descriptor is encoded on the hot path.
+struct MapKey {
+    const void* p; int a, b, c, d, e, f, g, h;
+    bool operator==(const MapKey& o) const { return p == o.p && a == o.a && b == o.b && c == o.c && d == o.d && e == o.e && f == o.f && g == o.g && h == o.h; }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey& k) const {
+        size_t x = reinterpret_cast<size_t>(k.p);
+        for (int v : {k.a, k.b, k.c, k.d, k.e, k.f, k.g, k.h}) x = x * 1000003u ^ (size_t)(unsigned)v;
+        return x;
+    }
+};
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+static std::mutex g_maps_mu;
+
+static int get_map_2d(CUtensorMap* out, const float* base, int rows, int cols, int box_rows) {
+    MapKey key{base, rows, cols, box_rows, 0, 0, 0, 0, 1};
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return I2V_OK; }
+    if (int r = make_map_2d(out, base, (uint64_t)rows, (uint64_t)cols, (uint32_t)box_rows)) return r;
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps.emplace(key, *out);
+    return I2V_OK;
+}
+static int get_map_im2col(CUtensorMap* out, const float* base, int N, int H, int W, int C, int R, int S, int stride, int pad) {
+    MapKey key{base, N, H, W, C, R, S, stride, 2 + 4 * pad};
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return I2V_OK; }
+    if (int r = make_map_im2col(out, base, N, H, W, C, R, S, stride, pad)) return r;
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps.emplace(key, *out);
+    return I2V_OK;
+}
+
+template <int BN, bool X3, bool IM2COL>
+static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, const TcArgs& args, cudaStream_t st) {
+    using L = TcSmem<BN, X3>;
+    auto kern = conv_tc_kernel<BN, X3, IM2COL>;
+    // two CTAs per SM so that one tile's epilogue overlaps another tile's main loop
+    static int stages = 0;
+    static size_t smem = 0;
+    if (stages == 0) {
+        int dev = 0, optin = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        const size_t budget = (size_t)(optin > 0 ? optin : 227 * 1024) / 2 - 2048;
+        const size_t fixed = 1024 /*align slack*/ + 512 /*barriers*/ + BN * 4;
+        int s = (int)((budget - fixed) / L::STAGE_BYTES);
+        if (s < 2) s = 2;        // fall back to one CTA per SM if two stages do not fit in half an SM
+        if (s > 6) s = 6;
+        smem = fixed + (size_t)s * L::STAGE_BYTES;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "conv_tc: shared memory attribute");
+        stages = s;
+    }
+    dim3 grid((unsigned)((args.M + TC_BM - 1) / TC_BM), (unsigned)(args.Cout / BN));
+    kern<<<grid, TC_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, args, stages);
+    I2V_LAUNCH_CHECK("i2v_conv_tc_f32");
+    return I2V_OK;
+}
+
+}  // namespace i2v
+
+using namespace i2v;
+
+extern "C" int i2v_conv_tc_supported(const i2v_conv_desc* d, int dgrad) {
+    if (!d) return 0;
+    if (d->R != d->S) return 0;
+    if (!dgrad) return (d->Cin % 32 == 0) && (d->Cout % 64 == 0) && d->pad < d->R;
+    // data gradient = forward-style implicit GEMM over dy with the flipped filter: stride 1 only
+    return d->stride == 1 && (d->Cout % 32 == 0) && (d->Cin % 64 == 0) && d->pad < d->R;
+}
+
+// Forward:  src = x  [N,H,W,Cin],  dst = y  [N,P,Q,Cout], w_* = [Cout, R*S*Cin]  K-major (tap-major, channel-minor)
+// Dgrad  :  src = dy [N,P,Q,Cout], dst = dx [N,H,W,Cin],  w_* = [Cin, R*S*Cout] with the filter flipped (host)
+extern "C" int i2v_conv_tc_f32(const i2v_conv_desc* d, int dgrad, const float* src, const float* w_hi, const float* w_lo,
+                               const float* bias, const float* residual, const float* mask_src, float* dst, int flags,
+                               i2v_stream_t stream) {
+    I2V_REQUIRE(d && src && w_hi && dst, "null pointer");
+    I2V_REQUIRE(i2v_conv_tc_supported(d, dgrad), "shape not supported by the tensor-core path");
+    if (d->N == 0) return I2V_OK;
+    if (int r = resolve_driver()) return r;
+    const bool x3 = w_lo != nullptr;
+    int N = d->N, H, W, C, P, Q, Cout, stride, pad;
+    if (!dgrad) { H = d->H; W = d->W; C = d->Cin; P = d->P; Q = d->Q; Cout = d->Cout; stride = d->stride; pad = d->pad; }
+    else        { H = d->P; W = d->Q; C = d->Cout; P = d->H; Q = d->W; Cout = d->Cin; stride = 1; pad = d->R - 1 - d->pad; }
+    const int R = d->R, S = d->S;
+    const bool im2col = !(R == 1 && S == 1 && stride == 1 && pad == 0);
+    I2V_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(w_hi) |
+                  reinterpret_cast<uintptr_t>(w_lo) | reinterpret_cast<uintptr_t>(residual) | reinterpret_cast<uintptr_t>(mask_src) |
+                  reinterpret_cast<uintptr_t>(bias)) & 15) == 0, "all tensors must be 16-byte aligned");
+    const int64_t M = (int64_t)N * P * Q;
+    I2V_REQUIRE(M < (int64_t)0x7fffffff, "too many output pixels for one launch");
+    // X3 needs 48 KB (BN=64) or 64 KB (BN=128) per stage: BN=64 keeps two stages in half an SM so that two
+    // CTAs are co-resident; plain TF32 has room for BN=128.  I2V_TC_BN=64|128 overrides for experiments.
+    int BN = (Cout % 128 == 0 && !x3) ? 128 : 64;
+    if (const char* e = getenv("I2V_TC_BN")) { int v = atoi(e); if ((v == 64 || v == 128) && Cout % v == 0) BN = v; }
+    const int Ktot = R * S * C;
+
+    CUtensorMap tmA, tmBhi, tmBlo;
+    if (im2col) { if (int r = get_map_im2col(&tmA, src, N, H, W, C, R, S, stride, pad)) return r; }
+    else        { if (int r = get_map_2d(&tmA, src, (int)M, C, TC_BM)) return r; }
+    if (int r = get_map_2d(&tmBhi, w_hi, Cout, Ktot, BN)) return r;
+    if (x3) { if (int r = get_map_2d(&tmBlo, w_lo, Cout, Ktot, BN)) return r; }
+    else tmBlo = tmBhi;
+
+    TcArgs a{};
+    a.bias = bias; a.residual = residual; a.mask_src = mask_src; a.dst = dst;
+    a.M = M; a.Cout = Cout; a.P = P; a.Q = Q; a.stride = stride; a.pad = pad; a.R = R; a.S = S; a.cblocks = C / 32;
+    a.relu = (flags & I2V_EPI_RELU) ? 1 : 0;
+    cudaStream_t st = as_stream(stream);
+#define I2V_TC_DISPATCH(BN_)                                                                        \
+    do {                                                                                            \
+        if (x3) return im2col ? tc_launch<BN_, true, true>(tmA, tmBhi, tmBlo, a, st) : tc_launch<BN_, true, false>(tmA, tmBhi, tmBlo, a, st);   \
+        return im2col ? tc_launch<BN_, false, true>(tmA, tmBhi, tmBlo, a, st) : tc_launch<BN_, false, false>(tmA, tmBhi, tmBlo, a, st);          \
+    } while (0)
+    if (BN == 128) I2V_TC_DISPATCH(128);
+    I2V_TC_DISPATCH(64);
+#undef I2V_TC_DISPATCH
+}

@@ -56,6 +56,13 @@ class _Conv:
         self.b_fwd = _pad_cols(bf)
         self.b_dgrad = _pad_cols(bd)
         self.bias = _pad_vec(shift)
+        # tensor-core operands: [Cout, (r,s,ci)] for fprop, flipped/transposed [Cin, (r,s,co)] for dgrad,
+        # each split exactly into hi = trunc_tf32 and lo = w - hi (3xTF32), plus a round-to-nearest TF32 copy
+        # for the plain-TF32 mode
+        tf = ws.permute(0, 2, 3, 1).reshape(cout, R * S * cin).contiguous()
+        td = ws.flip(2, 3).permute(1, 2, 3, 0).reshape(cin, R * S * cout).contiguous()
+        self.tc_fwd = _split_tf32(tf)
+        self.tc_dgrad = _split_tf32(td)
 
     def out_hw(self, h, w):
         return ((h + 2 * self.pad - self.R) // self.stride + 1, (w + 2 * self.pad - self.R) // self.stride + 1)
@@ -87,6 +94,16 @@ class _Concat:
 
     def __init__(self, name, xs, y):
         self.name, self.xs, self.y = name, xs, y
+
+
+def _split_tf32(w):
+    """(hi, lo, rna): hi = w with the low 13 mantissa bits cleared (what the tensor core reads), lo = w - hi
+    (exact in f32), rna = w rounded to nearest TF32."""
+    bits = w.contiguous().view(torch.int32)
+    hi = (bits & -8192).view(torch.float32)
+    lo = (w - hi).contiguous()
+    rna = ((bits + 4096) & -8192).view(torch.float32)
+    return hi.contiguous(), lo, rna.contiguous()
 
 
 def _pad_cols(m):
@@ -240,7 +257,7 @@ class NativeEngine:
                 raise NotImplementedError("hooked buffer %s is not a ReLU output" % b)
         if use_tensor_cores is None:
             use_tensor_cores = os.environ.get("I2V_NATIVE_TC", "1") != "0"
-        self.use_tc = use_tensor_cores and hasattr(capi, "conv_tc_supported")
+        self.use_tc = bool(use_tensor_cores)
         self._cache = {}
 
     @property
@@ -283,10 +300,19 @@ class NativeEngine:
 
     # ---- forward -------------------------------------------------------------------------------------
     def _conv_fwd(self, op, d, x, y, residual):
-        capi.conv_fwd_simt(d, x, op.b_fwd, op.bias, residual, y, relu=op.relu, x_nchw=op.x_nchw)
+        if self.use_tc and not op.x_nchw and capi.conv_tc_supported(d, 0):
+            hi, lo, rna = op.tc_fwd
+            capi.conv_tc(d, 0, x, hi if self.tf32x3 else rna, lo if self.tf32x3 else None, op.bias, residual, None, y,
+                         relu=op.relu)
+        else:
+            capi.conv_fwd_simt(d, x, op.b_fwd, op.bias, residual, y, relu=op.relu, x_nchw=op.x_nchw)
 
     def _conv_dgrad(self, op, d, dy, addend, mask_src, dx):
-        capi.conv_dgrad_simt(d, dy, op.b_dgrad, addend, mask_src, dx, x_nchw=op.x_nchw)
+        if self.use_tc and not op.x_nchw and capi.conv_tc_supported(d, 1):
+            hi, lo, rna = op.tc_dgrad
+            capi.conv_tc(d, 1, dy, hi if self.tf32x3 else rna, lo if self.tf32x3 else None, None, addend, mask_src, dx)
+        else:
+            capi.conv_dgrad_simt(d, dy, op.b_dgrad, addend, mask_src, dx, x_nchw=op.x_nchw)
 
     def features(self, img, need_grad):
         n, c, h, w = img.shape
@@ -357,9 +383,10 @@ class NativeEngine:
                 ready.add(op.x)
             elif op.kind == "pool":
                 mask = acts[op.x] if op.x in self.relu_typed else None
-                if op.x in ready or op.x in pending:
-                    raise NotImplementedError("pooling input with several consumers")
-                capi.maxpool_bwd(gy, plan["argmax"][op.y], mask, G[op.x], op.k, op.stride, op.pad)
+                if op.x in pending:
+                    raise NotImplementedError("pooling input that is also a residual source")
+                capi.maxpool_bwd(gy, plan["argmax"][op.y], mask, G[op.x], op.k, op.stride, op.pad,
+                                 accumulate=op.x in ready)       # hooked input: K1 wrote its gradient first
                 ready.add(op.x)
             else:
                 off = 0

@@ -179,6 +179,21 @@ int i2v_conv_fwd_simt_f32(const i2v_conv_desc* d, const float* x, const float* b
 int i2v_conv_dgrad_simt_f32(const i2v_conv_desc* d, const float* dy, const float* bmat, const float* addend,
                             const float* mask_src, float* dx, int flags, i2v_stream_t stream);
 
+/* Tensor-core path: the same convolution as an implicit GEMM on tcgen05 (kind::tf32, accumulator in TMEM,
+ * operands staged by TMA — im2col-mode tensor maps for R > 1 or stride > 1 — behind an mbarrier pipeline).
+ *   w_hi, w_lo : weights [Cout, R*S*Cin] K-major (tap-major, channel-minor), BN scale folded, split as
+ *                hi = trunc_tf32(w), lo = w - hi.  w_lo != NULL selects FP32-parity mode (3xTF32:
+ *                a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, FP32 accumulate); w_lo == NULL is plain TF32.
+ *   dgrad != 0 : data gradient of a stride-1 convolution: src = dy, dst = dx, and w_* is the flipped,
+ *                transposed filter [Cin, R*S*Cout] (w[co,ci,R-1-r,S-1-s]*bn_scale[co]).
+ *   epilogue   : dst = relu?( acc + bias [+ residual] ) * 1[mask_src > 0]   (each part optional)
+ * i2v_conv_tc_supported() says whether a shape is implemented (channels % 32 / % 64, stride-1 dgrad);
+ * unsupported shapes return I2V_EINVAL — the caller chooses the CUDA-core kernel explicitly.            */
+int i2v_conv_tc_supported(const i2v_conv_desc* d, int dgrad);
+int i2v_conv_tc_f32(const i2v_conv_desc* d, int dgrad, const float* src, const float* w_hi, const float* w_lo,
+                    const float* bias, const float* residual, const float* mask_src, float* dst, int flags,
+                    i2v_stream_t stream);
+
 /* k x k max pooling (stride, -inf padding), NHWC, C % 4 == 0.  argmax[N,P,Q,C] = r*k+s of the FIRST
  * maximum in window scan order (torch.nn.MaxPool2d); backward is the gather form (no atomics) and can
  * apply the ReLU-backward mask of the pooled tensor's producer.  torchvision resnet.maxpool (3,2,1),
@@ -186,7 +201,8 @@ int i2v_conv_dgrad_simt_f32(const i2v_conv_desc* d, const float* dy, const float
 int i2v_maxpool_fwd_f32(const float* x, float* y, uint8_t* argmax, int N, int H, int W, int C, int P, int Q,
                         int k, int stride, int pad, i2v_stream_t stream);
 int i2v_maxpool_bwd_f32(const float* dy, const uint8_t* argmax, const float* mask_src, float* dx, int N, int H,
-                        int W, int C, int P, int Q, int k, int stride, int pad, i2v_stream_t stream);
+                        int W, int C, int P, int Q, int k, int stride, int pad, int accumulate /* dx += */,
+                        i2v_stream_t stream);
 
 /* dst[m, dst_off : dst_off+Ccopy] (=|+=) src[m, src_off : src_off+Ccopy] — channel concat of SqueezeNet's
  * Fire modules (torch.cat([expand1x1, expand3x3], 1)) and its backward split.                        */
