@@ -39,6 +39,9 @@ SIGNATURES = {
     "i2v_layer_sums_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_i64, _c_int, _c_int, _c_p], _c_int),
     "i2v_conv_fwd_simt_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_dgrad_simt_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
+    "i2v_conv_stem_supported": ([_c_p], _c_int),
+    "i2v_conv_stem_fwd_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
+    "i2v_conv_stem_dgrad_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p], _c_int),
     "i2v_conv_tc_supported": ([_c_p, _c_int], _c_int),
     "i2v_conv_tc_f32": ([_c_p, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_maxpool_fwd_f32": ([_c_p, _c_p, _c_p] + [_c_int] * 9 + [_c_p], _c_int),
@@ -84,7 +87,7 @@ def load():
 # benchmark can time each kernel on the launching stream with CUDA events.
 LAUNCHES = {}
 PROFILE_EVENTS = None
-_NO_KERNEL = ("i2v_device_check", "i2v_adam_step_table", "i2v_conv_tc_supported")
+_NO_KERNEL = ("i2v_device_check", "i2v_adam_step_table", "i2v_conv_tc_supported", "i2v_conv_stem_supported")
 
 
 class _Timed:
@@ -256,6 +259,20 @@ def conv_dgrad_simt(desc, dy, bmat, addend, mask_src, dx, x_nchw=False):
     flags = LAYOUT_X_NCHW if x_nchw else 0
     _check(load().i2v_conv_dgrad_simt_f32(ctypes.addressof(desc), _dev(dy), _dev(bmat), _dev(addend), _dev(mask_src),
                                           _dev(dx), flags, _stream()), "i2v_conv_dgrad_simt_f32")
+
+
+def conv_stem_supported(desc):
+    return bool(load().i2v_conv_stem_supported(ctypes.addressof(desc)))
+
+
+def conv_stem_fwd(desc, x, w, bias, y, relu=True):
+    _check(load().i2v_conv_stem_fwd_f32(ctypes.addressof(desc), _dev(x), _dev(w), _dev(bias), _dev(y),
+                                        EPI_RELU if relu else 0, _stream()), "i2v_conv_stem_fwd_f32")
+
+
+def conv_stem_dgrad(desc, dy, w, dx):
+    _check(load().i2v_conv_stem_dgrad_f32(ctypes.addressof(desc), _dev(dy), _dev(w), _dev(dx), _stream()),
+           "i2v_conv_stem_dgrad_f32")
 
 
 def conv_tc_supported(desc, dgrad):

@@ -12,7 +12,13 @@
 // FP32-parity mode (X3 = true): the tensor core reads f32 bit patterns as TF32, i.e. it ignores the low
 // 13 mantissa bits.  Each operand is split exactly into hi = trunc_tf32(v) and lo = v - hi, and
 //     a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo          (the dropped a_lo*b_lo term is < 2^-22 |a*b|)
-// is accumulated in FP32 in TMEM: three MMAs per K-slice.  B_hi/B_lo are precomputed once per model;
+// is accumulated in FP32 in TMEM: three MMAs per K-slice.  The tensor core adds into its FP32 accumulator
+// with truncation (round toward zero), one truncation per MMA instruction, which shows up as a
+// systematic relative bias of ~(#instructions/2) ulp (measured 4e-5 at K = 576 with a single accumulator).
+// The two small cross terms therefore go to a SECOND TMEM accumulator (their magnitude is 2^-11 of the
+// main one, so its truncation error is negligible) and the two are added in the epilogue with a
+// round-to-nearest FADD; the main accumulator then sees K/8 truncations instead of 3K/8.
+// B_hi/B_lo are precomputed once per model;
 // A_hi is the raw tile (hardware truncation), A_lo is produced on the fly by four "split" warps that
 // rewrite each landed A tile into a second shared-memory buffer (element-wise, so the swizzle pattern is
 // preserved).  X3 = false is plain TF32 (one MMA per K-slice), the mode cuDNN uses with allow_tf32.
@@ -178,8 +184,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_init(accum_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 1) {   // TMEM: BN f32 columns x 128 lanes for the accumulator
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+    constexpr uint32_t kTmemCols = X3 ? 2 * BN : BN;   // main accumulator [+ cross-term accumulator]
+    if (warp == 1) {   // TMEM: 128 lanes x kTmemCols f32 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (threadIdx.x >= 128 && threadIdx.x - 128 < BN)
@@ -233,9 +240,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int kk = 0; kk < TC_BK / 8; ++kk) {              // UMMA K = 8 tf32 = 32 bytes: +2 in the >>4 address field
                     umma_tf32(tmem_base, da + 2 * kk, dbh + 2 * kk, idesc, (it | kk) ? 1u : 0u);
-                    if (X3) {
-                        umma_tf32(tmem_base, dal + 2 * kk, dbh + 2 * kk, idesc, 1u);
-                        umma_tf32(tmem_base, da + 2 * kk, dbl + 2 * kk, idesc, 1u);
+                    if (X3) {   // cross terms into the second accumulator (columns BN..2BN)
+                        umma_tf32(tmem_base + BN, dal + 2 * kk, dbh + 2 * kk, idesc, (it | kk) ? 1u : 0u);
+                        umma_tf32(tmem_base + BN, da + 2 * kk, dbl + 2 * kk, idesc, 1u);
                     }
                 }
                 umma_commit(&empty_bar[st]);       // frees the stage when these MMAs have read it
@@ -274,6 +281,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t r[32];
             tmem_ld32(lane_base + (uint32_t)c0, r);   // warp-collective: every lane participates
+            if (X3) {
+                uint32_t r2[32];
+                tmem_ld32(lane_base + (uint32_t)(BN + c0), r2);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])));
+            }
             if (m < args.M) {
                 const int64_t off = m * args.Cout + n0 + c0;
 #pragma unroll
@@ -300,7 +313,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(kTmemCols) : "memory");
     }
 }
 

@@ -319,8 +319,8 @@ static int cosine_launch(const float* a, const float* b, float* grad_a, float* c
 extern "C" int i2v_cosine_loss_grad_f32(const float* a, const float* b, float* grad_a, float* cos_out, int64_t N,
                                         int64_t D, const float* w_dev, float w_host, int relu_mask,
                                         i2v_stream_t stream) {
-    I2V_REQUIRE(N >= 0 && D >= 1, "bad sizes N=%lld D=%lld", (long long)N, (long long)D);
-    if (N == 0) return I2V_OK;   // empty batch (pointers may be null)
+    if (N == 0) return I2V_OK;   // empty batch (pointers may be null, D is whatever the caller computed)
+    I2V_REQUIRE(N > 0 && D >= 1, "bad sizes N=%lld D=%lld", (long long)N, (long long)D);
     I2V_REQUIRE(a && b, "null feature pointer");
     I2V_REQUIRE(N <= 0x7fffffff / 16, "too many frames in one call");
     const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |

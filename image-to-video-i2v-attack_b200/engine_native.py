@@ -63,6 +63,8 @@ class _Conv:
         td = ws.flip(2, 3).permute(1, 2, 3, 0).reshape(cin, R * S * cout).contiguous()
         self.tc_fwd = _split_tf32(tf)
         self.tc_dgrad = _split_tf32(td)
+        # first layer (Cin = 3): [(c,r,s), co] for the stem forward; its dgrad uses b_fwd = [(r,s), c, co]
+        self.w_stem = ws.permute(1, 2, 3, 0).reshape(cin * R * S, cout).contiguous() if x_nchw else None
 
     def out_hw(self, h, w):
         return ((h + 2 * self.pad - self.R) // self.stride + 1, (w + 2 * self.pad - self.R) // self.stride + 1)
@@ -258,6 +260,7 @@ class NativeEngine:
         if use_tensor_cores is None:
             use_tensor_cores = os.environ.get("I2V_NATIVE_TC", "1") != "0"
         self.use_tc = bool(use_tensor_cores)
+        self.use_stem = os.environ.get("I2V_NATIVE_STEM", "1") != "0"   # dedicated first-layer kernels
         self._cache = {}
 
     @property
@@ -300,7 +303,9 @@ class NativeEngine:
 
     # ---- forward -------------------------------------------------------------------------------------
     def _conv_fwd(self, op, d, x, y, residual):
-        if self.use_tc and not op.x_nchw and capi.conv_tc_supported(d, 0):
+        if op.x_nchw and residual is None and self.use_stem and capi.conv_stem_supported(d):
+            capi.conv_stem_fwd(d, x, op.w_stem, op.bias, y, relu=op.relu)
+        elif self.use_tc and not op.x_nchw and capi.conv_tc_supported(d, 0):
             hi, lo, rna = op.tc_fwd
             capi.conv_tc(d, 0, x, hi if self.tf32x3 else rna, lo if self.tf32x3 else None, op.bias, residual, None, y,
                          relu=op.relu)
@@ -308,7 +313,9 @@ class NativeEngine:
             capi.conv_fwd_simt(d, x, op.b_fwd, op.bias, residual, y, relu=op.relu, x_nchw=op.x_nchw)
 
     def _conv_dgrad(self, op, d, dy, addend, mask_src, dx):
-        if self.use_tc and not op.x_nchw and capi.conv_tc_supported(d, 1):
+        if op.x_nchw and addend is None and mask_src is None and self.use_stem and capi.conv_stem_supported(d):
+            capi.conv_stem_dgrad(d, dy, op.b_fwd, dx)
+        elif self.use_tc and not op.x_nchw and capi.conv_tc_supported(d, 1):
             hi, lo, rna = op.tc_dgrad
             capi.conv_tc(d, 1, dy, hi if self.tf32x3 else rna, lo if self.tf32x3 else None, None, addend, mask_src, dx)
         else:

@@ -179,6 +179,16 @@ int i2v_conv_fwd_simt_f32(const i2v_conv_desc* d, const float* x, const float* b
 int i2v_conv_dgrad_simt_f32(const i2v_conv_desc* d, const float* dy, const float* bmat, const float* addend,
                             const float* mask_src, float* dx, int flags, i2v_stream_t stream);
 
+/* First layer (Cin = 3, Cout = 64: ResNet 7x7/s2, AlexNet 11x11/s4, VGG 3x3/s1, SqueezeNet 3x3/s2).
+ *   fwd  : x [N,3,H,W] (the layout the update kernels keep the image in) -> y [N,P,Q,64] NHWC, + bias, ReLU;
+ *          w = [(c,r,s), 64] = weight[co,c,r,s]*bn_scale[co]
+ *   dgrad: dy [N,P,Q,64] -> dx [N,3,H,W] = dcost/dimage;  w = [(r,s), c, 64]
+ * torchvision `conv1/bn1/relu` (resnet) or `features[0:2]`; forward / backward of image_attacks.py:334 / 352. */
+int i2v_conv_stem_supported(const i2v_conv_desc* d);
+int i2v_conv_stem_fwd_f32(const i2v_conv_desc* d, const float* x, const float* w, const float* bias, float* y,
+                          int flags, i2v_stream_t stream);
+int i2v_conv_stem_dgrad_f32(const i2v_conv_desc* d, const float* dy, const float* w, float* dx, i2v_stream_t stream);
+
 /* Tensor-core path: the same convolution as an implicit GEMM on tcgen05 (kind::tf32, accumulator in TMEM,
  * operands staged by TMA — im2col-mode tensor maps for R > 1 or stride > 1 — behind an mbarrier pipeline).
  *   w_hi, w_lo : weights [Cout, R*S*Cin] K-major (tap-major, channel-minor), BN scale folded, split as

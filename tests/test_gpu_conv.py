@@ -163,3 +163,119 @@ def test_native_engine_matches_autograd(name, depth, side, mode):
     gimg = eng.input_grad(grads).cpu().double()
     err = (gimg - gref).abs().max() / gref.abs().max()
     assert err <= 2e-4, ("input gradient", err)
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core path (tcgen05 / TMEM / TMA), per layer
+# ------------------------------------------------------------------------------------------------
+TC_SHAPES = [
+    #  N  H   W   Cin  Cout k s p
+    (2, 56, 56, 64, 64, 1, 1, 0),      # 2-D tiled TMA, 2 k-blocks, BN=64
+    (2, 56, 56, 64, 256, 1, 1, 0),     # layer1 conv3
+    (2, 56, 56, 256, 64, 1, 1, 0),     # layer1 conv1 (8 k-blocks: pipeline wraps)
+    (2, 56, 56, 64, 64, 3, 1, 1),      # im2col TMA, padding rows/cols
+    (3, 28, 28, 128, 128, 3, 1, 1),    # tile spans image boundaries (784 px / image)
+    (2, 56, 56, 128, 128, 3, 2, 1),    # strided im2col (forward only on TC)
+    (2, 56, 56, 256, 512, 1, 2, 0),    # strided 1x1 (forward only on TC)
+    (1, 28, 28, 128, 512, 1, 1, 0),    # M = 784: last tile ragged (784 = 6*128 + 16)
+    (2, 14, 14, 256, 256, 3, 1, 1),    # layer3-like, 196 px / image
+    (1, 13, 13, 64, 192, 3, 1, 1),     # odd spatial size, Cout = 3*64
+    (1, 15, 15, 64, 192, 5, 1, 2),     # AlexNet conv2: 25 taps
+    (3, 32, 32, 64, 64, 3, 1, 1),      # VGG-on-32x32 shapes (tests): tiles cover several rows / several images
+    (3, 16, 16, 128, 128, 3, 1, 1),
+    (3, 8, 8, 256, 256, 3, 1, 1),
+    (3, 4, 4, 512, 512, 3, 1, 1),      # 48 pixels in total (< one tile), K = 4608: 144 pipeline iterations
+    (11, 4, 4, 64, 64, 3, 1, 1),       # one tile spans 8 whole images
+]
+
+
+def _tc_operands(w, scale):
+    from i2v_b200.engine_native import _split_tf32
+    ws = w * scale.view(-1, 1, 1, 1)
+    cout, cin, k, _ = w.shape
+    tf = ws.permute(0, 2, 3, 1).reshape(cout, k * k * cin).contiguous().to(DEV)
+    td = ws.flip(2, 3).permute(1, 2, 3, 0).reshape(cin, k * k * cout).contiguous().to(DEV)
+    return ws, _split_tf32(tf), _split_tf32(td)
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+@pytest.mark.parametrize("x3", [True, False])
+def test_conv_tc_fwd_and_dgrad(shape, x3):
+    """Error model: plain TF32 truncates both operands (~1e-3); 3xTF32 recovers the operands exactly and is left
+    with the tensor core's truncating FP32 accumulation, a bias of about (K/8)/2 ulp — bounded here by
+    1e-5 + K * 2^-24 relative to the largest output."""
+    N, H, W, Cin, Cout, k, s, p = shape
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    scale = torch.rand(Cout, generator=g) + 0.5
+    shift = torch.randn(Cout, generator=g) * 0.1
+    P, Q = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    res = torch.randn(N, Cout, P, Q, generator=g)
+    d = capi.ConvDesc(N, H, W, Cin, Cout, k, k, s, p, P, Q)
+    assert capi.conv_tc_supported(d, 0)
+    ws, (fh, fl, fr), (dh, dl, dr) = _tc_operands(w, scale)
+    xd = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    resd = res.permute(0, 2, 3, 1).contiguous().to(DEV)
+    bias = shift.to(DEV)
+    tol = (1e-5 + k * k * Cin * 2.0 ** -24) if x3 else 4e-3
+    for use_res, relu in ((False, False), (True, True)):
+        y = torch.full((N, P, Q, Cout), float("nan"), device=DEV)
+        capi.conv_tc(d, 0, xd, fh if x3 else fr, fl if x3 else None, bias, resd if use_res else None, None, y, relu=relu)
+        ref64 = _ref_conv(x, w, scale, shift, s, p, res if use_res else None, relu, torch.float64)
+        got = y.permute(0, 3, 1, 2).cpu().double()
+        assert torch.isfinite(got).all()
+        err = (got - ref64).abs().max() / ref64.abs().max()
+        assert err <= tol, ("fwd", err, tol)
+    if not capi.conv_tc_supported(d, 1):
+        assert s != 1
+        return
+    dy = torch.randn(N, Cout, P, Q, generator=g)
+    addend = torch.randn(N, Cin, H, W, generator=g)
+    act = torch.randn(N, Cin, H, W, generator=g)
+    dyd = dy.permute(0, 2, 3, 1).contiguous().to(DEV)
+    lay = lambda t: t.permute(0, 2, 3, 1).contiguous().to(DEV)
+    tol = (1e-5 + k * k * Cout * 2.0 ** -24) if x3 else 4e-3
+    for use_add, use_mask in ((False, False), (True, True)):
+        dx = torch.full((N, H, W, Cin), float("nan"), device=DEV)
+        capi.conv_tc(d, 1, dyd, dh if x3 else dr, dl if x3 else None, None, lay(addend) if use_add else None,
+                     lay(act) if use_mask else None, dx)
+        ref64 = torch.nn.grad.conv2d_input((N, Cin, H, W), ws.double(), dy.double(), s, p)
+        if use_add:
+            ref64 = ref64 + addend.double()
+        if use_mask:
+            ref64 = ref64 * (act > 0).double()
+        got = dx.permute(0, 3, 1, 2).cpu().double()
+        assert torch.isfinite(got).all()
+        err = (got - ref64).abs().max() / ref64.abs().max()
+        assert err <= tol, ("dgrad", err, tol)
+
+
+@pytest.mark.parametrize("H,W,k,s,p", [(224, 224, 7, 2, 3), (64, 64, 7, 2, 3), (64, 64, 11, 4, 2), (32, 32, 3, 1, 1),
+                                       (64, 64, 3, 2, 0), (37, 53, 7, 2, 3), (31, 45, 3, 2, 0), (50, 70, 11, 4, 2)])
+def test_stem_fwd_and_dgrad(H, W, k, s, p):
+    """Dedicated first-layer kernels (Cin = 3 -> Cout = 64) for every attacked family, incl. ragged sizes."""
+    g = torch.Generator().manual_seed(5)
+    N, Cin, Cout = 2, 3, 64
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    scale = torch.rand(Cout, generator=g) + 0.5
+    shift = torch.randn(Cout, generator=g) * 0.1
+    P, Q = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    d = capi.ConvDesc(N, H, W, Cin, Cout, k, k, s, p, P, Q)
+    assert capi.conv_stem_supported(d)
+    ws = w * scale.view(-1, 1, 1, 1)
+    wf = ws.permute(1, 2, 3, 0).reshape(Cin * k * k, Cout).contiguous().to(DEV)
+    wd = ws.permute(2, 3, 1, 0).reshape(k * k * Cin, Cout).contiguous().to(DEV)
+    y = torch.full((N, P, Q, Cout), float("nan"), device=DEV)
+    capi.conv_stem_fwd(d, x.to(DEV), wf, shift.to(DEV), y, relu=True)
+    ref = _ref_conv(x, w, scale, shift, s, p, None, True, torch.float64)
+    got = y.permute(0, 3, 1, 2).cpu().double()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max() / ref.abs().max() <= 2e-6
+    dy = torch.randn(N, Cout, P, Q, generator=g)
+    dx = torch.full((N, Cin, H, W), float("nan"), device=DEV)
+    capi.conv_stem_dgrad(d, dy.permute(0, 2, 3, 1).contiguous().to(DEV), wd, dx)
+    ref = torch.nn.grad.conv2d_input((N, Cin, H, W), ws.double(), dy.double(), s, p)
+    assert torch.isfinite(dx).all()
+    assert (dx.cpu().double() - ref).abs().max() / ref.abs().max() <= 2e-6

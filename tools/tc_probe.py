@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""Per-layer probe of the convolution kernels on the ResNet-50 -> layer2 shapes (run on the GPU box):
+accuracy against float64 (signed mean and max relative error) on 2 frames, and device time / TFLOP/s on
+`--frames` frames for the tensor-core kernel (3xTF32 and TF32), the CUDA-core kernel and cuDNN (FP32 and TF32)."""
+import argparse, json, os, sys
+import torch
+import torch.nn.functional as F
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from i2v_b200 import capi
+from i2v_b200.engine_native import _split_tf32, _pad_cols
+
+LAYERS = [  # name, H, Cin, Cout, k, s, p, count(fwd)
+    ("l1.conv1(64->64,1x1)", 56, 64, 64, 1, 1, 0, 1),
+    ("l1.conv2(64->64,3x3)", 56, 64, 64, 3, 1, 1, 3),
+    ("l1.conv3(64->256,1x1)", 56, 64, 256, 1, 1, 0, 4),
+    ("l1.conv1(256->64,1x1)", 56, 256, 64, 1, 1, 0, 2),
+    ("l2.0.conv1(256->128,1x1)", 56, 256, 128, 1, 1, 0, 1),
+    ("l2.0.conv2(128->128,3x3/2)", 56, 128, 128, 3, 2, 1, 1),
+    ("l2.0.ds(256->512,1x1/2)", 56, 256, 512, 1, 2, 0, 1),
+    ("l2.conv3(128->512,1x1)", 28, 128, 512, 1, 1, 0, 4),
+    ("l2.conv1(512->128,1x1)", 28, 512, 128, 1, 1, 0, 3),
+    ("l2.conv2(128->128,3x3)", 28, 128, 128, 3, 1, 1, 3),
+]
+
+
+def timeit(fn, iters=5):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sorted(ts)[len(ts) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--frames", type=int, default=32)
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    dev = "cuda"
+    capi.device_check(torch.device(dev, 0))
+    out = []
+    for name, H, Cin, Cout, k, s, p, cnt in LAYERS:
+        P = (H + 2 * p - k) // s + 1
+        g = torch.Generator().manual_seed(1)
+        w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5)
+        tf = w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous().to(dev)
+        hi, lo, rna = _split_tf32(tf)
+        bf = _pad_cols(w.permute(2, 3, 1, 0).reshape(-1, Cout)).to(dev)
+        rec = {"layer": name, "K": k * k * Cin}
+        # accuracy on 2 frames
+        x = torch.randn(2, Cin, H, H, generator=g)
+        ref = F.conv2d(x.double(), w.double(), None, s, p)
+        xd = x.permute(0, 2, 3, 1).contiguous().to(dev)
+        d = capi.ConvDesc(2, H, H, Cin, Cout, k, k, s, p, P, P)
+        for mode, (a, b) in (("x3", (hi, lo)), ("x1", (rna, None))):
+            y = torch.empty(2, P, P, Cout, device=dev)
+            capi.conv_tc(d, 0, xd, a, b, None, None, None, y)
+            e = (y.permute(0, 3, 1, 2).cpu().double() - ref)
+            rec["err_max_" + mode] = float(e.abs().max() / ref.abs().max())
+            rec["err_bias_" + mode] = float((e * ref.sign()).mean() / ref.abs().mean())
+        y = torch.empty(2, P, P, Cout, device=dev)
+        capi.conv_fwd_simt(d, xd, bf, None, None, y)
+        rec["err_max_simt"] = float((y.permute(0, 3, 1, 2).cpu().double() - ref).abs().max() / ref.abs().max())
+        # timing on `frames`
+        n = args.frames
+        xd = torch.randn(n, H, H, Cin, device=dev)
+        y = torch.empty(n, P, P, Cout, device=dev)
+        d = capi.ConvDesc(n, H, H, Cin, Cout, k, k, s, p, P, P)
+        flop = 2.0 * n * P * P * Cout * Cin * k * k
+        byts = 4.0 * (xd.numel() + y.numel())
+        for mode, fn in (("tc_x3", lambda: capi.conv_tc(d, 0, xd, hi, lo, None, None, None, y, relu=True)),
+                         ("tc_x1", lambda: capi.conv_tc(d, 0, xd, rna, None, None, None, None, y, relu=True)),
+                         ("simt", lambda: capi.conv_fwd_simt(d, xd, bf, None, None, y, relu=True))):
+            ms = timeit(fn)
+            rec["ms_" + mode] = ms
+            rec["tflops_" + mode] = flop / ms / 1e9
+            rec["gbs_" + mode] = byts / ms / 1e6
+        xc = xd.permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
+        wc = w.to(dev).contiguous(memory_format=torch.channels_last)
+        for tf32 in (False, True):
+            torch.backends.cudnn.allow_tf32 = tf32
+            ms = timeit(lambda: F.relu(F.conv2d(xc, wc, None, s, p)))
+            rec["ms_cudnn_" + ("tf32" if tf32 else "fp32")] = ms
+        torch.backends.cudnn.allow_tf32 = False
+        rec["us_per_frame_tc_x3"] = 1e3 * rec["ms_tc_x3"] / n
+        out.append(rec)
+        print(json.dumps(rec), flush=True)
+    if args.out:
+        json.dump(out, open(args.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
