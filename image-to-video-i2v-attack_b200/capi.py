@@ -44,6 +44,7 @@ SIGNATURES = {
     "i2v_conv_stem_dgrad_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p], _c_int),
     "i2v_conv_tc_supported": ([_c_p, _c_int], _c_int),
     "i2v_conv_tc_f32": ([_c_p, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
+    "i2v_conv_tc_dgrad_class_f32": ([_c_p, _c_int, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p], _c_int),
     "i2v_maxpool_fwd_f32": ([_c_p, _c_p, _c_p] + [_c_int] * 9 + [_c_p], _c_int),
     "i2v_maxpool_bwd_f32": ([_c_p, _c_p, _c_p, _c_p] + [_c_int] * 10 + [_c_p], _c_int),
     "i2v_copy_channels_f32": ([_c_p, _c_p, _c_i64] + [_c_int] * 6 + [_c_p], _c_int),
@@ -284,6 +285,13 @@ def conv_tc(desc, dgrad, src, w_hi, w_lo, bias, residual, mask_src, dst, relu=Fa
     _check(load().i2v_conv_tc_f32(ctypes.addressof(desc), int(dgrad), _dev(src), _dev(w_hi), _dev(w_lo), _dev(bias),
                                   _dev(residual), _dev(mask_src), _dev(dst), EPI_RELU if relu else 0, _stream()),
            "i2v_conv_tc_f32")
+
+
+def conv_tc_dgrad_class(desc, ph, pw, dy, w_hi, w_lo, addend, mask_src, dx):
+    """One stride-parity class of a strided data gradient on the tensor cores (see include/i2v_b200.h)."""
+    _check(load().i2v_conv_tc_dgrad_class_f32(ctypes.addressof(desc), ph, pw, _dev(dy), _dev(w_hi), _dev(w_lo),
+                                              _dev(addend), _dev(mask_src), _dev(dx), _stream()),
+           "i2v_conv_tc_dgrad_class_f32")
 
 
 def maxpool_fwd(x, y, argmax, k, stride, pad):

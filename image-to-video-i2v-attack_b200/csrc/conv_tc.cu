@@ -47,12 +47,16 @@ struct TcArgs {
     const float* residual;   // [M, Cout] or null
     const float* mask_src;   // [M, Cout] or null
     float* dst;              // [M, Cout]
-    int64_t M;               // N*P*Q output pixels
+    int64_t M;               // N*P*Q GEMM rows
     int Cout;
-    int P, Q;                // output spatial dims
-    int stride, pad, R, S;
+    int P, Q;                // row grid: m = (img, p, q)
+    int stride;              // im2col traversal stride of the window corner
+    int lower_h, lower_w;    // window corner of (p,q) = (0,0) in source coordinates (= -pad for a forward conv)
+    int taps_h, taps_w;      // K = (tap_h, tap_w, channel); TMA im2col offsets = (tap_w, tap_h)
     int cblocks;             // C / 32
     int relu;
+    // output row of GEMM row (img,p,q): ((img*out_H + p*out_s + out_h0)*out_W + q*out_s + out_w0); identity when out_s == 0
+    int out_s, out_h0, out_w0, out_H, out_W;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -165,7 +169,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t m0 = (int64_t)blockIdx.x * TC_BM;
     const int n0 = blockIdx.y * BN;
-    const int kiters = args.R * args.S * args.cblocks;
+    const int kiters = args.taps_h * args.taps_w * args.cblocks;
 
     auto stage_a = [&](int s) { return tiles + (size_t)s * L::STAGE_BYTES; };
     auto stage_alo = [&](int s) { return tiles + (size_t)s * L::STAGE_BYTES + TC_A_BYTES; };
@@ -205,12 +209,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 img = (int)(m0 / pq);
                 const int rem = (int)(m0 - (int64_t)img * pq);
                 const int p = rem / args.Q, q = rem - p * args.Q;
-                base_h = p * args.stride - args.pad;      // coordinate of the filter window's corner (tap 0,0)
-                base_w = q * args.stride - args.pad;
+                base_h = p * args.stride + args.lower_h;   // coordinate of the filter window's corner (tap 0,0)
+                base_w = q * args.stride + args.lower_w;
             }
             int it = 0;
-            for (int r = 0; r < args.R; ++r)
-                for (int s = 0; s < args.S; ++s)
+            for (int r = 0; r < args.taps_h; ++r)
+                for (int s = 0; s < args.taps_w; ++s)
                     for (int cb = 0; cb < args.cblocks; ++cb, ++it) {
                         const int st = it % stages;
                         const uint32_t ph = (uint32_t)(it / stages) & 1;
@@ -218,7 +222,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         mbar_arrive_expect_tx(&full_bar[st], TC_A_BYTES + L::B_BYTES * (X3 ? 2 : 1));
                         if (IM2COL) tma_load_im2col_4d(&tmA, &full_bar[st], stage_a(st), cb * TC_BK, base_w, base_h, img, (uint16_t)s, (uint16_t)r);
                         else        tma_load_2d(&tmA, &full_bar[st], stage_a(st), cb * TC_BK, (int)m0);
-                        const int kcol = ((r * args.S + s) * args.cblocks + cb) * TC_BK;
+                        const int kcol = ((r * args.taps_w + s) * args.cblocks + cb) * TC_BK;
                         tma_load_2d(&tmBhi, &full_bar[st], stage_bhi(st), kcol, n0);
                         if (X3) tma_load_2d(&tmBlo, &full_bar[st], stage_blo(st), kcol, n0);
                     }
@@ -275,7 +279,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===== epilogue ===========================================================================
         mbar_wait(accum_bar, 0);
         tc_fence_after();
-        const int64_t m = m0 + t;                  // thread t owns TMEM lane t = output pixel m
+        const int64_t m = m0 + t;                  // thread t owns TMEM lane t = GEMM row m
+        int64_t orow = m;
+        if (args.out_s != 0 && m < args.M) {       // strided data-gradient class: scatter rows into the full-resolution tensor
+            const int64_t pq = (int64_t)args.P * args.Q;
+            const int img = (int)(m / pq);
+            const int rem = (int)(m - (int64_t)img * pq);
+            const int p = rem / args.Q, q = rem - p * args.Q;
+            orow = ((int64_t)img * args.out_H + (p * args.out_s + args.out_h0)) * args.out_W + (q * args.out_s + args.out_w0);
+        }
         const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -288,7 +300,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])));
             }
             if (m < args.M) {
-                const int64_t off = m * args.Cout + n0 + c0;
+                const int64_t off = orow * args.Cout + n0 + c0;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     float4 v = make_float4(__uint_as_float(r[j]) + bias_s[c0 + j], __uint_as_float(r[j + 1]) + bias_s[c0 + j + 1],
@@ -312,6 +324,225 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// v2: persistent, fully warp-specialised variant.
+// One CTA per SM walks over (m-tile, n-tile) pairs; the TMA producer and the split warps run ahead across
+// tile boundaries, the accumulator is multi-buffered in TMEM so tile i+1's MMAs overlap tile i's epilogue,
+// which has its own four warps.  Removes the per-tile launch / TMEM-allocation / pipeline-fill bubbles that
+// dominate v1 on the many small-K 1x1 convolutions (measured v1: 2.2 us per 128x64 tile at K = 64).
+//   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM allocator   warps 4-7: A split (3xTF32)
+//   warps 8-11: epilogue (warp w owns TMEM lanes 32*(w%4)..+31)
+// ---------------------------------------------------------------------------------------------
+constexpr int TC2_THREADS = 384;
+
+template <int BN, bool X3, bool IM2COL>
+__global__ void __launch_bounds__(TC2_THREADS, 1)
+conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                       const __grid_constant__ CUtensorMap tmBlo, const TcArgs args, const int stages,
+                       const int num_m_tiles, const int num_n_tiles) {
+    using L = TcSmem<BN, X3>;
+    constexpr uint32_t kAccCols = X3 ? 2 * BN : BN;            // TMEM columns per accumulator stage
+    constexpr int kAcc = (512 / kAccCols) > 4 ? 4 : (512 / kAccCols);
+    constexpr uint32_t kTmemCols = kAccCols * kAcc;             // 256 or 512: a power of two
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* tiles = smem;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * L::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + stages;
+    uint64_t* split_bar = empty_bar + stages;
+    uint64_t* tfull_bar = split_bar + stages;
+    uint64_t* tempty_bar = tfull_bar + kAcc;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + kAcc);
+    float* bias_s = reinterpret_cast<float*>(tmem_slot + 2);    // [Cout]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kiters = args.taps_h * args.taps_w * args.cblocks;
+    const int num_tiles = num_m_tiles * num_n_tiles;
+
+    auto stage_a = [&](int s) { return tiles + (size_t)s * L::STAGE_BYTES; };
+    auto stage_alo = [&](int s) { return tiles + (size_t)s * L::STAGE_BYTES + TC_A_BYTES; };
+    auto stage_bhi = [&](int s) { return tiles + (size_t)s * L::STAGE_BYTES + TC_A_BYTES * (X3 ? 2 : 1); };
+    auto stage_blo = [&](int s) { return tiles + (size_t)s * L::STAGE_BYTES + TC_A_BYTES * 2 + L::B_BYTES; };
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA); prefetch_tmap(&tmBhi);
+        if (X3) prefetch_tmap(&tmBlo);
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+            mbar_init(&split_bar[s], 128);
+        }
+        for (int a = 0; a < kAcc; ++a) {
+            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tempty_bar[a], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < args.Cout; i += TC2_THREADS) bias_s[i] = args.bias ? args.bias[i] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer: runs ahead across tiles, bounded only by the smem ring ===================
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m_tile = tile / num_n_tiles, n_tile = tile - m_tile * num_n_tiles;
+                const int64_t m0 = (int64_t)m_tile * TC_BM;
+                const int n0 = n_tile * BN;
+                int img = 0, base_h = 0, base_w = 0;
+                if (IM2COL) {
+                    const int64_t pq = (int64_t)args.P * args.Q;
+                    img = (int)(m0 / pq);
+                    const int rem = (int)(m0 - (int64_t)img * pq);
+                    const int p = rem / args.Q, q = rem - p * args.Q;
+                    base_h = p * args.stride + args.lower_h;
+                    base_w = q * args.stride + args.lower_w;
+                }
+                for (int r = 0; r < args.taps_h; ++r)
+                    for (int s = 0; s < args.taps_w; ++s)
+                        for (int cb = 0; cb < args.cblocks; ++cb, ++it) {
+                            const int st = it % stages;
+                            const uint32_t ph = (uint32_t)(it / stages) & 1;
+                            mbar_wait(&empty_bar[st], ph ^ 1);
+                            mbar_arrive_expect_tx(&full_bar[st], TC_A_BYTES + L::B_BYTES * (X3 ? 2 : 1));
+                            if (IM2COL) tma_load_im2col_4d(&tmA, &full_bar[st], stage_a(st), cb * TC_BK, base_w, base_h, img, (uint16_t)s, (uint16_t)r);
+                            else        tma_load_2d(&tmA, &full_bar[st], stage_a(st), cb * TC_BK, (int)m0);
+                            const int kcol = ((r * args.taps_w + s) * args.cblocks + cb) * TC_BK;
+                            tma_load_2d(&tmBhi, &full_bar[st], stage_bhi(st), kcol, n0);
+                            if (X3) tma_load_2d(&tmBlo, &full_bar[st], stage_blo(st), kcol, n0);
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer ==============================================================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(BN);
+            int it = 0, t = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+                const int acc = t % kAcc;
+                const uint32_t aph = (uint32_t)(t / kAcc) & 1;
+                mbar_wait(&tempty_bar[acc], aph ^ 1);          // epilogue has drained this accumulator stage
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + (uint32_t)acc * kAccCols;
+                for (int kb = 0; kb < kiters; ++kb, ++it) {
+                    const int st = it % stages;
+                    const uint32_t ph = (uint32_t)(it / stages) & 1;
+                    mbar_wait(&full_bar[st], ph);
+                    if (X3) mbar_wait(&split_bar[st], ph);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_sw128(smem_u32(stage_a(st)));
+                    const uint64_t dbh = umma_desc_sw128(smem_u32(stage_bhi(st)));
+                    uint64_t dal = 0, dbl = 0;
+                    if (X3) { dal = umma_desc_sw128(smem_u32(stage_alo(st))); dbl = umma_desc_sw128(smem_u32(stage_blo(st))); }
+#pragma unroll
+                    for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                        umma_tf32(d0, da + 2 * kk, dbh + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
+                        if (X3) {
+                            umma_tf32(d0 + BN, dal + 2 * kk, dbh + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
+                            umma_tf32(d0 + BN, da + 2 * kk, dbl + 2 * kk, idesc, 1u);
+                        }
+                    }
+                    umma_commit(&empty_bar[st]);
+                }
+                umma_commit(&tfull_bar[acc]);
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===== A split (3xTF32 only) ====================================================================
+        if (X3) {
+            const int t128 = threadIdx.x - 128;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+                for (int kb = 0; kb < kiters; ++kb, ++it) {
+                    const int st = it % stages;
+                    const uint32_t ph = (uint32_t)(it / stages) & 1;
+                    mbar_wait(&full_bar[st], ph);
+                    const float4* src = reinterpret_cast<const float4*>(stage_a(st));
+                    float4* dst = reinterpret_cast<float4*>(stage_alo(st));
+#pragma unroll
+                    for (int j = 0; j < (int)(TC_A_BYTES / 16 / 128); ++j) {
+                        float4 v = src[t128 + 128 * j], o;
+                        o.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                        o.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                        o.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                        o.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                        dst[t128 + 128 * j] = o;
+                    }
+                    fence_proxy_async();
+                    mbar_arrive(&split_bar[st]);
+                }
+        }
+    } else if (warp >= 8) {
+        // ===== epilogue =================================================================================
+        const int t128 = threadIdx.x - 256;                     // TMEM lane = tile row
+        int t = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+            const int m_tile = tile / num_n_tiles, n_tile = tile - m_tile * num_n_tiles;
+            const int n0 = n_tile * BN;
+            const int acc = t % kAcc;
+            const uint32_t aph = (uint32_t)(t / kAcc) & 1;
+            const int64_t m = (int64_t)m_tile * TC_BM + t128;
+            int64_t orow = m;
+            if (args.out_s != 0 && m < args.M) {
+                const int64_t pq = (int64_t)args.P * args.Q;
+                const int img = (int)(m / pq);
+                const int rem = (int)(m - (int64_t)img * pq);
+                const int p = rem / args.Q, q = rem - p * args.Q;
+                orow = ((int64_t)img * args.out_H + (p * args.out_s + args.out_h0)) * args.out_W + (q * args.out_s + args.out_w0);
+            }
+            mbar_wait(&tfull_bar[acc], aph);
+            tc_fence_after();
+            const uint32_t lane_base = tmem_base + (uint32_t)acc * kAccCols + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(lane_base + (uint32_t)c0, r);
+                if (X3) {
+                    uint32_t r2[32];
+                    tmem_ld32(lane_base + (uint32_t)(BN + c0), r2);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])));
+                }
+                if (m < args.M) {
+                    const int64_t off = orow * args.Cout + n0 + c0;
+                    const float* bs = bias_s + n0 + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 v = make_float4(__uint_as_float(r[j]) + bs[j], __uint_as_float(r[j + 1]) + bs[j + 1],
+                                               __uint_as_float(r[j + 2]) + bs[j + 2], __uint_as_float(r[j + 3]) + bs[j + 3]);
+                        if (args.residual) {
+                            const float4 q = __ldg(reinterpret_cast<const float4*>(args.residual + off + j));
+                            v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+                        }
+                        if (args.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                        if (args.mask_src) {
+                            const float4 q = __ldg(reinterpret_cast<const float4*>(args.mask_src + off + j));
+                            if (!(q.x > 0.f)) v.x = 0.f; if (!(q.y > 0.f)) v.y = 0.f; if (!(q.z > 0.f)) v.z = 0.f; if (!(q.w > 0.f)) v.w = 0.f;
+                        }
+                        *reinterpret_cast<float4*>(args.dst + off + j) = v;
+                    }
+                }
+            }
+            tc_fence_before();                                   // TMEM reads done before the MMA warp may overwrite
+            mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(kTmemCols) : "memory");
     }
@@ -357,18 +588,20 @@ static int make_map_2d(CUtensorMap* map, const float* base, uint64_t rows, uint6
 }
 
 // im2col-mode map over an NHWC activation tensor: 32 channels x 128 pixels per load
-static int make_map_im2col(CUtensorMap* map, const float* base, int N, int H, int W, int C, int R, int S, int stride, int pad) {
+// Bounding box of the window corner in source coordinates: [lower, dim - 1 + upper] per axis (w, h).
+// Forward conv: lower = -pad, upper = pad - (filter - 1) (cutlass/conv/collective/detail.hpp
+// compute_{lower,upper}_corner_whd); a strided data-gradient class uses its own box (see tc_dgrad_class).
+static int make_map_im2col(CUtensorMap* map, const float* base, int N, int H, int W, int C, int lower_w, int lower_h,
+                           int upper_w, int upper_h, int stride) {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
-    // bounding box of the filter-window corner: lower = -pad, upper = pad - (filter - 1)   (dilation 1),
-    // cutlass/conv/collective/detail.hpp compute_{lower,upper}_corner_whd for fprop
-    int lower[2] = {-pad, -pad};
-    int upper[2] = {pad - (S - 1), pad - (R - 1)};
+    int lower[2] = {lower_w, lower_h};
+    int upper[2] = {upper_w, upper_h};
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = g_encode_im2col(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, lower, upper,
                                  TC_BK, TC_BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeIm2col failed (%d) N=%d H=%d W=%d C=%d R=%d stride=%d pad=%d", (int)r, N, H, W, C, R, stride, pad); return I2V_ECUDA; }
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeIm2col failed (%d) N=%d H=%d W=%d C=%d lower=(%d,%d) upper=(%d,%d) stride=%d", (int)r, N, H, W, C, lower_w, lower_h, upper_w, upper_h, stride); return I2V_ECUDA; }
     return I2V_OK;
 }
 
@@ -398,12 +631,13 @@ static int get_map_2d(CUtensorMap* out, const float* base, int rows, int cols, i
     g_maps.emplace(key, *out);
     return I2V_OK;
 }
-static int get_map_im2col(CUtensorMap* out, const float* base, int N, int H, int W, int C, int R, int S, int stride, int pad) {
-    MapKey key{base, N, H, W, C, R, S, stride, 2 + 4 * pad};
+static int get_map_im2col(CUtensorMap* out, const float* base, int N, int H, int W, int C, int lower_w, int lower_h,
+                          int upper_w, int upper_h, int stride) {
+    MapKey key{base, N, H, W, C, (lower_w + 64) * 256 + (lower_h + 64), (upper_w + 64) * 256 + (upper_h + 64), stride, 2};
     std::lock_guard<std::mutex> lk(g_maps_mu);
     auto it = g_maps.find(key);
     if (it != g_maps.end()) { *out = it->second; return I2V_OK; }
-    if (int r = make_map_im2col(out, base, N, H, W, C, R, S, stride, pad)) return r;
+    if (int r = make_map_im2col(out, base, N, H, W, C, lower_w, lower_h, upper_w, upper_h, stride)) return r;
     if (g_maps.size() > 4096) g_maps.clear();
     g_maps.emplace(key, *out);
     return I2V_OK;
@@ -436,56 +670,82 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUt
     return I2V_OK;
 }
 
-}  // namespace i2v
-
-using namespace i2v;
-
-extern "C" int i2v_conv_tc_supported(const i2v_conv_desc* d, int dgrad) {
-    if (!d) return 0;
-    if (d->R != d->S) return 0;
-    if (!dgrad) return (d->Cin % 32 == 0) && (d->Cout % 64 == 0) && d->pad < d->R;
-    // data gradient = forward-style implicit GEMM over dy with the flipped filter: stride 1 only
-    return d->stride == 1 && (d->Cout % 32 == 0) && (d->Cin % 64 == 0) && d->pad < d->R;
+template <int BN, bool X3, bool IM2COL>
+static int tc_launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, const TcArgs& args, cudaStream_t st) {
+    using L = TcSmem<BN, X3>;
+    auto kern = conv_tc_persist_kernel<BN, X3, IM2COL>;
+    static int stages = 0;
+    static size_t smem_fixed = 0;
+    if (stages == 0) {
+        int dev = 0, optin = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        const size_t budget = (size_t)(optin > 0 ? optin : 227 * 1024);
+        smem_fixed = 1024 /*align slack*/ + 512 /*barriers*/ + 2048 * 4 /*bias, Cout <= 2048*/;
+        int s = (int)((budget - smem_fixed) / L::STAGE_BYTES);
+        if (s > 8) s = 8;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_fixed + (size_t)s * L::STAGE_BYTES));
+        if (e != cudaSuccess) return cuda_fail(e, "conv_tc (persistent): shared memory attribute");
+        stages = s;
+    }
+    I2V_REQUIRE(args.Cout <= 2048, "Cout > 2048 not supported by the persistent tensor-core kernel");
+    const int num_m_tiles = (int)((args.M + TC_BM - 1) / TC_BM), num_n_tiles = args.Cout / BN;
+    const int64_t tiles = (int64_t)num_m_tiles * num_n_tiles;
+    const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+    kern<<<grid, TC2_THREADS, smem_fixed + (size_t)stages * L::STAGE_BYTES, st>>>(tmA, tmBhi, tmBlo, args, stages, num_m_tiles, num_n_tiles);
+    I2V_LAUNCH_CHECK("i2v_conv_tc_f32 (persistent)");
+    return I2V_OK;
 }
 
-// Forward:  src = x  [N,H,W,Cin],  dst = y  [N,P,Q,Cout], w_* = [Cout, R*S*Cin]  K-major (tap-major, channel-minor)
-// Dgrad  :  src = dy [N,P,Q,Cout], dst = dx [N,H,W,Cin],  w_* = [Cin, R*S*Cout] with the filter flipped (host)
-extern "C" int i2v_conv_tc_f32(const i2v_conv_desc* d, int dgrad, const float* src, const float* w_hi, const float* w_lo,
-                               const float* bias, const float* residual, const float* mask_src, float* dst, int flags,
-                               i2v_stream_t stream) {
-    I2V_REQUIRE(d && src && w_hi && dst, "null pointer");
-    I2V_REQUIRE(i2v_conv_tc_supported(d, dgrad), "shape not supported by the tensor-core path");
-    if (d->N == 0) return I2V_OK;
+// Common driver: `src` [N,H,W,C] is the gathered tensor, GEMM rows are the (img,p,q) grid, K = taps x C.
+struct TcProblem {
+    const float* src; int N, H, W, C;
+    int P, Q, stride, lower_h, lower_w, upper_h, upper_w, taps_h, taps_w;
+    const float* w_hi; const float* w_lo; int Cout;
+    const float* bias; const float* residual; const float* mask_src; float* dst; int relu;
+    int out_s, out_h0, out_w0, out_H, out_W;
+};
+
+static int tc_run(const TcProblem& pr, cudaStream_t st) {
     if (int r = resolve_driver()) return r;
-    const bool x3 = w_lo != nullptr;
-    int N = d->N, H, W, C, P, Q, Cout, stride, pad;
-    if (!dgrad) { H = d->H; W = d->W; C = d->Cin; P = d->P; Q = d->Q; Cout = d->Cout; stride = d->stride; pad = d->pad; }
-    else        { H = d->P; W = d->Q; C = d->Cout; P = d->H; Q = d->W; Cout = d->Cin; stride = 1; pad = d->R - 1 - d->pad; }
-    const int R = d->R, S = d->S;
-    const bool im2col = !(R == 1 && S == 1 && stride == 1 && pad == 0);
-    I2V_REQUIRE(((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(w_hi) |
-                  reinterpret_cast<uintptr_t>(w_lo) | reinterpret_cast<uintptr_t>(residual) | reinterpret_cast<uintptr_t>(mask_src) |
-                  reinterpret_cast<uintptr_t>(bias)) & 15) == 0, "all tensors must be 16-byte aligned");
-    const int64_t M = (int64_t)N * P * Q;
+    const bool x3 = pr.w_lo != nullptr;
+    const bool im2col = !(pr.taps_h == 1 && pr.taps_w == 1 && pr.stride == 1 && pr.lower_h == 0 && pr.lower_w == 0 &&
+                          pr.P == pr.H && pr.Q == pr.W);
+    I2V_REQUIRE(((reinterpret_cast<uintptr_t>(pr.src) | reinterpret_cast<uintptr_t>(pr.dst) | reinterpret_cast<uintptr_t>(pr.w_hi) |
+                  reinterpret_cast<uintptr_t>(pr.w_lo) | reinterpret_cast<uintptr_t>(pr.residual) | reinterpret_cast<uintptr_t>(pr.mask_src) |
+                  reinterpret_cast<uintptr_t>(pr.bias)) & 15) == 0, "all tensors must be 16-byte aligned");
+    const int64_t M = (int64_t)pr.N * pr.P * pr.Q;
     I2V_REQUIRE(M < (int64_t)0x7fffffff, "too many output pixels for one launch");
+    if (M == 0) return I2V_OK;
     // X3 needs 48 KB (BN=64) or 64 KB (BN=128) per stage: BN=64 keeps two stages in half an SM so that two
     // CTAs are co-resident; plain TF32 has room for BN=128.  I2V_TC_BN=64|128 overrides for experiments.
-    int BN = (Cout % 128 == 0 && !x3) ? 128 : 64;
-    if (const char* e = getenv("I2V_TC_BN")) { int v = atoi(e); if ((v == 64 || v == 128) && Cout % v == 0) BN = v; }
-    const int Ktot = R * S * C;
+    static const bool persistent = !(getenv("I2V_TC_PERSISTENT") && atoi(getenv("I2V_TC_PERSISTENT")) == 0);
+    int BN = (pr.Cout % 128 == 0 && (!x3 || persistent)) ? 128 : 64;
+    if (const char* e = getenv("I2V_TC_BN")) { int v = atoi(e); if ((v == 64 || v == 128) && pr.Cout % v == 0) BN = v; }
+    const int Ktot = pr.taps_h * pr.taps_w * pr.C;
 
     CUtensorMap tmA, tmBhi, tmBlo;
-    if (im2col) { if (int r = get_map_im2col(&tmA, src, N, H, W, C, R, S, stride, pad)) return r; }
-    else        { if (int r = get_map_2d(&tmA, src, (int)M, C, TC_BM)) return r; }
-    if (int r = get_map_2d(&tmBhi, w_hi, Cout, Ktot, BN)) return r;
-    if (x3) { if (int r = get_map_2d(&tmBlo, w_lo, Cout, Ktot, BN)) return r; }
+    if (im2col) { if (int r = get_map_im2col(&tmA, pr.src, pr.N, pr.H, pr.W, pr.C, pr.lower_w, pr.lower_h, pr.upper_w, pr.upper_h, pr.stride)) return r; }
+    else        { if (int r = get_map_2d(&tmA, pr.src, (int)M, pr.C, TC_BM)) return r; }
+    if (int r = get_map_2d(&tmBhi, pr.w_hi, pr.Cout, Ktot, BN)) return r;
+    if (x3) { if (int r = get_map_2d(&tmBlo, pr.w_lo, pr.Cout, Ktot, BN)) return r; }
     else tmBlo = tmBhi;
 
     TcArgs a{};
-    a.bias = bias; a.residual = residual; a.mask_src = mask_src; a.dst = dst;
-    a.M = M; a.Cout = Cout; a.P = P; a.Q = Q; a.stride = stride; a.pad = pad; a.R = R; a.S = S; a.cblocks = C / 32;
-    a.relu = (flags & I2V_EPI_RELU) ? 1 : 0;
-    cudaStream_t st = as_stream(stream);
+    a.bias = pr.bias; a.residual = pr.residual; a.mask_src = pr.mask_src; a.dst = pr.dst;
+    a.M = M; a.Cout = pr.Cout; a.P = pr.P; a.Q = pr.Q; a.stride = pr.stride; a.lower_h = pr.lower_h; a.lower_w = pr.lower_w;
+    a.taps_h = pr.taps_h; a.taps_w = pr.taps_w; a.cblocks = pr.C / 32; a.relu = pr.relu;
+    a.out_s = pr.out_s; a.out_h0 = pr.out_h0; a.out_w0 = pr.out_w0; a.out_H = pr.out_H; a.out_W = pr.out_W;
+#define I2V_TC_DISPATCH_P(BN_)                                                                      \
+    do {                                                                                            \
+        if (x3) return im2col ? tc_launch_persist<BN_, true, true>(tmA, tmBhi, tmBlo, a, st) : tc_launch_persist<BN_, true, false>(tmA, tmBhi, tmBlo, a, st);   \
+        return im2col ? tc_launch_persist<BN_, false, true>(tmA, tmBhi, tmBlo, a, st) : tc_launch_persist<BN_, false, false>(tmA, tmBhi, tmBlo, a, st);          \
+    } while (0)
+    if (persistent) {
+        if (BN == 128) I2V_TC_DISPATCH_P(128);
+        I2V_TC_DISPATCH_P(64);
+    }
+#undef I2V_TC_DISPATCH_P
 #define I2V_TC_DISPATCH(BN_)                                                                        \
     do {                                                                                            \
         if (x3) return im2col ? tc_launch<BN_, true, true>(tmA, tmBhi, tmBlo, a, st) : tc_launch<BN_, true, false>(tmA, tmBhi, tmBlo, a, st);   \
@@ -494,4 +754,74 @@ extern "C" int i2v_conv_tc_f32(const i2v_conv_desc* d, int dgrad, const float* s
     if (BN == 128) I2V_TC_DISPATCH(128);
     I2V_TC_DISPATCH(64);
 #undef I2V_TC_DISPATCH
+}
+
+}  // namespace i2v
+
+using namespace i2v;
+
+extern "C" int i2v_conv_tc_supported(const i2v_conv_desc* d, int dgrad) {
+    if (!d) return 0;
+    if (d->R != d->S || d->pad >= d->R) return 0;
+    if (!dgrad) return (d->Cin % 32 == 0) && (d->Cout % 64 == 0);
+    // stride 1: a forward-style implicit GEMM over dy with the flipped filter (i2v_conv_tc_f32, dgrad = 1);
+    // stride > 1: one launch per stride-parity class (i2v_conv_tc_dgrad_class_f32)
+    return (d->Cout % 32 == 0) && (d->Cin % 64 == 0) && d->stride >= 1 && d->stride <= 4;
+}
+
+// Forward:  src = x  [N,H,W,Cin],  dst = y  [N,P,Q,Cout], w_* = [Cout, R*S*Cin]  K-major (tap-major, channel-minor)
+// Dgrad  :  src = dy [N,P,Q,Cout], dst = dx [N,H,W,Cin],  w_* = [Cin, R*S*Cout] with the filter flipped (host); stride 1
+extern "C" int i2v_conv_tc_f32(const i2v_conv_desc* d, int dgrad, const float* src, const float* w_hi, const float* w_lo,
+                               const float* bias, const float* residual, const float* mask_src, float* dst, int flags,
+                               i2v_stream_t stream) {
+    I2V_REQUIRE(d && src && w_hi && dst, "null pointer");
+    I2V_REQUIRE(i2v_conv_tc_supported(d, dgrad) && (!dgrad || d->stride == 1), "shape not supported by this tensor-core entry point");
+    if (d->N == 0) return I2V_OK;
+    TcProblem pr{};
+    pr.src = src; pr.N = d->N; pr.w_hi = w_hi; pr.w_lo = w_lo; pr.bias = bias; pr.residual = residual; pr.mask_src = mask_src;
+    pr.dst = dst; pr.relu = (flags & I2V_EPI_RELU) ? 1 : 0;
+    pr.taps_h = d->R; pr.taps_w = d->S;
+    if (!dgrad) {
+        pr.H = d->H; pr.W = d->W; pr.C = d->Cin; pr.P = d->P; pr.Q = d->Q; pr.Cout = d->Cout; pr.stride = d->stride;
+        pr.lower_h = pr.lower_w = -d->pad; pr.upper_h = d->pad - (d->R - 1); pr.upper_w = d->pad - (d->S - 1);
+    } else {
+        const int padp = d->R - 1 - d->pad;
+        pr.H = d->P; pr.W = d->Q; pr.C = d->Cout; pr.P = d->H; pr.Q = d->W; pr.Cout = d->Cin; pr.stride = 1;
+        pr.lower_h = pr.lower_w = -padp; pr.upper_h = padp - (d->R - 1); pr.upper_w = padp - (d->S - 1);
+    }
+    return tc_run(pr, as_stream(stream));
+}
+
+// Strided data gradient, one stride-parity class per call.  Image rows h = stride*i + ph (columns likewise)
+// receive only the filter taps r = r0 + stride*a with r0 = (ph + pad) mod stride, from dy row
+// i + (ph + pad - r0)/stride - a: a dense, stride-1 problem over dy with A_h x A_w taps whose output rows are
+// scattered with pitch `stride` into dx.  w_* = [Cin, (tap_h, tap_w, co)] with tap_h = A_h-1-a (host: see
+// engine_native._class_weights).  Classes without taps (e.g. the odd rows of a 1x1/s2 conv) receive no gradient
+// from this conv: the call is a no-op for them and the caller owns their contents (addend already in place).
+extern "C" int i2v_conv_tc_dgrad_class_f32(const i2v_conv_desc* d, int ph, int pw, const float* dy, const float* w_hi,
+                                           const float* w_lo, const float* addend, const float* mask_src, float* dx,
+                                           i2v_stream_t stream) {
+    I2V_REQUIRE(d && dy && dx, "null pointer");
+    I2V_REQUIRE(i2v_conv_tc_supported(d, 1), "shape not supported by the tensor-core path");
+    const int st = d->stride;
+    I2V_REQUIRE(ph >= 0 && ph < st && pw >= 0 && pw < st, "class index out of range");
+    if (d->N == 0) return I2V_OK;
+    const int r0 = (ph + d->pad) % st, s0 = (pw + d->pad) % st;
+    const int Ah = r0 < d->R ? (d->R - 1 - r0) / st + 1 : 0;
+    const int Aw = s0 < d->S ? (d->S - 1 - s0) / st + 1 : 0;
+    const int Hc = ph < d->H ? (d->H - 1 - ph) / st + 1 : 0;
+    const int Wc = pw < d->W ? (d->W - 1 - pw) / st + 1 : 0;
+    if (Ah == 0 || Aw == 0 || Hc == 0 || Wc == 0) return I2V_OK;
+    I2V_REQUIRE(w_hi, "null weight pointer");
+    const int ch = (ph + d->pad - r0) / st, cw = (pw + d->pad - s0) / st;
+    TcProblem pr{};
+    pr.src = dy; pr.N = d->N; pr.H = d->P; pr.W = d->Q; pr.C = d->Cout;
+    pr.P = Hc; pr.Q = Wc; pr.stride = 1;
+    pr.lower_h = ch - (Ah - 1); pr.lower_w = cw - (Aw - 1);
+    pr.upper_h = pr.lower_h + Hc - d->P; pr.upper_w = pr.lower_w + Wc - d->Q;
+    pr.taps_h = Ah; pr.taps_w = Aw;
+    pr.w_hi = w_hi; pr.w_lo = w_lo; pr.Cout = d->Cin;
+    pr.bias = nullptr; pr.residual = addend; pr.mask_src = mask_src; pr.dst = dx; pr.relu = 0;
+    pr.out_s = st; pr.out_h0 = ph; pr.out_w0 = pw; pr.out_H = d->H; pr.out_W = d->W;
+    return tc_run(pr, as_stream(stream));
 }

@@ -63,6 +63,8 @@ class _Conv:
         td = ws.flip(2, 3).permute(1, 2, 3, 0).reshape(cin, R * S * cout).contiguous()
         self.tc_fwd = _split_tf32(tf)
         self.tc_dgrad = _split_tf32(td)
+        # strided data gradient: one weight matrix per stride-parity class (see i2v_conv_tc_dgrad_class_f32)
+        self.tc_dgrad_cls = _class_weights(ws, self.stride, self.pad) if self.stride > 1 and not x_nchw else None
         # first layer (Cin = 3): [(c,r,s), co] for the stem forward; its dgrad uses b_fwd = [(r,s), c, co]
         self.w_stem = ws.permute(1, 2, 3, 0).reshape(cin * R * S, cout).contiguous() if x_nchw else None
 
@@ -106,6 +108,24 @@ def _split_tf32(w):
     lo = (w - hi).contiguous()
     rna = ((bits + 4096) & -8192).view(torch.float32)
     return hi.contiguous(), lo, rna.contiguous()
+
+
+def _class_weights(ws, stride, pad):
+    """{(ph, pw): (hi, lo, rna) of [ci, (tap_h, tap_w, co)] or None}: rows h = stride*i + ph only see the taps
+    r = r0 + stride*a (r0 = (ph + pad) mod stride); tap_h = A_h-1-a, so the tap order is r descending."""
+    cout, cin, R, S = ws.shape
+    out = {}
+    for ph in range(stride):
+        rs = list(range((ph + pad) % stride, R, stride))[::-1]
+        for pw in range(stride):
+            ss = list(range((pw + pad) % stride, S, stride))[::-1]
+            if not rs or not ss:
+                out[(ph, pw)] = None
+                continue
+            sel = ws[:, :, rs, :][:, :, :, ss]                      # [co, ci, A_h, A_w]
+            b = sel.permute(1, 2, 3, 0).reshape(cin, len(rs) * len(ss) * cout).contiguous()
+            out[(ph, pw)] = _split_tf32(b)
+    return out
 
 
 def _pad_cols(m):
@@ -315,9 +335,20 @@ class NativeEngine:
     def _conv_dgrad(self, op, d, dy, addend, mask_src, dx):
         if op.x_nchw and addend is None and mask_src is None and self.use_stem and capi.conv_stem_supported(d):
             capi.conv_stem_dgrad(d, dy, op.b_fwd, dx)
-        elif self.use_tc and not op.x_nchw and capi.conv_tc_supported(d, 1):
+        elif self.use_tc and not op.x_nchw and op.stride == 1 and capi.conv_tc_supported(d, 1):
             hi, lo, rna = op.tc_dgrad
             capi.conv_tc(d, 1, dy, hi if self.tf32x3 else rna, lo if self.tf32x3 else None, None, addend, mask_src, dx)
+        elif (self.use_tc and not op.x_nchw and op.stride > 1 and capi.conv_tc_supported(d, 1)
+              and (addend is None or addend is dx or all(v is not None for v in op.tc_dgrad_cls.values()))):
+            # strided: one dense launch per stride-parity class; classes without taps keep what is there
+            if addend is None and any(v is None for v in op.tc_dgrad_cls.values()):
+                dx.zero_()
+            for (ph, pw), wt in op.tc_dgrad_cls.items():
+                if wt is None:
+                    continue
+                hi, lo, rna = wt
+                capi.conv_tc_dgrad_class(d, ph, pw, dy, hi if self.tf32x3 else rna, lo if self.tf32x3 else None,
+                                         addend, mask_src, dx)
         else:
             capi.conv_dgrad_simt(d, dy, op.b_dgrad, addend, mask_src, dx, x_nchw=op.x_nchw)
 

@@ -204,6 +204,15 @@ int i2v_conv_tc_f32(const i2v_conv_desc* d, int dgrad, const float* src, const f
                     const float* bias, const float* residual, const float* mask_src, float* dst, int flags,
                     i2v_stream_t stream);
 
+/* Strided data gradient on the tensor cores, one stride-parity class (ph, pw) per call: image rows
+ * h = stride*i + ph receive only the taps r = r0 + stride*a, r0 = (ph + pad) mod stride, from dy row
+ * i + (ph + pad - r0)/stride - a — a dense stride-1 implicit GEMM over dy whose output rows are scattered
+ * with pitch `stride` into dx.  w_* = [Cin, (tap_h, tap_w, co)], tap_h = A_h-1-a (hi/lo split as above).
+ * Classes without taps are a no-op (their pixels get no gradient from this conv).                       */
+int i2v_conv_tc_dgrad_class_f32(const i2v_conv_desc* d, int ph, int pw, const float* dy, const float* w_hi,
+                                const float* w_lo, const float* addend, const float* mask_src, float* dx,
+                                i2v_stream_t stream);
+
 /* k x k max pooling (stride, -inf padding), NHWC, C % 4 == 0.  argmax[N,P,Q,C] = r*k+s of the FIRST
  * maximum in window scan order (torch.nn.MaxPool2d); backward is the gather form (no atomics) and can
  * apply the ReLU-backward mask of the pooled tensor's producer.  torchvision resnet.maxpool (3,2,1),
