@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--engine", default=None, help="cudnn | cudnn_tf32 | native | native_tf32 (default: $I2V_ENGINE)")
+    ap.add_argument("--engine", default=None, help="native | native_tf32 | cudnn | cudnn_tf32 (default: $I2V_ENGINE or native)")
     ap.add_argument("--clips", type=int, default=CLIPS_PER_GPU, help="clips per GPU (default 16 = 512 frames)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -238,11 +238,12 @@ def run_b200_arm(args):
 
     # ---- per-kernel device time of OUR kernels inside the timed region (CUDA events, same stream) -----
     kern = {}
-    for name, e0, e1, nbytes in events:
-        k = kern.setdefault(name, {"ms": 0.0, "launches": 0, "bytes": 0})
+    for name, e0, e1, nbytes, flops in events:
+        k = kern.setdefault(name, {"ms": 0.0, "launches": 0, "bytes": 0, "flops": 0.0})
         k["ms"] += e0.elapsed_time(e1)
         k["launches"] += 1
         k["bytes"] += nbytes
+        k["flops"] += flops
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -250,6 +251,10 @@ def run_b200_arm(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    # tensor roofline for the TF32 convolutions: the kernel runs inside a long step => sustained bf16 figure; TF32
+    # issues at half the bf16 rate on the 5th-generation tensor cores (nominal 1.1 vs 2.25 PFLOP/s dense)
+    bf16_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    tf32_peak = bf16_peak / 2
     traffic = {}
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
@@ -260,11 +265,19 @@ def run_b200_arm(args):
         if k["ms"] <= 0:
             continue
         gbs = k["bytes"] / (k["ms"] * 1e-3) / 1e9
-        roof_all[name] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                          "launches": k["launches"], "avg_us": 1e3 * k["ms"] / k["launches"],
-                          "algorithmic_bytes_per_launch": k["bytes"] / k["launches"],
-                          "share_of_step": k["ms"] / ms_local,
-                          "traffic": traffic.get(name)}
+        r = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+             "launches": k["launches"], "avg_us": 1e3 * k["ms"] / k["launches"],
+             "algorithmic_bytes_per_launch": k["bytes"] / k["launches"],
+             "share_of_step": k["ms"] / ms_local, "traffic": traffic.get(name)}
+        if k["flops"] > 0:
+            tfl = k["flops"] / (k["ms"] * 1e-3) / 1e12
+            mma = 3.0 if engine_name == "native" else 1.0
+            r["tensor"] = {"achieved_algorithmic": tfl, "issued": tfl * mma, "peak": tf32_peak, "unit": "TFLOP/s",
+                           "frac_algorithmic": tfl / tf32_peak, "frac_issued": tfl * mma / tf32_peak,
+                           "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 issue rate)",
+                           "algorithmic_flops_per_launch": k["flops"] / k["launches"],
+                           "note": "FP32-parity mode issues 3 TF32 MMAs per algorithmic MAC" if mma == 3.0 else "plain TF32"}
+        roof_all[name] = r
     dominant = max(roof_all, key=lambda n: kern[n]["ms"]) if roof_all else None
     roofline = dict(roof_all[dominant], kernel=dominant, peak_source=peak_kind) if dominant else None
 

@@ -170,9 +170,11 @@ class ImageGuidedRun:
         capi.layer_sums(self.cos, self.coeffs if adaptive else None, self.prev, self.cost_log, self.step_idx,
                         mode=1 if adaptive else 0, coef_CE=self.coef_CE)
         if self.tap is not None:
+            # relu_masks: the activity decisions of this step's forward (valid when all frames fit one chunk)
+            masks = [e.relu_masks() if hasattr(e, "relu_masks") and len(self.spans) == 1 else None for e in self.engines]
             self.tap(self.step_no, dict(g=self.g_total.clone(), cos=self.cos.clone(), mod_before=self.mod.clone(),
                                         m_before=self.m.clone(), v_before=self.v.clone(),
-                                        true_image=self.true_img.clone()))
+                                        true_image=self.true_img.clone(), relu_masks=masks))
         capi.adam_compose_table(self.g_total, self.m, self.v, self.mod, self.x, self.true_img, self.epsilon, self.inner,
                                 self.table, self.step_idx, BETA1, BETA2, ADAM_EPS)
         capi.step_advance(self.step_idx)

@@ -43,6 +43,7 @@ SIGNATURES = {
     "i2v_conv_stem_fwd_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_stem_dgrad_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p], _c_int),
     "i2v_conv_tc_supported": ([_c_p, _c_int], _c_int),
+    "i2v_conv_tc_set_trace": ([_c_p, _c_int], _c_int),
     "i2v_conv_tc_f32": ([_c_p, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_tc_dgrad_class_f32": ([_c_p, _c_int, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p], _c_int),
     "i2v_maxpool_fwd_f32": ([_c_p, _c_p, _c_p] + [_c_int] * 9 + [_c_p], _c_int),
@@ -85,18 +86,21 @@ def load():
 
 # Launch accounting for bench.py: every successful kernel-launching call bumps LAUNCHES[name]; with
 # PROFILE_EVENTS set to a list, (name, start_event, end_event, bytes) tuples are appended so the
-# benchmark can time each kernel on the launching stream with CUDA events.
+# benchmark can time each kernel on the launching stream with CUDA events (bytes / flops = ALGORITHMIC figures of
+# tensors read + written once, 2 x MACs of the convolution).
 LAUNCHES = {}
 PROFILE_EVENTS = None
-_NO_KERNEL = ("i2v_device_check", "i2v_adam_step_table", "i2v_conv_tc_supported", "i2v_conv_stem_supported")
+_NO_KERNEL = ("i2v_device_check", "i2v_adam_step_table", "i2v_conv_tc_supported", "i2v_conv_stem_supported",
+              "i2v_conv_tc_set_trace")
 
 
 class _Timed:
-    __slots__ = ("name", "nbytes", "ev")
+    __slots__ = ("name", "nbytes", "flops", "ev")
 
-    def __init__(self, name, nbytes=0):
+    def __init__(self, name, nbytes=0, flops=0):
         self.name = name
         self.nbytes = nbytes
+        self.flops = flops
         self.ev = None
 
     def __enter__(self):
@@ -109,7 +113,7 @@ class _Timed:
         if self.ev is not None and exc[0] is None:
             end = torch.cuda.Event(enable_timing=True)
             end.record()
-            PROFILE_EVENTS.append((self.name, self.ev, end, self.nbytes))
+            PROFILE_EVENTS.append((self.name, self.ev, end, self.nbytes, self.flops))
         return False
 
 
@@ -249,6 +253,15 @@ def layer_sums(cos, coeffs=None, prev=None, cost_log=None, step_idx=None, mode=0
                                      L, N, mode, int(coef_CE), _stream()), "i2v_layer_sums_f32")
 
 
+# ------------------------------------------------------------------------------- K4 / K5 accounting
+def _conv_cost(d):
+    """(algorithmic bytes, flops) of one convolution launch: input + output once, 2 x MACs."""
+    nin = d.N * d.H * d.W * d.Cin
+    nout = d.N * d.P * d.Q * d.Cout
+    flops = 2.0 * nout * d.Cin * d.R * d.S
+    return 4 * (nin + nout), flops
+
+
 # ------------------------------------------------------------------------------- K4 / K5 (CUDA-core path)
 def conv_fwd_simt(desc, x, bmat, bias, residual, y, relu=False, x_nchw=False):
     flags = (EPI_RELU if relu else 0) | (LAYOUT_X_NCHW if x_nchw else 0)
@@ -267,13 +280,22 @@ def conv_stem_supported(desc):
 
 
 def conv_stem_fwd(desc, x, w, bias, y, relu=True):
-    _check(load().i2v_conv_stem_fwd_f32(ctypes.addressof(desc), _dev(x), _dev(w), _dev(bias), _dev(y),
-                                        EPI_RELU if relu else 0, _stream()), "i2v_conv_stem_fwd_f32")
+    nb, fl = _conv_cost(desc)
+    with _Timed("i2v_conv_stem_fwd_f32", nb, fl):
+        _check(load().i2v_conv_stem_fwd_f32(ctypes.addressof(desc), _dev(x), _dev(w), _dev(bias), _dev(y),
+                                            EPI_RELU if relu else 0, _stream()), "i2v_conv_stem_fwd_f32")
 
 
 def conv_stem_dgrad(desc, dy, w, dx):
-    _check(load().i2v_conv_stem_dgrad_f32(ctypes.addressof(desc), _dev(dy), _dev(w), _dev(dx), _stream()),
-           "i2v_conv_stem_dgrad_f32")
+    nb, fl = _conv_cost(desc)
+    with _Timed("i2v_conv_stem_dgrad_f32", nb, fl):
+        _check(load().i2v_conv_stem_dgrad_f32(ctypes.addressof(desc), _dev(dy), _dev(w), _dev(dx), _stream()),
+               "i2v_conv_stem_dgrad_f32")
+
+
+def conv_tc_set_trace(buf, tiles=0):
+    """Debug: buf = int64 CUDA tensor [tiles, 8] (or None) receiving CTA 0's pipeline time stamps."""
+    _check(load().i2v_conv_tc_set_trace(None if buf is None else _dev(buf, torch.int64), tiles), "i2v_conv_tc_set_trace")
 
 
 def conv_tc_supported(desc, dgrad):
@@ -282,30 +304,41 @@ def conv_tc_supported(desc, dgrad):
 
 def conv_tc(desc, dgrad, src, w_hi, w_lo, bias, residual, mask_src, dst, relu=False):
     """Tensor-core implicit GEMM (tcgen05/TMEM/TMA).  w_lo=None -> plain TF32, else 3xTF32 FP32-parity mode."""
-    _check(load().i2v_conv_tc_f32(ctypes.addressof(desc), int(dgrad), _dev(src), _dev(w_hi), _dev(w_lo), _dev(bias),
-                                  _dev(residual), _dev(mask_src), _dev(dst), EPI_RELU if relu else 0, _stream()),
-           "i2v_conv_tc_f32")
+    nb, fl = _conv_cost(desc)
+    nb += 4 * dst.numel() * ((residual is not None and residual is not dst) + (mask_src is not None))
+    with _Timed("i2v_conv_tc_f32", nb, fl):
+        _check(load().i2v_conv_tc_f32(ctypes.addressof(desc), int(dgrad), _dev(src), _dev(w_hi), _dev(w_lo), _dev(bias),
+                                      _dev(residual), _dev(mask_src), _dev(dst), EPI_RELU if relu else 0, _stream()),
+               "i2v_conv_tc_f32")
 
 
 def conv_tc_dgrad_class(desc, ph, pw, dy, w_hi, w_lo, addend, mask_src, dx):
     """One stride-parity class of a strided data gradient on the tensor cores (see include/i2v_b200.h)."""
-    _check(load().i2v_conv_tc_dgrad_class_f32(ctypes.addressof(desc), ph, pw, _dev(dy), _dev(w_hi), _dev(w_lo),
-                                              _dev(addend), _dev(mask_src), _dev(dx), _stream()),
-           "i2v_conv_tc_dgrad_class_f32")
+    # one stride-parity class: dy once, 1/stride^2 of dx (+ mask, + addend) and of the taps
+    st2 = desc.stride * desc.stride
+    nb, fl = _conv_cost(desc)
+    nout = desc.N * desc.P * desc.Q * desc.Cout
+    nb = 4 * nout + 4 * (dx.numel() // st2) * (1 + (addend is not None) + (mask_src is not None))
+    with _Timed("i2v_conv_tc_dgrad_class_f32", nb, fl / st2):
+        _check(load().i2v_conv_tc_dgrad_class_f32(ctypes.addressof(desc), ph, pw, _dev(dy), _dev(w_hi), _dev(w_lo),
+                                                  _dev(addend), _dev(mask_src), _dev(dx), _stream()),
+               "i2v_conv_tc_dgrad_class_f32")
 
 
 def maxpool_fwd(x, y, argmax, k, stride, pad):
     N, H, W, C = x.shape
     _, P, Q, _ = y.shape
-    _check(load().i2v_maxpool_fwd_f32(_dev(x), _dev(y), _dev(argmax, torch.uint8), N, H, W, C, P, Q, k, stride, pad,
-                                      _stream()), "i2v_maxpool_fwd_f32")
+    with _Timed("i2v_maxpool_fwd_f32", 4 * x.numel() + 5 * y.numel()):
+        _check(load().i2v_maxpool_fwd_f32(_dev(x), _dev(y), _dev(argmax, torch.uint8), N, H, W, C, P, Q, k, stride, pad,
+                                          _stream()), "i2v_maxpool_fwd_f32")
 
 
 def maxpool_bwd(dy, argmax, mask_src, dx, k, stride, pad, accumulate=False):
     N, H, W, C = dx.shape
     _, P, Q, _ = dy.shape
-    _check(load().i2v_maxpool_bwd_f32(_dev(dy), _dev(argmax, torch.uint8), _dev(mask_src), _dev(dx), N, H, W, C, P, Q,
-                                      k, stride, pad, int(accumulate), _stream()), "i2v_maxpool_bwd_f32")
+    with _Timed("i2v_maxpool_bwd_f32", 5 * dy.numel() + 4 * dx.numel() * (1 + (mask_src is not None) + bool(accumulate))):
+        _check(load().i2v_maxpool_bwd_f32(_dev(dy), _dev(argmax, torch.uint8), _dev(mask_src), _dev(dx), N, H, W, C, P, Q,
+                                          k, stride, pad, int(accumulate), _stream()), "i2v_maxpool_bwd_f32")
 
 
 def copy_channels(src, dst, src_off, dst_off, ccopy, accumulate=False):

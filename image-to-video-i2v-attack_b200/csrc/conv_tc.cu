@@ -57,7 +57,18 @@ struct TcArgs {
     int relu;
     // output row of GEMM row (img,p,q): ((img*out_H + p*out_s + out_h0)*out_W + q*out_s + out_w0); identity when out_s == 0
     int out_s, out_h0, out_w0, out_H, out_W;
+    // pipeline trace (debug, i2v_conv_tc_set_trace): CTA 0 stamps clock64() at 8 points of each of its first
+    // trace_tiles tiles — [tile][0] producer starts the tile, [1] producer issued its last load, [2] MMA warp owns
+    // an accumulator, [3] first operands landed (and split), [4] last MMA issued, [5] epilogue sees the
+    // accumulator, [6] epilogue done, [7] split warps done with the tile
+    unsigned long long* trace;
+    int trace_tiles;
 };
+#define TC_TRACE(slot, tile_no)                                                                          \
+    do {                                                                                                   \
+        if (args.trace && blockIdx.x == 0 && (tile_no) < args.trace_tiles)                                 \
+            args.trace[(size_t)(tile_no) * 8 + (slot)] = (unsigned long long)clock64();                    \
+    } while (0)
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -140,6 +151,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
                  : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+// 16 TMEM lanes x 16 columns per warp: thread t holds row t/4 (regs 4j+e) and row t/4+8 (regs 4j+2+e) of the lane
+// window, columns 8j + 2(t%4) + e (cute SM100_TMEM_LOAD_16dp256b2x) -- a quad owns 32 contiguous bytes of a row, so the
+// epilogue's global loads / stores are whole 32-byte sectors.  No wait: callers batch several loads per wait.
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 template <int BN, bool X3>
 struct TcSmem {
@@ -336,9 +357,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // which has its own four warps.  Removes the per-tile launch / TMEM-allocation / pipeline-fill bubbles that
 // dominate v1 on the many small-K 1x1 convolutions (measured v1: 2.2 us per 128x64 tile at K = 64).
 //   warp 0: TMA producer   warp 1: MMA issuer   warp 2: TMEM allocator   warps 4-7: A split (3xTF32)
-//   warps 8-11: epilogue (warp w owns TMEM lanes 32*(w%4)..+31)
+//   warps 8-15: epilogue.  Warp w owns TMEM lanes 32*(w%4)..+31 and the 16-column units u = (w-8)/4, +2, ...
+//   of the tile.  TMEM is read with the 16x256b shape (a quad of threads = 8 consecutive columns of one row), so
+//   residual / mask loads and the output stores are float2 accesses that fill whole 32-byte sectors; the loads of
+//   unit u+1 are issued before unit u is processed (and the first unit's before the accumulator is even
+//   complete), which is what keeps the HBM-bound 1x1 convolutions with a residual from serialising on latency
+//   (measured with the one-row-per-thread epilogue: 141 us for layer1.conv3 on 32 frames, 6.8 % tensor-pipe active).
+// 3xTF32 issue order per 8-wide k slice: one N = 2*BN instruction a_hi x [b_hi | b_lo] (B_hi and B_lo are adjacent
+// in the stage, main and cross accumulators are adjacent in TMEM), then a_lo x b_hi into the cross accumulator.
 // ---------------------------------------------------------------------------------------------
-constexpr int TC2_THREADS = 384;
+constexpr int TC2_THREADS = 512;
+constexpr int TC2_EPI_THREADS = 256;
 
 template <int BN, bool X3, bool IM2COL>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
@@ -379,7 +408,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
         for (int a = 0; a < kAcc; ++a) {
             mbar_init(&tfull_bar[a], 1);
-            mbar_init(&tempty_bar[a], 128);
+            mbar_init(&tempty_bar[a], TC2_EPI_THREADS);
         }
         fence_barrier_init();
     }
@@ -396,8 +425,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     if (warp == 0) {
         // ===== TMA producer: runs ahead across tiles, bounded only by the smem ring ===================
         if (lane == 0) {
-            int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int it = 0, tno = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tno) {
                 const int m_tile = tile / num_n_tiles, n_tile = tile - m_tile * num_n_tiles;
                 const int64_t m0 = (int64_t)m_tile * TC_BM;
                 const int n0 = n_tile * BN;
@@ -416,6 +445,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                             const int st = it % stages;
                             const uint32_t ph = (uint32_t)(it / stages) & 1;
                             mbar_wait(&empty_bar[st], ph ^ 1);
+                            if ((r | s | cb) == 0) TC_TRACE(0, tno);
                             mbar_arrive_expect_tx(&full_bar[st], TC_A_BYTES + L::B_BYTES * (X3 ? 2 : 1));
                             if (IM2COL) tma_load_im2col_4d(&tmA, &full_bar[st], stage_a(st), cb * TC_BK, base_w, base_h, img, (uint16_t)s, (uint16_t)r);
                             else        tma_load_2d(&tmA, &full_bar[st], stage_a(st), cb * TC_BK, (int)m0);
@@ -423,18 +453,21 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                             tma_load_2d(&tmBhi, &full_bar[st], stage_bhi(st), kcol, n0);
                             if (X3) tma_load_2d(&tmBlo, &full_bar[st], stage_blo(st), kcol, n0);
                         }
+                TC_TRACE(1, tno);
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer ==============================================================================
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_tf32(BN);
+            constexpr uint32_t idesc2 = umma_idesc_tf32(2 * BN);
             int it = 0, t = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
                 const int acc = t % kAcc;
                 const uint32_t aph = (uint32_t)(t / kAcc) & 1;
                 mbar_wait(&tempty_bar[acc], aph ^ 1);          // epilogue has drained this accumulator stage
                 tc_fence_after();
+                TC_TRACE(2, t);
                 const uint32_t d0 = tmem_base + (uint32_t)acc * kAccCols;
                 for (int kb = 0; kb < kiters; ++kb, ++it) {
                     const int st = it % stages;
@@ -442,29 +475,33 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     mbar_wait(&full_bar[st], ph);
                     if (X3) mbar_wait(&split_bar[st], ph);
                     tc_fence_after();
+                    if (kb == 0) TC_TRACE(3, t);
                     const uint64_t da = umma_desc_sw128(smem_u32(stage_a(st)));
                     const uint64_t dbh = umma_desc_sw128(smem_u32(stage_bhi(st)));
-                    uint64_t dal = 0, dbl = 0;
-                    if (X3) { dal = umma_desc_sw128(smem_u32(stage_alo(st))); dbl = umma_desc_sw128(smem_u32(stage_blo(st))); }
+                    uint64_t dal = 0;
+                    if (X3) dal = umma_desc_sw128(smem_u32(stage_alo(st)));
 #pragma unroll
                     for (int kk = 0; kk < TC_BK / 8; ++kk) {
-                        umma_tf32(d0, da + 2 * kk, dbh + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
                         if (X3) {
-                            umma_tf32(d0 + BN, dal + 2 * kk, dbh + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
-                            umma_tf32(d0 + BN, da + 2 * kk, dbl + 2 * kk, idesc, 1u);
+                            // [main | cross] += a_hi x [b_hi | b_lo]  (N = 2*BN), then cross += a_lo x b_hi
+                            umma_tf32(d0, da + 2 * kk, dbh + 2 * kk, idesc2, (kb | kk) ? 1u : 0u);
+                            umma_tf32(d0 + BN, dal + 2 * kk, dbh + 2 * kk, idesc, 1u);
+                        } else {
+                            umma_tf32(d0, da + 2 * kk, dbh + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
                         }
                     }
                     umma_commit(&empty_bar[st]);
                 }
                 umma_commit(&tfull_bar[acc]);
+                TC_TRACE(4, t);
             }
         }
     } else if (warp >= 4 && warp < 8) {
         // ===== A split (3xTF32 only) ====================================================================
         if (X3) {
             const int t128 = threadIdx.x - 128;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+            int it = 0, tno = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tno) {
                 for (int kb = 0; kb < kiters; ++kb, ++it) {
                     const int st = it % stages;
                     const uint32_t ph = (uint32_t)(it / stages) & 1;
@@ -483,59 +520,98 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     fence_proxy_async();
                     mbar_arrive(&split_bar[st]);
                 }
+                if (t128 == 0) TC_TRACE(7, tno);
+            }
         }
     } else if (warp >= 8) {
         // ===== epilogue =================================================================================
-        const int t128 = threadIdx.x - 256;                     // TMEM lane = tile row
+        constexpr int UNITS = BN / 32;                          // 16-column units per warp (two warps per lane quarter)
+        const int quarter = warp & 3;                           // TMEM lanes 32*quarter .. +31
+        const int uhalf = (warp - 8) >> 2;                      // this warp's units: uhalf, uhalf + 2, ...
+        const int lr = lane >> 2, lc = (lane & 3) * 2;
+        const float* __restrict__ resid = args.residual;
+        const float* __restrict__ masks = args.mask_src;
         int t = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
             const int m_tile = tile / num_n_tiles, n_tile = tile - m_tile * num_n_tiles;
             const int n0 = n_tile * BN;
             const int acc = t % kAcc;
             const uint32_t aph = (uint32_t)(t / kAcc) & 1;
-            const int64_t m = (int64_t)m_tile * TC_BM + t128;
-            int64_t orow = m;
-            if (args.out_s != 0 && m < args.M) {
-                const int64_t pq = (int64_t)args.P * args.Q;
-                const int img = (int)(m / pq);
-                const int rem = (int)(m - (int64_t)img * pq);
-                const int p = rem / args.Q, q = rem - p * args.Q;
-                orow = ((int64_t)img * args.out_H + (p * args.out_s + args.out_h0)) * args.out_W + (q * args.out_s + args.out_w0);
+            // this thread's four rows: (i, h) -> tile row 32*quarter + 16*i + 8*h + lr
+            int64_t off[4];
+            bool valid[4];
+#pragma unroll
+            for (int ih = 0; ih < 4; ++ih) {
+                const int64_t m = (int64_t)m_tile * TC_BM + quarter * 32 + (ih >> 1) * 16 + (ih & 1) * 8 + lr;
+                valid[ih] = m < args.M;
+                int64_t orow = m;
+                if (args.out_s != 0 && valid[ih]) {
+                    const int64_t pq = (int64_t)args.P * args.Q;
+                    const int img = (int)(m / pq);
+                    const int rem = (int)(m - (int64_t)img * pq);
+                    const int p = rem / args.Q, q = rem - p * args.Q;
+                    orow = ((int64_t)img * args.out_H + (p * args.out_s + args.out_h0)) * args.out_W + (q * args.out_s + args.out_w0);
+                }
+                off[ih] = orow * args.Cout + n0 + lc;
             }
+            float2 res[2][8], mk[2][8];                         // [buffer][(i,h) x j]
+            auto prefetch = [&](int buf, int c0) {
+#pragma unroll
+                for (int ih = 0; ih < 4; ++ih)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        float2 r = make_float2(0.f, 0.f), q = make_float2(1.f, 1.f);
+                        if (valid[ih]) {
+                            if (resid) r = __ldg(reinterpret_cast<const float2*>(resid + off[ih] + c0 + 8 * j));
+                            if (masks) q = __ldg(reinterpret_cast<const float2*>(masks + off[ih] + c0 + 8 * j));
+                        }
+                        res[buf][ih * 2 + j] = r;
+                        mk[buf][ih * 2 + j] = q;
+                    }
+            };
+            prefetch(0, uhalf * 16);                            // independent of the accumulator: issued before the wait
             mbar_wait(&tfull_bar[acc], aph);
             tc_fence_after();
-            const uint32_t lane_base = tmem_base + (uint32_t)acc * kAccCols + ((uint32_t)((warp & 3) * 32) << 16);
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld32(lane_base + (uint32_t)c0, r);
+            if (threadIdx.x == 256) TC_TRACE(5, t);
+            const uint32_t tacc = tmem_base + (uint32_t)acc * kAccCols + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll
+            for (int uu = 0; uu < UNITS; ++uu) {
+                const int c0 = (uhalf + 2 * uu) * 16;
+                if (uu + 1 < UNITS) prefetch((uu + 1) & 1, c0 + 32);
+                uint32_t a0[8], a1[8];                          // rows +0..15 and +16..31 of the quarter
+                tmem_ld_16x256b_x2(tacc + (uint32_t)c0, a0);
+                tmem_ld_16x256b_x2(tacc + (16u << 16) + (uint32_t)c0, a1);
                 if (X3) {
-                    uint32_t r2[32];
-                    tmem_ld32(lane_base + (uint32_t)(BN + c0), r2);
+                    uint32_t b0[8], b1[8];
+                    tmem_ld_16x256b_x2(tacc + (uint32_t)(BN + c0), b0);
+                    tmem_ld_16x256b_x2(tacc + (16u << 16) + (uint32_t)(BN + c0), b1);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(r2[j])));
-                }
-                if (m < args.M) {
-                    const int64_t off = orow * args.Cout + n0 + c0;
-                    const float* bs = bias_s + n0 + c0;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 v = make_float4(__uint_as_float(r[j]) + bs[j], __uint_as_float(r[j + 1]) + bs[j + 1],
-                                               __uint_as_float(r[j + 2]) + bs[j + 2], __uint_as_float(r[j + 3]) + bs[j + 3]);
-                        if (args.residual) {
-                            const float4 q = __ldg(reinterpret_cast<const float4*>(args.residual + off + j));
-                            v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
-                        }
-                        if (args.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-                        if (args.mask_src) {
-                            const float4 q = __ldg(reinterpret_cast<const float4*>(args.mask_src + off + j));
-                            if (!(q.x > 0.f)) v.x = 0.f; if (!(q.y > 0.f)) v.y = 0.f; if (!(q.z > 0.f)) v.z = 0.f; if (!(q.w > 0.f)) v.w = 0.f;
-                        }
-                        *reinterpret_cast<float4*>(args.dst + off + j) = v;
+                    for (int k = 0; k < 8; ++k) {
+                        a0[k] = __float_as_uint(__fadd_rn(__uint_as_float(a0[k]), __uint_as_float(b0[k])));
+                        a1[k] = __float_as_uint(__fadd_rn(__uint_as_float(a1[k]), __uint_as_float(b1[k])));
                     }
+                } else {
+                    tmem_ld_wait();
                 }
+                const float* bs = bias_s + n0 + c0 + lc;
+#pragma unroll
+                for (int ih = 0; ih < 4; ++ih)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const uint32_t* a = (ih >> 1) ? a1 : a0;
+                        const int reg = 4 * j + 2 * (ih & 1);
+                        float2 v = make_float2(__uint_as_float(a[reg]) + bs[8 * j], __uint_as_float(a[reg + 1]) + bs[8 * j + 1]);
+                        const float2 r = res[uu & 1][ih * 2 + j], q = mk[uu & 1][ih * 2 + j];
+                        v.x += r.x; v.y += r.y;
+                        if (args.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+                        if (!(q.x > 0.f)) v.x = 0.f;
+                        if (!(q.y > 0.f)) v.y = 0.f;
+                        if (valid[ih]) *reinterpret_cast<float2*>(args.dst + off[ih] + c0 + 8 * j) = v;
+                    }
             }
             tc_fence_before();                                   // TMEM reads done before the MMA warp may overwrite
+            if (threadIdx.x == 256) TC_TRACE(6, t);
             mbar_arrive(&tempty_bar[acc]);
         }
     }
@@ -697,6 +773,9 @@ static int tc_launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmBhi, c
     return I2V_OK;
 }
 
+static unsigned long long* g_trace = nullptr;
+static int g_trace_tiles = 0;
+
 // Common driver: `src` [N,H,W,C] is the gathered tensor, GEMM rows are the (img,p,q) grid, K = taps x C.
 struct TcProblem {
     const float* src; int N, H, W, C;
@@ -736,6 +815,7 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
     a.M = M; a.Cout = pr.Cout; a.P = pr.P; a.Q = pr.Q; a.stride = pr.stride; a.lower_h = pr.lower_h; a.lower_w = pr.lower_w;
     a.taps_h = pr.taps_h; a.taps_w = pr.taps_w; a.cblocks = pr.C / 32; a.relu = pr.relu;
     a.out_s = pr.out_s; a.out_h0 = pr.out_h0; a.out_w0 = pr.out_w0; a.out_H = pr.out_H; a.out_W = pr.out_W;
+    a.trace = g_trace; a.trace_tiles = g_trace_tiles;
 #define I2V_TC_DISPATCH_P(BN_)                                                                      \
     do {                                                                                            \
         if (x3) return im2col ? tc_launch_persist<BN_, true, true>(tmA, tmBhi, tmBlo, a, st) : tc_launch_persist<BN_, true, false>(tmA, tmBhi, tmBlo, a, st);   \
@@ -759,6 +839,12 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
 }  // namespace i2v
 
 using namespace i2v;
+
+extern "C" int i2v_conv_tc_set_trace(unsigned long long* device_buf, int tiles) {
+    g_trace = device_buf;
+    g_trace_tiles = device_buf ? tiles : 0;
+    return I2V_OK;
+}
 
 extern "C" int i2v_conv_tc_supported(const i2v_conv_desc* d, int dgrad) {
     if (!d) return 0;

@@ -37,6 +37,7 @@ class _Conv:
 
     def __init__(self, name, x, y, conv, bn, relu, residual=None, x_nchw=False):
         self.name, self.x, self.y, self.relu, self.residual, self.x_nchw = name, x, y, relu, residual, x_nchw
+        self.relu_skipped_before = 0     # ReLU calls of the torch module that this graph does not execute (see relu_masks)
         w = conv.weight.detach().float()
         cout, cin, R, S = w.shape
         if conv.groups != 1 or conv.dilation != (1, 1) or R != S or conv.stride[0] != conv.stride[1] \
@@ -226,6 +227,7 @@ def _build_sequential(features, targets):
             if id(m.expand3x3_activation) in remaining and len(remaining) == 1:
                 # scalar-depth hook (image_attacks.py:271): only the 3x3 branch of the last Fire is needed
                 ops.append(_Conv(e3, sq, e3, m.expand3x3, None, True))
+                ops[-1].relu_skipped_before = 1          # torch still runs expand1x1_activation before expand3x3_activation
                 chans[e3] = m.expand3x3.out_channels
                 relu_typed.add(e3)
                 hooks[id(m.expand3x3_activation)] = e3
@@ -370,9 +372,22 @@ class NativeEngine:
                     capi.copy_channels(acts[xn], acts[op.y], 0, off, self.chans[xn])
                     off += self.chans[xn]
         self._last = plan if need_grad else None
+        self._last_fwd = plan
         feats = [acts[b] for b in self.hook_bufs]
         # clean features are kept by the caller across the whole attack: hand out copies, the plan's buffers are reused
         return [f.clone() for f in feats] if not need_grad else feats
+
+    def relu_masks(self):
+        """Activity masks 1[activation > 0] of every ReLU of the last forward, in the torch module's ReLU call
+        order, as [n,C,h,w] bool tensors — the decisions the backward pass uses; None for a ReLU the truncated
+        graph does not execute.  For parity tests only (forces a sync)."""
+        acts = self._last_fwd["acts"]
+        out = []
+        for op in self.ops:
+            if op.kind == "conv" and op.relu:
+                out.extend([None] * op.relu_skipped_before)
+                out.append((acts[op.y] > 0).permute(0, 3, 1, 2).contiguous().cpu())
+        return out
 
     # ---- backward ------------------------------------------------------------------------------------
     def input_grad(self, grads):

@@ -9,7 +9,7 @@ implement raises.
 """
 import os
 
-DEFAULT_ENGINE = "cudnn"
+DEFAULT_ENGINE = "native"
 
 
 def resolve(engine=None):

@@ -204,6 +204,10 @@ int i2v_conv_tc_f32(const i2v_conv_desc* d, int dgrad, const float* src, const f
                     const float* bias, const float* residual, const float* mask_src, float* dst, int flags,
                     i2v_stream_t stream);
 
+/* Debug: subsequent tensor-core launches make CTA 0 stamp clock64() at 8 pipeline points of each of its first
+ * `tiles` tiles into device_buf[tiles][8] (see TcArgs::trace in csrc/conv_tc.cu); NULL switches it off.     */
+int i2v_conv_tc_set_trace(unsigned long long* device_buf, int tiles);
+
 /* Strided data gradient on the tensor cores, one stride-parity class (ph, pw) per call: image rows
  * h = stride*i + ph receive only the taps r = r0 + stride*a, r0 = (ph + pad) mod stride, from dy row
  * i + (ph + pad - r0)/stride - a — a dense stride-1 implicit GEMM over dy whose output rows are scattered

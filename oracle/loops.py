@@ -63,6 +63,67 @@ class HookedModel:
             h.remove()
 
 
+class _ForcedReLU(torch.autograd.Function):
+    """y = x * mask: the linear branch of ReLU selected by a GIVEN activity mask (forward and backward)."""
+
+    @staticmethod
+    def forward(ctx, x, mask):
+        ctx.save_for_backward(mask)
+        return x * mask
+
+    @staticmethod
+    def backward(ctx, gy):
+        (mask,) = ctx.saved_tensors
+        return gy * mask, None
+
+
+class forced_relu_masks:
+    """Context manager: the first len(masks) ReLU calls of `model` (execution order) use the given activity
+    masks instead of their own sign decision; a None entry and later calls (layers behind the hooks) are untouched.
+
+    ReLU is not differentiable at 0: two correct float32 implementations of the forward pass can decide
+    1[z > 0] differently for a pre-activation within rounding distance of 0, and that single decision changes
+    the gradient by O(1) for every pixel in the element's receptive field.  Forcing the decisions of the
+    implementation under test separates "were the decisions the same" (counted in `flips`) from "is the
+    gradient arithmetic right given the decisions" (compared tightly).  `flips` = number of forced decisions
+    that differ from the model's own, `total` = number of decisions."""
+
+    def __init__(self, model, masks):
+        self.model, self.masks = model, list(masks)
+        self.flips = self.total = 0
+
+    def __enter__(self):
+        self.i = 0
+        self.saved = []
+        outer = self
+
+        def make(mod):
+            def fwd(x):
+                if outer.i < len(outer.masks) and outer.masks[outer.i] is None:
+                    outer.i += 1                                  # a call the implementation under test does not make
+                    return F.relu(x)
+                if outer.i < len(outer.masks):
+                    mk = outer.masks[outer.i].to(x.dtype)
+                    outer.i += 1
+                    if tuple(mk.shape) != tuple(x.shape):
+                        raise ValueError("ReLU call %d: mask %s vs activation %s" % (outer.i - 1, tuple(mk.shape), tuple(x.shape)))
+                    outer.flips += int(((x.detach() > 0) != (mk > 0)).sum())
+                    outer.total += mk.numel()
+                    return _ForcedReLU.apply(x, mk)
+                return F.relu(x)
+            return fwd
+        for mod in self.model.modules():
+            if isinstance(mod, torch.nn.ReLU):
+                self.saved.append(mod)
+                mod.forward = make(mod)
+        return self
+
+    def __exit__(self, *exc):
+        for mod in self.saved:
+            del mod.forward
+        return False
+
+
 def _frames(videos):
     b, c, f, h, w = videos.shape
     return videos.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w).contiguous()
@@ -147,15 +208,18 @@ def image_guided_loop(hooked, videos, epsilon, steps, step_size, adaptive=False,
     return adv, cost_log, (np.stack(weights) if adaptive and steps else None), coeffs
 
 
-def teacher_forced_grad(hooked, frames, true_image, dtype=torch.float32, weights=None):
+def teacher_forced_grad(hooked, frames, true_image, dtype=torch.float32, weights=None, relu_masks=None):
     """dcost/dtrue_image of ONE step for a GIVEN true_image (image_attacks.py:334-352), in `dtype`.
 
     float64 is the accuracy arbiter of SURVEY.md 8(c): both float32 implementations (torch on the CPU —
     the reference's arithmetic — and the CUDA path) are scored by their distance to it, because at
     step 1 the gradient is a cancellation-level quantity and the reference does not reproduce itself
     across reduction orders (D8).  `hooked` models are converted to `dtype` in place.
+    relu_masks: optional, one list of [N,C,h,w] activity masks per hooked model (ReLU execution order) that the
+    adversarial forward/backward is forced to use (see forced_relu_masks); then a 4th value (flips, total) is returned.
     Returns (cost, grad [N,3,H,W] as float64 ndarray, cos [L,N])."""
     frames = torch.as_tensor(frames).to(dtype)
+    flips = total = 0
     ti = torch.as_tensor(np.ascontiguousarray(true_image)).to(dtype).requires_grad_(True)
     N = frames.shape[0]
     rows = []
@@ -163,7 +227,12 @@ def teacher_forced_grad(hooked, frames, true_image, dtype=torch.float32, weights
         hm.model.to(dtype)
         with torch.no_grad():
             init = [a.detach().clone() for a in hm.run(frames)]
-        acts = hm.run(ti)
+        if relu_masks is None:
+            acts = hm.run(ti)
+        else:
+            with forced_relu_masks(hm.model, relu_masks[hooked.index(hm)]) as fm:
+                acts = hm.run(ti)
+            flips, total = flips + fm.flips, total + fm.total
         for a, a0 in zip(acts, init):
             rows.append(F.cosine_similarity(a.view(N, -1), a0.view(N, -1)))
     stacked = torch.stack(rows)
@@ -172,6 +241,8 @@ def teacher_forced_grad(hooked, frames, true_image, dtype=torch.float32, weights
     else:
         cost = torch.mean(torch.sum(torch.as_tensor(weights).to(dtype).unsqueeze(1) * stacked, dim=1))
     (g,) = torch.autograd.grad(cost, ti)
+    if relu_masks is not None:
+        return float(cost.detach()), g.double().numpy(), stacked.detach().double().numpy(), (flips, total)
     return float(cost.detach()), g.double().numpy(), stacked.detach().double().numpy()
 
 

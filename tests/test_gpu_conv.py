@@ -140,36 +140,43 @@ def test_native_engine_matches_autograd(name, depth, side, mode):
     model = backbones.get_model(name)
     eng = NativeEngine(model, name, depth, tf32x3=True, use_tensor_cores=(mode == "tc"))
     feats = eng.features(img.to(DEV), need_grad=True)
-    # float64 reference on the CPU through the reference's own hook mechanism
+    # float64 reference on the CPU through the reference's own hook mechanism.  ReLU is not differentiable at 0:
+    # a pre-activation within rounding distance of 0 may be decided differently by two correct float32 forward
+    # passes, and one decision is an O(1) change of the gradient over that element's receptive field.  So the
+    # float64 backward is evaluated with the ENGINE's ReLU decisions (oracle.loops.forced_relu_masks) and compared
+    # tightly; the number of decisions that differ from float64's own is bounded separately.
+    from oracle import loops as OL
     ref_model = backbones.seeded_random_init(backbones.arch_of(name), 0).double()
     backbones.freeze_for_attack(ref_model)
     acts = []
     hs = [t.register_forward_hook(lambda m, i, o: acts.append(o)) for t in backbones.find_target_layers(ref_model, name, depth)]
     xi = img.double().requires_grad_(True)
-    ref_model(xi)
+    with OL.forced_relu_masks(ref_model, eng.relu_masks()) as fm:
+        ref_model(xi)
     for h in hs:
         h.remove()
+    assert fm.i == len(fm.masks)
+    assert fm.flips <= max(2, 2e-5 * fm.total), ("ReLU decisions differing from float64", fm.flips, fm.total)
     assert len(acts) == len(feats)
     ups = []
     for a, f in zip(acts, feats):
         got = f.permute(0, 3, 1, 2).cpu().double()
         assert got.shape == a.shape
         err = (got - a.detach()).abs().max() / a.detach().abs().max()
-        assert err <= 5e-5, ("feature", err)
-        up = torch.randn(a.shape, generator=g, dtype=torch.float64) * (a.detach() > 0)     # pre-activation gradient
+        # 3xTF32: exact operands, but the tensor core accumulates with truncation (K/8 truncations of the main
+        # accumulator): a systematic shrink of ~K * 2^-27 per layer that adds up over the depth of the stack
+        assert err <= (5e-5 if mode == "tc" else 5e-6), ("feature", err)
+        up = torch.randn(a.shape, generator=g, dtype=torch.float64) * (got > 0)     # pre-activation gradient
         ups.append(up)
     (gref,) = torch.autograd.grad(acts, xi, ups)
     grads = [u.permute(0, 2, 3, 1).contiguous().float().to(DEV) for u in ups]
     gimg = eng.input_grad(grads).cpu().double()
-    # A pre-activation within rounding distance of 0 can get a different ReLU mask than in float64 (the
-    # tensor-core path carries a ~1e-5 truncation bias, cuDNN/oneDNN differ the same way); one flipped mask is
-    # an O(1) error on a handful of gradient elements.  So: L2 error (robust to isolated flips) plus the
-    # fraction of elements that agree tightly, instead of the max norm.
     diff = (gimg - gref).abs()
     rel_l2 = diff.pow(2).sum().sqrt() / gref.pow(2).sum().sqrt()
-    close = (diff <= 2e-4 * gref.abs().max()).double().mean()
-    assert rel_l2 <= (2e-2 if mode == "tc" else 2e-3), ("input gradient L2", rel_l2)
-    assert close >= (0.98 if mode == "tc" else 0.999), ("input gradient agreement", close)
+    rel_max = diff.max() / gref.abs().max()
+    print("engine parity %s depth=%s mode=%s: relL2 %.2e relmax %.2e relu flips %d / %d" % (name, depth, mode, rel_l2, rel_max, fm.flips, fm.total))
+    assert rel_l2 <= (5e-5 if mode == "tc" else 5e-6), ("input gradient L2", rel_l2)
+    assert rel_max <= (2e-4 if mode == "tc" else 2e-5), ("input gradient max", rel_max)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -234,9 +241,9 @@ def test_conv_tc_fwd_and_dgrad(shape, x3):
         assert torch.isfinite(got).all()
         err = (got - ref64).abs().max() / ref64.abs().max()
         assert err <= tol, ("fwd", err, tol)
-    if not capi.conv_tc_supported(d, 1):
-        assert s != 1
+    if s != 1:      # strided data gradients go through the stride-parity classes (test_conv_tc_strided_dgrad_classes)
         return
+    assert capi.conv_tc_supported(d, 1)
     dy = torch.randn(N, Cout, P, Q, generator=g)
     addend = torch.randn(N, Cin, H, W, generator=g)
     act = torch.randn(N, Cin, H, W, generator=g)

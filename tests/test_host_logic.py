@@ -91,3 +91,40 @@ def test_loss_info_format():
     info = {}
     attack_loop.record_loss_info(info, ["a", "b"], np.array([1.9999996, 1.5], dtype=np.float32))
     assert info["a"][0] == {"cost": "1.9999996"} and info["b"][1] == {"cost": "1.5"}
+
+
+def test_forced_relu_masks_isolate_the_decisions():
+    """oracle.loops.forced_relu_masks: a float64 backward evaluated with the ReLU decisions of a float32 forward
+    reproduces the float32 gradient to rounding level, and counts the decisions that differ."""
+    import torch
+    from i2v_b200 import backbones
+    from oracle import loops as OL
+    name, depth = "resnet", 1
+    m32 = backbones.freeze_for_attack(backbones.seeded_random_init(backbones.arch_of(name), 0))
+    g = torch.Generator().manual_seed(3)
+    img = torch.randn(2, 3, 32, 32, generator=g)
+    masks, acts32 = [], []
+    hs = [mod.register_forward_hook(lambda mo, i, o: masks.append((o.detach() > 0).clone())) for mod in m32.modules()
+          if isinstance(mod, torch.nn.ReLU)]
+    tgt = backbones.find_target_layers(m32, name, depth)[0]
+    hs.append(tgt.register_forward_hook(lambda mo, i, o: acts32.append(o)))
+    x32 = img.clone().requires_grad_(True)
+    m32(x32)
+    for h in hs:
+        h.remove()
+    n_relu = 1 + 3 * 3        # stem + layer1's three bottlenecks: the decisions upstream of the hook
+    up = torch.randn(acts32[0].shape, generator=g)
+    (g32,) = torch.autograd.grad(acts32[0], x32, up)
+    m64 = backbones.freeze_for_attack(backbones.seeded_random_init(backbones.arch_of(name), 0)).double()
+    acts64 = []
+    h = backbones.find_target_layers(m64, name, depth)[0].register_forward_hook(lambda mo, i, o: acts64.append(o))
+    x64 = img.double().requires_grad_(True)
+    with OL.forced_relu_masks(m64, masks[:n_relu]) as fm:
+        m64(x64)
+    h.remove()
+    assert fm.i == n_relu and fm.total == sum(mk.numel() for mk in masks[:n_relu])
+    assert fm.flips <= 2
+    (g64,) = torch.autograd.grad(acts64[0], x64, up.double())
+    assert ((g32.double() - g64).abs().max() / g64.abs().max()) < 1e-5
+    # the context manager restores the modules
+    assert all("forward" not in vars(mod) for mod in m64.modules())

@@ -14,11 +14,13 @@ LAYERS = [  # name, H, Cin, Cout, k, s, p, count(fwd)
     ("l1.conv1(64->64,1x1)", 56, 64, 64, 1, 1, 0, 1),
     ("l1.conv2(64->64,3x3)", 56, 64, 64, 3, 1, 1, 3),
     ("l1.conv3(64->256,1x1)", 56, 64, 256, 1, 1, 0, 4),
+    ("l1.conv3(64->256,1x1)+res", 56, 64, 256, 1, 1, 0, 3),
     ("l1.conv1(256->64,1x1)", 56, 256, 64, 1, 1, 0, 2),
     ("l2.0.conv1(256->128,1x1)", 56, 256, 128, 1, 1, 0, 1),
     ("l2.0.conv2(128->128,3x3/2)", 56, 128, 128, 3, 2, 1, 1),
     ("l2.0.ds(256->512,1x1/2)", 56, 256, 512, 1, 2, 0, 1),
     ("l2.conv3(128->512,1x1)", 28, 128, 512, 1, 1, 0, 4),
+    ("l2.conv3(128->512,1x1)+res", 28, 128, 512, 1, 1, 0, 4),
     ("l2.conv1(512->128,1x1)", 28, 512, 128, 1, 1, 0, 3),
     ("l2.conv2(128->128,3x3)", 28, 128, 128, 3, 1, 1, 3),
 ]
@@ -73,8 +75,11 @@ def main():
         d = capi.ConvDesc(n, H, H, Cin, Cout, k, k, s, p, P, P)
         flop = 2.0 * n * P * P * Cout * Cin * k * k
         byts = 4.0 * (xd.numel() + y.numel())
-        for mode, fn in (("tc_x3", lambda: capi.conv_tc(d, 0, xd, hi, lo, None, None, None, y, relu=True)),
-                         ("tc_x1", lambda: capi.conv_tc(d, 0, xd, rna, None, None, None, None, y, relu=True)),
+        res = torch.randn_like(y) if name.endswith("+res") else None
+        if res is not None:
+            byts += 4.0 * y.numel()
+        for mode, fn in (("tc_x3", lambda: capi.conv_tc(d, 0, xd, hi, lo, None, res, None, y, relu=True)),
+                         ("tc_x1", lambda: capi.conv_tc(d, 0, xd, rna, None, None, res, None, y, relu=True)),
                          ("simt", lambda: capi.conv_fwd_simt(d, xd, bf, None, None, y, relu=True))):
             ms = timeit(fn)
             rec["ms_" + mode] = ms
