@@ -45,6 +45,7 @@ SIGNATURES = {
     "i2v_conv_tc_supported": ([_c_p, _c_int], _c_int),
     "i2v_conv_tc_set_trace": ([_c_p, _c_int], _c_int),
     "i2v_conv_tc_f32": ([_c_p, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
+    "i2v_conv_tc_bits_f32": ([_c_p, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_tc_dgrad_class_f32": ([_c_p, _c_int, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p], _c_int),
     "i2v_maxpool_fwd_f32": ([_c_p, _c_p, _c_p] + [_c_int] * 9 + [_c_p], _c_int),
     "i2v_maxpool_bwd_f32": ([_c_p, _c_p, _c_p, _c_p] + [_c_int] * 10 + [_c_p], _c_int),
@@ -302,13 +303,17 @@ def conv_tc_supported(desc, dgrad):
     return bool(load().i2v_conv_tc_supported(ctypes.addressof(desc), int(dgrad)))
 
 
-def conv_tc(desc, dgrad, src, w_hi, w_lo, bias, residual, mask_src, dst, relu=False):
-    """Tensor-core implicit GEMM (tcgen05/TMEM/TMA).  w_lo=None -> plain TF32, else 3xTF32 FP32-parity mode."""
+def conv_tc(desc, dgrad, src, w_hi, w_lo, bias, residual, mask_src, dst, relu=False, mask_bits=None):
+    """Tensor-core implicit GEMM (tcgen05/TMEM/TMA).  w_lo=None -> plain TF32, else 3xTF32 FP32-parity mode.
+    mask_bits: int32 [C_dst/32, M] — forward: receives the activity bits of dst; dgrad: the ReLU-backward mask."""
     nb, fl = _conv_cost(desc)
-    nb += 4 * dst.numel() * ((residual is not None and residual is not dst) + (mask_src is not None))
+    nb += 4 * dst.numel() * ((residual is not None) + (mask_src is not None))
+    if mask_bits is not None:
+        nb += 4 * mask_bits.numel()
     with _Timed("i2v_conv_tc_f32", nb, fl):
-        _check(load().i2v_conv_tc_f32(ctypes.addressof(desc), int(dgrad), _dev(src), _dev(w_hi), _dev(w_lo), _dev(bias),
-                                      _dev(residual), _dev(mask_src), _dev(dst), EPI_RELU if relu else 0, _stream()),
+        _check(load().i2v_conv_tc_bits_f32(ctypes.addressof(desc), int(dgrad), _dev(src), _dev(w_hi), _dev(w_lo), _dev(bias),
+                                           _dev(residual), _dev(mask_src), _dev(mask_bits, torch.int32), _dev(dst),
+                                           EPI_RELU if relu else 0, _stream()),
                "i2v_conv_tc_f32")
 
 

@@ -47,6 +47,8 @@ struct TcArgs {
     const float* residual;   // [M, Cout] or null
     const float* mask_src;   // [M, Cout] or null
     float* dst;              // [M, Cout]
+    const uint32_t* mask_bits;   // [Cout/32][M] bit j of word (w, m) = 1[mask source (m, 32w+j) > 0], or null   (TMA epilogue)
+    uint32_t* bits_out;          // [Cout/32][M] activity bits of dst written by the epilogue, or null           (TMA epilogue)
     int64_t M;               // N*P*Q GEMM rows
     int Cout;
     int P, Q;                // row grid: m = (img, p, q)
@@ -114,6 +116,13 @@ __device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap* map, uint6
                  :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 :: "l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory");
 }
@@ -150,6 +159,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                  : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// one TMEM lane (= tile row) per thread, 32 consecutive columns; no wait: callers batch loads per wait
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
 }
 
 // 16 TMEM lanes x 16 columns per warp: thread t holds row t/4 (regs 4j+e) and row t/4+8 (regs 4j+2+e) of the lane
@@ -369,10 +390,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 constexpr int TC2_THREADS = 512;
 constexpr int TC2_EPI_THREADS = 256;
 
-template <int BN, bool X3, bool IM2COL>
+// Epilogue v3 (EPI_TMA): no per-thread global access at all.  The two epilogue groups (warps 8-11, 12-15: one warp per
+// TMEM lane quarter) work on 128-row x 32-column sub-tiles: tcgen05.ld 32x32b (thread = tile row), + bias, + residual read
+// from a SWIZZLE_128B staging slot that a TMA load filled, ReLU, ReLU-backward mask from one bit-mask word per thread,
+// result written back to the same slot (conflict-free 128-bit accesses thanks to the swizzle) and shipped by ONE TMA
+// store; warps 2 / 3 (one elected lane each) issue a group's stores and residual loads, decoupled by mbarriers
+// (out_ready: slot written; slot_ready: slot free again / next residual landed).  Measured reason: with the v2 epilogue a
+// warp-level float2 access touches 8 cache lines, and the LSU wavefronts of output + residual + mask (3 x 2048 cycles per
+// 128x128 tile) made every 1x1 convolution epilogue-bound (2.5-4.5 us per tile against 1-1.5 us of main loop).
+constexpr uint32_t EPI_SLOT_BYTES = TC_BM * 32 * 4;            // 16 KB: 128 rows x 128 bytes
+constexpr uint32_t EPI_STAGING_BYTES = 4 * EPI_SLOT_BYTES;     // two slots per epilogue group
+
+template <int BN, bool X3, bool IM2COL, bool EPI_TMA>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
-                       const __grid_constant__ CUtensorMap tmBlo, const TcArgs args, const int stages,
+                       const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmOut,
+                       const __grid_constant__ CUtensorMap tmRes, const TcArgs args, const int stages,
                        const int num_m_tiles, const int num_n_tiles) {
     using L = TcSmem<BN, X3>;
     constexpr uint32_t kAccCols = X3 ? 2 * BN : BN;            // TMEM columns per accumulator stage
@@ -381,13 +414,16 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* tiles = smem;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)stages * L::STAGE_BYTES);
+    uint8_t* staging = smem + (size_t)stages * L::STAGE_BYTES;  // STAGE_BYTES is a multiple of 1024: stays swizzle-aligned
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + (EPI_TMA ? EPI_STAGING_BYTES : 0));
     uint64_t* empty_bar = full_bar + stages;
     uint64_t* split_bar = empty_bar + stages;
     uint64_t* tfull_bar = split_bar + stages;
     uint64_t* tempty_bar = tfull_bar + kAcc;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + kAcc);
-    float* bias_s = reinterpret_cast<float*>(tmem_slot + 2);    // [Cout]
+    uint64_t* out_ready = tempty_bar + kAcc;                    // [group][slot]
+    uint64_t* slot_ready = out_ready + 4;                       // [group][slot]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slot_ready + 4);
+    float* bias_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 2) + 15) & ~(uintptr_t)15);   // [Cout], 16-byte aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kiters = args.taps_h * args.taps_w * args.cblocks;
@@ -410,6 +446,11 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             mbar_init(&tfull_bar[a], 1);
             mbar_init(&tempty_bar[a], TC2_EPI_THREADS);
         }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&out_ready[i], TC2_EPI_THREADS / 2);
+            mbar_init(&slot_ready[i], 1);
+        }
+        if (EPI_TMA) { prefetch_tmap(&tmOut); prefetch_tmap(&tmRes); }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -523,8 +564,125 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 if (t128 == 0) TC_TRACE(7, tno);
             }
         }
-    } else if (warp >= 8) {
-        // ===== epilogue =================================================================================
+    } else if (EPI_TMA && (warp == 2 || warp == 3)) {
+        // ===== epilogue TMA issuer of group g = warp - 2: output stores and residual loads ================
+        if (lane == 0) {
+            const int g = warp - 2;
+            constexpr uint32_t SUBS = BN / 64;                  // sub-tiles per tile and group
+            const bool has_res = args.residual != nullptr;
+            uint8_t* sbase = staging + (size_t)g * 2 * EPI_SLOT_BYTES;
+            const uint32_t my_tiles = (uint32_t)((num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
+            const uint32_t total = my_tiles * SUBS;
+            auto coords = [&](uint32_t k, int& col, int& row) {
+                const int tile = (int)blockIdx.x + (int)(k / SUBS) * (int)gridDim.x;
+                const int m_tile = tile / num_n_tiles, n_tile = tile - m_tile * num_n_tiles;
+                col = n_tile * BN + (g + 2 * (int)(k % SUBS)) * 32;
+                row = m_tile * TC_BM;
+            };
+            int col, row;
+            for (uint32_t k = 0; k < 2 && k < total; ++k) {     // prime both slots
+                if (has_res) {
+                    coords(k, col, row);
+                    mbar_arrive_expect_tx(&slot_ready[g * 2 + k], EPI_SLOT_BYTES);
+                    tma_load_2d(&tmRes, &slot_ready[g * 2 + k], sbase + (size_t)k * EPI_SLOT_BYTES, col, row);
+                } else {
+                    mbar_arrive(&slot_ready[g * 2 + k]);
+                }
+            }
+            for (uint32_t k = 0; k < total; ++k) {
+                const uint32_t s = k & 1, ph = (k >> 1) & 1;
+                mbar_wait(&out_ready[g * 2 + s], ph);           // the group's 128 threads wrote the slot (and fenced)
+                coords(k, col, row);
+                tma_store_2d(&tmOut, sbase + (size_t)s * EPI_SLOT_BYTES, col, row);
+                bulk_commit();
+                if (k + 2 < total) {
+                    bulk_wait_read0();                           // the store has read the slot: it may be refilled
+                    if (has_res) {
+                        coords(k + 2, col, row);
+                        mbar_arrive_expect_tx(&slot_ready[g * 2 + s], EPI_SLOT_BYTES);
+                        tma_load_2d(&tmRes, &slot_ready[g * 2 + s], sbase + (size_t)s * EPI_SLOT_BYTES, col, row);
+                    } else {
+                        mbar_arrive(&slot_ready[g * 2 + s]);
+                    }
+                }
+            }
+            bulk_wait_all();
+        }
+    } else if (EPI_TMA && warp >= 8) {
+        // ===== epilogue v3: thread = tile row, 32-column sub-tiles through swizzled staging slots =========
+        constexpr int SUBS = BN / 64;
+        const int g = (warp - 8) >> 2;
+        const int row = (warp & 3) * 32 + lane;                 // tile row = TMEM lane
+        const uint32_t swz = (uint32_t)(row & 7);
+        uint8_t* sbase = staging + (size_t)g * 2 * EPI_SLOT_BYTES + (size_t)row * 128;
+        const bool has_res = args.residual != nullptr;
+        const uint32_t* __restrict__ mbits = args.mask_bits;
+        uint32_t* __restrict__ obits = args.bits_out;
+        uint32_t k = 0;
+        int t = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+            const int m_tile = tile / num_n_tiles, n_tile = tile - m_tile * num_n_tiles;
+            const int n0 = n_tile * BN;
+            const int acc = t % kAcc;
+            const uint32_t aph = (uint32_t)(t / kAcc) & 1;
+            const int64_t m = (int64_t)m_tile * TC_BM + row;
+            const bool valid = m < args.M;
+            uint32_t mw[SUBS];
+#pragma unroll
+            for (int j = 0; j < SUBS; ++j)
+                mw[j] = (mbits && valid) ? __ldg(mbits + (int64_t)(n0 / 32 + g + 2 * j) * args.M + m) : 0xFFFFFFFFu;
+            mbar_wait(&tfull_bar[acc], aph);
+            tc_fence_after();
+            if (threadIdx.x == 256) TC_TRACE(5, t);
+            const uint32_t tacc = tmem_base + (uint32_t)acc * kAccCols + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll
+            for (int j = 0; j < SUBS; ++j, ++k) {
+                const int c0 = (g + 2 * j) * 32;
+                uint32_t a[32];
+                tmem_ld32_nowait(tacc + (uint32_t)c0, a);
+                if (X3) {
+                    uint32_t b[32];
+                    tmem_ld32_nowait(tacc + (uint32_t)(BN + c0), b);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) a[i] = __float_as_uint(__fadd_rn(__uint_as_float(a[i]), __uint_as_float(b[i])));
+                } else {
+                    tmem_ld_wait();
+                }
+                if (j == SUBS - 1) {                             // accumulator drained: the MMA warp may reuse it
+                    tc_fence_before();
+                    mbar_arrive(&tempty_bar[acc]);
+                }
+                const uint32_t s = k & 1, ph = (k >> 1) & 1;
+                mbar_wait(&slot_ready[g * 2 + s], ph);          // residual landed / previous store has read the slot
+                uint8_t* srow = sbase + (size_t)s * EPI_SLOT_BYTES;
+                const float* bs = bias_s + n0 + c0;
+                const uint32_t mword = mw[j];
+                uint32_t oword = 0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4* p = reinterpret_cast<float4*>(srow + (((uint32_t)c ^ swz) << 4));
+                    const float4 bv = *reinterpret_cast<const float4*>(bs + 4 * c);
+                    float4 v = make_float4(__uint_as_float(a[4 * c]) + bv.x, __uint_as_float(a[4 * c + 1]) + bv.y,
+                                           __uint_as_float(a[4 * c + 2]) + bv.z, __uint_as_float(a[4 * c + 3]) + bv.w);
+                    if (has_res) { const float4 r = *p; v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+                    if (args.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    if (!((mword >> (4 * c)) & 1u)) v.x = 0.f;
+                    if (!((mword >> (4 * c + 1)) & 1u)) v.y = 0.f;
+                    if (!((mword >> (4 * c + 2)) & 1u)) v.z = 0.f;
+                    if (!((mword >> (4 * c + 3)) & 1u)) v.w = 0.f;
+                    oword |= (v.x > 0.f ? 1u : 0u) << (4 * c) | (v.y > 0.f ? 1u : 0u) << (4 * c + 1) |
+                             (v.z > 0.f ? 1u : 0u) << (4 * c + 2) | (v.w > 0.f ? 1u : 0u) << (4 * c + 3);
+                    *p = v;
+                }
+                if (obits && valid) obits[(int64_t)((n0 + c0) / 32) * args.M + m] = oword;
+                fence_proxy_async();                             // generic-proxy writes -> visible to the TMA store
+                mbar_arrive(&out_ready[g * 2 + s]);
+            }
+            if (threadIdx.x == 256) TC_TRACE(6, t);
+        }
+    } else if (!EPI_TMA && warp >= 8) {
+        // ===== epilogue v2 (strided scatter / f32 mask source) ============================================
         constexpr int UNITS = BN / 32;                          // 16-column units per warp (two warps per lane quarter)
         const int quarter = warp & 3;                           // TMEM lanes 32*quarter .. +31
         const int uhalf = (warp - 8) >> 2;                      // this warp's units: uhalf, uhalf + 2, ...
@@ -746,10 +904,11 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUt
     return I2V_OK;
 }
 
-template <int BN, bool X3, bool IM2COL>
-static int tc_launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, const TcArgs& args, cudaStream_t st) {
+template <int BN, bool X3, bool IM2COL, bool EPI_TMA>
+static int tc_launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, const CUtensorMap& tmOut,
+                             const CUtensorMap& tmRes, const TcArgs& args, cudaStream_t st) {
     using L = TcSmem<BN, X3>;
-    auto kern = conv_tc_persist_kernel<BN, X3, IM2COL>;
+    auto kern = conv_tc_persist_kernel<BN, X3, IM2COL, EPI_TMA>;
     static int stages = 0;
     static size_t smem_fixed = 0;
     if (stages == 0) {
@@ -757,9 +916,10 @@ static int tc_launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmBhi, c
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         const size_t budget = (size_t)(optin > 0 ? optin : 227 * 1024);
-        smem_fixed = 1024 /*align slack*/ + 512 /*barriers*/ + 2048 * 4 /*bias, Cout <= 2048*/;
+        smem_fixed = 1024 /*align slack*/ + 512 /*barriers*/ + 2048 * 4 /*bias, Cout <= 2048*/ + (EPI_TMA ? EPI_STAGING_BYTES : 0);
         int s = (int)((budget - smem_fixed) / L::STAGE_BYTES);
         if (s > 8) s = 8;
+        if (s < 2) { set_error("conv_tc (persistent): %d pipeline stages fit in shared memory", s); return I2V_ECUDA; }
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_fixed + (size_t)s * L::STAGE_BYTES));
         if (e != cudaSuccess) return cuda_fail(e, "conv_tc (persistent): shared memory attribute");
         stages = s;
@@ -768,7 +928,8 @@ static int tc_launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmBhi, c
     const int num_m_tiles = (int)((args.M + TC_BM - 1) / TC_BM), num_n_tiles = args.Cout / BN;
     const int64_t tiles = (int64_t)num_m_tiles * num_n_tiles;
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-    kern<<<grid, TC2_THREADS, smem_fixed + (size_t)stages * L::STAGE_BYTES, st>>>(tmA, tmBhi, tmBlo, args, stages, num_m_tiles, num_n_tiles);
+    kern<<<grid, TC2_THREADS, smem_fixed + (size_t)stages * L::STAGE_BYTES, st>>>(tmA, tmBhi, tmBlo, tmOut, tmRes, args, stages,
+                                                                                  num_m_tiles, num_n_tiles);
     I2V_LAUNCH_CHECK("i2v_conv_tc_f32 (persistent)");
     return I2V_OK;
 }
@@ -783,6 +944,7 @@ struct TcProblem {
     const float* w_hi; const float* w_lo; int Cout;
     const float* bias; const float* residual; const float* mask_src; float* dst; int relu;
     int out_s, out_h0, out_w0, out_H, out_W;
+    const uint32_t* mask_bits; uint32_t* bits_out;
 };
 
 static int tc_run(const TcProblem& pr, cudaStream_t st) {
@@ -803,27 +965,46 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
     if (const char* e = getenv("I2V_TC_BN")) { int v = atoi(e); if ((v == 64 || v == 128) && pr.Cout % v == 0) BN = v; }
     const int Ktot = pr.taps_h * pr.taps_w * pr.C;
 
-    CUtensorMap tmA, tmBhi, tmBlo;
+    // TMA epilogue (v3) whenever the output rows are dense and no f32 mask source is involved; the strided
+    // data-gradient classes and callers that pass an f32 mask keep the register/LSU epilogue (v2)
+    static const bool epi_tma_on = !(getenv("I2V_TC_EPI_TMA") && atoi(getenv("I2V_TC_EPI_TMA")) == 0);
+    const bool epi_tma = persistent && epi_tma_on && pr.out_s == 0 && pr.mask_src == nullptr;
+    I2V_REQUIRE(epi_tma || (pr.mask_bits == nullptr && pr.bits_out == nullptr),
+                "bit masks need the TMA epilogue (dense output rows, no f32 mask source)");
+
+    CUtensorMap tmA, tmBhi, tmBlo, tmOut, tmRes;
     if (im2col) { if (int r = get_map_im2col(&tmA, pr.src, pr.N, pr.H, pr.W, pr.C, pr.lower_w, pr.lower_h, pr.upper_w, pr.upper_h, pr.stride)) return r; }
     else        { if (int r = get_map_2d(&tmA, pr.src, (int)M, pr.C, TC_BM)) return r; }
     if (int r = get_map_2d(&tmBhi, pr.w_hi, pr.Cout, Ktot, BN)) return r;
     if (x3) { if (int r = get_map_2d(&tmBlo, pr.w_lo, pr.Cout, Ktot, BN)) return r; }
     else tmBlo = tmBhi;
+    tmOut = tmBhi; tmRes = tmBhi;
+    if (epi_tma) {
+        if (int r = get_map_2d(&tmOut, pr.dst, (int)M, pr.Cout, TC_BM)) return r;
+        if (pr.residual) { if (int r = get_map_2d(&tmRes, pr.residual, (int)M, pr.Cout, TC_BM)) return r; }
+    }
 
     TcArgs a{};
     a.bias = pr.bias; a.residual = pr.residual; a.mask_src = pr.mask_src; a.dst = pr.dst;
+    a.mask_bits = pr.mask_bits; a.bits_out = pr.bits_out;
     a.M = M; a.Cout = pr.Cout; a.P = pr.P; a.Q = pr.Q; a.stride = pr.stride; a.lower_h = pr.lower_h; a.lower_w = pr.lower_w;
     a.taps_h = pr.taps_h; a.taps_w = pr.taps_w; a.cblocks = pr.C / 32; a.relu = pr.relu;
     a.out_s = pr.out_s; a.out_h0 = pr.out_h0; a.out_w0 = pr.out_w0; a.out_H = pr.out_H; a.out_W = pr.out_W;
     a.trace = g_trace; a.trace_tiles = g_trace_tiles;
-#define I2V_TC_DISPATCH_P(BN_)                                                                      \
+#define I2V_TC_DISPATCH_P(BN_, EPI_)                                                                \
     do {                                                                                            \
-        if (x3) return im2col ? tc_launch_persist<BN_, true, true>(tmA, tmBhi, tmBlo, a, st) : tc_launch_persist<BN_, true, false>(tmA, tmBhi, tmBlo, a, st);   \
-        return im2col ? tc_launch_persist<BN_, false, true>(tmA, tmBhi, tmBlo, a, st) : tc_launch_persist<BN_, false, false>(tmA, tmBhi, tmBlo, a, st);          \
+        if (x3) return im2col ? tc_launch_persist<BN_, true, true, EPI_>(tmA, tmBhi, tmBlo, tmOut, tmRes, a, st)      \
+                              : tc_launch_persist<BN_, true, false, EPI_>(tmA, tmBhi, tmBlo, tmOut, tmRes, a, st);    \
+        return im2col ? tc_launch_persist<BN_, false, true, EPI_>(tmA, tmBhi, tmBlo, tmOut, tmRes, a, st)             \
+                      : tc_launch_persist<BN_, false, false, EPI_>(tmA, tmBhi, tmBlo, tmOut, tmRes, a, st);           \
     } while (0)
     if (persistent) {
-        if (BN == 128) I2V_TC_DISPATCH_P(128);
-        I2V_TC_DISPATCH_P(64);
+        if (epi_tma) {
+            if (BN == 128) I2V_TC_DISPATCH_P(128, true);
+            I2V_TC_DISPATCH_P(64, true);
+        }
+        if (BN == 128) I2V_TC_DISPATCH_P(128, false);
+        I2V_TC_DISPATCH_P(64, false);
     }
 #undef I2V_TC_DISPATCH_P
 #define I2V_TC_DISPATCH(BN_)                                                                        \
@@ -857,11 +1038,13 @@ extern "C" int i2v_conv_tc_supported(const i2v_conv_desc* d, int dgrad) {
 
 // Forward:  src = x  [N,H,W,Cin],  dst = y  [N,P,Q,Cout], w_* = [Cout, R*S*Cin]  K-major (tap-major, channel-minor)
 // Dgrad  :  src = dy [N,P,Q,Cout], dst = dx [N,H,W,Cin],  w_* = [Cin, R*S*Cout] with the filter flipped (host); stride 1
-extern "C" int i2v_conv_tc_f32(const i2v_conv_desc* d, int dgrad, const float* src, const float* w_hi, const float* w_lo,
-                               const float* bias, const float* residual, const float* mask_src, float* dst, int flags,
-                               i2v_stream_t stream) {
+// mask_bits: [C_dst/32][M] words, M = rows of dst; forward: OUTPUT (activity bits of dst, optional); dgrad: INPUT mask
+extern "C" int i2v_conv_tc_bits_f32(const i2v_conv_desc* d, int dgrad, const float* src, const float* w_hi, const float* w_lo,
+                                    const float* bias, const float* residual, const float* mask_src, uint32_t* mask_bits,
+                                    float* dst, int flags, i2v_stream_t stream) {
     I2V_REQUIRE(d && src && w_hi && dst, "null pointer");
     I2V_REQUIRE(i2v_conv_tc_supported(d, dgrad) && (!dgrad || d->stride == 1), "shape not supported by this tensor-core entry point");
+    I2V_REQUIRE(!(mask_bits && mask_src), "pass either an f32 mask source or a bit mask, not both");
     if (d->N == 0) return I2V_OK;
     TcProblem pr{};
     pr.src = src; pr.N = d->N; pr.w_hi = w_hi; pr.w_lo = w_lo; pr.bias = bias; pr.residual = residual; pr.mask_src = mask_src;
@@ -870,12 +1053,20 @@ extern "C" int i2v_conv_tc_f32(const i2v_conv_desc* d, int dgrad, const float* s
     if (!dgrad) {
         pr.H = d->H; pr.W = d->W; pr.C = d->Cin; pr.P = d->P; pr.Q = d->Q; pr.Cout = d->Cout; pr.stride = d->stride;
         pr.lower_h = pr.lower_w = -d->pad; pr.upper_h = d->pad - (d->R - 1); pr.upper_w = d->pad - (d->S - 1);
+        pr.bits_out = mask_bits;
     } else {
         const int padp = d->R - 1 - d->pad;
         pr.H = d->P; pr.W = d->Q; pr.C = d->Cout; pr.P = d->H; pr.Q = d->W; pr.Cout = d->Cin; pr.stride = 1;
         pr.lower_h = pr.lower_w = -padp; pr.upper_h = padp - (d->R - 1); pr.upper_w = padp - (d->S - 1);
+        pr.mask_bits = mask_bits;
     }
     return tc_run(pr, as_stream(stream));
+}
+
+extern "C" int i2v_conv_tc_f32(const i2v_conv_desc* d, int dgrad, const float* src, const float* w_hi, const float* w_lo,
+                               const float* bias, const float* residual, const float* mask_src, float* dst, int flags,
+                               i2v_stream_t stream) {
+    return i2v_conv_tc_bits_f32(d, dgrad, src, w_hi, w_lo, bias, residual, mask_src, nullptr, dst, flags, stream);
 }
 
 // Strided data gradient, one stride-parity class per call.  Image rows h = stride*i + ph (columns likewise)

@@ -283,6 +283,7 @@ class NativeEngine:
             use_tensor_cores = os.environ.get("I2V_NATIVE_TC", "1") != "0"
         self.use_tc = bool(use_tensor_cores)
         self.use_stem = os.environ.get("I2V_NATIVE_STEM", "1") != "0"   # dedicated first-layer kernels
+        self.use_bits = os.environ.get("I2V_NATIVE_BITS", "1") != "0"   # ReLU-backward masks as bits (TMA epilogue)
         self._cache = {}
 
     @property
@@ -296,7 +297,7 @@ class NativeEngine:
         if plan is not None:
             return plan
         dims = {"img": (h, w)}
-        acts, grads, argmax, descs = {}, {}, {}, {}
+        acts, grads, argmax, descs, bits = {}, {}, {}, {}, {}
         for op in self.ops:
             if op.kind == "conv":
                 ih, iw = dims[op.x]
@@ -304,6 +305,10 @@ class NativeEngine:
                 dims[op.y] = (oh, ow)
                 d = capi.ConvDesc(n, ih, iw, op.cin, op.cout, op.R, op.R, op.stride, op.pad, oh, ow)
                 descs[op.name] = d
+                # ReLU outputs produced by the tensor-core kernel also leave their activity as BITS ([C/32, M] words):
+                # the data gradients that need 1[activation > 0] then read 1/32 of the bytes (and run the TMA epilogue)
+                if op.relu and self.use_bits and self.use_tc and not op.x_nchw and capi.conv_tc_supported(d, 0):
+                    bits[op.y] = torch.empty(op.cout // 32, n * oh * ow, device=device, dtype=torch.int32)
             elif op.kind == "pool":
                 ih, iw = dims[op.x]
                 dims[op.y] = op.out_hw(ih, iw)
@@ -316,7 +321,7 @@ class NativeEngine:
         for name, t in acts.items():
             if name not in self.hook_bufs:
                 grads[name] = torch.empty_like(t)
-        plan = dict(dims=dims, acts=acts, grads=grads, argmax=argmax, descs=descs,
+        plan = dict(dims=dims, acts=acts, grads=grads, argmax=argmax, descs=descs, bits=bits,
                     gimg=torch.empty(n, 3, h, w, device=device, dtype=torch.float32))
         if len(self._cache) > 4:
             self._cache.clear()
@@ -324,22 +329,27 @@ class NativeEngine:
         return plan
 
     # ---- forward -------------------------------------------------------------------------------------
-    def _conv_fwd(self, op, d, x, y, residual):
+    def _conv_fwd(self, op, d, x, y, residual, bits_out=None):
         if op.x_nchw and residual is None and self.use_stem and capi.conv_stem_supported(d):
             capi.conv_stem_fwd(d, x, op.w_stem, op.bias, y, relu=op.relu)
         elif self.use_tc and not op.x_nchw and capi.conv_tc_supported(d, 0):
             hi, lo, rna = op.tc_fwd
             capi.conv_tc(d, 0, x, hi if self.tf32x3 else rna, lo if self.tf32x3 else None, op.bias, residual, None, y,
-                         relu=op.relu)
+                         relu=op.relu, mask_bits=bits_out)
         else:
             capi.conv_fwd_simt(d, x, op.b_fwd, op.bias, residual, y, relu=op.relu, x_nchw=op.x_nchw)
 
-    def _conv_dgrad(self, op, d, dy, addend, mask_src, dx):
+    def _conv_dgrad(self, op, d, dy, addend, mask_src, dx, mask_bits=None):
         if op.x_nchw and addend is None and mask_src is None and self.use_stem and capi.conv_stem_supported(d):
             capi.conv_stem_dgrad(d, dy, op.b_fwd, dx)
         elif self.use_tc and not op.x_nchw and op.stride == 1 and capi.conv_tc_supported(d, 1):
             hi, lo, rna = op.tc_dgrad
-            capi.conv_tc(d, 1, dy, hi if self.tf32x3 else rna, lo if self.tf32x3 else None, None, addend, mask_src, dx)
+            if mask_src is not None and mask_bits is not None:
+                mask_src = None                                   # same mask, 1/32 of the bytes
+            else:
+                mask_bits = None
+            capi.conv_tc(d, 1, dy, hi if self.tf32x3 else rna, lo if self.tf32x3 else None, None, addend, mask_src, dx,
+                         mask_bits=mask_bits)
         elif (self.use_tc and not op.x_nchw and op.stride > 1 and capi.conv_tc_supported(d, 1)
               and (addend is None or addend is dx or all(v is not None for v in op.tc_dgrad_cls.values()))):
             # strided: one dense launch per stride-parity class; classes without taps keep what is there
@@ -363,7 +373,8 @@ class NativeEngine:
         for op in self.ops:
             if op.kind == "conv":
                 x = img if op.x == "img" else acts[op.x]
-                self._conv_fwd(op, plan["descs"][op.name], x, acts[op.y], acts[op.residual] if op.residual else None)
+                self._conv_fwd(op, plan["descs"][op.name], x, acts[op.y], acts[op.residual] if op.residual else None,
+                               plan["bits"].get(op.y) if need_grad else None)
             elif op.kind == "pool":
                 capi.maxpool_fwd(acts[op.x], acts[op.y], plan["argmax"][op.y], op.k, op.stride, op.pad)
             else:
@@ -432,7 +443,7 @@ class NativeEngine:
                         raise RuntimeError("internal: two addends for %s" % op.x)
                 elif op.x in pending:
                     addend = pending.pop(op.x)
-                self._conv_dgrad(op, plan["descs"][op.name], gy, addend, mask, dx)
+                self._conv_dgrad(op, plan["descs"][op.name], gy, addend, mask, dx, plan["bits"].get(op.x))
                 ready.add(op.x)
             elif op.kind == "pool":
                 mask = acts[op.x] if op.x in self.relu_typed else None

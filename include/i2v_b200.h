@@ -203,6 +203,15 @@ int i2v_conv_tc_supported(const i2v_conv_desc* d, int dgrad);
 int i2v_conv_tc_f32(const i2v_conv_desc* d, int dgrad, const float* src, const float* w_hi, const float* w_lo,
                     const float* bias, const float* residual, const float* mask_src, float* dst, int flags,
                     i2v_stream_t stream);
+/* Same, with the ReLU-backward mask as BITS instead of an f32 tensor (1/32 of the mask traffic; the backward of
+ * torch's ReLU, image_attacks.py:352 through autograd).  mask_bits = [C_dst/32][M] uint32 words, M = rows of dst,
+ * bit j of word (w, m) <-> element (m, 32w + j).  dgrad = 0: OUTPUT, the activity bits 1[dst > 0] of this
+ * convolution's result (optional);  dgrad = 1: INPUT, dst is zeroed where the bit is clear.  mask_src and
+ * mask_bits are mutually exclusive.  With dense output rows and no f32 mask this entry point runs the TMA
+ * epilogue (TMEM -> swizzled shared-memory slot -> cp.async.bulk.tensor store; residual by TMA load).       */
+int i2v_conv_tc_bits_f32(const i2v_conv_desc* d, int dgrad, const float* src, const float* w_hi, const float* w_lo,
+                         const float* bias, const float* residual, const float* mask_src, uint32_t* mask_bits,
+                         float* dst, int flags, i2v_stream_t stream);
 
 /* Debug: subsequent tensor-core launches make CTA 0 stamp clock64() at 8 pipeline points of each of its first
  * `tiles` tiles into device_buf[tiles][8] (see TcArgs::trace in csrc/conv_tc.cu); NULL switches it off.     */

@@ -265,6 +265,58 @@ def test_conv_tc_fwd_and_dgrad(shape, x3):
         assert err <= tol, ("dgrad", err, tol)
 
 
+def _pack_bits(t_nhwc):
+    """[N,H,W,C] bool -> int32 [C/32, M] words, bit j of word (w, m) <-> channel 32w + j (include/i2v_b200.h)."""
+    C = t_nhwc.shape[-1]
+    b = t_nhwc.reshape(-1, C // 32, 32).to(torch.int64)
+    words = (b << torch.arange(32, device=b.device, dtype=torch.int64)).sum(-1)        # [M, C/32]
+    words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32)
+    return words.t().contiguous()
+
+
+@pytest.mark.parametrize("shape", [(2, 56, 56, 64, 256, 1, 1, 0), (3, 28, 28, 128, 128, 3, 1, 1), (1, 13, 13, 64, 192, 3, 1, 1),
+                                   (5, 28, 28, 512, 128, 1, 1, 0), (11, 4, 4, 64, 64, 3, 1, 1), (2, 56, 56, 64, 64, 1, 1, 0)])
+@pytest.mark.parametrize("x3", [True, False])
+def test_conv_tc_bit_masks(shape, x3):
+    """TMA epilogue: the forward's activity bits equal 1[y > 0] exactly, and a data gradient masked by bits (with an
+    in-place addend) is bit-identical to the same launch with the f32 mask source (register epilogue)."""
+    N, H, W, Cin, Cout, k, s, p = shape
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    scale = torch.rand(Cout, generator=g) + 0.5
+    shift = torch.randn(Cout, generator=g) * 0.1
+    P, Q = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    d = capi.ConvDesc(N, H, W, Cin, Cout, k, k, s, p, P, Q)
+    ws, (fh, fl, fr), (dh, dl, dr) = _tc_operands(w, scale)
+    lay = lambda t: t.permute(0, 2, 3, 1).contiguous().to(DEV)
+    xd, bias = lay(x), shift.to(DEV)
+    res = lay(torch.randn(N, Cout, P, Q, generator=g))
+    M = N * P * Q
+    for use_res in (False, True):
+        y = torch.full((N, P, Q, Cout), float("nan"), device=DEV)
+        bits = torch.zeros(Cout // 32, M, dtype=torch.int32, device=DEV)
+        capi.conv_tc(d, 0, xd, fh if x3 else fr, fl if x3 else None, bias, res if use_res else None, None, y, relu=True,
+                     mask_bits=bits)
+        y_plain = torch.full_like(y, float("nan"))
+        capi.conv_tc(d, 0, xd, fh if x3 else fr, fl if x3 else None, bias, res if use_res else None, None, y_plain, relu=True)
+        assert torch.isfinite(y).all()
+        assert torch.equal(y, y_plain)
+        assert torch.equal(bits, _pack_bits(y > 0))
+    # data gradient: mask by bits == mask by the f32 tensor, also with dx += (in place)
+    dy = lay(torch.randn(N, Cout, P, Q, generator=g))
+    act = lay(torch.randn(N, Cin, H, W, generator=g))
+    add = lay(torch.randn(N, Cin, H, W, generator=g))
+    abits = _pack_bits(act > 0)
+    for inplace in (False, True):
+        want = add.clone() if inplace else torch.full_like(add, float("nan"))
+        capi.conv_tc(d, 1, dy, dh if x3 else dr, dl if x3 else None, None, want if inplace else add, act, want)
+        got = add.clone() if inplace else torch.full_like(add, float("nan"))
+        capi.conv_tc(d, 1, dy, dh if x3 else dr, dl if x3 else None, None, got if inplace else add, None, got, mask_bits=abits)
+        assert torch.isfinite(got).all()
+        assert torch.equal(got, want)
+
+
 @pytest.mark.parametrize("H,W,k,s,p", [(224, 224, 7, 2, 3), (64, 64, 7, 2, 3), (64, 64, 11, 4, 2), (32, 32, 3, 1, 1),
                                        (64, 64, 3, 2, 0), (37, 53, 7, 2, 3), (31, 45, 3, 2, 0), (50, 70, 11, 4, 2)])
 def test_stem_fwd_and_dgrad(H, W, k, s, p):
