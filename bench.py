@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--clips", type=int, default=CLIPS_PER_GPU, help="clips per GPU (default 16 = 512 frames)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--shapes", action="store_true", help="print a per-shape timing table of the convolutions to stderr")
     return ap.parse_args()
 
 
@@ -237,13 +238,21 @@ def run_b200_arm(args):
     value = world * N * K / (ms / 1e3)
 
     # ---- per-kernel device time of OUR kernels inside the timed region (CUDA events, same stream) -----
-    kern = {}
-    for name, e0, e1, nbytes, flops in events:
+    kern, by_shape = {}, {}
+    for name, e0, e1, nbytes, flops, detail in events:
         k = kern.setdefault(name, {"ms": 0.0, "launches": 0, "bytes": 0, "flops": 0.0})
-        k["ms"] += e0.elapsed_time(e1)
+        dt = e0.elapsed_time(e1)
+        k["ms"] += dt
         k["launches"] += 1
         k["bytes"] += nbytes
         k["flops"] += flops
+        if detail is not None:
+            d = by_shape.setdefault(detail, {"ms": 0.0, "launches": 0, "bytes": 0})
+            d["ms"] += dt; d["launches"] += 1; d["bytes"] += nbytes
+    if args.shapes and rank == 0:       # per-shape table of the tensor-core convolutions, in-situ (stderr)
+        for detail, d in sorted(by_shape.items(), key=lambda kv: -kv[1]["ms"]):
+            print("%-44s n=%-5d avg %7.1f us  %6.0f GB/s  share %.3f" % (detail, d["launches"], 1e3 * d["ms"] / d["launches"],
+                                                                        d["bytes"] / d["ms"] / 1e6, d["ms"] / ms_local), file=sys.stderr)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

@@ -53,9 +53,19 @@ def clip_of(frames, b, f):
     return frames.reshape(b, f, c, h, w).permute(0, 2, 1, 3, 4)
 
 
-def _chunk_frames(engines, N, chunk):
+def _chunk_frames(engines, N, chunk, h=None, w=None, device=None):
+    """Frames per forward/backward sub-batch: explicit argument > $I2V_CHUNK > what the engines ask for given the
+    image size and the free device memory (engines that do not size themselves report `preferred_chunk`)."""
     if chunk is None:
-        chunk = int(os.environ.get("I2V_CHUNK", "0")) or min(getattr(e, "preferred_chunk", 128) for e in engines)
+        chunk = int(os.environ.get("I2V_CHUNK", "0"))
+    if not chunk:
+        asks = []
+        for e in engines:
+            if h is not None and hasattr(e, "frames_per_chunk"):
+                asks.append(e.frames_per_chunk(h, w, N, device, share=1.0 / len(engines)))
+            else:
+                asks.append(getattr(e, "preferred_chunk", 128))
+        chunk = min(asks)
     return max(1, min(int(chunk), N))
 
 
@@ -100,7 +110,7 @@ class ImageGuidedRun:
         frames = frames_of(videos.to(device=device, dtype=torch.float32, non_blocking=True))
         N = self.N = b * f
         inner = self.inner = h * w
-        chunk = self.chunk = _chunk_frames(self.engines, N, self.chunk_request)
+        chunk = self.chunk = _chunk_frames(self.engines, N, self.chunk_request, h, w, device)
         self.spans = [(s, min(s + chunk, N)) for s in range(0, N, chunk)]
         steps = self.steps
 
@@ -172,9 +182,10 @@ class ImageGuidedRun:
         if self.tap is not None:
             # relu_masks: the activity decisions of this step's forward (valid when all frames fit one chunk)
             masks = [e.relu_masks() if hasattr(e, "relu_masks") and len(self.spans) == 1 else None for e in self.engines]
+            pools = [e.pool_indices() if hasattr(e, "pool_indices") and len(self.spans) == 1 else None for e in self.engines]
             self.tap(self.step_no, dict(g=self.g_total.clone(), cos=self.cos.clone(), mod_before=self.mod.clone(),
                                         m_before=self.m.clone(), v_before=self.v.clone(),
-                                        true_image=self.true_img.clone(), relu_masks=masks))
+                                        true_image=self.true_img.clone(), relu_masks=masks, pool_indices=pools))
         capi.adam_compose_table(self.g_total, self.m, self.v, self.mod, self.x, self.true_img, self.epsilon, self.inner,
                                 self.table, self.step_idx, BETA1, BETA2, ADAM_EPS)
         capi.step_advance(self.step_idx)
@@ -188,6 +199,125 @@ class ImageGuidedRun:
         cost_host = self.cost_log[:n].cpu().numpy() if n > 0 else np.zeros(0, dtype=np.float32)
         weights_host = self.weights_log[:n].cpu().numpy() if self.adaptive and n > 0 else None
         return LoopResult(adv, cost_host, weights_host, None)
+
+
+class DispersionRun(ImageGuidedRun):
+    """Dispersion Reduction (reference image_attacks.py:129-234, `ImageGuidedStd_Adam`): same skeleton as the
+    I2V loop (modifier 196-199, compose 211-212, Adam 221-223, final compose 230-234) with
+    cost = sum over hooked layers of `activations.std()` (214-220) and no clean-feature pass.
+
+    std() runs over the WHOLE [N,C,h,w] map, so all frames of a call are coupled: when the frames are
+    processed in several chunks the step makes two passes — forward + K6 accumulate over every chunk, then
+    forward again + K6 gradient + data gradient per chunk.  With one chunk (N <= chunk, the reference's
+    batch-size-1 runs) the single forward serves both."""
+
+    def __init__(self, engines, epsilon, steps, step_size, chunk=None, tap=None):
+        super().__init__(engines, epsilon, steps, step_size, chunk=chunk, tap=tap)
+
+    def setup(self, videos):
+        if videos.dim() != 5 or videos.shape[1] != 3:
+            raise ValueError("videos must be [b,3,f,h,w], got %s" % (tuple(videos.shape),))
+        device = torch.device("cuda", torch.cuda.current_device())
+        capi.device_check(device)
+        b, c, f, h, w = videos.shape
+        self.b, self.f = b, f
+        frames = frames_of(videos.to(device=device, dtype=torch.float32, non_blocking=True))
+        N = self.N = b * f
+        inner = self.inner = h * w
+        chunk = self.chunk = _chunk_frames(self.engines, N, self.chunk_request, h, w, device)
+        self.spans = [(s, min(s + chunk, N)) for s in range(0, N, chunk)]
+        steps = self.steps
+        self.x = torch.empty_like(frames)
+        capi.denorm(frames, self.x, inner)                                      # image_attacks.py:201
+        self.mod = torch.empty_like(frames)
+        capi.fill(self.mod, INIT_MODIFIER)                                      # image_attacks.py:197
+        self.m = torch.zeros_like(frames)
+        self.v = torch.zeros_like(frames)
+        self.true_img = torch.empty_like(frames)
+        self.g_total = torch.empty_like(frames)
+        self.acc = torch.zeros(self.n_layers, 2, device=device, dtype=torch.float64)
+        self.stats = torch.zeros(self.n_layers, 4, device=device, dtype=torch.float32)
+        self.workspace = capi.std_workspace(device)
+        self.grads = None
+        self.step_idx = torch.zeros(1, device=device, dtype=torch.int32)
+        self.cost_log = torch.zeros(max(steps, 1), device=device, dtype=torch.float32)
+        self.table = capi.adam_step_table(steps, self.step_size, BETA1, BETA2).to(device)
+        capi.compose_norm(self.x, self.mod, self.true_img, self.epsilon, inner)   # image_attacks.py:211-212
+        self.step_no = 0
+        return self
+
+    def _grad_bufs(self, feats_per_engine):
+        if self.grads is None:
+            self.grads = [[torch.empty((self.chunk,) + tuple(t.shape[1:]), device=t.device, dtype=torch.float32) for t in fe]
+                          for fe in feats_per_engine]
+        return self.grads
+
+    def _backward_chunk(self, s0, s1, feats_per_engine):
+        layer = 0
+        grads = self._grad_bufs(feats_per_engine)
+        for ei, (e, feats, gr) in enumerate(zip(self.engines, feats_per_engine, grads)):
+            gviews = []
+            for a, ga in zip(feats, gr):
+                gv = ga[:s1 - s0]
+                capi.std_grad(a, gv, self.stats[layer], relu_mask=e.relu_masked_grads)
+                gviews.append(gv)
+                layer += 1
+            g = e.input_grad(gviews)
+            if ei == 0:
+                self.g_total[s0:s1].copy_(g)
+            else:
+                self.g_total[s0:s1].add_(g)
+
+    def step(self):
+        if self.step_no >= self.steps:
+            raise RuntimeError("all %d steps of this run are done" % self.steps)
+        self.acc.zero_()
+        numel = [0] * self.n_layers
+        single = len(self.spans) == 1
+        kept = None
+        for (s0, s1) in self.spans:                                             # pass 1: statistics of every hooked map
+            layer = 0
+            feats_per_engine = []
+            for e in self.engines:
+                feats = e.features(self.true_img[s0:s1], need_grad=True)        # image_attacks.py:214
+                feats_per_engine.append(feats)
+                for a in feats:
+                    capi.std_accumulate(a, self.workspace, self.acc[layer])
+                    numel[layer] += a.numel()
+                    layer += 1
+            kept = feats_per_engine
+        for layer in range(self.n_layers):                                      # image_attacks.py:216-220
+            capi.std_finalize(self.acc[layer], numel[layer], self.stats[layer], self.cost_log, self.step_idx,
+                              add_to_cost=layer > 0)
+        if single:
+            self._backward_chunk(self.spans[0][0], self.spans[0][1], kept)      # image_attacks.py:222 (cost.backward())
+        else:
+            if len(self.engines) > 1:
+                raise NotImplementedError("multi-chunk dispersion reduction with several backbones")
+            for (s0, s1) in self.spans:                                         # pass 2: forward again, gradient, backward
+                feats_per_engine = [e.features(self.true_img[s0:s1], need_grad=True) for e in self.engines]
+                self._backward_chunk(s0, s1, feats_per_engine)
+        if self.tap is not None:
+            self.tap(self.step_no, dict(g=self.g_total.clone(), stats=self.stats.clone(), mod_before=self.mod.clone(),
+                                        m_before=self.m.clone(), v_before=self.v.clone(), true_image=self.true_img.clone()))
+        capi.adam_compose_table(self.g_total, self.m, self.v, self.mod, self.x, self.true_img, self.epsilon, self.inner,
+                                self.table, self.step_idx, BETA1, BETA2, ADAM_EPS)   # image_attacks.py:221-223, 211-212
+        capi.step_advance(self.step_idx)
+        self.step_no += 1
+
+    def finish(self):
+        adv = clip_of(self.true_img, self.b, self.f)                            # image_attacks.py:230-234
+        n = self.step_no
+        cost_host = self.cost_log[:n].cpu().numpy() if n > 0 else np.zeros(0, dtype=np.float32)
+        return LoopResult(adv, cost_host, None, None)
+
+
+def run_dispersion(engines, videos, epsilon, steps, step_size, chunk=None, tap=None):
+    run = DispersionRun(engines, epsilon, steps, step_size, chunk=chunk, tap=tap)
+    run.setup(videos)
+    for _ in range(run.steps):
+        run.step()
+    return run.finish()
 
 
 def run_image_guided(engines, videos, epsilon, steps, step_size, adaptive=False, coeffs=None, momentum=0.0,

@@ -37,11 +37,19 @@ SIGNATURES = {
     "i2v_cosine_loss_grad_f32": ([_c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_p, _c_f, _c_int, _c_p], _c_int),
     "i2v_layer_reweight_f32": ([_c_p, _c_p, _c_int, _c_f, _c_p, _c_p, _c_p, _c_p], _c_int),
     "i2v_layer_sums_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_i64, _c_int, _c_int, _c_p], _c_int),
+    "i2v_std_workspace_doubles": ([], _c_int),
+    "i2v_std_accumulate_f32": ([_c_p, _c_i64, _c_p, _c_p, _c_p], _c_int),
+    "i2v_std_finalize_f32": ([_c_p, _c_i64, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
+    "i2v_std_grad_f32": ([_c_p, _c_p, _c_i64, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_fwd_simt_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_dgrad_simt_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_stem_supported": ([_c_p], _c_int),
     "i2v_conv_stem_fwd_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_stem_dgrad_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p], _c_int),
+    "i2v_conv_stem_dgrad_tc_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p], _c_int),
+    "i2v_conv_stem_dgrad_tc_group": ([_c_p], _c_int),
+    "i2v_conv_stem_fwd_tc_group": ([_c_p], _c_int),
+    "i2v_conv_stem_fwd_tc_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_tc_supported": ([_c_p, _c_int], _c_int),
     "i2v_conv_tc_set_trace": ([_c_p, _c_int], _c_int),
     "i2v_conv_tc_f32": ([_c_p, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
@@ -91,18 +99,19 @@ def load():
 # tensors read + written once, 2 x MACs of the convolution).
 LAUNCHES = {}
 PROFILE_EVENTS = None
-_NO_KERNEL = ("i2v_device_check", "i2v_adam_step_table", "i2v_conv_tc_supported", "i2v_conv_stem_supported",
+_NO_KERNEL = ("i2v_device_check", "i2v_std_workspace_doubles", "i2v_adam_step_table", "i2v_conv_tc_supported", "i2v_conv_stem_supported",
               "i2v_conv_tc_set_trace")
 
 
 class _Timed:
-    __slots__ = ("name", "nbytes", "flops", "ev")
+    __slots__ = ("name", "nbytes", "flops", "ev", "detail")
 
-    def __init__(self, name, nbytes=0, flops=0):
+    def __init__(self, name, nbytes=0, flops=0, detail=None):
         self.name = name
         self.nbytes = nbytes
         self.flops = flops
         self.ev = None
+        self.detail = detail
 
     def __enter__(self):
         if PROFILE_EVENTS is not None:
@@ -114,7 +123,7 @@ class _Timed:
         if self.ev is not None and exc[0] is None:
             end = torch.cuda.Event(enable_timing=True)
             end.record()
-            PROFILE_EVENTS.append((self.name, self.ev, end, self.nbytes, self.flops))
+            PROFILE_EVENTS.append((self.name, self.ev, end, self.nbytes, self.flops, self.detail))
         return False
 
 
@@ -263,6 +272,30 @@ def _conv_cost(d):
     return 4 * (nin + nout), flops
 
 
+# ------------------------------------------------------------------------------- K6 (dispersion reduction)
+def std_workspace(device):
+    return torch.empty(load().i2v_std_workspace_doubles(), device=device, dtype=torch.float64)
+
+
+def std_accumulate(a, workspace, acc):
+    """acc[0] += sum(a), acc[1] += sum(a*a) (float64 [2] device tensor)."""
+    with _Timed("i2v_std_accumulate_f32", 4 * a.numel()):
+        _check(load().i2v_std_accumulate_f32(_dev(a), a.numel(), _dev(workspace, torch.float64), _dev(acc, torch.float64),
+                                             _stream()), "i2v_std_accumulate_f32")
+
+
+def std_finalize(acc, n_total, stats, cost_log=None, step_idx=None, add_to_cost=False):
+    """stats[0:3] = mean, unbiased std, 1/((n-1) std); cost_log[step] (+)= std."""
+    _check(load().i2v_std_finalize_f32(_dev(acc, torch.float64), int(n_total), _dev(stats), _dev(cost_log),
+                                       _dev(step_idx, torch.int32), int(add_to_cost), _stream()), "i2v_std_finalize_f32")
+
+
+def std_grad(a, grad, stats, relu_mask=False):
+    with _Timed("i2v_std_grad_f32", 8 * a.numel()):
+        _check(load().i2v_std_grad_f32(_dev(a), _dev(grad), a.numel(), _dev(stats), int(bool(relu_mask)), _stream()),
+               "i2v_std_grad_f32")
+
+
 # ------------------------------------------------------------------------------- K4 / K5 (CUDA-core path)
 def conv_fwd_simt(desc, x, bmat, bias, residual, y, relu=False, x_nchw=False):
     flags = (EPI_RELU if relu else 0) | (LAYOUT_X_NCHW if x_nchw else 0)
@@ -294,6 +327,33 @@ def conv_stem_dgrad(desc, dy, w, dx):
                "i2v_conv_stem_dgrad_f32")
 
 
+def conv_stem_dgrad_tc(desc, dy, wz_hi, wz_lo, z_scratch, dx):
+    """First-layer data gradient as a tcgen05 GEMM over the output channels + col2im (see include/i2v_b200.h)."""
+    nb, fl = _conv_cost(desc)
+    with _Timed("i2v_conv_stem_dgrad_f32", nb, fl):
+        _check(load().i2v_conv_stem_dgrad_tc_f32(ctypes.addressof(desc), _dev(dy), _dev(wz_hi), _dev(wz_lo), _dev(z_scratch),
+                                                 _dev(dx), _stream()), "i2v_conv_stem_dgrad_tc_f32")
+
+
+def stem_dgrad_tc_scratch_floats(desc):
+    g = load().i2v_conv_stem_dgrad_tc_group(ctypes.addressof(desc))
+    return (3 * desc.R * desc.S + 31) // 32 * 32 * g * desc.P * desc.Q
+
+
+def conv_stem_fwd_tc(desc, x, wk_hi, wk_lo, bias, col_scratch, y, relu=False):
+    """First-layer forward as im2col + tcgen05 GEMM (see include/i2v_b200.h)."""
+    nb, fl = _conv_cost(desc)
+    with _Timed("i2v_conv_stem_fwd_f32", nb, fl):
+        _check(load().i2v_conv_stem_fwd_tc_f32(ctypes.addressof(desc), _dev(x), _dev(wk_hi), _dev(wk_lo), _dev(bias),
+                                               _dev(col_scratch), _dev(y), EPI_RELU if relu else 0, _stream()),
+               "i2v_conv_stem_fwd_tc_f32")
+
+
+def stem_fwd_tc_scratch_floats(desc):
+    g = load().i2v_conv_stem_fwd_tc_group(ctypes.addressof(desc))
+    return (3 * desc.R * desc.S + 31) // 32 * 32 * g * desc.P * desc.Q
+
+
 def conv_tc_set_trace(buf, tiles=0):
     """Debug: buf = int64 CUDA tensor [tiles, 8] (or None) receiving CTA 0's pipeline time stamps."""
     _check(load().i2v_conv_tc_set_trace(None if buf is None else _dev(buf, torch.int64), tiles), "i2v_conv_tc_set_trace")
@@ -310,7 +370,13 @@ def conv_tc(desc, dgrad, src, w_hi, w_lo, bias, residual, mask_src, dst, relu=Fa
     nb += 4 * dst.numel() * ((residual is not None) + (mask_src is not None))
     if mask_bits is not None:
         nb += 4 * mask_bits.numel()
-    with _Timed("i2v_conv_tc_f32", nb, fl):
+    detail = None
+    if PROFILE_EVENTS is not None:
+        detail = "%s %dx%d %d->%d k%ds%d%s%s%s" % ("dgrad" if dgrad else "fwd", desc.H, desc.W, desc.Cin, desc.Cout, desc.R,
+                                                  desc.stride, " +res" if residual is not None else "",
+                                                  " +mask" if mask_src is not None else "",
+                                                  " +bits" if mask_bits is not None else "")
+    with _Timed("i2v_conv_tc_f32", nb, fl, detail):
         _check(load().i2v_conv_tc_bits_f32(ctypes.addressof(desc), int(dgrad), _dev(src), _dev(w_hi), _dev(w_lo), _dev(bias),
                                            _dev(residual), _dev(mask_src), _dev(mask_bits, torch.int32), _dev(dst),
                                            EPI_RELU if relu else 0, _stream()),

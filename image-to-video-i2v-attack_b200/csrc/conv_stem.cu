@@ -171,6 +171,114 @@ stem_dgrad_kernel(const StemArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// col2im of the tensor-core first-layer data gradient (i2v_conv_stem_dgrad_tc_f32): zt = planes [(c,r,s)][m],
+// m = (n,p,q).  One image pixel per thread; a warp owns 32 pixels of ONE stride class of one image row, so its
+// tap set is warp-uniform and every plane read is 128 contiguous bytes.  Taps are summed in (r, s) order.
+// grid (ceil(W / (32*stride*warps_per_class...)), H, N): block = 8 warps = 8/stride pixel groups x stride classes
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+stem_col2im_kernel(const float* __restrict__ zt, float* __restrict__ dx, int N, int H, int W, int P, int Q, int R, int st,
+                   int pad, int64_t M) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cls = warp % st;                                   // w mod stride of this warp's pixels
+    const int grp = warp / st;                                   // 8/st groups of 32 pixels per block
+    const int h = blockIdx.y, n = blockIdx.z;
+    const int w = (blockIdx.x * (8 / st) + grp) * 32 * st + lane * st + cls;
+    if (w >= W) return;
+    const int RR = R * R;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+    for (int r = (h + pad) % st; r < R; r += st) {
+        const int hp = h + pad - r;
+        if (hp < 0) break;
+        const int p = hp / st;
+        if (p >= P) continue;
+        for (int s = (cls + pad) % st; s < R; s += st) {           // (w + pad) % st == (cls + pad) % st
+            const int wq = w + pad - s;
+            if (wq < 0) break;
+            const int q = wq / st;
+            if (q >= Q) continue;
+            const float* z = zt + (int64_t)(r * R + s) * M + ((int64_t)n * P + p) * Q + q;
+            acc0 += __ldg(z);
+            acc1 += __ldg(z + (int64_t)RR * M);
+            acc2 += __ldg(z + (int64_t)2 * RR * M);
+        }
+    }
+    const int64_t o = (((int64_t)n * 3) * H + h) * W + w;
+    dx[o] = acc0;
+    dx[o + (int64_t)H * W] = acc1;
+    dx[o + (int64_t)2 * H * W] = acc2;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// im2col of the tensor-core first-layer forward (i2v_conv_stem_fwd_tc_f32): x [N,3,H,W] -> col [(n,p,q)][Kp],
+// k = (c,r,s), zero beyond 3*R*R and outside the image.  One CTA per output row (n, p): the R input rows of the
+// three channels are staged in shared memory (zero-padded), then every thread assembles float4s of the row-major
+// patch matrix through a k -> staged-offset table; global writes are fully coalesced (Kp floats per pixel).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+stem_im2col_kernel(const float* __restrict__ x, float* __restrict__ col, int n0, int H, int W, int P, int Q, int R, int st,
+                   int pad, int Kp) {
+    extern __shared__ __align__(16) float smem[];
+    const int pitch = (Q - 1) * st + R;                         // staged columns: image columns -pad .. -pad+pitch-1
+    int* tbl = reinterpret_cast<int*>(smem);                     // [Kp] staged offset of tap k at q = 0, or -1
+    float* rows = smem + Kp;                                     // [3][R][pitch]
+    const int p = blockIdx.x, n = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int K = 3 * R * R;
+    for (int k = tid; k < Kp; k += 256) {
+        int off = -1;
+        if (k < K) { const int c = k / (R * R), rs = k - c * R * R, r = rs / R, s = rs - r * R; off = (c * R + r) * pitch + s; }
+        tbl[k] = off;
+    }
+    const int iy0 = p * st - pad;
+    for (int i = tid; i < 3 * R * pitch; i += 256) {
+        const int cr = i / pitch, xx = i - cr * pitch;
+        const int c = cr / R, r = cr - c * R;
+        const int iy = iy0 + r, ix = xx - pad;
+        float v = 0.f;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + (((int64_t)(n0 + n) * 3 + c) * H + iy) * W + ix);
+        rows[i] = v;
+    }
+    __syncthreads();
+    const int k4n = Kp / 4;
+    float4* out = reinterpret_cast<float4*>(col + ((int64_t)n * P + p) * Q * Kp);
+    for (int i = tid; i < Q * k4n; i += 256) {
+        const int q = i / k4n, k = (i - q * k4n) * 4;
+        const int base = q * st;
+        const int o0 = tbl[k], o1 = tbl[k + 1], o2 = tbl[k + 2], o3 = tbl[k + 3];
+        float4 v;
+        v.x = o0 >= 0 ? rows[o0 + base] : 0.f;
+        v.y = o1 >= 0 ? rows[o1 + base] : 0.f;
+        v.z = o2 >= 0 ? rows[o2 + base] : 0.f;
+        v.w = o3 >= 0 ? rows[o3 + base] : 0.f;
+        out[i] = v;
+    }
+}
+
+// frames [n0, n0 + n) of x -> col (rows of frame n0 first)
+int stem_im2col_launch(const float* x, float* col, int n0, int n, int H, int W, int P, int Q, int R, int stride, int pad, int Kp,
+                       cudaStream_t st) {
+    const int pitch = (Q - 1) * stride + R;
+    const size_t smem = ((size_t)Kp + (size_t)3 * R * pitch) * sizeof(float);
+    I2V_REQUIRE(smem <= 200 * 1024, "stem im2col: input rows do not fit in shared memory");
+    cudaError_t e = cudaFuncSetAttribute(stem_im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "i2v_conv_stem_fwd_tc_f32 (im2col shared memory)");
+    dim3 grid((unsigned)P, (unsigned)n);
+    stem_im2col_kernel<<<grid, 256, smem, st>>>(x, col, n0, H, W, P, Q, R, stride, pad, Kp);
+    I2V_LAUNCH_CHECK("i2v_conv_stem_fwd_tc_f32 (im2col)");
+    return I2V_OK;
+}
+
+int stem_col2im_launch(const float* zt, float* dx, int N, int H, int W, int P, int Q, int R, int stride, int pad, cudaStream_t st) {
+    I2V_REQUIRE(stride == 1 || stride == 2 || stride == 4 || stride == 8, "col2im: stride must divide 8");
+    const int per_block = (8 / stride) * 32 * stride;              // image columns per block
+    dim3 grid((unsigned)((W + per_block - 1) / per_block), (unsigned)H, (unsigned)N);
+    stem_col2im_kernel<<<grid, 256, 0, st>>>(zt, dx, N, H, W, P, Q, R, stride, pad, (int64_t)N * P * Q);
+    I2V_LAUNCH_CHECK("i2v_conv_stem_dgrad_tc_f32 (col2im)");
+    return I2V_OK;
+}
+
 }  // namespace i2v
 
 using namespace i2v;

@@ -49,6 +49,9 @@ struct TcArgs {
     float* dst;              // [M, Cout]
     const uint32_t* mask_bits;   // [Cout/32][M] bit j of word (w, m) = 1[mask source (m, 32w+j) > 0], or null   (TMA epilogue)
     uint32_t* bits_out;          // [Cout/32][M] activity bits of dst written by the epilogue, or null           (TMA epilogue)
+    int out_transposed;          // TMA epilogue: dst is [Cout][M] (column planes) instead of [M][Cout]; no residual / bits
+    int store_cols;              // TMA epilogue: 32-column sub-tiles starting at or beyond this column are not stored
+    int prefetch_tiles;          // L2 prefetch distance in tiles of this CTA (A of 1x1 convolutions, residual sub-tiles); 0 = off
     int64_t M;               // N*P*Q GEMM rows
     int Cout;
     int P, Q;                // row grid: m = (img, p, q)
@@ -123,6 +126,11 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// L2 prefetch of a 2-D tile (no shared memory, no completion tracking): turns the later TMA load's DRAM latency into an
+// L2 hit, which is what a pipeline with only 2-3 shared-memory stages of 48-64 KB needs
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" :: "l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory");
 }
@@ -479,6 +487,14 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     const int p = rem / args.Q, q = rem - p * args.Q;
                     base_h = p * args.stride + args.lower_h;
                     base_w = q * args.stride + args.lower_w;
+                } else if (args.prefetch_tiles > 0) {
+                    // the first tiles' prefetches are issued up front, afterwards one tile per tile
+                    for (int d = (tno == 0 ? 1 : args.prefetch_tiles); d <= args.prefetch_tiles; ++d) {
+                        const int ptile = tile + d * (int)gridDim.x;
+                        if (ptile >= num_tiles) break;
+                        const int pm = ptile / num_n_tiles;
+                        for (int cb = 0; cb < args.cblocks; ++cb) tma_prefetch_l2_2d(&tmA, cb * TC_BK, pm * TC_BM);
+                    }
                 }
                 for (int r = 0; r < args.taps_h; ++r)
                     for (int s = 0; s < args.taps_w; ++s)
@@ -487,6 +503,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                             const uint32_t ph = (uint32_t)(it / stages) & 1;
                             mbar_wait(&empty_bar[st], ph ^ 1);
                             if ((r | s | cb) == 0) TC_TRACE(0, tno);
+                            // (measured: deriving B_lo on the fly in the split warps instead of loading it — 25-33 % fewer TMA
+                            // rows per k-step — made every layer 5-15 % SLOWER: the four split warps are the tighter resource)
                             mbar_arrive_expect_tx(&full_bar[st], TC_A_BYTES + L::B_BYTES * (X3 ? 2 : 1));
                             if (IM2COL) tma_load_im2col_4d(&tmA, &full_bar[st], stage_a(st), cb * TC_BK, base_w, base_h, img, (uint16_t)s, (uint16_t)r);
                             else        tma_load_2d(&tmA, &full_bar[st], stage_a(st), cb * TC_BK, (int)m0);
@@ -580,6 +598,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 row = m_tile * TC_BM;
             };
             int col, row;
+            const uint32_t pf = has_res ? (uint32_t)args.prefetch_tiles * SUBS : 0u;   // L2 prefetch distance in sub-tiles
+            for (uint32_t k = 2; k < 2 + pf && k < total; ++k) { coords(k, col, row); tma_prefetch_l2_2d(&tmRes, col, row); }
             for (uint32_t k = 0; k < 2 && k < total; ++k) {     // prime both slots
                 if (has_res) {
                     coords(k, col, row);
@@ -593,11 +613,15 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 const uint32_t s = k & 1, ph = (k >> 1) & 1;
                 mbar_wait(&out_ready[g * 2 + s], ph);           // the group's 128 threads wrote the slot (and fenced)
                 coords(k, col, row);
-                tma_store_2d(&tmOut, sbase + (size_t)s * EPI_SLOT_BYTES, col, row);
+                if (col < args.store_cols) {
+                    if (args.out_transposed) tma_store_2d(&tmOut, sbase + (size_t)s * EPI_SLOT_BYTES, row, col);
+                    else                     tma_store_2d(&tmOut, sbase + (size_t)s * EPI_SLOT_BYTES, col, row);
+                }
                 bulk_commit();
                 if (k + 2 < total) {
                     bulk_wait_read0();                           // the store has read the slot: it may be refilled
                     if (has_res) {
+                        if (pf && k + 2 + pf < total) { coords(k + 2 + pf, col, row); tma_prefetch_l2_2d(&tmRes, col, row); }
                         coords(k + 2, col, row);
                         mbar_arrive_expect_tx(&slot_ready[g * 2 + s], EPI_SLOT_BYTES);
                         tma_load_2d(&tmRes, &slot_ready[g * 2 + s], sbase + (size_t)s * EPI_SLOT_BYTES, col, row);
@@ -657,6 +681,14 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 mbar_wait(&slot_ready[g * 2 + s], ph);          // residual landed / previous store has read the slot
                 uint8_t* srow = sbase + (size_t)s * EPI_SLOT_BYTES;
                 const float* bs = bias_s + n0 + c0;
+                if (args.out_transposed) {                       // slot = [32 columns][128 rows]: plain bias add, no swizzle
+                    float* tcol = reinterpret_cast<float*>(staging + (size_t)(g * 2 + s) * EPI_SLOT_BYTES) + row;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) tcol[i * TC_BM] = __uint_as_float(a[i]) + bs[i];
+                    fence_proxy_async();
+                    mbar_arrive(&out_ready[g * 2 + s]);
+                    continue;
+                }
                 const uint32_t mword = mw[j];
                 uint32_t oword = 0;
 #pragma unroll
@@ -821,6 +853,20 @@ static int make_map_2d(CUtensorMap* map, const float* base, uint64_t rows, uint6
     return I2V_OK;
 }
 
+// 2-D row-major [rows, cols] f32, box [box_rows, box_cols], no swizzle (transposed epilogue store: rows = channels,
+// cols = GEMM rows)
+static int make_map_2d_plain(CUtensorMap* map, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols) {
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * sizeof(float)};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (plain) failed (%d) rows=%llu cols=%llu", (int)r, (unsigned long long)rows, (unsigned long long)cols); return I2V_ECUDA; }
+    return I2V_OK;
+}
+
 // im2col-mode map over an NHWC activation tensor: 32 channels x 128 pixels per load
 // Bounding box of the window corner in source coordinates: [lower, dim - 1 + upper] per axis (w, h).
 // Forward conv: lower = -pad, upper = pad - (filter - 1) (cutlass/conv/collective/detail.hpp
@@ -861,6 +907,16 @@ static int get_map_2d(CUtensorMap* out, const float* base, int rows, int cols, i
     auto it = g_maps.find(key);
     if (it != g_maps.end()) { *out = it->second; return I2V_OK; }
     if (int r = make_map_2d(out, base, (uint64_t)rows, (uint64_t)cols, (uint32_t)box_rows)) return r;
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps.emplace(key, *out);
+    return I2V_OK;
+}
+static int get_map_2d_plain(CUtensorMap* out, const float* base, int rows, int cols, int box_rows, int box_cols) {
+    MapKey key{base, rows, cols, box_rows, box_cols, 0, 0, 0, 3};
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return I2V_OK; }
+    if (int r = make_map_2d_plain(out, base, (uint64_t)rows, (uint64_t)cols, (uint32_t)box_rows, (uint32_t)box_cols)) return r;
     if (g_maps.size() > 4096) g_maps.clear();
     g_maps.emplace(key, *out);
     return I2V_OK;
@@ -945,6 +1001,7 @@ struct TcProblem {
     const float* bias; const float* residual; const float* mask_src; float* dst; int relu;
     int out_s, out_h0, out_w0, out_H, out_W;
     const uint32_t* mask_bits; uint32_t* bits_out;
+    int out_transposed, store_cols;     // TMA epilogue: dst = [Cout][M]; only columns < store_cols are written (0 = all)
 };
 
 static int tc_run(const TcProblem& pr, cudaStream_t st) {
@@ -979,14 +1036,22 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
     if (x3) { if (int r = get_map_2d(&tmBlo, pr.w_lo, pr.Cout, Ktot, BN)) return r; }
     else tmBlo = tmBhi;
     tmOut = tmBhi; tmRes = tmBhi;
+    I2V_REQUIRE(!pr.out_transposed || (epi_tma && !pr.residual && !pr.mask_bits && !pr.bits_out && !pr.relu && M % 4 == 0),
+                "transposed output needs the TMA epilogue without residual / masks / ReLU and M % 4 == 0");
     if (epi_tma) {
-        if (int r = get_map_2d(&tmOut, pr.dst, (int)M, pr.Cout, TC_BM)) return r;
+        if (pr.out_transposed) { if (int r = get_map_2d_plain(&tmOut, pr.dst, pr.Cout, (int)M, 32, TC_BM)) return r; }
+        else                   { if (int r = get_map_2d(&tmOut, pr.dst, (int)M, pr.Cout, TC_BM)) return r; }
         if (pr.residual) { if (int r = get_map_2d(&tmRes, pr.residual, (int)M, pr.Cout, TC_BM)) return r; }
     }
 
     TcArgs a{};
     a.bias = pr.bias; a.residual = pr.residual; a.mask_src = pr.mask_src; a.dst = pr.dst;
     a.mask_bits = pr.mask_bits; a.bits_out = pr.bits_out;
+    a.out_transposed = pr.out_transposed; a.store_cols = pr.store_cols > 0 ? pr.store_cols : pr.Cout;
+    // measured (profiles/): no gain in the attack pipeline, where a layer's input was written by the previous launch and
+    // is largely L2-resident already -> off by default
+    static const int prefetch_tiles = getenv("I2V_TC_PREFETCH") ? atoi(getenv("I2V_TC_PREFETCH")) : 0;
+    a.prefetch_tiles = prefetch_tiles > 0 ? (prefetch_tiles < 8 ? prefetch_tiles : 8) : 0;
     a.M = M; a.Cout = pr.Cout; a.P = pr.P; a.Q = pr.Q; a.stride = pr.stride; a.lower_h = pr.lower_h; a.lower_w = pr.lower_w;
     a.taps_h = pr.taps_h; a.taps_w = pr.taps_w; a.cblocks = pr.C / 32; a.relu = pr.relu;
     a.out_s = pr.out_s; a.out_h0 = pr.out_h0; a.out_w0 = pr.out_w0; a.out_H = pr.out_H; a.out_W = pr.out_W;
@@ -1067,6 +1132,90 @@ extern "C" int i2v_conv_tc_f32(const i2v_conv_desc* d, int dgrad, const float* s
                                const float* bias, const float* residual, const float* mask_src, float* dst, int flags,
                                i2v_stream_t stream) {
     return i2v_conv_tc_bits_f32(d, dgrad, src, w_hi, w_lo, bias, residual, mask_src, nullptr, dst, flags, stream);
+}
+
+// First-layer data gradient on the tensor cores.  dcost/dimage[n,c,h,w] = sum_{r,s,co} dy[n,p,q,co] * W[co,c,r,s] with
+// h = stride*p - pad + r (w likewise) has only three output channels: as an implicit GEMM over image pixels it would
+// waste the tensor core on N = 3.  Instead the contraction over co is done FIRST, as a plain GEMM
+//     Z[(n,p,q), (c,r,s)] = sum_co dy[(n,p,q), co] * W[co, (c,r,s)]          (M = N*P*Q, N = 3*R*S padded, K = Cout)
+// whose result is stored transposed (planes Z^T[(c,r,s)][m]) by the TMA epilogue, and a col2im pass then gathers
+// the <= ceil(R/stride)^2 taps of every image pixel from those planes with fully coalesced reads (each Z element
+// is read exactly once).  wz_* = [NZ, Cout] K-major = w_stem rows (c,r,s) zero-padded to NZ = ceil(3*R*S / 64) * 64.
+// bytes of scratch a frame group may take ($I2V_STEM_GROUP_MB, default 48 MB: L2-resident between the two passes)
+static int64_t stem_group_bytes() {
+    static const int64_t mb = getenv("I2V_STEM_GROUP_MB") ? atoll(getenv("I2V_STEM_GROUP_MB")) : 48;
+    return (mb > 0 ? mb : 48) << 20;
+}
+
+extern "C" int i2v_conv_stem_dgrad_tc_group(const i2v_conv_desc* d) {
+    if (!d) return 0;
+    const int64_t per_frame = (int64_t)d->P * d->Q * ((3 * d->R * d->S + 31) / 32 * 32) * 4;
+    int64_t g = stem_group_bytes() / (per_frame > 0 ? per_frame : 1);
+    if (g < 1) g = 1;
+    if (g > d->N) g = d->N;
+    while (g > 1 && (g * d->P * d->Q) % 4 != 0) --g;             // transposed TMA store: plane pitch multiple of 16 bytes
+    return (int)g;
+}
+
+extern "C" int i2v_conv_stem_dgrad_tc_f32(const i2v_conv_desc* d, const float* dy, const float* wz_hi, const float* wz_lo,
+                                          float* z_scratch, float* dx, i2v_stream_t stream) {
+    I2V_REQUIRE(d && dy && wz_hi && z_scratch && dx, "null pointer");
+    I2V_REQUIRE(d->Cin == 3 && d->R == d->S && d->Cout % 32 == 0 && d->stride >= 1 && d->pad < d->R, "not a first-layer shape");
+    if (d->N == 0) return I2V_OK;
+    const int cols = 3 * d->R * d->S;
+    const int NZ = (cols + 63) / 64 * 64;
+    // frames in groups whose Z planes (<= ~48 MB) are still L2-resident when the col2im pass reads them
+    const int G = i2v_conv_stem_dgrad_tc_group(d);
+    for (int n0 = 0; n0 < d->N; n0 += G) {
+        const int n = d->N - n0 < G ? d->N - n0 : G;
+        I2V_REQUIRE(((int64_t)n * d->P * d->Q) % 4 == 0, "frames-per-group * P * Q must be a multiple of 4");
+        TcProblem pr{};
+        pr.src = dy + (int64_t)n0 * d->P * d->Q * d->Cout; pr.N = n; pr.H = d->P; pr.W = d->Q; pr.C = d->Cout;
+        pr.P = d->P; pr.Q = d->Q; pr.stride = 1;
+        pr.taps_h = pr.taps_w = 1;
+        pr.w_hi = wz_hi; pr.w_lo = wz_lo; pr.Cout = NZ; pr.dst = z_scratch;
+        pr.out_transposed = 1; pr.store_cols = (cols + 31) / 32 * 32;
+        if (int r = tc_run(pr, as_stream(stream))) return r;
+        if (int r = stem_col2im_launch(z_scratch, dx + (int64_t)n0 * 3 * d->H * d->W, n, d->H, d->W, d->P, d->Q, d->R, d->stride,
+                                       d->pad, as_stream(stream))) return r;
+    }
+    return I2V_OK;
+}
+
+// First-layer forward on the tensor cores: a 12-byte pixel cannot be a TMA row, so the patch matrix
+// col[(n,p,q)][Kp] (k = (c,r,s), Kp = 3*R*S rounded up to 32) is materialised by an im2col pass and the convolution
+// becomes a plain GEMM with K = Kp (bias + ReLU in the TMA epilogue).  Frames are processed in groups whose patch
+// matrix (<= ~48 MB) is still L2-resident when the GEMM reads it, so the extra traffic stays on chip.
+// wk_* = [Cout, Kp] K-major; col_scratch holds i2v_conv_stem_fwd_tc_group(d) * P*Q*Kp floats.
+extern "C" int i2v_conv_stem_fwd_tc_group(const i2v_conv_desc* d) {
+    if (!d) return 0;
+    const int Kp = (3 * d->R * d->S + 31) / 32 * 32;
+    const int64_t per_frame = (int64_t)d->P * d->Q * Kp * 4;
+    int64_t g = stem_group_bytes() / (per_frame > 0 ? per_frame : 1);
+    if (g < 1) g = 1;
+    if (g > d->N) g = d->N;
+    return (int)g;
+}
+
+extern "C" int i2v_conv_stem_fwd_tc_f32(const i2v_conv_desc* d, const float* x, const float* wk_hi, const float* wk_lo,
+                                        const float* bias, float* col_scratch, float* y, int flags, i2v_stream_t stream) {
+    I2V_REQUIRE(d && x && wk_hi && col_scratch && y, "null pointer");
+    I2V_REQUIRE(d->Cin == 3 && d->R == d->S && d->Cout % 64 == 0 && d->stride >= 1 && d->pad < d->R, "not a first-layer shape");
+    if (d->N == 0) return I2V_OK;
+    const int Kp = (3 * d->R * d->S + 31) / 32 * 32;
+    const int G = i2v_conv_stem_fwd_tc_group(d);
+    for (int n0 = 0; n0 < d->N; n0 += G) {
+        const int n = d->N - n0 < G ? d->N - n0 : G;
+        if (int r = stem_im2col_launch(x, col_scratch, n0, n, d->H, d->W, d->P, d->Q, d->R, d->stride, d->pad, Kp, as_stream(stream)))
+            return r;
+        TcProblem pr{};
+        pr.src = col_scratch; pr.N = n; pr.H = d->P; pr.W = d->Q; pr.C = Kp; pr.P = d->P; pr.Q = d->Q; pr.stride = 1;
+        pr.taps_h = pr.taps_w = 1;
+        pr.w_hi = wk_hi; pr.w_lo = wk_lo; pr.Cout = d->Cout; pr.bias = bias; pr.relu = (flags & I2V_EPI_RELU) ? 1 : 0;
+        pr.dst = y + (int64_t)n0 * d->P * d->Q * d->Cout;
+        if (int r = tc_run(pr, as_stream(stream))) return r;
+    }
+    return I2V_OK;
 }
 
 // Strided data gradient, one stride-parity class per call.  Image rows h = stride*i + ph (columns likewise)

@@ -68,6 +68,18 @@ class _Conv:
         self.tc_dgrad_cls = _class_weights(ws, self.stride, self.pad) if self.stride > 1 and not x_nchw else None
         # first layer (Cin = 3): [(c,r,s), co] for the stem forward; its dgrad uses b_fwd = [(r,s), c, co]
         self.w_stem = ws.permute(1, 2, 3, 0).reshape(cin * R * S, cout).contiguous() if x_nchw else None
+        # first-layer data gradient on the tensor cores: rows (c,r,s) zero-padded to a multiple of 64, TF32 hi/lo split
+        self.tc_stem_dgrad = None
+        if x_nchw and cin == 3 and cout % 32 == 0:
+            nz = (cin * R * S + 63) // 64 * 64
+            wz = torch.cat([self.w_stem, self.w_stem.new_zeros(nz - cin * R * S, cout)], 0).contiguous()
+            self.tc_stem_dgrad = _split_tf32(wz)
+        # first-layer forward as im2col + GEMM: [Cout, Kp] K-major, k = (c,r,s) zero-padded to a multiple of 32
+        self.tc_stem_fwd = None
+        if x_nchw and cin == 3 and cout % 64 == 0:
+            kp = (cin * R * S + 31) // 32 * 32
+            wk = torch.cat([self.w_stem.t(), self.w_stem.new_zeros(cout, kp - cin * R * S)], 1).contiguous()
+            self.tc_stem_fwd = _split_tf32(wk)
 
     def out_hw(self, h, w):
         return ((h + 2 * self.pad - self.R) // self.stride + 1, (w + 2 * self.pad - self.R) // self.stride + 1)
@@ -102,13 +114,15 @@ class _Concat:
 
 
 def _split_tf32(w):
-    """(hi, lo, rna): hi = w with the low 13 mantissa bits cleared (what the tensor core reads), lo = w - hi
-    (exact in f32), rna = w rounded to nearest TF32."""
-    bits = w.contiguous().view(torch.int32)
+    """(raw, lo, rna) operands of the tensor-core kernels.  raw = w itself: the tensor core reads an f32 bit pattern
+    as TF32, i.e. it ignores the low 13 mantissa bits, so the raw weights ARE B_hi; lo = w - trunc_tf32(w) (exact in
+    f32) — a non-null lo is what selects the 3xTF32 mode; rna = w rounded to nearest TF32 for the plain-TF32 mode."""
+    w = w.contiguous()
+    bits = w.view(torch.int32)
     hi = (bits & -8192).view(torch.float32)
     lo = (w - hi).contiguous()
     rna = ((bits + 4096) & -8192).view(torch.float32)
-    return hi.contiguous(), lo, rna.contiguous()
+    return w, lo, rna.contiguous()
 
 
 def _class_weights(ws, stride, pad):
@@ -258,7 +272,7 @@ def _build_sequential(features, targets):
 
 class NativeEngine:
     relu_masked_grads = True    # K1 applies 1[feature > 0]: gradients are kept pre-activation
-    preferred_chunk = 32        # frames per forward/backward: ~4 GB of NHWC activations + gradients for ResNet-50 layer2
+    preferred_chunk = 128       # fallback when the image size is not known (see frames_per_chunk)
 
     def __init__(self, model, model_name, depth, tf32x3=True, use_tensor_cores=None):
         self.model = backbones.freeze_for_attack(model)
@@ -284,11 +298,37 @@ class NativeEngine:
         self.use_tc = bool(use_tensor_cores)
         self.use_stem = os.environ.get("I2V_NATIVE_STEM", "1") != "0"   # dedicated first-layer kernels
         self.use_bits = os.environ.get("I2V_NATIVE_BITS", "1") != "0"   # ReLU-backward masks as bits (TMA epilogue)
+        self.use_stem_tc = os.environ.get("I2V_NATIVE_STEM_TC", "1") != "0"   # first-layer dgrad as tcgen05 GEMM + col2im
+        self._zbuf = None
         self._cache = {}
 
     @property
     def num_layers(self):
         return len(self.hook_bufs)
+
+    def bytes_per_frame(self, h, w):
+        """Activation + gradient + mask bytes one frame needs in a chunk's buffer plan (see _plan)."""
+        dims, total = {"img": (h, w)}, 3 * h * w * 4
+        for op in self.ops:
+            if op.kind == "conv":
+                dims[op.y] = op.out_hw(*dims[op.x])
+            elif op.kind == "pool":
+                dims[op.y] = op.out_hw(*dims[op.x])
+            else:
+                dims[op.y] = dims[op.xs[0]]
+            oh, ow = dims[op.y]
+            elems = oh * ow * self.chans[op.y]
+            total += elems * 4 * (1 if op.y in self.hook_bufs else 2) + (elems if op.kind == "pool" else 0) + elems // 8
+        return total
+
+    def frames_per_chunk(self, h, w, n_frames, device, share=1.0):
+        """Frames per forward/backward sub-batch.  Large chunks win (measured on B200, ResNet-50 layer2 at 224^2:
+        8.8k / 11.3k / 12.2k / 12.9k frame-steps/s at 32 / 64 / 128 / 256 frames): every launch has ~15 us of fixed
+        cost (prologue, pipeline ramp, last-wave imbalance) and the persistent kernels' tile counts quantise against
+        the 148 SMs; the limit is memory — at most `share` x 60 % of what is free now, and 256 frames."""
+        free, _ = torch.cuda.mem_get_info(device)
+        fit = int(free * 0.6 * share // max(1, self.bytes_per_frame(h, w)))
+        return max(1, min(n_frames, 256, fit))
 
     # ---- per-(n,h,w) buffer plan -------------------------------------------------------------------
     def _plan(self, n, h, w, device):
@@ -330,7 +370,14 @@ class NativeEngine:
 
     # ---- forward -------------------------------------------------------------------------------------
     def _conv_fwd(self, op, d, x, y, residual, bits_out=None):
-        if op.x_nchw and residual is None and self.use_stem and capi.conv_stem_supported(d):
+        if op.x_nchw and residual is None and self.use_tc and self.use_stem_tc and op.tc_stem_fwd is not None:
+            hi, lo, rna = op.tc_stem_fwd
+            nfl = capi.stem_fwd_tc_scratch_floats(d)
+            if self._zbuf is None or self._zbuf.numel() < nfl:
+                self._zbuf = torch.empty(nfl, device=x.device, dtype=torch.float32)
+            capi.conv_stem_fwd_tc(d, x, hi if self.tf32x3 else rna, lo if self.tf32x3 else None, op.bias, self._zbuf, y,
+                                  relu=op.relu)
+        elif op.x_nchw and residual is None and self.use_stem and capi.conv_stem_supported(d):
             capi.conv_stem_fwd(d, x, op.w_stem, op.bias, y, relu=op.relu)
         elif self.use_tc and not op.x_nchw and capi.conv_tc_supported(d, 0):
             hi, lo, rna = op.tc_fwd
@@ -340,7 +387,14 @@ class NativeEngine:
             capi.conv_fwd_simt(d, x, op.b_fwd, op.bias, residual, y, relu=op.relu, x_nchw=op.x_nchw)
 
     def _conv_dgrad(self, op, d, dy, addend, mask_src, dx, mask_bits=None):
-        if op.x_nchw and addend is None and mask_src is None and self.use_stem and capi.conv_stem_supported(d):
+        if (op.x_nchw and addend is None and mask_src is None and self.use_tc and self.use_stem_tc
+                and op.tc_stem_dgrad is not None and (d.N * d.P * d.Q) % 4 == 0):
+            hi, lo, rna = op.tc_stem_dgrad
+            nfl = capi.stem_dgrad_tc_scratch_floats(d)
+            if self._zbuf is None or self._zbuf.numel() < nfl:
+                self._zbuf = torch.empty(nfl, device=dy.device, dtype=torch.float32)
+            capi.conv_stem_dgrad_tc(d, dy, hi if self.tf32x3 else rna, lo if self.tf32x3 else None, self._zbuf, dx)
+        elif op.x_nchw and addend is None and mask_src is None and self.use_stem and capi.conv_stem_supported(d):
             capi.conv_stem_dgrad(d, dy, op.b_fwd, dx)
         elif self.use_tc and not op.x_nchw and op.stride == 1 and capi.conv_tc_supported(d, 1):
             hi, lo, rna = op.tc_dgrad
@@ -398,6 +452,24 @@ class NativeEngine:
             if op.kind == "conv" and op.relu:
                 out.extend([None] * op.relu_skipped_before)
                 out.append((acts[op.y] > 0).permute(0, 3, 1, 2).contiguous().cpu())
+        return out
+
+    def pool_indices(self):
+        """Winners of every max pooling of the last forward, in the torch module's MaxPool2d call order, as int64
+        [n,C,P,Q] flat indices h*W + w into the pooled plane (torch's `return_indices` convention) — the decisions
+        the backward pass routes gradients by.  For parity tests only (forces a sync)."""
+        plan = self._last_fwd
+        out = []
+        for op in self.ops:
+            if op.kind != "pool":
+                continue
+            am = plan["argmax"][op.y].to(torch.int64)                       # [n,P,Q,C]: r*k + s of the first maximum
+            n, P, Q, C = am.shape
+            ih, iw = plan["dims"][op.x]
+            p = torch.arange(P, device=am.device).view(1, P, 1, 1) * op.stride - op.pad
+            q = torch.arange(Q, device=am.device).view(1, 1, Q, 1) * op.stride - op.pad
+            flat = (p + am // op.k) * iw + (q + am % op.k)
+            out.append(flat.permute(0, 3, 1, 2).contiguous().cpu())
         return out
 
     # ---- backward ------------------------------------------------------------------------------------

@@ -14,7 +14,7 @@ import torch
 
 from i2v_b200 import attack_loop, backbones, capi, engines
 
-__all__ = ["Attack", "get_model", "get_models", "ImageGuidedFMDirection_Adam",
+__all__ = ["Attack", "get_model", "get_models", "ImageGuidedStd_Adam", "ImageGuidedFMDirection_Adam",
            "ImageGuidedFML2_Adam_MultiModels"]
 
 
@@ -62,6 +62,32 @@ def get_model(model_name):
 def get_models(model_name_lists):
     """reference image_attacks.py:110-115"""
     return backbones.get_models(model_name_lists)
+
+
+class ImageGuidedStd_Adam(Attack):
+    """Dispersion Reduction (DR) attack — reference image_attacks.py:129-234 (the baseline `image_main.py`
+    dispatches next to I2V): minimise the standard deviation of the hooked feature map.
+
+    parameters:
+        model_name_lists: [one image model name]
+        depth: {1,2,3,4}
+    """
+
+    def __init__(self, model_name_lists, depth, step_size, epsilon=16 / 255, steps=10, *, engine=None):
+        super(ImageGuidedStd_Adam, self).__init__("ImageGuidedStd_Adam")
+        self.epsilon = epsilon
+        self.steps = steps
+        self.step_size = step_size
+        self.loss_info = {}
+        self.depth = depth
+        self.model = get_models(model_name_lists)[0]
+        self.model_name = model_name_lists[0]
+        self._engine = engines.make_engine(self.model, self.model_name, depth, engine)
+
+    def forward(self, videos, labels, video_names):
+        res = attack_loop.run_dispersion([self._engine], videos, self.epsilon, self.steps, self.step_size)
+        attack_loop.record_loss_info(self.loss_info, video_names, res.cost)
+        return res.adv
 
 
 class ImageGuidedFMDirection_Adam(Attack):

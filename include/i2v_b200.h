@@ -179,6 +179,21 @@ int i2v_conv_fwd_simt_f32(const i2v_conv_desc* d, const float* x, const float* b
 int i2v_conv_dgrad_simt_f32(const i2v_conv_desc* d, const float* dy, const float* bmat, const float* addend,
                             const float* mask_src, float* dx, int flags, i2v_stream_t stream);
 
+/* ---- K6: Dispersion-Reduction loss (reference image_attacks.py:129-234, ImageGuidedStd_Adam) ---------------
+ * cost = activations.std() over the WHOLE hooked feature map [N,C,h,w], unbiased (image_attacks.py:216-220);
+ * d cost / d x_i = (x_i - mean) / ((n - 1) * std).  The map may be fed in slices (frame chunks):
+ *   i2v_std_accumulate_f32  acc[0] += sum(a), acc[1] += sum(a*a) over n elements (FP64, fixed order);
+ *                           workspace >= i2v_std_workspace_doubles() doubles; the caller zeroes acc per step
+ *   i2v_std_finalize_f32    stats = {mean, std, 1/((n_total-1)*std)} (f32) from acc; cost_log[*step_idx] = std
+ *                           (add_to_cost: += , the reference sums the per-layer stds, image_attacks.py:220)
+ *   i2v_std_grad_f32        grad = (a - mean) * stats[2], zeroed where a <= 0 if relu_mask (pre-activation
+ *                           gradient convention of the native engine)                                      */
+int i2v_std_workspace_doubles(void);
+int i2v_std_accumulate_f32(const float* a, int64_t n, double* workspace, double* acc, i2v_stream_t stream);
+int i2v_std_finalize_f32(const double* acc, int64_t n_total, float* stats, float* cost_log, const int* step_idx,
+                         int add_to_cost, i2v_stream_t stream);
+int i2v_std_grad_f32(const float* a, float* grad, int64_t n, const float* stats, int relu_mask, i2v_stream_t stream);
+
 /* First layer (Cin = 3, Cout = 64: ResNet 7x7/s2, AlexNet 11x11/s4, VGG 3x3/s1, SqueezeNet 3x3/s2).
  *   fwd  : x [N,3,H,W] (the layout the update kernels keep the image in) -> y [N,P,Q,64] NHWC, + bias, ReLU;
  *          w = [(c,r,s), 64] = weight[co,c,r,s]*bn_scale[co]
@@ -191,9 +206,12 @@ int i2v_conv_stem_dgrad_f32(const i2v_conv_desc* d, const float* dy, const float
 
 /* Tensor-core path: the same convolution as an implicit GEMM on tcgen05 (kind::tf32, accumulator in TMEM,
  * operands staged by TMA — im2col-mode tensor maps for R > 1 or stride > 1 — behind an mbarrier pipeline).
- *   w_hi, w_lo : weights [Cout, R*S*Cin] K-major (tap-major, channel-minor), BN scale folded, split as
- *                hi = trunc_tf32(w), lo = w - hi.  w_lo != NULL selects FP32-parity mode (3xTF32:
- *                a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, FP32 accumulate); w_lo == NULL is plain TF32.
+ *   w_hi, w_lo : weights [Cout, R*S*Cin] K-major (tap-major, channel-minor), BN scale folded.  w_hi = the f32
+ *                weights themselves (the tensor core reads the upper 19 bits of an f32 pattern, i.e.
+ *                hi = trunc_tf32(w)); w_lo = w - trunc_tf32(w), exact in f32.  w_lo != NULL selects FP32-parity
+ *                mode (3xTF32: a_hi*b_hi + a_lo*b_hi + a_hi*b_lo, FP32 accumulate; A_lo is derived on the fly
+ *                from the raw activation tile); w_lo == NULL is plain TF32 (pass weights rounded to nearest
+ *                TF32 as w_hi).
  *   dgrad != 0 : data gradient of a stride-1 convolution: src = dy, dst = dx, and w_* is the flipped,
  *                transposed filter [Cin, R*S*Cout] (w[co,ci,R-1-r,S-1-s]*bn_scale[co]).
  *   epilogue   : dst = relu?( acc + bias [+ residual] ) * 1[mask_src > 0]   (each part optional)
@@ -212,6 +230,26 @@ int i2v_conv_tc_f32(const i2v_conv_desc* d, int dgrad, const float* src, const f
 int i2v_conv_tc_bits_f32(const i2v_conv_desc* d, int dgrad, const float* src, const float* w_hi, const float* w_lo,
                          const float* bias, const float* residual, const float* mask_src, uint32_t* mask_bits,
                          float* dst, int flags, i2v_stream_t stream);
+
+/* First-layer data gradient on the tensor cores (replaces i2v_conv_stem_dgrad_f32 when Cout % 32 == 0):
+ * Z[(n,p,q), (c,r,s)] = sum_co dy * W is one tcgen05 GEMM whose result is stored as planes Z^T[(c,r,s)][m] into
+ * z_scratch, then a col2im gather produces dx [N,3,H,W].
+ * wz_hi / wz_lo = [NZ, Cout] K-major: rows (c,r,s) of weight[co,c,r,s]*bn_scale[co], zero-padded to
+ * NZ = ceil(3*R*S/64)*64, split into TF32 hi / lo (wz_lo = NULL: plain TF32).  N*P*Q % 4 == 0.            */
+int i2v_conv_stem_dgrad_tc_f32(const i2v_conv_desc* d, const float* dy, const float* wz_hi, const float* wz_lo,
+                               float* z_scratch, float* dx, i2v_stream_t stream);
+/* Frames are processed in groups of i2v_conv_stem_dgrad_tc_group(d) so that a group's Z planes are still
+ * L2-resident when col2im reads them: z_scratch needs ceil(3*R*S/32)*32 * group*P*Q floats.                 */
+int i2v_conv_stem_dgrad_tc_group(const i2v_conv_desc* d);
+
+/* First-layer forward on the tensor cores (replaces i2v_conv_stem_fwd_f32 when Cout % 64 == 0): an im2col pass
+ * writes the patch matrix col[(n,p,q)][Kp], k = (c,r,s), Kp = ceil(3*R*S/32)*32, for a group of
+ * i2v_conv_stem_fwd_tc_group(d) frames (L2-resident), and a tcgen05 GEMM with K = Kp applies the filters, bias and
+ * ReLU.  wk_hi / wk_lo = [Cout, Kp] K-major (zero-padded), TF32 hi / lo split (wk_lo = NULL: plain TF32);
+ * col_scratch holds group * P*Q*Kp floats; y = [N,P,Q,Cout] NHWC.                                           */
+int i2v_conv_stem_fwd_tc_group(const i2v_conv_desc* d);
+int i2v_conv_stem_fwd_tc_f32(const i2v_conv_desc* d, const float* x, const float* wk_hi, const float* wk_lo,
+                             const float* bias, float* col_scratch, float* y, int flags, i2v_stream_t stream);
 
 /* Debug: subsequent tensor-core launches make CTA 0 stamp clock64() at 8 pipeline points of each of its first
  * `tiles` tiles into device_buf[tiles][8] (see TcArgs::trace in csrc/conv_tc.cu); NULL switches it off.     */

@@ -77,6 +77,25 @@ class _ForcedReLU(torch.autograd.Function):
         return gy * mask, None
 
 
+class _ForcedMaxPool(torch.autograd.Function):
+    """y[n,c,p,q] = x[n,c].flatten()[idx[n,c,p,q]]: max pooling with GIVEN window winners (forward and backward)."""
+
+    @staticmethod
+    def forward(ctx, x, idx):
+        ctx.save_for_backward(idx)
+        ctx.in_shape = x.shape
+        n, c = x.shape[:2]
+        return x.reshape(n, c, -1).gather(2, idx.reshape(n, c, -1)).reshape(idx.shape)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (idx,) = ctx.saved_tensors
+        n, c, h, w = ctx.in_shape
+        gx = torch.zeros(n, c, h * w, dtype=gy.dtype)
+        gx.scatter_add_(2, idx.reshape(n, c, -1), gy.reshape(n, c, -1))
+        return gx.reshape(n, c, h, w), None
+
+
 class forced_relu_masks:
     """Context manager: the first len(masks) ReLU calls of `model` (execution order) use the given activity
     masks instead of their own sign decision; a None entry and later calls (layers behind the hooks) are untouched.
@@ -88,9 +107,14 @@ class forced_relu_masks:
     gradient arithmetic right given the decisions" (compared tightly).  `flips` = number of forced decisions
     that differ from the model's own, `total` = number of decisions."""
 
-    def __init__(self, model, masks):
+    def __init__(self, model, masks, pools=None):
+        """pools: optional list of int64 [N,C,P,Q] flat indices (h*W + w into the pooled plane), one per MaxPool2d call
+        in execution order — max pooling has the same discontinuity (two window entries within rounding distance of
+        each other), so its winners are forced too; calls beyond the list keep their own decision."""
         self.model, self.masks = model, list(masks)
+        self.pools = list(pools) if pools is not None else []
         self.flips = self.total = 0
+        self.pool_flips = self.pool_total = 0
 
     def __enter__(self):
         self.i = 0
@@ -112,10 +136,30 @@ class forced_relu_masks:
                     return _ForcedReLU.apply(x, mk)
                 return F.relu(x)
             return fwd
+        self.pi = 0
+
+        def make_pool(mod):
+            def fwd(x):
+                if outer.pi >= len(outer.pools) or outer.pools[outer.pi] is None:
+                    outer.pi += 1
+                    return F.max_pool2d(x, mod.kernel_size, mod.stride, mod.padding, mod.dilation, mod.ceil_mode)
+                idx = outer.pools[outer.pi]
+                outer.pi += 1
+                _, own = F.max_pool2d(x.detach(), mod.kernel_size, mod.stride, mod.padding, mod.dilation, mod.ceil_mode,
+                                      return_indices=True)
+                if tuple(own.shape) != tuple(idx.shape):
+                    raise ValueError("MaxPool call %d: indices %s vs %s" % (outer.pi - 1, tuple(idx.shape), tuple(own.shape)))
+                outer.pool_flips += int((own != idx).sum())
+                outer.pool_total += idx.numel()
+                return _ForcedMaxPool.apply(x, idx)
+            return fwd
         for mod in self.model.modules():
             if isinstance(mod, torch.nn.ReLU):
                 self.saved.append(mod)
                 mod.forward = make(mod)
+            elif isinstance(mod, torch.nn.MaxPool2d) and self.pools:
+                self.saved.append(mod)
+                mod.forward = make_pool(mod)
         return self
 
     def __exit__(self, *exc):
@@ -208,7 +252,48 @@ def image_guided_loop(hooked, videos, epsilon, steps, step_size, adaptive=False,
     return adv, cost_log, (np.stack(weights) if adaptive and steps else None), coeffs
 
 
-def teacher_forced_grad(hooked, frames, true_image, dtype=torch.float32, weights=None, relu_masks=None):
+def dispersion_loop(hooked, videos, epsilon, steps, step_size, loss_mode="torch", tap=None):
+    """image_attacks.py:190-234 (`ImageGuidedStd_Adam.forward`, Dispersion Reduction).
+
+    hooked   : [HookedModel] (one image model)
+    loss_mode: 'torch' — Tensor.std() + autograd in f32, the reference's own arithmetic
+               'f64'   — the float64 analytic std gradient of oracle.std_loss_grad_f64
+    Returns (adv [b,3,f,h,w] float32 ndarray, cost [steps] float32)."""
+    videos = torch.as_tensor(videos, dtype=torch.float32)
+    b, c, f, h, w = videos.shape
+    inner = h * w
+    frames = _frames(videos)                                                   # 195-196
+    x = O.denorm(frames.numpy(), inner)                                        # 201
+    mod = np.full_like(x, np.float32(INIT_MODIFIER))                           # 197
+    m = np.zeros_like(x)                                                       # Adam state (199)
+    v = np.zeros_like(x)
+    cost_log = np.zeros(steps, dtype=np.float32)
+    true_np = O.compose_norm(x, mod, epsilon, inner)                           # 211-212
+    for i in range(steps):
+        true_image = torch.from_numpy(true_np.copy()).requires_grad_(True)
+        acts = [a for hm in hooked for a in hm.run(true_image)]                # 214
+        if loss_mode == "torch":
+            cost = torch.sum(torch.stack([a.std() for a in acts]))             # 216-220
+            (g,) = torch.autograd.grad(cost, true_image)                       # 222
+            cost_val = np.float32(cost.detach().numpy())
+        else:
+            ups, total = [], 0.0
+            for a in acts:
+                sd, _, gr = O.std_loss_grad_f64(a.detach().numpy())
+                total += sd
+                ups.append(torch.from_numpy(gr.astype(np.float32)).view_as(a))
+            (g,) = torch.autograd.grad(acts, true_image, ups)
+            cost_val = np.float32(total)
+        cost_log[i] = cost_val
+        g_np = g.numpy()
+        m, v, mod, true_np = O.adam_compose(g_np, m, v, mod, x, epsilon, inner, i + 1, step_size)   # 221-223, 211-212
+        if tap is not None:
+            tap(i, dict(g=g_np, m=m, v=v, mod=mod, true_image=true_np))
+    adv = true_np.reshape(b, f, c, h, w).transpose(0, 2, 1, 3, 4)              # 230-234
+    return adv, cost_log
+
+
+def teacher_forced_grad(hooked, frames, true_image, dtype=torch.float32, weights=None, relu_masks=None, pool_indices=None):
     """dcost/dtrue_image of ONE step for a GIVEN true_image (image_attacks.py:334-352), in `dtype`.
 
     float64 is the accuracy arbiter of SURVEY.md 8(c): both float32 implementations (torch on the CPU —
@@ -217,6 +302,8 @@ def teacher_forced_grad(hooked, frames, true_image, dtype=torch.float32, weights
     across reduction orders (D8).  `hooked` models are converted to `dtype` in place.
     relu_masks: optional, one list of [N,C,h,w] activity masks per hooked model (ReLU execution order) that the
     adversarial forward/backward is forced to use (see forced_relu_masks); then a 4th value (flips, total) is returned.
+    pool_indices: optional, one list of int64 [N,C,P,Q] max-pool winners per hooked model (MaxPool2d execution order),
+    forced together with the ReLU decisions (differing winners are counted in `flips`).
     Returns (cost, grad [N,3,H,W] as float64 ndarray, cos [L,N])."""
     frames = torch.as_tensor(frames).to(dtype)
     flips = total = 0
@@ -230,9 +317,10 @@ def teacher_forced_grad(hooked, frames, true_image, dtype=torch.float32, weights
         if relu_masks is None:
             acts = hm.run(ti)
         else:
-            with forced_relu_masks(hm.model, relu_masks[hooked.index(hm)]) as fm:
+            pools = pool_indices[hooked.index(hm)] if pool_indices is not None else None
+            with forced_relu_masks(hm.model, relu_masks[hooked.index(hm)], pools) as fm:
                 acts = hm.run(ti)
-            flips, total = flips + fm.flips, total + fm.total
+            flips, total = flips + fm.flips + fm.pool_flips, total + fm.total + fm.pool_total
         for a, a0 in zip(acts, init):
             rows.append(F.cosine_similarity(a.view(N, -1), a0.view(N, -1)))
     stacked = torch.stack(rows)

@@ -35,6 +35,9 @@ def run_image_guided(ref, kind, names, depths, shape, steps, step_size, **kw):
         if kind == "i2v":
             atk = ref.image_attacks.ImageGuidedFMDirection_Adam(names, depth=depths, step_size=step_size, steps=steps)
             models = [atk.model]
+        elif kind == "dr":
+            atk = ref.image_attacks.ImageGuidedStd_Adam(names, depth=depths, step_size=step_size, steps=steps)
+            models = [atk.model]
         elif kind == "ens":
             atk = ref.image_attacks.ImageGuidedFML2_Adam_MultiModels(names, depths, steps=steps)
             models = atk.models
@@ -59,7 +62,7 @@ def run_image_guided(ref, kind, names, depths, shape, steps, step_size, **kw):
     # (ensemble fixtures keep only the first gradient: the Adam arithmetic is pinned by the i2v ones)
     for tag, r in (("first", spy.records[0]), ("last", spy.records[-1])):
         rec["g_mod_" + tag] = r["grad"].numpy()
-        if kind != "i2v":
+        if kind not in ("i2v", "dr"):
             break
         rec["mod_" + tag] = r["param"].numpy()
         rec["m_" + tag] = r["exp_avg"].numpy()
@@ -98,6 +101,8 @@ def main():
     jobs = {
         "i2v_resnet50_d2_32": lambda: run_image_guided(ref, "i2v", ["resnet"], 2, (1, 2, 32, 32), 3, 0.005),
         "i2v_vgg_d3_32": lambda: run_image_guided(ref, "i2v", ["vgg"], 3, (1, 2, 32, 32), 2, 0.005),
+        "dr_resnet50_d2_32": lambda: run_image_guided(ref, "dr", ["resnet"], 2, (1, 2, 32, 32), 3, 0.005),
+        "dr_vgg_d2_32": lambda: run_image_guided(ref, "dr", ["vgg"], 2, (1, 3, 32, 32), 2, 0.005),
         "ens_4models_64": lambda: run_image_guided(
             ref, "ens", ens_names, {"resnet": 2, "vgg": 3, "squeezenet": 2, "alexnet": 3}, (1, 2, 64, 64), 3, 0.005),
         "aens_4models_64": lambda: run_image_guided(

@@ -142,3 +142,20 @@ def layer_sums(cosv, coeffs=None, mode=0, coef_CE=False):
     lib().oracle_layer_sums_f32(_ptr(cosv), _ptr(cz) if cz is not None else None, _ptr(prev), ctypes.byref(cost),
                                 ci(L), i64(N), ci(mode), ci(int(coef_CE)))
     return cost.value, prev
+
+
+def std_loss_grad_f64(a, relu_mask=False):
+    """Dispersion-Reduction loss of reference image_attacks.py:216-220 restated in float64 numpy:
+    cost = torch.Tensor.std() of the whole feature map (unbiased, n-1), and its autograd gradient
+    d std / d a_i = (a_i - mean) / ((n - 1) std).  relu_mask zeroes the gradient where a <= 0 (the
+    pre-activation convention of the native engine: the hooked map is a ReLU output).
+    Returns (std, mean, grad float64 of a's shape)."""
+    a64 = np.asarray(a, dtype=np.float64)
+    n = a64.size
+    mean = a64.sum() / n
+    d = a64 - mean
+    sd = np.sqrt((d * d).sum() / (n - 1))
+    g = d / ((n - 1) * sd)
+    if relu_mask:
+        g = np.where(a64 > 0, g, 0.0)
+    return sd, mean, g

@@ -384,3 +384,60 @@ def test_conv_tc_strided_dgrad_classes(shape, x3):
         want = torch.where(has, want * (act > 0).double(), want)
         err = (got - want).abs().max() / want.abs().max()
         assert err <= tol, (err, tol)
+
+
+@pytest.mark.parametrize("H,W,k,s,p,n", [(224, 224, 7, 2, 3, 2), (64, 64, 7, 2, 3, 3), (64, 64, 11, 4, 2, 1), (32, 32, 3, 1, 1, 2),
+                                         (63, 63, 3, 2, 0, 4)])
+@pytest.mark.parametrize("x3", [True, False])
+def test_stem_dgrad_tc(H, W, k, s, p, n, x3):
+    """First-layer data gradient as a tcgen05 GEMM over the output channels + col2im, against float64 autograd
+    (same error model as test_conv_tc_fwd_and_dgrad with K = Cout = 64, plus <= ceil(k/s)^2 f32 additions)."""
+    from i2v_b200.engine_native import _split_tf32
+    g = torch.Generator().manual_seed(3)
+    Cout = 64
+    w = torch.randn(Cout, 3, k, k, generator=g) / (3 * k * k) ** 0.5
+    P, Q = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    if (n * P * Q) % 4:
+        pytest.skip("N*P*Q % 4 != 0: the engine uses the CUDA-core stem kernel")
+    dy = torch.randn(n, Cout, P, Q, generator=g)
+    d = capi.ConvDesc(n, H, W, 3, Cout, k, k, s, p, P, Q)
+    rows = 3 * k * k
+    nz = (rows + 63) // 64 * 64
+    wz = torch.cat([w.permute(1, 2, 3, 0).reshape(rows, Cout), torch.zeros(nz - rows, Cout)], 0).contiguous().to(DEV)
+    hi, lo, rna = _split_tf32(wz)
+    z = torch.full((capi.stem_dgrad_tc_scratch_floats(d),), float("nan"), device=DEV)
+    dx = torch.full((n, 3, H, W), float("nan"), device=DEV)
+    capi.conv_stem_dgrad_tc(d, dy.permute(0, 2, 3, 1).contiguous().to(DEV), hi if x3 else rna, lo if x3 else None, z, dx)
+    ref64 = torch.nn.grad.conv2d_input((n, 3, H, W), w.double(), dy.double(), s, p)
+    got = dx.cpu().double()
+    assert torch.isfinite(got).all()
+    err = (got - ref64).abs().max() / ref64.abs().max()
+    assert err <= ((2e-5 + Cout * 2.0 ** -24) if x3 else 4e-3), err
+
+
+@pytest.mark.parametrize("H,W,k,s,p,n", [(224, 224, 7, 2, 3, 7), (64, 64, 7, 2, 3, 3), (64, 64, 11, 4, 2, 1), (32, 32, 3, 1, 1, 2),
+                                         (63, 63, 3, 2, 0, 4)])
+@pytest.mark.parametrize("x3", [True, False])
+def test_stem_fwd_tc(H, W, k, s, p, n, x3):
+    """First-layer forward as im2col + tcgen05 GEMM (K = 3*k*k padded to 32), bias + ReLU fused, against float64;
+    n = 7 at 224x224 spans two frame groups."""
+    from i2v_b200.engine_native import _split_tf32
+    g = torch.Generator().manual_seed(4)
+    Cout = 64
+    x = torch.randn(n, 3, H, W, generator=g)
+    w = torch.randn(Cout, 3, k, k, generator=g) / (3 * k * k) ** 0.5
+    shift = torch.randn(Cout, generator=g) * 0.1
+    P, Q = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    d = capi.ConvDesc(n, H, W, 3, Cout, k, k, s, p, P, Q)
+    K = 3 * k * k
+    kp = (K + 31) // 32 * 32
+    wk = torch.cat([w.reshape(Cout, K), torch.zeros(Cout, kp - K)], 1).contiguous().to(DEV)
+    hi, lo, rna = _split_tf32(wk)
+    col = torch.full((capi.stem_fwd_tc_scratch_floats(d),), float("nan"), device=DEV)
+    y = torch.full((n, P, Q, Cout), float("nan"), device=DEV)
+    capi.conv_stem_fwd_tc(d, x.to(DEV), hi if x3 else rna, lo if x3 else None, shift.to(DEV), col, y, relu=True)
+    ref64 = _ref_conv(x, w, torch.ones(Cout), shift, s, p, None, True, torch.float64)
+    got = y.permute(0, 3, 1, 2).cpu().double()
+    assert torch.isfinite(got).all()
+    err = (got - ref64).abs().max() / ref64.abs().max()
+    assert err <= ((1e-5 + K * 2.0 ** -24) if x3 else 4e-3), err

@@ -294,3 +294,36 @@ def test_layer_reweight_and_sums(L, momentum):
         prev = prev_o
         dp.copy_(gpu(prev))
         capi.step_advance(step_idx)
+
+
+@pytest.mark.parametrize("shape,chunks", [((2, 512, 28, 28), 1), ((5, 64, 7, 9), 2), ((3, 1, 1, 7), 3), ((1, 128, 56, 56), 1)])
+@pytest.mark.parametrize("relu_mask", [False, True])
+def test_std_loss_grad_vs_float64(shape, chunks, relu_mask):
+    """K6 (Dispersion Reduction): unbiased std of the whole map and its gradient against the float64 oracle, with the
+    map fed in frame chunks (ragged sizes included); repeated runs are bit-identical (fixed reduction order)."""
+    rng = np.random.default_rng(3)
+    a = np.maximum(rng.standard_normal(shape) + 0.3, 0).astype(np.float32)
+    sd64, mean64, g64 = O.std_loss_grad_f64(a, relu_mask=relu_mask)
+    ad = torch.from_numpy(a).cuda()
+    ws = capi.std_workspace(ad.device)
+    outs = []
+    for rep in range(2):
+        acc = torch.zeros(2, dtype=torch.float64, device="cuda")
+        stats = torch.zeros(4, device="cuda")
+        cost = torch.full((3,), 7.0, device="cuda")
+        step = torch.tensor([1], dtype=torch.int32, device="cuda")
+        bounds = np.linspace(0, shape[0], chunks + 1).astype(int)
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            if hi > lo:
+                capi.std_accumulate(ad[lo:hi], ws, acc)
+        capi.std_finalize(acc, a.size, stats, cost, step, add_to_cost=True)
+        grad = torch.full_like(ad, float("nan"))
+        for lo, hi in zip(bounds[:-1], bounds[1:]):
+            if hi > lo:
+                capi.std_grad(ad[lo:hi], grad[lo:hi], stats, relu_mask=relu_mask)
+        outs.append((stats.cpu().numpy(), grad.cpu().numpy(), cost.cpu().numpy()))
+    (st, gr, cost), (st2, gr2, _) = outs
+    assert np.array_equal(st, st2) and np.array_equal(gr, gr2)
+    assert abs(st[0] - mean64) <= 2e-7 * abs(mean64) and abs(st[1] - sd64) <= 2e-7 * sd64
+    assert cost[0] == 7.0 and cost[2] == 7.0 and abs(cost[1] - (7.0 + sd64)) <= 1e-6
+    assert np.abs(gr - g64).max() <= 5e-7 * np.abs(g64).max()

@@ -128,3 +128,37 @@ def test_forced_relu_masks_isolate_the_decisions():
     assert ((g32.double() - g64).abs().max() / g64.abs().max()) < 1e-5
     # the context manager restores the modules
     assert all("forward" not in vars(mod) for mod in m64.modules())
+
+
+def test_forced_maxpool_winners_reproduce_autograd():
+    """oracle.loops.forced_relu_masks with the model's OWN ReLU decisions and max-pool winners must reproduce the plain
+    forward and gradient exactly, and count zero flips; a swapped winner must be counted and change the gradient."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from oracle import loops as OL
+    torch.manual_seed(0)
+    model = nn.Sequential(nn.Conv2d(3, 4, 3, padding=1), nn.ReLU(), nn.MaxPool2d(3, 2, 1), nn.Conv2d(4, 4, 3, padding=1),
+                          nn.ReLU(), nn.MaxPool2d(2, 2, 0, ceil_mode=True)).double()
+    x = torch.randn(2, 3, 9, 9, dtype=torch.float64, requires_grad=True)
+    y = model(x)
+    (g,) = torch.autograd.grad(y.square().sum(), x)
+    masks, pools, h = [], [], x.detach()
+    for m in model:
+        if isinstance(m, nn.MaxPool2d):
+            h, idx = F.max_pool2d(h, m.kernel_size, m.stride, m.padding, 1, m.ceil_mode, return_indices=True)
+            pools.append(idx)
+        else:
+            h = m(h)
+            if isinstance(m, nn.ReLU):
+                masks.append(h > 0)
+    with OL.forced_relu_masks(model, masks, pools) as fm:
+        y2 = model(x)
+        (g2,) = torch.autograd.grad(y2.square().sum(), x)
+    assert fm.flips == 0 and fm.pool_flips == 0 and fm.pool_total == sum(p.numel() for p in pools)
+    assert torch.equal(y2, y) and torch.allclose(g2, g, rtol=0, atol=1e-15)
+    bad = [p.clone() for p in pools]
+    bad[0][0, 0, 1, 1] = bad[0][0, 0, 1, 1] + 1                      # neighbouring column of the same window row
+    with OL.forced_relu_masks(model, masks, bad) as fm:
+        (g3,) = torch.autograd.grad(model(x).square().sum(), x)
+    assert fm.pool_flips >= 1 and not torch.equal(g3, g)     # (the changed value may move a winner downstream too)
+    assert model[2].forward.__func__ is nn.MaxPool2d.forward          # patches removed

@@ -148,6 +148,23 @@ def test_aens_coef_ce_loop_matches_reference(golden):
     _close_adv(adv, g["adv"], min_equal=0.6)   # + K2's float64 exp vs torch's float32 softmax
 
 
+@pytest.mark.parametrize("fixture,name,depth", [("dr_resnet50_d2_32", "resnet", 2), ("dr_vgg_d2_32", "vgg", 2)])
+def test_dispersion_loop_matches_reference(golden, fixture, name, depth):
+    """Dispersion Reduction (image_attacks.py:129-234): the loop restatement against the unmodified class, and the
+    float64 analytic std gradient against torch's autograd of Tensor.std()."""
+    g = golden(fixture)
+    hooked = _hooked([name], depth)
+    _check_weights(g, hooked)
+    adv, cost = OL.dispersion_loop(hooked, g["videos"], float(g["epsilon"]), int(g["steps"]), float(g["step_size"]))
+    assert np.allclose(cost, g["cost"], rtol=1e-6)
+    _close_adv(adv, g["adv"])
+    a = torch.randn(3, 8, 5, 5, dtype=torch.float64, generator=torch.Generator().manual_seed(1)).relu().requires_grad_(True)
+    sd = a.std()
+    (ga,) = torch.autograd.grad(sd, a)
+    sd_o, _, g_o = O.std_loss_grad_f64(a.detach().numpy())
+    assert abs(sd_o - float(sd)) <= 1e-14 and np.allclose(g_o, ga.numpy(), rtol=1e-12, atol=1e-18)
+
+
 def test_base_attacks_match_reference(golden):
     g = golden("base_tiny3d")
     model = synth.TinyVideoNet()

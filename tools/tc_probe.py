@@ -26,15 +26,21 @@ LAYERS = [  # name, H, Cin, Cout, k, s, p, count(fwd)
 ]
 
 
-def timeit(fn, iters=5):
+def timeit(fn, iters=5, reps=8):
+    """ms per call: `reps` back-to-back launches between two events (the queue stays fed, so the host-side launch
+    cost of the python binding (~15 us) is not in the number; inputs of <= 50 MB stay L2-warm, as they are in the
+    pipeline where the producing layer has just written them)."""
     for _ in range(2):
         fn()
     torch.cuda.synchronize()
     ts = []
     for _ in range(iters):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / reps)
     return sorted(ts)[len(ts) // 2]
 
 
