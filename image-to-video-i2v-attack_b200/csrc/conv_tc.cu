@@ -1141,10 +1141,13 @@ extern "C" int i2v_conv_tc_f32(const i2v_conv_desc* d, int dgrad, const float* s
 // whose result is stored transposed (planes Z^T[(c,r,s)][m]) by the TMA epilogue, and a col2im pass then gathers
 // the <= ceil(R/stride)^2 taps of every image pixel from those planes with fully coalesced reads (each Z element
 // is read exactly once).  wz_* = [NZ, Cout] K-major = w_stem rows (c,r,s) zero-padded to NZ = ceil(3*R*S / 64) * 64.
-// bytes of scratch a frame group may take ($I2V_STEM_GROUP_MB, default 48 MB: L2-resident between the two passes)
+// bytes of scratch a frame group may take ($I2V_STEM_GROUP_MB).  Measured (profiles/r01_bench_engine_chunk_sweep.json):
+// groups small enough to keep the scratch L2-resident (48 MB = 6 frames at 224^2) lose more to the ~15 us fixed cost of
+// every extra launch pair than they save in HBM traffic — 256 frames: 2.10 / 1.81 ms grouped vs 1.49 / 1.30 ms in one
+// pass (dgrad / fwd) — so the default only bounds the scratch allocation (4 GB).
 static int64_t stem_group_bytes() {
-    static const int64_t mb = getenv("I2V_STEM_GROUP_MB") ? atoll(getenv("I2V_STEM_GROUP_MB")) : 48;
-    return (mb > 0 ? mb : 48) << 20;
+    static const int64_t mb = getenv("I2V_STEM_GROUP_MB") ? atoll(getenv("I2V_STEM_GROUP_MB")) : 4096;
+    return (mb > 0 ? mb : 4096) << 20;
 }
 
 extern "C" int i2v_conv_stem_dgrad_tc_group(const i2v_conv_desc* d) {
@@ -1164,7 +1167,7 @@ extern "C" int i2v_conv_stem_dgrad_tc_f32(const i2v_conv_desc* d, const float* d
     if (d->N == 0) return I2V_OK;
     const int cols = 3 * d->R * d->S;
     const int NZ = (cols + 63) / 64 * 64;
-    // frames in groups whose Z planes (<= ~48 MB) are still L2-resident when the col2im pass reads them
+    // frames in groups that bound the scratch (see stem_group_bytes)
     const int G = i2v_conv_stem_dgrad_tc_group(d);
     for (int n0 = 0; n0 < d->N; n0 += G) {
         const int n = d->N - n0 < G ? d->N - n0 : G;
@@ -1184,8 +1187,8 @@ extern "C" int i2v_conv_stem_dgrad_tc_f32(const i2v_conv_desc* d, const float* d
 
 // First-layer forward on the tensor cores: a 12-byte pixel cannot be a TMA row, so the patch matrix
 // col[(n,p,q)][Kp] (k = (c,r,s), Kp = 3*R*S rounded up to 32) is materialised by an im2col pass and the convolution
-// becomes a plain GEMM with K = Kp (bias + ReLU in the TMA epilogue).  Frames are processed in groups whose patch
-// matrix (<= ~48 MB) is still L2-resident when the GEMM reads it, so the extra traffic stays on chip.
+// becomes a plain GEMM with K = Kp (bias + ReLU in the TMA epilogue).  Frames are processed in groups that bound the
+// scratch (see stem_group_bytes).
 // wk_* = [Cout, Kp] K-major; col_scratch holds i2v_conv_stem_fwd_tc_group(d) * P*Q*Kp floats.
 extern "C" int i2v_conv_stem_fwd_tc_group(const i2v_conv_desc* d) {
     if (!d) return 0;

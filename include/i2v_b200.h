@@ -238,13 +238,13 @@ int i2v_conv_tc_bits_f32(const i2v_conv_desc* d, int dgrad, const float* src, co
  * NZ = ceil(3*R*S/64)*64, split into TF32 hi / lo (wz_lo = NULL: plain TF32).  N*P*Q % 4 == 0.            */
 int i2v_conv_stem_dgrad_tc_f32(const i2v_conv_desc* d, const float* dy, const float* wz_hi, const float* wz_lo,
                                float* z_scratch, float* dx, i2v_stream_t stream);
-/* Frames are processed in groups of i2v_conv_stem_dgrad_tc_group(d) so that a group's Z planes are still
- * L2-resident when col2im reads them: z_scratch needs ceil(3*R*S/32)*32 * group*P*Q floats.                 */
+/* Frames are processed in groups of i2v_conv_stem_dgrad_tc_group(d) (bounds the scratch; $I2V_STEM_GROUP_MB):
+ * z_scratch needs ceil(3*R*S/32)*32 * group*P*Q floats.                                                     */
 int i2v_conv_stem_dgrad_tc_group(const i2v_conv_desc* d);
 
 /* First-layer forward on the tensor cores (replaces i2v_conv_stem_fwd_f32 when Cout % 64 == 0): an im2col pass
  * writes the patch matrix col[(n,p,q)][Kp], k = (c,r,s), Kp = ceil(3*R*S/32)*32, for a group of
- * i2v_conv_stem_fwd_tc_group(d) frames (L2-resident), and a tcgen05 GEMM with K = Kp applies the filters, bias and
+ * i2v_conv_stem_fwd_tc_group(d) frames, and a tcgen05 GEMM with K = Kp applies the filters, bias and
  * ReLU.  wk_hi / wk_lo = [Cout, Kp] K-major (zero-padded), TF32 hi / lo split (wk_lo = NULL: plain TF32);
  * col_scratch holds group * P*Q*Kp floats; y = [N,P,Q,Cout] NHWC.                                           */
 int i2v_conv_stem_fwd_tc_group(const i2v_conv_desc* d);

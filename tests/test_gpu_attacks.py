@@ -7,6 +7,8 @@ teacher-forced per-step state (tight), costs (1e-5 relative), gradient-sign agre
 gradients above the noise level, and the end state after a few free-running steps with the measured
 oracle-vs-reference spread as the yardstick.  The eps-ball / [0,1] bounds are exact properties.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -348,3 +350,21 @@ def test_transform_video_helpers():
     assert np.array_equal(got.cpu().numpy(), want)
     back = a._transform_video(got.clone(), "back")
     assert np.array_equal(back.cpu().numpy(), O.denorm(want, 64))
+
+
+def test_image_main_driver_end_to_end(tmp_path):
+    """`image_main.py` as run_image_guided.py launches it: artefact names, shapes and dtypes of image_main.py:90-95."""
+    import json
+    import image_main
+    image_main.main(["--attack_method", "ImageGuidedFMDirection_Adam", "--depth", "2", "--step", "2", "--step_size", "0.005",
+                     "--synthetic", "--num_clips", "3", "--frames", "2", "--side", "32", "--opt_path", str(tmp_path),
+                     "--batch_nums", "1", "--batch_index", "1", "--weights", "random"])
+    out = os.path.join(str(tmp_path), "Image-ImageGuidedFMDirection_Adam-2-")
+    for idx in range(3):
+        adv = np.load(os.path.join(out, "%d-adv.npy" % idx))
+        assert adv.shape == (3, 2, 32, 32) and adv.dtype == np.float32 and np.isfinite(adv).all()
+        clean, _ = synth.clip(idx, b=1, f=2, h=32, w=32)
+        _bounds_ok(clean.numpy(), adv[None])
+        assert np.abs(adv - clean.numpy()[0]).max() > 0
+    info = json.load(open(os.path.join(out, "loss_info_1.json")))
+    assert sorted(info) == ["synthetic_%05d" % i for i in range(3)] and sorted(info["synthetic_00000"]) == ["0", "1"]

@@ -1,4 +1,5 @@
 """Host-side logic that needs no GPU: depth -> layer mapping, name handling, sharding, step scalars."""
+import os
 import numpy as np
 import pytest
 import torch
@@ -162,3 +163,23 @@ def test_forced_maxpool_winners_reproduce_autograd():
         (g3,) = torch.autograd.grad(model(x).square().sum(), x)
     assert fm.pool_flips >= 1 and not torch.equal(g3, g)     # (the changed value may move a winner downstream too)
     assert model[2].forward.__func__ is nn.MaxPool2d.forward          # patches removed
+
+
+def test_image_main_host_logic(tmp_path):
+    """The drop-in driver: reference flags and defaults (image_main.py:15-48), the adv_path naming (45), the
+    contiguous --batch_nums/--batch_index slices (61-63) and the synthetic loader's tuple layout."""
+    import image_main
+    args = image_main.arg_parse(["--attack_method", "ImageGuidedFMDirection_Adam", "--step", "7", "--depth", "2",
+                                 "--file_prefix", "run1", "--opt_path", str(tmp_path)])
+    assert args.step_size == 0.004 and args.batch_size == 1 and args.direction_image_model == "resnet"
+    assert args.adv_path == os.path.join(str(tmp_path), "Image-ImageGuidedFMDirection_Adam-7-run1")
+    sl = image_main.SyntheticLoader(5, 2, 4, 16)
+    assert len(sl) == 3
+    batch, labels, names = sl.step(2)                      # ragged last batch
+    assert tuple(batch.shape) == (1, 3, 4, 16, 16) and labels.tolist() == [4] and names == ["synthetic_00004"]
+    batch, labels, names = sl.step(0)
+    assert tuple(batch.shape) == (2, 3, 4, 16, 16) and labels.dtype == torch.int64
+    v, _ = __import__("i2v_b200.synth", fromlist=["clip"]).clip(1, b=1, f=4, h=16, w=16)
+    assert torch.equal(batch[1:], v)
+    with pytest.raises(ValueError):
+        image_main.build_attack(image_main.arg_parse(["--attack_method", "nope"]))
