@@ -32,7 +32,7 @@ class AENS_I2V_MF(Attack):
     """
 
     def __init__(self, model_name_lists, depths, step_size, momentum=0, coef_CE=False, epsilon=16 / 255, steps=60,
-                 *, engine=None):
+                 *, engine=None, placement=None):
         super(AENS_I2V_MF, self).__init__("AENS_I2V_MF")
         self.epsilon = epsilon
         self.steps = steps
@@ -41,10 +41,22 @@ class AENS_I2V_MF(Attack):
         self.depths = depths
         self.momentum = momentum
         self.coef_CE = coef_CE
-        self.models = get_models(model_name_lists)
         self.model_names = model_name_lists
-        self._engines = [engines.make_engine(m, n, depths[n], engine) for m, n in zip(self.models, self.model_names)]
-        n_layers = sum(e.num_layers for e in self._engines)
+        # placement='ensemble' (extension): one backbone per GPU under torch.distributed — this rank builds only its
+        # members; dcost/dtrue_image and the cosine rows are summed over the ensemble group every step (i2v_b200/dist.py)
+        self._plan = None
+        layers_per_model = [len(depths[n]) if isinstance(depths[n], (list, tuple)) else 1 for n in model_name_lists]
+        if placement == "ensemble":
+            from i2v_b200 import dist as D
+            self._plan = D.EnsemblePlan(model_name_lists, layers_per_model)
+            mine = [model_name_lists[i] for i in self._plan.members]
+        elif placement is None:
+            mine = list(model_name_lists)
+        else:
+            raise ValueError("placement must be None or 'ensemble', got %r" % (placement,))
+        self.models = get_models(mine)
+        self._engines = [engines.make_engine(m, n, depths[n], engine) for m, n in zip(self.models, mine)]
+        n_layers = sum(layers_per_model)
         if n_layers != 2 * len(model_name_lists):
             raise ValueError("AENS_I2V_MF keeps 2 coefficients per model (reference TPAMI_attack.py:165): "
                              "%d models need %d hooked layers in total, depths give %d"
@@ -55,9 +67,13 @@ class AENS_I2V_MF(Attack):
 
     def forward(self, videos, labels, video_names):
         begin = time.time()
+        extra = {}
+        if self._plan is not None:
+            extra = dict(reduce_hook=self._plan.hook(), layer_offsets=self._plan.layer_offsets,
+                         n_layers_total=self._plan.n_layers_total)
         res = attack_loop.run_image_guided(self._engines, videos, self.epsilon, self.steps, self.step_size,
                                            adaptive=True, coeffs=self.coeffs, momentum=self.momentum,
-                                           coef_CE=self.coef_CE)
+                                           coef_CE=self.coef_CE, **extra)
         self.weights = [w.copy() for w in res.weights] if res.weights is not None else []
         cost_saved = np.zeros(self.steps)
         cost_saved[:] = res.cost

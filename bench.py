@@ -32,6 +32,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line (NCCL's version banner goes to stderr)
 
 METRIC = "attack_frame_steps_per_sec"
 UNIT = "frame-steps/s"
@@ -234,6 +235,7 @@ def run_b200_arm(args):
     events, capi.PROFILE_EVENTS = capi.PROFILE_EVENTS, None
     launches = dict(capi.LAUNCHES)
     res = run.finish()
+    chunk_frames = run.chunk
     ms = D.max_over_ranks(ms_local, device)
     value = world * N * K / (ms / 1e3)
 
@@ -296,6 +298,12 @@ def run_b200_arm(args):
         names = ["clip%d" % i for i in range(clips)]
         labels = torch.zeros(clips, dtype=torch.long)
         out_host = torch.empty(videos.shape, dtype=torch.float32).pin_memory()
+        del run                                        # the device-resident arm's state goes back to the allocator
+        # one untimed call first: a sweep attacks clip batch after clip batch, so the steady state has a warm caching
+        # allocator (the first call pays ~0.3 s of cudaMalloc for 4 GB of per-call state)
+        adv = atk(host_videos, labels, names)
+        out_host.copy_(adv, non_blocking=True)
+        del adv
         D.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -308,7 +316,7 @@ def run_b200_arm(args):
         e2e = {"value": world * N * K / (e2e_ms / 1e3), "unit": UNIT, "ms_total": e2e_ms,
                "h2d_bytes_per_step": host_videos.numel() * 4 / K, "d2h_bytes_per_step": (out_host.numel() * 4 + 4 * K) / K,
                "note": "one attack(videos, labels, names) call of K steps incl. setup, clean-feature pass, H2D of the "
-                       "clips and D2H of the adversarial clips; bytes are per call / K"}
+                       "clips and D2H of the adversarial clips (second call: warm allocator); bytes are per call / K"}
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -324,7 +332,7 @@ def run_b200_arm(args):
                                    "clips x %d frames x 3x%dx%d per GPU, FP32 parity mode" % (clips, FRAMES, SIDE, SIDE),
                        "frames_per_gpu": N, "eps": "16/255", "step_size": STEP_SIZE, "engine": engine_name,
                        "weights": "torchvision random init, seed 0", "l2": "inputs_exceed_l2 (no flush needed)",
-                       "chunk_frames": run.chunk, "final_cost": float(res.cost[-1]) if len(res.cost) else None},
+                       "chunk_frames": chunk_frames, "final_cost": float(res.cost[-1]) if len(res.cost) else None},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(sum(launches.values())),
             "gpu_launches_by_kernel": launches, "roofline": roofline, "roofline_all": roof_all,
             "cpu_baseline": cpu_base,

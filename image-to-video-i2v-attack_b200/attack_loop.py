@@ -58,6 +58,8 @@ def _chunk_frames(engines, N, chunk, h=None, w=None, device=None):
     image size and the free device memory (engines that do not size themselves report `preferred_chunk`)."""
     if chunk is None:
         chunk = int(os.environ.get("I2V_CHUNK", "0"))
+    if not chunk and not engines:
+        chunk = N
     if not chunk:
         asks = []
         for e in engines:
@@ -83,7 +85,10 @@ class ImageGuidedRun:
     """
 
     def __init__(self, engines, epsilon, steps, step_size, adaptive=False, coeffs=None, momentum=0.0,
-                 coef_CE=False, chunk=None, reduce_hook=None, tap=None):
+                 coef_CE=False, chunk=None, reduce_hook=None, tap=None, layer_offsets=None, n_layers_total=None):
+        """layer_offsets / n_layers_total: one-backbone-per-GPU ensembles (dist.ensemble_plan) — `engines` are then only
+        this rank's members, layer_offsets[i] is the row of engine i's first hooked layer in the ensemble-wide
+        [L, N] cosine table and reduce_hook sums the rows and the input gradient over the ensemble group."""
         self.engines = list(engines)
         self.epsilon = float(epsilon)
         self.steps = int(steps)
@@ -95,7 +100,14 @@ class ImageGuidedRun:
         self.chunk_request = chunk
         self.reduce_hook = reduce_hook
         self.tap = tap
-        self.n_layers = sum(e.num_layers for e in self.engines)
+        self.n_layers = sum(e.num_layers for e in self.engines) if n_layers_total is None else int(n_layers_total)
+        if layer_offsets is None:
+            layer_offsets, off = [], 0
+            for e in self.engines:
+                layer_offsets.append(off)
+                off += e.num_layers
+        self.layer_offsets = list(layer_offsets)
+        self.owned_rows = sorted(o + k for o, e in zip(self.layer_offsets, self.engines) for k in range(e.num_layers))
         if adaptive and (coeffs is None or coeffs.numel() != self.n_layers):
             raise ValueError("adaptive mode needs a coeffs tensor with one entry per hooked layer (%d)" % self.n_layers)
         self.step_no = 0
@@ -138,6 +150,8 @@ class ImageGuidedRun:
                       for fe in self.init_feats]
 
         self.cos = torch.zeros(self.n_layers, N, device=device, dtype=torch.float32)
+        foreign = [r for r in range(self.n_layers) if r not in set(self.owned_rows)]
+        self.foreign_rows = torch.tensor(foreign, device=device, dtype=torch.long) if foreign else None
         self.step_idx = torch.zeros(1, device=device, dtype=torch.int32)
         self.cost_log = torch.zeros(max(steps, 1), device=device, dtype=torch.float32)
         self.table = capi.adam_step_table(steps, self.step_size, BETA1, BETA2).to(device)
@@ -157,9 +171,11 @@ class ImageGuidedRun:
         adaptive = self.adaptive
         if adaptive:
             capi.layer_reweight(self.coeffs, self.prev, self.momentum, self.w_out, self.weights_log, self.step_idx)
+        if not self.engines:                                   # an idle rank of an ensemble group contributes zeros
+            self.g_total.zero_()
         for (s0, s1) in self.spans:
-            layer = 0
             for ei, (e, f0, gr) in enumerate(zip(self.engines, self.init_feats, self.grads)):
+                layer = self.layer_offsets[ei]
                 feats = e.features(self.true_img[s0:s1], need_grad=True)
                 gviews = []
                 for a, a0, ga in zip(feats, f0, gr):
@@ -175,6 +191,8 @@ class ImageGuidedRun:
                 else:
                     self.g_total[s0:s1].add_(g)
         if self.reduce_hook is not None:
+            if self.foreign_rows is not None:                  # rows of peers still hold last step's sums
+                self.cos.index_fill_(0, self.foreign_rows, 0.0)
             self.reduce_hook.grad(self.g_total)
             self.reduce_hook.cos_rows(self.cos)
         capi.layer_sums(self.cos, self.coeffs if adaptive else None, self.prev, self.cost_log, self.step_idx,
@@ -321,8 +339,9 @@ def run_dispersion(engines, videos, epsilon, steps, step_size, chunk=None, tap=N
 
 
 def run_image_guided(engines, videos, epsilon, steps, step_size, adaptive=False, coeffs=None, momentum=0.0,
-                     coef_CE=False, chunk=None, reduce_hook=None, tap=None):
-    run = ImageGuidedRun(engines, epsilon, steps, step_size, adaptive, coeffs, momentum, coef_CE, chunk, reduce_hook, tap)
+                     coef_CE=False, chunk=None, reduce_hook=None, tap=None, layer_offsets=None, n_layers_total=None):
+    run = ImageGuidedRun(engines, epsilon, steps, step_size, adaptive, coeffs, momentum, coef_CE, chunk, reduce_hook, tap,
+                         layer_offsets, n_layers_total)
     run.setup(videos)
     for _ in range(run.steps):
         run.step()

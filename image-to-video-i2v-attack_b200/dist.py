@@ -26,6 +26,7 @@ def init_from_env(backend=None):
     """Initialise the default process group from torchrun's environment (no-op for WORLD_SIZE=1)."""
     rank, local_rank, world = env_world()
     if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout for results (NCCL prints its version banner there)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         if backend is None:
@@ -70,6 +71,46 @@ def ensemble_placement(model_names, rank, world):
             return [], None
         return [rank % M], rank // M
     return list(range(rank, M, world)), 0
+
+
+class EnsemblePlan:
+    """One backbone per GPU (BASELINE.json configs[2]): which ensemble members this rank computes, where their
+    hooked layers sit in the ensemble-wide [L, N] cosine table, and the process group the per-step exchange
+    (sum of dcost/dtrue_image, fill-in of the peers' cosine rows) runs over.
+
+    world >= M: rank r computes member r mod M in replica r // M (M ranks per replica, each replica a separate
+    group that attacks its own clips); world < M: members are dealt round-robin and the group is the world.
+    Every rank must construct the plan (dist.new_group is collective)."""
+
+    def __init__(self, model_names, layers_per_model, rank=None, world=None):
+        if rank is None:
+            rank = dist.get_rank() if dist.is_initialized() else 0
+        if world is None:
+            world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank, self.world = rank, world
+        M = len(model_names)
+        self.members, self.replica = ensemble_placement(model_names, rank, world)
+        offsets, off = [], 0
+        for n in layers_per_model:
+            offsets.append(off)
+            off += int(n)
+        self.n_layers_total = off
+        self.layer_offsets = [offsets[m] for m in self.members]
+        self.replicas = max(1, world // M) if world >= M else 1
+        self.group = None
+        if dist.is_initialized() and world > 1:
+            if world >= M:
+                for rep in range(self.replicas):                  # collective: same order on every rank
+                    g = dist.new_group(list(range(rep * M, (rep + 1) * M)))
+                    if rep == self.replica:
+                        self.group = g
+            else:
+                self.group = dist.group.WORLD
+        self.active = self.replica is not None
+
+    def hook(self):
+        on = self.group is not None
+        return ReduceHook(self.group, sum_grad=on, sum_cos=on)
 
 
 class ReduceHook:

@@ -125,18 +125,32 @@ class ImageGuidedFML2_Adam_MultiModels(Attack):
     `step_size` is fixed at 0.005 as in the reference (image_attacks.py:376).
     """
 
-    def __init__(self, model_name_lists, depths, epsilon=16 / 255, steps=60, *, engine=None):
+    def __init__(self, model_name_lists, depths, epsilon=16 / 255, steps=60, *, engine=None, placement=None):
         super(ImageGuidedFML2_Adam_MultiModels, self).__init__("ImageGuidedFML2_Adam_MultiModels")
         self.epsilon = epsilon
         self.steps = steps
         self.step_size = 0.005
         self.loss_info = {}
         self.depths = depths
-        self.models = get_models(model_name_lists)
         self.model_names = model_name_lists
-        self._engines = [engines.make_engine(m, n, depths[n], engine) for m, n in zip(self.models, self.model_names)]
+        # placement='ensemble' (extension): one backbone per GPU under torch.distributed (i2v_b200/dist.py: EnsemblePlan)
+        self._plan = None
+        if placement == "ensemble":
+            from i2v_b200 import dist as D
+            self._plan = D.EnsemblePlan(model_name_lists, [1] * len(model_name_lists))
+            mine = [model_name_lists[i] for i in self._plan.members]
+        elif placement is None:
+            mine = list(model_name_lists)
+        else:
+            raise ValueError("placement must be None or 'ensemble', got %r" % (placement,))
+        self.models = get_models(mine)
+        self._engines = [engines.make_engine(m, n, depths[n], engine) for m, n in zip(self.models, mine)]
 
     def forward(self, videos, labels, video_names):
-        res = attack_loop.run_image_guided(self._engines, videos, self.epsilon, self.steps, self.step_size)
+        extra = {}
+        if self._plan is not None:
+            extra = dict(reduce_hook=self._plan.hook(), layer_offsets=self._plan.layer_offsets,
+                         n_layers_total=self._plan.n_layers_total)
+        res = attack_loop.run_image_guided(self._engines, videos, self.epsilon, self.steps, self.step_size, **extra)
         attack_loop.record_loss_info(self.loss_info, video_names, res.cost)
         return res.adv
