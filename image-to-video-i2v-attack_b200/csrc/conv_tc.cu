@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                        const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmOut,
                        const __grid_constant__ CUtensorMap tmRes, const TcArgs args, const int stages,
-                       const int num_m_tiles, const int num_n_tiles) {
+                       const int num_m_tiles, const int num_n_tiles, const int epi_slots) {
     using L = TcSmem<BN, X3>;
     constexpr uint32_t kAccCols = X3 ? 2 * BN : BN;            // TMEM columns per accumulator stage
     constexpr int kAcc = (512 / kAccCols) > 4 ? 4 : (512 / kAccCols);
@@ -423,7 +423,10 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* tiles = smem;
     uint8_t* staging = smem + (size_t)stages * L::STAGE_BYTES;  // STAGE_BYTES is a multiple of 1024: stays swizzle-aligned
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + (EPI_TMA ? EPI_STAGING_BYTES : 0));
+    // staging: epi_slots (1 or 2) slots of 16 KB per epilogue group.  K-heavy layers without a residual take ONE slot
+    // per group so that a third 64 KB pipeline stage fits (3xTF32, BN = 128): with two stages the tensor pipe idled
+    // ~45 % of the time waiting for the next k-step's operands (measured 53 % active on the 3x3 128->128 layers)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + (EPI_TMA ? (size_t)epi_slots * 2 * EPI_SLOT_BYTES : 0));
     uint64_t* empty_bar = full_bar + stages;
     uint64_t* split_bar = empty_bar + stages;
     uint64_t* tfull_bar = split_bar + stages;
@@ -465,7 +468,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < args.Cout; i += TC2_THREADS) bias_s[i] = args.bias ? args.bias[i] : 0.f;
+    if (!EPI_TMA)      // the TMA epilogue reads the bias through the read-only path (warp-uniform addresses): no smem
+        for (int i = threadIdx.x; i < args.Cout; i += TC2_THREADS) bias_s[i] = args.bias ? args.bias[i] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -588,7 +592,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const int g = warp - 2;
             constexpr uint32_t SUBS = BN / 64;                  // sub-tiles per tile and group
             const bool has_res = args.residual != nullptr;
-            uint8_t* sbase = staging + (size_t)g * 2 * EPI_SLOT_BYTES;
+            const uint32_t ns = (uint32_t)epi_slots;
+            uint8_t* sbase = staging + (size_t)g * ns * EPI_SLOT_BYTES;
             const uint32_t my_tiles = (uint32_t)((num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
             const uint32_t total = my_tiles * SUBS;
             auto coords = [&](uint32_t k, int& col, int& row) {
@@ -599,8 +604,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             };
             int col, row;
             const uint32_t pf = has_res ? (uint32_t)args.prefetch_tiles * SUBS : 0u;   // L2 prefetch distance in sub-tiles
-            for (uint32_t k = 2; k < 2 + pf && k < total; ++k) { coords(k, col, row); tma_prefetch_l2_2d(&tmRes, col, row); }
-            for (uint32_t k = 0; k < 2 && k < total; ++k) {     // prime both slots
+            for (uint32_t k = ns; k < ns + pf && k < total; ++k) { coords(k, col, row); tma_prefetch_l2_2d(&tmRes, col, row); }
+            for (uint32_t k = 0; k < ns && k < total; ++k) {    // prime the slots
                 if (has_res) {
                     coords(k, col, row);
                     mbar_arrive_expect_tx(&slot_ready[g * 2 + k], EPI_SLOT_BYTES);
@@ -610,7 +615,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 }
             }
             for (uint32_t k = 0; k < total; ++k) {
-                const uint32_t s = k & 1, ph = (k >> 1) & 1;
+                const uint32_t s = k % ns, ph = (k / ns) & 1;
                 mbar_wait(&out_ready[g * 2 + s], ph);           // the group's 128 threads wrote the slot (and fenced)
                 coords(k, col, row);
                 if (col < args.store_cols) {
@@ -618,11 +623,11 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     else                     tma_store_2d(&tmOut, sbase + (size_t)s * EPI_SLOT_BYTES, col, row);
                 }
                 bulk_commit();
-                if (k + 2 < total) {
+                if (k + ns < total) {
                     bulk_wait_read0();                           // the store has read the slot: it may be refilled
                     if (has_res) {
-                        if (pf && k + 2 + pf < total) { coords(k + 2 + pf, col, row); tma_prefetch_l2_2d(&tmRes, col, row); }
-                        coords(k + 2, col, row);
+                        if (pf && k + ns + pf < total) { coords(k + ns + pf, col, row); tma_prefetch_l2_2d(&tmRes, col, row); }
+                        coords(k + ns, col, row);
                         mbar_arrive_expect_tx(&slot_ready[g * 2 + s], EPI_SLOT_BYTES);
                         tma_load_2d(&tmRes, &slot_ready[g * 2 + s], sbase + (size_t)s * EPI_SLOT_BYTES, col, row);
                     } else {
@@ -638,8 +643,10 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int g = (warp - 8) >> 2;
         const int row = (warp & 3) * 32 + lane;                 // tile row = TMEM lane
         const uint32_t swz = (uint32_t)(row & 7);
-        uint8_t* sbase = staging + (size_t)g * 2 * EPI_SLOT_BYTES + (size_t)row * 128;
+        const uint32_t ns = (uint32_t)epi_slots;
+        uint8_t* sbase = staging + (size_t)g * ns * EPI_SLOT_BYTES + (size_t)row * 128;
         const bool has_res = args.residual != nullptr;
+        const float* __restrict__ gbias = args.bias;
         const uint32_t* __restrict__ mbits = args.mask_bits;
         uint32_t* __restrict__ obits = args.bits_out;
         uint32_t k = 0;
@@ -677,14 +684,14 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     tc_fence_before();
                     mbar_arrive(&tempty_bar[acc]);
                 }
-                const uint32_t s = k & 1, ph = (k >> 1) & 1;
+                const uint32_t s = k % ns, ph = (k / ns) & 1;
                 mbar_wait(&slot_ready[g * 2 + s], ph);          // residual landed / previous store has read the slot
                 uint8_t* srow = sbase + (size_t)s * EPI_SLOT_BYTES;
-                const float* bs = bias_s + n0 + c0;
+                const float4* bs4 = reinterpret_cast<const float4*>(gbias + n0 + c0);   // warp-uniform: one broadcast per load
                 if (args.out_transposed) {                       // slot = [32 columns][128 rows]: plain bias add, no swizzle
-                    float* tcol = reinterpret_cast<float*>(staging + (size_t)(g * 2 + s) * EPI_SLOT_BYTES) + row;
+                    float* tcol = reinterpret_cast<float*>(staging + ((size_t)g * ns + s) * EPI_SLOT_BYTES) + row;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) tcol[i * TC_BM] = __uint_as_float(a[i]) + bs[i];
+                    for (int i = 0; i < 32; ++i) tcol[i * TC_BM] = __uint_as_float(a[i]) + (gbias ? __ldg(gbias + n0 + c0 + i) : 0.f);
                     fence_proxy_async();
                     mbar_arrive(&out_ready[g * 2 + s]);
                     continue;
@@ -694,7 +701,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     float4* p = reinterpret_cast<float4*>(srow + (((uint32_t)c ^ swz) << 4));
-                    const float4 bv = *reinterpret_cast<const float4*>(bs + 4 * c);
+                    const float4 bv = gbias ? __ldg(bs4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
                     float4 v = make_float4(__uint_as_float(a[4 * c]) + bv.x, __uint_as_float(a[4 * c + 1]) + bv.y,
                                            __uint_as_float(a[4 * c + 2]) + bv.z, __uint_as_float(a[4 * c + 3]) + bv.w);
                     if (has_res) { const float4 r = *p; v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
@@ -965,27 +972,35 @@ static int tc_launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmBhi, c
                              const CUtensorMap& tmRes, const TcArgs& args, cudaStream_t st) {
     using L = TcSmem<BN, X3>;
     auto kern = conv_tc_persist_kernel<BN, X3, IM2COL, EPI_TMA>;
-    static int stages = 0;
-    static size_t smem_fixed = 0;
-    if (stages == 0) {
+    static size_t budget = 0;
+    if (budget == 0) {
         int dev = 0, optin = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        const size_t budget = (size_t)(optin > 0 ? optin : 227 * 1024);
-        smem_fixed = 1024 /*align slack*/ + 512 /*barriers*/ + 2048 * 4 /*bias, Cout <= 2048*/ + (EPI_TMA ? EPI_STAGING_BYTES : 0);
-        int s = (int)((budget - smem_fixed) / L::STAGE_BYTES);
-        if (s > 8) s = 8;
-        if (s < 2) { set_error("conv_tc (persistent): %d pipeline stages fit in shared memory", s); return I2V_ECUDA; }
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem_fixed + (size_t)s * L::STAGE_BYTES));
+        const size_t b = (size_t)(optin > 0 ? optin : 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b);
         if (e != cudaSuccess) return cuda_fail(e, "conv_tc (persistent): shared memory attribute");
-        stages = s;
+        budget = b;
     }
     I2V_REQUIRE(args.Cout <= 2048, "Cout > 2048 not supported by the persistent tensor-core kernel");
+    // epilogue staging: two 16 KB slots per group when a residual streams through them or the tile is short (the
+    // epilogue is then on the critical path); one slot per group for K-heavy layers, which frees room for one more
+    // pipeline stage ($I2V_TC_EPI_SLOTS=1|2 overrides)
+    static const int slots_env = getenv("I2V_TC_EPI_SLOTS") ? atoi(getenv("I2V_TC_EPI_SLOTS")) : 0;
+    const int kiters = args.taps_h * args.taps_w * args.cblocks;
+    int slots = (args.residual != nullptr || kiters < 8) ? 2 : 1;
+    if (slots_env == 1 || slots_env == 2) slots = slots_env;
+    const size_t fixed = 1008 /*align slack*/ + 512 /*barriers*/ +
+                         (EPI_TMA ? (size_t)slots * 2 * EPI_SLOT_BYTES : (size_t)2048 * 4 /*bias, Cout <= 2048*/);
+    int stages = (int)((budget - fixed) / L::STAGE_BYTES);
+    if (stages > 8) stages = 8;
+    if (stages < 2) { set_error("conv_tc (persistent): %d pipeline stages fit in shared memory", stages); return I2V_ECUDA; }
+    I2V_REQUIRE(!EPI_TMA || args.bias == nullptr || (reinterpret_cast<uintptr_t>(args.bias) & 15) == 0, "bias must be 16-byte aligned");
     const int num_m_tiles = (int)((args.M + TC_BM - 1) / TC_BM), num_n_tiles = args.Cout / BN;
     const int64_t tiles = (int64_t)num_m_tiles * num_n_tiles;
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-    kern<<<grid, TC2_THREADS, smem_fixed + (size_t)stages * L::STAGE_BYTES, st>>>(tmA, tmBhi, tmBlo, tmOut, tmRes, args, stages,
-                                                                                  num_m_tiles, num_n_tiles);
+    kern<<<grid, TC2_THREADS, fixed + (size_t)stages * L::STAGE_BYTES, st>>>(tmA, tmBhi, tmBlo, tmOut, tmRes, args, stages,
+                                                                            num_m_tiles, num_n_tiles, slots);
     I2V_LAUNCH_CHECK("i2v_conv_tc_f32 (persistent)");
     return I2V_OK;
 }
