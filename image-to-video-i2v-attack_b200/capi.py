@@ -37,6 +37,7 @@ SIGNATURES = {
     "i2v_cosine_loss_grad_f32": ([_c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_p, _c_f, _c_int, _c_p], _c_int),
     "i2v_layer_reweight_f32": ([_c_p, _c_p, _c_int, _c_f, _c_p, _c_p, _c_p, _c_p], _c_int),
     "i2v_layer_sums_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_i64, _c_int, _c_int, _c_p], _c_int),
+    "i2v_depthwise_stencil_f32": ([_c_p, _c_p, _c_i64, _c_int, _c_int, _c_int, _c_p, _c_int, _c_int, _c_int, _c_p], _c_int),
     "i2v_std_workspace_doubles": ([], _c_int),
     "i2v_std_accumulate_f32": ([_c_p, _c_i64, _c_p, _c_p, _c_p], _c_int),
     "i2v_std_finalize_f32": ([_c_p, _c_i64, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
@@ -52,6 +53,7 @@ SIGNATURES = {
     "i2v_conv_stem_fwd_tc_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_tc_supported": ([_c_p, _c_int], _c_int),
     "i2v_conv_tc_set_trace": ([_c_p, _c_int], _c_int),
+    "i2v_mma_probe": ([_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_p, _c_p], _c_int),
     "i2v_conv_tc_f32": ([_c_p, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_tc_bits_f32": ([_c_p, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_tc_dgrad_class_f32": ([_c_p, _c_int, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p], _c_int),
@@ -272,6 +274,18 @@ def _conv_cost(d):
     return 4 * (nin + nout), flops
 
 
+# ------------------------------------------------------------------------------- K7 (TI gradient smoothing)
+def depthwise_stencil(src, dst, kernel):
+    """src/dst [B,C,T,H,W] contiguous; kernel [kt,kh,kw] (or [kh,kw]: per-frame 2-D) float32 device tensor."""
+    B, C, T, H, W = src.shape
+    if kernel.dim() == 2:
+        kernel = kernel.unsqueeze(0)
+    kt, kh, kw = kernel.shape
+    _check(load().i2v_depthwise_stencil_f32(_dev(src), _dev(dst), B * C, T, H, W, _dev(kernel), kt, kh, kw, _stream()),
+           "i2v_depthwise_stencil_f32")
+    return dst
+
+
 # ------------------------------------------------------------------------------- K6 (dispersion reduction)
 def std_workspace(device):
     return torch.empty(load().i2v_std_workspace_doubles(), device=device, dtype=torch.float64)
@@ -354,6 +368,14 @@ def stem_fwd_tc_scratch_floats(desc):
     return (3 * desc.R * desc.S + 31) // 32 * 32 * g * desc.P * desc.Q
 
 
+def mma_probe(N, accs, a_tmem, count, ctas=1, issuers=1):
+    """(issue cycles, completion cycles) of `count` tcgen05 TF32 MMAs (debug / measurement, see include/i2v_b200.h)."""
+    out = torch.zeros(2, dtype=torch.int64, device="cuda")
+    _check(load().i2v_mma_probe(N, accs, int(a_tmem), count, ctas, issuers, _dev(out, torch.int64), _stream()), "i2v_mma_probe")
+    torch.cuda.synchronize()
+    return tuple(int(v) for v in out.tolist())
+
+
 def conv_tc_set_trace(buf, tiles=0):
     """Debug: buf = int64 CUDA tensor [tiles, 8] (or None) receiving CTA 0's pipeline time stamps."""
     _check(load().i2v_conv_tc_set_trace(None if buf is None else _dev(buf, torch.int64), tiles), "i2v_conv_tc_set_trace")
@@ -404,12 +426,17 @@ def maxpool_fwd(x, y, argmax, k, stride, pad):
                                           _stream()), "i2v_maxpool_fwd_f32")
 
 
-def maxpool_bwd(dy, argmax, mask_src, dx, k, stride, pad, accumulate=False):
+def maxpool_bwd(dy, argmax, mask_src, dx, k, stride, pad, accumulate=False, mask_pooled=False):
+    """mask_pooled: mask_src is the pooled OUTPUT y (1[y > 0] = 1[x[argmax] > 0]) instead of the input activation."""
     N, H, W, C = dx.shape
     _, P, Q, _ = dy.shape
-    with _Timed("i2v_maxpool_bwd_f32", 5 * dy.numel() + 4 * dx.numel() * (1 + (mask_src is not None) + bool(accumulate))):
+    nb = 5 * dy.numel() + 4 * dx.numel() * (1 + bool(accumulate))
+    if mask_src is not None:
+        nb += 4 * mask_src.numel()
+    with _Timed("i2v_maxpool_bwd_f32", nb):
         _check(load().i2v_maxpool_bwd_f32(_dev(dy), _dev(argmax, torch.uint8), _dev(mask_src), _dev(dx), N, H, W, C, P, Q,
-                                          k, stride, pad, int(accumulate), _stream()), "i2v_maxpool_bwd_f32")
+                                          k, stride, pad, int(bool(accumulate)) | (2 if mask_pooled else 0), _stream()),
+               "i2v_maxpool_bwd_f32")
 
 
 def copy_channels(src, dst, src_off, dst_off, ccopy, accumulate=False):

@@ -244,10 +244,13 @@ maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* 
 }
 
 // dx[img,h,w,c] = sum over the windows that contain (h,w) and whose argmax IS (h,w) of dy; optionally
-// multiplied by the ReLU-backward mask of the pooled tensor's producer (mask_src = that forward activation).
+// multiplied by the ReLU-backward mask of the pooled tensor's producer: mask_src = that forward activation x
+// (mask_pooled = 0), or the POOLED output y (mask_pooled = 1) — the winner of a window IS y, so 1[x[argmax] > 0] =
+// 1[y > 0], and y is k*k/stride^2 times smaller than x (the stem activation is then never read in the backward pass).
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ argmax, const float* __restrict__ mask_src,
-                   float* __restrict__ dx, int N, int H, int W, int C, int P, int Q, int k, int stride, int pad, int accumulate) {
+                   float* __restrict__ dx, int N, int H, int W, int C, int P, int Q, int k, int stride, int pad, int accumulate,
+                   int mask_pooled) {
     const int C4 = C >> 2;
     const int64_t total = (int64_t)N * H * W * C4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -269,14 +272,18 @@ maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ arg
                 const int want = r * k + s;
                 const int64_t o = (((int64_t)img * P + pp) * Q + q) * C4 + c4;
                 const uchar4 a = __ldg(reinterpret_cast<const uchar4*>(argmax) + o);
-                const float4 d = __ldg(reinterpret_cast<const float4*>(dy) + o);
+                float4 d = __ldg(reinterpret_cast<const float4*>(dy) + o);
+                if (mask_pooled) {
+                    const float4 yv = __ldg(reinterpret_cast<const float4*>(mask_src) + o);
+                    if (!(yv.x > 0.f)) d.x = 0.f; if (!(yv.y > 0.f)) d.y = 0.f; if (!(yv.z > 0.f)) d.z = 0.f; if (!(yv.w > 0.f)) d.w = 0.f;
+                }
                 if (a.x == want) g[0] += d.x;
                 if (a.y == want) g[1] += d.y;
                 if (a.z == want) g[2] += d.z;
                 if (a.w == want) g[3] += d.w;
             }
         }
-        if (mask_src) {
+        if (mask_src && !mask_pooled) {
             const float4 mk = __ldg(reinterpret_cast<const float4*>(mask_src) + i);
             if (!(mk.x > 0.f)) g[0] = 0.f; if (!(mk.y > 0.f)) g[1] = 0.f; if (!(mk.z > 0.f)) g[2] = 0.f; if (!(mk.w > 0.f)) g[3] = 0.f;
         }
@@ -373,13 +380,15 @@ extern "C" int i2v_maxpool_fwd_f32(const float* x, float* y, uint8_t* argmax, in
 }
 
 extern "C" int i2v_maxpool_bwd_f32(const float* dy, const uint8_t* argmax, const float* mask_src, float* dx, int N, int H,
-                                   int W, int C, int P, int Q, int k, int stride, int pad, int accumulate,
+                                   int W, int C, int P, int Q, int k, int stride, int pad, int flags,
                                    i2v_stream_t stream) {
     I2V_REQUIRE(dy && argmax && dx, "null pointer");
     I2V_REQUIRE(C % 4 == 0 && k >= 1 && k <= 15 && stride >= 1 && pad >= 0 && pad < k, "unsupported pooling shape");
+    I2V_REQUIRE(!(flags & 2) || mask_src, "I2V_POOL_MASK_POOLED needs mask_src = the pooled output");
     if (N == 0) return I2V_OK;
     const int64_t total = (int64_t)N * H * W * (C / 4);
-    maxpool_bwd_kernel<<<grid1d(total), 256, 0, as_stream(stream)>>>(dy, argmax, mask_src, dx, N, H, W, C, P, Q, k, stride, pad, accumulate);
+    maxpool_bwd_kernel<<<grid1d(total), 256, 0, as_stream(stream)>>>(dy, argmax, mask_src, dx, N, H, W, C, P, Q, k, stride, pad,
+                                                                     flags & 1, (flags >> 1) & 1);
     I2V_LAUNCH_CHECK("i2v_maxpool_bwd_f32");
     return I2V_OK;
 }

@@ -181,6 +181,24 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
                  : "r"(taddr) : "memory");
 }
 
+// registers -> one TMEM lane per thread, 32 consecutive columns
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                 "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                    "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+                    "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+                    "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+                 : "memory");
+}
+// D[tmem] (+)= A[tmem] x B[smem]: A operand in tensor memory (lane = row m, column = k element; cute SM100_MMA_TF32_TS)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 // 16 TMEM lanes x 16 columns per warp: thread t holds row t/4 (regs 4j+e) and row t/4+8 (regs 4j+2+e) of the lane
 // window, columns 8j + 2(t%4) + e (cute SM100_TMEM_LOAD_16dp256b2x) -- a quad owns 32 contiguous bytes of a row, so the
 // epilogue's global loads / stores are whole 32-byte sectors.  No wait: callers batch several loads per wait.
@@ -409,20 +427,29 @@ constexpr int TC2_EPI_THREADS = 256;
 constexpr uint32_t EPI_SLOT_BYTES = TC_BM * 32 * 4;            // 16 KB: 128 rows x 128 bytes
 constexpr uint32_t EPI_STAGING_BYTES = 4 * EPI_SLOT_BYTES;     // two slots per epilogue group
 
-template <int BN, bool X3, bool IM2COL, bool EPI_TMA>
+template <int BN, bool X3, bool IM2COL, bool EPI_TMA, bool ALO_TMEM>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                        const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmOut,
                        const __grid_constant__ CUtensorMap tmRes, const TcArgs args, const int stages,
                        const int num_m_tiles, const int num_n_tiles, const int epi_slots) {
     using L = TcSmem<BN, X3>;
-    constexpr uint32_t kAccCols = X3 ? 2 * BN : BN;            // TMEM columns per accumulator stage
-    constexpr int kAcc = (512 / kAccCols) > 4 ? 4 : (512 / kAccCols);
-    constexpr uint32_t kTmemCols = kAccCols * kAcc;             // 256 or 512: a power of two
+    static_assert(!ALO_TMEM || (X3 && EPI_TMA), "A_lo in tensor memory is a 3xTF32 / TMA-epilogue variant");
+    // ALO_TMEM = the DUAL-ISSUER variant.  Measured (tools/mma_probe.py, profiles/r01_mma_issue_probe.txt): ONE thread
+    // issues a tcgen05.mma every ~200 cycles whatever its width (N = 64..256, floor N/2 cycles), while several issuing
+    // warps proceed concurrently at that same rate each — the 3xTF32 main loop (8 MMAs per k-step) was issue-bound.
+    // So the two MMAs of a k-slice go to two issuers with DISJOINT accumulators: warp 1 issues a_hi x [b_hi | b_lo]
+    // (main | cross), warp 2 issues a_lo x b_hi with A_lo read from tensor memory into a third accumulator (cross2);
+    // the epilogue adds the three.  TMEM: kAcc stages of [main | cross | cross2] in 384 columns + a 4-slot A_lo ring.
+    constexpr uint32_t kAccCols = X3 ? (ALO_TMEM ? 3 * BN : 2 * BN) : BN;   // TMEM columns per accumulator stage
+    constexpr int kAcc = ALO_TMEM ? (int)(384 / kAccCols) : ((512 / kAccCols) > 4 ? 4 : (512 / kAccCols));
+    constexpr uint32_t kAloBase = 384, kAloSlots = 4;
+    constexpr uint32_t kTmemCols = ALO_TMEM ? 512 : kAccCols * kAcc;   // 256 or 512: a power of two
+    constexpr uint32_t kStageBytes = ALO_TMEM ? L::STAGE_BYTES - TC_A_BYTES : L::STAGE_BYTES;   // no A_lo tile in smem
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* tiles = smem;
-    uint8_t* staging = smem + (size_t)stages * L::STAGE_BYTES;  // STAGE_BYTES is a multiple of 1024: stays swizzle-aligned
+    uint8_t* staging = smem + (size_t)stages * kStageBytes;     // stage sizes are multiples of 1024: stays swizzle-aligned
     // staging: epi_slots (1 or 2) slots of 16 KB per epilogue group.  K-heavy layers without a residual take ONE slot
     // per group so that a third 64 KB pipeline stage fits (3xTF32, BN = 128): with two stages the tensor pipe idled
     // ~45 % of the time waiting for the next k-step's operands (measured 53 % active on the 3x3 128->128 layers)
@@ -440,21 +467,21 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int kiters = args.taps_h * args.taps_w * args.cblocks;
     const int num_tiles = num_m_tiles * num_n_tiles;
 
-    auto stage_a = [&](int s) { return tiles + (size_t)s * L::STAGE_BYTES; };
-    auto stage_alo = [&](int s) { return tiles + (size_t)s * L::STAGE_BYTES + TC_A_BYTES; };
-    auto stage_bhi = [&](int s) { return tiles + (size_t)s * L::STAGE_BYTES + TC_A_BYTES * (X3 ? 2 : 1); };
-    auto stage_blo = [&](int s) { return tiles + (size_t)s * L::STAGE_BYTES + TC_A_BYTES * 2 + L::B_BYTES; };
+    auto stage_a = [&](int s) { return tiles + (size_t)s * kStageBytes; };
+    auto stage_alo = [&](int s) { return tiles + (size_t)s * kStageBytes + TC_A_BYTES; };
+    auto stage_bhi = [&](int s) { return tiles + (size_t)s * kStageBytes + TC_A_BYTES * ((X3 && !ALO_TMEM) ? 2 : 1); };
+    auto stage_blo = [&](int s) { return stage_bhi(s) + L::B_BYTES; };
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA); prefetch_tmap(&tmBhi);
         if (X3) prefetch_tmap(&tmBlo);
         for (int s = 0; s < stages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], ALO_TMEM ? 2 : 1);        // dual issuer: both MMA warps release a stage
             mbar_init(&split_bar[s], 128);
         }
         for (int a = 0; a < kAcc; ++a) {
-            mbar_init(&tfull_bar[a], 1);
+            mbar_init(&tfull_bar[a], ALO_TMEM ? 2 : 1);        // ... and both complete an accumulator stage
             mbar_init(&tempty_bar[a], TC2_EPI_THREADS);
         }
         for (int i = 0; i < 4; ++i) {
@@ -536,19 +563,19 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     const int st = it % stages;
                     const uint32_t ph = (uint32_t)(it / stages) & 1;
                     mbar_wait(&full_bar[st], ph);
-                    if (X3) mbar_wait(&split_bar[st], ph);
+                    if (X3 && !ALO_TMEM) mbar_wait(&split_bar[st], ph);
                     tc_fence_after();
                     if (kb == 0) TC_TRACE(3, t);
                     const uint64_t da = umma_desc_sw128(smem_u32(stage_a(st)));
                     const uint64_t dbh = umma_desc_sw128(smem_u32(stage_bhi(st)));
                     uint64_t dal = 0;
-                    if (X3) dal = umma_desc_sw128(smem_u32(stage_alo(st)));
+                    if (X3 && !ALO_TMEM) dal = umma_desc_sw128(smem_u32(stage_alo(st)));
 #pragma unroll
                     for (int kk = 0; kk < TC_BK / 8; ++kk) {
                         if (X3) {
                             // [main | cross] += a_hi x [b_hi | b_lo]  (N = 2*BN), then cross += a_lo x b_hi
                             umma_tf32(d0, da + 2 * kk, dbh + 2 * kk, idesc2, (kb | kk) ? 1u : 0u);
-                            umma_tf32(d0 + BN, dal + 2 * kk, dbh + 2 * kk, idesc, 1u);
+                            if (!ALO_TMEM) umma_tf32(d0 + BN, dal + 2 * kk, dbh + 2 * kk, idesc, 1u);
                         } else {
                             umma_tf32(d0, da + 2 * kk, dbh + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
                         }
@@ -559,11 +586,124 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 TC_TRACE(4, t);
             }
         }
+    } else if (ALO_TMEM && warp == 2) {
+        // ===== second MMA issuer: cross2 += a_lo (tensor memory) x b_hi ===================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(BN);
+            int it = 0, t = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+                const int acc = t % kAcc;
+                const uint32_t aph = (uint32_t)(t / kAcc) & 1;
+                mbar_wait(&tempty_bar[acc], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d2 = tmem_base + (uint32_t)acc * kAccCols + 2u * BN;
+                for (int kb = 0; kb < kiters; ++kb, ++it) {
+                    const int st = it % stages;
+                    const uint32_t ph = (uint32_t)(it / stages) & 1;
+                    mbar_wait(&full_bar[st], ph);               // b_hi landed
+                    mbar_wait(&split_bar[st], ph);              // a_lo of this k-step is in its ring slot
+                    tc_fence_after();
+                    const uint64_t dbh = umma_desc_sw128(smem_u32(stage_bhi(st)));
+                    const uint32_t talo = tmem_base + kAloBase + (uint32_t)(it % kAloSlots) * 32u;
+#pragma unroll
+                    for (int kk = 0; kk < TC_BK / 8; ++kk)
+                        umma_tf32_ts(d2, talo + 8u * kk, dbh + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
+                    umma_commit(&empty_bar[st]);
+                }
+                umma_commit(&tfull_bar[acc]);
+            }
+        }
+    } else if (ALO_TMEM && warp == 3) {
+        // ===== epilogue TMA issuer of BOTH groups (warp 2 issues MMAs here): polls the groups' out_ready barriers ====
+        if (lane == 0) {
+            constexpr uint32_t SUBS = BN / 64;
+            const bool has_res = args.residual != nullptr;
+            const uint32_t ns = (uint32_t)epi_slots;
+            const uint32_t my_tiles = (uint32_t)((num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
+            const uint32_t total = my_tiles * SUBS;
+            auto coords = [&](int g, uint32_t k, int& col, int& row) {
+                const int tile = (int)blockIdx.x + (int)(k / SUBS) * (int)gridDim.x;
+                const int m_tile = tile / num_n_tiles, n_tile = tile - m_tile * num_n_tiles;
+                col = n_tile * BN + (g + 2 * (int)(k % SUBS)) * 32;
+                row = m_tile * TC_BM;
+            };
+            auto refill = [&](int g, uint32_t k) {              // slot k % ns of group g is free: next residual or a plain arrive
+                const uint32_t s = k % ns;
+                if (has_res) {
+                    int col, row;
+                    coords(g, k, col, row);
+                    mbar_arrive_expect_tx(&slot_ready[g * 2 + s], EPI_SLOT_BYTES);
+                    tma_load_2d(&tmRes, &slot_ready[g * 2 + s], staging + ((size_t)g * ns + s) * EPI_SLOT_BYTES, col, row);
+                } else {
+                    mbar_arrive(&slot_ready[g * 2 + s]);
+                }
+            };
+            for (int g = 0; g < 2; ++g)
+                for (uint32_t k = 0; k < ns && k < total; ++k) refill(g, k);
+            uint32_t kdone[2] = {0, 0};
+            const long long t0 = clock64();
+            while (kdone[0] < total || kdone[1] < total) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const uint32_t k = kdone[g];
+                    if (k >= total) continue;
+                    const uint32_t s = k % ns, ph = (k / ns) & 1;
+                    if (!mbar_try_wait(&out_ready[g * 2 + s], ph)) continue;
+                    int col, row;
+                    coords(g, k, col, row);
+                    const uint8_t* slot = staging + ((size_t)g * ns + s) * EPI_SLOT_BYTES;
+                    if (col < args.store_cols) {
+                        if (args.out_transposed) tma_store_2d(&tmOut, slot, row, col);
+                        else                     tma_store_2d(&tmOut, slot, col, row);
+                    }
+                    bulk_commit();
+                    if (k + ns < total) {
+                        bulk_wait_read0();
+                        refill(g, k + ns);
+                    }
+                    kdone[g] = k + 1;
+                }
+                if (clock64() - t0 > 40000000000LL) { printf("i2v conv_tc: epilogue issuer timeout (block %d)\n", blockIdx.x); __trap(); }
+            }
+            bulk_wait_all();
+        }
     } else if (warp >= 4 && warp < 8) {
         // ===== A split (3xTF32 only) ====================================================================
         if (X3) {
             const int t128 = threadIdx.x - 128;
             int it = 0, tno = 0;
+            if (ALO_TMEM) {
+                // A_lo goes to TENSOR MEMORY instead of shared memory: thread = tile row (TMEM lane), 32 k-values of its
+                // row read from the swizzled A tile, lo parts written with tcgen05.st into a ring of 32-column slots that
+                // the second MMA of the k-step reads as its A operand.  Saves, per k-step, the 16 KB shared-memory write
+                // of A_lo and the 16 KB the tensor core would read back — shared-memory bandwidth (128 B/clk) is what
+                // bounds the BN = 64 layers: 120 KB per k-step against 640 cycles of MMA.
+                const int row = t128;                              // warp w -> TMEM lanes 32*(w%4)..+31 (warps 4-7)
+                const uint32_t swz = (uint32_t)(row & 7);
+                const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kAloBase;
+                for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tno) {
+                    for (int kb = 0; kb < kiters; ++kb, ++it) {
+                        const int st = it % stages;
+                        const uint32_t ph = (uint32_t)(it / stages) & 1;
+                        mbar_wait(&full_bar[st], ph);
+                        const uint8_t* arow = stage_a(st) + (size_t)row * 128;
+                        uint32_t lo[32];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 v = *reinterpret_cast<const float4*>(arow + (((uint32_t)c ^ swz) << 4));
+                            lo[4 * c + 0] = __float_as_uint(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+                            lo[4 * c + 1] = __float_as_uint(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+                            lo[4 * c + 2] = __float_as_uint(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+                            lo[4 * c + 3] = __float_as_uint(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+                        }
+                        tmem_st32(lane_addr + (uint32_t)(it % kAloSlots) * 32u, lo);
+                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                        tc_fence_before();
+                        mbar_arrive(&split_bar[st]);
+                    }
+                    if (t128 == 0) TC_TRACE(7, tno);
+                }
+            } else {
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tno) {
                 for (int kb = 0; kb < kiters; ++kb, ++it) {
                     const int st = it % stages;
@@ -585,8 +725,9 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 }
                 if (t128 == 0) TC_TRACE(7, tno);
             }
+            }
         }
-    } else if (EPI_TMA && (warp == 2 || warp == 3)) {
+    } else if (EPI_TMA && !ALO_TMEM && (warp == 2 || warp == 3)) {
         // ===== epilogue TMA issuer of group g = warp - 2: output stores and residual loads ================
         if (lane == 0) {
             const int g = warp - 2;
@@ -666,24 +807,37 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             tc_fence_after();
             if (threadIdx.x == 256) TC_TRACE(5, t);
             const uint32_t tacc = tmem_base + (uint32_t)acc * kAccCols + ((uint32_t)((warp & 3) * 32) << 16);
+            // drain this thread's part of the accumulator stage into registers FIRST and hand the stage back (the
+            // dual-issuer variant has a single stage at BN = 128: the MMA warps wait for exactly this)
+            uint32_t vals[SUBS][32];
 #pragma unroll
-            for (int j = 0; j < SUBS; ++j, ++k) {
+            for (int j = 0; j < SUBS; ++j) {
                 const int c0 = (g + 2 * j) * 32;
-                uint32_t a[32];
-                tmem_ld32_nowait(tacc + (uint32_t)c0, a);
+                tmem_ld32_nowait(tacc + (uint32_t)c0, vals[j]);
                 if (X3) {
                     uint32_t b[32];
                     tmem_ld32_nowait(tacc + (uint32_t)(BN + c0), b);
                     tmem_ld_wait();
+                    if (ALO_TMEM) {                              // cross + cross2 first (both ~2^-11 of main), then + main
+                        uint32_t c2[32];
+                        tmem_ld32_nowait(tacc + (uint32_t)(2 * BN + c0), c2);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) a[i] = __float_as_uint(__fadd_rn(__uint_as_float(a[i]), __uint_as_float(b[i])));
+                        for (int i = 0; i < 32; ++i) b[i] = __float_as_uint(__fadd_rn(__uint_as_float(b[i]), __uint_as_float(c2[i])));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        vals[j][i] = __float_as_uint(__fadd_rn(__uint_as_float(vals[j][i]), __uint_as_float(b[i])));
                 } else {
                     tmem_ld_wait();
                 }
-                if (j == SUBS - 1) {                             // accumulator drained: the MMA warp may reuse it
-                    tc_fence_before();
-                    mbar_arrive(&tempty_bar[acc]);
-                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);                       // accumulator drained: the MMA warps may reuse it
+#pragma unroll
+            for (int j = 0; j < SUBS; ++j, ++k) {
+                const int c0 = (g + 2 * j) * 32;
+                uint32_t (&a)[32] = vals[j];
                 const uint32_t s = k % ns, ph = (k / ns) & 1;
                 mbar_wait(&slot_ready[g * 2 + s], ph);          // residual landed / previous store has read the slot
                 uint8_t* srow = sbase + (size_t)s * EPI_SLOT_BYTES;
@@ -967,11 +1121,12 @@ static int tc_launch(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUt
     return I2V_OK;
 }
 
-template <int BN, bool X3, bool IM2COL, bool EPI_TMA>
+template <int BN, bool X3, bool IM2COL, bool EPI_TMA, bool ALO_TMEM>
 static int tc_launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, const CUtensorMap& tmOut,
                              const CUtensorMap& tmRes, const TcArgs& args, cudaStream_t st) {
     using L = TcSmem<BN, X3>;
-    auto kern = conv_tc_persist_kernel<BN, X3, IM2COL, EPI_TMA>;
+    auto kern = conv_tc_persist_kernel<BN, X3, IM2COL, EPI_TMA, ALO_TMEM>;
+    constexpr size_t kStageBytes = ALO_TMEM ? L::STAGE_BYTES - TC_A_BYTES : L::STAGE_BYTES;
     static size_t budget = 0;
     if (budget == 0) {
         int dev = 0, optin = 0;
@@ -983,24 +1138,24 @@ static int tc_launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmBhi, c
         budget = b;
     }
     I2V_REQUIRE(args.Cout <= 2048, "Cout > 2048 not supported by the persistent tensor-core kernel");
-    // epilogue staging: two 16 KB slots per group when a residual streams through them or the tile is short (the
-    // epilogue is then on the critical path); one slot per group for K-heavy layers, which frees room for one more
-    // pipeline stage ($I2V_TC_EPI_SLOTS=1|2 overrides)
+    // epilogue staging: two 16 KB slots per group when the tile is short (the epilogue is then on the critical path);
+    // one slot per group for K-heavy layers, which frees room for one more pipeline stage ($I2V_TC_EPI_SLOTS=1|2 overrides)
     static const int slots_env = getenv("I2V_TC_EPI_SLOTS") ? atoi(getenv("I2V_TC_EPI_SLOTS")) : 0;
     const int kiters = args.taps_h * args.taps_w * args.cblocks;
-    int slots = (args.residual != nullptr || kiters < 8) ? 2 : 1;
+    int slots = kiters < 8 ? 2 : 1;       // measured: with >= 8 k-steps per tile one slot wins even when a residual streams through
     if (slots_env == 1 || slots_env == 2) slots = slots_env;
     const size_t fixed = 1008 /*align slack*/ + 512 /*barriers*/ +
                          (EPI_TMA ? (size_t)slots * 2 * EPI_SLOT_BYTES : (size_t)2048 * 4 /*bias, Cout <= 2048*/);
-    int stages = (int)((budget - fixed) / L::STAGE_BYTES);
+    int stages = (int)((budget - fixed) / kStageBytes);
     if (stages > 8) stages = 8;
+    if (ALO_TMEM && stages > 4) stages = 4;            // the A_lo ring in tensor memory has 4 slots
     if (stages < 2) { set_error("conv_tc (persistent): %d pipeline stages fit in shared memory", stages); return I2V_ECUDA; }
     I2V_REQUIRE(!EPI_TMA || args.bias == nullptr || (reinterpret_cast<uintptr_t>(args.bias) & 15) == 0, "bias must be 16-byte aligned");
     const int num_m_tiles = (int)((args.M + TC_BM - 1) / TC_BM), num_n_tiles = args.Cout / BN;
     const int64_t tiles = (int64_t)num_m_tiles * num_n_tiles;
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-    kern<<<grid, TC2_THREADS, fixed + (size_t)stages * L::STAGE_BYTES, st>>>(tmA, tmBhi, tmBlo, tmOut, tmRes, args, stages,
-                                                                            num_m_tiles, num_n_tiles, slots);
+    kern<<<grid, TC2_THREADS, fixed + (size_t)stages * kStageBytes, st>>>(tmA, tmBhi, tmBlo, tmOut, tmRes, args, stages,
+                                                                         num_m_tiles, num_n_tiles, slots);
     I2V_LAUNCH_CHECK("i2v_conv_tc_f32 (persistent)");
     return I2V_OK;
 }
@@ -1071,20 +1226,31 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
     a.taps_h = pr.taps_h; a.taps_w = pr.taps_w; a.cblocks = pr.C / 32; a.relu = pr.relu;
     a.out_s = pr.out_s; a.out_h0 = pr.out_h0; a.out_w0 = pr.out_w0; a.out_H = pr.out_H; a.out_W = pr.out_W;
     a.trace = g_trace; a.trace_tiles = g_trace_tiles;
-#define I2V_TC_DISPATCH_P(BN_, EPI_)                                                                \
+#define I2V_TC_DISPATCH_P(BN_, EPI_, ALO_)                                                          \
     do {                                                                                            \
-        if (x3) return im2col ? tc_launch_persist<BN_, true, true, EPI_>(tmA, tmBhi, tmBlo, tmOut, tmRes, a, st)      \
-                              : tc_launch_persist<BN_, true, false, EPI_>(tmA, tmBhi, tmBlo, tmOut, tmRes, a, st);    \
-        return im2col ? tc_launch_persist<BN_, false, true, EPI_>(tmA, tmBhi, tmBlo, tmOut, tmRes, a, st)             \
-                      : tc_launch_persist<BN_, false, false, EPI_>(tmA, tmBhi, tmBlo, tmOut, tmRes, a, st);           \
+        if (x3) return im2col ? tc_launch_persist<BN_, true, true, EPI_, ALO_>(tmA, tmBhi, tmBlo, tmOut, tmRes, a, st)      \
+                              : tc_launch_persist<BN_, true, false, EPI_, ALO_>(tmA, tmBhi, tmBlo, tmOut, tmRes, a, st);    \
+        return im2col ? tc_launch_persist<BN_, false, true, EPI_, false>(tmA, tmBhi, tmBlo, tmOut, tmRes, a, st)            \
+                      : tc_launch_persist<BN_, false, false, EPI_, false>(tmA, tmBhi, tmBlo, tmOut, tmRes, a, st);          \
     } while (0)
     if (persistent) {
         if (epi_tma) {
-            if (BN == 128) I2V_TC_DISPATCH_P(128, true);
-            I2V_TC_DISPATCH_P(64, true);
+            // dual-issuer variant (A_lo in tensor memory): BN = 64 always (two accumulator stages remain), BN = 128 for
+            // K-heavy tiles only — with its single accumulator stage the short tiles of the HBM-bound 1x1 layers lose the
+            // main-loop / epilogue overlap (measured 64->256 +res: 409 vs 345 us per 256 frames).
+            // $I2V_TC_ALO_TMEM=0 selects the single-issuer kernel everywhere, =2 the dual-issuer kernel everywhere
+            static const int alo_env = getenv("I2V_TC_ALO_TMEM") ? atoi(getenv("I2V_TC_ALO_TMEM")) : 1;
+            const int kit = pr.taps_h * pr.taps_w * (pr.C / 32);
+            const bool alo = x3 && alo_env != 0 && (BN == 64 || kit >= 8 || alo_env == 2);
+            if (alo) {
+                if (BN == 128) I2V_TC_DISPATCH_P(128, true, true);
+                I2V_TC_DISPATCH_P(64, true, true);
+            }
+            if (BN == 128) I2V_TC_DISPATCH_P(128, true, false);
+            I2V_TC_DISPATCH_P(64, true, false);
         }
-        if (BN == 128) I2V_TC_DISPATCH_P(128, false);
-        I2V_TC_DISPATCH_P(64, false);
+        if (BN == 128) I2V_TC_DISPATCH_P(128, false, false);
+        I2V_TC_DISPATCH_P(64, false, false);
     }
 #undef I2V_TC_DISPATCH_P
 #define I2V_TC_DISPATCH(BN_)                                                                        \

@@ -518,6 +518,9 @@ class NativeEngine:
                 self._conv_dgrad(op, plan["descs"][op.name], gy, addend, mask, dx, plan["bits"].get(op.x))
                 ready.add(op.x)
             elif op.kind == "pool":
+                # ReLU-backward mask of the pooled tensor's producer.  (The same mask can be taken from the POOLED output —
+                # maxpool_bwd(mask_pooled=True), 1/4 of the mask bytes — but the extra load inside the window loop made the
+                # kernel slower on B200: 926 vs 839 us per 256 frames, so the input activation stays the mask source.)
                 mask = acts[op.x] if op.x in self.relu_typed else None
                 if op.x in pending:
                     raise NotImplementedError("pooling input that is also a residual source")

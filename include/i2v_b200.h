@@ -179,6 +179,13 @@ int i2v_conv_fwd_simt_f32(const i2v_conv_desc* d, const float* x, const float* b
 int i2v_conv_dgrad_simt_f32(const i2v_conv_desc* d, const float* dy, const float* bmat, const float* addend,
                             const float* mask_src, float* dx, int flags, i2v_stream_t stream);
 
+/* ---- K7: depth-wise "same" stencil, the gradient smoothing of the translation-invariant attacks -------------
+ * base_attacks.py:438-449 (TIFGSM: 15x15 Gaussian per frame, kt = 1) and 636-648 (TIFGSM3D: 15x15x15).
+ * src/dst = `volumes` = B*C independent [T,H,W] volumes (a contiguous [B,C,T,H,W] gradient), k = [kt,kh,kw]
+ * (odd extents, <= 8192 taps), zero padding: out[v,t,h,w] = sum k[a,b,c] * in[v,t+a-kt/2,h+b-kh/2,w+c-kw/2]. */
+int i2v_depthwise_stencil_f32(const float* src, float* dst, int64_t volumes, int T, int H, int W, const float* k,
+                              int kt, int kh, int kw, i2v_stream_t stream);
+
 /* ---- K6: Dispersion-Reduction loss (reference image_attacks.py:129-234, ImageGuidedStd_Adam) ---------------
  * cost = activations.std() over the WHOLE hooked feature map [N,C,h,w], unbiased (image_attacks.py:216-220);
  * d cost / d x_i = (x_i - mean) / ((n - 1) * std).  The map may be fed in slices (frame chunks):
@@ -251,6 +258,12 @@ int i2v_conv_stem_fwd_tc_group(const i2v_conv_desc* d);
 int i2v_conv_stem_fwd_tc_f32(const i2v_conv_desc* d, const float* x, const float* wk_hi, const float* wk_lo,
                              const float* bias, float* col_scratch, float* y, int flags, i2v_stream_t stream);
 
+/* Debug / measurement: issue-rate probe of tcgen05.mma.kind::tf32 (M = 128, K = 8): `count` MMAs of width N into
+ * `accs` round-robin accumulators with A from shared memory (a_tmem = 0) or tensor memory, on `ctas` CTAs;
+ * out[0] = cycles to issue, out[1] = cycles until completion (CTA 0).  tools/mma_probe.py prints the table.   */
+int i2v_mma_probe(int N, int accs, int a_tmem, int count, int ctas, int issuers /* 1..3 concurrently issuing warps */,
+                  long long* out, i2v_stream_t stream);
+
 /* Debug: subsequent tensor-core launches make CTA 0 stamp clock64() at 8 pipeline points of each of its first
  * `tiles` tiles into device_buf[tiles][8] (see TcArgs::trace in csrc/conv_tc.cu); NULL switches it off.     */
 int i2v_conv_tc_set_trace(unsigned long long* device_buf, int tiles);
@@ -270,8 +283,13 @@ int i2v_conv_tc_dgrad_class_f32(const i2v_conv_desc* d, int ph, int pw, const fl
  * vgg (2,2,0), alexnet / squeezenet (3,2,0; ceil_mode via P,Q).                                      */
 int i2v_maxpool_fwd_f32(const float* x, float* y, uint8_t* argmax, int N, int H, int W, int C, int P, int Q,
                         int k, int stride, int pad, i2v_stream_t stream);
+/* flags: bit 0 (I2V_POOL_ACCUMULATE) dx += ; bit 1 (I2V_POOL_MASK_POOLED) mask_src is the POOLED output y
+ * [N,P,Q,C] instead of the pooled tensor's input x [N,H,W,C]: the winner of a window is y itself, so
+ * 1[x[argmax] > 0] = 1[y > 0], and y is stride^2 times smaller than x.                                   */
+#define I2V_POOL_ACCUMULATE 1
+#define I2V_POOL_MASK_POOLED 2
 int i2v_maxpool_bwd_f32(const float* dy, const uint8_t* argmax, const float* mask_src, float* dx, int N, int H,
-                        int W, int C, int P, int Q, int k, int stride, int pad, int accumulate /* dx += */,
+                        int W, int C, int P, int Q, int k, int stride, int pad, int flags,
                         i2v_stream_t stream);
 
 /* dst[m, dst_off : dst_off+Ccopy] (=|+=) src[m, src_off : src_off+Ccopy] — channel concat of SqueezeNet's

@@ -109,6 +109,15 @@ def test_maxpool_fwd_bwd(H, W, k, s, p, ceil):
     capi.maxpool_bwd(dy.permute(0, 2, 3, 1).contiguous().to(DEV), am, xd, dx, k, s, p)
     got = dx.permute(0, 3, 1, 2).cpu()
     assert torch.allclose(got, ref * nz, rtol=1e-6, atol=1e-7)
+    # the same mask taken from the pooled output (1[y > 0] = 1[x[argmax] > 0]) is bit-identical, also with dx +=
+    dx2 = torch.full_like(xd, float("nan"))
+    capi.maxpool_bwd(dy.permute(0, 2, 3, 1).contiguous().to(DEV), am, y, dx2, k, s, p, mask_pooled=True)
+    assert torch.equal(dx2, dx)
+    base = torch.randn_like(xd)
+    acc1, acc2 = base.clone(), base.clone()
+    capi.maxpool_bwd(dy.permute(0, 2, 3, 1).contiguous().to(DEV), am, xd, acc1, k, s, p, accumulate=True)
+    capi.maxpool_bwd(dy.permute(0, 2, 3, 1).contiguous().to(DEV), am, y, acc2, k, s, p, accumulate=True, mask_pooled=True)
+    assert torch.equal(acc1, acc2)
 
 
 def test_copy_channels():
@@ -279,7 +288,7 @@ def _pack_bits(t_nhwc):
 @pytest.mark.parametrize("x3", [True, False])
 def test_conv_tc_bit_masks(shape, x3):
     """TMA epilogue: the forward's activity bits equal 1[y > 0] exactly, and a data gradient masked by bits (with an
-    in-place addend) is bit-identical to the same launch with the f32 mask source (register epilogue)."""
+    in-place addend) makes the same mask decisions as the same launch with the f32 mask source (register epilogue)."""
     N, H, W, Cin, Cout, k, s, p = shape
     g = torch.Generator().manual_seed(5)
     x = torch.randn(N, Cin, H, W, generator=g)
@@ -314,7 +323,10 @@ def test_conv_tc_bit_masks(shape, x3):
         got = add.clone() if inplace else torch.full_like(add, float("nan"))
         capi.conv_tc(d, 1, dy, dh if x3 else dr, dl if x3 else None, None, got if inplace else add, None, got, mask_bits=abits)
         assert torch.isfinite(got).all()
-        assert torch.equal(got, want)
+        # same mask decisions exactly; values to rounding (the dual-issuer kernel keeps the two cross terms in separate
+        # accumulators, the register-epilogue kernel in one)
+        assert torch.equal(got == 0, want == 0)
+        assert (got - want).abs().max() <= 2e-6 * want.abs().max()
 
 
 @pytest.mark.parametrize("H,W,k,s,p", [(224, 224, 7, 2, 3), (64, 64, 7, 2, 3), (64, 64, 11, 4, 2), (32, 32, 3, 1, 1),
