@@ -6,15 +6,22 @@ attacks on a white-box *video* model.  The model's forward/backward is the calle
 re-normalise block that every class repeats (289-293, 334-338, ...) and MI's per-frame mean-|g|
 normalisation + momentum (328-332, utils.py:58-67) run in this repo's K3b / K3c kernels.
 
-The remaining variants (DIFGSM, TIFGSM, SGM, SIM, TIFGSM3D, TAP) share the same update block and are
-listed as "next" in SURVEY.md 8(f).
+The transfer-enhancing variants of SURVEY.md 8(f) rank 3 share that update block and differ only in how the
+gradient is obtained / conditioned: `DIFGSM` (342-411, random resize + pad of the input), `TIFGSM` (413-479,
+per-frame 15x15 Gaussian smoothing of the gradient: K7 stencil kernel), `SGM` (481-551, ReLU backward hooks),
+`SIM` (553-611, gradient averaged over 5 input scales), `TIFGSM3D` (613-683, 15x15x15 smoothing + frame-level
+mean-|g| normalisation).  `TAP` (685-814) hooks layers of gluoncv video models (`model_type` i3d / slowfast /
+tpn) that are not installable offline and stays out of scope.
 """
+import random
+
+import numpy as np
 import torch
 import torch.nn as nn
 
 from i2v_b200 import capi
 
-__all__ = ["Attack", "FGSM", "BIM", "MIFGSM"]
+__all__ = ["Attack", "FGSM", "BIM", "MIFGSM", "DIFGSM", "TIFGSM", "SGM", "SIM", "TIFGSM3D"]
 
 
 class Attack(object):
@@ -237,3 +244,187 @@ class MIFGSM(Attack):
             capi.mi_sign_step_project(adv_videos, grad, momentum, norm, unnorm_videos, float(self.decay),
                                       float(self.step_size), float(self.epsilon))    # 328-338
         return adv_videos
+
+
+# --------------------------------------------------------------------------------------------------------------
+# transfer-enhancing variants: same K3b update block, different gradient
+# --------------------------------------------------------------------------------------------------------------
+class _SignLoopAttack(Attack):
+    """Shared skeleton of DIFGSM / TIFGSM / SGM / SIM / TIFGSM3D (reference base_attacks.py:378-411 and its copies):
+
+        for steps:  grad = self._gradient(adv, labels, loss)             # subclass
+                    [momentum]  see _accumulate                          # subclass-specific normalisation
+                    K3b: denorm -> + step*sign(grad) -> eps-projection -> [0,1] clamp -> renorm   (405-409)
+    """
+
+    def _setup(self, epsilon, steps, decay, momentum):
+        self.epsilon = epsilon
+        self.steps = steps
+        self.step_size = self.epsilon / self.steps
+        self.decay = decay
+        self.momentum = momentum
+
+    def _gradient(self, adv_videos, labels, loss):
+        return self._ce_grad(adv_videos, labels, loss)
+
+    def _accumulate(self, grad, momentum):
+        """reference 394-398 (DI / SGM / SIM): grad /= ||grad||_1; grad += momentum*decay; momentum = grad."""
+        grad = grad / torch.norm(grad, p=1)
+        grad = grad + momentum * self.decay
+        return grad, grad
+
+    def forward(self, videos, labels):
+        videos = videos.to(self.device)
+        labels = labels.to(self.device)
+        loss = nn.CrossEntropyLoss()
+        inner = self._inner(videos)
+        momentum = torch.zeros_like(videos, memory_format=torch.contiguous_format)
+        unnorm_videos = torch.empty_like(videos, memory_format=torch.contiguous_format)
+        capi.denorm(videos.detach().contiguous(), unnorm_videos, inner)
+        adv_videos = videos.clone().detach().contiguous()
+        for _ in range(self.steps):
+            grad = self._gradient(adv_videos, labels, loss)
+            if self.momentum:
+                grad, momentum = self._accumulate(grad, momentum)
+            adv_videos = adv_videos.detach()
+            capi.sign_step_project(adv_videos, grad.contiguous(), unnorm_videos, float(self.step_size), float(self.epsilon),
+                                   inner, project=True)
+        return adv_videos
+
+
+class DIFGSM(_SignLoopAttack):
+    """Diverse Inputs Method (reference base_attacks.py:342-411).  The random resize (nearest) to rnd in [224, 250),
+    zero padding to 250 x 250 at a random offset and resize back to 224 x 224 are the reference's constants (356-376):
+    like the reference this class needs 224 x 224 frames.  RNG consumption order is the reference's
+    (random.random, then three torch.randint calls), so seeded runs follow the same transformations."""
+
+    def __init__(self, model, epsilon=16 / 255, steps=10, decay=1.0, momentum=False):
+        super(DIFGSM, self).__init__("DIFGSM", model)
+        self._setup(epsilon, steps, decay, momentum)
+
+    def _input_diversity(self, videos):
+        if random.random() < 0.5:
+            return videos
+        rnd = torch.randint(224, 250, size=(1, 1)).item()
+        rescaled = videos.view((-1,) + videos.shape[2:])
+        rescaled = torch.nn.functional.interpolate(rescaled, size=[rnd, rnd], mode="nearest")
+        h_rem = 250 - rnd
+        w_rem = 250 - rnd
+        pad_top = torch.randint(0, h_rem, size=(1, 1)).item()
+        pad_bottom = h_rem - pad_top
+        pad_left = torch.randint(0, w_rem, size=(1, 1)).item()
+        pad_right = w_rem - pad_left
+        padded = nn.functional.pad(rescaled, [pad_left, pad_right, pad_top, pad_bottom])
+        padded = torch.nn.functional.interpolate(padded, size=[224, 224], mode="nearest")
+        return padded.view(videos.shape)
+
+    def _gradient(self, adv_videos, labels, loss):
+        adv_videos.requires_grad = True
+        outputs = self.model(self._input_diversity(adv_videos))
+        cost = self._targeted * loss(outputs, labels).to(self.device)
+        return torch.autograd.grad(cost, adv_videos, retain_graph=False, create_graph=False)[0].contiguous()
+
+
+def _gaussian_1d(kernlen, nsig):
+    """scipy.stats.norm.pdf(np.linspace(-nsig, nsig, kernlen)) without the scipy import (reference 427-429)."""
+    x = np.linspace(-nsig, nsig, kernlen)
+    return np.exp(-0.5 * x * x) / np.sqrt(2.0 * np.pi)
+
+
+class TIFGSM(_SignLoopAttack):
+    """Translation-Invariant attack (reference base_attacks.py:413-479): every frame of the gradient is smoothed with
+    a depth-wise 15 x 15 Gaussian (K7 `i2v_depthwise_stencil_f32` instead of 3*T grouped conv2d calls) and divided by
+    mean(|g|) over dims (1,2,3) — i.e. per (clip, image COLUMN), the reference's axes (447)."""
+
+    def __init__(self, model, epsilon=16 / 255, steps=10, decay=1.0, momentum=False):
+        super(TIFGSM, self).__init__("MIFGSM", model)          # the reference registers it under "MIFGSM" (416)
+        self._setup(epsilon, steps, decay, momentum)
+        kern1d = _gaussian_1d(15, 3)
+        kernel_raw = np.outer(kern1d, kern1d)
+        kernel = (kernel_raw / kernel_raw.sum()).astype(np.float32)                  # 427-432
+        self.stack_kernel = torch.from_numpy(np.expand_dims(np.stack([kernel, kernel, kernel]), 1)).to(self.device)
+        self._kernel = torch.from_numpy(kernel).to(self.device).contiguous()
+
+    def _conv2d_frame(self, grads):
+        out_grads = torch.empty_like(grads, memory_format=torch.contiguous_format)
+        capi.depthwise_stencil(grads.contiguous(), out_grads, self._kernel)           # 441-446
+        return out_grads / torch.mean(torch.abs(out_grads), [1, 2, 3], True)          # 447
+
+    def _gradient(self, adv_videos, labels, loss):
+        return self._conv2d_frame(self._ce_grad(adv_videos, labels, loss))
+
+    def _accumulate(self, grad, momentum):
+        grad = grad + momentum * self.decay                                           # 463-465 (no L1 normalisation)
+        return grad, grad
+
+
+class SGM(_SignLoopAttack):
+    """Skip Gradient Method (reference base_attacks.py:481-551): the gradient through every module whose name contains
+    'relu' (but not '0.relu') is scaled by gamma**0.5 by a backward hook registered once in the constructor."""
+
+    def __init__(self, model, epsilon=16 / 255, steps=10, decay=1.0, gamma=0.5, momentum=False):
+        super(SGM, self).__init__("SGM", model)
+        self._setup(epsilon, steps, decay, momentum)
+        self.gamma = gamma
+        self._register_hook_for_model(self.model)
+
+    def _register_hook_for_model(self, model):
+        scale = float(np.power(self.gamma, 0.5))
+
+        def _backward_hook(module, grad_in, grad_out):
+            if isinstance(module, nn.ReLU):
+                return (scale * grad_in[0],)
+
+        self._sgm_handles = []
+        for name, module in model.named_modules():
+            if "relu" in name and "0.relu" not in name:
+                # the reference's (deprecated) non-full hook; it is exact for a single-op module such as nn.ReLU
+                self._sgm_handles.append(module.register_backward_hook(_backward_hook))
+
+
+class SIM(_SignLoopAttack):
+    """Scale-Invariant attack (reference base_attacks.py:553-611): the gradient is the mean over `sclae_step` copies
+    of the input scaled by 1 / 2**i (the reference's spelling of the keyword is kept)."""
+
+    def __init__(self, model, epsilon=16 / 255, steps=10, decay=1.0, sclae_step=5, momentum=False):
+        super(SIM, self).__init__("SIM", model)
+        self._setup(epsilon, steps, decay, momentum)
+        self.sclae_step = sclae_step
+
+    def _gradient(self, adv_videos, labels, loss):
+        mean_grad = None
+        for i in range(self.sclae_step):
+            tmp_videos = 1 / 2 ** i * adv_videos                                       # 572 (gradient w.r.t. the SCALED input)
+            grad = self._ce_grad(tmp_videos.detach(), labels, loss)
+            mean_grad = grad if mean_grad is None else mean_grad + grad
+        return mean_grad / self.sclae_step
+
+
+class TIFGSM3D(_SignLoopAttack):
+    """Translation-Invariant attack with a 15 x 15 x 15 Gaussian over (T, H, W) (reference base_attacks.py:613-683):
+    K7 stencil, then utils.norm_grads (frame-level mean-|g|, K3c reduction)."""
+
+    def __init__(self, model, epsilon=16 / 255, steps=10, decay=1.0, momentum=False):
+        super(TIFGSM3D, self).__init__("TIFGSM3D", model)
+        self._setup(epsilon, steps, decay, momentum)
+        kern1d = _gaussian_1d(15, 3)
+        kernel_raw = np.outer(kern1d, kern1d)
+        used_kernel = np.zeros((15, 15, 15))
+        for i in range(15):
+            used_kernel[i] = kern1d[i] * kernel_raw                                   # 629-631
+        kernel = (used_kernel / used_kernel.sum()).astype(np.float32)
+        self.stack_kernel = torch.from_numpy(np.expand_dims(np.stack([kernel, kernel, kernel]), 1)).to(self.device)
+        self._kernel = torch.from_numpy(kernel).to(self.device).contiguous()
+
+    def _conv3d_frame(self, grads):
+        from utils import norm_grads
+        out_grads = torch.empty_like(grads, memory_format=torch.contiguous_format)
+        capi.depthwise_stencil(grads.contiguous(), out_grads, self._kernel)           # 640
+        return norm_grads(out_grads, True)                                            # 649
+
+    def _gradient(self, adv_videos, labels, loss):
+        return self._conv3d_frame(self._ce_grad(adv_videos, labels, loss))
+
+    def _accumulate(self, grad, momentum):
+        grad = grad + momentum * self.decay                                           # 667-669
+        return grad, grad

@@ -46,3 +46,33 @@ class TinyVideoNet(torch.nn.Module):
         x = torch.relu(self.conv1(x))
         x = torch.relu(self.conv2(x))
         return self.fc(x.mean(dim=(2, 3, 4)))
+
+
+class TinyReluVideoNet(torch.nn.Module):
+    """TinyVideoNet with nn.ReLU MODULES named `layer.N.relu` — what SGM's hook registration looks for
+    (reference base_attacks.py:512-514: names containing 'relu' but not '0.relu')."""
+
+    class Block(torch.nn.Module):
+        def __init__(self, cin, cout, stride):
+            super().__init__()
+            self.conv = torch.nn.Conv3d(cin, cout, 3, stride=stride, padding=1)
+            self.relu = torch.nn.ReLU()
+            self.skip = cin == cout and stride == 1      # residual block: scaling the ReLU branch's gradient then matters
+
+        def forward(self, x):
+            y = self.relu(self.conv(x))
+            return x + y if self.skip else y
+
+    def __init__(self, num_classes=10, width=8, seed=0):
+        super().__init__()
+        state = torch.random.get_rng_state()
+        torch.manual_seed(seed)
+        try:
+            self.layer = torch.nn.Sequential(self.Block(3, width, 1), self.Block(width, width * 2, (1, 2, 2)),
+                                             self.Block(width * 2, width * 2, 1))
+            self.fc = torch.nn.Linear(width * 2, num_classes)
+        finally:
+            torch.random.set_rng_state(state)
+
+    def forward(self, x):
+        return self.fc(self.layer(x).mean(dim=(2, 3, 4)))

@@ -382,3 +382,130 @@ def mifgsm(model, videos, labels, epsilon=16 / 255, steps=10, decay=1.0, targete
         norm = O.frame_absmean(g)                                              # 328 -> utils.py:63
         adv, momentum = O.mi_sign_step_project(adv, g, momentum, norm, x, decay, step_size, epsilon)   # 328-338
     return adv
+
+
+# --------------------------------------------------------------------------------------------------
+# base_attacks.py:342-683 — transfer-enhancing variants (same update block, different gradient)
+# --------------------------------------------------------------------------------------------------
+def _sign_loop(model, videos, labels, epsilon, steps, grad_fn, accumulate=None, targeted=1):
+    """The loop every variant repeats (e.g. base_attacks.py:378-411): grad -> [momentum] -> update block."""
+    model.eval()
+    videos = np.ascontiguousarray(videos, dtype=np.float32)
+    inner = videos.shape[2] * videos.shape[3] * videos.shape[4]
+    step_size = epsilon / steps
+    momentum = np.zeros_like(videos)
+    x = O.denorm(videos, inner)
+    adv = videos.copy()
+    for _ in range(steps):
+        g = grad_fn(adv)
+        if accumulate is not None:
+            g, momentum = accumulate(g, momentum)
+        adv = O.sign_step_project(adv, g, x, step_size, epsilon, inner)
+    return adv
+
+
+def _l1_momentum(decay):
+    def acc(g, momentum):                                                       # base_attacks.py:394-398
+        gt = torch.from_numpy(g)
+        gt = gt / torch.norm(gt, p=1)
+        gt = gt + torch.from_numpy(momentum) * decay
+        return gt.numpy(), gt.numpy()
+    return acc
+
+
+def _plain_momentum(decay):
+    def acc(g, momentum):                                                       # base_attacks.py:463-465
+        gt = torch.from_numpy(g) + torch.from_numpy(momentum) * decay
+        return gt.numpy(), gt.numpy()
+    return acc
+
+
+def input_diversity(videos):
+    """base_attacks.py:356-376, statement by statement (RNG consumption order included)."""
+    import random
+    if random.random() < 0.5:
+        return videos
+    rnd = torch.randint(224, 250, size=(1, 1)).item()
+    rescaled = videos.view((-1,) + videos.shape[2:])
+    rescaled = F.interpolate(rescaled, size=[rnd, rnd], mode="nearest")
+    h_rem = 250 - rnd
+    w_rem = 250 - rnd
+    pad_top = torch.randint(0, h_rem, size=(1, 1)).item()
+    pad_bottom = h_rem - pad_top
+    pad_left = torch.randint(0, w_rem, size=(1, 1)).item()
+    pad_right = w_rem - pad_left
+    padded = F.pad(rescaled, [pad_left, pad_right, pad_top, pad_bottom])
+    padded = F.interpolate(padded, size=[224, 224], mode="nearest")
+    return padded.view(videos.shape)
+
+
+def difgsm(model, videos, labels, epsilon=16 / 255, steps=10, decay=1.0, momentum=False, targeted=1):
+    """base_attacks.py:378-411"""
+    def grad_fn(adv):
+        adv_t = torch.from_numpy(adv.copy()).requires_grad_(True)
+        cost = targeted * torch.nn.CrossEntropyLoss()(model(input_diversity(adv_t)), labels)
+        return torch.autograd.grad(cost, adv_t)[0].numpy()
+    return _sign_loop(model, videos, labels, epsilon, steps, grad_fn, _l1_momentum(decay) if momentum else None)
+
+
+def gaussian_kernel(kernlen=15, nsig=3, dims=2):
+    """base_attacks.py:427-432 (2-D) and 624-633 (3-D), float32 as the reference casts it."""
+    x = np.linspace(-nsig, nsig, kernlen)
+    kern1d = np.exp(-0.5 * x * x) / np.sqrt(2.0 * np.pi)                        # scipy.stats.norm.pdf
+    raw = np.outer(kern1d, kern1d)
+    if dims == 2:
+        return (raw / raw.sum()).astype(np.float32)
+    used = np.stack([kern1d[i] * raw for i in range(kernlen)])
+    return (used / used.sum()).astype(np.float32)
+
+
+def tifgsm(model, videos, labels, epsilon=16 / 255, steps=10, decay=1.0, momentum=False, targeted=1):
+    """base_attacks.py:451-479 with _conv2d_frame 434-449 (depth-wise conv per frame, mean over dims (1,2,3))."""
+    k = torch.from_numpy(gaussian_kernel(15, 3, 2))
+    stack = k.expand(3, 1, 15, 15).contiguous()
+
+    def grad_fn(adv):
+        g = torch.from_numpy(_ce_grad(model, adv, labels, targeted))
+        out = torch.zeros_like(g)
+        for i in range(g.shape[2]):
+            out[:, :, i] = F.conv2d(g[:, :, i], stack, groups=3, stride=1, padding=7)
+        out = out / torch.mean(torch.abs(out), [1, 2, 3], True)
+        return out.numpy()
+    return _sign_loop(model, videos, labels, epsilon, steps, grad_fn, _plain_momentum(decay) if momentum else None)
+
+
+def sim(model, videos, labels, epsilon=16 / 255, steps=10, decay=1.0, scale_step=5, momentum=False, targeted=1):
+    """base_attacks.py:563-611"""
+    def grad_fn(adv):
+        mean_grad = None
+        for i in range(scale_step):
+            g = _ce_grad(model, (1 / 2 ** i * torch.from_numpy(adv)).numpy(), labels, targeted)
+            mean_grad = g if mean_grad is None else mean_grad + g
+        return mean_grad / scale_step
+    return _sign_loop(model, videos, labels, epsilon, steps, grad_fn, _l1_momentum(decay) if momentum else None)
+
+
+def sgm(model, videos, labels, epsilon=16 / 255, steps=10, decay=1.0, gamma=0.5, momentum=False, targeted=1):
+    """base_attacks.py:495-551: backward hooks scale the gradient through the named ReLU modules by gamma**0.5."""
+    scale = float(np.power(gamma, 0.5))
+    handles = [m.register_full_backward_hook(lambda mod, gin, gout: (scale * gin[0],))
+               for name, m in model.named_modules() if "relu" in name and "0.relu" not in name and isinstance(m, torch.nn.ReLU)]
+    try:
+        return _sign_loop(model, videos, labels, epsilon, steps, lambda adv: _ce_grad(model, adv, labels, targeted),
+                          _l1_momentum(decay) if momentum else None)
+    finally:
+        for h in handles:
+            h.remove()
+
+
+def tifgsm3d(model, videos, labels, epsilon=16 / 255, steps=10, decay=1.0, momentum=False, targeted=1):
+    """base_attacks.py:651-683 with _conv3d_frame 635-649 (conv3d + utils.norm_grads frame level)."""
+    k = torch.from_numpy(gaussian_kernel(15, 3, 3))
+    stack = k.expand(3, 1, 15, 15, 15).contiguous()
+
+    def grad_fn(adv):
+        g = torch.from_numpy(_ce_grad(model, adv, labels, targeted))
+        out = F.conv3d(g, stack, groups=3, stride=1, padding=7)
+        norm = O.frame_absmean(out.numpy())
+        return out.numpy() / norm[:, None, :, None, None]
+    return _sign_loop(model, videos, labels, epsilon, steps, grad_fn, _plain_momentum(decay) if momentum else None)

@@ -93,6 +93,41 @@ def run_base(ref):
     return rec
 
 
+def run_base_variants(ref):
+    """DIFGSM / TIFGSM / SGM / SIM / TIFGSM3D of the unmodified reference (base_attacks.py:342-683) on seeded inputs."""
+    import random
+    rec = {}
+    torch.manual_seed(0)
+    model = synth.TinyVideoNet()
+    videos, _ = synth.clip(3, b=1, f=32, h=12, w=12)
+    labels = torch.tensor([3])
+    rec["videos"], rec["labels"] = videos.numpy(), labels.numpy()
+    rec["weight_checksums"] = weight_checksum(model)[None]
+    for mom in (False, True):
+        tag = "_mom" if mom else ""
+        rec["tifgsm3" + tag] = ref.base_attacks.TIFGSM(model, steps=3, momentum=mom)(videos.clone(), labels).numpy()
+        rec["sim2" + tag] = ref.base_attacks.SIM(model, steps=2, momentum=mom)(videos.clone(), labels).numpy()
+        rec["tifgsm3d2" + tag] = ref.base_attacks.TIFGSM3D(model, steps=2, momentum=mom)(videos.clone(), labels).numpy()
+    relu_model = synth.TinyReluVideoNet()
+    rec["relu_weight_checksums"] = weight_checksum(relu_model)[None]
+    for mom in (False, True):
+        tag = "_mom" if mom else ""
+        with LR.quiet():
+            atk = ref.base_attacks.SGM(synth.TinyReluVideoNet(), steps=3, momentum=mom)
+            rec["sgm3" + tag] = atk(videos.clone(), labels).numpy()
+    rec["bim3_relu"] = ref.base_attacks.BIM(synth.TinyReluVideoNet(), steps=3)(videos.clone(), labels).numpy()
+    # DI needs 224 x 224 frames (constants of base_attacks.py:356-376).  To keep the fixture small the input is
+    # synth.clip(5, b=1, f=2, h=224, w=224) (regenerated by the tests) and only the perturbation adv - videos is
+    # stored, as float16 (|delta| <= eps/std = 0.28: 1e-4 resolution, enough to compare sign patterns)
+    di_videos, _ = synth.clip(5, b=1, f=2, h=224, w=224)
+    for mom in (False, True):
+        random.seed(11)
+        torch.manual_seed(11)
+        adv = ref.base_attacks.DIFGSM(model, steps=4, momentum=mom)(di_videos.clone(), labels)
+        rec["difgsm4_delta16" + ("_mom" if mom else "")] = (adv - di_videos).numpy().astype(np.float16)
+    return rec
+
+
 def main():
     torch.set_num_threads(THREADS)
     os.makedirs(OUT, exist_ok=True)
@@ -111,6 +146,7 @@ def main():
             ref, "aens", ["resnet", "squeezenet"], {"resnet": [1, 2], "squeezenet": [2, 3]}, (1, 2, 64, 64), 2, 0.005,
             coef_CE=True),
         "base_tiny3d": lambda: run_base(ref),
+        "base_variants": lambda: run_base_variants(ref),
     }
     only = sys.argv[1:]
     for name, job in jobs.items():

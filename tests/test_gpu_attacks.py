@@ -368,3 +368,51 @@ def test_image_main_driver_end_to_end(tmp_path):
         assert np.abs(adv - clean.numpy()[0]).max() > 0
     info = json.load(open(os.path.join(out, "loss_info_1.json")))
     assert sorted(info) == ["synthetic_%05d" % i for i in range(3)] and sorted(info["synthetic_00000"]) == ["0", "1"]
+
+
+def test_base_variants_match_reference_fixture(golden):
+    """DIFGSM / TIFGSM / SGM / SIM / TIFGSM3D (base_attacks.py:342-683) on the GPU against the unmodified classes: the
+    K3b update block is bit-exact given the gradient, the gradient itself comes from cuDNN / the K7 stencil instead of
+    oneDNN, so the bar is the fraction of identical pixels after the sign steps and the exact eps-ball."""
+    import random
+    g = golden("base_variants")
+    labels = torch.from_numpy(g["labels"])
+    v = torch.from_numpy(g["videos"])
+
+    def frac_equal(adv, ref):
+        adv = adv.cpu().numpy()
+        _bounds_ok(g["videos"], adv)
+        return float((np.abs(adv - ref) < 1e-6).mean())
+
+    stats = {}
+    for mom in (False, True):
+        tag = "_mom" if mom else ""
+        model = synth.TinyVideoNet().cuda()
+        stats["tifgsm" + tag] = frac_equal(base_attacks.TIFGSM(model, steps=3, momentum=mom)(v.clone(), labels), g["tifgsm3" + tag])
+        stats["sim" + tag] = frac_equal(base_attacks.SIM(model, steps=2, momentum=mom)(v.clone(), labels), g["sim2" + tag])
+        stats["tifgsm3d" + tag] = frac_equal(base_attacks.TIFGSM3D(model, steps=2, momentum=mom)(v.clone(), labels), g["tifgsm3d2" + tag])
+        stats["sgm" + tag] = frac_equal(base_attacks.SGM(synth.TinyReluVideoNet().cuda(), steps=3, momentum=mom)(v.clone(), labels),
+                                        g["sgm3" + tag])
+        di_videos, _ = synth.clip(5, b=1, f=2, h=224, w=224)
+        random.seed(11)
+        torch.manual_seed(11)
+        adv = base_attacks.DIFGSM(model, steps=4, momentum=mom)(di_videos.clone(), labels).cpu().numpy()
+        _bounds_ok(di_videos.numpy(), adv)
+        stats["difgsm" + tag] = float((np.abs(adv - di_videos.numpy() - g["difgsm4_delta16" + tag].astype(np.float32)) < 2e-3).mean())
+    _record("base_variants/frac_equal", **stats)
+    for k, val in stats.items():
+        assert val > 0.99, (k, val, stats)
+
+
+def test_depthwise_stencil_vs_torch():
+    """K7 against F.conv2d / F.conv3d (groups = 3, zero padding) in float64, ragged sizes included."""
+    gen = torch.Generator().manual_seed(2)
+    for (B, T, H, W, kt, kh, kw) in [(2, 3, 12, 12, 1, 15, 15), (1, 16, 9, 13, 15, 15, 15), (1, 2, 5, 7, 1, 3, 5), (1, 4, 6, 6, 3, 1, 1)]:
+        x = torch.randn(B, 3, T, H, W, generator=gen)
+        k = torch.rand(kt, kh, kw, generator=gen)
+        out = torch.full_like(x, float("nan")).cuda()
+        capi.depthwise_stencil(x.cuda(), out, k.cuda())
+        ref = torch.nn.functional.conv3d(x.double(), k.double().expand(3, 1, kt, kh, kw).contiguous(), groups=3,
+                                         padding=(kt // 2, kh // 2, kw // 2))
+        err = (out.cpu().double() - ref).abs().max() / ref.abs().max()
+        assert err < 2e-6, (B, T, H, W, kt, kh, kw, float(err))

@@ -180,6 +180,35 @@ def test_base_attacks_match_reference(golden):
     assert (mi == g["mifgsm3"]).mean() > 0.9999   # norm is a float64 mean here, a float32 one in torch
 
 
+def test_base_variants_match_reference(golden):
+    """DIFGSM / TIFGSM / SGM / SIM / TIFGSM3D restatements (oracle/loops.py) against the unmodified classes.  The
+    update block is bit-exact given the gradient; what differs is float32 summation order inside torch ops on two
+    code paths of the same library, so the bar is the fraction of identical pixels (sign steps amplify a gradient
+    that rounds to the other side of zero into a full step)."""
+    import random
+    g = golden("base_variants")
+    model = synth.TinyVideoNet()
+    p = next(model.parameters()).detach().double()
+    if not np.allclose([p.sum().item(), p.abs().sum().item(), float(p.flatten()[0])], g["weight_checksums"][0], rtol=0, atol=0):
+        pytest.skip("random init differs from the fixture's")
+    labels = torch.from_numpy(g["labels"])
+    v = g["videos"]
+    for mom in (False, True):
+        tag = "_mom" if mom else ""
+        assert (OL.tifgsm(model, v, labels, steps=3, momentum=mom) == g["tifgsm3" + tag]).mean() > 0.999
+        assert (OL.sim(model, v, labels, steps=2, momentum=mom) == g["sim2" + tag]).mean() > 0.999
+        assert (OL.tifgsm3d(model, v, labels, steps=2, momentum=mom) == g["tifgsm3d2" + tag]).mean() > 0.999
+        assert (OL.sgm(synth.TinyReluVideoNet(), v, labels, steps=3, momentum=mom) == g["sgm3" + tag]).mean() > 0.999
+        di_videos, _ = synth.clip(5, b=1, f=2, h=224, w=224)
+        random.seed(11)
+        torch.manual_seed(11)
+        adv = OL.difgsm(model, di_videos.numpy(), labels, steps=4, momentum=mom)
+        delta = adv - di_videos.numpy()
+        assert (np.abs(delta - g["difgsm4_delta16" + tag].astype(np.float32)) < 2e-3).mean() > 0.999
+    # the SGM hooks do change the result (gamma = 0.5 through three ReLU modules), i.e. the fixture exercises them
+    assert (g["sgm3"] != g["bim3_relu"]).mean() > 0.01
+
+
 def test_eps_bound_never_violated(golden):
     """clamp(modifier, ±eps) is exact; on adv - x the f32 add may exceed eps by 1 ulp(1.0)."""
     g = golden("i2v_resnet50_d2_32")
