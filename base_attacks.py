@@ -21,6 +21,10 @@ import torch.nn as nn
 
 from i2v_b200 import capi
 
+# FP32-parity mode (BASELINE north star): gradients of the white-box model are taken with TF32 off; set to False to
+# keep whatever torch.backends.* says
+FP32_PARITY = True
+
 __all__ = ["Attack", "FGSM", "BIM", "MIFGSM", "DIFGSM", "TIFGSM", "SGM", "SIM", "TIFGSM3D"]
 
 
@@ -159,9 +163,18 @@ class Attack(object):
     def _ce_grad(self, adv_videos, labels, loss):
         """cost = _targeted * CE(model(adv), labels); d cost / d adv (reference base_attacks.py:283-287)."""
         adv_videos.requires_grad = True
-        outputs = self.model(adv_videos)
-        cost = self._targeted * loss(outputs, labels).to(self.device)
-        grad = torch.autograd.grad(cost, adv_videos, retain_graph=False, create_graph=False)[0]
+        # FP32-parity mode: the white-box model is an opaque nn.Module that runs on cuDNN / cuBLAS, whose defaults would
+        # silently compute convolutions in TF32 (1e-3 relative) and flip the sign of small gradient entries
+        prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        if FP32_PARITY:
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            outputs = self.model(adv_videos)
+            cost = self._targeted * loss(outputs, labels).to(self.device)
+            grad = torch.autograd.grad(cost, adv_videos, retain_graph=False, create_graph=False)[0]
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
         return grad.contiguous()
 
     @staticmethod

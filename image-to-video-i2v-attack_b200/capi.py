@@ -58,6 +58,7 @@ SIGNATURES = {
     "i2v_conv_tc_bits_f32": ([_c_p, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_tc_dgrad_class_f32": ([_c_p, _c_int, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p], _c_int),
     "i2v_maxpool_fwd_f32": ([_c_p, _c_p, _c_p] + [_c_int] * 9 + [_c_p], _c_int),
+    "i2v_maxpool_fwd_flags_f32": ([_c_p, _c_p, _c_p] + [_c_int] * 10 + [_c_p], _c_int),
     "i2v_maxpool_bwd_f32": ([_c_p, _c_p, _c_p, _c_p] + [_c_int] * 10 + [_c_p], _c_int),
     "i2v_copy_channels_f32": ([_c_p, _c_p, _c_i64] + [_c_int] * 6 + [_c_p], _c_int),
 }
@@ -418,12 +419,14 @@ def conv_tc_dgrad_class(desc, ph, pw, dy, w_hi, w_lo, addend, mask_src, dx):
                "i2v_conv_tc_dgrad_class_f32")
 
 
-def maxpool_fwd(x, y, argmax, k, stride, pad):
+def maxpool_fwd(x, y, argmax, k, stride, pad, mark_dead=False):
+    """mark_dead: x is a ReLU output; windows whose maximum is not > 0 get argmax = 255 (no winner) so that maxpool_bwd
+    needs no ReLU-backward mask."""
     N, H, W, C = x.shape
     _, P, Q, _ = y.shape
     with _Timed("i2v_maxpool_fwd_f32", 4 * x.numel() + 5 * y.numel()):
-        _check(load().i2v_maxpool_fwd_f32(_dev(x), _dev(y), _dev(argmax, torch.uint8), N, H, W, C, P, Q, k, stride, pad,
-                                          _stream()), "i2v_maxpool_fwd_f32")
+        _check(load().i2v_maxpool_fwd_flags_f32(_dev(x), _dev(y), _dev(argmax, torch.uint8), N, H, W, C, P, Q, k, stride, pad,
+                                                4 if mark_dead else 0, _stream()), "i2v_maxpool_fwd_f32")
 
 
 def maxpool_bwd(dy, argmax, mask_src, dx, k, stride, pad, accumulate=False, mask_pooled=False):

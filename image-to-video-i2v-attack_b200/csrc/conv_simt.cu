@@ -209,28 +209,38 @@ conv_gather_gemm_kernel(const ConvArgs p) {
 // --------------------------------------------------------------------------------------------------
 // max pooling, NHWC, window k x k, stride s, padding pad (-inf), optional ceil_mode handled by the host
 // through (P, Q).  argmax = r*k + s of the FIRST maximum in scan order (torch.nn.MaxPool2d semantics).
+// One CTA per (image, output row): all index arithmetic is 32-bit and per-row (the first version spent its time in
+// three 64-bit divisions per element: 962 / 334 us per 256 frames of ResNet's stem where HBM needs ~200 / 170 us).
+// mark_dead: the pooled tensor is a ReLU output, so a window whose maximum is not > 0 can never pass a gradient on
+// (1[x[argmax] > 0] = 1[y > 0]); it is marked argmax = 255 and the backward pass needs no ReLU mask at all.
 // --------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ argmax, int N, int H, int W,
-                   int C, int P, int Q, int k, int stride, int pad) {
-    const int C4 = C >> 2;
-    const int64_t total = (int64_t)N * P * Q * C4;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c4 = (int)(i % C4);
-        int64_t t = i / C4;
-        const int q = (int)(t % Q); t /= Q;
-        const int pp = (int)(t % P);
-        const int img = (int)(t / P);
+constexpr int kPoolThreads = 256;
+constexpr unsigned char kPoolNoWinner = 255;
+
+__global__ void __launch_bounds__(kPoolThreads)
+maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ argmax, int H, int W,
+                   int C4, int P, int Q, int k, int stride, int pad, int mark_dead) {
+    const int row = blockIdx.x;                      // img * P + pp
+    const int img = row / P, pp = row - img * P;
+    int r_lo = pad - pp * stride; if (r_lo < 0) r_lo = 0;
+    int r_hi = H - 1 - (pp * stride - pad); if (r_hi > k - 1) r_hi = k - 1;
+    const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x) + (int64_t)img * H * W * C4;
+    float4* __restrict__ y4 = reinterpret_cast<float4*>(y) + (int64_t)row * Q * C4;
+    uchar4* __restrict__ a4 = reinterpret_cast<uchar4*>(argmax) + (int64_t)row * Q * C4;
+    const int items = Q * C4;
+    for (int idx = threadIdx.x; idx < items; idx += kPoolThreads) {
+        const int q = idx / C4, c4 = idx - q * C4;
+        int s_lo = pad - q * stride; if (s_lo < 0) s_lo = 0;
+        int s_hi = W - 1 - (q * stride - pad); if (s_hi > k - 1) s_hi = k - 1;
         float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         int arg[4] = {0, 0, 0, 0};
         bool any = false;
-        for (int r = 0; r < k; ++r) {
-            const int iy = pp * stride - pad + r;
-            if (iy < 0 || iy >= H) continue;
-            for (int s = 0; s < k; ++s) {
-                const int ix = q * stride - pad + s;
-                if (ix < 0 || ix >= W) continue;
-                const float4 v = __ldg(reinterpret_cast<const float4*>(x + (((int64_t)img * H + iy) * W + ix) * C) + c4);
+        for (int r = r_lo; r <= r_hi; ++r) {
+            const int64_t xr = (int64_t)(pp * stride - pad + r) * W * C4 + c4;
+            const int ix0 = q * stride - pad;
+#pragma unroll 3
+            for (int s = s_lo; s <= s_hi; ++s) {
+                const float4 v = __ldg(x4 + xr + (ix0 + s) * C4);
                 const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
@@ -238,43 +248,51 @@ maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* 
                 any = true;
             }
         }
-        reinterpret_cast<float4*>(y)[i] = make_float4(best[0], best[1], best[2], best[3]);
-        reinterpret_cast<uchar4*>(argmax)[i] = make_uchar4((unsigned char)arg[0], (unsigned char)arg[1], (unsigned char)arg[2], (unsigned char)arg[3]);
+        if (mark_dead) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (!(best[j] > 0.f)) arg[j] = kPoolNoWinner;
+        }
+        y4[idx] = make_float4(best[0], best[1], best[2], best[3]);
+        a4[idx] = make_uchar4((unsigned char)arg[0], (unsigned char)arg[1], (unsigned char)arg[2], (unsigned char)arg[3]);
     }
 }
 
 // dx[img,h,w,c] = sum over the windows that contain (h,w) and whose argmax IS (h,w) of dy; optionally
 // multiplied by the ReLU-backward mask of the pooled tensor's producer: mask_src = that forward activation x
 // (mask_pooled = 0), or the POOLED output y (mask_pooled = 1) — the winner of a window IS y, so 1[x[argmax] > 0] =
-// 1[y > 0], and y is k*k/stride^2 times smaller than x (the stem activation is then never read in the backward pass).
-__global__ void __launch_bounds__(256)
+// 1[y > 0], and y is k*k/stride^2 times smaller than x.  With argmax written by the forward pass's mark_dead mode no mask
+// is needed (dead windows have no winner).  One CTA per (image, input row); the sum runs over windows in (p, q) order.
+__global__ void __launch_bounds__(kPoolThreads)
 maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ argmax, const float* __restrict__ mask_src,
-                   float* __restrict__ dx, int N, int H, int W, int C, int P, int Q, int k, int stride, int pad, int accumulate,
+                   float* __restrict__ dx, int H, int W, int C4, int P, int Q, int k, int stride, int pad, int accumulate,
                    int mask_pooled) {
-    const int C4 = C >> 2;
-    const int64_t total = (int64_t)N * H * W * C4;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c4 = (int)(i % C4);
-        int64_t t = i / C4;
-        const int w = (int)(t % W); t /= W;
-        const int h = (int)(t % H);
-        const int img = (int)(t / H);
-        float g[4] = {0.f, 0.f, 0.f, 0.f};
-        // windows p with p*stride - pad <= h <= p*stride - pad + k - 1
-        int p_lo = (h + pad - k + 1 + stride - 1) / stride; if (h + pad - k + 1 < 0) p_lo = 0;
-        int p_hi = (h + pad) / stride; if (p_hi > P - 1) p_hi = P - 1;
+    const int row = blockIdx.x;                      // img * H + h
+    const int img = row / H, h = row - img * H;
+    // windows p with p*stride - pad <= h <= p*stride - pad + k - 1
+    int p_lo = (h + pad - k + 1 + stride - 1) / stride; if (h + pad - k + 1 < 0) p_lo = 0;
+    int p_hi = (h + pad) / stride; if (p_hi > P - 1) p_hi = P - 1;
+    const float4* __restrict__ dy4 = reinterpret_cast<const float4*>(dy) + (int64_t)img * P * Q * C4;
+    const uchar4* __restrict__ am4 = reinterpret_cast<const uchar4*>(argmax) + (int64_t)img * P * Q * C4;
+    const float4* __restrict__ yk4 = mask_pooled ? reinterpret_cast<const float4*>(mask_src) + (int64_t)img * P * Q * C4 : nullptr;
+    const float4* __restrict__ mk4 = (mask_src && !mask_pooled) ? reinterpret_cast<const float4*>(mask_src) + (int64_t)row * W * C4 : nullptr;
+    float4* __restrict__ dx4 = reinterpret_cast<float4*>(dx) + (int64_t)row * W * C4;
+    const int items = W * C4;
+    for (int idx = threadIdx.x; idx < items; idx += kPoolThreads) {
+        const int w = idx / C4, c4 = idx - w * C4;
         int q_lo = (w + pad - k + 1 + stride - 1) / stride; if (w + pad - k + 1 < 0) q_lo = 0;
         int q_hi = (w + pad) / stride; if (q_hi > Q - 1) q_hi = Q - 1;
+        float g[4] = {0.f, 0.f, 0.f, 0.f};
         for (int pp = p_lo; pp <= p_hi; ++pp) {
             const int r = h - (pp * stride - pad);
+#pragma unroll 2
             for (int q = q_lo; q <= q_hi; ++q) {
-                const int s = w - (q * stride - pad);
-                const int want = r * k + s;
-                const int64_t o = (((int64_t)img * P + pp) * Q + q) * C4 + c4;
-                const uchar4 a = __ldg(reinterpret_cast<const uchar4*>(argmax) + o);
-                float4 d = __ldg(reinterpret_cast<const float4*>(dy) + o);
-                if (mask_pooled) {
-                    const float4 yv = __ldg(reinterpret_cast<const float4*>(mask_src) + o);
+                const int want = r * k + (w - (q * stride - pad));
+                const int o = (pp * Q + q) * C4 + c4;
+                const uchar4 a = __ldg(am4 + o);
+                float4 d = __ldg(dy4 + o);
+                if (yk4) {
+                    const float4 yv = __ldg(yk4 + o);
                     if (!(yv.x > 0.f)) d.x = 0.f; if (!(yv.y > 0.f)) d.y = 0.f; if (!(yv.z > 0.f)) d.z = 0.f; if (!(yv.w > 0.f)) d.w = 0.f;
                 }
                 if (a.x == want) g[0] += d.x;
@@ -283,15 +301,15 @@ maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ arg
                 if (a.w == want) g[3] += d.w;
             }
         }
-        if (mask_src && !mask_pooled) {
-            const float4 mk = __ldg(reinterpret_cast<const float4*>(mask_src) + i);
+        if (mk4) {
+            const float4 mk = __ldg(mk4 + idx);
             if (!(mk.x > 0.f)) g[0] = 0.f; if (!(mk.y > 0.f)) g[1] = 0.f; if (!(mk.z > 0.f)) g[2] = 0.f; if (!(mk.w > 0.f)) g[3] = 0.f;
         }
         if (accumulate) {   // the pooled tensor's input has another consumer (a hooked layer: K1 wrote its gradient first)
-            const float4 o = reinterpret_cast<const float4*>(dx)[i];
+            const float4 o = dx4[idx];
             g[0] += o.x; g[1] += o.y; g[2] += o.z; g[3] += o.w;
         }
-        reinterpret_cast<float4*>(dx)[i] = make_float4(g[0], g[1], g[2], g[3]);
+        dx4[idx] = make_float4(g[0], g[1], g[2], g[3]);
     }
 }
 
@@ -368,15 +386,21 @@ extern "C" int i2v_conv_dgrad_simt_f32(const i2v_conv_desc* d, const float* dy, 
     return conv_launch(d, 1, dy, bmat, nullptr, addend, mask_src, dx, flags & ~I2V_EPI_RELU, as_stream(stream));
 }
 
-extern "C" int i2v_maxpool_fwd_f32(const float* x, float* y, uint8_t* argmax, int N, int H, int W, int C, int P, int Q,
-                                   int k, int stride, int pad, i2v_stream_t stream) {
+extern "C" int i2v_maxpool_fwd_flags_f32(const float* x, float* y, uint8_t* argmax, int N, int H, int W, int C, int P, int Q,
+                                         int k, int stride, int pad, int flags, i2v_stream_t stream) {
     I2V_REQUIRE(x && y && argmax, "null pointer");
     I2V_REQUIRE(C % 4 == 0 && k >= 1 && k <= 15 && stride >= 1 && pad >= 0 && pad < k, "unsupported pooling shape");
-    if (N == 0) return I2V_OK;
-    const int64_t total = (int64_t)N * P * Q * (C / 4);
-    maxpool_fwd_kernel<<<grid1d(total), 256, 0, as_stream(stream)>>>(x, y, argmax, N, H, W, C, P, Q, k, stride, pad);
+    I2V_REQUIRE((int64_t)P * Q * (C / 4) < 0x7fffffff && (int64_t)N * P < 0x7fffffff, "pooled plane too large");
+    if (N == 0 || P == 0 || Q == 0) return I2V_OK;
+    maxpool_fwd_kernel<<<(unsigned)(N * P), kPoolThreads, 0, as_stream(stream)>>>(x, y, argmax, H, W, C / 4, P, Q, k, stride, pad,
+                                                                                  (flags & 4) ? 1 : 0);
     I2V_LAUNCH_CHECK("i2v_maxpool_fwd_f32");
     return I2V_OK;
+}
+
+extern "C" int i2v_maxpool_fwd_f32(const float* x, float* y, uint8_t* argmax, int N, int H, int W, int C, int P, int Q,
+                                   int k, int stride, int pad, i2v_stream_t stream) {
+    return i2v_maxpool_fwd_flags_f32(x, y, argmax, N, H, W, C, P, Q, k, stride, pad, 0, stream);
 }
 
 extern "C" int i2v_maxpool_bwd_f32(const float* dy, const uint8_t* argmax, const float* mask_src, float* dx, int N, int H,
@@ -385,10 +409,10 @@ extern "C" int i2v_maxpool_bwd_f32(const float* dy, const uint8_t* argmax, const
     I2V_REQUIRE(dy && argmax && dx, "null pointer");
     I2V_REQUIRE(C % 4 == 0 && k >= 1 && k <= 15 && stride >= 1 && pad >= 0 && pad < k, "unsupported pooling shape");
     I2V_REQUIRE(!(flags & 2) || mask_src, "I2V_POOL_MASK_POOLED needs mask_src = the pooled output");
-    if (N == 0) return I2V_OK;
-    const int64_t total = (int64_t)N * H * W * (C / 4);
-    maxpool_bwd_kernel<<<grid1d(total), 256, 0, as_stream(stream)>>>(dy, argmax, mask_src, dx, N, H, W, C, P, Q, k, stride, pad,
-                                                                     flags & 1, (flags >> 1) & 1);
+    I2V_REQUIRE((int64_t)P * Q * (C / 4) < 0x7fffffff && (int64_t)N * H < 0x7fffffff, "pooled plane too large");
+    if (N == 0 || H == 0 || W == 0) return I2V_OK;
+    maxpool_bwd_kernel<<<(unsigned)(N * H), kPoolThreads, 0, as_stream(stream)>>>(dy, argmax, mask_src, dx, H, W, C / 4, P, Q, k, stride,
+                                                                                  pad, flags & 1, (flags >> 1) & 1);
     I2V_LAUNCH_CHECK("i2v_maxpool_bwd_f32");
     return I2V_OK;
 }

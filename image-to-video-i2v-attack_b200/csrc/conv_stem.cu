@@ -177,12 +177,12 @@ stem_dgrad_kernel(const StemArgs a) {
 // tap set is warp-uniform and every plane read is 128 contiguous bytes.  Taps are summed in (r, s) order.
 // grid (ceil(W / (32*stride*warps_per_class...)), H, N): block = 8 warps = 8/stride pixel groups x stride classes
 // ---------------------------------------------------------------------------------------------------------
+// generic tap loops (any R / stride): fallback for filters with more than 4 taps per axis
 __global__ void __launch_bounds__(256)
-stem_col2im_kernel(const float* __restrict__ zt, float* __restrict__ dx, int N, int H, int W, int P, int Q, int R, int st,
-                   int pad, int64_t M) {
+stem_col2im_loop_kernel(const float* __restrict__ zt, float* __restrict__ dx, int N, int H, int W, int P, int Q, int R, int st,
+                        int pad, int64_t M) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cls = warp % st;                                   // w mod stride of this warp's pixels
-    const int grp = warp / st;                                   // 8/st groups of 32 pixels per block
+    const int cls = warp % st, grp = warp / st;
     const int h = blockIdx.y, n = blockIdx.z;
     const int w = (blockIdx.x * (8 / st) + grp) * 32 * st + lane * st + cls;
     if (w >= W) return;
@@ -193,7 +193,7 @@ stem_col2im_kernel(const float* __restrict__ zt, float* __restrict__ dx, int N, 
         if (hp < 0) break;
         const int p = hp / st;
         if (p >= P) continue;
-        for (int s = (cls + pad) % st; s < R; s += st) {           // (w + pad) % st == (cls + pad) % st
+        for (int s = (cls + pad) % st; s < R; s += st) {
             const int wq = w + pad - s;
             if (wq < 0) break;
             const int q = wq / st;
@@ -204,6 +204,50 @@ stem_col2im_kernel(const float* __restrict__ zt, float* __restrict__ dx, int N, 
             acc2 += __ldg(z + (int64_t)2 * RR * M);
         }
     }
+    const int64_t o = (((int64_t)n * 3) * H + h) * W + w;
+    dx[o] = acc0;
+    dx[o + (int64_t)H * W] = acc1;
+    dx[o + (int64_t)2 * H * W] = acc2;
+}
+
+// TAPS = ceil(R / stride) taps per axis at most: all <= 3*TAPS^2 plane reads of a pixel are issued BEFORE the first add
+// (the first version looped with data-dependent bounds: three loads in flight per thread, i.e. latency-bound at ~50 % of
+// the HBM rate); invalid taps read nothing and add +0, which leaves the (r, s)-ordered sum bit-identical.
+template <int TAPS>
+__global__ void __launch_bounds__(256)
+stem_col2im_kernel(const float* __restrict__ zt, float* __restrict__ dx, int N, int H, int W, int P, int Q, int R, int st,
+                   int pad, int64_t M) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cls = warp % st;                                   // w mod stride of this warp's pixels
+    const int grp = warp / st;                                   // 8/st groups of 32 pixels per block
+    const int h = blockIdx.y, n = blockIdx.z;
+    const int w = (blockIdx.x * (8 / st) + grp) * 32 * st + lane * st + cls;
+    if (w >= W) return;
+    const int RR = R * R;
+    const int r0 = (h + pad) % st, s0 = (cls + pad) % st;       // (w + pad) % st == (cls + pad) % st
+    const float* __restrict__ zn = zt + (int64_t)n * P * Q;
+    float v[3][TAPS * TAPS];
+#pragma unroll
+    for (int a = 0; a < TAPS; ++a) {
+        const int r = r0 + a * st;
+        const int hp = h + pad - r;
+        const int p = hp / st;
+        const bool okr = r < R && hp >= 0 && p < P;
+#pragma unroll
+        for (int b = 0; b < TAPS; ++b) {
+            const int s = s0 + b * st;
+            const int wq = w + pad - s;
+            const int q = wq / st;
+            const bool ok = okr && s < R && wq >= 0 && q < Q;
+            const float* z = zn + (int64_t)(r * R + s) * M + (int64_t)p * Q + q;
+            v[0][a * TAPS + b] = ok ? __ldg(z) : 0.f;
+            v[1][a * TAPS + b] = ok ? __ldg(z + (int64_t)RR * M) : 0.f;
+            v[2][a * TAPS + b] = ok ? __ldg(z + (int64_t)2 * RR * M) : 0.f;
+        }
+    }
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < TAPS * TAPS; ++i) { acc0 += v[0][i]; acc1 += v[1][i]; acc2 += v[2][i]; }
     const int64_t o = (((int64_t)n * 3) * H + h) * W + w;
     dx[o] = acc0;
     dx[o + (int64_t)H * W] = acc1;
@@ -274,7 +318,19 @@ int stem_col2im_launch(const float* zt, float* dx, int N, int H, int W, int P, i
     I2V_REQUIRE(stride == 1 || stride == 2 || stride == 4 || stride == 8, "col2im: stride must divide 8");
     const int per_block = (8 / stride) * 32 * stride;              // image columns per block
     dim3 grid((unsigned)((W + per_block - 1) / per_block), (unsigned)H, (unsigned)N);
-    stem_col2im_kernel<<<grid, 256, 0, st>>>(zt, dx, N, H, W, P, Q, R, stride, pad, (int64_t)N * P * Q);
+    const int taps = (R + stride - 1) / stride;
+    const int64_t M = (int64_t)N * P * Q;
+    if (taps > 4) {
+        stem_col2im_loop_kernel<<<grid, 256, 0, st>>>(zt, dx, N, H, W, P, Q, R, stride, pad, M);
+        I2V_LAUNCH_CHECK("i2v_conv_stem_dgrad_tc_f32 (col2im)");
+        return I2V_OK;
+    }
+    switch (taps) {
+        case 1: stem_col2im_kernel<1><<<grid, 256, 0, st>>>(zt, dx, N, H, W, P, Q, R, stride, pad, M); break;
+        case 2: stem_col2im_kernel<2><<<grid, 256, 0, st>>>(zt, dx, N, H, W, P, Q, R, stride, pad, M); break;
+        case 3: stem_col2im_kernel<3><<<grid, 256, 0, st>>>(zt, dx, N, H, W, P, Q, R, stride, pad, M); break;
+        default: stem_col2im_kernel<4><<<grid, 256, 0, st>>>(zt, dx, N, H, W, P, Q, R, stride, pad, M); break;
+    }
     I2V_LAUNCH_CHECK("i2v_conv_stem_dgrad_tc_f32 (col2im)");
     return I2V_OK;
 }

@@ -1241,7 +1241,8 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
             // $I2V_TC_ALO_TMEM=0 selects the single-issuer kernel everywhere, =2 the dual-issuer kernel everywhere
             static const int alo_env = getenv("I2V_TC_ALO_TMEM") ? atoi(getenv("I2V_TC_ALO_TMEM")) : 1;
             const int kit = pr.taps_h * pr.taps_w * (pr.C / 32);
-            const bool alo = x3 && alo_env != 0 && (BN == 64 || kit >= 8 || alo_env == 2);
+            static const int alo_minkit = getenv("I2V_TC_ALO_MINKIT") ? atoi(getenv("I2V_TC_ALO_MINKIT")) : 8;
+            const bool alo = x3 && alo_env != 0 && (BN == 64 || kit >= alo_minkit || alo_env == 2);
             if (alo) {
                 if (BN == 128) I2V_TC_DISPATCH_P(128, true, true);
                 I2V_TC_DISPATCH_P(64, true, true);

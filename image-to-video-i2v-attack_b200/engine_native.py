@@ -430,7 +430,9 @@ class NativeEngine:
                 self._conv_fwd(op, plan["descs"][op.name], x, acts[op.y], acts[op.residual] if op.residual else None,
                                plan["bits"].get(op.y) if need_grad else None)
             elif op.kind == "pool":
-                capi.maxpool_fwd(acts[op.x], acts[op.y], plan["argmax"][op.y], op.k, op.stride, op.pad)
+                # a ReLU output is pooled: windows with nothing > 0 are marked "no winner", which IS the ReLU-backward mask
+                capi.maxpool_fwd(acts[op.x], acts[op.y], plan["argmax"][op.y], op.k, op.stride, op.pad,
+                                 mark_dead=op.x in self.relu_typed)
             else:
                 off = 0
                 for xn in op.xs:
@@ -468,6 +470,11 @@ class NativeEngine:
             ih, iw = plan["dims"][op.x]
             p = torch.arange(P, device=am.device).view(1, P, 1, 1) * op.stride - op.pad
             q = torch.arange(Q, device=am.device).view(1, 1, Q, 1) * op.stride - op.pad
+            # dead windows (mark_dead: nothing > 0, argmax = 255) pass no gradient whichever element is named the winner:
+            # report the first valid element of the window, which is what torch picks among equal zeros
+            r0 = (-p).clamp(min=0)
+            s0 = (-q).clamp(min=0)
+            am = torch.where(am == 255, r0 * op.k + s0, am)
             flat = (p + am // op.k) * iw + (q + am % op.k)
             out.append(flat.permute(0, 3, 1, 2).contiguous().cpu())
         return out
@@ -518,13 +525,12 @@ class NativeEngine:
                 self._conv_dgrad(op, plan["descs"][op.name], gy, addend, mask, dx, plan["bits"].get(op.x))
                 ready.add(op.x)
             elif op.kind == "pool":
-                # ReLU-backward mask of the pooled tensor's producer.  (The same mask can be taken from the POOLED output —
-                # maxpool_bwd(mask_pooled=True), 1/4 of the mask bytes — but the extra load inside the window loop made the
-                # kernel slower on B200: 926 vs 839 us per 256 frames, so the input activation stays the mask source.)
-                mask = acts[op.x] if op.x in self.relu_typed else None
+                # ReLU-backward mask of the pooled tensor's producer: 1[x[argmax] > 0] = 1[y > 0] was folded into the argmax
+                # plane by the forward pass (mark_dead), so no mask tensor is read here (the stem activation, 4x the pooled
+                # bytes, is never touched in the backward pass).
                 if op.x in pending:
                     raise NotImplementedError("pooling input that is also a residual source")
-                capi.maxpool_bwd(gy, plan["argmax"][op.y], mask, G[op.x], op.k, op.stride, op.pad,
+                capi.maxpool_bwd(gy, plan["argmax"][op.y], None, G[op.x], op.k, op.stride, op.pad,
                                  accumulate=op.x in ready)       # hooked input: K1 wrote its gradient first
                 ready.add(op.x)
             else:

@@ -283,6 +283,11 @@ int i2v_conv_tc_dgrad_class_f32(const i2v_conv_desc* d, int ph, int pw, const fl
  * vgg (2,2,0), alexnet / squeezenet (3,2,0; ceil_mode via P,Q).                                      */
 int i2v_maxpool_fwd_f32(const float* x, float* y, uint8_t* argmax, int N, int H, int W, int C, int P, int Q,
                         int k, int stride, int pad, i2v_stream_t stream);
+/* flags: bit 2 (I2V_POOL_MARK_DEAD): the pooled tensor is a ReLU output — windows whose maximum is not > 0 are marked
+ * argmax = 255 (no winner), so the backward pass routes nothing through them and needs no ReLU-backward mask.     */
+#define I2V_POOL_MARK_DEAD 4
+int i2v_maxpool_fwd_flags_f32(const float* x, float* y, uint8_t* argmax, int N, int H, int W, int C, int P, int Q,
+                              int k, int stride, int pad, int flags, i2v_stream_t stream);
 /* flags: bit 0 (I2V_POOL_ACCUMULATE) dx += ; bit 1 (I2V_POOL_MASK_POOLED) mask_src is the POOLED output y
  * [N,P,Q,C] instead of the pooled tensor's input x [N,H,W,C]: the winner of a window is y itself, so
  * 1[x[argmax] > 0] = 1[y > 0], and y is stride^2 times smaller than x.                                   */

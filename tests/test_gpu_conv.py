@@ -118,6 +118,16 @@ def test_maxpool_fwd_bwd(H, W, k, s, p, ceil):
     capi.maxpool_bwd(dy.permute(0, 2, 3, 1).contiguous().to(DEV), am, xd, acc1, k, s, p, accumulate=True)
     capi.maxpool_bwd(dy.permute(0, 2, 3, 1).contiguous().to(DEV), am, y, acc2, k, s, p, accumulate=True, mask_pooled=True)
     assert torch.equal(acc1, acc2)
+    # mark_dead: the ReLU-backward mask folded into the argmax plane by the forward pass (255 = no winner) — same y,
+    # and the unmasked backward over that plane is bit-identical to the masked one
+    y3 = torch.empty_like(y)
+    am3 = torch.empty_like(am)
+    capi.maxpool_fwd(xd, y3, am3, k, s, p, mark_dead=True)
+    assert torch.equal(y3, y)
+    assert torch.equal(am3 == 255, ~(y > 0)) and torch.equal(am3[y > 0], am[y > 0])
+    dx3 = torch.full_like(xd, float("nan"))
+    capi.maxpool_bwd(dy.permute(0, 2, 3, 1).contiguous().to(DEV), am3, None, dx3, k, s, p)
+    assert torch.equal(dx3, dx)
 
 
 def test_copy_channels():
