@@ -260,43 +260,47 @@ stem_col2im_kernel(const float* __restrict__ zt, float* __restrict__ dx, int N, 
 // three channels are staged in shared memory (zero-padded), then every thread assembles float4s of the row-major
 // patch matrix through a k -> staged-offset table; global writes are fully coalesced (Kp floats per pixel).
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+// (ncu on the first version — one flat index per float4 with a division and a table lookup per element — showed it
+// issue-bound: 84 % issue-active at 45 % of the DRAM rate.  Now a thread owns ONE group of four k's for the whole row, so
+// its four staged offsets are loop invariants and the inner loop is 4 LDS + 1 STG.128; taps beyond 3*R*R point at a
+// zero row, so there is no select either.)
+__global__ void __launch_bounds__(320)
 stem_im2col_kernel(const float* __restrict__ x, float* __restrict__ col, int n0, int H, int W, int P, int Q, int R, int st,
-                   int pad, int Kp) {
+                   int pad, int Kp, int qlanes) {
     extern __shared__ __align__(16) float smem[];
     const int pitch = (Q - 1) * st + R;                         // staged columns: image columns -pad .. -pad+pitch-1
-    int* tbl = reinterpret_cast<int*>(smem);                     // [Kp] staged offset of tap k at q = 0, or -1
-    float* rows = smem + Kp;                                     // [3][R][pitch]
+    float* rows = smem;                                          // [3*R + 1][pitch]; the last row is zeros (padding taps)
     const int p = blockIdx.x, n = blockIdx.y;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
     const int K = 3 * R * R;
-    for (int k = tid; k < Kp; k += 256) {
-        int off = -1;
-        if (k < K) { const int c = k / (R * R), rs = k - c * R * R, r = rs / R, s = rs - r * R; off = (c * R + r) * pitch + s; }
-        tbl[k] = off;
-    }
     const int iy0 = p * st - pad;
-    for (int i = tid; i < 3 * R * pitch; i += 256) {
-        const int cr = i / pitch, xx = i - cr * pitch;
+    for (int cr = warp; cr <= 3 * R; cr += nwarps) {             // one staged row per warp and turn
         const int c = cr / R, r = cr - c * R;
-        const int iy = iy0 + r, ix = xx - pad;
-        float v = 0.f;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(x + (((int64_t)(n0 + n) * 3 + c) * H + iy) * W + ix);
-        rows[i] = v;
+        const int iy = iy0 + r;
+        const bool row_ok = cr < 3 * R && iy >= 0 && iy < H;
+        const float* __restrict__ src = x + (((int64_t)(n0 + n) * 3 + (row_ok ? c : 0)) * H + (row_ok ? iy : 0)) * W;
+        for (int xx = lane; xx < pitch; xx += 32) {
+            const int ix = xx - pad;
+            rows[cr * pitch + xx] = (row_ok && ix >= 0 && ix < W) ? __ldg(src + ix) : 0.f;
+        }
+    }
+    const int k4n = Kp / 4;
+    const int k4 = tid % k4n, ql = tid / k4n;                    // this thread's k group and first pixel
+    int off[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int k = k4 * 4 + j;
+        int o = 3 * R * pitch;                                   // zero row
+        if (k < K) { const int c = k / (R * R), rs = k - c * R * R, r = rs / R, s = rs - r * R; o = (c * R + r) * pitch + s; }
+        off[j] = o;
     }
     __syncthreads();
-    const int k4n = Kp / 4;
-    float4* out = reinterpret_cast<float4*>(col + ((int64_t)n * P + p) * Q * Kp);
-    for (int i = tid; i < Q * k4n; i += 256) {
-        const int q = i / k4n, k = (i - q * k4n) * 4;
+    if (ql >= qlanes) return;
+    float4* out = reinterpret_cast<float4*>(col + ((int64_t)n * P + p) * Q * Kp) + k4;
+#pragma unroll 2
+    for (int q = ql; q < Q; q += qlanes) {
         const int base = q * st;
-        const int o0 = tbl[k], o1 = tbl[k + 1], o2 = tbl[k + 2], o3 = tbl[k + 3];
-        float4 v;
-        v.x = o0 >= 0 ? rows[o0 + base] : 0.f;
-        v.y = o1 >= 0 ? rows[o1 + base] : 0.f;
-        v.z = o2 >= 0 ? rows[o2 + base] : 0.f;
-        v.w = o3 >= 0 ? rows[o3 + base] : 0.f;
-        out[i] = v;
+        out[(int64_t)q * k4n] = make_float4(rows[off[0] + base], rows[off[1] + base], rows[off[2] + base], rows[off[3] + base]);
     }
 }
 
@@ -304,12 +308,16 @@ stem_im2col_kernel(const float* __restrict__ x, float* __restrict__ col, int n0,
 int stem_im2col_launch(const float* x, float* col, int n0, int n, int H, int W, int P, int Q, int R, int stride, int pad, int Kp,
                        cudaStream_t st) {
     const int pitch = (Q - 1) * stride + R;
-    const size_t smem = ((size_t)Kp + (size_t)3 * R * pitch) * sizeof(float);
+    const size_t smem = (size_t)(3 * R + 1) * pitch * sizeof(float);
     I2V_REQUIRE(smem <= 200 * 1024, "stem im2col: input rows do not fit in shared memory");
+    const int k4n = Kp / 4;
+    I2V_REQUIRE(k4n >= 1 && k4n <= 320, "stem im2col: filter too large");
+    const int qlanes = 320 / k4n;                                // pixels in flight per turn; threads = k4n * qlanes <= 320
+    const int threads = (k4n * qlanes + 31) / 32 * 32;
     cudaError_t e = cudaFuncSetAttribute(stem_im2col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "i2v_conv_stem_fwd_tc_f32 (im2col shared memory)");
     dim3 grid((unsigned)P, (unsigned)n);
-    stem_im2col_kernel<<<grid, 256, smem, st>>>(x, col, n0, H, W, P, Q, R, stride, pad, Kp);
+    stem_im2col_kernel<<<grid, threads, smem, st>>>(x, col, n0, H, W, P, Q, R, stride, pad, Kp, qlanes);
     I2V_LAUNCH_CHECK("i2v_conv_stem_fwd_tc_f32 (im2col)");
     return I2V_OK;
 }

@@ -1236,12 +1236,13 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
     if (persistent) {
         if (epi_tma) {
             // dual-issuer variant (A_lo in tensor memory): BN = 64 always (two accumulator stages remain), BN = 128 for
-            // K-heavy tiles only — with its single accumulator stage the short tiles of the HBM-bound 1x1 layers lose the
-            // main-loop / epilogue overlap (measured 64->256 +res: 409 vs 345 us per 256 frames).
+            // tiles of >= 4 k-steps only — with its single accumulator stage the shortest tiles (K = 64) of the HBM-bound 1x1
+            // layers lose the main-loop / epilogue overlap (measured per 256 frames: 64->256 +res 418 vs 360 us at threshold
+            // 2; 256->128 dgrad (K = 128) 357 vs 429 us at threshold 4 against 8).  $I2V_TC_ALO_MINKIT overrides.
             // $I2V_TC_ALO_TMEM=0 selects the single-issuer kernel everywhere, =2 the dual-issuer kernel everywhere
             static const int alo_env = getenv("I2V_TC_ALO_TMEM") ? atoi(getenv("I2V_TC_ALO_TMEM")) : 1;
             const int kit = pr.taps_h * pr.taps_w * (pr.C / 32);
-            static const int alo_minkit = getenv("I2V_TC_ALO_MINKIT") ? atoi(getenv("I2V_TC_ALO_MINKIT")) : 8;
+            static const int alo_minkit = getenv("I2V_TC_ALO_MINKIT") ? atoi(getenv("I2V_TC_ALO_MINKIT")) : 4;
             const bool alo = x3 && alo_env != 0 && (BN == 64 || kit >= alo_minkit || alo_env == 2);
             if (alo) {
                 if (BN == 128) I2V_TC_DISPATCH_P(128, true, true);
