@@ -13,6 +13,7 @@ per-frame 15x15 Gaussian smoothing of the gradient: K7 stencil kernel), `SGM` (4
 mean-|g| normalisation).  `TAP` (685-814) hooks layers of gluoncv video models (`model_type` i3d / slowfast /
 tpn) that are not installable offline and stays out of scope.
 """
+import contextlib
 import random
 
 import numpy as np
@@ -25,7 +26,21 @@ from i2v_b200 import capi
 # keep whatever torch.backends.* says
 FP32_PARITY = True
 
-__all__ = ["Attack", "FGSM", "BIM", "MIFGSM", "DIFGSM", "TIFGSM", "SGM", "SIM", "TIFGSM3D"]
+__all__ = ["Attack", "FGSM", "BIM", "MIFGSM", "DIFGSM", "TIFGSM", "SGM", "SIM", "TIFGSM3D", "TAP"]
+
+
+@contextlib.contextmanager
+def fp32_parity():
+    """The white-box model is an opaque nn.Module that runs on cuDNN / cuBLAS, whose defaults would silently compute
+    convolutions in TF32 (1e-3 relative) and flip the sign of small gradient entries: TF32 off inside, restored after."""
+    prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    if FP32_PARITY:
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        yield
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
 
 
 class Attack(object):
@@ -163,18 +178,10 @@ class Attack(object):
     def _ce_grad(self, adv_videos, labels, loss):
         """cost = _targeted * CE(model(adv), labels); d cost / d adv (reference base_attacks.py:283-287)."""
         adv_videos.requires_grad = True
-        # FP32-parity mode: the white-box model is an opaque nn.Module that runs on cuDNN / cuBLAS, whose defaults would
-        # silently compute convolutions in TF32 (1e-3 relative) and flip the sign of small gradient entries
-        prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
-        if FP32_PARITY:
-            torch.backends.cudnn.allow_tf32 = False
-            torch.backends.cuda.matmul.allow_tf32 = False
-        try:
+        with fp32_parity():
             outputs = self.model(adv_videos)
             cost = self._targeted * loss(outputs, labels).to(self.device)
             grad = torch.autograd.grad(cost, adv_videos, retain_graph=False, create_graph=False)[0]
-        finally:
-            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
         return grad.contiguous()
 
     @staticmethod
@@ -441,3 +448,118 @@ class TIFGSM3D(_SignLoopAttack):
     def _accumulate(self, grad, momentum):
         grad = grad + momentum * self.decay                                           # 667-669
         return grad, grad
+
+
+class TAP(Attack):
+    """Transferable Adversarial Perturbations (reference base_attacks.py:685-814).
+
+    params = {'kernlen': 3, 'temporal_kernlen': 3, 'eta': 1e3, 'conv3d': True, 'model_type': 'i3d'|'slowfast'|'tpn'}
+    (`model_type` selects the hooked layers exactly as 738-744 does; `target_layers`, a list of modules, is an extension for
+    other models).  cost = CE + 1e3 * sum|box(pert / std)| + 0.05 * sum_l |sgn(f_l) sqrt|f_l| - sgn(f0_l) sqrt|f0_l||_2
+    (the reference hard-codes 1e3 and 0.05, 799, and ignores `eta`).
+
+    The CE and feature-distance terms go through the opaque white-box model with torch autograd (so the reference's
+    behaviour at exactly-zero features — a NaN derivative of sign*sqrt|.| — is inherited, not re-defined); the box-filter
+    regulariser and its gradient are two passes of the K7 stencil (uniform kernels are symmetric, so the transposed
+    convolution is the same stencil over sign(out)); the update is K3b.  `loss_info` is keyed by the step index (the
+    reference's key `i` is shadowed by the feature loop, 790, and ends up being a tensor)."""
+
+    def __init__(self, model, params, epsilon=16 / 255, steps=10):
+        super(TAP, self).__init__("TAP", model)
+        self.epsilon = epsilon
+        self.steps = steps
+        self.step_size = self.epsilon / self.steps
+        self.target_layers = None
+        for name, value in params.items():
+            setattr(self, name, value)
+        if self.kernlen % 2 != 1 or self.temporal_kernlen % 2 != 1:
+            raise ValueError("TAP needs odd kernlen / temporal_kernlen ('same' padding, 725-734)")
+        kernel = self._initial_kernel_uniform(self.kernlen).astype(np.float32)                        # 701
+        stack_kernel = np.stack([kernel, kernel, kernel])
+        self.stack_2d_kernel = torch.from_numpy(np.expand_dims(stack_kernel, 1)).to(self.device)      # 703
+        kernel_3d = self._initial_kernel_uniform_3d(self.kernlen, self.temporal_kernlen)             # 705
+        stack_kernel_3d = np.stack([kernel_3d, kernel_3d, kernel_3d])
+        self.stack_3d_kernel = torch.from_numpy(np.expand_dims(stack_kernel_3d, 1)).to(self.device)   # 707
+        self._k2d = torch.from_numpy(kernel).to(self.device).contiguous()
+        self._k3d = torch.from_numpy(kernel_3d.astype(np.float32)).to(self.device).contiguous()
+        self.loss_info = {}
+        self._activation_hook()
+
+    def _initial_kernel_uniform(self, kernlen):
+        kern1d = np.ones(kernlen)
+        kernel_raw = np.outer(kern1d, kern1d)
+        return kernel_raw / kernel_raw.sum()
+
+    def _initial_kernel_uniform_3d(self, kernlen, temporal_kernel):
+        kern3d = np.ones((temporal_kernel, kernlen, kernlen))
+        return kern3d / kern3d.sum()
+
+    def _find_target_layer(self):
+        if self.target_layers is not None:
+            return list(self.target_layers)
+        model_type = getattr(self, "model_type", "")
+        if "i3d" in model_type:
+            return [self.model.res_layers._modules["0"], self.model.res_layers._modules["1"]]
+        if "slowfast" in model_type:
+            return [self.model._modules["slow_res2"], self.model._modules["slow_res3"], self.model._modules["fast_res2"],
+                    self.model._modules["fast_res3"]]
+        if "tpn" in model_type:
+            return [self.model.layer1, self.model.layer2]
+        raise ValueError("TAP: params['model_type'] must contain i3d, slowfast or tpn (or pass params['target_layers'])")
+
+    def _activation_hook(self):
+        self.activations = {"value": []}
+
+        def forward_hook(module, input, output):
+            self.activations["value"] += [output]
+            return None
+
+        for layer in self._find_target_layer():
+            layer.register_forward_hook(forward_hook)
+
+    def _reg_cost_and_grad(self, adv_videos, videos):
+        """reg = sum |box * ((adv - videos) / std)| (792-797, 720-735) and d reg / d adv."""
+        std = torch.as_tensor(self.std, dtype=adv_videos.dtype, device=self.device)[None, :, None, None, None]
+        perts = ((adv_videos - videos) / std).contiguous()                                            # 792, _transform_perts
+        kernel = self._k3d if self.conv3d else self._k2d
+        out = capi.depthwise_stencil(perts, torch.empty_like(perts), kernel)
+        reg_cost = out.abs().sum()
+        back = capi.depthwise_stencil(torch.sign(out), torch.empty_like(perts), kernel)
+        return reg_cost, back / std
+
+    def forward(self, videos, labels):
+        batch_size = videos.shape[0]
+        self.loss_info = {}
+        videos = videos.to(self.device).contiguous()
+        labels = labels.to(self.device)
+        inner = self._inner(videos)
+        with fp32_parity(), torch.no_grad():
+            self.activations = {"value": []}
+            self.model(videos)                                                                        # 768-769
+            ori_feature_map = [f.detach() for f in self.activations["value"]]
+        loss = nn.CrossEntropyLoss()
+        unnorm_videos = torch.empty_like(videos)
+        capi.denorm(videos.detach(), unnorm_videos, inner)                                            # 772
+        adv_videos = videos.clone().detach()                                                          # 773
+        for step in range(self.steps):
+            self.activations = {"value": []}
+            adv_videos.requires_grad = True
+            with fp32_parity():
+                outputs = self.model(adv_videos)                                                      # 779
+                cost1 = self._targeted * loss(outputs, labels).to(self.device)                        # 782
+                feat_distance = []
+                for i, j in zip(self.activations["value"], ori_feature_map):                          # 787-789
+                    this_distance = torch.norm((torch.sign(i) * torch.sqrt(torch.abs(i))).reshape(batch_size, -1) -
+                                               (torch.sign(j) * torch.sqrt(torch.abs(j))).reshape(batch_size, -1), p=2, dim=1)
+                    feat_distance.append(this_distance)
+                cost2 = torch.sum(torch.stack(feat_distance), 0)                                      # 790
+                grad = torch.autograd.grad((cost1 + 0.05 * cost2).sum(), adv_videos, retain_graph=False,
+                                           create_graph=False)[0]
+            adv_videos = adv_videos.detach()
+            reg_cost, reg_grad = self._reg_cost_and_grad(adv_videos, videos)                          # 792-797
+            grad = (grad + 1e3 * reg_grad).contiguous()                                               # 799
+            capi.sign_step_project(adv_videos, grad, unnorm_videos, float(self.step_size), float(self.epsilon), inner,
+                                   project=True)                                                      # 806-810
+            self.loss_info[step] = {"ce loss": cost1.detach().cpu().numpy(), "reg_cost": reg_cost.detach().cpu().numpy(),
+                                    "distance": cost2.detach().cpu().numpy()}
+        return adv_videos

@@ -38,6 +38,12 @@ SIGNATURES = {
     "i2v_layer_reweight_f32": ([_c_p, _c_p, _c_int, _c_f, _c_p, _c_p, _c_p, _c_p], _c_int),
     "i2v_layer_sums_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_i64, _c_int, _c_int, _c_p], _c_int),
     "i2v_depthwise_stencil_f32": ([_c_p, _c_p, _c_i64, _c_int, _c_int, _c_int, _c_p, _c_int, _c_int, _c_int, _c_p], _c_int),
+    "i2v_temporal_shift_stack_f32": ([_c_p, _c_p, _c_i64, _c_int, _c_i64, _c_p, _c_int, _c_p], _c_int),
+    "i2v_temporal_combine_f32": ([_c_p, _c_p, _c_p, _c_int, _c_d, _c_p, _c_i64, _c_int, _c_i64, _c_p], _c_int),
+    "i2v_ila_workspace_doubles": ([], _c_int),
+    "i2v_ila_loss_f32": ([_c_p, _c_p, _c_p, _c_i64, _c_f, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
+    "i2v_ila_grad_f32": ([_c_p, _c_p, _c_p, _c_p, _c_i64, _c_p, _c_p], _c_int),
+    "i2v_sign_descent_compose_f32": ([_c_p, _c_p, _c_p, _c_p, _c_i64, _c_i64, _c_int, _c_f, _c_f, _c_p], _c_int),
     "i2v_std_workspace_doubles": ([], _c_int),
     "i2v_std_accumulate_f32": ([_c_p, _c_i64, _c_p, _c_p, _c_p], _c_int),
     "i2v_std_finalize_f32": ([_c_p, _c_i64, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
@@ -102,7 +108,7 @@ def load():
 # tensors read + written once, 2 x MACs of the convolution).
 LAUNCHES = {}
 PROFILE_EVENTS = None
-_NO_KERNEL = ("i2v_device_check", "i2v_std_workspace_doubles", "i2v_adam_step_table", "i2v_conv_tc_supported", "i2v_conv_stem_supported",
+_NO_KERNEL = ("i2v_device_check", "i2v_std_workspace_doubles", "i2v_ila_workspace_doubles", "i2v_adam_step_table", "i2v_conv_tc_supported", "i2v_conv_stem_supported",
               "i2v_conv_tc_set_trace")
 
 
@@ -285,6 +291,68 @@ def depthwise_stencil(src, dst, kernel):
     _check(load().i2v_depthwise_stencil_f32(_dev(src), _dev(dst), B * C, T, H, W, _dev(kernel), kt, kh, kw, _stream()),
            "i2v_depthwise_stencil_f32")
     return dst
+
+
+# ------------------------------------------------------------------------------- K8 (temporal translation)
+def _host_i32(values):
+    import numpy as np
+    return np.ascontiguousarray(values, dtype=np.int32)
+
+
+def temporal_shift_stack(adv, out, moves):
+    """adv [B,C,T,H,W] -> out [D,B,C,T,H,W]: frame t of variant d goes to frame (t + moves[d]) mod T
+    (reference video_attacks.py:93-105, one variant per entry of cycle_move_list)."""
+    B, C, T, H, W = adv.shape
+    mv = _host_i32(moves)
+    if tuple(out.shape) != (len(mv),) + tuple(adv.shape):
+        raise I2VError("out must be [D,B,C,T,H,W]")
+    with _Timed("i2v_temporal_shift_stack_f32", 4 * adv.numel() * (1 + len(mv))):
+        _check(load().i2v_temporal_shift_stack_f32(_dev(adv), _dev(out), B * C, T, H * W, mv.ctypes.data, len(mv), _stream()),
+               "i2v_temporal_shift_stack_f32")
+    return out
+
+
+def temporal_combine(grads, kernel, moves, weight, out):
+    """grads [D,B,C,T,H,W] -> out [B,C,T,H,W] = (1-weight) * sum_d k_d G_d[t] + weight * sum_d k_d G_d[(t+moves[d]) mod T]
+    (reference video_attacks.py:163-177); `kernel` and `moves` are HOST sequences of length D."""
+    import numpy as np
+    D, B, C, T, H, W = grads.shape
+    mv = _host_i32(moves)
+    k = np.ascontiguousarray(kernel, dtype=np.float32).reshape(-1)
+    if len(mv) != D or k.size != D:
+        raise I2VError("kernel / moves must have one entry per gradient variant")
+    with _Timed("i2v_temporal_combine_f32", 4 * out.numel() * (1 + D)):
+        _check(load().i2v_temporal_combine_f32(_dev(grads), k.ctypes.data, mv.ctypes.data, D, float(weight), _dev(out), B * C, T,
+                                               H * W, _stream()), "i2v_temporal_combine_f32")
+    return out
+
+
+# ------------------------------------------------------------------------------- K9 (ILAF loss) / K3d (ILAF update)
+def ila_workspace(device):
+    return torch.empty(load().i2v_ila_workspace_doubles(), device=device, dtype=torch.float64)
+
+
+def ila_loss(f, f_ori, d0, init_norm, workspace, stats, cost_log=None, step_idx=None, add_to_cost=False):
+    """stats[0:4] = cA, cB, loss, |f - f_ori| of one hooked layer (reference image_attacks.py:596-611)."""
+    with _Timed("i2v_ila_loss_f32", 12 * f.numel()):
+        _check(load().i2v_ila_loss_f32(_dev(f), _dev(f_ori), _dev(d0), f.numel(), float(init_norm),
+                                       _dev(workspace, torch.float64), _dev(stats), _dev(cost_log),
+                                       _dev(step_idx, torch.int32), int(add_to_cost), _stream()), "i2v_ila_loss_f32")
+
+
+def ila_grad(f, f_ori, d0, grad, stats):
+    with _Timed("i2v_ila_grad_f32", 16 * f.numel()):
+        _check(load().i2v_ila_grad_f32(_dev(f), _dev(f_ori), _dev(d0), _dev(grad), f.numel(), _dev(stats), _stream()),
+               "i2v_ila_grad_f32")
+    return grad
+
+
+def sign_descent_compose(g, mod, x, next_img, eps, step_size, inner, channels=3):
+    """modifier -= step_size * sign(dcost/dmodifier) through the compose block, then the next true_image
+    (reference image_attacks.py:615-617, 582-585)."""
+    with _Timed("i2v_sign_descent_compose_f32", 20 * g.numel()):
+        _check(load().i2v_sign_descent_compose_f32(_dev(g), _dev(mod), _dev(x), _dev(next_img), g.numel(), inner, channels, eps,
+                                                   step_size, _stream()), "i2v_sign_descent_compose_f32")
 
 
 # ------------------------------------------------------------------------------- K6 (dispersion reduction)

@@ -227,6 +227,44 @@ adam_compose_kernel(const float* __restrict__ g, float* __restrict__ m, float* _
             adam1(g[i], m[i], v[i], mod[i], x[i], out[i], eps, s, chan_of<IdxT>(i, inner, C), false);
 }
 
+// K3d: ILAF's update (image_attacks.py:615-617 + 582-585 of the next iteration): sign-gradient DESCENT on the modifier,
+// fused with the backward of the compose/normalise block in front of it and the compose/normalise behind it.
+__device__ __forceinline__ void sign_descent1(float g, float& mod, float x, float& out, float eps, float step, int c) {
+    const float sd = chan_std(c);
+    float mc = clampf(mod, -eps, eps);
+    float sum = __fadd_rn(x, mc);
+    bool inside = (sum >= 0.0f) && (sum <= 1.0f) && (mod >= -eps) && (mod <= eps);
+    float gm = __fmul_rn(__fdiv_rn(g, sd), inside ? 1.0f : 0.0f);
+    float mod2 = __fsub_rn(mod, __fmul_rn(step, signf(gm)));
+    mod = mod2;
+    out = compose1(x, mod2, eps, c);
+}
+
+template <typename IdxT, bool UNIFORM>
+__global__ void __launch_bounds__(kThreads)
+sign_descent_compose_kernel(const float* __restrict__ g, float* __restrict__ mod, const float* __restrict__ x,
+                            float* __restrict__ out, IdxT n, IdxT inner, int C, float eps, float step) {
+    ChanIter<IdxT, UNIFORM> it{inner, C};
+    const IdxT nv = n / 4;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4* d4 = reinterpret_cast<float4*>(mod);
+    float4* o4 = reinterpret_cast<float4*>(out);
+    for (IdxT iv = (IdxT)blockIdx.x * kThreads + threadIdx.x; iv < nv; iv += (IdxT)gridDim.x * kThreads) {
+        int c[4]; it.channels(iv, c);
+        float4 gg = ld_stream(g4 + iv);
+        float4 xx = ld_stream(x4 + iv);
+        float4 dd = ld_plain(d4 + iv);
+        float4 oo;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sign_descent1(lane(gg, j), lane(dd, j), lane(xx, j), lane(oo, j), eps, step, c[j]);
+        d4[iv] = dd;
+        st_stream(o4 + iv, oo);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (IdxT i = nv * 4; i < n; ++i) sign_descent1(g[i], mod[i], x[i], out[i], eps, step, chan_of<IdxT>(i, inner, C));
+}
+
 // K3b
 template <typename IdxT, bool UNIFORM>
 __global__ void __launch_bounds__(kThreads)
@@ -488,6 +526,26 @@ extern "C" int i2v_sign_step_project_f32(float* adv, const float* g, const float
         else sign_step_kernel<uint64_t, false><<<grid, kThreads, 0, st>>>(adv, g, x, (uint64_t)n, (uint64_t)inner, channels, step_size, eps, project);
     }
     I2V_LAUNCH_CHECK("i2v_sign_step_project_f32");
+    return I2V_OK;
+}
+
+extern "C" int i2v_sign_descent_compose_f32(const float* g, float* mod, const float* x, float* next_img, int64_t n,
+                                           int64_t inner, int channels, float eps, float step_size, i2v_stream_t stream) {
+    if (int r = check_layout(g, n, inner, channels)) return r;
+    if (n == 0) return I2V_OK;
+    I2V_REQUIRE(channels == 3, "sign-step kernels take the reference's 3-channel layouts only");
+    I2V_REQUIRE(mod && x && next_img, "null state pointer");
+    I2V_REQUIRE(aligned16(mod) && aligned16(x) && aligned16(next_img), "state pointers must be 16-byte aligned");
+    cudaStream_t st = as_stream(stream);
+    const int grid = grid_for(sign_descent_compose_kernel<uint32_t, true>, n / 4);
+    if (n < (int64_t)0x7fffffff) {
+        if (inner % 4 == 0) sign_descent_compose_kernel<uint32_t, true><<<grid, kThreads, 0, st>>>(g, mod, x, next_img, (uint32_t)n, (uint32_t)inner, channels, eps, step_size);
+        else sign_descent_compose_kernel<uint32_t, false><<<grid, kThreads, 0, st>>>(g, mod, x, next_img, (uint32_t)n, (uint32_t)inner, channels, eps, step_size);
+    } else {
+        if (inner % 4 == 0) sign_descent_compose_kernel<uint64_t, true><<<grid, kThreads, 0, st>>>(g, mod, x, next_img, (uint64_t)n, (uint64_t)inner, channels, eps, step_size);
+        else sign_descent_compose_kernel<uint64_t, false><<<grid, kThreads, 0, st>>>(g, mod, x, next_img, (uint64_t)n, (uint64_t)inner, channels, eps, step_size);
+    }
+    I2V_LAUNCH_CHECK("i2v_sign_descent_compose_f32");
     return I2V_OK;
 }
 

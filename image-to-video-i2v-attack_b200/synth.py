@@ -76,3 +76,25 @@ class TinyReluVideoNet(torch.nn.Module):
 
     def forward(self, x):
         return self.fc(self.layer(x).mean(dim=(2, 3, 4)))
+
+
+class TinyTPNLike(torch.nn.Module):
+    """Seeded stand-in with the attribute names the reference's `model_type == 'tpn'` branches hook (`layer1`, `layer2`:
+    TAP base_attacks.py:738-744, ILAF image_attacks.py:514-520).  The hooked modules are bare Conv3d layers (the ReLUs are
+    functional), so hooked features have no exact zeros — TAP's sign(f)*sqrt(|f|) has a NaN derivative at 0."""
+
+    def __init__(self, num_classes=10, width=8, seed=0):
+        super().__init__()
+        state = torch.random.get_rng_state()
+        torch.manual_seed(seed)
+        try:
+            self.layer1 = torch.nn.Conv3d(3, width, 3, padding=1)
+            self.layer2 = torch.nn.Conv3d(width, width * 2, 3, stride=(1, 2, 2), padding=1)
+            self.fc = torch.nn.Linear(width * 2, num_classes)
+        finally:
+            torch.random.set_rng_state(state)
+
+    def forward(self, x):
+        x = torch.relu(self.layer1(x))
+        x = torch.relu(self.layer2(x))
+        return self.fc(x.mean(dim=(2, 3, 4)))

@@ -186,6 +186,34 @@ int i2v_conv_dgrad_simt_f32(const i2v_conv_desc* d, const float* dy, const float
 int i2v_depthwise_stencil_f32(const float* src, float* dst, int64_t volumes, int T, int H, int W, const float* k,
                               int kt, int kh, int kw, i2v_stream_t stream);
 
+/* ---- K8: temporal translation (reference video_attacks.py, TemporalTranslation) ------------------------------
+ * i2v_temporal_shift_stack_f32: the D cyclically shifted copies of the clip fed to the model each step
+ *   (93-105 `_cycle_move`, 192-200): out[d][bc][(t + moves[d]) mod T][hw] = adv[bc][t][hw]; adv = [B*C, T, HW].
+ * i2v_temporal_combine_f32: the gradient augmentation (163-177 with `_conv1d_frame` 80-91) over grads = [D][B*C,T,HW]:
+ *   out = f32(1-weight) * sum_d k[d]*G_d[t] + f32(weight) * sum_d k[d]*G_d[(t + moves[d]) mod T]   (d-ordered FMAs).
+ * `moves` and `kernel` are HOST arrays of length D <= 32 (they travel as kernel parameters).                  */
+int i2v_temporal_shift_stack_f32(const float* adv, float* out, int64_t BC, int T, int64_t HW, const int* moves, int D,
+                                 i2v_stream_t stream);
+int i2v_temporal_combine_f32(const float* grads, const float* kernel, const int* moves, int D, double weight, float* out,
+                             int64_t BC, int T, int64_t HW, i2v_stream_t stream);
+
+/* ---- K9: ILAF intermediate-level loss (reference image_attacks.py:586-612) and K3d, its update block -------
+ * Per hooked layer, delta = f - f_ori, n = |delta|_2, d0 = the unit displacement of the example being fine-tuned,
+ * init_norm = its length:  loss = -(0.5 n / init_norm + <d0, delta / n>).
+ *   i2v_ila_loss_f32  one HBM pass (FP64 block sums, fixed order) + finalize: stats = {cA, cB, loss, n} with
+ *                     d loss / d f = cA * delta + cB * d0; cost_log[*step_idx] (+)= loss.  workspace >=
+ *                     i2v_ila_workspace_doubles() doubles.
+ *   i2v_ila_grad_f32  grad = cA * (f - f_ori) + cB * d0.
+ *   i2v_sign_descent_compose_f32 (615-617, 582-585): gm = (g / std_c) * 1[0 <= x+clamp(mod) <= 1] * 1[|mod| <= eps];
+ *                     mod -= step_size * sign(gm); next_img = (clamp(x + clamp(mod,+-eps),0,1) - mean_c)/std_c.      */
+int i2v_ila_workspace_doubles(void);
+int i2v_ila_loss_f32(const float* f, const float* f_ori, const float* d0, int64_t n, float init_norm, double* workspace,
+                     float* stats, float* cost_log, const int* step_idx, int add_to_cost, i2v_stream_t stream);
+int i2v_ila_grad_f32(const float* f, const float* f_ori, const float* d0, float* grad, int64_t n, const float* stats,
+                     i2v_stream_t stream);
+int i2v_sign_descent_compose_f32(const float* g, float* mod, const float* x, float* next_img, int64_t n, int64_t inner,
+                                 int channels, float eps, float step_size, i2v_stream_t stream);
+
 /* ---- K6: Dispersion-Reduction loss (reference image_attacks.py:129-234, ImageGuidedStd_Adam) ---------------
  * cost = activations.std() over the WHOLE hooked feature map [N,C,h,w], unbiased (image_attacks.py:216-220);
  * d cost / d x_i = (x_i - mean) / ((n - 1) * std).  The map may be fed in slices (frame chunks):

@@ -14,6 +14,7 @@ temporarily pointed at stubs for their un-installable imports:
   * `image_cam`, `image_cam_utils`       (image_attacks.py:7,9 — dead GradCAM code that pulls cv2)
   * `torchvision.models.<ctor>(pretrained=True)` → seeded random init (no network)
   * `Tensor.cuda` / `Module.cuda` → identity when no GPU is visible (image_attacks.py:45,103,297)
+  * `numpy.math` → the `math` module (video_attacks.py:72 calls `np.math.exp`, removed in numpy 2)
 
 No reference source is copied or edited.
 """
@@ -103,7 +104,7 @@ def _load_as(alias, filename, extra_modules):
 
 
 def load(arch_map=None):
-    """Return a namespace with the reference modules: .image_attacks, .TPAMI_attack, .base_attacks, .utils"""
+    """Return a namespace with the reference modules: .image_attacks, .TPAMI_attack, .base_attacks, .video_attacks, .utils"""
     if not available():
         raise RuntimeError("reference not present at %s" % REFERENCE_ROOT)
     if "ns" in _loaded:
@@ -132,6 +133,11 @@ def load(arch_map=None):
         TPAMI_attack=_load_as("ref_TPAMI_attack", "TPAMI_attack.py", cam),
         base_attacks=_load_as("ref_base_attacks", "base_attacks.py", cam),
     )
+    import math
+    import numpy
+    if not hasattr(numpy, "math"):
+        numpy.math = math                                   # video_attacks.py:72 (np.math.exp)
+    ns.video_attacks = _load_as("ref_video_attacks", "video_attacks.py", dict(cam, base_attacks=ns.base_attacks))
     _loaded["ns"] = ns
     return ns
 

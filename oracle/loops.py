@@ -509,3 +509,186 @@ def tifgsm3d(model, videos, labels, epsilon=16 / 255, steps=10, decay=1.0, momen
         norm = O.frame_absmean(out.numpy())
         return out.numpy() / norm[:, None, :, None, None]
     return _sign_loop(model, videos, labels, epsilon, steps, grad_fn, _plain_momentum(decay) if momentum else None)
+
+
+# --------------------------------------------------------------------------------------------------
+# video_attacks.py:14-229 — TemporalTranslation
+# --------------------------------------------------------------------------------------------------
+def tt_kernel(kernlen, mode):
+    """video_attacks.py:51-78 (`np.math.exp` restated with math.exp)."""
+    import math
+    if mode == "gaussian":
+        k = (kernlen - 1) / 2
+        sigma = k / 3
+        k = int(k)
+        kern1d = np.array([1 / (sigma * np.sqrt(2 * np.pi)) * math.exp(-(x ** 2) / (2 * (sigma ** 2))) for x in range(-k, k + 1)])
+    elif mode == "linear":
+        k = int((kernlen - 1) / 2)
+        half = [1 - i / (k + 1) for i in range(k + 1)]
+        kern1d = np.array(half[::-1][:-1] + half)
+    else:
+        kern1d = np.ones(kernlen)
+    return (kern1d / kern1d.sum()).astype(np.float32)
+
+
+def _cycle(videos, move, frames):
+    """video_attacks.py:93-105: new[:, :, (i + direction*|move| % frames) % frames] = videos[:, :, i]."""
+    direction = -1 if move < 0 else 1
+    amount = abs(move) % frames
+    new = torch.zeros_like(videos)
+    for i in range(frames):
+        new[:, :, (i + direction * amount) % frames] = videos[:, :, i]
+    return new
+
+
+def temporal_translation(model, videos, labels, kernlen, weight, momentum=False, kernel_mode="gaussian", epsilon=16 / 255,
+                         steps=10, delay=1.0, targeted=1, tpnet=False):
+    """video_attacks.py:179-229 with move_type 'adj' (the deterministic one); batch of one clip, as the reference needs."""
+    import math
+    model.eval()
+    videos = np.ascontiguousarray(videos, dtype=np.float32)
+    B, C, T, H, W = videos.shape
+    inner = T * H * W
+    frames = T                                                                  # 36 hard-codes 32
+    step_size = epsilon / steps
+    max_move = int((kernlen - 1) / 2)
+    moves = [i for i in range(-max_move, max_move + 1)]                         # 47-50
+    kernel = torch.from_numpy(tt_kernel(kernlen, kernel_mode))[None]            # 45
+    mom = np.zeros_like(videos)                                                 # 182
+    x = O.denorm(videos, inner)                                                 # 185
+    adv = videos.copy()                                                         # 186
+    for _ in range(steps):
+        adv_t = torch.from_numpy(adv)
+        batch_inps = torch.cat([_cycle(adv_t, m, frames) for m in moves], dim=0)           # 191-200
+        length = len(moves)
+        batch_times = length if tpnet else 5                                    # 202-206
+        batch_size = math.ceil(length / batch_times)
+        grads = []
+        for i in range(batch_times):                                            # 208-210
+            sl = batch_inps[i * batch_size:min((i + 1) * batch_size, length)]
+            if sl.shape[0] == 0:
+                continue                                                        # (the reference raises in torch.cat([]) here)
+            used_labels = torch.cat([labels] * sl.shape[0], dim=0)              # 152
+            inp = sl.clone().requires_grad_(True)
+            cost = targeted * torch.nn.CrossEntropyLoss()(model(inp), used_labels)
+            grads.append(torch.autograd.grad(cost, inp)[0])
+        grads = torch.unsqueeze(torch.cat(grads, dim=0), dim=1)                 # 212-213: [D, N, C, T, H, W]
+        same = grads.clone()                                                    # 170
+        diff = torch.zeros_like(grads)
+        for ind, m in enumerate(moves):                                         # 172-173
+            diff[ind] = _cycle(grads[ind], -m, frames)
+        D = grads.shape[0]
+        s_conv = torch.matmul(kernel, same.reshape(D, -1)).reshape(grads.shape[1:])        # 80-91
+        d_conv = torch.matmul(kernel, diff.reshape(D, -1)).reshape(grads.shape[1:])
+        g = ((1 - weight) * s_conv + weight * d_conv).numpy()                   # 176
+        if momentum:                                                            # 217-220
+            norm = O.frame_absmean(g)
+            adv, mom = O.mi_sign_step_project(adv, g, mom, norm, x, delay, step_size, epsilon)
+        else:
+            adv = O.sign_step_project(adv, g, x, step_size, epsilon, inner)     # 224-228
+    return adv
+
+
+# --------------------------------------------------------------------------------------------------
+# base_attacks.py:685-814 — TAP
+# --------------------------------------------------------------------------------------------------
+def tap(model, layers, videos, labels, kernlen=3, temporal_kernlen=3, conv3d=True, epsilon=16 / 255, steps=10, targeted=1):
+    """base_attacks.py:757-814; `layers` = the hooked modules (738-744).  Returns (adv, [per-step (ce, reg, distance)])."""
+    model.eval()
+    store = []
+    handles = [m.register_forward_hook(lambda mod, inp, out: store.append(out)) for m in layers]
+    try:
+        videos_np = np.ascontiguousarray(videos, dtype=np.float32)
+        videos_t = torch.from_numpy(videos_np)
+        batch_size = videos_np.shape[0]
+        inner = videos_np.shape[2] * videos_np.shape[3] * videos_np.shape[4]
+        step_size = epsilon / steps
+        k2 = torch.full((3, 1, kernlen, kernlen), 1.0 / (kernlen * kernlen))                               # 701-703
+        k3 = torch.full((3, 1, temporal_kernlen, kernlen, kernlen), 1.0 / (temporal_kernlen * kernlen * kernlen))   # 705-707
+        std = torch.tensor(O.STD)[:, None, None, None]
+        del store[:]
+        model(videos_t)                                                          # 768-769
+        ori = [f.detach() for f in store]
+        x = O.denorm(videos_np, inner)                                           # 772
+        adv = videos_np.copy()                                                   # 773
+        info = []
+        for _ in range(steps):
+            del store[:]
+            adv_t = torch.from_numpy(adv.copy()).requires_grad_(True)
+            outputs = model(adv_t)                                               # 779
+            cost1 = targeted * torch.nn.CrossEntropyLoss()(outputs, labels)      # 782
+            dist = []
+            for i, j in zip(list(store), ori):                                   # 787-789
+                dist.append(torch.norm((torch.sign(i) * torch.sqrt(torch.abs(i))).reshape(batch_size, -1) -
+                                       (torch.sign(j) * torch.sqrt(torch.abs(j))).reshape(batch_size, -1), p=2, dim=1))
+            cost2 = torch.sum(torch.stack(dist), 0)                              # 790
+            perts = (adv_t - videos_t) / std                                     # 792 (_transform_perts)
+            if conv3d:                                                           # 793-796
+                out = F.conv3d(perts, k3, groups=3, stride=1,
+                               padding=[int((temporal_kernlen - 1) / 2), int((kernlen - 1) / 2), int((kernlen - 1) / 2)])
+            else:
+                out = torch.zeros_like(perts)
+                for t in range(perts.shape[2]):
+                    out[:, :, t] = F.conv2d(perts[:, :, t], k2, groups=3, stride=1, padding=[int((kernlen - 1) / 2)] * 2)
+            reg = torch.sum(torch.abs(out))
+            cost = cost1 + 1e3 * reg + 0.05 * cost2                              # 799
+            (g,) = torch.autograd.grad(cost.sum(), adv_t)
+            info.append((float(cost1), float(reg), cost2.detach().numpy().copy()))
+            adv = O.sign_step_project(adv, g.numpy(), x, step_size, epsilon, inner)   # 806-810
+        return adv, info
+    finally:
+        for h in handles:
+            h.remove()
+
+
+# --------------------------------------------------------------------------------------------------
+# image_attacks.py:498-629 — ILAF
+# --------------------------------------------------------------------------------------------------
+def ilaf(model, layers, videos, ori_videos, epsilon=16 / 255, steps=60, step_size=0.005):
+    """image_attacks.py:534-629; `layers` = the hooked modules (514-520).  Returns (returned tensor, unscrambled clip,
+    [per-step cost])."""
+    store = []
+    handles = [m.register_forward_hook(lambda mod, inp, out: store.append(out)) for m in layers]
+    try:
+        videos_np = np.ascontiguousarray(videos, dtype=np.float32)
+        ori_np = np.ascontiguousarray(ori_videos, dtype=np.float32)
+        b, c, f, h, w = videos_np.shape
+        inner = f * h * w
+        with torch.no_grad():
+            del store[:]
+            model(torch.from_numpy(ori_np))                                      # 542-550
+            ori_maps = [a.detach() for a in store]
+            del store[:]
+            model(torch.from_numpy(videos_np))                                   # 553-561
+            adv_maps = [a.detach() for a in store]
+        init_dirs, init_norms = [], []
+        for o, a in zip(ori_maps, adv_maps):                                     # 563-569
+            d = a - o
+            n = torch.norm(d, p=2)
+            init_norms.append(n)
+            init_dirs.append(d / torch.norm(d, p=2, keepdim=True))
+        ori_unnorm = O.denorm(ori_np, inner)                                     # 573
+        modifier = O.denorm(videos_np, inner) - ori_unnorm                       # 572, 575
+        costs = []
+        true_image = O.compose_norm(ori_unnorm, modifier, epsilon, inner)        # 582-585
+        for _ in range(steps):
+            del store[:]
+            inp = torch.from_numpy(true_image.copy()).requires_grad_(True)
+            model(inp)                                                           # 588
+            losses = []
+            for o, s, d0, n0 in zip(ori_maps, list(store), init_dirs, init_norms):   # 596-611
+                sd = s - o
+                sn = torch.norm(sd, p=2)
+                sdir = sd / torch.norm(sd, p=2, keepdim=True)
+                magnitude_gain = sn / n0
+                angle_loss = torch.mm(d0.view(1, -1), sdir.view(1, -1).transpose(1, 0))
+                losses.append(-(0.5 * magnitude_gain + angle_loss))
+            cost = torch.sum(torch.stack(losses))                                # 612
+            (g,) = torch.autograd.grad(cost, inp)                                # 614 (through the compose block below)
+            costs.append(float(cost))
+            modifier, true_image = O.sign_descent_compose(g.numpy(), modifier, ori_unnorm, epsilon, step_size, inner)   # 615-617
+        out = torch.from_numpy(true_image).reshape(b, f, c, h, w).permute([0, 2, 1, 3, 4])   # 627-629
+        return out.numpy(), true_image, costs
+    finally:
+        for h in handles:
+            h.remove()

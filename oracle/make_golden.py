@@ -128,6 +128,43 @@ def run_base_variants(ref):
     return rec
 
 
+def run_video_variants(ref):
+    """TemporalTranslation (video_attacks.py), TAP (base_attacks.py:685-814) and ILAF (image_attacks.py:498-629) on the
+    seeded `synth.TinyTPNLike` stand-in (model_type 'tpn' -> layer1 / layer2 hooks), one 32-frame 12x12 clip."""
+    rec = {}
+    videos, _ = synth.clip(3, b=1, f=32, h=12, w=12)
+    labels = torch.tensor([3])
+    rec["videos"], rec["labels"] = videos.numpy(), labels.numpy()
+    rec["weight_checksums"] = weight_checksum(synth.TinyTPNLike())[None]
+
+    def tt(kernlen, weight, mode, steps, mom):
+        with LR.quiet():
+            atk = ref.video_attacks.TemporalTranslation(
+                synth.TinyTPNLike(), {"kernlen": kernlen, "momentum": mom, "weight": weight, "move_type": "adj",
+                                      "kernel_mode": mode}, steps=steps)
+            return atk(videos.clone(), labels).detach().numpy()
+    rec["tt3_k5"] = tt(5, 0.5, "gaussian", 3, False)
+    rec["tt3_k5_mom"] = tt(5, 0.5, "gaussian", 3, True)
+    rec["tt2_k9_linear"] = tt(9, 0.3, "linear", 2, False)
+    for conv3d in (True, False):
+        with LR.quiet():
+            atk = ref.base_attacks.TAP(synth.TinyTPNLike(), {"kernlen": 3, "temporal_kernlen": 3, "eta": 1e3, "conv3d": conv3d,
+                                                            "model_type": "tpn"}, steps=3)
+            adv = atk(videos.clone(), labels).detach().numpy()
+        tag = "3d" if conv3d else "2d"
+        rec["tap3_" + tag] = adv
+        last = list(atk.loss_info.values())[-1]      # the reference keys loss_info by a tensor (790 shadows `i`): one entry survives
+        rec["tap3_%s_last_losses" % tag] = np.array([float(last["ce loss"]), float(last["reg_cost"]),
+                                                     float(np.asarray(last["distance"]).reshape(-1)[0])], dtype=np.float64)
+    with LR.quiet():
+        model = synth.TinyTPNLike()
+        atk = ref.image_attacks.ILAF(model, "tpn", step_size=0.005, steps=4)
+        out = atk(torch.from_numpy(rec["tt3_k5"]).clone(), videos.clone(), labels, ["v0"])
+    rec["ilaf4"] = out.detach().contiguous().numpy()
+    rec["ilaf4_costs"] = np.array([float(atk.loss_info["v0"][i]["cost"]) for i in range(4)], dtype=np.float64)
+    return rec
+
+
 def main():
     torch.set_num_threads(THREADS)
     os.makedirs(OUT, exist_ok=True)
@@ -147,6 +184,7 @@ def main():
             coef_CE=True),
         "base_tiny3d": lambda: run_base(ref),
         "base_variants": lambda: run_base_variants(ref),
+        "video_variants": lambda: run_video_variants(ref),
     }
     only = sys.argv[1:]
     for name, job in jobs.items():

@@ -82,6 +82,49 @@ def adam_compose(g, m, v, mod, x, eps, inner, step, lr, beta1=0.9, beta2=0.999, 
     return m, v, mod, out
 
 
+def sign_descent_compose(g, mod, x, eps, step_size, inner, channels=3):
+    """ILAF's update block (image_attacks.py:615-617 + recompose); returns (mod, next_img)."""
+    g, x = _f32(g), _f32(x)
+    mod = _f32(mod).copy()
+    out = np.empty_like(x)
+    lib().oracle_sign_descent_compose_f32(_ptr(g), _ptr(mod), _ptr(x), _ptr(out), i64(x.size), i64(inner), ci(channels),
+                                          cf(eps), cf(step_size))
+    return mod, out
+
+
+def temporal_shift_stack(adv, moves):
+    """adv [B,C,T,H,W] -> [D,B,C,T,H,W] with frame t of variant d moved to (t + moves[d]) mod T (video_attacks.py:93-105)."""
+    adv = _f32(adv)
+    B, C, T, H, W = adv.shape
+    mv = np.ascontiguousarray(moves, dtype=np.int32)
+    out = np.empty((len(mv),) + adv.shape, dtype=np.float32)
+    lib().oracle_temporal_shift_stack_f32(_ptr(adv), _ptr(out), i64(B * C), ci(T), i64(H * W),
+                                          mv.ctypes.data_as(ctypes.c_void_p), ci(len(mv)))
+    return out
+
+
+def temporal_combine(grads, kernel, moves, weight):
+    """grads [D,B,C,T,H,W] -> [B,C,T,H,W] (video_attacks.py:163-177)."""
+    grads = _f32(grads)
+    D, B, C, T, H, W = grads.shape
+    mv = np.ascontiguousarray(moves, dtype=np.int32)
+    k = _f32(kernel)
+    out = np.empty(grads.shape[1:], dtype=np.float32)
+    lib().oracle_temporal_combine_f32(_ptr(grads), _ptr(k), mv.ctypes.data_as(ctypes.c_void_p), ci(D), cd(weight), _ptr(out),
+                                      i64(B * C), ci(T), i64(H * W))
+    return out
+
+
+def ila_loss_grad_f64(f, f_ori, d0, init_norm, want_grad=True):
+    """ILAF per-layer loss (float64) and d loss / d f (image_attacks.py:596-611)."""
+    f, f_ori, d0 = _f32(f), _f32(f_ori), _f32(d0)
+    loss = ctypes.c_double()
+    grad = np.empty(f.shape, dtype=np.float64) if want_grad else None
+    lib().oracle_ila_loss_grad_f64(_ptr(f), _ptr(f_ori), _ptr(d0), cd(init_norm), i64(f.size), ctypes.byref(loss),
+                                   grad.ctypes.data_as(ctypes.c_void_p) if want_grad else None)
+    return loss.value, grad
+
+
 def adam_step_scalars(lr, beta1, beta2, step):
     a, b = cf(), cf()
     lib().oracle_adam_step_scalars(cd(lr), cd(beta1), cd(beta2), ci(step), ctypes.byref(a), ctypes.byref(b))

@@ -402,8 +402,10 @@ def test_base_variants_match_reference_fixture(golden):
     _record("base_variants/frac_equal", **stats)
     # TI variants smooth the gradient (stable signs); the others take the raw sign of a cuDNN-vs-oneDNN gradient whose
     # near-zero entries flip, each flip moving a pixel by 2*step/std per step (same floor as BIM / MI above: 0.98)
+    # measured with TF32 off for the white-box model: 1.0 everywhere except DI (0.988 / 0.994), whose nearest-neighbour
+    # resize turns one flipped gradient sign into a different sampled pixel
     for k, val in stats.items():
-        assert val > (0.99 if k.startswith("tifgsm") else 0.96), (k, val, stats)
+        assert val > (0.97 if k.startswith("difgsm") else 0.995), (k, val, stats)
 
 
 def test_depthwise_stencil_vs_torch():
@@ -418,3 +420,53 @@ def test_depthwise_stencil_vs_torch():
                                          padding=(kt // 2, kh // 2, kw // 2))
         err = (out.cpu().double() - ref).abs().max() / ref.abs().max()
         assert err < 2e-6, (B, T, H, W, kt, kh, kw, float(err))
+
+
+def test_video_variants_match_reference_fixture(golden):
+    """TemporalTranslation (video_attacks.py), TAP (base_attacks.py:685-814) and ILAF (image_attacks.py:498-629) on the
+    GPU against the unmodified classes run on the CPU (tests/golden/video_variants.npz).  The K8 / K3b / K3c / K3d / K7 /
+    K9 arithmetic is pinned bit-exactly or against float64 in test_gpu_kernels.py; here the white-box model's gradient
+    comes from cuDNN instead of oneDNN, so the bar is the fraction of identical pixels after the sign steps (each flip of
+    a near-zero gradient moves a pixel by 2*step/std), the exact eps-ball and the per-step costs."""
+    import image_attacks
+    import video_attacks
+    g = golden("video_variants")
+    v = torch.from_numpy(g["videos"])
+    labels = torch.from_numpy(g["labels"])
+
+    def frac_equal(adv, ref, base=None):
+        adv = adv.detach().cpu().numpy()
+        _bounds_ok(g["videos"] if base is None else base, adv)
+        return float((np.abs(adv - ref) < 1e-6).mean())
+
+    stats = {}
+
+    def tt(kernlen, weight, mode, steps, mom):
+        atk = video_attacks.TemporalTranslation(
+            synth.TinyTPNLike().cuda(), {"kernlen": kernlen, "momentum": mom, "weight": weight, "move_type": "adj",
+                                         "kernel_mode": mode}, steps=steps)
+        return atk(v.clone(), labels)
+    adv_tt = tt(5, 0.5, "gaussian", 3, False)
+    stats["tt3_k5"] = frac_equal(adv_tt, g["tt3_k5"])
+    stats["tt3_k5_mom"] = frac_equal(tt(5, 0.5, "gaussian", 3, True), g["tt3_k5_mom"])
+    stats["tt2_k9_linear"] = frac_equal(tt(9, 0.3, "linear", 2, False), g["tt2_k9_linear"])
+    # kernlen 7 makes the reference's 5-way split produce an empty model batch (torch.cat([]) raises there): runs here
+    adv7 = tt(7, 0.5, "gaussian", 1, True)
+    _bounds_ok(g["videos"], adv7.cpu().numpy())
+    for conv3d, tag in ((True, "3d"), (False, "2d")):
+        atk = base_attacks.TAP(synth.TinyTPNLike().cuda(), {"kernlen": 3, "temporal_kernlen": 3, "eta": 1e3, "conv3d": conv3d,
+                                                            "model_type": "tpn"}, steps=3)
+        stats["tap3_" + tag] = frac_equal(atk(v.clone(), labels), g["tap3_" + tag])
+        last = atk.loss_info[2]
+        got = np.array([float(last["ce loss"]), float(last["reg_cost"]), float(np.asarray(last["distance"]).reshape(-1)[0])])
+        assert np.allclose(got, g["tap3_%s_last_losses" % tag], rtol=2e-2), (got, g["tap3_%s_last_losses" % tag])
+    il = image_attacks.ILAF(synth.TinyTPNLike().cuda(), "tpn", step_size=0.005, steps=4)
+    out = il(torch.from_numpy(g["tt3_k5"]).clone(), v.clone(), labels, ["v0"])
+    assert tuple(out.shape) == tuple(g["ilaf4"].shape)
+    stats["ilaf4"] = float((np.abs(out.detach().cpu().numpy() - g["ilaf4"]) < 1e-6).mean())
+    _bounds_ok(g["videos"], il.last_adv.cpu().numpy())
+    costs = np.array([float(il.loss_info["v0"][i]["cost"]) for i in range(4)])
+    assert np.allclose(costs, g["ilaf4_costs"], rtol=2e-4), (costs, g["ilaf4_costs"])
+    _record("video_variants/frac_equal", **stats)
+    for k, val in stats.items():                  # measured: 1.0 except tap3_2d 0.99986
+        assert val > 0.995, (k, val, stats)

@@ -327,3 +327,67 @@ def test_std_loss_grad_vs_float64(shape, chunks, relu_mask):
     assert abs(st[0] - mean64) <= 2e-7 * abs(mean64) and abs(st[1] - sd64) <= 2e-7 * sd64
     assert cost[0] == 7.0 and cost[2] == 7.0 and abs(cost[1] - (7.0 + sd64)) <= 1e-6
     assert np.abs(gr - g64).max() <= 5e-7 * np.abs(g64).max()
+
+
+# ---- K8 temporal translation, K3d / K9 ILAF ----------------------------------------------
+@pytest.mark.parametrize("shape", [(1, 3, 32, 12, 12), (2, 3, 8, 7, 5), (1, 3, 16, 28, 28), (0, 3, 4, 4, 4)])
+def test_temporal_shift_and_combine_bit_exact(shape):
+    rng = np.random.default_rng(21)
+    adv = rng.standard_normal(shape).astype(np.float32)
+    T = shape[2]
+    moves = [-3, -2, -1, 0, 1, 2, 3, T + 5, -(T + 1)]
+    out = torch.full((len(moves),) + shape, float("nan"), device=DEV)
+    capi.temporal_shift_stack(gpu(adv), out, moves)
+    if adv.size:
+        assert bits_equal(out.cpu().numpy(), O.temporal_shift_stack(adv, moves))
+    D = 7
+    grads = rng.standard_normal((D,) + shape).astype(np.float32)
+    k = rng.random(D).astype(np.float32)
+    k /= k.sum()
+    mv = [-3, -2, -1, 0, 1, 2, 3]
+    for weight in (0.5, 0.3, 0.0, 1.0):
+        got = torch.full(shape, float("nan"), device=DEV)
+        capi.temporal_combine(gpu(grads), k, mv, weight, got)
+        if adv.size:
+            assert bits_equal(got.cpu().numpy(), O.temporal_combine(grads, k, mv, weight)), weight
+
+
+@pytest.mark.parametrize("shape,inner", [((1, 3, 8, 12, 12), 8 * 144), ((2, 3, 3, 5, 7), 105), ((3, 3, 8, 8), 64), ((0, 3, 2, 4, 4), 32)])
+def test_sign_descent_compose_bit_exact(shape, inner):
+    rng = np.random.default_rng(31)
+    x = rng.random(shape, dtype=np.float32)
+    mod = (rng.standard_normal(shape) * 0.08).astype(np.float32)
+    g = rng.standard_normal(shape).astype(np.float32)
+    if g.size:
+        g.reshape(-1)[:5] = 0.0
+        x.reshape(-1)[5:9] = [0.0, 1.0, 0.0, 1.0]
+    md, img = gpu(mod), torch.full(shape, float("nan"), device=DEV)
+    for step in range(3):
+        capi.sign_descent_compose(gpu(g), md, gpu(x), img, EPS, 0.005, inner)
+        mod, want = O.sign_descent_compose(g, mod, x, EPS, 0.005, inner)
+        assert bits_equal(md.cpu().numpy(), mod) and bits_equal(img.cpu().numpy(), want), step
+        g = np.roll(g, 3).copy()
+
+
+@pytest.mark.parametrize("n", [16 * 16 * 6 * 6, 4099, 512 * 8 * 14 * 14, 3])
+def test_ila_loss_grad_vs_float64(n):
+    rng = np.random.default_rng(41)
+    f = rng.standard_normal(n).astype(np.float32)
+    o = (f + 0.3 * rng.standard_normal(n)).astype(np.float32)
+    d0 = rng.standard_normal(n)
+    n0 = float(np.linalg.norm(d0)) * 0.8
+    d0 = (d0 / np.linalg.norm(d0)).astype(np.float32)
+    loss64, grad64 = O.ila_loss_grad_f64(f, o, d0, n0)
+    ws = capi.ila_workspace(torch.device(DEV))
+    stats = torch.zeros(4, device=DEV)
+    cost = torch.zeros(3, device=DEV)
+    idx = torch.tensor([1], device=DEV, dtype=torch.int32)
+    capi.ila_loss(gpu(f), gpu(o), gpu(d0), n0, ws, stats, cost, idx)
+    capi.ila_loss(gpu(f), gpu(o), gpu(d0), n0, ws, stats, cost, idx, add_to_cost=True)
+    grad = capi.ila_grad(gpu(f), gpu(o), gpu(d0), torch.empty(n, device=DEV), stats).cpu().numpy()
+    st = stats.cpu().numpy()
+    assert abs(st[2] - loss64) <= 2e-6 * abs(loss64)
+    assert abs(st[3] - np.linalg.norm(f.astype(np.float64) - o)) <= 1e-6 * st[3]
+    c = cost.cpu().numpy()
+    assert c[0] == 0 and c[2] == 0 and abs(c[1] - 2 * loss64) <= 4e-6 * abs(loss64)
+    assert np.abs(grad - grad64).max() <= 3e-6 * np.abs(grad64).max()

@@ -183,3 +183,53 @@ def test_image_main_host_logic(tmp_path):
     assert torch.equal(batch[1:], v)
     with pytest.raises(ValueError):
         image_main.build_attack(image_main.arg_parse(["--attack_method", "nope"]))
+
+
+def test_temporal_translation_host_side():
+    """video_attacks.TemporalTranslation: variant kernels (video_attacks.py:51-78) and frame moves (93-146) — host logic only."""
+    import random
+    import video_attacks
+    from i2v_b200 import synth
+    from oracle import loops as OL
+    model = synth.TinyTPNLike()
+    for mode in ("gaussian", "linear", "random"):
+        for kernlen in (3, 5, 9):
+            atk = video_attacks.TemporalTranslation(model, {"kernlen": kernlen, "momentum": False, "weight": 0.5,
+                                                            "move_type": "adj", "kernel_mode": mode})
+            assert np.array_equal(atk._kernel_host, OL.tt_kernel(kernlen, mode))
+            assert atk.cycle_move_list == list(range(-(kernlen // 2), kernlen // 2 + 1))
+            assert tuple(atk.kernel.shape) == (1, kernlen) and abs(float(atk.kernel.sum()) - 1) < 1e-6
+            assert atk.step_size == atk.epsilon / atk.steps and atk.frames == 32
+    atk.move_type = "adj"
+    assert [atk._effective_move(m, 32) for m in (-3, 0, 2, 35)] == [-3, 0, 2, 3]
+    atk.move_type = "large"            # 107-120: |m| -> (|m| + frames/2 - 1) mod frames, 0 stays
+    assert [atk._effective_move(m, 32) for m in (-3, 0, 2)] == [-18, 0, 17]
+    atk.move_type = "random"           # 122-135: one randint(0, 100) per non-zero move
+    random.seed(4)
+    got = [atk._effective_move(m, 32) for m in (-1, 0, 1)]
+    random.seed(4)
+    want = [-(random.randint(0, 100) % 32), 0, random.randint(0, 100) % 32]
+    assert got == want
+    with pytest.raises(ValueError):
+        video_attacks.TemporalTranslation(model, {"kernlen": 3, "momentum": False, "weight": 0.5, "move_type": "adj",
+                                                  "kernel_mode": "cubic"})
+
+
+def test_tap_and_ilaf_constructors():
+    import base_attacks
+    import image_attacks
+    from i2v_b200 import synth
+    model = synth.TinyTPNLike()
+    tap = base_attacks.TAP(model, {"kernlen": 3, "temporal_kernlen": 5, "eta": 1e3, "conv3d": True, "model_type": "tpn"})
+    assert tuple(tap.stack_2d_kernel.shape) == (3, 1, 3, 3) and tuple(tap.stack_3d_kernel.shape) == (3, 1, 5, 3, 3)
+    assert abs(float(tap.stack_3d_kernel[0].sum()) - 1) < 1e-6 and tap.step_size == tap.epsilon / tap.steps
+    assert tap._find_target_layer() == [model.layer1, model.layer2]
+    with pytest.raises(ValueError):
+        base_attacks.TAP(model, {"kernlen": 4, "temporal_kernlen": 3, "conv3d": True, "model_type": "tpn"})
+    with pytest.raises(ValueError):
+        base_attacks.TAP(synth.TinyTPNLike(), {"kernlen": 3, "temporal_kernlen": 3, "conv3d": True, "model_type": "resnet"})
+    il = image_attacks.ILAF(model, "tpn")
+    assert il._find_target_layer() is model.layer2 and il.steps == 60 and il.step_size == 0.005
+    assert image_attacks.ILAF(model, "other", target_layers=[model.layer1])._find_target_layer() == [model.layer1]
+    with pytest.raises(ValueError):
+        image_attacks.ILAF(model, "resnet")

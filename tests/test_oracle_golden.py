@@ -218,3 +218,89 @@ def test_eps_bound_never_violated(golden):
     adv01 = O.denorm(OL._frames(torch.from_numpy(np.ascontiguousarray(g["adv"]))).numpy(), inner)
     assert np.abs(adv01 - x).max() <= np.float32(EPS) + 2 * np.finfo(np.float32).eps
     assert adv01.min() >= -1e-6 and adv01.max() <= 1 + 1e-6
+
+
+# ---- TemporalTranslation / TAP / ILAF ----------------------------------------------
+def test_temporal_pieces_match_their_torch_statements():
+    """The C pieces of the TemporalTranslation restatement against the reference's own statements: `_cycle_move`
+    (video_attacks.py:93-105) is a roll, `_grad_augmentation` (163-177) two [1,D] x [D,M] products and a blend."""
+    rng = np.random.default_rng(5)
+    adv = rng.standard_normal((2, 3, 8, 3, 5)).astype(np.float32)
+    moves = [-2, -1, 0, 1, 2, 11, -9]
+    st = O.temporal_shift_stack(adv, moves)
+    for d, m in enumerate(moves):
+        assert np.array_equal(st[d], OL._cycle(torch.from_numpy(adv), m, 8).numpy())
+        assert np.array_equal(st[d], np.roll(adv, m, axis=2))
+    D = 5
+    g = rng.standard_normal((D, 1, 3, 8, 3, 5)).astype(np.float32)
+    k = OL.tt_kernel(D, "gaussian")
+    mv = [-2, -1, 0, 1, 2]
+    out = O.temporal_combine(g, k, mv, 0.3)
+    gt = torch.from_numpy(g)
+    diff = torch.stack([OL._cycle(gt[i], -m, 8) for i, m in enumerate(mv)])
+    kt = torch.from_numpy(k)[None]
+    ref = (1 - 0.3) * torch.matmul(kt, gt.reshape(D, -1)) + 0.3 * torch.matmul(kt, diff.reshape(D, -1))
+    assert np.allclose(out.reshape(-1), ref.numpy().reshape(-1), rtol=2e-6, atol=1e-7)
+
+
+def test_sign_descent_and_ila_pieces_match_autograd():
+    """K3d restated (image_attacks.py:615-617 through the compose block 582-585) and the ILAF layer loss (596-611)
+    against torch autograd of the reference's own expressions."""
+    rng = np.random.default_rng(9)
+    eps, step = 16 / 255, 0.005
+    x = rng.random((1, 3, 4, 6, 6)).astype(np.float32)
+    mod = (rng.standard_normal(x.shape) * 0.08).astype(np.float32)       # some outside +-eps, some sums outside [0,1]
+    g = rng.standard_normal(x.shape).astype(np.float32)
+    g[0, 0, 0, 0, :3] = 0.0
+    inner = 4 * 6 * 6
+    mod2, img2 = O.sign_descent_compose(g, mod, x, eps, step, inner)
+    m_t = torch.from_numpy(mod.copy()).requires_grad_(True)
+    mean = torch.tensor(O.MEAN)[None, :, None, None, None]
+    std = torch.tensor(O.STD)[None, :, None, None, None]
+    ti = (torch.clamp(torch.from_numpy(x) + torch.clamp(m_t, min=-eps, max=eps), min=0, max=1) - mean) / std
+    (gm,) = torch.autograd.grad(ti, m_t, grad_outputs=torch.from_numpy(g))
+    want = m_t.detach() - step * gm.sign()
+    assert np.array_equal(mod2, want.numpy())
+    ti2 = (torch.clamp(torch.from_numpy(x) + torch.clamp(want, min=-eps, max=eps), min=0, max=1) - mean) / std
+    assert np.array_equal(img2, ti2.numpy())
+
+    f = rng.standard_normal(500).astype(np.float32)
+    o = rng.standard_normal(500).astype(np.float32)
+    d0 = rng.standard_normal(500)
+    n0 = float(np.linalg.norm(d0)) * 1.7
+    d0 = (d0 / np.linalg.norm(d0)).astype(np.float32)
+    loss, grad = O.ila_loss_grad_f64(f, o, d0, n0)
+    ft = torch.from_numpy(f).double().requires_grad_(True)
+    sd = ft - torch.from_numpy(o).double()
+    sn = torch.norm(sd, p=2)
+    ref = -(0.5 * sn / n0 + torch.mm(torch.from_numpy(d0).double().view(1, -1), (sd / sn).view(1, -1).transpose(1, 0)))
+    (gr,) = torch.autograd.grad(ref.sum(), ft)
+    assert abs(loss - float(ref)) <= 1e-12 and np.allclose(grad, gr.numpy(), rtol=1e-10, atol=1e-14)
+
+
+def test_video_variant_loops_match_reference(golden):
+    """TemporalTranslation, TAP and ILAF restatements (oracle/loops.py) against the UNMODIFIED reference classes
+    (tests/golden/video_variants.npz, oracle/make_golden.py:run_video_variants)."""
+    g = golden("video_variants")
+    videos, labels = g["videos"], torch.from_numpy(g["labels"])
+    p = next(synth.TinyTPNLike().parameters()).detach().double()
+    if not np.allclose([p.sum().item(), p.abs().sum().item(), float(p.flatten()[0])], g["weight_checksums"][0], rtol=0, atol=0):
+        pytest.skip("random init differs from the fixture's")
+
+    def frac(a, b):
+        return float((np.abs(a - b) < 1e-6).mean())
+
+    m = synth.TinyTPNLike()
+    assert frac(OL.temporal_translation(m, videos, labels, 5, 0.5, steps=3), g["tt3_k5"]) == 1.0
+    assert frac(OL.temporal_translation(m, videos, labels, 5, 0.5, momentum=True, steps=3), g["tt3_k5_mom"]) == 1.0
+    assert frac(OL.temporal_translation(m, videos, labels, 9, 0.3, kernel_mode="linear", steps=2), g["tt2_k9_linear"]) == 1.0
+    for conv3d, tag in ((True, "3d"), (False, "2d")):
+        adv, info = OL.tap(m, [m.layer1, m.layer2], videos, labels, conv3d=conv3d, steps=3)
+        assert frac(adv, g["tap3_" + tag]) == 1.0
+        want = g["tap3_%s_last_losses" % tag]
+        assert np.allclose([info[-1][0], info[-1][1], float(info[-1][2][0])], want, rtol=1e-5)
+    out, clip, costs = OL.ilaf(m, [m.layer2], g["tt3_k5"], videos, steps=4)
+    assert frac(out, g["ilaf4"]) == 1.0
+    assert np.allclose(costs, g["ilaf4_costs"], rtol=1e-6)
+    # 627-629 reinterpret [b,3,f,h,w] as [b,f,3,h,w]: the returned tensor is NOT the clip (a reference defect that is kept)
+    assert not np.array_equal(out, clip) and np.array_equal(np.sort(out.reshape(-1)), np.sort(clip.reshape(-1)))
