@@ -55,6 +55,7 @@ SIGNATURES = {
     "i2v_conv_stem_dgrad_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p], _c_int),
     "i2v_conv_stem_dgrad_tc_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p], _c_int),
     "i2v_conv_stem_dgrad_tc_group": ([_c_p], _c_int),
+    "i2v_conv_stem_dgrad_tc_rows": ([_c_int], _c_int),
     "i2v_conv_stem_fwd_tc_group": ([_c_p], _c_int),
     "i2v_conv_stem_fwd_tc_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_tc_supported": ([_c_p, _c_int], _c_int),
@@ -108,7 +109,7 @@ def load():
 # tensors read + written once, 2 x MACs of the convolution).
 LAUNCHES = {}
 PROFILE_EVENTS = None
-_NO_KERNEL = ("i2v_device_check", "i2v_std_workspace_doubles", "i2v_ila_workspace_doubles", "i2v_adam_step_table", "i2v_conv_tc_supported", "i2v_conv_stem_supported",
+_NO_KERNEL = ("i2v_conv_stem_dgrad_tc_rows", "i2v_device_check", "i2v_std_workspace_doubles", "i2v_ila_workspace_doubles", "i2v_adam_step_table", "i2v_conv_tc_supported", "i2v_conv_stem_supported",
               "i2v_conv_tc_set_trace")
 
 
@@ -416,6 +417,11 @@ def conv_stem_dgrad_tc(desc, dy, wz_hi, wz_lo, z_scratch, dx):
     with _Timed("i2v_conv_stem_dgrad_f32", nb, fl):
         _check(load().i2v_conv_stem_dgrad_tc_f32(ctypes.addressof(desc), _dev(dy), _dev(wz_hi), _dev(wz_lo), _dev(z_scratch),
                                                  _dev(dx), _stream()), "i2v_conv_stem_dgrad_tc_f32")
+
+
+def stem_dgrad_tc_rows(cols):
+    """Rows of the zero-padded [(c,r,s), Cout] weight matrix i2v_conv_stem_dgrad_tc_f32 expects."""
+    return int(load().i2v_conv_stem_dgrad_tc_rows(int(cols)))
 
 
 def stem_dgrad_tc_scratch_floats(desc):

@@ -1172,6 +1172,7 @@ struct TcProblem {
     int out_s, out_h0, out_w0, out_H, out_W;
     const uint32_t* mask_bits; uint32_t* bits_out;
     int out_transposed, store_cols;     // TMA epilogue: dst = [Cout][M]; only columns < store_cols are written (0 = all)
+    int force_dual;                     // take the dual-issuer kernel whatever the tile length (first-layer dgrad GEMM)
 };
 
 static int tc_run(const TcProblem& pr, cudaStream_t st) {
@@ -1243,7 +1244,7 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
             static const int alo_env = getenv("I2V_TC_ALO_TMEM") ? atoi(getenv("I2V_TC_ALO_TMEM")) : 1;
             const int kit = pr.taps_h * pr.taps_w * (pr.C / 32);
             static const int alo_minkit = getenv("I2V_TC_ALO_MINKIT") ? atoi(getenv("I2V_TC_ALO_MINKIT")) : 4;
-            const bool alo = x3 && alo_env != 0 && (BN == 64 || kit >= alo_minkit || alo_env == 2);
+            const bool alo = x3 && alo_env != 0 && (BN == 64 || kit >= alo_minkit || alo_env == 2 || pr.force_dual);
             if (alo) {
                 if (BN == 128) I2V_TC_DISPATCH_P(128, true, true);
                 I2V_TC_DISPATCH_P(64, true, true);
@@ -1328,6 +1329,21 @@ extern "C" int i2v_conv_tc_f32(const i2v_conv_desc* d, int dgrad, const float* s
 // groups small enough to keep the scratch L2-resident (48 MB = 6 frames at 224^2) lose more to the ~15 us fixed cost of
 // every extra launch pair than they save in HBM traffic — 256 frames: 2.10 / 1.81 ms grouped vs 1.49 / 1.30 ms in one
 // pass (dgrad / fwd) — so the default only bounds the scratch allocation (4 GB).
+// Rows (c,r,s) of the first-layer dgrad weight matrix are zero-padded to a multiple of 64 (BN = 64 tiles) or, with
+// $I2V_STEM_NZ=128, of 128: BN = 128 tiles need a third fewer MMA instructions per pixel tile (the cost of an instruction
+// does not depend on its N) at the price of a single accumulator stage.  Measured (256 frames of ResNet's stem): 1.71 ms
+// with 128 against 1.37 ms with 64 — the two-k-step tiles of this GEMM need the main-loop / epilogue overlap more than they
+// need fewer instructions, so 64 stays the default.
+static int stem_nz_multiple() {
+    static const int m = getenv("I2V_STEM_NZ") ? atoi(getenv("I2V_STEM_NZ")) : 64;
+    return m == 128 ? 128 : 64;
+}
+
+extern "C" int i2v_conv_stem_dgrad_tc_rows(int cols) {
+    const int m = stem_nz_multiple();
+    return (cols + m - 1) / m * m;
+}
+
 static int64_t stem_group_bytes() {
     static const int64_t mb = getenv("I2V_STEM_GROUP_MB") ? atoll(getenv("I2V_STEM_GROUP_MB")) : 4096;
     return (mb > 0 ? mb : 4096) << 20;
@@ -1349,7 +1365,7 @@ extern "C" int i2v_conv_stem_dgrad_tc_f32(const i2v_conv_desc* d, const float* d
     I2V_REQUIRE(d->Cin == 3 && d->R == d->S && d->Cout % 32 == 0 && d->stride >= 1 && d->pad < d->R, "not a first-layer shape");
     if (d->N == 0) return I2V_OK;
     const int cols = 3 * d->R * d->S;
-    const int NZ = (cols + 63) / 64 * 64;
+    const int NZ = i2v_conv_stem_dgrad_tc_rows(cols);
     // frames in groups that bound the scratch (see stem_group_bytes)
     const int G = i2v_conv_stem_dgrad_tc_group(d);
     for (int n0 = 0; n0 < d->N; n0 += G) {
@@ -1361,6 +1377,7 @@ extern "C" int i2v_conv_stem_dgrad_tc_f32(const i2v_conv_desc* d, const float* d
         pr.taps_h = pr.taps_w = 1;
         pr.w_hi = wz_hi; pr.w_lo = wz_lo; pr.Cout = NZ; pr.dst = z_scratch;
         pr.out_transposed = 1; pr.store_cols = (cols + 31) / 32 * 32;
+        pr.force_dual = NZ % 128 == 0;
         if (int r = tc_run(pr, as_stream(stream))) return r;
         if (int r = stem_col2im_launch(z_scratch, dx + (int64_t)n0 * 3 * d->H * d->W, n, d->H, d->W, d->P, d->Q, d->R, d->stride,
                                        d->pad, as_stream(stream))) return r;

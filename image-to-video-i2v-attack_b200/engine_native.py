@@ -71,7 +71,7 @@ class _Conv:
         # first-layer data gradient on the tensor cores: rows (c,r,s) zero-padded to a multiple of 64, TF32 hi/lo split
         self.tc_stem_dgrad = None
         if x_nchw and cin == 3 and cout % 32 == 0:
-            nz = (cin * R * S + 63) // 64 * 64
+            nz = capi.stem_dgrad_tc_rows(cin * R * S)
             wz = torch.cat([self.w_stem, self.w_stem.new_zeros(nz - cin * R * S, cout)], 0).contiguous()
             self.tc_stem_dgrad = _split_tf32(wz)
         # first-layer forward as im2col + GEMM: [Cout, Kp] K-major, k = (c,r,s) zero-padded to a multiple of 32

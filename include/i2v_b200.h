@@ -271,6 +271,9 @@ int i2v_conv_tc_bits_f32(const i2v_conv_desc* d, int dgrad, const float* src, co
  * z_scratch, then a col2im gather produces dx [N,3,H,W].
  * wz_hi / wz_lo = [NZ, Cout] K-major: rows (c,r,s) of weight[co,c,r,s]*bn_scale[co], zero-padded to
  * NZ = ceil(3*R*S/64)*64, split into TF32 hi / lo (wz_lo = NULL: plain TF32).  N*P*Q % 4 == 0.            */
+/* rows of wz_* the first-layer dgrad GEMM expects for `cols` = 3*R*S filter columns (zero-padded to a multiple of 64,
+ * or of 128 with $I2V_STEM_NZ=128) */
+int i2v_conv_stem_dgrad_tc_rows(int cols);
 int i2v_conv_stem_dgrad_tc_f32(const i2v_conv_desc* d, const float* dy, const float* wz_hi, const float* wz_lo,
                                float* z_scratch, float* dx, i2v_stream_t stream);
 /* Frames are processed in groups of i2v_conv_stem_dgrad_tc_group(d) (bounds the scratch; $I2V_STEM_GROUP_MB):

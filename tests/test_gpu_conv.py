@@ -424,7 +424,7 @@ def test_stem_dgrad_tc(H, W, k, s, p, n, x3):
     dy = torch.randn(n, Cout, P, Q, generator=g)
     d = capi.ConvDesc(n, H, W, 3, Cout, k, k, s, p, P, Q)
     rows = 3 * k * k
-    nz = (rows + 63) // 64 * 64
+    nz = capi.stem_dgrad_tc_rows(rows)
     wz = torch.cat([w.permute(1, 2, 3, 0).reshape(rows, Cout), torch.zeros(nz - rows, Cout)], 0).contiguous().to(DEV)
     hi, lo, rna = _split_tf32(wz)
     z = torch.full((capi.stem_dgrad_tc_scratch_floats(d),), float("nan"), device=DEV)
