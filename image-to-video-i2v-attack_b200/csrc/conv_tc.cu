@@ -441,6 +441,12 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // So the two MMAs of a k-slice go to two issuers with DISJOINT accumulators: warp 1 issues a_hi x [b_hi | b_lo]
     // (main | cross), warp 2 issues a_lo x b_hi with A_lo read from tensor memory into a third accumulator (cross2);
     // the epilogue adds the three.  TMEM: kAcc stages of [main | cross | cross2] in 384 columns + a 4-slot A_lo ring.
+    // (Tried and measured NOT to help: a THIRD issuing warp for the K-heavy BN = 64 layers — k-slices 0..2 on warps 1 / 2,
+    // both instructions of k-slice 3 on a 17th warp into its own accumulators, three instructions per issuer and k-step
+    // instead of four.  3x3 64->64 at 256 frames: 474 us against 454 us with two issuers in the same run.  So once two
+    // threads issue, these layers are no longer bound by the issue rate; what remains is operand delivery — every SM
+    // pulls the same 16 KB weight block and a 16 KB im2col tile per k-step through L2, 8 TB/s in aggregate — which is
+    // what TMA multicast across a CTA pair / cta_group::2 would halve.)
     constexpr uint32_t kAccCols = X3 ? (ALO_TMEM ? 3 * BN : 2 * BN) : BN;   // TMEM columns per accumulator stage
     constexpr int kAcc = ALO_TMEM ? (int)(384 / kAccCols) : ((512 / kAccCols) > 4 ? 4 : (512 / kAccCols));
     constexpr uint32_t kAloBase = 384, kAloSlots = 4;
