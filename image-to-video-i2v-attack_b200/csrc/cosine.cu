@@ -65,6 +65,11 @@ cosine_loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b
     const bool hints = hint_mode != 0;
     // Persistent clusters: the grid holds as many clusters as are co-resident and each walks over frames
     // with that stride, so no SM slot idles waiting for 16 free slots in one GPC between frames.
+    // Split cluster barrier: after the coefficients are published CTA-wide the threads only ARRIVE at the cluster barrier
+    // (their remote reads of the other CTAs' partials are done) and go straight into the gradient pass; the matching
+    // WAIT comes right before this CTA overwrites its partial for the next frame (or exits).  One cluster-wide barrier
+    // latency per frame leaves the critical path.
+    bool pending = false;
     for (int64_t frame = blockIdx.x / S; frame < N; frame += gridDim.x / S) {
     const float* af = a + frame * D;
     const float* bf = b + frame * D;
@@ -133,6 +138,7 @@ cosine_loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b
     dot = warp_sum(dot); aa = warp_sum(aa); bb = warp_sum(bb);
     if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = CosPartial{dot, aa, bb};
     __syncthreads();
+    if (pending) { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); pending = false; }
     if (threadIdx.x < 32) {
         CosPartial s{0.0, 0.0, 0.0};
         if (threadIdx.x < kCosThreads / 32) s = warp_part[threadIdx.x];
@@ -160,7 +166,9 @@ cosine_loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b
             if (rank == 0 && cos_out) cos_out[frame] = (float)cosv;
         }
     }
-    cluster.sync();   // remote reads done before cta_part is reused / the CTA exits; publishes coef
+    __syncthreads();  // publishes coef; warp 0's remote reads precede its arrival below
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    pending = true;
     if (grad == nullptr) continue;
 
     const CosCoef c = coef;
@@ -198,6 +206,7 @@ cosine_loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b
         }
     }
     }   // frames
+    if (pending) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // nobody reads an exited CTA's partial
 }
 
 // K2: one warp.  coeffs <- softmax(softmax(prev) + momentum*coeffs)   (TPAMI_attack.py:265)
@@ -272,9 +281,11 @@ static int pick_cluster(int64_t N, int64_t units) {
         int v = atoi(e);
         if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) return v;
     }
-    // As many CTAs per frame as possible (more of the frame on-chip, fewer frames in flight so the
-    // un-stashed tails stay in L2), while every CTA keeps >= 16K elements to stream.
-    int S = 16;
+    // 8 CTAs per frame while every CTA keeps >= 16K elements to stream.  Measured with the L2 hints (256 frames of
+    // ResNet layer2, timed alone): 289 us at 8, 311 us at 16, 337 us at 4 — 16 keeps more of a frame on-chip but pays a
+    // cluster-wide reduction per 200 KB streamed and fits the GPCs worse; the evict_last tails of 37 frames in flight
+    // (85 MB) still sit in the 126 MB L2.
+    int S = 8;
     while (S > 1 && units / S < 4096) S >>= 1;
     (void)N;
     return S;
