@@ -459,7 +459,8 @@ class TAP(Attack):
     (the reference hard-codes 1e3 and 0.05, 799, and ignores `eta`).
 
     The CE and feature-distance terms go through the opaque white-box model with torch autograd (so the reference's
-    behaviour at exactly-zero features — a NaN derivative of sign*sqrt|.| — is inherited, not re-defined); the box-filter
+    behaviour at exactly-zero features — a NaN derivative of sign*sqrt|.| — is inherited, not re-defined; K3b then treats a
+    NaN gradient entry as sign 0 and leaves that pixel where it is, where torch.sign would turn it into NaN); the box-filter
     regulariser and its gradient are two passes of the K7 stencil (uniform kernels are symmetric, so the transposed
     convolution is the same stencil over sign(out)); the update is K3b.  `loss_info` is keyed by the step index (the
     reference's key `i` is shadowed by the feature loop, 790, and ends up being a tensor)."""
