@@ -434,7 +434,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                        const __grid_constant__ CUtensorMap tmRes, const TcArgs args, const int stages,
                        const int num_m_tiles, const int num_n_tiles, const int epi_slots) {
     using L = TcSmem<BN, X3>;
-    static_assert(!ALO_TMEM || (X3 && EPI_TMA), "A_lo in tensor memory is a 3xTF32 / TMA-epilogue variant");
+    static_assert(!ALO_TMEM || X3, "A_lo in tensor memory is a 3xTF32 variant");
     // ALO_TMEM = the DUAL-ISSUER variant.  Measured (tools/mma_probe.py, profiles/r01_mma_issue_probe.txt): ONE thread
     // issues a tcgen05.mma every ~200 cycles whatever its width (N = 64..256, floor N/2 cycles), while several issuing
     // warps proceed concurrently at that same rate each — the 3xTF32 main loop (8 MMAs per k-step) was issue-bound.
@@ -619,7 +619,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 umma_commit(&tfull_bar[acc]);
             }
         }
-    } else if (ALO_TMEM && warp == 3) {
+    } else if (ALO_TMEM && EPI_TMA && warp == 3) {
         // ===== epilogue TMA issuer of BOTH groups (warp 2 issues MMAs here): polls the groups' out_ready barriers ====
         if (lane == 0) {
             constexpr uint32_t SUBS = BN / 64;
@@ -942,7 +942,19 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     uint32_t b0[8], b1[8];
                     tmem_ld_16x256b_x2(tacc + (uint32_t)(BN + c0), b0);
                     tmem_ld_16x256b_x2(tacc + (16u << 16) + (uint32_t)(BN + c0), b1);
-                    tmem_ld_wait();
+                    if (ALO_TMEM) {                              // dual issuer: cross + cross2 first, then + main
+                        uint32_t e0[8], e1[8];
+                        tmem_ld_16x256b_x2(tacc + (uint32_t)(2 * BN + c0), e0);
+                        tmem_ld_16x256b_x2(tacc + (16u << 16) + (uint32_t)(2 * BN + c0), e1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            b0[k] = __float_as_uint(__fadd_rn(__uint_as_float(b0[k]), __uint_as_float(e0[k])));
+                            b1[k] = __float_as_uint(__fadd_rn(__uint_as_float(b1[k]), __uint_as_float(e1[k])));
+                        }
+                    } else {
+                        tmem_ld_wait();
+                    }
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         a0[k] = __float_as_uint(__fadd_rn(__uint_as_float(a0[k]), __uint_as_float(b0[k])));
@@ -950,6 +962,10 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     }
                 } else {
                     tmem_ld_wait();
+                }
+                if (uu == UNITS - 1) {                           // last TMEM read of the tile: hand the stage back before the
+                    tc_fence_before();                           // (slow) global stores — the dual-issuer kernel has ONE stage
+                    mbar_arrive(&tempty_bar[acc]);               // at BN = 128 and its MMA warps wait for exactly this
                 }
                 const float* bs = bias_s + n0 + c0 + lc;
 #pragma unroll
@@ -967,9 +983,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                         if (valid[ih]) *reinterpret_cast<float2*>(args.dst + off[ih] + c0 + 8 * j) = v;
                     }
             }
-            tc_fence_before();                                   // TMEM reads done before the MMA warp may overwrite
             if (threadIdx.x == 256) TC_TRACE(6, t);
-            mbar_arrive(&tempty_bar[acc]);
         }
     }
 
@@ -1257,6 +1271,19 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
             }
             if (BN == 128) I2V_TC_DISPATCH_P(128, true, false);
             I2V_TC_DISPATCH_P(64, true, false);
+        }
+        // register epilogue (strided data-gradient classes, f32 mask sources): dual issuers are available behind
+        // $I2V_TC_ALO_REGEPI=1 but OFF by default — measured on the stride-2 classes of ResNet's layer2.0 (256 frames):
+        // 234 us per launch with them against 171 us without; the per-thread global stores of this epilogue are slow
+        // enough that the single accumulator stage of the BN = 128 dual-issuer layout costs more than the issue rate gains
+        {
+            static const int alo_env2 = getenv("I2V_TC_ALO_REGEPI") ? atoi(getenv("I2V_TC_ALO_REGEPI")) : 0;
+            static const int alo_minkit2 = getenv("I2V_TC_ALO_MINKIT") ? atoi(getenv("I2V_TC_ALO_MINKIT")) : 4;
+            const int kit2 = pr.taps_h * pr.taps_w * (pr.C / 32);
+            if (x3 && alo_env2 != 0 && (BN == 64 || kit2 >= alo_minkit2)) {
+                if (BN == 128) I2V_TC_DISPATCH_P(128, false, true);
+                I2V_TC_DISPATCH_P(64, false, true);
+            }
         }
         if (BN == 128) I2V_TC_DISPATCH_P(128, false, false);
         I2V_TC_DISPATCH_P(64, false, false);
