@@ -296,11 +296,13 @@ maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* 
 // (mask_pooled = 0), or the POOLED output y (mask_pooled = 1) — the winner of a window IS y, so 1[x[argmax] > 0] =
 // 1[y > 0], and y is k*k/stride^2 times smaller than x.  With argmax written by the forward pass's mark_dead mode no mask
 // is needed (dead windows have no winner).  One CTA per (image, input row); the sum runs over windows in (p, q) order.
-template <int KT, int ST>
+// MASK: 0 = none (the forward pass marked dead windows), 1 = f32 activation of the pooled tensor's producer, 2 = pooled
+// output — a template parameter so that the hot (mask-free) instantiation carries none of the mask code.
+template <int KT, int ST, int MASK>
 __global__ void __launch_bounds__(kPoolThreads)
 maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ argmax, const float* __restrict__ mask_src,
                    float* __restrict__ dx, int H, int W, int C4, unsigned c4_magic, int P, int Q, int k_rt, int stride_rt, int pad,
-                   int accumulate, int mask_pooled) {
+                   int accumulate) {
     const int k = KT > 0 ? KT : k_rt, stride = KT > 0 ? ST : stride_rt;
     constexpr int NW = KT > 0 ? (KT + ST - 1) / ST : 1;         // windows per axis that can contain a pixel
     const int row = blockIdx.x;                      // img * H + h
@@ -310,8 +312,8 @@ maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ arg
     int p_hi = (h + pad) / stride; if (p_hi > P - 1) p_hi = P - 1;
     const float4* __restrict__ dy4 = reinterpret_cast<const float4*>(dy) + (int64_t)img * P * Q * C4;
     const uchar4* __restrict__ am4 = reinterpret_cast<const uchar4*>(argmax) + (int64_t)img * P * Q * C4;
-    const float4* __restrict__ yk4 = mask_pooled ? reinterpret_cast<const float4*>(mask_src) + (int64_t)img * P * Q * C4 : nullptr;
-    const float4* __restrict__ mk4 = (mask_src && !mask_pooled) ? reinterpret_cast<const float4*>(mask_src) + (int64_t)row * W * C4 : nullptr;
+    const float4* __restrict__ yk4 = MASK == 2 ? reinterpret_cast<const float4*>(mask_src) + (int64_t)img * P * Q * C4 : nullptr;
+    const float4* __restrict__ mk4 = MASK == 1 ? reinterpret_cast<const float4*>(mask_src) + (int64_t)row * W * C4 : nullptr;
     float4* __restrict__ dx4 = reinterpret_cast<float4*>(dx) + (int64_t)row * W * C4;
     const int items = W * C4;
     for (int idx = threadIdx.x; idx < items; idx += kPoolThreads) {
@@ -331,7 +333,7 @@ maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ arg
                     const int o = (pp * Q + q) * C4 + c4;
                     a[i * NW + j] = ok ? __ldg(am4 + o) : make_uchar4(kPoolNoWinner, kPoolNoWinner, kPoolNoWinner, kPoolNoWinner);
                     d[i * NW + j] = ok ? __ldg(dy4 + o) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (yk4 && ok) {
+                    if (MASK == 2 && ok) {
                         const float4 yv = __ldg(yk4 + o);
                         float4& dd = d[i * NW + j];
                         if (!(yv.x > 0.f)) dd.x = 0.f; if (!(yv.y > 0.f)) dd.y = 0.f; if (!(yv.z > 0.f)) dd.z = 0.f; if (!(yv.w > 0.f)) dd.w = 0.f;
@@ -358,7 +360,7 @@ maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ arg
                     const int o = (pp * Q + q) * C4 + c4;
                     const uchar4 a = __ldg(am4 + o);
                     float4 d = __ldg(dy4 + o);
-                    if (yk4) {
+                    if (MASK == 2) {
                         const float4 yv = __ldg(yk4 + o);
                         if (!(yv.x > 0.f)) d.x = 0.f; if (!(yv.y > 0.f)) d.y = 0.f; if (!(yv.z > 0.f)) d.z = 0.f; if (!(yv.w > 0.f)) d.w = 0.f;
                     }
@@ -369,7 +371,7 @@ maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ arg
                 }
             }
         }
-        if (mk4) {
+        if (MASK == 1) {
             const float4 mk = __ldg(mk4 + idx);
             if (!(mk.x > 0.f)) g[0] = 0.f; if (!(mk.y > 0.f)) g[1] = 0.f; if (!(mk.z > 0.f)) g[2] = 0.f; if (!(mk.w > 0.f)) g[3] = 0.f;
         }
@@ -491,12 +493,17 @@ extern "C" int i2v_maxpool_bwd_f32(const float* dy, const uint8_t* argmax, const
     const int C4 = C / 4, acc = flags & 1, mp = (flags >> 1) & 1;
     const unsigned magic = C4 == 1 ? 0u : (unsigned)((0x100000000ULL + C4 - 1) / C4);
     const unsigned grid = (unsigned)(N * H);
-    if (k == 3 && stride == 2)
-        maxpool_bwd_kernel<3, 2><<<grid, kPoolThreads, 0, as_stream(stream)>>>(dy, argmax, mask_src, dx, H, W, C4, magic, P, Q, k, stride, pad, acc, mp);
-    else if (k == 2 && stride == 2)
-        maxpool_bwd_kernel<2, 2><<<grid, kPoolThreads, 0, as_stream(stream)>>>(dy, argmax, mask_src, dx, H, W, C4, magic, P, Q, k, stride, pad, acc, mp);
-    else
-        maxpool_bwd_kernel<0, 0><<<grid, kPoolThreads, 0, as_stream(stream)>>>(dy, argmax, mask_src, dx, H, W, C4, magic, P, Q, k, stride, pad, acc, mp);
+    const int mode = mask_src ? (mp ? 2 : 1) : 0;
+#define I2V_POOL_BWD(KT_, ST_)                                                                                                  \
+    do {                                                                                                                        \
+        if (mode == 0) maxpool_bwd_kernel<KT_, ST_, 0><<<grid, kPoolThreads, 0, as_stream(stream)>>>(dy, argmax, mask_src, dx, H, W, C4, magic, P, Q, k, stride, pad, acc);       \
+        else if (mode == 1) maxpool_bwd_kernel<KT_, ST_, 1><<<grid, kPoolThreads, 0, as_stream(stream)>>>(dy, argmax, mask_src, dx, H, W, C4, magic, P, Q, k, stride, pad, acc);  \
+        else maxpool_bwd_kernel<KT_, ST_, 2><<<grid, kPoolThreads, 0, as_stream(stream)>>>(dy, argmax, mask_src, dx, H, W, C4, magic, P, Q, k, stride, pad, acc);                 \
+    } while (0)
+    if (k == 3 && stride == 2) I2V_POOL_BWD(3, 2);
+    else if (k == 2 && stride == 2) I2V_POOL_BWD(2, 2);
+    else I2V_POOL_BWD(0, 0);
+#undef I2V_POOL_BWD
     I2V_LAUNCH_CHECK("i2v_maxpool_bwd_f32");
     return I2V_OK;
 }

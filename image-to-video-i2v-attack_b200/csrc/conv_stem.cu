@@ -225,24 +225,28 @@ stem_col2im_kernel(const float* __restrict__ zt, float* __restrict__ dx, int N, 
     if (w >= W) return;
     const int RR = R * R;
     const int r0 = (h + pad) % st, s0 = (cls + pad) % st;       // (w + pad) % st == (cls + pad) % st
-    const float* __restrict__ zn = zt + (int64_t)n * P * Q;
+    // tap (a, b): r = r0 + a*st, s = s0 + b*st, p = p0 - a, q = q0 - b  =>  the plane address is AFFINE in (a, b):
+    // z(a, b) = z00 + a*(st*R*M - Q) + b*(st*M - 1)  (two 64-bit adds per tap instead of a multiply chain)
+    const int p0 = (h + pad - r0) / st, q0 = (w + pad - s0) / st;         // h + pad - r0 and w + pad - s0 are multiples of st
+    const float* __restrict__ z00 = zt + (int64_t)n * P * Q + (int64_t)(r0 * R + s0) * M + (int64_t)p0 * Q + q0;
+    const int64_t step_a = (int64_t)st * R * M - Q, step_b = (int64_t)st * M - 1;
+    const int64_t plane1 = (int64_t)RR * M, plane2 = 2 * plane1;
     float v[3][TAPS * TAPS];
 #pragma unroll
     for (int a = 0; a < TAPS; ++a) {
         const int r = r0 + a * st;
-        const int hp = h + pad - r;
-        const int p = hp / st;
-        const bool okr = r < R && hp >= 0 && p < P;
+        const int p = p0 - a;
+        const bool okr = r < R && p >= 0 && p < P;
+        const float* za = z00 + a * step_a;
 #pragma unroll
         for (int b = 0; b < TAPS; ++b) {
             const int s = s0 + b * st;
-            const int wq = w + pad - s;
-            const int q = wq / st;
-            const bool ok = okr && s < R && wq >= 0 && q < Q;
-            const float* z = zn + (int64_t)(r * R + s) * M + (int64_t)p * Q + q;
+            const int q = q0 - b;
+            const bool ok = okr && s < R && q >= 0 && q < Q;
+            const float* z = za + b * step_b;
             v[0][a * TAPS + b] = ok ? __ldg(z) : 0.f;
-            v[1][a * TAPS + b] = ok ? __ldg(z + (int64_t)RR * M) : 0.f;
-            v[2][a * TAPS + b] = ok ? __ldg(z + (int64_t)2 * RR * M) : 0.f;
+            v[1][a * TAPS + b] = ok ? __ldg(z + plane1) : 0.f;
+            v[2][a * TAPS + b] = ok ? __ldg(z + plane2) : 0.f;
         }
     }
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
