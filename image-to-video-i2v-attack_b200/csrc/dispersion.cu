@@ -64,12 +64,19 @@ std_partial_kernel(const float* __restrict__ a, int64_t n, double* __restrict__ 
     }
 }
 
+// One WARP: lane l adds partials l, l + 32, ... in order, then a fixed-shape butterfly — still one fixed summation order
+// for a given block count.  (The first version walked all ~1200 partials with ONE thread: a chain of dependent-latency
+// global loads that took ~80 us, five times the HBM pass it follows.)
 __global__ void std_combine_kernel(const double* __restrict__ partials, int blocks, double* __restrict__ acc) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double t1 = acc[0], t2 = acc[1];
-    for (int b = 0; b < blocks; ++b) { t1 += partials[2 * b]; t2 += partials[2 * b + 1]; }
-    acc[0] = t1;
-    acc[1] = t2;
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    double t1 = 0.0, t2 = 0.0;
+    for (int b = threadIdx.x; b < blocks; b += 32) { t1 += partials[2 * b]; t2 += partials[2 * b + 1]; }
+    t1 = warp_sum(t1);
+    t2 = warp_sum(t2);
+    if (threadIdx.x == 0) {
+        acc[0] += t1;
+        acc[1] += t2;
+    }
 }
 
 __global__ void std_finalize_kernel(const double* __restrict__ acc, int64_t n, float* __restrict__ stats,

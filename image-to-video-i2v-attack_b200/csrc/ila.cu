@@ -60,12 +60,15 @@ ila_partial_kernel(const float* __restrict__ f, const float* __restrict__ o, con
     }
 }
 
-// one thread: partials in block order -> (sum delta^2, sum d0*delta) -> loss and the two gradient coefficients
+// one warp: partials in a fixed order -> (sum delta^2, sum d0*delta) -> loss and the two gradient coefficients
 __global__ void ila_finalize_kernel(const double* __restrict__ partials, int blocks, float init_norm, float* __restrict__ stats,
                                     float* __restrict__ cost_log, const int* __restrict__ step_idx, int add_to_cost) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double t1 = 0.0, t2 = 0.0;
-    for (int b = 0; b < blocks; ++b) { t1 += partials[2 * b]; t2 += partials[2 * b + 1]; }
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    double t1 = 0.0, t2 = 0.0;                                   // lane l: partials l, l + 32, ... in order, then a butterfly
+    for (int b = threadIdx.x; b < blocks; b += 32) { t1 += partials[2 * b]; t2 += partials[2 * b + 1]; }
+    t1 = warp_sum(t1);
+    t2 = warp_sum(t2);
+    if (threadIdx.x != 0) return;
     const double n = sqrt(t1), n0 = (double)init_norm;
     const double loss = -(0.5 * n / n0 + t2 / n);
     stats[0] = (float)(-(0.5 / (n0 * n) - t2 / (n * n * n)));

@@ -113,6 +113,57 @@ def main():
     # a small-N case: one clip (config 1), 32 frames
     a32, b32, g32 = a[:32], b[:32], grad[:32]
     report("i2v_cosine_loss_grad_f32", 12 * 32 * D, lambda: capi.cosine_loss_grad(a32, b32, g32, cos[:32]), {"frames": 32})
+    del a, b, grad, a32, b32, g32
+    torch.cuda.empty_cache()
+
+    # K3d (ILAF update), K8 (TemporalTranslation, 7 variants), K9 (ILAF layer loss), K6 (DR), max pooling of ResNet's stem
+    clips = max(1, N // 32)
+    shp = (clips, 3, 32, 224, 224)
+    n5 = clips * 3 * 32 * 224 * 224
+    inner5 = 32 * 224 * 224
+    g = torch.randn(shp, device=dev)
+    x = torch.rand(shp, device=dev)
+    mod = torch.zeros(shp, device=dev)
+    out = torch.empty(shp, device=dev)
+    report("i2v_sign_descent_compose_f32", 20 * n5, lambda: capi.sign_descent_compose(g, mod, x, out, 16 / 255, 0.005, inner5))
+    D7 = 7
+    tclips = max(1, min(clips, 4))
+    tshape = (tclips, 3, 32, 224, 224)
+    tn = tclips * 3 * 32 * 224 * 224
+    stack = torch.empty((D7,) + tshape, device=dev)
+    adv = torch.randn(tshape, device=dev)
+    moves = [-3, -2, -1, 0, 1, 2, 3]
+    report("i2v_temporal_shift_stack_f32", 4 * tn * (1 + D7), lambda: capi.temporal_shift_stack(adv, stack, moves), {"clips": tclips})
+    kern = [1.0 / D7] * D7
+    tout = torch.empty(tshape, device=dev)
+    report("i2v_temporal_combine_f32", 4 * tn * (1 + D7), lambda: capi.temporal_combine(stack, kern, moves, 0.5, tout), {"clips": tclips})
+    del stack, adv, tout, g, x, mod, out
+    torch.cuda.empty_cache()
+    nf = N * 512 * 28 * 28 // 4
+    f = torch.randn(nf, device=dev)
+    o = torch.randn(nf, device=dev)
+    d0 = torch.randn(nf, device=dev)
+    d0 /= d0.norm()
+    ws = capi.ila_workspace(dev)
+    stats = torch.zeros(4, device=dev)
+    gr = torch.empty(nf, device=dev)
+    report("i2v_ila_loss_f32", 12 * nf, lambda: capi.ila_loss(f, o, d0, 1.0, ws, stats))
+    report("i2v_ila_grad_f32", 16 * nf, lambda: capi.ila_grad(f, o, d0, gr, stats))
+    acc = torch.zeros(2, device=dev, dtype=torch.float64)
+    sw = capi.std_workspace(dev)
+    report("i2v_std_accumulate_f32", 4 * nf, lambda: capi.std_accumulate(f, sw, acc))
+    del f, o, d0, gr
+    torch.cuda.empty_cache()
+    pf = min(N, 256)
+    xs = torch.relu(torch.randn(pf, 112, 112, 64, device=dev))
+    ys = torch.empty(pf, 56, 56, 64, device=dev)
+    am = torch.empty(pf, 56, 56, 64, device=dev, dtype=torch.uint8)
+    report("i2v_maxpool_fwd_f32 (3,2,1) mark_dead", 4 * xs.numel() + 5 * ys.numel(), lambda: capi.maxpool_fwd(xs, ys, am, 3, 2, 1, mark_dead=True),
+           {"frames": pf})
+    dys = torch.randn_like(ys)
+    dxs = torch.empty_like(xs)
+    report("i2v_maxpool_bwd_f32 (3,2,1) no mask", 5 * ys.numel() + 4 * xs.numel(), lambda: capi.maxpool_bwd(dys, am, None, dxs, 3, 2, 1),
+           {"frames": pf})
     if args.out:
         with open(args.out, "w") as f:
             json.dump(results, f, indent=1)
