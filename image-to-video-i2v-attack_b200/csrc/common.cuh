@@ -31,6 +31,7 @@ inline cudaStream_t as_stream(i2v_stream_t s) { return reinterpret_cast<cudaStre
 int stem_im2col_launch(const float* x, float* col, int n0, int n, int H, int W, int P, int Q, int R, int stride, int pad, int Kp,
                        cudaStream_t st);
 int stem_col2im_launch(const float* zt, float* dx, int N, int H, int W, int P, int Q, int R, int stride, int pad, cudaStream_t st);
+int stem_pack_nhwc4_launch(const float* x, float* xp, int N, int H, int W, int Hp, int Wp, int pad, cudaStream_t st);
 
 // 148 SMs on B200; queried once (falls back to 148 if the query fails before a device exists).
 int sm_count();

@@ -326,6 +326,31 @@ int stem_im2col_launch(const float* x, float* col, int n0, int n, int H, int W, 
     return I2V_OK;
 }
 
+// x [N,3,H,W] -> xp [N,Hp,Wp,4]: zero border of `pad` pixels (more on the right if Wp asks for it), channel 3 = 0.
+// One thread per padded pixel: three coalesced plane reads, one 16-byte store.
+__global__ void __launch_bounds__(256)
+stem_pack_nhwc4_kernel(const float* __restrict__ x, float4* __restrict__ xp, int H, int W, int Hp, int Wp, int pad) {
+    const int row = blockIdx.x;                       // n * Hp + hp
+    const int n = row / Hp, hp = row - n * Hp;
+    const int h = hp - pad;
+    const bool row_ok = h >= 0 && h < H;
+    const float* __restrict__ src = x + ((int64_t)n * 3 * H + (row_ok ? h : 0)) * W;
+    const int64_t plane = (int64_t)H * W;
+    for (int wp = threadIdx.x; wp < Wp; wp += 256) {
+        const int w = wp - pad;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row_ok && w >= 0 && w < W) { v.x = __ldg(src + w); v.y = __ldg(src + plane + w); v.z = __ldg(src + 2 * plane + w); }
+        xp[(int64_t)row * Wp + wp] = v;
+    }
+}
+
+int stem_pack_nhwc4_launch(const float* x, float* xp, int N, int H, int W, int Hp, int Wp, int pad, cudaStream_t st) {
+    I2V_REQUIRE((reinterpret_cast<uintptr_t>(xp) & 15) == 0, "padded image scratch must be 16-byte aligned");
+    stem_pack_nhwc4_kernel<<<(unsigned)(N * Hp), 256, 0, st>>>(x, reinterpret_cast<float4*>(xp), H, W, Hp, Wp, pad);
+    I2V_LAUNCH_CHECK("i2v_conv_stem_fwd_direct_f32 (pack)");
+    return I2V_OK;
+}
+
 int stem_col2im_launch(const float* zt, float* dx, int N, int H, int W, int P, int Q, int R, int stride, int pad, cudaStream_t st) {
     I2V_REQUIRE(stride == 1 || stride == 2 || stride == 4 || stride == 8, "col2im: stride must divide 8");
     const int per_block = (8 / stride) * 32 * stride;              // image columns per block

@@ -51,6 +51,8 @@ struct TcArgs {
     uint32_t* bits_out;          // [Cout/32][M] activity bits of dst written by the epilogue, or null           (TMA epilogue)
     int out_transposed;          // TMA epilogue: dst is [Cout][M] (column planes) instead of [M][Cout]; no residual / bits
     int store_cols;              // TMA epilogue: 32-column sub-tiles starting at or beyond this column are not stored
+    int stem4d;                  // direct first-layer forward: A tiles are 16 x 8 pixel boxes of a padded NHWC4 image (see
+    int stem_tq, stem_tp;        // i2v_conv_stem_fwd_direct_f32); tiles per image row / column
     int prefetch_tiles;          // L2 prefetch distance in tiles of this CTA (A of 1x1 convolutions, residual sub-tiles); 0 = off
     int64_t M;               // N*P*Q GEMM rows
     int Cout;
@@ -118,6 +120,14 @@ __device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap* map, uint6
                  " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
                  :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
                  : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 :: "l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -544,6 +554,14 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                             // rows per k-step — made every layer 5-15 % SLOWER: the four split warps are the tighter resource)
                             mbar_arrive_expect_tx(&full_bar[st], TC_A_BYTES + L::B_BYTES * (X3 ? 2 : 1));
                             if (IM2COL) tma_load_im2col_4d(&tmA, &full_bar[st], stage_a(st), cb * TC_BK, base_w, base_h, img, (uint16_t)s, (uint16_t)r);
+                            else if (args.stem4d) {
+                                // filter row r of a 16 x 8 pixel box: 32 floats (8 padded pixels x 4) per output pixel, rows of
+                                // parity r % 2 (tmA even / tmRes odd: the residual map is free, a first layer has none)
+                                const int per = args.stem_tq * args.stem_tp;
+                                const int im = m_tile / per, rem = m_tile - im * per;
+                                const int pt = rem / args.stem_tq, qt = rem - pt * args.stem_tq;
+                                tma_load_4d((r & 1) ? &tmRes : &tmA, &full_bar[st], stage_a(st), 0, qt * 16, pt * 8 + (r >> 1), im);
+                            }
                             else        tma_load_2d(&tmA, &full_bar[st], stage_a(st), cb * TC_BK, (int)m0);
                             const int kcol = ((r * args.taps_w + s) * args.cblocks + cb) * TC_BK;
                             tma_load_2d(&tmBhi, &full_bar[st], stage_bhi(st), kcol, n0);
@@ -659,8 +677,14 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     coords(g, k, col, row);
                     const uint8_t* slot = staging + ((size_t)g * ns + s) * EPI_SLOT_BYTES;
                     if (col < args.store_cols) {
-                        if (args.out_transposed) tma_store_2d(&tmOut, slot, row, col);
-                        else                     tma_store_2d(&tmOut, slot, col, row);
+                        if (args.stem4d) {
+                            const int m_tile = row / TC_BM, per = args.stem_tq * args.stem_tp;
+                            const int im = m_tile / per, rem = m_tile - im * per;
+                            const int pt = rem / args.stem_tq, qt = rem - pt * args.stem_tq;
+                            tma_store_4d(&tmOut, slot, col, qt * 16, pt * 8, im);
+                        }
+                        else if (args.out_transposed) tma_store_2d(&tmOut, slot, row, col);
+                        else                          tma_store_2d(&tmOut, slot, col, row);
                     }
                     bulk_commit();
                     if (k + ns < total) {
@@ -1066,6 +1090,26 @@ static int make_map_im2col(CUtensorMap* map, const float* base, int N, int H, in
     return I2V_OK;
 }
 
+// 4-D tiled map with explicit byte strides (dims / strides innermost first; box = {32, 16, 8, 1} floats x pixels x rows x
+// images, SWIZZLE_128B): the 16 x 8 pixel boxes of the direct first-layer forward.  Strides may OVERLAP the inner extent
+// (the 8-pixel window of output pixel q+1 starts two pixels after that of q).
+static int make_map_4d(CUtensorMap* map, const float* base, const uint64_t dims[4], const uint64_t strides_bytes[3]) {
+    cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+    cuuint64_t st[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+    cuuint32_t box[4] = {TC_BK, 16, 8, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), d, st, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (4-D) failed (%d) dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu)", (int)r,
+                  (unsigned long long)d[0], (unsigned long long)d[1], (unsigned long long)d[2], (unsigned long long)d[3],
+                  (unsigned long long)st[0], (unsigned long long)st[1], (unsigned long long)st[2]);
+        return I2V_ECUDA;
+    }
+    return I2V_OK;
+}
+
 // Tensor maps are keyed by (pointer, geometry): the engine reuses its activation buffers every step, so
 // after the first step no descriptor is encoded on the hot path.
 struct MapKey {
@@ -1098,6 +1142,17 @@ static int get_map_2d_plain(CUtensorMap* out, const float* base, int rows, int c
     auto it = g_maps.find(key);
     if (it != g_maps.end()) { *out = it->second; return I2V_OK; }
     if (int r = make_map_2d_plain(out, base, (uint64_t)rows, (uint64_t)cols, (uint32_t)box_rows, (uint32_t)box_cols)) return r;
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps.emplace(key, *out);
+    return I2V_OK;
+}
+static int get_map_4d(CUtensorMap* out, const float* base, const uint64_t dims[4], const uint64_t strides_bytes[3]) {
+    MapKey key{base, (int)dims[1], (int)dims[2], (int)dims[3], (int)(strides_bytes[0]), (int)(strides_bytes[1] & 0x7fffffff),
+               (int)(strides_bytes[2] & 0x7fffffff), (int)(strides_bytes[2] >> 31), 4};
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return I2V_OK; }
+    if (int r = make_map_4d(out, base, dims, strides_bytes)) return r;
     if (g_maps.size() > 4096) g_maps.clear();
     g_maps.emplace(key, *out);
     return I2V_OK;
@@ -1452,6 +1507,70 @@ extern "C" int i2v_conv_stem_fwd_tc_f32(const i2v_conv_desc* d, const float* x, 
         if (int r = tc_run(pr, as_stream(stream))) return r;
     }
     return I2V_OK;
+}
+
+// EXPERIMENTAL ($I2V_STEM_DIRECT=1 in the engine): first-layer forward WITHOUT the patch matrix.  The image is packed once
+// into a zero-padded NHWC4 copy xp [N, Hp, Wp, 4] (Hp = H + 2 pad, Wp >= W + 2 pad; 16 bytes per pixel), and filter row r
+// of output pixel (p, q) is then the 32 contiguous floats xp[n, stride*p + r, stride*q .. stride*q + 7, 0..3] — S <= 8
+// taps x 3 channels, the rest meets zero weights.  A TMA tile is a 16 x 8 box of output pixels (4-D tiled map whose q
+// stride of 32 bytes overlaps the 128-byte window; one map per row parity, stride 2 only), K = R k-steps of 32, the
+// GEMM and its TMA epilogue (4-D store of the same box) are the persistent dual-issuer kernel.
+// Against the im2col path this drops ~2 GB of scratch traffic each way per 256 frames at 224^2 and adds 40 % MMA work.
+// wr_* = [Cout, R*32] K-major, k = r*32 + s*4 + c (zero where s >= S or c == 3), TF32 hi / lo split.
+extern "C" int i2v_conv_stem_fwd_direct_supported(const i2v_conv_desc* d) {
+    return d && d->Cin == 3 && d->R == d->S && d->S >= 5 && d->S <= 8 && d->stride == 2 && d->Cout == 64 && d->pad < d->R;
+}
+
+static void stem_direct_geometry(const i2v_conv_desc* d, int* Hp, int* Wp) {
+    *Hp = d->H + 2 * d->pad;
+    const int need = (d->Q - 1) * d->stride + 8;
+    const int wp = d->W + 2 * d->pad;
+    *Wp = wp > need ? wp : need;
+}
+
+extern "C" int64_t i2v_conv_stem_fwd_direct_scratch_floats(const i2v_conv_desc* d) {
+    if (!d) return 0;
+    int Hp, Wp;
+    stem_direct_geometry(d, &Hp, &Wp);
+    return (int64_t)d->N * Hp * Wp * 4;
+}
+
+extern "C" int i2v_conv_stem_fwd_direct_f32(const i2v_conv_desc* d, const float* x, const float* wr_hi, const float* wr_lo,
+                                            const float* bias, float* xp_scratch, float* y, int flags, i2v_stream_t stream) {
+    I2V_REQUIRE(d && x && wr_hi && wr_lo && xp_scratch && y, "null pointer (the direct first-layer forward is 3xTF32 only)");
+    I2V_REQUIRE(i2v_conv_stem_fwd_direct_supported(d), "shape not supported by the direct first-layer forward");
+    if (d->N == 0) return I2V_OK;
+    if (int r = resolve_driver()) return r;
+    int Hp, Wp;
+    stem_direct_geometry(d, &Hp, &Wp);
+    if (int r = stem_pack_nhwc4_launch(x, xp_scratch, d->N, d->H, d->W, Hp, Wp, d->pad, as_stream(stream))) return r;
+    const int st = d->stride;
+    CUtensorMap tmA, tmAodd, tmBhi, tmBlo, tmOut;
+    const uint64_t row_bytes = (uint64_t)Wp * 16, img_bytes = (uint64_t)Hp * row_bytes;
+    {
+        const uint64_t dims[4] = {TC_BK, (uint64_t)d->Q, (uint64_t)((Hp + 1) / 2), (uint64_t)d->N};
+        const uint64_t strides[3] = {(uint64_t)st * 16, (uint64_t)st * row_bytes, img_bytes};
+        if (int r = get_map_4d(&tmA, xp_scratch, dims, strides)) return r;
+        const uint64_t dims_odd[4] = {TC_BK, (uint64_t)d->Q, (uint64_t)(Hp / 2), (uint64_t)d->N};
+        if (int r = get_map_4d(&tmAodd, xp_scratch + (size_t)Wp * 4, dims_odd, strides)) return r;
+    }
+    {
+        const uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->Q, (uint64_t)d->P, (uint64_t)d->N};
+        const uint64_t strides[3] = {(uint64_t)d->Cout * 4, (uint64_t)d->Q * d->Cout * 4, (uint64_t)d->P * d->Q * d->Cout * 4};
+        if (int r = get_map_4d(&tmOut, y, dims, strides)) return r;
+    }
+    const int Ktot = d->R * TC_BK;
+    if (int r = get_map_2d(&tmBhi, wr_hi, d->Cout, Ktot, 64)) return r;
+    if (int r = get_map_2d(&tmBlo, wr_lo, d->Cout, Ktot, 64)) return r;
+    TcArgs a{};
+    a.bias = bias; a.dst = y;
+    a.store_cols = d->Cout;
+    a.stem4d = st; a.stem_tq = (d->Q + 15) / 16; a.stem_tp = (d->P + 7) / 8;
+    a.M = (int64_t)d->N * a.stem_tq * a.stem_tp * TC_BM;        // every tile row is "valid": the TMA store clips the boxes
+    a.Cout = d->Cout; a.P = d->P; a.Q = d->Q; a.stride = 1;
+    a.taps_h = d->R; a.taps_w = 1; a.cblocks = 1; a.relu = (flags & I2V_EPI_RELU) ? 1 : 0;
+    a.trace = g_trace; a.trace_tiles = g_trace_tiles;
+    return tc_launch_persist<64, true, false, true, true>(tmA, tmBhi, tmBlo, tmOut, tmAodd, a, as_stream(stream));
 }
 
 // Strided data gradient, one stride-parity class per call.  Image rows h = stride*i + ph (columns likewise)

@@ -74,6 +74,12 @@ class _Conv:
             nz = capi.stem_dgrad_tc_rows(cin * R * S)
             wz = torch.cat([self.w_stem, self.w_stem.new_zeros(nz - cin * R * S, cout)], 0).contiguous()
             self.tc_stem_dgrad = _split_tf32(wz)
+        # EXPERIMENTAL direct first-layer forward ($I2V_STEM_DIRECT=1): [Cout, R*32] K-major, k = r*32 + s*4 + c
+        self.tc_stem_direct = None
+        if x_nchw and cin == 3 and cout == 64 and R == S and 5 <= S <= 8 and self.stride == 2:
+            wr = ws.new_zeros(cout, R, 8, 4)
+            wr[:, :, :S, :3] = ws.permute(0, 2, 3, 1)
+            self.tc_stem_direct = _split_tf32(wr.reshape(cout, R * 32).contiguous())
         # first-layer forward as im2col + GEMM: [Cout, Kp] K-major, k = (c,r,s) zero-padded to a multiple of 32
         self.tc_stem_fwd = None
         if x_nchw and cin == 3 and cout % 64 == 0:
@@ -300,6 +306,9 @@ class NativeEngine:
         self.use_bits = os.environ.get("I2V_NATIVE_BITS", "1") != "0"   # ReLU-backward masks as bits (TMA epilogue)
         self.use_stem_tc = os.environ.get("I2V_NATIVE_STEM_TC", "1") != "0"   # first-layer dgrad as tcgen05 GEMM + col2im
         self._zbuf = None
+        # EXPERIMENTAL: first-layer forward without the im2col patch matrix (i2v_conv_stem_fwd_direct_f32)
+        self.stem_direct = os.environ.get("I2V_STEM_DIRECT", "0") == "1"
+        self._xpbuf = None
         self._cache = {}
 
     @property
@@ -370,7 +379,14 @@ class NativeEngine:
 
     # ---- forward -------------------------------------------------------------------------------------
     def _conv_fwd(self, op, d, x, y, residual, bits_out=None):
-        if op.x_nchw and residual is None and self.use_tc and self.use_stem_tc and op.tc_stem_fwd is not None:
+        if (op.x_nchw and residual is None and self.use_tc and self.use_stem_tc and self.tf32x3 and self.stem_direct
+                and op.tc_stem_direct is not None and capi.conv_stem_fwd_direct_supported(d)):
+            hi, lo, _ = op.tc_stem_direct
+            nfl = capi.stem_fwd_direct_scratch_floats(d)
+            if self._xpbuf is None or self._xpbuf.numel() < nfl:
+                self._xpbuf = torch.empty(nfl, device=x.device, dtype=torch.float32)
+            capi.conv_stem_fwd_direct(d, x, hi, lo, op.bias, self._xpbuf, y, relu=op.relu)
+        elif op.x_nchw and residual is None and self.use_tc and self.use_stem_tc and op.tc_stem_fwd is not None:
             hi, lo, rna = op.tc_stem_fwd
             nfl = capi.stem_fwd_tc_scratch_floats(d)
             if self._zbuf is None or self._zbuf.numel() < nfl:

@@ -286,6 +286,14 @@ int i2v_conv_stem_dgrad_tc_group(const i2v_conv_desc* d);
  * ReLU.  wk_hi / wk_lo = [Cout, Kp] K-major (zero-padded), TF32 hi / lo split (wk_lo = NULL: plain TF32);
  * col_scratch holds group * P*Q*Kp floats; y = [N,P,Q,Cout] NHWC.                                           */
 int i2v_conv_stem_fwd_tc_group(const i2v_conv_desc* d);
+/* EXPERIMENTAL alternative without the patch matrix (engine: $I2V_STEM_DIRECT=1; S in 5..8, stride 2, Cout = 64, 3xTF32
+ * only): the image is packed into a zero-padded NHWC4 copy (xp_scratch, i2v_conv_stem_fwd_direct_scratch_floats(d)
+ * floats) and every filter row is a 32-float window of it read by a 4-D tiled TMA box of 16 x 8 output pixels.
+ * wr_hi / wr_lo = [Cout, R*32] K-major, k = r*32 + s*4 + c, zero where s >= S or c == 3.                           */
+int     i2v_conv_stem_fwd_direct_supported(const i2v_conv_desc* d);
+int64_t i2v_conv_stem_fwd_direct_scratch_floats(const i2v_conv_desc* d);
+int     i2v_conv_stem_fwd_direct_f32(const i2v_conv_desc* d, const float* x, const float* wr_hi, const float* wr_lo,
+                                     const float* bias, float* xp_scratch, float* y, int flags, i2v_stream_t stream);
 int i2v_conv_stem_fwd_tc_f32(const i2v_conv_desc* d, const float* x, const float* wk_hi, const float* wk_lo,
                              const float* bias, float* col_scratch, float* y, int flags, i2v_stream_t stream);
 

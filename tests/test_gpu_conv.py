@@ -408,6 +408,33 @@ def test_conv_tc_strided_dgrad_classes(shape, x3):
         assert err <= tol, (err, tol)
 
 
+@pytest.mark.parametrize("H,W,k,s,p,n", [(224, 224, 7, 2, 3, 3), (64, 64, 7, 2, 3, 2), (37, 53, 7, 2, 3, 1), (62, 30, 5, 2, 2, 2),
+                                         (112, 112, 7, 2, 3, 5)])
+def test_stem_fwd_direct(H, W, k, s, p, n):
+    """EXPERIMENTAL first-layer forward without the patch matrix: padded NHWC4 copy + 4-D tiled TMA boxes of 16 x 8 output
+    pixels whose q stride overlaps the 8-pixel window (ragged P / Q exercise the TMA zero fill and store clipping)."""
+    from i2v_b200.engine_native import _split_tf32
+    g = torch.Generator().manual_seed(4)
+    Cout = 64
+    x = torch.randn(n, 3, H, W, generator=g)
+    w = torch.randn(Cout, 3, k, k, generator=g) / (3 * k * k) ** 0.5
+    shift = torch.randn(Cout, generator=g) * 0.1
+    P, Q = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    d = capi.ConvDesc(n, H, W, 3, Cout, k, k, s, p, P, Q)
+    assert capi.conv_stem_fwd_direct_supported(d)
+    wr = torch.zeros(Cout, k, 8, 4)
+    wr[:, :, :k, :3] = w.permute(0, 2, 3, 1)
+    hi, lo, _ = _split_tf32(wr.reshape(Cout, k * 32).contiguous().to(DEV))
+    xp = torch.full((capi.stem_fwd_direct_scratch_floats(d),), float("nan"), device=DEV)
+    y = torch.full((n, P, Q, Cout), float("nan"), device=DEV)
+    capi.conv_stem_fwd_direct(d, x.to(DEV), hi, lo, shift.to(DEV), xp, y, relu=True)
+    ref64 = _ref_conv(x, w, torch.ones(Cout), shift, s, p, None, True, torch.float64)
+    got = y.permute(0, 3, 1, 2).cpu().double()
+    assert torch.isfinite(got).all()
+    err = (got - ref64).abs().max() / ref64.abs().max()
+    assert err <= (1e-5 + 3 * k * k * 2.0 ** -24), err
+
+
 @pytest.mark.parametrize("H,W,k,s,p,n", [(224, 224, 7, 2, 3, 2), (64, 64, 7, 2, 3, 3), (64, 64, 11, 4, 2, 1), (32, 32, 3, 1, 1, 2),
                                          (63, 63, 3, 2, 0, 4)])
 @pytest.mark.parametrize("x3", [True, False])
