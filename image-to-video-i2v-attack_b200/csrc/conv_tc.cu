@@ -456,7 +456,11 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // instead of four.  3x3 64->64 at 256 frames: 474 us against 454 us with two issuers in the same run.  So once two
     // threads issue, these layers are no longer bound by the issue rate; what remains is operand delivery — every SM
     // pulls the same 16 KB weight block and a 16 KB im2col tile per k-step through L2, 8 TB/s in aggregate — which is
-    // what TMA multicast across a CTA pair / cta_group::2 would halve.)
+    // what TMA multicast across a CTA pair / cta_group::2 would halve.  Two more layouts of the same kernel were measured on
+    // that layer and dropped: ONE accumulator stage + an 8-slot A_lo ring so that 6 shared-memory stages are in flight
+    // instead of 4 (447.8 against 447.4 us: not bound by pipeline depth either), and BOTH A operands in tensor memory —
+    // the split warps also copy the raw tile, both MMAs read A from TMEM, 16 KB less shared-memory traffic per k-step
+    // (453.7 against 429.9 us: not shared-memory bandwidth).  Plain TF32 without any split runs the layer in 321 us.)
     constexpr uint32_t kAccCols = X3 ? (ALO_TMEM ? 3 * BN : 2 * BN) : BN;   // TMEM columns per accumulator stage
     constexpr int kAcc = ALO_TMEM ? (int)(384 / kAccCols) : ((512 / kAccCols) > 4 ? 4 : (512 / kAccCols));
     constexpr uint32_t kAloBase = 384, kAloSlots = 4;
