@@ -470,3 +470,29 @@ def test_video_variants_match_reference_fixture(golden):
     _record("video_variants/frac_equal", **stats)
     for k, val in stats.items():                  # measured: 1.0 except tap3_2d 0.99986
         assert val > 0.995, (k, val, stats)
+
+
+def test_temporal_translation_helpers():
+    """The reference's private helpers kept on the class (video_attacks.py:80-177) against their torch statements."""
+    import random
+    import video_attacks
+    atk = video_attacks.TemporalTranslation(synth.TinyTPNLike().cuda(), {"kernlen": 5, "momentum": False, "weight": 0.3,
+                                                                         "move_type": "adj", "kernel_mode": "linear"})
+    g = torch.Generator().manual_seed(3)
+    v = torch.randn(1, 3, 32, 6, 6, generator=g).cuda()
+    assert torch.equal(atk._cycle_move(v, -2), torch.roll(v, -2, dims=2))
+    assert torch.equal(atk._cycle_move_large(v, 2), torch.roll(v, 17, dims=2))
+    assert torch.equal(atk._cycle_move_large(v, -3), torch.roll(v, -18, dims=2))
+    random.seed(5)
+    got = atk._cycle_move_random(v, 1)
+    random.seed(5)
+    assert torch.equal(got, torch.roll(v, random.randint(0, 100) % 32, dims=2))
+    ex = atk._exchange_move(v, [(0, 5), (7, 9)])
+    assert torch.equal(ex[:, :, 0], v[:, :, 5]) and torch.equal(ex[:, :, 9], v[:, :, 7]) and torch.equal(ex[:, :, 3], v[:, :, 3])
+    grads = torch.randn(5, 1, 3, 32, 6, 6, generator=g).cuda()
+    k = atk.kernel.double()
+    s_conv = torch.matmul(k, grads.double().reshape(5, -1)).reshape(1, 3, 32, 6, 6)
+    assert torch.allclose(atk._conv1d_frame(grads).double(), s_conv, rtol=1e-6, atol=1e-7)
+    diff = torch.stack([torch.roll(grads[i], -m, dims=2) for i, m in enumerate(atk.cycle_move_list)])      # 172-173
+    d_conv = torch.matmul(k, diff.double().reshape(5, -1)).reshape(1, 3, 32, 6, 6)
+    assert torch.allclose(atk._grad_augmentation(grads).double(), 0.7 * s_conv + 0.3 * d_conv, rtol=1e-6, atol=1e-7)

@@ -96,6 +96,47 @@ class TemporalTranslation(Attack):
         capi.temporal_shift_stack(adv_videos.contiguous(), out, [direction * (abs(cycle_move) % adv_videos.shape[2])])
         return out[0]
 
+    def _cycle_move_large(self, adv_videos, cycle_move):
+        """107-120: |move| -> (|move| + frames/2 - 1) mod frames (0 stays 0)."""
+        frames = adv_videos.shape[2]
+        direction = -1 if cycle_move < 0 else 1
+        amount = abs(cycle_move)
+        amount = amount % frames if amount == 0 else (amount + (int(frames / 2) - 1)) % frames
+        out = torch.empty((1,) + tuple(adv_videos.shape), device=adv_videos.device, dtype=adv_videos.dtype)
+        capi.temporal_shift_stack(adv_videos.contiguous(), out, [direction * amount])
+        return out[0]
+
+    def _cycle_move_random(self, adv_videos, cycle_move):
+        """122-135: a random amount (one `random.randint(0, 100)`) for every non-zero move."""
+        frames = adv_videos.shape[2]
+        direction = -1 if cycle_move < 0 else 1
+        amount = 0 if cycle_move == 0 else random.randint(0, 100) % frames
+        out = torch.empty((1,) + tuple(adv_videos.shape), device=adv_videos.device, dtype=adv_videos.dtype)
+        capi.temporal_shift_stack(adv_videos.contiguous(), out, [direction * amount])
+        return out[0]
+
+    def _exchange_move(self, adv_videos, exchange_lists):
+        """137-143: swap pairs of frames (index plumbing; not used by forward())."""
+        new_videos = adv_videos.clone()
+        for one_frame, ano_frame in exchange_lists:
+            new_videos[:, :, one_frame] = adv_videos[:, :, ano_frame]
+            new_videos[:, :, ano_frame] = adv_videos[:, :, one_frame]
+        return new_videos
+
+    def _conv1d_frame(self, grads):
+        """80-91: grads [D,N,C,T,H,W] -> sum_d kernel[d] * grads[d] (K8 with weight 0)."""
+        D, N, C, T, H, W = grads.shape
+        out = torch.empty((N, C, T, H, W), device=grads.device, dtype=grads.dtype)
+        capi.temporal_combine(grads.contiguous().view(D, N, C, T, H, W), self._kernel_host, [0] * D, 0.0, out)
+        return out
+
+    def _grad_augmentation(self, grads):
+        """163-177: (1-weight) * conv1d(grads) + weight * conv1d(grads shifted back by their nominal moves), one K8 pass."""
+        D, N, C, T, H, W = grads.shape
+        out = torch.empty((N, C, T, H, W), device=grads.device, dtype=grads.dtype)
+        capi.temporal_combine(grads.contiguous(), self._kernel_host, self.cycle_move_list, self.weight, out)
+        return out
+
     def _get_grad(self, adv_videos, labels, loss):
         """150-157: CE gradient of one slice of the variant stack ([n_var * B, 3, T, H, W])."""
         return self._ce_grad(adv_videos, labels, loss)
