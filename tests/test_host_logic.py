@@ -233,3 +233,27 @@ def test_tap_and_ilaf_constructors():
     assert image_attacks.ILAF(model, "other", target_layers=[model.layer1])._find_target_layer() == [model.layer1]
     with pytest.raises(ValueError):
         image_attacks.ILAF(model, "resnet")
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's own CPU loop on the host cores) prints exactly one JSON line with the
+    contract's keys; under torchrun only rank 0 prints."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    r = json.loads(lines[0])
+    assert r["impl"] == "reference" and r["metric"] == "attack_frame_steps_per_sec" and r["unit"] == "frame-steps/s"
+    assert r["higher_is_better"] is True and r["value"] > 0 and r["gpu_launches"] == 0 and r["vs_baseline"] is None
+    assert r["cpu_baseline"]["kind"] in ("reference", "port") and r["cpu_baseline"]["cores"] >= 1
+    assert r["e2e"] == {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in r["config"]
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2"],
+                         capture_output=True, text=True, timeout=600, cwd=root, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
