@@ -23,11 +23,17 @@
 // rewrite each landed A tile into a second shared-memory buffer (element-wise, so the swizzle pattern is
 // preserved).  X3 = false is plain TF32 (one MMA per K-slice), the mode cuDNN uses with allow_tf32.
 //
-// Epilogue (same four warps, after the main loop): TMEM -> registers (tcgen05.ld 32x32b.x32: one
-// pixel-row per thread), + bias, + residual, ReLU, ReLU-backward mask, 128-bit stores to NHWC.
-//
-// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM allocator,
-// warps 4..7 = A-split during the main loop, then epilogue (warp w owns TMEM lanes 32*(w%4)..+31).
+// Two kernels live in this file:
+//   conv_tc_kernel          (v1) one tile per CTA, 256 threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator,
+//                           warps 4..7 A-split during the main loop, then the epilogue (TMEM -> registers -> 128-bit stores).
+//                           Kept as the simple reference implementation ($I2V_TC_PERSISTENT=0).
+//   conv_tc_persist_kernel  (v2, the one the engine runs) persistent, 512 threads, one CTA per SM: producer, one or TWO MMA
+//                           issuers (A_lo in tensor memory), epilogue-TMA issuer(s), four split warps, eight epilogue warps;
+//                           accumulators multi-buffered in TMEM; TMA epilogue through swizzled staging slots with bit-packed
+//                           ReLU masks, or a register epilogue for scattered (strided-class) output rows.  Its variants,
+//                           what was measured for each and what was tried and dropped are described next to the code.
+// Host side: tensor-map cache, shape dispatch (tc_run), the first-layer entry points (im2col + GEMM, GEMM + col2im, and the
+// experimental patch-matrix-free forward) and the strided data-gradient classes.
 // Every mbarrier wait has a clock-based watchdog that traps instead of hanging the GPU.
 #include <cuda.h>
 #include <stdlib.h>
