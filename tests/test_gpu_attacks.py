@@ -496,3 +496,25 @@ def test_temporal_translation_helpers():
     diff = torch.stack([torch.roll(grads[i], -m, dims=2) for i, m in enumerate(atk.cycle_move_list)])      # 172-173
     d_conv = torch.matmul(k, diff.double().reshape(5, -1)).reshape(1, 3, 32, 6, 6)
     assert torch.allclose(atk._grad_augmentation(grads).double(), 0.7 * s_conv + 0.3 * d_conv, rtol=1e-6, atol=1e-7)
+
+
+def test_attack_driver_end_to_end(tmp_path):
+    """`attack.py` (reference attack.py:1-96) with the stand-in model: both dispatch branches, artefact names / shapes /
+    dtypes of 92-96, the eps-ball."""
+    import attack
+    common = ["--synthetic", "--model", "tiny", "--num_clips", "3", "--batch_size", "2", "--frames", "8", "--side", "16",
+              "--num_classes", "10", "--opt_path", str(tmp_path), "--step", "2"]
+    attack.main(common + ["--attack_type", "image", "--attack_method", "MIFGSM"])
+    attack.main(common + ["--attack_type", "video", "--attack_method", "TemporalTranslation", "--kernlen", "5",
+                          "--augmentation_weight", "0.5", "--iterative_momentum"])
+    for sub in ("tiny-MIFGSM-2-", "tiny-TemporalTranslation-2-"):
+        for idx in range(3):
+            adv = np.load(os.path.join(str(tmp_path), sub, "%d-adv.npy" % idx))
+            ori = np.load(os.path.join(str(tmp_path), sub, "%d-ori.npy" % idx))
+            assert adv.shape == ori.shape == (3, 8, 16, 16) and adv.dtype == np.float32 and np.isfinite(adv).all()
+            clean, _ = synth.clip(idx, b=1, f=8, h=16, w=16)
+            assert np.array_equal(ori, clean.numpy()[0])
+            _bounds_ok(clean.numpy(), adv[None])
+            assert np.abs(adv - ori).max() > 0
+    with pytest.raises(ValueError):
+        attack.main(common + ["--attack_type", "video", "--attack_method", "BIM"])

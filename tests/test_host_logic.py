@@ -257,3 +257,23 @@ def test_bench_reference_arm_contract():
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2"],
                          capture_output=True, text=True, timeout=600, cwd=root, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_attack_driver_host_side(tmp_path):
+    """attack.py: flags, output directory name (attack.py:54-57) and the class dispatch (76-84) — no GPU needed."""
+    import attack
+    import base_attacks
+    import video_attacks
+    from i2v_b200 import synth
+    args = attack.arg_parse(["--model", "tiny", "--attack_method", "TIFGSM", "--step", "3", "--file_prefix", "x",
+                             "--opt_path", str(tmp_path)])
+    assert args.adv_path == os.path.join(str(tmp_path), "tiny-TIFGSM-3-x") and args.attack_type == "image"
+    model = synth.TinyVideoNet()
+    atk = attack.build_attack(args, model)
+    assert isinstance(atk, base_attacks.TIFGSM) and atk.steps == 3
+    args = attack.arg_parse(["--attack_type", "video", "--attack_method", "TemporalTranslation", "--kernlen", "7",
+                             "--augmentation_weight", "0.3", "--move_type", "large", "--kernel_mode", "linear"])
+    atk = attack.build_attack(args, model)
+    assert isinstance(atk, video_attacks.TemporalTranslation) and atk.kernlen == 7 and atk.weight == 0.3
+    assert atk.move_type == "large" and atk.momentum is False and len(atk.cycle_move_list) == 7
+    assert attack.standin_model("r3d_18", 7).fc.out_features == 7
