@@ -518,3 +518,21 @@ def test_attack_driver_end_to_end(tmp_path):
             assert np.abs(adv - ori).max() > 0
     with pytest.raises(ValueError):
         attack.main(common + ["--attack_type", "video", "--attack_method", "BIM"])
+
+
+def test_fine_tune_driver_end_to_end(tmp_path):
+    """attack.py -> image_fine_tune_attack.py: ILAF over the saved `{label}-adv.npy` / `{label}-ori.npy` pairs."""
+    import attack
+    import image_fine_tune_attack as ft
+    src, dst = os.path.join(str(tmp_path), "src"), os.path.join(str(tmp_path), "dst")
+    attack.main(["--synthetic", "--model", "tiny", "--num_clips", "2", "--batch_size", "1", "--frames", "8", "--side", "16",
+                 "--num_classes", "10", "--opt_path", src, "--step", "2", "--attack_method", "BIM"])
+    pairs = os.path.join(src, "tiny-BIM-2-")
+    atk = ft.main(["--synthetic", "--white_model", "tpn_tiny", "--num_classes", "10", "--used_adv", pairs, "--used_ori", pairs,
+                   "--opt_path", dst, "--steps", "3"])
+    for idx in range(2):
+        out = np.load(os.path.join(dst, "%d-adv.npy" % idx))
+        assert out.shape == (3, 8, 16, 16) and out.dtype == np.float32 and np.isfinite(out).all()
+    clean, _ = synth.clip(1, b=1, f=8, h=16, w=16)
+    _bounds_ok(clean.numpy(), atk.last_adv.cpu().numpy())                 # the plain (unscrambled) clip of the last call
+    assert sorted(atk.loss_info["..."]) == [0, 1, 2]

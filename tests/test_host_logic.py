@@ -277,3 +277,19 @@ def test_attack_driver_host_side(tmp_path):
     assert isinstance(atk, video_attacks.TemporalTranslation) and atk.kernlen == 7 and atk.weight == 0.3
     assert atk.move_type == "large" and atk.momentum is False and len(atk.cycle_move_list) == 7
     assert attack.standin_model("r3d_18", 7).fc.out_features == 7
+
+
+def test_fine_tune_driver_host_side(tmp_path):
+    """image_fine_tune_attack.py: AdvDataset over saved pairs (16-37) and the flags — no GPU needed."""
+    import image_fine_tune_attack as ft
+    rng = np.random.default_rng(0)
+    for label in (7, 12):
+        np.save(os.path.join(str(tmp_path), "%d-adv" % label), rng.standard_normal((3, 4, 6, 6)).astype(np.float32))
+        np.save(os.path.join(str(tmp_path), "%d-ori" % label), rng.standard_normal((3, 4, 6, 6)).astype(np.float32))
+    ds = ft.AdvDataset(str(tmp_path), str(tmp_path))
+    assert len(ds) == 2
+    vid, ori, label = ds[0]
+    assert tuple(vid.shape) == tuple(ori.shape) == (1, 3, 4, 6, 6) and label.dtype == torch.int64
+    assert int(label) in (7, 12) and np.array_equal(vid[0].numpy(), np.load(os.path.join(str(tmp_path), "%d-adv.npy" % int(label))))
+    args = ft.arg_parse(["--white_model", "tpn_tiny", "--used_adv", "a", "--used_ori", "b", "--opt_path", "c", "--synthetic"])
+    assert args.attack_method == "ILAF" and args.steps == 60 and args.step_size == 0.005 and args.synthetic
