@@ -293,3 +293,19 @@ def test_fine_tune_driver_host_side(tmp_path):
     assert int(label) in (7, 12) and np.array_equal(vid[0].numpy(), np.load(os.path.join(str(tmp_path), "%d-adv.npy" % int(label))))
     args = ft.arg_parse(["--white_model", "tpn_tiny", "--used_adv", "a", "--used_ori", "b", "--opt_path", "c", "--synthetic"])
     assert args.attack_method == "ILAF" and args.steps == 60 and args.step_size == 0.005 and args.synthetic
+
+
+def test_image_main_ucf101_host_side(tmp_path):
+    """image_main_ucf101.py = image_main.py with the reference's four differences (step default 10, UCF loader /
+    labels mod 101, ENS gets steps, video_names = str(label tensor)) — flags and loader only, no GPU."""
+    import image_main_ucf101 as u
+    args = u.arg_parse(["--synthetic", "--num_clips", "205", "--batch_size", "2", "--frames", "2", "--side", "8", "--opt_path",
+                        str(tmp_path), "--file_prefix", "p"])
+    assert args.step == 10 and args.adv_path == os.path.join(str(tmp_path), "Image-ImageGuidedFMDirection_Adam-10-p")
+    assert u.arg_parse(["--step", "7"]).step == 7 and u.arg_parse(["--step=9"]).step == 9
+    n, get_step = u.get_loader(args)
+    assert n == 103
+    vids, labs, names = get_step(101)                       # clips 202, 203 -> labels 0, 1 (mod 101)
+    assert tuple(vids.shape) == (2, 3, 2, 8, 8) and labs.tolist() == [0, 1]
+    vids, labs, names = get_step(102)
+    assert vids.shape[0] == 1 and labs.tolist() == [204 % 400 % 101]
