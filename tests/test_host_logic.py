@@ -309,3 +309,17 @@ def test_image_main_ucf101_host_side(tmp_path):
     assert tuple(vids.shape) == (2, 3, 2, 8, 8) and labs.tolist() == [0, 1]
     vids, labs, names = get_step(102)
     assert vids.shape[0] == 1 and labs.tolist() == [204 % 400 % 101]
+
+
+def test_attack_ucf101_host_side(tmp_path):
+    """attack_ucf101.py: output directory names (57-59), 101 classes, fixed TemporalTranslation parameters (87)."""
+    import attack_ucf101 as au
+    import video_attacks
+    from i2v_b200 import synth
+    args = au.arg_parse(["--model", "tiny", "--attack_method", "BIM", "--step", "4", "--opt_path", str(tmp_path)])
+    assert args.adv_path == os.path.join(str(tmp_path), "UCF101_Image-tiny-BIM-4-") and args.num_classes == 101
+    args = au.arg_parse(["--model", "tiny", "--attack_type", "video", "--attack_method", "TemporalTranslation", "--kernlen", "5",
+                         "--opt_path", str(tmp_path)])
+    assert args.adv_path.endswith("UCF101_Video-tiny-TemporalTranslation-10-")
+    atk = au.build_attack(args, synth.TinyVideoNet())
+    assert isinstance(atk, video_attacks.TemporalTranslation) and atk.kernlen == 15 and atk.weight == 1.0 and atk.momentum is False
