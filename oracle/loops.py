@@ -541,9 +541,24 @@ def _cycle(videos, move, frames):
     return new
 
 
+def _cycle_amount(move, frames, move_type):
+    """video_attacks.py:93-135: the frame shift each move type applies for a nominal `move` (random: one randint draw)."""
+    import random
+    direction = -1 if move < 0 else 1
+    amount = abs(move)
+    if move_type == "adj":
+        amount = amount % frames
+    elif move_type == "large":
+        amount = amount % frames if amount == 0 else (amount + (int(frames / 2) - 1)) % frames
+    else:
+        amount = amount % frames if move == 0 else random.randint(0, 100) % frames
+    return direction * amount
+
+
 def temporal_translation(model, videos, labels, kernlen, weight, momentum=False, kernel_mode="gaussian", epsilon=16 / 255,
-                         steps=10, delay=1.0, targeted=1, tpnet=False):
-    """video_attacks.py:179-229 with move_type 'adj' (the deterministic one); batch of one clip, as the reference needs."""
+                         steps=10, delay=1.0, targeted=1, tpnet=False, move_type="adj"):
+    """video_attacks.py:179-229; batch of one clip, as the reference needs.  The INPUT shifts follow `move_type`
+    (192-199); the gradients are shifted back by the NOMINAL moves whatever the move type (172-173 call `_cycle_move`)."""
     import math
     model.eval()
     videos = np.ascontiguousarray(videos, dtype=np.float32)
@@ -559,7 +574,7 @@ def temporal_translation(model, videos, labels, kernlen, weight, momentum=False,
     adv = videos.copy()                                                         # 186
     for _ in range(steps):
         adv_t = torch.from_numpy(adv)
-        batch_inps = torch.cat([_cycle(adv_t, m, frames) for m in moves], dim=0)           # 191-200
+        batch_inps = torch.cat([_cycle(adv_t, _cycle_amount(m, frames, move_type), frames) for m in moves], dim=0)   # 191-200
         length = len(moves)
         batch_times = length if tpnet else 5                                    # 202-206
         batch_size = math.ceil(length / batch_times)

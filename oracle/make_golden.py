@@ -146,6 +146,17 @@ def run_video_variants(ref):
     rec["tt3_k5"] = tt(5, 0.5, "gaussian", 3, False)
     rec["tt3_k5_mom"] = tt(5, 0.5, "gaussian", 3, True)
     rec["tt2_k9_linear"] = tt(9, 0.3, "linear", 2, False)
+
+    def tt_move(move_type):
+        import random
+        random.seed(21)
+        with LR.quiet():
+            atk = ref.video_attacks.TemporalTranslation(
+                synth.TinyTPNLike(), {"kernlen": 5, "momentum": True, "weight": 0.7, "move_type": move_type,
+                                      "kernel_mode": "random"}, steps=2)
+            return atk(videos.clone(), labels).detach().numpy()
+    rec["tt2_k5_large"] = tt_move("large")
+    rec["tt2_k5_randommove"] = tt_move("random")
     for conv3d in (True, False):
         with LR.quiet():
             atk = ref.base_attacks.TAP(synth.TinyTPNLike(), {"kernlen": 3, "temporal_kernlen": 3, "eta": 1e3, "conv3d": conv3d,

@@ -294,6 +294,11 @@ def test_video_variant_loops_match_reference(golden):
     assert frac(OL.temporal_translation(m, videos, labels, 5, 0.5, steps=3), g["tt3_k5"]) == 1.0
     assert frac(OL.temporal_translation(m, videos, labels, 5, 0.5, momentum=True, steps=3), g["tt3_k5_mom"]) == 1.0
     assert frac(OL.temporal_translation(m, videos, labels, 9, 0.3, kernel_mode="linear", steps=2), g["tt2_k9_linear"]) == 1.0
+    import random
+    for move_type, key in (("large", "tt2_k5_large"), ("random", "tt2_k5_randommove")):      # uniform kernel, momentum, w = 0.7
+        random.seed(21)
+        got = OL.temporal_translation(m, videos, labels, 5, 0.7, momentum=True, kernel_mode="random", steps=2, move_type=move_type)
+        assert frac(got, g[key]) == 1.0, move_type
     for conv3d, tag in ((True, "3d"), (False, "2d")):
         adv, info = OL.tap(m, [m.layer1, m.layer2], videos, labels, conv3d=conv3d, steps=3)
         assert frac(adv, g["tap3_" + tag]) == 1.0
