@@ -1158,7 +1158,7 @@ static int get_map_2d_plain(CUtensorMap* out, const float* base, int rows, int c
 }
 static int get_map_4d(CUtensorMap* out, const float* base, const uint64_t dims[4], const uint64_t strides_bytes[3]) {
     MapKey key{base, (int)dims[1], (int)dims[2], (int)dims[3], (int)(strides_bytes[0]), (int)(strides_bytes[1] & 0x7fffffff),
-               (int)(strides_bytes[2] & 0x7fffffff), (int)(strides_bytes[2] >> 31), 4};
+               (int)(strides_bytes[2] & 0x7fffffff), (int)(((strides_bytes[2] >> 31) << 12) | (dims[0] & 0xfff)), 4};
     std::lock_guard<std::mutex> lk(g_maps_mu);
     auto it = g_maps.find(key);
     if (it != g_maps.end()) { *out = it->second; return I2V_OK; }
