@@ -10,8 +10,9 @@ The transfer-enhancing variants of SURVEY.md 8(f) rank 3 share that update block
 gradient is obtained / conditioned: `DIFGSM` (342-411, random resize + pad of the input), `TIFGSM` (413-479,
 per-frame 15x15 Gaussian smoothing of the gradient: K7 stencil kernel), `SGM` (481-551, ReLU backward hooks),
 `SIM` (553-611, gradient averaged over 5 input scales), `TIFGSM3D` (613-683, 15x15x15 smoothing + frame-level
-mean-|g| normalisation).  `TAP` (685-814) hooks layers of gluoncv video models (`model_type` i3d / slowfast /
-tpn) that are not installable offline and stays out of scope.
+mean-|g| normalisation), `TAP` (685-814, feature-magnification loss on hooked layers of a video model — `model_type`
+i3d / slowfast / tpn pick the layers, the `target_layers` attribute any other modules — plus the box-filter regulariser on the K7
+stencil kernel).
 """
 import contextlib
 import random

@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--clips", type=int, default=CLIPS_PER_GPU, help="clips per GPU (default 16 = 512 frames)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cudnn-baseline", action="store_true")
+    ap.add_argument("--no-ensemble", action="store_true", help="skip the configs[2] leg (runs when N is a multiple of 4)")
     ap.add_argument("--shapes", action="store_true", help="print a per-shape timing table of the convolutions to stderr")
     return ap.parse_args()
 
@@ -120,8 +122,9 @@ def cpu_reference_rate(steps, frames=32, side=SIDE, budget_s=40.0):
     """frame-steps/s of the reference's I2V loop on the host cores, all threads.
 
     kind 'reference': the unmodified class from /root/reference (build container only);
-    kind 'port'     : oracle/loops.py, the line-by-line CPU restatement (what travels to the GPU box).
-    Both run the reference's FULL forward + autograd with weight gradients, as the reference does.
+    kind 'port'     : oracle/loops.py, the line-by-line CPU restatement (what travels to the GPU box), run with
+                      weight_grads=True: FULL forward (layers after the hook, avgpool, fc included) and `cost.backward()`
+                      with every backbone parameter requiring grad, exactly the work image_attacks.py:334, 351-353 does.
     The sample is one config-1 clip (32 frames of 3x224x224); the per-step time is measured between the
     first and the last optimizer step so that model construction and the clean-feature pass are excluded.
     """
@@ -135,6 +138,7 @@ def cpu_reference_rate(steps, frames=32, side=SIDE, budget_s=40.0):
     steps = max(2, steps)
     if LR.available():
         kind = "reference"
+        work = "the unmodified reference class: full forward, cost.backward() incl. all weight gradients"
         ref = LR.load()
         orig = torch.optim.Adam
 
@@ -152,16 +156,20 @@ def cpu_reference_rate(steps, frames=32, side=SIDE, budget_s=40.0):
             torch.optim.Adam = orig
     else:
         kind = "port"
+        work = ("oracle/loops.py port of the reference loop: full forward, cost.backward() with all backbone parameters "
+                "requiring grad (weight gradients computed, as image_attacks.py:351-353)")
         from oracle import loops as OL
         model = backbones.seeded_random_init("resnet50", 0)
+        assert all(p.requires_grad for p in model.parameters())
         hooked = [OL.HookedModel(model, "resnet", DEPTH)]
-        OL.image_guided_loop(hooked, videos.numpy(), EPS, steps, STEP_SIZE,
+        OL.image_guided_loop(hooked, videos.numpy(), EPS, steps, STEP_SIZE, weight_grads=True,
                              tap=lambda i, d: stamps.append(time.perf_counter()))
+        assert model.conv1.weight.grad is not None and model.layer4[-1].conv3.weight.grad is not None
     dt = (stamps[-1] - stamps[0]) / (len(stamps) - 1)
     return {"value": frames / dt, "unit": UNIT, "cores": cores, "threads": torch.get_num_threads(), "kind": kind,
-            "ms_per_step": dt * 1e3,
-            "sample": "1 clip x %d frames x 3x%dx%d, %d steps, I2V ResNet-50 layer2 (full forward + weight grads as the "
-                      "reference runs it), per-step time between first and last optimizer step" % (frames, side, side, steps)}
+            "ms_per_step": dt * 1e3, "weight_grads": True,
+            "sample": "1 clip x %d frames x 3x%dx%d, %d steps, I2V ResNet-50 layer2 on %d host threads; kind=%s: %s; "
+                      "per-step time between first and last optimizer step" % (frames, side, side, steps, cores, kind, work)}
 
 
 def run_reference_arm(args):
@@ -176,11 +184,225 @@ def run_reference_arm(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "I2V ResNet-50 layer2 cosine attack, CPU reference path, bounded sample: " + base["sample"],
                    "eps": "16/255", "step_size": STEP_SIZE},
-        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "weight_grads", "sample")},
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+
+# --------------------------------------------------------------------------------------------------
+# measured TF32 tensor peak, library (cuDNN) baselines, the reference loop as-is on the GPU
+# --------------------------------------------------------------------------------------------------
+def measure_tf32_peak(device, n=8192, sustain_s=2.0):
+    """torch.matmul on two n^3 float32 operands with allow_tf32=True (cuBLAS TF32 tensor-core GEMM), measured the way
+    MEASURED_PEAKS.json measures bf16: best of 10 (burst) and back to back for `sustain_s` (sustained), 2*n^3 flops."""
+    import torch
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn(n, n, device=device)
+        b = torch.randn(n, n, device=device)
+        c = torch.empty(n, n, device=device)
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize()
+        best = float("inf")
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, b, out=c); e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(10, int(sustain_s * 1e3 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize()
+        sustained = e0.elapsed_time(e1) / reps
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    fl = 2.0 * n ** 3
+    return {"burst_tflops": fl / (best * 1e-3) / 1e12, "sustained_tflops": fl / (sustained * 1e-3) / 1e12,
+            "how": "torch.matmul f32 %d^3, allow_tf32=True: best of 10 / back to back for %.0f s" % (n, sustain_s)}
+
+
+def _time_run(run, warm, timed):
+    import torch
+    for _ in range(warm):
+        run.step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(timed):
+        run.step()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / timed
+
+
+def cudnn_baselines(dev_videos, native_value):
+    """Library baselines of the SAME step on the SAME clips, frame-steps/s on one GPU:
+
+    truncated : comparison point (ii) — torchvision modules through cuDNN, cut at the hooked layer, input gradient only
+                (i2v_b200/engine_cudnn.py), feeding the same K1 / K3a kernels; FP32 (`cudnn.allow_tf32=False`, the
+                parity-equivalent arm) and TF32, NCHW and channels_last.
+    as_is     : comparison point (i) — the reference's loop as image_attacks.py:294-364 runs it on a GPU: FULL forward of
+                the torchvision model with a forward hook, F.cosine_similarity, `cost.backward()` with every weight
+                requiring grad, torch.optim.Adam on the modifier, `print(cost)`-style host sync every step; restated here
+                with torch ops only (no kernel of this repo on the path)."""
+    import torch
+    import torch.nn.functional as F
+    from i2v_b200 import attack_loop, backbones, engines
+    out = {"unit": UNIT, "frames": int(dev_videos.shape[0] * dev_videos.shape[2]), "truncated_dgrad_only": {}, "as_is": {}}
+    for name in ("cudnn", "cudnn_tf32", "cudnn_cl", "cudnn_tf32_cl"):
+        eng = engines.make_engine(backbones.get_model("resnet50"), "resnet50", DEPTH, name)
+        run = attack_loop.ImageGuidedRun([eng], EPS, 5, STEP_SIZE)
+        run.setup(dev_videos)
+        ms = _time_run(run, 2, 3)
+        out["truncated_dgrad_only"][name] = {"value": run.N / (ms * 1e-3), "ms_per_step": ms, "chunk_frames": run.chunk}
+        del run, eng
+        torch.cuda.empty_cache()
+
+    # ---- the reference loop as-is (4 clips = 128 frames: a full ResNet-50 autograd graph at 512 frames does not leave
+    # room next to the rest of the bench; the reference's own usage is batch size 1, image_main.py:82-89) ------------
+    vids = dev_videos[:4]
+    b, c, f, h, w = vids.shape
+    mean = torch.tensor([0.485, 0.456, 0.406], device=vids.device).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225], device=vids.device).view(1, 3, 1, 1)
+    for tag, tf32 in (("fp32", False), ("tf32", True)):
+        prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        try:
+            model = backbones.seeded_random_init("resnet50", 0).to(vids.device)
+            model.train()
+            for m in model.modules():
+                if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.BatchNorm1d)):
+                    m.eval()
+            acts = []
+            model.layer2[-1].register_forward_hook(lambda mod, i, o: acts.append(o))
+            image_inps = vids.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)
+            modifier = torch.nn.Parameter(torch.full((b * f, c, h, w), 0.01 / 255, device=vids.device))
+            opt = torch.optim.Adam([modifier], lr=STEP_SIZE)
+            unnorm = (image_inps * std + mean).detach()
+            model(image_inps)
+            init = acts.pop().detach()
+            times, cost_host = [], None
+            for i in range(6):
+                if i == 2:
+                    torch.cuda.synchronize(); t0 = time.perf_counter()
+                del acts[:]
+                true_image = torch.clamp(unnorm + torch.clamp(modifier, min=-EPS, max=EPS), min=0, max=1)
+                true_image = (true_image - mean) / std
+                model(true_image)
+                cost = torch.sum(F.cosine_similarity(acts[0].view(b * f, -1), init.view(b * f, -1)))
+                opt.zero_grad()
+                cost.backward()
+                opt.step()
+                cost_host = float(cost.detach().cpu())          # the reference prints the cost every step
+            torch.cuda.synchronize()
+            ms = (time.perf_counter() - t0) * 1e3 / 4
+            out["as_is"][tag] = {"value": b * f / (ms * 1e-3), "ms_per_step": ms, "frames": b * f, "final_cost": cost_host}
+            del model, modifier, opt, acts, init, cost, true_image
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+        torch.cuda.empty_cache()
+    best_fp32 = max(v["value"] for k, v in out["truncated_dgrad_only"].items() if "tf32" not in k)
+    best_tf32 = max(v["value"] for k, v in out["truncated_dgrad_only"].items() if "tf32" in k)
+    out["native_fp32_parity_over"] = {"cudnn_truncated_fp32": native_value / best_fp32, "cudnn_truncated_tf32": native_value / best_tf32,
+                                      "reference_as_is_gpu_fp32": native_value / out["as_is"]["fp32"]["value"],
+                                      "reference_as_is_gpu_tf32": native_value / out["as_is"]["tf32"]["value"]}
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# BASELINE.json configs[2]: ensemble, one backbone per GPU, NCCL all-reduce of the perturbation gradient
+# --------------------------------------------------------------------------------------------------
+ENSEMBLE_MODELS = ["resnet50", "vgg", "densenet121", "squeezenet"]
+
+
+class _TimedHook:
+    """dist.ReduceHook with CUDA events around the two collectives of a step."""
+
+    def __init__(self, inner):
+        import torch
+        self.inner, self.torch, self.marks = inner, torch, []
+
+    def _ev(self):
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def grad(self, g):
+        a = self._ev()
+        self.inner.grad(g)
+        self.marks.append([a, self._ev()])
+
+    def cos_rows(self, cos):
+        self.inner.cos_rows(cos)
+        self.marks[-1].append(self._ev())
+
+
+def ensemble_leg(rank, world, device, steps):
+    """AENS-I2V (TPAMI_attack.py:141-320) over ENSEMBLE_MODELS, layers [2, 3] of each, placement='ensemble': rank r holds
+    member r mod 4 of replica r // 4, every replica attacks its own 32-frame clip, and each step all-reduces
+    dcost/dtrue_image (19.3 MB) and the [8, 32] cosine table inside the replica's NCCL group.  Reports whole-job
+    frame-steps/s, the per-member compute time before the exchange (the load imbalance) and the time inside the
+    collectives (for every rank but the slowest this includes waiting for it)."""
+    import torch
+    import torch.distributed as tdist
+    import TPAMI_attack
+    from i2v_b200 import attack_loop, dist as D, synth
+    M = len(ENSEMBLE_MODELS)
+    if world < M or world % M:
+        return None
+    atk = TPAMI_attack.AENS_I2V_MF(ENSEMBLE_MODELS, {n: [2, 3] for n in ENSEMBLE_MODELS}, STEP_SIZE, momentum=0.5,
+                                   steps=steps, placement="ensemble")
+    plan = atk._plan
+    videos = synth.clip(1000 + plan.replica, b=1, f=FRAMES, h=SIDE, w=SIDE)[0].to(device)
+    W = 2
+    hook = _TimedHook(plan.hook())
+    run = attack_loop.ImageGuidedRun(atk._engines, EPS, W + steps, STEP_SIZE, adaptive=True, coeffs=atk.coeffs, momentum=0.5,
+                                     reduce_hook=hook, layer_offsets=plan.layer_offsets, n_layers_total=plan.n_layers_total)
+    run.setup(videos)
+    for _ in range(W):
+        run.step()
+    hook.marks.clear()
+    D.barrier()
+    torch.cuda.synchronize()
+    starts = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        s = torch.cuda.Event(enable_timing=True); s.record(); starts.append(s)
+        run.step()
+    e1.record()
+    torch.cuda.synchronize()
+    D.barrier()
+    ms = D.max_over_ranks(e0.elapsed_time(e1), device) / steps
+    compute = sum(s.elapsed_time(m[0]) for s, m in zip(starts, hook.marks)) / steps
+    coll = sum(m[0].elapsed_time(m[2]) for m in hook.marks) / steps
+    mine = torch.tensor([compute, coll], device=device, dtype=torch.float64)
+    allv = [torch.zeros_like(mine) for _ in range(world)]
+    tdist.all_gather(allv, mine)
+    res = run.finish()
+    if rank != 0:
+        return None
+    per = {}
+    for r, t in enumerate(allv):
+        per["rank%d:%s" % (r, ENSEMBLE_MODELS[r % M])] = {"compute_ms": float(t[0]), "collectives_incl_wait_ms": float(t[1])}
+    comp = [float(t[0]) for t in allv]
+    return {"workload": "AENS-I2V, %s, layers [2,3] each, one backbone per GPU, %d replica(s) x one %d-frame 3x%dx%d clip, "
+                        "FP32 parity mode" % ("/".join(ENSEMBLE_MODELS), world // M, FRAMES, SIDE, SIDE),
+            "value": (world // M) * FRAMES / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
+            "allreduce_bytes_per_step": FRAMES * 3 * SIDE * SIDE * 4 + 2 * M * FRAMES * 4,
+            "allreduce_ms_per_step": min(float(t[1]) for t in allv),
+            "allreduce_share_of_step": min(float(t[1]) for t in allv) / ms,
+            "member_compute_ms_max_over_min": max(comp) / max(min(comp), 1e-9), "per_rank": per,
+            "final_cost": float(res.cost[-1]), "nccl_group_size": M}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -264,8 +486,8 @@ def run_b200_arm(args):
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     # tensor roofline for the TF32 convolutions: the kernel runs inside a long step => sustained bf16 figure; TF32
     # issues at half the bf16 rate on the 5th-generation tensor cores (nominal 1.1 vs 2.25 PFLOP/s dense)
-    bf16_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    tf32_peak = bf16_peak / 2
+    tf32_meas = measure_tf32_peak(device) if rank == 0 else {"burst_tflops": 1.0, "sustained_tflops": 1.0, "how": ""}
+    tf32_peak = tf32_meas["sustained_tflops"]          # the convolutions run inside a long step: sustained figure
     traffic = {}
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
@@ -285,7 +507,7 @@ def run_b200_arm(args):
             mma = 3.0 if engine_name == "native" else 1.0
             r["tensor"] = {"achieved_algorithmic": tfl, "issued": tfl * mma, "peak": tf32_peak, "unit": "TFLOP/s",
                            "frac_algorithmic": tfl / tf32_peak, "frac_issued": tfl * mma / tf32_peak,
-                           "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 issue rate)",
+                           "peak_source": "measured in this run: " + tf32_meas["how"] + " (sustained)",
                            "algorithmic_flops_per_launch": k["flops"] / k["launches"],
                            "note": "FP32-parity mode issues 3 TF32 MMAs per algorithmic MAC" if mma == 3.0 else "plain TF32"}
         roof_all[name] = r
@@ -318,10 +540,23 @@ def run_b200_arm(args):
                "note": "one attack(videos, labels, names) call of K steps incl. setup, clean-feature pass, H2D of the "
                        "clips and D2H of the adversarial clips (second call: warm allocator); bytes are per call / K"}
 
+    cudnn_base = None
+    if rank == 0 and world == 1 and not args.no_cudnn_baseline:
+        if "run" in locals():
+            del run
+        torch.cuda.empty_cache()
+        cudnn_base = cudnn_baselines(dev_videos, value)
+    ens = None
+    if world >= len(ENSEMBLE_MODELS) and world % len(ENSEMBLE_MODELS) == 0 and not args.no_ensemble:
+        if "run" in locals():
+            del run
+        del atk, eng
+        torch.cuda.empty_cache()
+        ens = ensemble_leg(rank, world, device, max(2, min(K, 10)))
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         b = cpu_reference_rate(4)
-        cpu_base = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu_base = {k: b[k] for k in ("value", "unit", "cores", "kind", "weight_grads", "sample")}
 
     if rank == 0:
         line = {
@@ -335,7 +570,7 @@ def run_b200_arm(args):
                        "chunk_frames": chunk_frames, "final_cost": float(res.cost[-1]) if len(res.cost) else None},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(sum(launches.values())),
             "gpu_launches_by_kernel": launches, "roofline": roofline, "roofline_all": roof_all,
-            "cpu_baseline": cpu_base,
+            "cpu_baseline": cpu_base, "cudnn_baseline": cudnn_base, "tf32_peak": tf32_meas, "ensemble": ens,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

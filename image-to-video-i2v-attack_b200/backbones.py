@@ -11,9 +11,12 @@ Differences from the reference, all deliberate:
         'resnet' as ResNet-50; truncated at depth <= 2 the two are the same network).
   * D3  DenseNet has no branch in the reference's `_find_target_layer` (it would crash); here depth d
         hooks `features.denseblock{d}` — an extension, not reference behaviour.
-  * weights: `pretrained=True` needs the network.  Policy 'auto' (default) loads torchvision's
-        IMAGENET1K_V1 weights when they are already in the local hub cache and otherwise uses seeded
-        random init; 'random' always does the latter (tests, benchmarks); 'pretrained' insists.
+  * weights: the reference hard-requires `pretrained=True` (image_attacks.py:86-98) and so does the default policy
+        here, 'pretrained': torchvision's IMAGENET1K_V1 weights from the local hub cache, RuntimeError when they are
+        missing (there is no network to fetch them).  Seeded random init is an explicit opt-in — policy 'random'
+        (`set_weight_policy('random')`, `--weights random`, $I2V_WEIGHTS=random) — used by tests and benchmarks;
+        'auto' (cached weights if present, else random init with a warning) must be asked for as well.
+        `WEIGHT_SOURCE[arch]` records what every constructed backbone actually got; the drivers write it out.
   * unknown names raise ValueError listing the supported ones (the reference raises
         UnboundLocalError).
 """
@@ -48,14 +51,15 @@ SUPPORTED = tuple(sorted(FAMILY))
 
 # name -> torchvision constructor name; tests set {'resnet': 'resnet50'} to follow BASELINE.json
 ARCH_OVERRIDE = {}
-_WEIGHT_POLICY = {"mode": os.environ.get("I2V_WEIGHTS", "auto"), "seed": int(os.environ.get("I2V_WEIGHT_SEED", "0"))}
+_WEIGHT_POLICY = {"mode": os.environ.get("I2V_WEIGHTS", "pretrained"), "seed": int(os.environ.get("I2V_WEIGHT_SEED", "0"))}
+WEIGHT_SOURCE = {}     # arch -> "pretrained:<file>" | "random:seed=<n>", what get_model() last built for it
 
 for _kv in filter(None, os.environ.get("I2V_ARCH_MAP", "").split(",")):
     _k, _v = _kv.split("=")
     ARCH_OVERRIDE[_k.strip()] = _v.strip()
 
 
-def set_weight_policy(mode="auto", seed=0):
+def set_weight_policy(mode="pretrained", seed=0):
     if mode not in ("auto", "random", "pretrained"):
         raise ValueError("weight policy must be auto|random|pretrained, got %r" % (mode,))
     _WEIGHT_POLICY["mode"] = mode
@@ -107,13 +111,18 @@ def get_model(model_name, device=None):
         w = _pretrained_cached(arch)
         if w is not None:
             model = getattr(torchvision.models, arch)(weights=w)
+            WEIGHT_SOURCE[arch] = "pretrained:" + os.path.basename(w.url)
         elif mode == "pretrained":
-            raise RuntimeError("pretrained weights for %s are not in the local torch hub cache" % arch)
+            raise RuntimeError("pretrained ImageNet weights for %s are not in the local torch hub cache (%s) and cannot be "
+                               "downloaded here; a random-weight surrogate has no transfer value, so it is opt-in: "
+                               "--weights random / I2V_WEIGHTS=random / backbones.set_weight_policy('random')"
+                               % (arch, os.path.join(torch.hub.get_dir(), "checkpoints")))
         else:
             warnings.warn("i2v_b200: no cached ImageNet weights for %s; using seeded random init (seed %d)"
                           % (arch, _WEIGHT_POLICY["seed"]))
     if model is None:
         model = seeded_random_init(arch, _WEIGHT_POLICY["seed"])
+        WEIGHT_SOURCE[arch] = "random:seed=%d" % _WEIGHT_POLICY["seed"]
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
     model.to(device)

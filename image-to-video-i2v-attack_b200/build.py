@@ -42,6 +42,7 @@ def build(force=False, verbose=False):
     sources = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "i2v_b200.h"))
+    headers.append(os.path.join(HERE, "..", "include", "i2v_b200_debug.h"))
     stamp = os.path.join(OBJ, "stamp.txt")
     want = _digest([os.path.join(CSRC, s) for s in sources] + headers, (ARCH, COMMON, PER_FILE))
     if not force and os.path.isfile(LIB) and os.path.isfile(stamp) and open(stamp).read().strip() == want:

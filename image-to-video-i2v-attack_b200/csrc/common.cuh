@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include "../../include/i2v_b200.h"
+#include "../../include/i2v_b200_debug.h"
 
 namespace i2v {
 

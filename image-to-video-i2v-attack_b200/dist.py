@@ -89,6 +89,11 @@ class EnsemblePlan:
             world = dist.get_world_size() if dist.is_initialized() else 1
         self.rank, self.world = rank, world
         M = len(model_names)
+        if world > M and world % M != 0:
+            # a rank outside every replica group would run the attack with no backbone (zero gradient, no collective)
+            # and hand back a clean clip as "adversarial": refuse the layout instead
+            raise ValueError("one-backbone-per-GPU placement needs a world size that is a multiple of the %d ensemble "
+                             "members (or smaller than it), got %d" % (M, world))
         self.members, self.replica = ensemble_placement(model_names, rank, world)
         offsets, off = [], 0
         for n in layers_per_model:

@@ -22,8 +22,11 @@ class CudnnEngine:
     relu_masked_grads = False   # autograd applies the hooked ReLU's backward itself
     preferred_chunk = 128       # frames per forward/backward: bounds autograd's saved activations
 
-    def __init__(self, model, model_name, depth, allow_tf32=False):
+    def __init__(self, model, model_name, depth, allow_tf32=False, channels_last=False):
         self.model = backbones.freeze_for_attack(model)
+        self.channels_last = bool(channels_last)
+        if self.channels_last:
+            self.model.to(memory_format=torch.channels_last)
         self.model_name = model_name
         self.depth = depth
         self.allow_tf32 = allow_tf32
@@ -62,7 +65,7 @@ class CudnnEngine:
         prev_tf32 = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = self.allow_tf32
         try:
-            self.model(img)
+            self.model(img.contiguous(memory_format=torch.channels_last) if self.channels_last else img)
         except _StopForward:
             pass
         finally:

@@ -148,7 +148,8 @@ class ImageGuidedFML2_Adam_MultiModels(Attack):
         self._plan = None
         if placement == "ensemble":
             from i2v_b200 import dist as D
-            self._plan = D.EnsemblePlan(model_name_lists, [1] * len(model_name_lists))
+            self._plan = D.EnsemblePlan(model_name_lists, [len(depths[n]) if isinstance(depths[n], (list, tuple)) else 1
+                                                           for n in model_name_lists])
             mine = [model_name_lists[i] for i in self._plan.members]
         elif placement is None:
             mine = list(model_name_lists)

@@ -58,7 +58,9 @@ def arg_parse(argv=None):
     parser.add_argument("--side", type=int, default=224)
     parser.add_argument("--momentum", type=float, default=0.0, help="AENS_I2V_MF")
     parser.add_argument("--engine", type=str, default=None, help="native | native_tf32 | cudnn | cudnn_tf32")
-    parser.add_argument("--weights", type=str, default="auto", help="auto | random | pretrained (backbones.set_weight_policy)")
+    parser.add_argument("--weights", type=str, default=os.environ.get("I2V_WEIGHTS", "pretrained"),
+                        help="pretrained (default, as the reference: fails when the ImageNet checkpoints are not cached) | "
+                             "random (seeded random init: tests / benchmarks only) | auto (backbones.set_weight_policy)")
     args = parser.parse_args(argv)
     args.adv_path = os.path.join(args.opt_path, "{}-{}-{}-{}".format("Image", args.attack_method, args.step, args.file_prefix))
     return args
@@ -105,16 +107,23 @@ class SyntheticLoader:
 
 
 def get_loader(args):
+    """image_main.py:52-58.  Without --synthetic the reference's own data pipeline is REQUIRED: its `datasets` module
+    and the gluoncv config helpers of its `utils.py` (CONFIG_PATHS, get_cfg_custom) must be importable from the
+    reference environment ($I2V_REFERENCE_ROOT on sys.path).  Nothing is substituted silently: a missing pipeline is a
+    SystemExit, a broken dataset raises whatever it raises."""
     if not args.synthetic:
         try:
-            from datasets import get_dataset                      # the reference's loader, if its environment exists
-            from utils import CONFIG_PATHS, get_cfg_custom
-            cfg = get_cfg_custom(CONFIG_PATHS["i3d_resnet101"], args.batch_size)
-            loader = get_dataset(cfg)
-            items = list(loader)
-            return len(items), lambda i: items[i]
-        except Exception as exc:                                  # noqa: BLE001 — gluoncv / decord / data are absent offline
-            print("reference data pipeline unavailable (%s: %s) -> synthetic clips" % (type(exc).__name__, exc))
+            from datasets import get_dataset                      # the reference's loader (gluoncv + decord)
+            import utils as ref_utils
+            CONFIG_PATHS, get_cfg_custom = ref_utils.CONFIG_PATHS, ref_utils.get_cfg_custom
+        except (ImportError, AttributeError) as exc:
+            raise SystemExit("image_main.py: the reference data pipeline is not importable (%s: %s); run inside the "
+                             "reference environment or pass --synthetic for seeded synthetic clips"
+                             % (type(exc).__name__, exc))
+        cfg = get_cfg_custom(CONFIG_PATHS["i3d_resnet101"], args.batch_size)
+        loader = get_dataset(cfg)
+        items = list(loader)
+        return len(items), lambda i: items[i]
     sl = SyntheticLoader(args.num_clips, args.batch_size, args.frames, args.side)
     return len(sl), sl.step
 
@@ -163,8 +172,7 @@ def main(argv=None):
     elif args.gpu is not None:
         torch.cuda.set_device(int(args.gpu.split(",")[0]))
     from i2v_b200 import backbones
-    if args.weights != "auto":
-        backbones.set_weight_policy(args.weights, 0)
+    backbones.set_weight_policy(args.weights, 0)
     os.makedirs(args.adv_path, exist_ok=True)
     print(args)
 
@@ -188,6 +196,11 @@ def main(argv=None):
     saver.close()
     with open(os.path.join(args.adv_path, "loss_info_{}.json".format(index)), "w") as opt:   # image_main.py:94-95
         json.dump(attack_method.loss_info, opt)
+    # provenance next to the artefacts: which weights the surrogate backbones really had and where the clips came from
+    with open(os.path.join(args.adv_path, "run_info_{}.json".format(index)), "w") as opt:
+        json.dump({"args": {k: v for k, v in vars(args).items()}, "weight_source": dict(backbones.WEIGHT_SOURCE),
+                   "data_source": "synthetic (i2v_b200.synth.clip)" if args.synthetic else "reference loader",
+                   "clips": len(mine)}, opt, indent=1)
 
 
 if __name__ == "__main__":

@@ -42,11 +42,12 @@ def build_attack(args):
 def get_loader(args):
     if not args.synthetic:
         try:
-            from dataset_ucf101 import attack_genearte_dataeset    # the reference's UCF-101 loader, if its environment exists
-            items = list(attack_genearte_dataeset(args.batch_size))
-            return len(items), lambda i: items[i]
-        except Exception as exc:                                  # noqa: BLE001 — decord / the videos are absent offline
-            print("reference UCF-101 pipeline unavailable (%s: %s) -> synthetic clips" % (type(exc).__name__, exc))
+            from dataset_ucf101 import attack_genearte_dataeset    # the reference's UCF-101 loader (decord + the videos)
+        except ImportError as exc:
+            raise SystemExit("image_main_ucf101.py: the reference UCF-101 pipeline is not importable (%s); run inside the "
+                             "reference environment or pass --synthetic for seeded synthetic clips" % exc)
+        items = list(attack_genearte_dataeset(args.batch_size))
+        return len(items), lambda i: items[i]
     sl = im.SyntheticLoader(args.num_clips, args.batch_size, args.frames, args.side)
 
     def step(i):
@@ -63,8 +64,7 @@ def main(argv=None):
     elif args.gpu is not None:
         torch.cuda.set_device(int(args.gpu.split(",")[0]))
     from i2v_b200 import backbones
-    if args.weights != "auto":
-        backbones.set_weight_policy(args.weights, 0)
+    backbones.set_weight_policy(args.weights, 0)
     os.makedirs(args.adv_path, exist_ok=True)
     print(args)
     n_steps, get_step = get_loader(args)
@@ -87,6 +87,10 @@ def main(argv=None):
     saver.close()
     with open(os.path.join(args.adv_path, "loss_info_{}.json".format(index)), "w") as opt:
         json.dump(attack_method.loss_info, opt)
+    with open(os.path.join(args.adv_path, "run_info_{}.json".format(index)), "w") as opt:
+        json.dump({"args": dict(vars(args)), "weight_source": dict(backbones.WEIGHT_SOURCE),
+                   "data_source": "synthetic (i2v_b200.synth.clip)" if args.synthetic else "reference loader",
+                   "clips": len(mine)}, opt, indent=1)
     return attack_method
 
 

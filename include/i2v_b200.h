@@ -297,16 +297,6 @@ int     i2v_conv_stem_fwd_direct_f32(const i2v_conv_desc* d, const float* x, con
 int i2v_conv_stem_fwd_tc_f32(const i2v_conv_desc* d, const float* x, const float* wk_hi, const float* wk_lo,
                              const float* bias, float* col_scratch, float* y, int flags, i2v_stream_t stream);
 
-/* Debug / measurement: issue-rate probe of tcgen05.mma.kind::tf32 (M = 128, K = 8): `count` MMAs of width N into
- * `accs` round-robin accumulators with A from shared memory (a_tmem = 0) or tensor memory, on `ctas` CTAs;
- * out[0] = cycles to issue, out[1] = cycles until completion (CTA 0).  tools/mma_probe.py prints the table.   */
-int i2v_mma_probe(int N, int accs, int a_tmem, int count, int ctas, int issuers /* 1..3 concurrently issuing warps */,
-                  long long* out, i2v_stream_t stream);
-
-/* Debug: subsequent tensor-core launches make CTA 0 stamp clock64() at 8 pipeline points of each of its first
- * `tiles` tiles into device_buf[tiles][8] (see TcArgs::trace in csrc/conv_tc.cu); NULL switches it off.     */
-int i2v_conv_tc_set_trace(unsigned long long* device_buf, int tiles);
-
 /* Strided data gradient on the tensor cores, one stride-parity class (ph, pw) per call: image rows
  * h = stride*i + ph receive only the taps r = r0 + stride*a, r0 = (ph + pad) mod stride, from dy row
  * i + (ph + pad - r0)/stride - a — a dense stride-1 implicit GEMM over dy whose output rows are scattered

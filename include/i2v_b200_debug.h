@@ -1,0 +1,24 @@
+/* i2v_b200_debug.h — measurement hooks of libi2v_b200.so used by tools/ (tools/mma_probe.py, tools/tc_trace.py,
+ * tools/stem_direct_trace.py).  NOT part of the product ABI of include/i2v_b200.h: nothing on the attack path calls
+ * them, a binding of the reference does not need them, and they may change without notice.                        */
+#ifndef I2V_B200_DEBUG_H_
+#define I2V_B200_DEBUG_H_
+#include "i2v_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Debug / measurement: issue-rate probe of tcgen05.mma.kind::tf32 (M = 128, K = 8): `count` MMAs of width N into
+ * `accs` round-robin accumulators with A from shared memory (a_tmem = 0) or tensor memory, on `ctas` CTAs;
+ * out[0] = cycles to issue, out[1] = cycles until completion (CTA 0).  tools/mma_probe.py prints the table.   */
+int i2v_mma_probe(int N, int accs, int a_tmem, int count, int ctas, int issuers /* 1..3 concurrently issuing warps */,
+                  long long* out, i2v_stream_t stream);
+
+/* Debug: subsequent tensor-core launches make CTA 0 stamp clock64() at 8 pipeline points of each of its first
+ * `tiles` tiles into device_buf[tiles][8] (see TcArgs::trace in csrc/conv_tc.cu); NULL switches it off.     */
+int i2v_conv_tc_set_trace(unsigned long long* device_buf, int tiles);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* I2V_B200_DEBUG_H_ */

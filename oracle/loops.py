@@ -174,8 +174,13 @@ def _frames(videos):
 
 
 def image_guided_loop(hooked, videos, epsilon, steps, step_size, adaptive=False, coeffs=None, momentum=0.0,
-                      coef_CE=False, cos_mode="torch", tap=None):
+                      coef_CE=False, cos_mode="torch", tap=None, weight_grads=False):
     """image_attacks.py:294-364 / 426-496 (adaptive=False) and TPAMI_attack.py:223-320 (adaptive=True).
+
+    weight_grads: True = `cost.backward()` exactly as image_attacks.py:351-352 runs it — the backbone's parameters
+              require grad, so every step also computes (and accumulates into .grad, nothing ever zeroes them) all
+              weight gradients; this is the COST the reference pays and what the bench's CPU arm times.  False =
+              `autograd.grad(cost, true_image)`: same dcost/dtrue_image bit for bit, weight gradients pruned (tests).
 
     hooked  : list of HookedModel (one per image model, reference order)
     cos_mode: 'torch' — F.cosine_similarity + autograd in f32, the reference's own arithmetic
@@ -232,7 +237,11 @@ def image_guided_loop(hooked, videos, epsilon, steps, step_size, adaptive=False,
                 prev = (each if coef_CE else torch.sum(stacked.detach(), dim=1)).detach().numpy().copy()  # 293-297
             else:
                 cost = torch.sum(stacked)                                      # 347
-            (g,) = torch.autograd.grad(cost, true_image)                       # 352
+            if weight_grads:
+                cost.backward()                                                # 352, weights included
+                g = true_image.grad
+            else:
+                (g,) = torch.autograd.grad(cost, true_image)                   # 352
             cost_val = np.float32(cost.detach().numpy())
             cos_np = stacked.detach().numpy()
         else:

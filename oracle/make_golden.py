@@ -176,6 +176,40 @@ def run_video_variants(ref):
     return rec
 
 
+def run_config1_60step(ref, frames=32, side=224, steps=60, step_size=0.005):
+    """BASELINE.json configs[0] at its own size and step budget (/root/reference/run_image_guided.py:63-70: 60 steps of
+    0.005 on one 32-frame 224x224 clip; image_attacks.py:294-364).  The input is synth.clip(0, b=1, f=32, h=224, w=224),
+    regenerated by the tests; stored are the 60 costs, the final perturbation adv - videos as float16 (|delta| <=
+    eps/std = 0.28: 2.4e-4 resolution against the 1/255/std = 0.017 agreement threshold), and of the FIRST step's
+    dcost/dmodifier only what the sign-agreement score needs: the sign bits, the |g| > 1e-3 max mask, max |g|."""
+    videos, labels = synth.clip(0, b=1, f=frames, h=side, w=side)
+    with LR.quiet():
+        atk = ref.image_attacks.ImageGuidedFMDirection_Adam(["resnet"], depth=2, step_size=step_size, steps=steps)
+    first = {}
+    orig = torch.optim.Adam
+
+    class FirstGrad(orig):
+        def step(self, closure=None):
+            if not first:
+                first["g"] = self.param_groups[0]["params"][0].grad.detach().clone()
+            return super().step(closure)
+    torch.optim.Adam = FirstGrad
+    try:
+        with LR.quiet():
+            adv = atk(videos.clone(), labels, ["clip0"])
+    finally:
+        torch.optim.Adam = orig
+    g = first["g"].numpy()
+    gmax = np.abs(g).max()
+    return {"frames": frames, "side": side, "steps": steps, "step_size": step_size, "epsilon": 16 / 255,
+            "weight_checksums": weight_checksum(atk.model)[None],
+            "cost": np.array([float(atk.loss_info["clip0"][i]["cost"]) for i in range(steps)], dtype=np.float32),
+            "delta16": (adv.detach().contiguous() - videos).numpy().astype(np.float16),
+            "g_first_shape": np.array(g.shape), "g_first_max": np.float64(gmax),
+            "g_first_pos_bits": np.packbits(g.reshape(-1) > 0), "g_first_neg_bits": np.packbits(g.reshape(-1) < 0),
+            "g_first_big_bits": np.packbits(np.abs(g.reshape(-1)) > 1e-3 * gmax)}
+
+
 def main():
     torch.set_num_threads(THREADS)
     os.makedirs(OUT, exist_ok=True)
@@ -196,6 +230,7 @@ def main():
         "base_tiny3d": lambda: run_base(ref),
         "base_variants": lambda: run_base_variants(ref),
         "video_variants": lambda: run_video_variants(ref),
+        "i2v_resnet50_d2_224_60step": lambda: run_config1_60step(ref),
     }
     only = sys.argv[1:]
     for name, job in jobs.items():

@@ -10,9 +10,21 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared():
+    """Every function any header under include/ declares (i2v_b200.h = the product ABI, i2v_b200_debug.h = the
+    measurement hooks the tools use)."""
+    names = set()
+    for fn in sorted(os.listdir(os.path.join(ROOT, "include"))):
+        if not fn.endswith(".h"):
+            continue
+        text = open(os.path.join(ROOT, "include", fn)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names.update(re.findall(r"\b(i2v_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
+
+
+def test_product_header_has_no_debug_hooks():
     text = open(os.path.join(ROOT, "include", "i2v_b200.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(i2v_[a-z0-9_]+)\s*\(", text)))
+    assert "i2v_mma_probe" not in text and "i2v_conv_tc_set_trace" not in text
 
 
 @pytest.fixture(scope="module")

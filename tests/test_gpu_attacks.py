@@ -215,7 +215,7 @@ def test_i2v_step1_vs_reference_tap(golden, engine):
     s, r = _grad_scores(g_mod, ref.astype(np.float64))
     _record("i2v_resnet50_d2_32/%s/step1_vs_reference" % engine, sign=s, relL2=r)
     assert np.allclose(res.cost, g["cost"][:1], rtol=1e-5)
-    assert s >= 0.97          # float32-vs-float32 floor measured by the survey: 99.7 % (same code, threads differ)
+    assert s >= 0.995         # float32-vs-float32 floor measured by the survey: 99.7 % (same code, threads differ)
 
 
 @pytest.mark.parametrize("engine", ENGINES)
@@ -276,20 +276,110 @@ def test_aens_coef_ce_and_validation(golden, engine):
         TPAMI_attack.AENS_I2V_MF(["resnet"], {"resnet": [1, 2, 3]}, 0.005, engine=engine)
 
 
-def test_chunking_does_not_change_the_result():
-    """Frames are independent units: any chunking of N gives bit-identical perturbations."""
+@pytest.mark.parametrize("engine", ENGINES)
+def test_chunking_does_not_change_the_result(engine):
+    """Frames are independent units: any chunking of N gives the same costs; on the native engine (deterministic
+    per-frame arithmetic: fixed k-order per output element, per-frame K1 clusters, per-row pooling) the adversarial clip
+    and the cost log are BIT-identical whatever the chunk size."""
     videos, _ = synth.clip(1, b=1, f=6, h=64, w=64)
     out = []
     for chunk in (6, 4, 1):
         model = backbones.get_model("resnet")
-        eng = engines.make_engine(model, "resnet", 2, "cudnn")
+        eng = engines.make_engine(model, "resnet", 2, engine)
         res = attack_loop.run_image_guided([eng], videos, EPS, 3, 0.005, chunk=chunk)
         out.append((res.adv.cpu().numpy(), res.cost))
-    # cuDNN may pick different algorithms for different batch sizes, so only the cost is compared
-    # tightly (the trajectories are chaotic in the conv rounding noise, SURVEY.md D8)
     for adv, cost in out[1:]:
-        assert np.allclose(cost, out[0][1], rtol=1e-5)
-        assert np.abs(adv - out[0][0]).max() <= 2 * 3 * 0.005 / 0.224 * 1.01
+        if engine.startswith("native"):
+            assert np.array_equal(cost, out[0][1]) and np.array_equal(adv, out[0][0])
+        else:
+            # cuDNN may pick different algorithms for different batch sizes, so only the cost is compared
+            # (the trajectories are chaotic in the conv rounding noise, SURVEY.md D8)
+            assert np.allclose(cost, out[0][1], rtol=1e-5)
+
+
+def test_native_chunking_bit_identical_at_benchmark_size():
+    """bench.py's configuration (BASELINE.json configs[1]) relies on this: 224 x 224 frames on the native engine in
+    256-frame chunks plus a remainder chunk with a different (n, h, w) buffer plan.  288 frames (9 clips x 32), two
+    steps: chunk 256 (256 + 32), 100 (100 + 100 + 88), 7 (41 x 7 + 1) and the first clip alone must agree BIT for bit in
+    the adversarial clip and the per-step cost (the cost of a sub-batch is compared through its own frames' cosines)."""
+    clips = 9
+    videos = torch.cat([synth.clip(40 + i, b=1, f=32, h=224, w=224)[0] for i in range(clips)], 0)
+    eng = engines.make_engine(backbones.get_model("resnet"), "resnet", 2, "native")
+    ref_adv = ref_cost = None
+    for chunk in (256, 100, 7):
+        run = attack_loop.ImageGuidedRun([eng], EPS, 2, 0.005, chunk=chunk)
+        run.setup(videos)
+        assert run.chunk == chunk and len(run.spans) == -(-clips * 32 // chunk)
+        for _ in range(2):
+            run.step()
+        cos = run.cos.clone()
+        res = run.finish()
+        adv = res.adv.contiguous()
+        if ref_adv is None:
+            ref_adv, ref_cost, ref_cos = adv, res.cost, cos
+            _bounds_ok(videos[:1].numpy(), adv[:1].cpu().numpy())
+            assert float((adv != videos.cuda()).float().mean()) > 0.5
+        else:
+            assert np.array_equal(res.cost, ref_cost), (chunk, res.cost, ref_cost)
+            assert torch.equal(cos, ref_cos), chunk
+            assert torch.equal(adv, ref_adv), chunk
+        del run, res
+    one = attack_loop.run_image_guided([eng], videos[:1], EPS, 2, 0.005, chunk=32)
+    assert torch.equal(one.adv.contiguous(), ref_adv[:1])
+
+
+def test_i2v_gradients_vs_float64_arbiter_at_224():
+    """The teacher-forced float64 arbiter at the benchmark's own layer shapes: two 224 x 224 frames through ResNet-50 up to
+    layer2 (M = 2*112*112 stem rows, 56 x 56 and 28 x 28 bottlenecks), native engine, three steps, with the engine's ReLU
+    and max-pool decisions forced on the arbiter — same bounds as the small-shape cases."""
+    videos, _ = synth.clip(2, b=1, f=2, h=224, w=224)
+    eng = engines.make_engine(backbones.get_model("resnet"), "resnet", 2, "native")
+    taps = {}
+    attack_loop.run_image_guided([eng], videos, EPS, 3, 0.005, tap=lambda i, d: taps.setdefault(i, d))
+    _teacher_forced_steps("i2v_resnet_d2_224/native", ["resnet"], 2, taps, videos)
+
+
+def test_config1_60_steps_vs_reference_fixture(golden):
+    """BASELINE.json configs[0]/[1] at the reference's own size and step budget (run_image_guided.py:63-70: 60 steps of
+    0.005, one 32-frame 224 x 224 clip; image_attacks.py:294-364), free running, native engine, against the UNMODIFIED
+    reference class (tests/golden/i2v_resnet50_d2_224_60step.npz, oracle/make_golden.py).
+
+    Asserted: every one of the 60 costs within 1e-5 relative (north star), step-1 gradient-sign agreement on the
+    |g| > 1e-3 max elements >= 0.995 (the float32-vs-float32 floor is 0.997: profiles/r02_reference_self_agreement.json is
+    the reference against itself with another thread count), the eps-ball and [0,1] exactly.  The agreement of the final
+    perturbation is REPORTED (gpurun_out/parity_stats.json -> profiles/r02_parity_60step.json) next to the same figure of
+    the reference against itself, and asserted only against that floor (the trajectory is chaotic in the
+    convolution rounding noise, so 99 % is not reachable by the reference itself)."""
+    g = golden("i2v_resnet50_d2_224_60step")
+    steps, f, side = int(g["steps"]), int(g["frames"]), int(g["side"])
+    videos, _ = synth.clip(0, b=1, f=f, h=side, w=side)
+    taps = {}
+
+    def tap(i, d):
+        if i == 0:
+            taps[0] = d["g"].cpu().numpy()
+    eng = engines.make_engine(backbones.get_model("resnet"), "resnet", 2, "native")
+    res = attack_loop.run_image_guided([eng], videos, EPS, steps, float(g["step_size"]), tap=tap)
+    cost_err = float(np.abs(res.cost / g["cost"] - 1).max())
+    adv = res.adv.cpu().numpy()
+    _bounds_ok(videos.numpy(), adv)
+    d = np.abs((adv - videos.numpy()) - g["delta16"].astype(np.float32))
+    n = int(np.prod(g["g_first_shape"]))
+    big = np.unpackbits(g["g_first_big_bits"])[:n].astype(bool)
+    pos, neg = np.unpackbits(g["g_first_pos_bits"])[:n].astype(bool), np.unpackbits(g["g_first_neg_bits"])[:n].astype(bool)
+    g_mod = (taps[0] / O.STD[None, :, None, None]).reshape(-1)          # dcost/dmodifier = dcost/dtrue_image / std
+    same = ((g_mod > 0) == pos) & ((g_mod < 0) == neg)
+    sign_big = float(same[big].mean())
+    # the same run without the per-step host sync of the tap must give the same clip (device-side logs only)
+    res2 = attack_loop.run_image_guided([eng], videos, EPS, steps, float(g["step_size"]))
+    assert torch.equal(res2.adv, res.adv) and np.array_equal(res2.cost, res.cost)
+    _record("config1_60step/native", cost_rel_err_max=cost_err, final_frac_within_1_255=(d <= (1 / 255) / 0.225).mean(),
+            final_frac_within_f16_ulp=(d <= 2.5e-4).mean(), final_max_abs=d.max(), step1_sign_agreement_big=sign_big,
+            step1_sign_agreement_all=same.mean(), step1_gmax=float(np.abs(g_mod).max()), ref_step1_gmax=float(g["g_first_max"]),
+            final_cost=float(res.cost[-1]), ref_final_cost=float(g["cost"][-1]))
+    assert cost_err <= 1e-5, cost_err
+    assert sign_big >= 0.995, sign_big
+    assert (d <= (1 / 255) / 0.225).mean() >= 0.5        # floor: see the docstring; the measured figure is recorded
 
 
 def test_base_attacks_match_reference_fixture(golden):
@@ -450,6 +540,16 @@ def test_video_variants_match_reference_fixture(golden):
     stats["tt3_k5"] = frac_equal(adv_tt, g["tt3_k5"])
     stats["tt3_k5_mom"] = frac_equal(tt(5, 0.5, "gaussian", 3, True), g["tt3_k5_mom"])
     stats["tt2_k9_linear"] = frac_equal(tt(9, 0.3, "linear", 2, False), g["tt2_k9_linear"])
+
+    def tt_move(move_type):
+        import random
+        random.seed(21)                                  # oracle/make_golden.py: tt_move (video_attacks.py:107-135)
+        atk = video_attacks.TemporalTranslation(
+            synth.TinyTPNLike().cuda(), {"kernlen": 5, "momentum": True, "weight": 0.7, "move_type": move_type,
+                                         "kernel_mode": "random"}, steps=2)
+        return atk(v.clone(), labels)
+    stats["tt2_k5_large"] = frac_equal(tt_move("large"), g["tt2_k5_large"])
+    stats["tt2_k5_randommove"] = frac_equal(tt_move("random"), g["tt2_k5_randommove"])
     # kernlen 7 makes the reference's 5-way split produce an empty model batch (torch.cat([]) raises there): runs here
     adv7 = tt(7, 0.5, "gaussian", 1, True)
     _bounds_ok(g["videos"], adv7.cpu().numpy())

@@ -101,6 +101,58 @@ def test_adam_compose_bit_exact_over_steps(shape, inner, channels):
         assert (np.abs(mod) > EPS).any(), "test should drive some modifiers outside the eps ball"
 
 
+@pytest.mark.parametrize("foreach", [True, False])
+def test_adam_vs_torch_cuda_adam(foreach):
+    """K3a against the optimiser the reference really hits: `torch.optim.Adam([modifier], lr)` on CUDA
+    (image_attacks.py:306, `.cuda()` hard-coded at 304; torch picks the foreach path there).  Same gradients into both for
+    six steps (1e-9..1e-2 magnitudes, 5 % exact zeros).  The C oracle — and K3a, bit for bit — follows torch's CPU Adam
+    (tests/test_oracle_golden.py); torch's CUDA kernels group `addcmul` / `addcdiv` as a + alpha*(b*c) resp. a +
+    alpha*(b/c) with the compiler's FMA contraction, so the bar here is what two correct float32 Adams can differ by: m
+    and v within 1 ulp, the modifier within 2 ulp of its per-step increment scale, with the exact-agreement fractions
+    recorded (gpurun_out/parity_stats.json)."""
+    shape, inner = (4, 3, 56, 56), 56 * 56
+    rng = np.random.default_rng(9)
+    x01 = _rand01(shape, 10)
+    lr = 0.005
+    mod = torch.nn.Parameter(torch.full(shape, 0.01 / 255, device=DEV))
+    opt = torch.optim.Adam([mod], lr=lr, foreach=foreach)
+    d = dict(m=torch.zeros(shape, device=DEV), v=torch.zeros(shape, device=DEV), mod=torch.full(shape, 0.01 / 255, device=DEV),
+             x=gpu(x01), out=torch.empty(shape, device=DEV))
+    stats = {}
+    for step in range(1, 7):
+        g = (rng.standard_normal(shape) * 10.0 ** rng.uniform(-9, -2, size=shape)).astype(np.float32)
+        g[rng.random(shape) < 0.05] = 0.0
+        # K3a takes dcost/dtrue_image and applies the chain rule through compose (1/std, clamp masks) itself; hand torch
+        # the SAME dcost/dmodifier: inside the eps ball and away from the [0,1] borders it is g / std
+        std = np.asarray(O.STD, dtype=np.float32)[None, :, None, None]
+        modh = d["mod"].cpu().numpy()
+        ssum = x01 + np.clip(modh, -np.float32(EPS), np.float32(EPS))
+        live = (np.abs(modh) <= np.float32(EPS)) & (ssum >= 0) & (ssum <= 1)      # closed-interval clamp masks
+        gm = np.where(live, g / std, np.float32(0)).astype(np.float32)
+        mod.grad = gpu(gm)
+        opt.step()
+        capi.adam_compose(gpu(g), d["m"], d["v"], d["mod"], d["x"], d["out"], EPS, inner, step, lr)
+        st = opt.state[mod]
+        um = ulp_diff(d["m"].cpu().numpy(), st["exp_avg"].cpu().numpy())
+        uv = ulp_diff(d["v"].cpu().numpy(), st["exp_avg_sq"].cpu().numpy())
+        dm = np.abs(d["mod"].cpu().numpy().astype(np.float64) - mod.detach().cpu().numpy().astype(np.float64))
+        stats["step%d" % step] = dict(m_max_ulp=int(um.max()), v_max_ulp=int(uv.max()), m_equal=float((um == 0).mean()),
+                                      v_equal=float((uv == 0).mean()), mod_equal=float((dm == 0).mean()),
+                                      mod_max_abs=float(dm.max()))
+        assert um.max() <= 1 and uv.max() <= 1, (step, stats)
+        assert dm.max() <= step * 4 * lr * 2.0 ** -23, (step, stats)      # increments are <= ~lr: 2 ulp of lr per step
+        # keep both trajectories on the same state so that every step is an independent comparison
+        with torch.no_grad():
+            mod.copy_(d["mod"])
+            st["exp_avg"].copy_(d["m"])
+            st["exp_avg_sq"].copy_(d["v"])
+    import json
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "adam_vs_torch_cuda_%s.json" % ("foreach" if foreach else "single")), "w") as f:
+        json.dump(stats, f, indent=1, sort_keys=True)
+
+
 @pytest.mark.parametrize("shape,inner", [((2, 3, 4, 6, 6), 144), ((1, 3, 3, 5, 7), 105), ((3, 3, 8, 8), 64)])
 @pytest.mark.parametrize("project", [True, False])
 def test_sign_step_project_bit_exact(shape, inner, project):

@@ -85,6 +85,15 @@ def test_round_robin_shard_and_ensemble_placement():
     assert D.ensemble_placement(names, 6, 8) == ([2], 1)
     assert D.ensemble_placement(names, 1, 2) == ([1, 3], 0)
     assert D.ensemble_placement(names, 4, 5) == ([], None)
+    # ... which is why the plan refuses such a world: the idle rank would "attack" with no backbone at all
+    with pytest.raises(ValueError):
+        D.EnsemblePlan(names, [1, 1, 1, 1], rank=4, world=5)
+    with pytest.raises(ValueError):
+        D.EnsemblePlan(names, [2, 2, 2, 2], rank=0, world=6)
+    plan = D.EnsemblePlan(names, [2, 2, 2, 2], rank=6, world=8)
+    assert plan.members == [2] and plan.replica == 1 and plan.layer_offsets == [4] and plan.n_layers_total == 8 and plan.active
+    plan = D.EnsemblePlan(names, [1, 1, 1, 1], rank=1, world=2)
+    assert plan.members == [1, 3] and plan.layer_offsets == [1, 3]
 
 
 def test_loss_info_format():
@@ -183,6 +192,29 @@ def test_image_main_host_logic(tmp_path):
     assert torch.equal(batch[1:], v)
     with pytest.raises(ValueError):
         image_main.build_attack(image_main.arg_parse(["--attack_method", "nope"]))
+    # no silent substitutions: the default weight policy is the reference's `pretrained=True`, and without --synthetic
+    # the reference's data pipeline must really be importable
+    assert args.weights == os.environ.get("I2V_WEIGHTS", "pretrained") and not args.synthetic
+    with pytest.raises(SystemExit) as exc:
+        image_main.get_loader(args)
+    assert "--synthetic" in str(exc.value)
+
+
+def test_weight_policy_defaults_to_pretrained_and_records_the_source():
+    """image_attacks.py:86-98 hard-requires pretrained=True; so does the default policy — random init is an opt-in."""
+    saved = dict(backbones._WEIGHT_POLICY)
+    try:
+        backbones.set_weight_policy()
+        assert backbones._WEIGHT_POLICY["mode"] == "pretrained"
+        if backbones._pretrained_cached("squeezenet1_1") is None:
+            with pytest.raises(RuntimeError) as exc:
+                backbones.get_model("squeezenet", device=torch.device("cpu"))
+            assert "I2V_WEIGHTS=random" in str(exc.value)
+        backbones.set_weight_policy("random", 3)
+        backbones.get_model("squeezenet", device=torch.device("cpu"))
+        assert backbones.WEIGHT_SOURCE["squeezenet1_1"] == "random:seed=3"
+    finally:
+        backbones._WEIGHT_POLICY.update(saved)
 
 
 def test_temporal_translation_host_side():
@@ -251,6 +283,7 @@ def test_bench_reference_arm_contract():
     assert r["impl"] == "reference" and r["metric"] == "attack_frame_steps_per_sec" and r["unit"] == "frame-steps/s"
     assert r["higher_is_better"] is True and r["value"] > 0 and r["gpu_launches"] == 0 and r["vs_baseline"] is None
     assert r["cpu_baseline"]["kind"] in ("reference", "port") and r["cpu_baseline"]["cores"] >= 1
+    assert r["cpu_baseline"]["weight_grads"] is True and "kind=" + r["cpu_baseline"]["kind"] in r["cpu_baseline"]["sample"]
     assert r["e2e"] == {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in r["config"]
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")

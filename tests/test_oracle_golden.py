@@ -116,6 +116,48 @@ def test_i2v_loop_matches_reference(golden):
     _close_adv(adv, g["adv"])
 
 
+def test_port_with_weight_grads_is_the_same_loop(golden):
+    """bench.py's CPU arm runs the port with weight_grads=True (`cost.backward()`, every backbone parameter requiring grad,
+    image_attacks.py:351-353): same costs and adversarial clip bit for bit as the pruned-autograd variant the parity tests
+    use, and the weight gradients really are computed (the cost the reference pays)."""
+    g = golden("i2v_resnet50_d2_32")
+    hooked = _hooked(["resnet"], 2)
+    adv0, cost0, _, _ = OL.image_guided_loop(hooked, g["videos"], float(g["epsilon"]), 2, float(g["step_size"]))
+    assert hooked[0].model.conv1.weight.grad is None
+    hooked = _hooked(["resnet"], 2)
+    adv1, cost1, _, _ = OL.image_guided_loop(hooked, g["videos"], float(g["epsilon"]), 2, float(g["step_size"]), weight_grads=True)
+    assert np.array_equal(adv0, adv1) and np.array_equal(cost0, cost1)
+    wg = hooked[0].model.layer2[0].conv1.weight.grad
+    assert wg is not None and float(wg.abs().sum()) > 0
+
+
+def test_config1_60step_fixture_first_steps(golden):
+    """The benchmark-size fixture (32 frames x 3x224x224, 60 steps, unmodified reference class): the oracle port reproduces
+    its first two costs and the sign pattern of the first dcost/dmodifier (the port runs the same torch ops in the same
+    order, so the gradient is bit-identical; the later steps are pinned on the GPU side)."""
+    from i2v_b200 import synth
+    g = golden("i2v_resnet50_d2_224_60step")
+    assert g["cost"].shape == (60,) and g["delta16"].shape == (1, 3, 32, 224, 224)
+    assert np.abs(g["delta16"].astype(np.float32)).max() <= (16 / 255) / 0.224 * 1.001
+    videos, _ = synth.clip(0, b=1, f=int(g["frames"]), h=int(g["side"]), w=int(g["side"]))
+    hooked = _hooked(["resnet"], 2)
+    _check_weights(g, hooked)
+    taps = {}
+    _, cost, _, _ = OL.image_guided_loop(hooked, videos.numpy(), float(g["epsilon"]), 2, float(g["step_size"]),
+                                         tap=lambda i, d: taps.setdefault(i, d["g"].copy()))
+    assert np.allclose(cost, g["cost"][:2], rtol=1e-6)
+    gm = (taps[0] / O.STD[None, :, None, None]).reshape(-1)
+    n = gm.size
+    # the fixture holds dcost/dMODIFIER (zero where the [0,1] clamp is active, image_attacks.py:331); the port taps
+    # dcost/dtrue_image and leaves the clamp masks to the Adam block: compare where the clamp is inactive
+    x = O.denorm(OL._frames(videos).numpy(), int(g["side"]) ** 2).reshape(-1)
+    live = (x + np.float32(OL.INIT_MODIFIER) <= 1) & (x + np.float32(OL.INIT_MODIFIER) >= 0)
+    pos, neg = np.unpackbits(g["g_first_pos_bits"])[:n].astype(bool), np.unpackbits(g["g_first_neg_bits"])[:n].astype(bool)
+    assert live.mean() > 0.999 and not (pos | neg)[~live].any()
+    assert np.array_equal((gm > 0)[live], pos[live]) and np.array_equal((gm < 0)[live], neg[live])
+    assert abs(np.abs(gm[live]).max() / float(g["g_first_max"]) - 1) < 1e-6
+
+
 def test_i2v_vgg_loop_matches_reference(golden):
     g, adv, cost, _, _ = _loop_case(golden, "i2v_vgg_d3_32", ["vgg"], 3)
     assert np.allclose(cost, g["cost"], rtol=1e-6)
