@@ -164,7 +164,7 @@ def cpu_reference_rate(steps, frames=32, side=SIDE, budget_s=40.0):
         hooked = [OL.HookedModel(model, "resnet", DEPTH)]
         OL.image_guided_loop(hooked, videos.numpy(), EPS, steps, STEP_SIZE, weight_grads=True,
                              tap=lambda i, d: stamps.append(time.perf_counter()))
-        assert model.conv1.weight.grad is not None and model.layer4[-1].conv3.weight.grad is not None
+        assert model.conv1.weight.grad is not None and model.layer2[-1].conv3.weight.grad is not None   # layers up to the hook
     dt = (stamps[-1] - stamps[0]) / (len(stamps) - 1)
     return {"value": frames / dt, "unit": UNIT, "cores": cores, "threads": torch.get_num_threads(), "kind": kind,
             "ms_per_step": dt * 1e3, "weight_grads": True,
@@ -252,9 +252,8 @@ def cudnn_baselines(dev_videos, native_value):
     as_is     : comparison point (i) — the reference's loop as image_attacks.py:294-364 runs it on a GPU: FULL forward of
                 the torchvision model with a forward hook, F.cosine_similarity, `cost.backward()` with every weight
                 requiring grad, torch.optim.Adam on the modifier, `print(cost)`-style host sync every step; restated here
-                with torch ops only (no kernel of this repo on the path)."""
+                with torch ops only in tools/reference_on_gpu.py (no kernel of this repo on the path)."""
     import torch
-    import torch.nn.functional as F
     from i2v_b200 import attack_loop, backbones, engines
     out = {"unit": UNIT, "frames": int(dev_videos.shape[0] * dev_videos.shape[2]), "truncated_dgrad_only": {}, "as_is": {}}
     for name in ("cudnn", "cudnn_tf32", "cudnn_cl", "cudnn_tf32_cl"):
@@ -268,47 +267,14 @@ def cudnn_baselines(dev_videos, native_value):
 
     # ---- the reference loop as-is (4 clips = 128 frames: a full ResNet-50 autograd graph at 512 frames does not leave
     # room next to the rest of the bench; the reference's own usage is batch size 1, image_main.py:82-89) ------------
+    from tools import reference_on_gpu
     vids = dev_videos[:4]
-    b, c, f, h, w = vids.shape
-    mean = torch.tensor([0.485, 0.456, 0.406], device=vids.device).view(1, 3, 1, 1)
-    std = torch.tensor([0.229, 0.224, 0.225], device=vids.device).view(1, 3, 1, 1)
     for tag, tf32 in (("fp32", False), ("tf32", True)):
-        prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
-        torch.backends.cudnn.allow_tf32 = tf32
-        torch.backends.cuda.matmul.allow_tf32 = tf32
-        try:
-            model = backbones.seeded_random_init("resnet50", 0).to(vids.device)
-            model.train()
-            for m in model.modules():
-                if isinstance(m, (torch.nn.BatchNorm2d, torch.nn.BatchNorm1d)):
-                    m.eval()
-            acts = []
-            model.layer2[-1].register_forward_hook(lambda mod, i, o: acts.append(o))
-            image_inps = vids.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)
-            modifier = torch.nn.Parameter(torch.full((b * f, c, h, w), 0.01 / 255, device=vids.device))
-            opt = torch.optim.Adam([modifier], lr=STEP_SIZE)
-            unnorm = (image_inps * std + mean).detach()
-            model(image_inps)
-            init = acts.pop().detach()
-            times, cost_host = [], None
-            for i in range(6):
-                if i == 2:
-                    torch.cuda.synchronize(); t0 = time.perf_counter()
-                del acts[:]
-                true_image = torch.clamp(unnorm + torch.clamp(modifier, min=-EPS, max=EPS), min=0, max=1)
-                true_image = (true_image - mean) / std
-                model(true_image)
-                cost = torch.sum(F.cosine_similarity(acts[0].view(b * f, -1), init.view(b * f, -1)))
-                opt.zero_grad()
-                cost.backward()
-                opt.step()
-                cost_host = float(cost.detach().cpu())          # the reference prints the cost every step
-            torch.cuda.synchronize()
-            ms = (time.perf_counter() - t0) * 1e3 / 4
-            out["as_is"][tag] = {"value": b * f / (ms * 1e-3), "ms_per_step": ms, "frames": b * f, "final_cost": cost_host}
-            del model, modifier, opt, acts, init, cost, true_image
-        finally:
-            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+        r = reference_on_gpu.run(vids, 6, STEP_SIZE, EPS, tf32=tf32, timed_from=2)
+        nfr = int(vids.shape[0] * vids.shape[2])
+        out["as_is"][tag] = {"value": nfr / (r["ms_per_step"] * 1e-3), "ms_per_step": r["ms_per_step"], "frames": nfr,
+                             "final_cost": float(r["cost"][-1])}
+        del r
         torch.cuda.empty_cache()
     best_fp32 = max(v["value"] for k, v in out["truncated_dgrad_only"].items() if "tf32" not in k)
     best_tf32 = max(v["value"] for k, v in out["truncated_dgrad_only"].items() if "tf32" in k)

@@ -108,6 +108,12 @@ class ImageGuidedRun:
                 off += e.num_layers
         self.layer_offsets = list(layer_offsets)
         self.owned_rows = sorted(o + k for o, e in zip(self.layer_offsets, self.engines) for k in range(e.num_layers))
+        # CUDA-graph replay of the step (see step()): needs engines whose step is a fixed launch sequence on fixed
+        # buffers (the native ones), no per-step host work (tap) and no collective inside the step; $I2V_GRAPH=0 disables
+        self.use_graph = (os.environ.get("I2V_GRAPH", "1") != "0" and tap is None and reduce_hook is None
+                          and bool(self.engines) and all(getattr(e, "graph_safe", False) for e in self.engines))
+        self._graph = None
+        self._graph_launches = {}
         if adaptive and (coeffs is None or coeffs.numel() != self.n_layers):
             raise ValueError("adaptive mode needs a coeffs tensor with one entry per hooked layer (%d)" % self.n_layers)
         self.step_no = 0
@@ -140,7 +146,9 @@ class ImageGuidedRun:
         for e in self.engines:
             per_layer = None
             for (s0, s1) in self.spans:
-                fe = e.features(frames[s0:s1], need_grad=False)
+                # native engines hand out views of their reusable buffers (clone=False): one copy into the per-call store
+                fe = e.features(frames[s0:s1], need_grad=False, clone=False) if getattr(e, "relu_masked_grads", None) is not None \
+                    and hasattr(e, "_plan") else e.features(frames[s0:s1], need_grad=False)
                 if per_layer is None:
                     per_layer = [torch.empty((N,) + tuple(t.shape[1:]), device=device, dtype=torch.float32) for t in fe]
                 for dst, t in zip(per_layer, fe):
@@ -166,8 +174,30 @@ class ImageGuidedRun:
         return self
 
     def step(self):
+        """One attack step.  Step 0 runs eagerly (the engines size their buffers on first use); when nothing needs the
+        host inside the step (no tap, no collective, no per-kernel profiling) step 1 is captured into a CUDA graph —
+        every launch of the step, all chunks — and steps 1.. are replays of it: the device step counter and the Adam
+        scalar table (K3a) make the step body iteration-invariant."""
         if self.step_no >= self.steps:
             raise RuntimeError("all %d steps of this run are done" % self.steps)
+        if self._graph is not None and capi.PROFILE_EVENTS is None:
+            self._graph.replay()
+            for k, v in self._graph_launches.items():
+                capi.LAUNCHES[k] = capi.LAUNCHES.get(k, 0) + v
+        elif (self.use_graph and self._graph is None and self.step_no >= 1 and self.steps - self.step_no >= 2
+              and capi.PROFILE_EVENTS is None):
+            before = dict(capi.LAUNCHES)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                self._step_body()
+            self._graph_launches = {k: v - before.get(k, 0) for k, v in capi.LAUNCHES.items() if v != before.get(k, 0)}
+            self._graph = graph
+            graph.replay()                       # capture only records: this replay IS the step
+        else:
+            self._step_body()
+        self.step_no += 1
+
+    def _step_body(self):
         adaptive = self.adaptive
         if adaptive:
             capi.layer_reweight(self.coeffs, self.prev, self.momentum, self.w_out, self.weights_log, self.step_idx)
@@ -185,6 +215,9 @@ class ImageGuidedRun:
                                           relu_mask=e.relu_masked_grads)
                     gviews.append(gv)
                     layer += 1
+                if ei == 0 and getattr(e, "writes_input_grad_in_place", False):
+                    e.input_grad(gviews, out=self.g_total[s0:s1])      # the first-layer data gradient lands in place
+                    continue
                 g = e.input_grad(gviews)
                 if ei == 0:
                     self.g_total[s0:s1].copy_(g)
@@ -207,7 +240,6 @@ class ImageGuidedRun:
         capi.adam_compose_table(self.g_total, self.m, self.v, self.mod, self.x, self.true_img, self.epsilon, self.inner,
                                 self.table, self.step_idx, BETA1, BETA2, ADAM_EPS)
         capi.step_advance(self.step_idx)
-        self.step_no += 1
 
     def finish(self):
         # `true_img` holds (clamp(x + clamp(mod, ±eps), 0, 1) - mean)/std for the final modifier, which is

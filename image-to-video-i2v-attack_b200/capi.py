@@ -28,6 +28,8 @@ SIGNATURES = {
     "i2v_compose_norm_f32": ([_c_p, _c_p, _c_p, _c_i64, _c_i64, _c_int, _c_f, _c_p], _c_int),
     "i2v_fill_f32": ([_c_p, _c_f, _c_i64, _c_p], _c_int),
     "i2v_adam_compose_f32": ([_c_p] * 6 + [_c_i64, _c_i64, _c_int, _c_f, _c_d, _c_d, _c_d, _c_d, _c_int, _c_p], _c_int),
+    "i2v_set_adam_arithmetic": ([_c_int], _c_int),
+    "i2v_get_adam_arithmetic": ([], _c_int),
     "i2v_adam_step_table": ([_c_p, _c_int, _c_d, _c_d, _c_d], _c_int),
     "i2v_adam_compose_table_f32": ([_c_p] * 6 + [_c_i64, _c_i64, _c_int, _c_f, _c_f, _c_f, _c_f, _c_f, _c_p, _c_p, _c_p], _c_int),
     "i2v_step_advance": ([_c_p, _c_p], _c_int),
@@ -71,6 +73,9 @@ SIGNATURES = {
     "i2v_maxpool_fwd_flags_f32": ([_c_p, _c_p, _c_p] + [_c_int] * 10 + [_c_p], _c_int),
     "i2v_maxpool_bwd_f32": ([_c_p, _c_p, _c_p, _c_p] + [_c_int] * 10 + [_c_p], _c_int),
     "i2v_copy_channels_f32": ([_c_p, _c_p, _c_i64] + [_c_int] * 6 + [_c_p], _c_int),
+    "i2v_bn_relu_f32": ([_c_p, _c_i64, _c_int, _c_int, _c_int, _c_p, _c_p, _c_p, _c_p], _c_int),
+    "i2v_avgpool2_fwd_f32": ([_c_p, _c_p] + [_c_int] * 6 + [_c_p], _c_int),
+    "i2v_avgpool2_bwd_f32": ([_c_p, _c_p] + [_c_int] * 6 + [_c_p], _c_int),
 }
 
 EPI_RELU = 1
@@ -112,7 +117,7 @@ def load():
 # tensors read + written once, 2 x MACs of the convolution).
 LAUNCHES = {}
 PROFILE_EVENTS = None
-_NO_KERNEL = ("i2v_conv_stem_fwd_direct_supported", "i2v_conv_stem_fwd_direct_scratch_floats", "i2v_conv_stem_dgrad_tc_rows", "i2v_device_check", "i2v_std_workspace_doubles", "i2v_ila_workspace_doubles", "i2v_adam_step_table", "i2v_conv_tc_supported", "i2v_conv_stem_supported",
+_NO_KERNEL = ("i2v_set_adam_arithmetic", "i2v_conv_stem_fwd_direct_supported", "i2v_conv_stem_fwd_direct_scratch_floats", "i2v_conv_stem_dgrad_tc_rows", "i2v_device_check", "i2v_std_workspace_doubles", "i2v_ila_workspace_doubles", "i2v_adam_step_table", "i2v_conv_tc_supported", "i2v_conv_stem_supported",
               "i2v_conv_tc_set_trace")
 
 
@@ -204,6 +209,18 @@ def adam_compose(g, m, v, mod, x, next_img, eps, inner, step, lr, beta1=0.9, bet
     _check(load().i2v_adam_compose_f32(_dev(g), _dev(m), _dev(v), _dev(mod), _dev(x), _dev(next_img), g.numel(), inner,
                                        channels, eps, lr, beta1, beta2, adam_eps, step, _stream()),
            "i2v_adam_compose_f32")
+
+
+def set_adam_arithmetic(which):
+    """'cuda' (default): K3a reproduces torch's CUDA foreach Adam bit for bit — the optimiser the reference hits;
+    'cpu': torch's CPU Adam, the arithmetic of the committed CPU fixtures and of oracle.adam_compose(arith='cpu')."""
+    if which not in ("cuda", "cpu"):
+        raise ValueError("adam arithmetic must be 'cuda' or 'cpu', got %r" % (which,))
+    _check(load().i2v_set_adam_arithmetic(1 if which == "cuda" else 0), "i2v_set_adam_arithmetic")
+
+
+def get_adam_arithmetic():
+    return "cuda" if load().i2v_get_adam_arithmetic() else "cpu"
 
 
 def adam_step_table(steps, lr, beta1=0.9, beta2=0.999):
@@ -540,3 +557,26 @@ def copy_channels(src, dst, src_off, dst_off, ccopy, accumulate=False):
     M = src.numel() // src.shape[-1]
     _check(load().i2v_copy_channels_f32(_dev(src), _dev(dst), M, src.shape[-1], src_off, dst.shape[-1], dst_off, ccopy,
                                         int(accumulate), _stream()), "i2v_copy_channels_f32")
+
+
+# ------------------------------------------------------------------------------- DenseNet pieces
+def bn_relu(src, C, scale, shift, dst):
+    """dst [M, Cp] = relu(scale * src[:, :C] + shift) (zero for channels C..Cp-1); src is [M, src_ld] with src_ld >= C."""
+    M = src.numel() // src.shape[-1]
+    with _Timed("i2v_bn_relu_f32", 4 * M * (C + dst.shape[-1])):
+        _check(load().i2v_bn_relu_f32(_dev(src), M, C, dst.shape[-1], src.shape[-1], _dev(scale), _dev(shift), _dev(dst),
+                                      _stream()), "i2v_bn_relu_f32")
+
+
+def avgpool2_fwd(x, y, dst_off=0):
+    """x [N,H,W,C] -> y[..., dst_off : dst_off+C] of y [N,H//2,W//2,dst_ld] (2x2 / stride 2, floor mode)."""
+    N, H, W, C = x.shape
+    with _Timed("i2v_avgpool2_fwd_f32", 4 * x.numel() + x.numel()):
+        _check(load().i2v_avgpool2_fwd_f32(_dev(x), _dev(y), N, H, W, C, y.shape[-1], dst_off, _stream()), "i2v_avgpool2_fwd_f32")
+
+
+def avgpool2_bwd(dy, dx, src_off=0):
+    """dx [N,H,W,C] = the gradient of avgpool2_fwd given dy[..., src_off : src_off+C] of dy [N,H//2,W//2,src_ld]."""
+    N, H, W, C = dx.shape
+    with _Timed("i2v_avgpool2_bwd_f32", 4 * dx.numel() + dx.numel()):
+        _check(load().i2v_avgpool2_bwd_f32(_dev(dy), _dev(dx), N, H, W, C, dy.shape[-1], src_off, _stream()), "i2v_avgpool2_bwd_f32")

@@ -12,6 +12,7 @@
 // so the compiler can neither contract nor reassociate; results are bit-identical to
 // oracle/i2v_oracle.c for any grid size.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace i2v {
 
@@ -85,6 +86,7 @@ struct AdamScalars {
     float adam_eps;  // f32(1e-8)
     float bc2_sqrt;  // f32(sqrt(1 - beta2^t))
     float neg_ss;    // f32(-lr / (1 - beta1^t))
+    int cuda_arith;  // 1: torch's CUDA (foreach) Adam kernels, 0: torch's CPU Adam kernels (i2v_set_adam_arithmetic)
 };
 
 __device__ __forceinline__ void adam1(float g, float& m, float& v, float& mod, float x, float& out,
@@ -96,9 +98,19 @@ __device__ __forceinline__ void adam1(float g, float& m, float& v, float& mod, f
     bool inside = (sum >= 0.0f) && (sum <= 1.0f) && (mod >= -eps) && (mod <= eps);
     float gm = __fmul_rn(__fdiv_rn(g, sd), inside ? 1.0f : 0.0f);
     float m2 = __fmaf_rn(s.w1, __fsub_rn(gm, m), m);
-    float v2 = __fmaf_rn(__fmul_rn(s.a2, gm), gm, __fmul_rn(v, s.beta2));
-    float den = __fadd_rn(__fdiv_rn(__fsqrt_rn(v2), s.bc2_sqrt), s.adam_eps);
-    float mod2 = __fadd_rn(mod, __fdiv_rn(__fmul_rn(s.neg_ss, m2), den));
+    // The two torch back ends group addcmul_ / addcdiv_ differently (probed bit for bit: tools/adam_cuda_probe.py,
+    // profiles/r02_adam_cuda_probe.json).  CUDA (what the reference runs, `.cuda()` is hard-coded at image_attacks.py:304):
+    //   v = fma(a2, g*g, v*b2);  mod = fma(-ss, m / den, mod)     CPU:  v = fma(a2*g, g, v*b2);  mod = mod + (-ss*m) / den
+    float v2, mod2;
+    if (s.cuda_arith) {
+        v2 = __fmaf_rn(s.a2, __fmul_rn(gm, gm), __fmul_rn(v, s.beta2));
+        float den = __fadd_rn(__fdiv_rn(__fsqrt_rn(v2), s.bc2_sqrt), s.adam_eps);
+        mod2 = __fmaf_rn(s.neg_ss, __fdiv_rn(m2, den), mod);
+    } else {
+        v2 = __fmaf_rn(__fmul_rn(s.a2, gm), gm, __fmul_rn(v, s.beta2));
+        float den = __fadd_rn(__fdiv_rn(__fsqrt_rn(v2), s.bc2_sqrt), s.adam_eps);
+        mod2 = __fadd_rn(mod, __fdiv_rn(__fmul_rn(s.neg_ss, m2), den));
+    }
     m = m2; v = v2; mod = mod2;
     out = compose1(x, mod2, eps, c);
 }
@@ -442,6 +454,23 @@ extern "C" int i2v_fill_f32(float* p, float value, int64_t n, i2v_stream_t strea
     return I2V_OK;
 }
 
+// Which of torch's two Adam arithmetics K3a reproduces bit for bit: 1 (default) = the CUDA foreach kernels the reference
+// hits, 0 = the CPU kernels the committed fixtures were generated with.  $I2V_ADAM_ARITH=cpu|cuda sets the initial value.
+static int g_adam_cuda_arith = -1;
+static int adam_cuda_arith() {
+    if (g_adam_cuda_arith < 0) {
+        const char* e = getenv("I2V_ADAM_ARITH");
+        g_adam_cuda_arith = (e && e[0] == 'c' && e[1] == 'p') ? 0 : 1;
+    }
+    return g_adam_cuda_arith;
+}
+extern "C" int i2v_set_adam_arithmetic(int cuda_arith) {
+    I2V_REQUIRE(cuda_arith == 0 || cuda_arith == 1, "adam arithmetic must be 0 (torch CPU kernels) or 1 (torch CUDA kernels)");
+    g_adam_cuda_arith = cuda_arith;
+    return I2V_OK;
+}
+extern "C" int i2v_get_adam_arithmetic(void) { return adam_cuda_arith(); }
+
 // The step scalars are formed exactly as torch.optim.adam._single_tensor_adam does for python-float
 // hyper-parameters: double arithmetic on the host, rounded to f32 when they meet the f32 tensor.
 static void adam_step_scalars(double lr, double beta1, double beta2, int step, float* bc2_sqrt, float* neg_ss) {
@@ -486,6 +515,7 @@ extern "C" int i2v_adam_compose_f32(const float* g, float* m, float* v, float* m
     s.beta2 = (float)beta2;
     s.a2 = (float)(1.0 - beta2);
     s.adam_eps = (float)adam_eps;
+    s.cuda_arith = adam_cuda_arith();
     adam_step_scalars(lr, beta1, beta2, step, &s.bc2_sqrt, &s.neg_ss);
     return adam_launch<false>(g, m, v, mod, x, next_img, n, inner, channels, eps, s, nullptr, nullptr, as_stream(stream));
 }
@@ -498,7 +528,7 @@ extern "C" int i2v_adam_compose_table_f32(const float* g, float* m, float* v, fl
     if (n == 0) return I2V_OK;
     I2V_REQUIRE(m && v && mod && x && next_img && step_table && step_idx, "null state pointer");
     I2V_REQUIRE(aligned16(m) && aligned16(v) && aligned16(mod) && aligned16(x) && aligned16(next_img), "state pointers must be 16-byte aligned");
-    AdamScalars s{w1, beta2, a2, adam_eps, 0.f, 0.f};
+    AdamScalars s{w1, beta2, a2, adam_eps, 0.f, 0.f, adam_cuda_arith()};
     return adam_launch<true>(g, m, v, mod, x, next_img, n, inner, channels, eps, s, step_table, step_idx, as_stream(stream));
 }
 

@@ -16,8 +16,8 @@ taken from it, so random-init / pretrained policies of backbones.py apply unchan
     Conv(x -> y, folded weights, relu, residual)     MaxPool(x -> y)     Concat(xs -> y)   (Fire)
 
 Supported families: resnet (Bottleneck nets), vgg, alexnet, squeezenet — every hook point of
-reference image_attacks.py:260-271 and TPAMI_attack.py:176-200.  DenseNet (BN-ReLU-Conv ordering,
-average pooling) is not implemented here and raises; use engine='cudnn' for it.
+reference image_attacks.py:260-271 and TPAMI_attack.py:176-200.  DenseNet (BN-ReLU-Conv ordering, dense
+concatenation, average pooling) has its own engine on the same kernels: engine_densenet.DenseNetEngine.
 
 Kernel selection per conv: the tcgen05 tensor-core implicit GEMM (conv_tc.cu) when it supports the
 shape, otherwise the CUDA-core gather-GEMM (conv_simt.cu).  `tf32x3=True` (default, "FP32 parity
@@ -279,6 +279,8 @@ def _build_sequential(features, targets):
 class NativeEngine:
     relu_masked_grads = True    # K1 applies 1[feature > 0]: gradients are kept pre-activation
     preferred_chunk = 128       # fallback when the image size is not known (see frames_per_chunk)
+    graph_safe = True           # a step is a fixed sequence of launches on buffers that live as long as the engine
+    writes_input_grad_in_place = True   # input_grad(grads, out=...)
 
     def __init__(self, model, model_name, depth, tf32x3=True, use_tensor_cores=None):
         self.model = backbones.freeze_for_attack(model)
@@ -290,8 +292,9 @@ class NativeEngine:
         elif fam in ("vgg", "alexnet", "squeezenet"):
             self.ops, hooks, self.chans, self.relu_typed = _build_sequential(model.features, self.targets)
         else:
-            raise NotImplementedError("the native engine does not implement the %s family (pre-activation BN, average "
-                                      "pooling); use engine='cudnn'" % fam)
+            raise NotImplementedError("NativeEngine builds Conv / MaxPool / Concat graphs; the %s family (pre-activation "
+                                      "BN, average pooling) is engine_densenet.DenseNetEngine — engines.make_engine picks "
+                                      "it" % fam)
         # hook buffers in reference order = forward execution order of the target modules
         self.hook_bufs = [hooks[id(t)] for t in self.targets]
         order = {op.y: i for i, op in enumerate(self.ops)}
@@ -434,7 +437,9 @@ class NativeEngine:
         else:
             capi.conv_dgrad_simt(d, dy, op.b_dgrad, addend, mask_src, dx, x_nchw=op.x_nchw)
 
-    def features(self, img, need_grad):
+    def features(self, img, need_grad, clone=True):
+        """Hooked feature maps of `img` (NHWC views of this engine's reusable buffers when need_grad, or when the caller
+        passes clone=False and copies them out itself before the next call)."""
         n, c, h, w = img.shape
         if c != 3 or not img.is_contiguous():
             raise ValueError("expected a contiguous [n,3,H,W] image batch")
@@ -458,7 +463,7 @@ class NativeEngine:
         self._last_fwd = plan
         feats = [acts[b] for b in self.hook_bufs]
         # clean features are kept by the caller across the whole attack: hand out copies, the plan's buffers are reused
-        return [f.clone() for f in feats] if not need_grad else feats
+        return [f.clone() for f in feats] if (not need_grad and clone) else feats
 
     def relu_masks(self):
         """Activity masks 1[activation > 0] of every ReLU of the last forward, in the torch module's ReLU call
@@ -496,10 +501,15 @@ class NativeEngine:
         return out
 
     # ---- backward ------------------------------------------------------------------------------------
-    def input_grad(self, grads):
+    def input_grad(self, grads, out=None):
+        """dcost/dimg [n,3,H,W] given dcost/dfeat of every hooked layer; written into `out` when given (the attack loop
+        passes its slice of the batch-wide gradient, so no copy follows), else into this engine's own buffer."""
         plan = self._last
         if plan is None:
             raise RuntimeError("input_grad() needs a preceding features(..., need_grad=True)")
+        gimg = plan["gimg"] if out is None else out
+        if gimg.shape != plan["gimg"].shape or not gimg.is_contiguous():
+            raise ValueError("out must be a contiguous %s tensor" % (tuple(plan["gimg"].shape),))
         acts = plan["acts"]
         G = dict(plan["grads"])
         ready = set()
@@ -528,7 +538,7 @@ class NativeEngine:
                         G[r] = gy                         # pre-activation shortcut (downsample output): same gradient
                         ready.add(r)
                 if op.x == "img":
-                    dx, mask = plan["gimg"], None
+                    dx, mask = gimg, None
                 else:
                     dx, mask = G[op.x], (acts[op.x] if op.x in self.relu_typed else None)
                 addend = None
@@ -559,4 +569,4 @@ class NativeEngine:
                         ready.add(xn)
                     off += self.chans[xn]
         self._last = None
-        return plan["gimg"]
+        return gimg

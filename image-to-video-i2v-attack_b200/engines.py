@@ -26,5 +26,9 @@ def make_engine(model, model_name, depth, engine=None):
     if name.startswith("cudnn"):
         from .engine_cudnn import CudnnEngine
         return CudnnEngine(model, model_name, depth, allow_tf32="tf32" in name, channels_last=name.endswith("_cl"))
+    from . import backbones
+    if backbones.family_of(model_name) == "densenet":
+        from .engine_densenet import DenseNetEngine
+        return DenseNetEngine(model, model_name, depth, tf32x3=not name.endswith("tf32"))
     from .engine_native import NativeEngine
     return NativeEngine(model, model_name, depth, tf32x3=not name.endswith("tf32"))

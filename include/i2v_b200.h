@@ -70,10 +70,15 @@ int i2v_fill_f32(float* p, float value, int64_t n, i2v_stream_t stream);
  * Arithmetic (every op one f32 rounding; `fma` = fused):
  *   gm   = (g / std_c) * 1[0 <= x+clamp(mod) <= 1] * 1[-eps <= mod <= eps]   autograd of 331-332
  *   m    = fma(f32(1-beta1), gm - m, m)                                      torch.optim.Adam lerp_
- *   v    = fma(f32(1-beta2)*gm, gm, v*f32(beta2))                            mul_ + addcmul_
+ *   v    = fma(f32(1-beta2), gm*gm, v*f32(beta2))                            mul_ + addcmul_      [CUDA arithmetic]
  *   den  = sqrt(v) / f32(sqrt(1-beta2^step)) + f32(adam_eps)
- *   mod  = mod + (f32(-lr/(1-beta1^step)) * m) / den                         addcdiv_
- * replaces image_attacks.py:351-353 (+331-332 of the next iteration); `step` is 1-based.          */
+ *   mod  = fma(f32(-lr/(1-beta1^step)), m / den, mod)                        addcdiv_             [CUDA arithmetic]
+ * replaces image_attacks.py:351-353 (+331-332 of the next iteration); `step` is 1-based.
+ * torch's CPU kernels group the last two differently — v = fma(f32(1-beta2)*gm, gm, v*beta2), mod = mod + (ss*m)/den —
+ * and K3a reproduces either bit for bit: i2v_set_adam_arithmetic(1) = torch's CUDA foreach Adam (default: the reference
+ * hard-codes .cuda(), image_attacks.py:304), 0 = torch's CPU Adam (what the committed CPU fixtures were made with).   */
+int i2v_set_adam_arithmetic(int cuda_arith);
+int i2v_get_adam_arithmetic(void);
 int i2v_adam_compose_f32(const float* g, float* m, float* v, float* mod, const float* x,
                          float* next_img, int64_t n, int64_t inner, int channels, float eps,
                          double lr, double beta1, double beta2, double adam_eps, int step,
@@ -325,6 +330,18 @@ int i2v_maxpool_fwd_flags_f32(const float* x, float* y, uint8_t* argmax, int N, 
 int i2v_maxpool_bwd_f32(const float* dy, const uint8_t* argmax, const float* mask_src, float* dx, int N, int H,
                         int W, int C, int P, int Q, int k, int stride, int pad, int flags,
                         i2v_stream_t stream);
+
+/* DenseNet (reference image_attacks.py:95-98 constructs it; hook `features.denseblock{d}`).
+ * Pre-activation: dst[m, c] = max(0, scale[c]*src[m*src_ld + c] + shift[c]) for c < C, 0 for C <= c < Cp — eval-mode
+ * BatchNorm (scale = gamma/sqrt(var+eps), shift = beta - mean*scale) + ReLU of the first C channels of a concat buffer
+ * with row pitch src_ld, written densely as [M, Cp] (torchvision densenet._DenseLayer.norm1/relu1, _Transition.norm/relu).
+ * All channel counts are multiples of 4.                                                                        */
+int i2v_bn_relu_f32(const float* src, int64_t M, int C, int Cp, int src_ld, const float* scale, const float* shift,
+                    float* dst, i2v_stream_t stream);
+/* 2x2 / stride-2 average pooling of a transition (floor mode), NHWC: forward writes channels [dst_off, dst_off+C) of
+ * rows with pitch dst_ld (the next block's concat buffer); backward reads such a slice and writes dx [N,H,W,C] densely. */
+int i2v_avgpool2_fwd_f32(const float* x, float* y, int N, int H, int W, int C, int dst_ld, int dst_off, i2v_stream_t stream);
+int i2v_avgpool2_bwd_f32(const float* dy, float* dx, int N, int H, int W, int C, int src_ld, int src_off, i2v_stream_t stream);
 
 /* dst[m, dst_off : dst_off+Ccopy] (=|+=) src[m, src_off : src_off+Ccopy] — channel concat of SqueezeNet's
  * Fire modules (torch.cat([expand1x1, expand3x3], 1)) and its backward split.                        */

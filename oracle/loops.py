@@ -35,6 +35,11 @@ def target_layers(model, family, depth):
         if is_list:
             return [model.features[table[d]] for d in ds]
         return [model.features[table[ds[0]]].expand3x3_activation]
+    if family == "densenet":
+        # NOT in the reference (its _find_target_layer has no DenseNet branch and would crash): the
+        # extension this repo defines — depth d hooks features.denseblock{d} — restated here so that the float64
+        # arbiter can check the native DenseNet engine
+        return [getattr(model.features, "denseblock{}".format(d)) for d in ds]
     raise ValueError(family)
 
 

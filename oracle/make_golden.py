@@ -210,6 +210,35 @@ def run_config1_60step(ref, frames=32, side=224, steps=60, step_size=0.005):
             "g_first_big_bits": np.packbits(np.abs(g.reshape(-1)) > 1e-3 * gmax)}
 
 
+def add_float64_arbiter(path, frames=32, side=224):
+    """Adds the float64 arbiter of the FIRST step to the 60-step fixture: dcost/dtrue_image of image_attacks.py:334-352 for
+    the step-1 true_image (x + 0.01/255, clamped, normalised) evaluated by torch autograd in float64 on the CPU
+    (oracle.loops.teacher_forced_grad) — sign bits, the |g| > 1e-3 max mask and max |g|, of dcost/dmodifier = g / std.
+    At this size the reference's own float32 gradient is ~10 % (relative L2) away from it (the cosine's f32 sums), so
+    the arbiter, not the reference, is what a more accurate implementation can be held to."""
+    from oracle import loops as OL
+    from oracle import oracle as O
+    from i2v_b200 import backbones
+    rec = dict(np.load(path))
+    videos, _ = synth.clip(0, b=1, f=frames, h=side, w=side)
+    fr = OL._frames(videos)
+    x = O.denorm(fr.numpy(), side * side)
+    ti = O.compose_norm(x, np.full_like(x, np.float32(OL.INIT_MODIFIER)), 16 / 255, side * side)
+    hooked = [OL.HookedModel(backbones.seeded_random_init("resnet50", 0), "resnet", 2)]
+    _, g64, _ = OL.teacher_forced_grad(hooked, fr, ti, torch.float64)
+    gm = (g64 / O.STD[None, :, None, None].astype(np.float64)).reshape(-1)
+    gmax = np.abs(gm).max()
+    rec["g64_first_max"] = np.float64(gmax)
+    rec["g64_first_pos_bits"] = np.packbits(gm > 0)
+    rec["g64_first_big_bits"] = np.packbits(np.abs(gm) > 1e-3 * gmax)
+    n = gm.size
+    pos = np.unpackbits(rec["g_first_pos_bits"])[:n].astype(bool)
+    big = np.abs(gm) > 1e-3 * gmax
+    rec["ref_vs_f64_sign_agreement_big"] = np.float64(((gm > 0) == pos)[big].mean())
+    np.savez_compressed(path, **rec)
+    print("float64 arbiter added: reference-vs-float64 step-1 sign agreement %.5f" % rec["ref_vs_f64_sign_agreement_big"])
+
+
 def main():
     torch.set_num_threads(THREADS)
     os.makedirs(OUT, exist_ok=True)
@@ -240,6 +269,8 @@ def main():
         path = os.path.join(OUT, name + ".npz")
         np.savez_compressed(path, **rec)
         print("%-24s %8.1f KB" % (name, os.path.getsize(path) / 1024))
+        if name == "i2v_resnet50_d2_224_60step":
+            add_float64_arbiter(path)
 
 
 if __name__ == "__main__":

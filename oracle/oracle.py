@@ -72,13 +72,15 @@ def compose_norm(x, mod, eps, inner, channels=3):
     return out
 
 
-def adam_compose(g, m, v, mod, x, eps, inner, step, lr, beta1=0.9, beta2=0.999, adam_eps=1e-8, channels=3):
-    """In-place on copies; returns (m, v, mod, next_img)."""
+def adam_compose(g, m, v, mod, x, eps, inner, step, lr, beta1=0.9, beta2=0.999, adam_eps=1e-8, channels=3, arith="cpu"):
+    """In-place on copies; returns (m, v, mod, next_img).  arith: 'cpu' = torch's CPU Adam kernels (what the CPU fixtures
+    were generated with), 'cuda' = torch's CUDA foreach Adam kernels (what the reference hits on its own platform)."""
     g, x = _f32(g), _f32(x)
     m, v, mod = _f32(m).copy(), _f32(v).copy(), _f32(mod).copy()
     out = np.empty_like(x)
     lib().oracle_adam_compose_f32(_ptr(g), _ptr(m), _ptr(v), _ptr(mod), _ptr(x), _ptr(out), i64(x.size), i64(inner),
-                                  ci(channels), cf(eps), cd(lr), cd(beta1), cd(beta2), cd(adam_eps), ci(step))
+                                  ci(channels), cf(eps), cd(lr), cd(beta1), cd(beta2), cd(adam_eps), ci(step),
+                                  ci(1 if arith == "cuda" else 0))
     return m, v, mod, out
 
 

@@ -142,9 +142,34 @@ def test_copy_channels():
     assert torch.equal(back, b + 1)
 
 
+def test_bn_relu_and_avgpool2():
+    """The DenseNet pieces (csrc/dense.cu) against their torch statements: pre-activation BatchNorm(eval) + ReLU of a
+    channel prefix of a concat buffer (zero-padded dense output), 2x2 average pooling into / out of a channel slice."""
+    g = torch.Generator().manual_seed(3)
+    cat = torch.randn(3, 5, 7, 96, generator=g).to(DEV)
+    scale = (torch.rand(64, generator=g) + 0.5).to(DEV)
+    shift = torch.randn(64, generator=g).to(DEV)
+    t = torch.full((3, 5, 7, 128), float("nan"), device=DEV)
+    capi.bn_relu(cat, 64, scale, shift, t)
+    want = torch.relu(torch.addcmul(shift, cat[..., :64], scale))
+    assert torch.allclose(t[..., :64], want, rtol=1e-6, atol=1e-7) and torch.equal(t[..., 64:], torch.zeros_like(t[..., 64:]))
+    x = torch.randn(2, 7, 6, 32, generator=g).to(DEV)                    # odd height: floor mode drops the last row
+    y = torch.zeros(2, 3, 3, 80, device=DEV)
+    capi.avgpool2_fwd(x, y, dst_off=16)
+    ref = torch.nn.functional.avg_pool2d(x.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
+    assert torch.allclose(y[..., 16:48], ref, rtol=1e-6, atol=1e-7)
+    assert torch.equal(y[..., :16], torch.zeros_like(y[..., :16])) and torch.equal(y[..., 48:], torch.zeros_like(y[..., 48:]))
+    dy = torch.randn(2, 3, 3, 80, generator=g).to(DEV)
+    dx = torch.full_like(x, float("nan"))
+    capi.avgpool2_bwd(dy, dx, src_off=16)
+    xr = x.clone().requires_grad_(True)
+    torch.nn.functional.avg_pool2d(xr.permute(0, 3, 1, 2), 2, 2).backward(dy[..., 16:48].permute(0, 3, 1, 2))
+    assert torch.allclose(dx, xr.grad, rtol=1e-6, atol=1e-7)
+
+
 ENGINE_CASES = [("resnet", 2, 64), ("resnet", [1, 2], 64), ("resnet", 3, 64), ("vgg", 3, 32), ("vgg", [2, 3], 32),
                 ("alexnet", 3, 64), ("alexnet", [2, 3], 64), ("squeezenet", 2, 64), ("squeezenet", [2, 3], 64),
-                ("squeezenet", 4, 64)]
+                ("squeezenet", 4, 64), ("densenet", 1, 64), ("densenet", [2, 3], 64), ("densenet161", 2, 64)]
 
 
 @pytest.mark.parametrize("name,depth,side", ENGINE_CASES)
@@ -157,7 +182,11 @@ def test_native_engine_matches_autograd(name, depth, side, mode):
     g = torch.Generator().manual_seed(7)
     img = torch.randn(3, 3, side, side, generator=g)
     model = backbones.get_model(name)
-    eng = NativeEngine(model, name, depth, tf32x3=True, use_tensor_cores=(mode == "tc"))
+    if backbones.family_of(name) == "densenet":
+        from i2v_b200.engine_densenet import DenseNetEngine
+        eng = DenseNetEngine(model, name, depth, tf32x3=True, use_tensor_cores=(mode == "tc"))
+    else:
+        eng = NativeEngine(model, name, depth, tf32x3=True, use_tensor_cores=(mode == "tc"))
     feats = eng.features(img.to(DEV), need_grad=True)
     # float64 reference on the CPU through the reference's own hook mechanism.  ReLU is not differentiable at 0:
     # a pre-activation within rounding distance of 0 may be decided differently by two correct float32 forward
@@ -185,7 +214,9 @@ def test_native_engine_matches_autograd(name, depth, side, mode):
         # 3xTF32: exact operands, but the tensor core accumulates with truncation (K/8 truncations of the main
         # accumulator): a systematic shrink of ~K * 2^-27 per layer that adds up over the depth of the stack
         assert err <= (5e-5 if mode == "tc" else 5e-6), ("feature", err)
-        up = torch.randn(a.shape, generator=g, dtype=torch.float64) * (got > 0)     # pre-activation gradient
+        up = torch.randn(a.shape, generator=g, dtype=torch.float64)
+        if eng.relu_masked_grads:
+            up = up * (got > 0)                                                     # pre-activation gradient
         ups.append(up)
     (gref,) = torch.autograd.grad(acts, xi, ups)
     grads = [u.permute(0, 2, 3, 1).contiguous().float().to(DEV) for u in ups]
