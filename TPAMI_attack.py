@@ -73,7 +73,7 @@ class AENS_I2V_MF(Attack):
                          n_layers_total=self._plan.n_layers_total)
         res = attack_loop.run_image_guided(self._engines, videos, self.epsilon, self.steps, self.step_size,
                                            adaptive=True, coeffs=self.coeffs, momentum=self.momentum,
-                                           coef_CE=self.coef_CE, **extra)
+                                           coef_CE=self.coef_CE, cache=self.__dict__.setdefault("_run_cache", {}), **extra)
         self.weights = [w.copy() for w in res.weights] if res.weights is not None else []
         cost_saved = np.zeros(self.steps)
         cost_saved[:] = res.cost

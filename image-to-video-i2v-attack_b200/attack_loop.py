@@ -114,11 +114,17 @@ class ImageGuidedRun:
                           and bool(self.engines) and all(getattr(e, "graph_safe", False) for e in self.engines))
         self._graph = None
         self._graph_launches = {}
+        self._graph_gen = None
+        self._alloc_key = None
+        self.reusable = False        # set by run_image_guided(cache=...): finish() then hands out a copy of the result
         if adaptive and (coeffs is None or coeffs.numel() != self.n_layers):
             raise ValueError("adaptive mode needs a coeffs tensor with one entry per hooked layer (%d)" % self.n_layers)
         self.step_no = 0
 
     def setup(self, videos):
+        """Start an attack call on `videos`.  A run object can be set up again for another batch of the same shape: its
+        device state and — the point — its captured CUDA graph are then reused, so a sweep of batch-size-1 calls
+        (image_main.py:82-89) pays for capture and instantiation once, not per clip."""
         if videos.dim() != 5 or videos.shape[1] != 3:
             raise ValueError("videos must be [b,3,f,h,w], got %s" % (tuple(videos.shape),))
         device = torch.device("cuda", torch.cuda.current_device())
@@ -128,47 +134,63 @@ class ImageGuidedRun:
         frames = frames_of(videos.to(device=device, dtype=torch.float32, non_blocking=True))
         N = self.N = b * f
         inner = self.inner = h * w
-        chunk = self.chunk = _chunk_frames(self.engines, N, self.chunk_request, h, w, device)
-        self.spans = [(s, min(s + chunk, N)) for s in range(0, N, chunk)]
         steps = self.steps
-
-        self.x = torch.empty_like(frames)
+        key = (b, f, h, w, device.index)
+        reuse = self._alloc_key == key
+        if not reuse:
+            self._graph = None
+            chunk = self.chunk = _chunk_frames(self.engines, N, self.chunk_request, h, w, device)
+            self.spans = [(s, min(s + chunk, N)) for s in range(0, N, chunk)]
+            self.x = torch.empty_like(frames)
+            self.mod = torch.empty_like(frames)
+            self.m = torch.empty_like(frames)
+            self.v = torch.empty_like(frames)
+            self.true_img = torch.empty_like(frames)
+            self.g_total = torch.empty_like(frames)
+            self.init_feats = None
+        chunk = self.chunk
         capi.denorm(frames, self.x, inner)                                      # image_attacks.py:308
-        self.mod = torch.empty_like(frames)
         capi.fill(self.mod, INIT_MODIFIER)                                      # image_attacks.py:304
-        self.m = torch.zeros_like(frames)
-        self.v = torch.zeros_like(frames)
-        self.true_img = torch.empty_like(frames)
-        self.g_total = torch.empty_like(frames)
+        self.m.zero_()
+        self.v.zero_()
 
         # clean features (image_attacks.py:318-323; TPAMI_attack.py:241-253), kept for all N frames
-        self.init_feats = []
-        for e in self.engines:
-            per_layer = None
+        init_feats = []
+        for ei, e in enumerate(self.engines):
+            per_layer = self.init_feats[ei] if reuse else None
             for (s0, s1) in self.spans:
                 # native engines hand out views of their reusable buffers (clone=False): one copy into the per-call store
-                fe = e.features(frames[s0:s1], need_grad=False, clone=False) if getattr(e, "relu_masked_grads", None) is not None \
-                    and hasattr(e, "_plan") else e.features(frames[s0:s1], need_grad=False)
+                fe = e.features(frames[s0:s1], need_grad=False, clone=False) if hasattr(e, "buffer_generation") \
+                    else e.features(frames[s0:s1], need_grad=False)
                 if per_layer is None:
                     per_layer = [torch.empty((N,) + tuple(t.shape[1:]), device=device, dtype=torch.float32) for t in fe]
                 for dst, t in zip(per_layer, fe):
                     dst[s0:s1].copy_(t)
-            self.init_feats.append(per_layer)
-        self.grads = [[torch.empty((chunk,) + tuple(t.shape[1:]), device=device, dtype=torch.float32) for t in fe]
-                      for fe in self.init_feats]
-
-        self.cos = torch.zeros(self.n_layers, N, device=device, dtype=torch.float32)
-        foreign = [r for r in range(self.n_layers) if r not in set(self.owned_rows)]
-        self.foreign_rows = torch.tensor(foreign, device=device, dtype=torch.long) if foreign else None
-        self.step_idx = torch.zeros(1, device=device, dtype=torch.int32)
-        self.cost_log = torch.zeros(max(steps, 1), device=device, dtype=torch.float32)
-        self.table = capi.adam_step_table(steps, self.step_size, BETA1, BETA2).to(device)
-        if self.adaptive:
-            self.prev = torch.ones(self.n_layers, device=device, dtype=torch.float32)   # TPAMI_attack.py:257
-            self.w_out = torch.empty(self.n_layers, device=device, dtype=torch.float32)
-            self.weights_log = torch.zeros(max(steps, 1), self.n_layers, device=device, dtype=torch.float32)
+            init_feats.append(per_layer)
+        self.init_feats = init_feats
+        if not reuse:
+            self.grads = [[torch.empty((chunk,) + tuple(t.shape[1:]), device=device, dtype=torch.float32) for t in fe]
+                          for fe in self.init_feats]
+            self.cos = torch.zeros(self.n_layers, N, device=device, dtype=torch.float32)
+            foreign = [r for r in range(self.n_layers) if r not in set(self.owned_rows)]
+            self.foreign_rows = torch.tensor(foreign, device=device, dtype=torch.long) if foreign else None
+            self.step_idx = torch.zeros(1, device=device, dtype=torch.int32)
+            self.cost_log = torch.zeros(max(steps, 1), device=device, dtype=torch.float32)
+            self.table = capi.adam_step_table(steps, self.step_size, BETA1, BETA2).to(device)
+            if self.adaptive:
+                self.prev = torch.ones(self.n_layers, device=device, dtype=torch.float32)   # TPAMI_attack.py:257
+                self.w_out = torch.empty(self.n_layers, device=device, dtype=torch.float32)
+                self.weights_log = torch.zeros(max(steps, 1), self.n_layers, device=device, dtype=torch.float32)
+            else:
+                self.prev = self.w_out = self.weights_log = None
         else:
-            self.prev = self.w_out = self.weights_log = None
+            self.cos.zero_()
+            self.step_idx.zero_()
+            self.cost_log.zero_()
+            if self.adaptive:
+                self.prev.fill_(1.0)
+                self.weights_log.zero_()
+        self._alloc_key = key
         capi.compose_norm(self.x, self.mod, self.true_img, self.epsilon, inner)   # image_attacks.py:331-332
         self.step_no = 0
         return self
@@ -180,6 +202,8 @@ class ImageGuidedRun:
         scalar table (K3a) make the step body iteration-invariant."""
         if self.step_no >= self.steps:
             raise RuntimeError("all %d steps of this run are done" % self.steps)
+        if self._graph is not None and self._graph_gen != self._buffer_gen():
+            self._graph = None                   # an engine re-allocated its buffers since the capture
         if self._graph is not None and capi.PROFILE_EVENTS is None:
             self._graph.replay()
             for k, v in self._graph_launches.items():
@@ -192,10 +216,14 @@ class ImageGuidedRun:
                 self._step_body()
             self._graph_launches = {k: v - before.get(k, 0) for k, v in capi.LAUNCHES.items() if v != before.get(k, 0)}
             self._graph = graph
+            self._graph_gen = self._buffer_gen()
             graph.replay()                       # capture only records: this replay IS the step
         else:
             self._step_body()
         self.step_no += 1
+
+    def _buffer_gen(self):
+        return tuple(getattr(e, "buffer_generation", 0) for e in self.engines)
 
     def _step_body(self):
         adaptive = self.adaptive
@@ -244,7 +272,8 @@ class ImageGuidedRun:
     def finish(self):
         # `true_img` holds (clamp(x + clamp(mod, ±eps), 0, 1) - mean)/std for the final modifier, which is
         # exactly image_attacks.py:360-361.
-        adv = clip_of(self.true_img, self.b, self.f)
+        # (a reusable run keeps its buffers for the next call: the caller gets its own copy of the result)
+        adv = clip_of(self.true_img.clone() if self.reusable else self.true_img, self.b, self.f)
         n = self.step_no
         cost_host = self.cost_log[:n].cpu().numpy() if n > 0 else np.zeros(0, dtype=np.float32)
         weights_host = self.weights_log[:n].cpu().numpy() if self.adaptive and n > 0 else None
@@ -371,9 +400,24 @@ def run_dispersion(engines, videos, epsilon, steps, step_size, chunk=None, tap=N
 
 
 def run_image_guided(engines, videos, epsilon, steps, step_size, adaptive=False, coeffs=None, momentum=0.0,
-                     coef_CE=False, chunk=None, reduce_hook=None, tap=None, layer_offsets=None, n_layers_total=None):
-    run = ImageGuidedRun(engines, epsilon, steps, step_size, adaptive, coeffs, momentum, coef_CE, chunk, reduce_hook, tap,
-                         layer_offsets, n_layers_total)
+                     coef_CE=False, chunk=None, reduce_hook=None, tap=None, layer_offsets=None, n_layers_total=None,
+                     cache=None):
+    """cache: a dict owned by the caller (the attack object).  The run — device state, captured CUDA graph — is kept in it
+    and set up again when the next call has the same configuration and clip shape."""
+    run = None
+    key = (float(epsilon), int(steps), float(step_size), bool(adaptive), float(momentum), bool(coef_CE), chunk,
+           tuple(id(e) for e in engines), None if coeffs is None else coeffs.data_ptr())
+    if cache is not None and tap is None and reduce_hook is None:
+        if cache.get("key") == key:
+            run = cache["run"]
+        else:
+            cache.clear()
+    if run is None:
+        run = ImageGuidedRun(engines, epsilon, steps, step_size, adaptive, coeffs, momentum, coef_CE, chunk, reduce_hook, tap,
+                             layer_offsets, n_layers_total)
+        if cache is not None and tap is None and reduce_hook is None:
+            run.reusable = True
+            cache["key"], cache["run"] = key, run
     run.setup(videos)
     for _ in range(run.steps):
         run.step()

@@ -128,6 +128,7 @@ class DenseNetEngine(NativeEngine):
         self.stem_direct = False
         self._xpbuf = None
         self._cache = {}
+        self.buffer_generation = 0
         self.hook_bufs = ["cat%d" % b for b in self.hook_blocks]
 
     @property
@@ -201,6 +202,7 @@ class DenseNetEngine(NativeEngine):
             plan["d_" + tr.name] = capi.ConvDesc(n, bh, bw, tr.cp, tr.cout, 1, 1, 1, 0, bh, bw)
         if len(self._cache) > 4:
             self._cache.clear()
+            self.buffer_generation += 1      # captured CUDA graphs that point into the old buffers are stale
         self._cache[key] = plan
         return plan
 

@@ -313,6 +313,7 @@ class NativeEngine:
         self.stem_direct = os.environ.get("I2V_STEM_DIRECT", "0") == "1"
         self._xpbuf = None
         self._cache = {}
+        self.buffer_generation = 0
 
     @property
     def num_layers(self):
@@ -377,6 +378,7 @@ class NativeEngine:
                     gimg=torch.empty(n, 3, h, w, device=device, dtype=torch.float32))
         if len(self._cache) > 4:
             self._cache.clear()
+            self.buffer_generation += 1      # captured CUDA graphs that point into the old buffers are stale
         self._cache[key] = plan
         return plan
 
@@ -388,12 +390,14 @@ class NativeEngine:
             nfl = capi.stem_fwd_direct_scratch_floats(d)
             if self._xpbuf is None or self._xpbuf.numel() < nfl:
                 self._xpbuf = torch.empty(nfl, device=x.device, dtype=torch.float32)
+                self.buffer_generation += 1
             capi.conv_stem_fwd_direct(d, x, hi, lo, op.bias, self._xpbuf, y, relu=op.relu)
         elif op.x_nchw and residual is None and self.use_tc and self.use_stem_tc and op.tc_stem_fwd is not None:
             hi, lo, rna = op.tc_stem_fwd
             nfl = capi.stem_fwd_tc_scratch_floats(d)
             if self._zbuf is None or self._zbuf.numel() < nfl:
                 self._zbuf = torch.empty(nfl, device=x.device, dtype=torch.float32)
+                self.buffer_generation += 1
             capi.conv_stem_fwd_tc(d, x, hi if self.tf32x3 else rna, lo if self.tf32x3 else None, op.bias, self._zbuf, y,
                                   relu=op.relu)
         elif op.x_nchw and residual is None and self.use_stem and capi.conv_stem_supported(d):
@@ -412,6 +416,7 @@ class NativeEngine:
             nfl = capi.stem_dgrad_tc_scratch_floats(d)
             if self._zbuf is None or self._zbuf.numel() < nfl:
                 self._zbuf = torch.empty(nfl, device=dy.device, dtype=torch.float32)
+                self.buffer_generation += 1
             capi.conv_stem_dgrad_tc(d, dy, hi if self.tf32x3 else rna, lo if self.tf32x3 else None, self._zbuf, dx)
         elif op.x_nchw and addend is None and mask_src is None and self.use_stem and capi.conv_stem_supported(d):
             capi.conv_stem_dgrad(d, dy, op.b_fwd, dx)

@@ -122,7 +122,8 @@ class ImageGuidedFMDirection_Adam(Attack):
 
     def forward(self, videos, labels, video_names):
         # labels are moved to the GPU and never read by the reference (image_attacks.py:298)
-        res = attack_loop.run_image_guided([self._engine], videos, self.epsilon, self.steps, self.step_size)
+        res = attack_loop.run_image_guided([self._engine], videos, self.epsilon, self.steps, self.step_size,
+                                           cache=self.__dict__.setdefault("_run_cache", {}))
         attack_loop.record_loss_info(self.loss_info, video_names, res.cost)
         return res.adv
 
@@ -163,7 +164,8 @@ class ImageGuidedFML2_Adam_MultiModels(Attack):
         if self._plan is not None:
             extra = dict(reduce_hook=self._plan.hook(), layer_offsets=self._plan.layer_offsets,
                          n_layers_total=self._plan.n_layers_total)
-        res = attack_loop.run_image_guided(self._engines, videos, self.epsilon, self.steps, self.step_size, **extra)
+        res = attack_loop.run_image_guided(self._engines, videos, self.epsilon, self.steps, self.step_size,
+                                           cache=self.__dict__.setdefault("_run_cache", {}), **extra)
         attack_loop.record_loss_info(self.loss_info, video_names, res.cost)
         return res.adv
 

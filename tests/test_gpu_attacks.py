@@ -331,6 +331,52 @@ def test_cuda_graph_replay_is_bit_identical_to_the_eager_loop(adaptive, monkeypa
     assert out[0][3] == out[1][3] and sum(out[1][3].values()) > 100
 
 
+def test_repeated_calls_reuse_the_run_and_its_graph():
+    """A sweep calls the attack object clip after clip (image_main.py:82-89): the second call of the same shape reuses the
+    first call's device state and captured graph and must give exactly what a fresh attack object gives; a call with another
+    shape in between starts over; the result of an earlier call is not overwritten by a later one."""
+    v1, _ = synth.clip(11, b=1, f=4, h=64, w=64)
+    v2, _ = synth.clip(12, b=1, f=4, h=64, w=64)
+    v3, _ = synth.clip(13, b=1, f=2, h=32, w=32)
+    lab = torch.zeros(1, dtype=torch.long)
+
+    def fresh(v, name):
+        a = image_attacks.ImageGuidedFMDirection_Adam(["resnet"], depth=2, step_size=0.005, steps=5, engine="native")
+        out = a(v, lab, [name])
+        return out.clone(), a.loss_info[name]
+    want = [fresh(v, "c%d" % i) for i, v in enumerate((v1, v2, v3))]
+    atk = image_attacks.ImageGuidedFMDirection_Adam(["resnet"], depth=2, step_size=0.005, steps=5, engine="native")
+    got1 = atk(v1, lab, ["c0"])
+    run = atk._run_cache["run"]
+    assert run._graph is not None
+    got2 = atk(v2, lab, ["c1"])
+    assert atk._run_cache["run"] is run and run._graph is not None
+    assert torch.equal(got1, want[0][0]) and torch.equal(got2, want[1][0])          # got1 survived the second call
+    got3 = atk(v3, lab, ["c2"])
+    assert torch.equal(got3, want[2][0])
+    got1b = atk(v1, lab, ["c0b"])
+    assert torch.equal(got1b, want[0][0])
+    for i in range(3):
+        assert atk.loss_info["c%d" % i] == want[i][1]
+    # AENS: the persistent coefficient vector carries over between calls exactly as without reuse (TPAMI_attack.py:165, 265)
+    names = ["resnet", "squeezenet"]
+    a1 = TPAMI_attack.AENS_I2V_MF(names, {n: [1, 2] for n in names}, 0.005, momentum=0.5, steps=4, engine="native")
+    r1 = [a1(v, lab, ["x"])[0].clone() for v in (v1, v2)]
+    w1 = np.stack(a1.weights)
+    import os
+    os.environ["I2V_GRAPH"] = "0"
+    try:
+        a2 = TPAMI_attack.AENS_I2V_MF(names, {n: [1, 2] for n in names}, 0.005, momentum=0.5, steps=4, engine="native")
+        r2 = []
+        for v in (v1, v2):
+            a2.__dict__["_run_cache"] = {}               # no reuse, no graph: the plain loop
+            r2.append(a2(v, lab, ["x"])[0].clone())
+        w2 = np.stack(a2.weights)
+    finally:
+        del os.environ["I2V_GRAPH"]
+    assert torch.equal(r1[0], r2[0]) and torch.equal(r1[1], r2[1]) and np.array_equal(w1, w2)
+
+
 def test_native_chunking_bit_identical_at_benchmark_size():
     """bench.py's configuration (BASELINE.json configs[1]) relies on this: 224 x 224 frames on the native engine in
     256-frame chunks plus a remainder chunk with a different (n, h, w) buffer plan.  288 frames (9 clips x 32), two

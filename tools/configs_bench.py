@@ -2,8 +2,8 @@
 """Throughput of BASELINE.json's configs[2..4] through the PUBLIC drop-in classes (configs[0] / [1] are bench.py's
 `--impl reference` and default lines).  One JSON object per config on stdout, all of them in --out.
 
-  config 3  AENS_I2V_MF over resnet / vgg / squeezenet / alexnet, depths [2,3] each (the ensemble the reference can run:
-            DenseNet hooks do not exist there), one 32-frame 224^2 clip per call.  Single process = all four
+  config 3  AENS_I2V_MF over resnet50 / vgg16 / densenet121 / squeezenet1_1, depths [2,3] each (BASELINE.json's ensemble;
+            the DenseNet hook is this repo's extension), one 32-frame 224^2 clip per call.  Single process = all four
             backbones on this GPU; under torchrun with world % 4 == 0, one backbone per GPU (placement='ensemble').
   config 4  Kinetics-val-shaped sweep: independent batch-size-1 calls of the config-1 attack (I2V ResNet-50 layer2,
             60 steps), clips dealt round-robin over the ranks (no collective); `--clips` clips in total.
@@ -71,14 +71,14 @@ def main():
             results.append(rec)
 
     if "3" in only:
-        names = ["resnet", "vgg", "squeezenet", "alexnet"]
+        names = ["resnet", "vgg", "densenet121", "squeezenet"]          # BASELINE.json configs[2] (native DenseNet engine)
         ens = world > 1 and world % 4 == 0
         atk = TPAMI_attack.AENS_I2V_MF(names, {n: [2, 3] for n in names}, 0.005, momentum=0.5, steps=args.steps,
                                        placement="ensemble" if ens else None)
         v, lab = synth.clip(0, b=1, f=32, h=224, w=224)
         v = v.to(dev)
         sec = timed(lambda: atk(v, lab, ["c"]), 2)
-        emit({"config": 3, "workload": "AENS_I2V_MF resnet50/vgg16/squeezenet1_1/alexnet depths [2,3], 1 clip x 32 x 3x224x224, "
+        emit({"config": 3, "workload": "AENS_I2V_MF resnet50/vgg16/densenet121/squeezenet1_1 depths [2,3], 1 clip x 32 x 3x224x224, "
               "%d steps, %s" % (args.steps, "one backbone per GPU (NCCL all-reduce of dcost/dimage)" if ens else
                                 "all backbones on one GPU"),
               "frame_steps": 32 * args.steps * (world // 4 if ens else 1), "seconds": sec})
