@@ -65,6 +65,7 @@ SIGNATURES = {
     "i2v_conv_stem_fwd_tc_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_tc_supported": ([_c_p, _c_int], _c_int),
     "i2v_conv_tc_set_trace": ([_c_p, _c_int], _c_int),
+    "i2v_conv_tc_set_pair_minkit": ([_c_int], _c_int),
     "i2v_mma_probe": ([_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_p, _c_p], _c_int),
     "i2v_conv_tc_f32": ([_c_p, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_tc_bits_f32": ([_c_p, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
@@ -117,7 +118,7 @@ def load():
 # tensors read + written once, 2 x MACs of the convolution).
 LAUNCHES = {}
 PROFILE_EVENTS = None
-_NO_KERNEL = ("i2v_set_adam_arithmetic", "i2v_conv_stem_fwd_direct_supported", "i2v_conv_stem_fwd_direct_scratch_floats", "i2v_conv_stem_dgrad_tc_rows", "i2v_device_check", "i2v_std_workspace_doubles", "i2v_ila_workspace_doubles", "i2v_adam_step_table", "i2v_conv_tc_supported", "i2v_conv_stem_supported",
+_NO_KERNEL = ("i2v_set_adam_arithmetic", "i2v_conv_tc_set_pair_minkit", "i2v_conv_stem_fwd_direct_supported", "i2v_conv_stem_fwd_direct_scratch_floats", "i2v_conv_stem_dgrad_tc_rows", "i2v_device_check", "i2v_std_workspace_doubles", "i2v_ila_workspace_doubles", "i2v_adam_step_table", "i2v_conv_tc_supported", "i2v_conv_stem_supported",
               "i2v_conv_tc_set_trace")
 
 
@@ -491,6 +492,11 @@ def mma_probe(N, accs, a_tmem, count, ctas=1, issuers=1):
 def conv_tc_set_trace(buf, tiles=0):
     """Debug: buf = int64 CUDA tensor [tiles, 8] (or None) receiving CTA 0's pipeline time stamps."""
     _check(load().i2v_conv_tc_set_trace(None if buf is None else _dev(buf, torch.int64), tiles), "i2v_conv_tc_set_trace")
+
+
+def conv_tc_set_pair_minkit(min_ksteps):
+    """Tiles of >= min_ksteps k-steps run on the CTA-pair (cta_group::2) kernel; 0 = never."""
+    _check(load().i2v_conv_tc_set_pair_minkit(int(min_ksteps)), "i2v_conv_tc_set_pair_minkit")
 
 
 def conv_tc_supported(desc, dgrad):

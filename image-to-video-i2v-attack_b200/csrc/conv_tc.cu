@@ -1030,6 +1030,402 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------
+// CTA-pair kernel: tcgen05.mma.cta_group::2 (M = 256: two SMs, 128 pixels each, ONE instruction for both) for the
+// 3xTF32 / dual-issuer / TMA-epilogue configuration of the persistent kernel above.
+//
+// Why: a tcgen05.mma.kind::tf32 is accepted every ~237 cycles per issuing thread whatever its shape (profiles/
+// r01_mma_issue_probe.txt), and every SM pulls the complete weight block of every k-step through L2.  A pair halves both:
+// the leader CTA's two issuers drive both SMs, and each CTA loads only HALF of the weight rows of a k-step — the tensor core
+// reads B from both CTAs' shared memory (N is split across the pair).
+//
+// Layout of one pipeline stage in EACH CTA (rank r of the cluster, h = BN/2):
+//     A   [128 pixels x 32 ch]                this CTA's own pixel tile (im2col / tiled TMA), signals the LOCAL barrier afull
+//     B   [h rows of B_hi | h rows of B_lo]   weight rows n0 + r*h .. +h-1, loaded with cta_group::2 TMA: the bytes of both
+//                                             CTAs complete on the LEADER's barrier `full`
+//   MMA1 (leader warp 1)  [d0 .. d0+2BN)  += a_hi x B  with N = 2*BN: each CTA contributes its BN rows, so the accumulator
+//        columns are [main(0:h) | cross(0:h) | main(h:BN) | cross(h:BN)]  (main = a_hi b_hi, cross = a_hi b_lo)
+//   MMA2 (leader warp 2)  [d0+2BN .. +BN) += a_lo (tensor memory, written by each CTA's split warps) x B with N = BN: each CTA
+//        contributes its first h rows = its B_hi half -> cross2 = a_lo b_hi in natural column order.
+// Barriers: afull / empty / tfull / out_ready / slot_ready are per CTA (tcgen05.commit multicasts to both); full / split /
+// tempty live in the leader and receive remote arrivals (release.cluster) from the peer's producer, split and epilogue
+// threads — the peer's split threads arrive only after they have seen their own A tile land, which is also what tells the
+// leader's first issuer that the peer's a_hi is in place.  Everything behind the accumulator (epilogue warps, TMA stores,
+// residual loads, mask bits) is the per-CTA code of the kernel above with the column map of the pair layout.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;       // shared::cluster address of the same offset in the even (leader) CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_leader(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;"
+                 :: "r"(smem_u32(bar) & kPeerBitMask), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > 8000000000LL) { printf("i2v conv_tc pair: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    }
+}
+// cta_group::2 TMA: the transaction bytes complete on the LEADER CTA's barrier at the same offset
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma2_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// arrives once on the barrier at this offset in BOTH CTAs of the pair when all prior MMAs of this thread are complete
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ constexpr uint32_t umma2_idesc_tf32(int n) {      // M = 256 across the pair
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int BN, bool IM2COL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
+conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                    const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmOut,
+                    const __grid_constant__ CUtensorMap tmRes, const TcArgs args, const int stages,
+                    const int num_m_tiles, const int num_n_tiles, const int epi_slots) {
+    constexpr int H = BN / 2;                                   // weight rows of a k-step held by each CTA (per hi / lo)
+    constexpr uint32_t kBBytes = (uint32_t)BN * TC_BK * 4;      // [h x b_hi | h x b_lo]
+    constexpr uint32_t kStageBytes = TC_A_BYTES + kBBytes;
+    constexpr uint32_t kAccCols = 3 * BN;                       // [MMA1: 2*BN | cross2: BN]
+    constexpr int kAcc = (int)(384 / kAccCols);
+    constexpr uint32_t kAloBase = 384, kAloSlots = 4, kTmemCols = 512;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* tiles = smem;
+    uint8_t* staging = smem + (size_t)stages * kStageBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + (size_t)epi_slots * 2 * EPI_SLOT_BYTES);   // leader's is used
+    uint64_t* afull_bar = full_bar + stages;                    // local: this CTA's A tile landed
+    uint64_t* empty_bar = afull_bar + stages;                   // local: both issuers are done with the stage (multicast commit)
+    uint64_t* split_bar = empty_bar + stages;                   // leader's: 2 x 128 split threads
+    uint64_t* tfull_bar = split_bar + stages;                   // local (multicast commit)
+    uint64_t* tempty_bar = tfull_bar + kAcc;                    // leader's: 2 x 256 epilogue threads
+    uint64_t* out_ready = tempty_bar + kAcc;
+    uint64_t* slot_ready = out_ready + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slot_ready + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int kiters = args.taps_h * args.taps_w * args.cblocks;
+    const int pid = (int)(blockIdx.x >> 1), npairs = (int)(gridDim.x >> 1);
+    const int num_ptiles = ((num_m_tiles + 1) >> 1) * num_n_tiles;   // a pair tile = two consecutive m-tiles x one n-tile
+
+    auto stage_a = [&](int s) { return tiles + (size_t)s * kStageBytes; };
+    auto stage_b = [&](int s) { return tiles + (size_t)s * kStageBytes + TC_A_BYTES; };
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA); prefetch_tmap(&tmBhi); prefetch_tmap(&tmBlo); prefetch_tmap(&tmOut); prefetch_tmap(&tmRes);
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full_bar[s], 2);                         // the two producers' arrive.expect_tx
+            mbar_init(&afull_bar[s], 1);
+            mbar_init(&empty_bar[s], 2);                        // both issuers release a stage
+            mbar_init(&split_bar[s], 256);
+        }
+        for (int a = 0; a < kAcc; ++a) {
+            mbar_init(&tfull_bar[a], 2);
+            mbar_init(&tempty_bar[a], 2 * TC2_EPI_THREADS);
+        }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&out_ready[i], TC2_EPI_THREADS / 2);
+            mbar_init(&slot_ready[i], 1);
+        }
+        fence_barrier_init();
+    }
+    cluster_sync_all();                                          // both CTAs' barriers exist before anyone arrives remotely
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own A tile -> afull (local); own half of the weight rows -> full (leader) =========
+        if (lane == 0) {
+            int it = 0;
+            for (int pt = pid; pt < num_ptiles; pt += npairs) {
+                const int pm = pt / num_n_tiles, n_tile = pt - pm * num_n_tiles;
+                const int m_tile = 2 * pm + (int)rank;
+                const int64_t m0 = (int64_t)m_tile * TC_BM;
+                const int n0 = n_tile * BN + (int)rank * H;
+                int img = 0, base_h = 0, base_w = 0;
+                if (IM2COL) {
+                    const int64_t pq = (int64_t)args.P * args.Q;
+                    img = (int)(m0 / pq);
+                    const int rem = (int)(m0 - (int64_t)img * pq);
+                    const int p = rem / args.Q, q = rem - p * args.Q;
+                    base_h = p * args.stride + args.lower_h;
+                    base_w = q * args.stride + args.lower_w;
+                }
+                for (int r = 0; r < args.taps_h; ++r)
+                    for (int s = 0; s < args.taps_w; ++s)
+                        for (int cb = 0; cb < args.cblocks; ++cb, ++it) {
+                            const int st = it % stages;
+                            const uint32_t ph = (uint32_t)(it / stages) & 1;
+                            mbar_wait(&empty_bar[st], ph ^ 1);
+                            mbar_arrive_expect_tx(&afull_bar[st], TC_A_BYTES);
+                            if (IM2COL) tma_load_im2col_4d(&tmA, &afull_bar[st], stage_a(st), cb * TC_BK, base_w, base_h, img, (uint16_t)s, (uint16_t)r);
+                            else        tma_load_2d(&tmA, &afull_bar[st], stage_a(st), cb * TC_BK, (int)m0);
+                            const int kcol = ((r * args.taps_w + s) * args.cblocks + cb) * TC_BK;
+                            mbar_arrive_expect_tx_leader(&full_bar[st], kBBytes);
+                            tma_load_2d_2sm(&tmBhi, &full_bar[st], stage_b(st), kcol, n0);
+                            tma_load_2d_2sm(&tmBlo, &full_bar[st], stage_b(st) + (size_t)H * TC_BK * 4, kcol, n0);
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer 1 (leader): [main | cross] halves of both CTAs += a_hi x [b_hi half | b_lo half] ==================
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc2 = umma2_idesc_tf32(2 * BN);
+            int it = 0, t = 0;
+            for (int pt = pid; pt < num_ptiles; pt += npairs, ++t) {
+                const int acc = t % kAcc;
+                const uint32_t aph = (uint32_t)(t / kAcc) & 1;
+                mbar_wait_cluster(&tempty_bar[acc], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + (uint32_t)acc * kAccCols;
+                for (int kb = 0; kb < kiters; ++kb, ++it) {
+                    const int st = it % stages;
+                    const uint32_t ph = (uint32_t)(it / stages) & 1;
+                    mbar_wait_cluster(&full_bar[st], ph);        // the weight rows of both CTAs
+                    mbar_wait(&afull_bar[st], ph);               // this CTA's a_hi
+                    mbar_wait_cluster(&split_bar[st], ph);       // the peer's a_hi (its split threads saw it land)
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_sw128(smem_u32(stage_a(st)));
+                    const uint64_t db = umma_desc_sw128(smem_u32(stage_b(st)));
+#pragma unroll
+                    for (int kk = 0; kk < TC_BK / 8; ++kk)
+                        umma2_tf32(d0, da + 2 * kk, db + 2 * kk, idesc2, (kb | kk) ? 1u : 0u);
+                    umma2_commit(&empty_bar[st]);
+                }
+                umma2_commit(&tfull_bar[acc]);
+            }
+        }
+    } else if (warp == 2) {
+        // ===== MMA issuer 2 (leader): cross2 += a_lo (tensor memory of each CTA) x b_hi halves ===============================
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = umma2_idesc_tf32(BN);
+            int it = 0, t = 0;
+            for (int pt = pid; pt < num_ptiles; pt += npairs, ++t) {
+                const int acc = t % kAcc;
+                const uint32_t aph = (uint32_t)(t / kAcc) & 1;
+                mbar_wait_cluster(&tempty_bar[acc], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d2 = tmem_base + (uint32_t)acc * kAccCols + 2u * BN;
+                for (int kb = 0; kb < kiters; ++kb, ++it) {
+                    const int st = it % stages;
+                    const uint32_t ph = (uint32_t)(it / stages) & 1;
+                    mbar_wait_cluster(&full_bar[st], ph);
+                    mbar_wait_cluster(&split_bar[st], ph);       // a_lo of both CTAs is in its ring slot
+                    tc_fence_after();
+                    const uint64_t db = umma_desc_sw128(smem_u32(stage_b(st)));
+                    const uint32_t talo = tmem_base + kAloBase + (uint32_t)(it % kAloSlots) * 32u;
+#pragma unroll
+                    for (int kk = 0; kk < TC_BK / 8; ++kk)
+                        umma2_tf32_ts(d2, talo + 8u * kk, db + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
+                    umma2_commit(&empty_bar[st]);
+                }
+                umma2_commit(&tfull_bar[acc]);
+            }
+        }
+    } else if (warp == 3) {
+        // ===== epilogue TMA issuer of both groups (per CTA): output stores, residual loads ==================================
+        if (lane == 0) {
+            constexpr uint32_t SUBS = BN / 64;
+            const bool has_res = args.residual != nullptr;
+            const uint32_t ns = (uint32_t)epi_slots;
+            const uint32_t my_tiles = (uint32_t)((num_ptiles - pid + npairs - 1) / npairs);
+            const uint32_t total = my_tiles * SUBS;
+            auto coords = [&](int g, uint32_t k, int& col, int& row) {
+                const int pt = pid + (int)(k / SUBS) * npairs;
+                const int pm = pt / num_n_tiles, n_tile = pt - pm * num_n_tiles;
+                col = n_tile * BN + (g + 2 * (int)(k % SUBS)) * 32;
+                row = (2 * pm + (int)rank) * TC_BM;
+            };
+            auto refill = [&](int g, uint32_t k) {
+                const uint32_t s = k % ns;
+                if (has_res) {
+                    int col, row;
+                    coords(g, k, col, row);
+                    mbar_arrive_expect_tx(&slot_ready[g * 2 + s], EPI_SLOT_BYTES);
+                    tma_load_2d(&tmRes, &slot_ready[g * 2 + s], staging + ((size_t)g * ns + s) * EPI_SLOT_BYTES, col, row);
+                } else {
+                    mbar_arrive(&slot_ready[g * 2 + s]);
+                }
+            };
+            for (int g = 0; g < 2; ++g)
+                for (uint32_t k = 0; k < ns && k < total; ++k) refill(g, k);
+            uint32_t kdone[2] = {0, 0};
+            const long long t0 = clock64();
+            while (kdone[0] < total || kdone[1] < total) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const uint32_t k = kdone[g];
+                    if (k >= total) continue;
+                    const uint32_t s = k % ns, ph = (k / ns) & 1;
+                    if (!mbar_try_wait(&out_ready[g * 2 + s], ph)) continue;
+                    int col, row;
+                    coords(g, k, col, row);
+                    const uint8_t* slot = staging + ((size_t)g * ns + s) * EPI_SLOT_BYTES;
+                    if (col < args.store_cols && row < (int64_t)num_m_tiles * TC_BM) tma_store_2d(&tmOut, slot, col, row);
+                    bulk_commit();
+                    if (k + ns < total) {
+                        bulk_wait_read0();
+                        refill(g, k + ns);
+                    }
+                    kdone[g] = k + 1;
+                }
+                if (clock64() - t0 > 40000000000LL) { printf("i2v conv_tc pair: epilogue issuer timeout (block %d)\n", blockIdx.x); __trap(); }
+            }
+            bulk_wait_all();
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===== A split (both CTAs): a_lo of the own tile -> own tensor memory; arrive on the LEADER's split barrier ==========
+        const int row = threadIdx.x - 128;
+        const uint32_t swz = (uint32_t)(row & 7);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kAloBase;
+        int it = 0;
+        for (int pt = pid; pt < num_ptiles; pt += npairs) {
+            for (int kb = 0; kb < kiters; ++kb, ++it) {
+                const int st = it % stages;
+                const uint32_t ph = (uint32_t)(it / stages) & 1;
+                mbar_wait(&afull_bar[st], ph);
+                const uint8_t* arow = stage_a(st) + (size_t)row * 128;
+                uint32_t lo[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 v = *reinterpret_cast<const float4*>(arow + (((uint32_t)c ^ swz) << 4));
+                    lo[4 * c + 0] = __float_as_uint(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+                    lo[4 * c + 1] = __float_as_uint(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+                    lo[4 * c + 2] = __float_as_uint(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+                    lo[4 * c + 3] = __float_as_uint(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+                }
+                tmem_st32(lane_addr + (uint32_t)(it % kAloSlots) * 32u, lo);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                mbar_arrive_leader(&split_bar[st]);
+            }
+        }
+    } else if (warp >= 8) {
+        // ===== epilogue v3 (per CTA), pair column map ======================================================================
+        constexpr int SUBS = BN / 64;
+        const int g = (warp - 8) >> 2;
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t swz = (uint32_t)(row & 7);
+        const uint32_t ns = (uint32_t)epi_slots;
+        uint8_t* sbase = staging + (size_t)g * ns * EPI_SLOT_BYTES + (size_t)row * 128;
+        const bool has_res = args.residual != nullptr;
+        const float* __restrict__ gbias = args.bias;
+        const uint32_t* __restrict__ mbits = args.mask_bits;
+        uint32_t* __restrict__ obits = args.bits_out;
+        uint32_t k = 0;
+        int t = 0;
+        for (int pt = pid; pt < num_ptiles; pt += npairs, ++t) {
+            const int pm = pt / num_n_tiles, n_tile = pt - pm * num_n_tiles;
+            const int m_tile = 2 * pm + (int)rank;
+            const int n0 = n_tile * BN;
+            const int acc = t % kAcc;
+            const uint32_t aph = (uint32_t)(t / kAcc) & 1;
+            const int64_t m = (int64_t)m_tile * TC_BM + row;
+            const bool valid = m < args.M;
+            uint32_t mw[SUBS];
+#pragma unroll
+            for (int j = 0; j < SUBS; ++j)
+                mw[j] = (mbits && valid) ? __ldg(mbits + (int64_t)(n0 / 32 + g + 2 * j) * args.M + m) : 0xFFFFFFFFu;
+            mbar_wait(&tfull_bar[acc], aph);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + (uint32_t)acc * kAccCols + ((uint32_t)((warp & 3) * 32) << 16);
+            uint32_t vals[SUBS][32];
+#pragma unroll
+            for (int j = 0; j < SUBS; ++j) {
+                const int c0 = (g + 2 * j) * 32;                                   // output column block of this sub-tile
+                const int cm = c0 < H ? c0 : BN + (c0 - H);                        // where MMA1 put main(c0 ..): see the layout
+                uint32_t b[32];
+                {
+                    uint32_t c2[32];
+                    tmem_ld32_nowait(tacc + (uint32_t)(cm + H), b);                // cross
+                    tmem_ld32_nowait(tacc + (uint32_t)(2 * BN + c0), c2);          // cross2
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) b[i] = __float_as_uint(__fadd_rn(__uint_as_float(b[i]), __uint_as_float(c2[i])));
+                }
+                tmem_ld32_nowait(tacc + (uint32_t)cm, vals[j]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    vals[j][i] = __float_as_uint(__fadd_rn(__uint_as_float(vals[j][i]), __uint_as_float(b[i])));
+            }
+            tc_fence_before();
+            mbar_arrive_leader(&tempty_bar[acc]);
+#pragma unroll
+            for (int j = 0; j < SUBS; ++j, ++k) {
+                const int c0 = (g + 2 * j) * 32;
+                uint32_t (&a)[32] = vals[j];
+                const uint32_t s = k % ns, ph = (k / ns) & 1;
+                mbar_wait(&slot_ready[g * 2 + s], ph);
+                uint8_t* srow = sbase + (size_t)s * EPI_SLOT_BYTES;
+                const float4* bs4 = reinterpret_cast<const float4*>(gbias + n0 + c0);
+                const uint32_t mword = mw[j];
+                uint32_t oword = 0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4* p = reinterpret_cast<float4*>(srow + (((uint32_t)c ^ swz) << 4));
+                    const float4 bv = gbias ? __ldg(bs4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 v = make_float4(__uint_as_float(a[4 * c]) + bv.x, __uint_as_float(a[4 * c + 1]) + bv.y,
+                                           __uint_as_float(a[4 * c + 2]) + bv.z, __uint_as_float(a[4 * c + 3]) + bv.w);
+                    if (has_res) { const float4 r = *p; v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w; }
+                    if (args.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    if (!((mword >> (4 * c)) & 1u)) v.x = 0.f;
+                    if (!((mword >> (4 * c + 1)) & 1u)) v.y = 0.f;
+                    if (!((mword >> (4 * c + 2)) & 1u)) v.z = 0.f;
+                    if (!((mword >> (4 * c + 3)) & 1u)) v.w = 0.f;
+                    oword |= (v.x > 0.f ? 1u : 0u) << (4 * c) | (v.y > 0.f ? 1u : 0u) << (4 * c + 1) |
+                             (v.z > 0.f ? 1u : 0u) << (4 * c + 2) | (v.w > 0.f ? 1u : 0u) << (4 * c + 3);
+                    *p = v;
+                }
+                if (obits && valid) obits[(int64_t)((n0 + c0) / 32) * args.M + m] = oword;
+                fence_proxy_async();
+                mbar_arrive(&out_ready[g * 2 + s]);
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                  // nobody leaves (or frees tensor memory) while the peer may still signal / read here
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host: tensor maps (driver entry points resolved at run time: no link-time libcuda dependency)
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1245,6 +1641,47 @@ static int tc_launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmBhi, c
     return I2V_OK;
 }
 
+
+// CTA-pair launch (conv_tc_pair_kernel): clusters of 2, one cluster per SM pair; tmBhi / tmBlo are HALF-height boxes (BN/2 rows)
+template <int BN, bool IM2COL>
+static int tc_launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, const CUtensorMap& tmOut,
+                          const CUtensorMap& tmRes, const TcArgs& args, cudaStream_t st) {
+    auto kern = conv_tc_pair_kernel<BN, IM2COL>;
+    constexpr size_t kStageBytes = TC_A_BYTES + (size_t)BN * TC_BK * 4;
+    static size_t budget = 0;
+    if (budget == 0) {
+        int dev = 0, optin = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        const size_t b = (size_t)(optin > 0 ? optin : 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b);
+        if (e != cudaSuccess) return cuda_fail(e, "conv_tc (pair): shared memory attribute");
+        budget = b;
+    }
+    static const int slots_env = getenv("I2V_TC_EPI_SLOTS") ? atoi(getenv("I2V_TC_EPI_SLOTS")) : 0;
+    int slots = 2;                          // a pair stage is 24-32 KB: four stages and two staging slots per group fit
+    if (slots_env == 1 || slots_env == 2) slots = slots_env;
+    const size_t fixed = 1008 + 1024 + (size_t)slots * 2 * EPI_SLOT_BYTES;
+    int stages = (int)((budget - fixed) / kStageBytes);
+    if (stages > 4) stages = 4;             // the A_lo ring in tensor memory has 4 slots
+    if (stages < 2) { set_error("conv_tc (pair): %d pipeline stages fit in shared memory", stages); return I2V_ECUDA; }
+    I2V_REQUIRE(args.bias == nullptr || (reinterpret_cast<uintptr_t>(args.bias) & 15) == 0, "bias must be 16-byte aligned");
+    const int num_m_tiles = (int)((args.M + TC_BM - 1) / TC_BM), num_n_tiles = args.Cout / BN;
+    const int64_t ptiles = (int64_t)((num_m_tiles + 1) / 2) * num_n_tiles;
+    const int pairs = (int)(ptiles < sm_count() / 2 ? ptiles : sm_count() / 2);
+    kern<<<2 * pairs, TC2_THREADS, fixed + (size_t)stages * kStageBytes, st>>>(tmA, tmBhi, tmBlo, tmOut, tmRes, args, stages,
+                                                                              num_m_tiles, num_n_tiles, slots);
+    I2V_LAUNCH_CHECK("i2v_conv_tc_f32 (pair)");
+    return I2V_OK;
+}
+
+// minimum k-steps per tile from which the CTA-pair kernel takes over (0 = never); $I2V_TC_PAIR, i2v_conv_tc_set_pair_minkit
+static int g_pair_minkit = -1;
+static int pair_min_ksteps() {
+    if (g_pair_minkit < 0) g_pair_minkit = getenv("I2V_TC_PAIR") ? atoi(getenv("I2V_TC_PAIR")) : 0;
+    return g_pair_minkit;
+}
+
 static unsigned long long* g_trace = nullptr;
 static int g_trace_tiles = 0;
 
@@ -1330,6 +1767,18 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
             const int kit = pr.taps_h * pr.taps_w * (pr.C / 32);
             static const int alo_minkit = getenv("I2V_TC_ALO_MINKIT") ? atoi(getenv("I2V_TC_ALO_MINKIT")) : 4;
             const bool alo = x3 && alo_env != 0 && (BN == 64 || kit >= alo_minkit || alo_env == 2 || pr.force_dual);
+            // CTA pairs (tcgen05.mma.cta_group::2, half of the weight rows per CTA): $I2V_TC_PAIR = minimum k-steps per tile
+            // from which the pair kernel takes over (0 = never); needs at least two m-tiles
+            const int pair_minkit = pair_min_ksteps();
+            if (alo && pair_minkit > 0 && kit >= pair_minkit && !pr.out_transposed && M > TC_BM) {
+                CUtensorMap hBhi, hBlo;
+                if (int r = get_map_2d(&hBhi, pr.w_hi, pr.Cout, Ktot, BN / 2)) return r;
+                if (int r = get_map_2d(&hBlo, pr.w_lo, pr.Cout, Ktot, BN / 2)) return r;
+                if (BN == 128) return im2col ? tc_launch_pair<128, true>(tmA, hBhi, hBlo, tmOut, tmRes, a, st)
+                                             : tc_launch_pair<128, false>(tmA, hBhi, hBlo, tmOut, tmRes, a, st);
+                return im2col ? tc_launch_pair<64, true>(tmA, hBhi, hBlo, tmOut, tmRes, a, st)
+                              : tc_launch_pair<64, false>(tmA, hBhi, hBlo, tmOut, tmRes, a, st);
+            }
             if (alo) {
                 if (BN == 128) I2V_TC_DISPATCH_P(128, true, true);
                 I2V_TC_DISPATCH_P(64, true, true);
@@ -1367,6 +1816,11 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
 }  // namespace i2v
 
 using namespace i2v;
+
+extern "C" int i2v_conv_tc_set_pair_minkit(int min_ksteps) {
+    g_pair_minkit = min_ksteps < 0 ? 0 : min_ksteps;
+    return I2V_OK;
+}
 
 extern "C" int i2v_conv_tc_set_trace(unsigned long long* device_buf, int tiles) {
     g_trace = device_buf;

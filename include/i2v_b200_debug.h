@@ -18,6 +18,11 @@ int i2v_mma_probe(int N, int accs, int a_tmem, int count, int ctas, int issuers 
  * `tiles` tiles into device_buf[tiles][8] (see TcArgs::trace in csrc/conv_tc.cu); NULL switches it off.     */
 int i2v_conv_tc_set_trace(unsigned long long* device_buf, int tiles);
 
+/* Tuning: tiles of at least `min_ksteps` k-steps (taps x Cin/32) of the 3xTF32 / TMA-epilogue configuration run on the
+ * CTA-pair kernel (tcgen05.mma.cta_group::2, half of the weight rows per CTA; csrc/conv_tc.cu: conv_tc_pair_kernel);
+ * 0 = never.  Initial value: $I2V_TC_PAIR.                                                                       */
+int i2v_conv_tc_set_pair_minkit(int min_ksteps);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2,6 +2,8 @@
 native engine's truncated forward + input gradient, against PyTorch float64 on the CPU (the arbiter)
 and float32 (the reference's arithmetic).  Tolerance: max |err| <= 2e-5 * max |ref| for a single layer in
 FP32 mode (observed ~1e-6); the float32 torch result must not be meaningfully closer than ours."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -260,6 +262,52 @@ def _tc_operands(w, scale):
     tf = ws.permute(0, 2, 3, 1).reshape(cout, k * k * cin).contiguous().to(DEV)
     td = ws.flip(2, 3).permute(1, 2, 3, 0).reshape(cin, k * k * cout).contiguous().to(DEV)
     return ws, _split_tf32(tf), _split_tf32(td)
+
+
+@pytest.fixture
+def pair_kernel():
+    """Every 3xTF32 / TMA-epilogue launch of the test runs on the CTA-pair kernel (tcgen05.mma.cta_group::2)."""
+    capi.conv_tc_set_pair_minkit(1)
+    yield
+    capi.conv_tc_set_pair_minkit(int(os.environ.get("I2V_TC_PAIR", "0")))
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_conv_tc_pair_kernel_is_bit_identical(shape, pair_kernel):
+    """The CTA-pair kernel computes every output element with the same operands in the same k-order as the single-CTA
+    dual-issuer kernel, so forward (+bias, residual, ReLU, activity bits) and data gradient (+addend, bit mask) must be
+    BIT-identical to it — odd tile counts (a phantom second m-tile), ragged last tiles and multi-image tiles included."""
+    N, H, W, Cin, Cout, k, s, p = shape
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(N, H, W, Cin, generator=g).to(DEV)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    scale = torch.rand(Cout, generator=g) + 0.5
+    bias = (torch.randn(Cout, generator=g) * 0.1).to(DEV)
+    P, Q = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    res = torch.randn(N, P, Q, Cout, generator=g).to(DEV)
+    d = capi.ConvDesc(N, H, W, Cin, Cout, k, k, s, p, P, Q)
+    ws, (fh, fl, fr), (dh, dl, dr) = _tc_operands(w, scale)
+    out = {}
+    for pair in (0, 1):
+        capi.conv_tc_set_pair_minkit(pair)
+        y = torch.full((N, P, Q, Cout), float("nan"), device=DEV)
+        bits = torch.zeros(Cout // 32, N * P * Q, device=DEV, dtype=torch.int32)
+        capi.conv_tc(d, 0, x, fh, fl, bias, res, None, y, relu=True, mask_bits=bits)
+        y2 = torch.full((N, P, Q, Cout), float("nan"), device=DEV)
+        capi.conv_tc(d, 0, x, fh, fl, bias, None, None, y2, relu=False)
+        dx = None
+        if s == 1 and capi.conv_tc_supported(d, 1):
+            dy = torch.randn(N, P, Q, Cout, generator=torch.Generator().manual_seed(5)).to(DEV)
+            add = torch.randn(N, H, W, Cin, generator=torch.Generator().manual_seed(6)).to(DEV)
+            mb = torch.randint(-2 ** 31, 2 ** 31 - 1, (Cin // 32, N * H * W), generator=torch.Generator().manual_seed(7),
+                               dtype=torch.int64).to(torch.int32).to(DEV)
+            dx = torch.full((N, H, W, Cin), float("nan"), device=DEV)
+            capi.conv_tc(d, 1, dy, dh, dl, None, add, None, dx, mask_bits=mb)
+        out[pair] = (y, bits, y2, dx)
+    assert torch.isfinite(out[1][0]).all() and torch.isfinite(out[1][2]).all()
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
+    if out[0][3] is not None:
+        assert torch.isfinite(out[1][3]).all() and torch.equal(out[0][3], out[1][3])
 
 
 @pytest.mark.parametrize("shape", TC_SHAPES)
