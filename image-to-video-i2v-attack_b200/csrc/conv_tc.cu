@@ -76,6 +76,7 @@ struct TcArgs {
     // accumulator, [6] epilogue done, [7] split warps done with the tile
     unsigned long long* trace;
     int trace_tiles;
+    int dbg;                     // pair kernel timing experiments ($I2V_TC_PAIR_DBG): bit 0 skips MMA1, bit 1 skips MMA2, bit 2 skips the A split (wrong results)
 };
 #define TC_TRACE(slot, tile_no)                                                                          \
     do {                                                                                                   \
@@ -726,6 +727,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                         const int st = it % stages;
                         const uint32_t ph = (uint32_t)(it / stages) & 1;
                         mbar_wait(&full_bar[st], ph);
+                        if (args.dbg & 4) { mbar_arrive(&split_bar[st]); continue; }     // timing experiment: no split work
                         const uint8_t* arow = stage_a(st) + (size_t)row * 128;
                         uint32_t lo[32];
 #pragma unroll
@@ -1059,15 +1061,19 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(smem_u32(bar) & kPeerBitMask) : "memory");
+    // default semantics (release at CTA scope), as cutlass::arch::ClusterBarrier::arrive(cta_id): a .release.cluster here
+    // compiles to MEMBAR.ALL.GPU + CCTL.IVALL per arrive — measured ~1 us per k-step on every split thread.  What crosses
+    // the pair is produced and consumed by the async / tensor-core proxies (TMA writes, tcgen05.st, tcgen05.mma reads),
+    // ordered by the tcgen05 fences around the barrier.
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx_leader(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;"
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;"
                  :: "r"(smem_u32(bar) & kPeerBitMask), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
@@ -1169,8 +1175,8 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 0) {
         // ===== TMA producer (both CTAs): own A tile -> afull (local); own half of the weight rows -> full (leader) =========
         if (lane == 0) {
-            int it = 0;
-            for (int pt = pid; pt < num_ptiles; pt += npairs) {
+            int it = 0, tno = 0;
+            for (int pt = pid; pt < num_ptiles; pt += npairs, ++tno) {
                 const int pm = pt / num_n_tiles, n_tile = pt - pm * num_n_tiles;
                 const int m_tile = 2 * pm + (int)rank;
                 const int64_t m0 = (int64_t)m_tile * TC_BM;
@@ -1190,6 +1196,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             const int st = it % stages;
                             const uint32_t ph = (uint32_t)(it / stages) & 1;
                             mbar_wait(&empty_bar[st], ph ^ 1);
+                            if ((r | s | cb) == 0) TC_TRACE(0, tno);
                             mbar_arrive_expect_tx(&afull_bar[st], TC_A_BYTES);
                             if (IM2COL) tma_load_im2col_4d(&tmA, &afull_bar[st], stage_a(st), cb * TC_BK, base_w, base_h, img, (uint16_t)s, (uint16_t)r);
                             else        tma_load_2d(&tmA, &afull_bar[st], stage_a(st), cb * TC_BK, (int)m0);
@@ -1198,6 +1205,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             tma_load_2d_2sm(&tmBhi, &full_bar[st], stage_b(st), kcol, n0);
                             tma_load_2d_2sm(&tmBlo, &full_bar[st], stage_b(st) + (size_t)H * TC_BK * 4, kcol, n0);
                         }
+                TC_TRACE(1, tno);
             }
         }
     } else if (warp == 1) {
@@ -1210,6 +1218,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const uint32_t aph = (uint32_t)(t / kAcc) & 1;
                 mbar_wait_cluster(&tempty_bar[acc], aph ^ 1);
                 tc_fence_after();
+                TC_TRACE(2, t);
                 const uint32_t d0 = tmem_base + (uint32_t)acc * kAccCols;
                 for (int kb = 0; kb < kiters; ++kb, ++it) {
                     const int st = it % stages;
@@ -1218,14 +1227,16 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     mbar_wait(&afull_bar[st], ph);               // this CTA's a_hi
                     mbar_wait_cluster(&split_bar[st], ph);       // the peer's a_hi (its split threads saw it land)
                     tc_fence_after();
+                    if (kb == 0) TC_TRACE(3, t);
                     const uint64_t da = umma_desc_sw128(smem_u32(stage_a(st)));
                     const uint64_t db = umma_desc_sw128(smem_u32(stage_b(st)));
 #pragma unroll
                     for (int kk = 0; kk < TC_BK / 8; ++kk)
-                        umma2_tf32(d0, da + 2 * kk, db + 2 * kk, idesc2, (kb | kk) ? 1u : 0u);
+                        if (!(args.dbg & 1)) umma2_tf32(d0, da + 2 * kk, db + 2 * kk, idesc2, (kb | kk) ? 1u : 0u);
                     umma2_commit(&empty_bar[st]);
                 }
                 umma2_commit(&tfull_bar[acc]);
+                TC_TRACE(4, t);
             }
         }
     } else if (warp == 2) {
@@ -1249,7 +1260,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const uint32_t talo = tmem_base + kAloBase + (uint32_t)(it % kAloSlots) * 32u;
 #pragma unroll
                     for (int kk = 0; kk < TC_BK / 8; ++kk)
-                        umma2_tf32_ts(d2, talo + 8u * kk, db + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
+                        if (!(args.dbg & 2)) umma2_tf32_ts(d2, talo + 8u * kk, db + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
                     umma2_commit(&empty_bar[st]);
                 }
                 umma2_commit(&tfull_bar[acc]);
@@ -1311,12 +1322,13 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int row = threadIdx.x - 128;
         const uint32_t swz = (uint32_t)(row & 7);
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kAloBase;
-        int it = 0;
-        for (int pt = pid; pt < num_ptiles; pt += npairs) {
+        int it = 0, tno = 0;
+        for (int pt = pid; pt < num_ptiles; pt += npairs, ++tno) {
             for (int kb = 0; kb < kiters; ++kb, ++it) {
                 const int st = it % stages;
                 const uint32_t ph = (uint32_t)(it / stages) & 1;
                 mbar_wait(&afull_bar[st], ph);
+                if (args.dbg & 4) { mbar_arrive_leader(&split_bar[st]); continue; }      // timing experiment: no split work
                 const uint8_t* arow = stage_a(st) + (size_t)row * 128;
                 uint32_t lo[32];
 #pragma unroll
@@ -1332,6 +1344,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tc_fence_before();
                 mbar_arrive_leader(&split_bar[st]);
             }
+            if (row == 0) TC_TRACE(7, tno);
         }
     } else if (warp >= 8) {
         // ===== epilogue v3 (per CTA), pair column map ======================================================================
@@ -1361,6 +1374,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 mw[j] = (mbits && valid) ? __ldg(mbits + (int64_t)(n0 / 32 + g + 2 * j) * args.M + m) : 0xFFFFFFFFu;
             mbar_wait(&tfull_bar[acc], aph);
             tc_fence_after();
+            if (threadIdx.x == 256) TC_TRACE(5, t);
             const uint32_t tacc = tmem_base + (uint32_t)acc * kAccCols + ((uint32_t)((warp & 3) * 32) << 16);
             uint32_t vals[SUBS][32];
 #pragma unroll
@@ -1414,6 +1428,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 fence_proxy_async();
                 mbar_arrive(&out_ready[g * 2 + s]);
             }
+            if (threadIdx.x == 256) TC_TRACE(6, t);
         }
     }
 
@@ -1664,6 +1679,8 @@ static int tc_launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmBhi, cons
     const size_t fixed = 1008 + 1024 + (size_t)slots * 2 * EPI_SLOT_BYTES;
     int stages = (int)((budget - fixed) / kStageBytes);
     if (stages > 4) stages = 4;             // the A_lo ring in tensor memory has 4 slots
+    static const int stages_env = getenv("I2V_TC_PAIR_STAGES") ? atoi(getenv("I2V_TC_PAIR_STAGES")) : 0;
+    if (stages_env >= 2 && stages_env < stages) stages = stages_env;
     if (stages < 2) { set_error("conv_tc (pair): %d pipeline stages fit in shared memory", stages); return I2V_ECUDA; }
     I2V_REQUIRE(args.bias == nullptr || (reinterpret_cast<uintptr_t>(args.bias) & 15) == 0, "bias must be 16-byte aligned");
     const int num_m_tiles = (int)((args.M + TC_BM - 1) / TC_BM), num_n_tiles = args.Cout / BN;
@@ -1675,10 +1692,12 @@ static int tc_launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmBhi, cons
     return I2V_OK;
 }
 
-// minimum k-steps per tile from which the CTA-pair kernel takes over (0 = never); $I2V_TC_PAIR, i2v_conv_tc_set_pair_minkit
-static int g_pair_minkit = -1;
+// CTA-pair kernel selection ($I2V_TC_PAIR, i2v_conv_tc_set_pair_minkit): n > 0 = every tile of >= n k-steps, 0 = never,
+// -1 (default) = where it was measured to win in the attack step (profiles/r02_pair_kernel.md): convolutions that stream a
+// residual / addend through the epilogue, from 4 k-steps per tile
+static int g_pair_minkit = -2;
 static int pair_min_ksteps() {
-    if (g_pair_minkit < 0) g_pair_minkit = getenv("I2V_TC_PAIR") ? atoi(getenv("I2V_TC_PAIR")) : 0;
+    if (g_pair_minkit == -2) g_pair_minkit = getenv("I2V_TC_PAIR") ? atoi(getenv("I2V_TC_PAIR")) : -1;
     return g_pair_minkit;
 }
 
@@ -1749,6 +1768,8 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
     a.taps_h = pr.taps_h; a.taps_w = pr.taps_w; a.cblocks = pr.C / 32; a.relu = pr.relu;
     a.out_s = pr.out_s; a.out_h0 = pr.out_h0; a.out_w0 = pr.out_w0; a.out_H = pr.out_H; a.out_W = pr.out_W;
     a.trace = g_trace; a.trace_tiles = g_trace_tiles;
+    static const int pair_dbg = getenv("I2V_TC_PAIR_DBG") ? atoi(getenv("I2V_TC_PAIR_DBG")) : 0;
+    a.dbg = pair_dbg;
 #define I2V_TC_DISPATCH_P(BN_, EPI_, ALO_)                                                          \
     do {                                                                                            \
         if (x3) return im2col ? tc_launch_persist<BN_, true, true, EPI_, ALO_>(tmA, tmBhi, tmBlo, tmOut, tmRes, a, st)      \
@@ -1770,7 +1791,8 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
             // CTA pairs (tcgen05.mma.cta_group::2, half of the weight rows per CTA): $I2V_TC_PAIR = minimum k-steps per tile
             // from which the pair kernel takes over (0 = never); needs at least two m-tiles
             const int pair_minkit = pair_min_ksteps();
-            if (alo && pair_minkit > 0 && kit >= pair_minkit && !pr.out_transposed && M > TC_BM) {
+            const bool pair_on = pair_minkit > 0 ? kit >= pair_minkit : (pair_minkit == -1 && pr.residual != nullptr && kit >= 4);
+            if (alo && pair_on && !pr.out_transposed && M > TC_BM) {
                 CUtensorMap hBhi, hBlo;
                 if (int r = get_map_2d(&hBhi, pr.w_hi, pr.Cout, Ktot, BN / 2)) return r;
                 if (int r = get_map_2d(&hBlo, pr.w_lo, pr.Cout, Ktot, BN / 2)) return r;
@@ -1818,7 +1840,7 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
 using namespace i2v;
 
 extern "C" int i2v_conv_tc_set_pair_minkit(int min_ksteps) {
-    g_pair_minkit = min_ksteps < 0 ? 0 : min_ksteps;
+    g_pair_minkit = min_ksteps < -1 ? -1 : min_ksteps;
     return I2V_OK;
 }
 

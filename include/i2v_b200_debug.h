@@ -20,7 +20,8 @@ int i2v_conv_tc_set_trace(unsigned long long* device_buf, int tiles);
 
 /* Tuning: tiles of at least `min_ksteps` k-steps (taps x Cin/32) of the 3xTF32 / TMA-epilogue configuration run on the
  * CTA-pair kernel (tcgen05.mma.cta_group::2, half of the weight rows per CTA; csrc/conv_tc.cu: conv_tc_pair_kernel);
- * 0 = never.  Initial value: $I2V_TC_PAIR.                                                                       */
+ * 0 = never; -1 (the default) = only the convolutions that stream a residual / addend through the epilogue, from 4
+ * k-steps — where the pair was measured to win in the attack step.  Initial value: $I2V_TC_PAIR.                  */
 int i2v_conv_tc_set_pair_minkit(int min_ksteps);
 
 #ifdef __cplusplus

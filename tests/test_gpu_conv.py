@@ -269,7 +269,7 @@ def pair_kernel():
     """Every 3xTF32 / TMA-epilogue launch of the test runs on the CTA-pair kernel (tcgen05.mma.cta_group::2)."""
     capi.conv_tc_set_pair_minkit(1)
     yield
-    capi.conv_tc_set_pair_minkit(int(os.environ.get("I2V_TC_PAIR", "0")))
+    capi.conv_tc_set_pair_minkit(int(os.environ.get("I2V_TC_PAIR", "-1")))
 
 
 @pytest.mark.parametrize("shape", TC_SHAPES)
