@@ -402,12 +402,16 @@ def run_b200_arm(args):
     eng = atk._engine
 
     # ---- device-resident arm: W warm-up steps + exactly K timed steps of one attack call --------------
-    run = attack_loop.ImageGuidedRun([eng], EPS, W + K, STEP_SIZE)
+    # The timed steps run the way the product runs them: step 0 eager, step 1 captured into a CUDA graph, the rest
+    # replays (attack_loop.ImageGuidedRun.step) — no per-kernel instrumentation inside the timed region.  The per-kernel
+    # CUDA-event timings behind `roofline` come from K more steps of the SAME run executed eagerly right after it
+    # (events around every launch on the launching stream); their sum over the profiled steps is reported as
+    # `profiled_ms_per_step` next to the graph-replayed `ms_per_step`.
+    run = attack_loop.ImageGuidedRun([eng], EPS, W + 2 * K, STEP_SIZE)
     run.setup(dev_videos)
     for _ in range(W):
         run.step()
     capi.LAUNCHES.clear()
-    capi.PROFILE_EVENTS = []
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
     D.barrier()
     torch.cuda.synchronize()
@@ -420,8 +424,17 @@ def run_b200_arm(args):
     D.barrier()
     clocks = sampler.stop() if sampler else None
     ms_local = ev0.elapsed_time(ev1)
-    events, capi.PROFILE_EVENTS = capi.PROFILE_EVENTS, None
     launches = dict(capi.LAUNCHES)
+    graph_replayed = run._graph is not None
+    capi.PROFILE_EVENTS = []
+    pv0, pv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pv0.record()
+    for _ in range(K):
+        run.step()
+    pv1.record()
+    torch.cuda.synchronize()
+    events, capi.PROFILE_EVENTS = capi.PROFILE_EVENTS, None
+    prof_ms_local = pv0.elapsed_time(pv1)
     res = run.finish()
     chunk_frames = run.chunk
     ms = D.max_over_ranks(ms_local, device)
@@ -442,7 +455,7 @@ def run_b200_arm(args):
     if args.shapes and rank == 0:       # per-shape table of the tensor-core convolutions, in-situ (stderr)
         for detail, d in sorted(by_shape.items(), key=lambda kv: -kv[1]["ms"]):
             print("%-44s n=%-5d avg %7.1f us  %6.0f GB/s  share %.3f" % (detail, d["launches"], 1e3 * d["ms"] / d["launches"],
-                                                                        d["bytes"] / d["ms"] / 1e6, d["ms"] / ms_local), file=sys.stderr)
+                                                                        d["bytes"] / d["ms"] / 1e6, d["ms"] / prof_ms_local), file=sys.stderr)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -467,7 +480,7 @@ def run_b200_arm(args):
         r = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
              "launches": k["launches"], "avg_us": 1e3 * k["ms"] / k["launches"],
              "algorithmic_bytes_per_launch": k["bytes"] / k["launches"],
-             "share_of_step": k["ms"] / ms_local, "traffic": traffic.get(name)}
+             "share_of_step": k["ms"] / prof_ms_local, "traffic": traffic.get(name)}
         if k["flops"] > 0:
             tfl = k["flops"] / (k["ms"] * 1e-3) / 1e12
             mma = 3.0 if engine_name == "native" else 1.0
@@ -479,6 +492,17 @@ def run_b200_arm(args):
         roof_all[name] = r
     dominant = max(roof_all, key=lambda n: kern[n]["ms"]) if roof_all else None
     roofline = dict(roof_all[dominant], kernel=dominant, peak_source=peak_kind) if dominant else None
+    if roofline and "tensor" in roofline and roofline["tensor"]["frac_issued"] > roofline["frac"]:
+        # The convolution launches are a mix of HBM-bound (1x1) and tensor-bound (3x3, K-heavy) shapes; the roofline
+        # that binds the aggregate is the one it sits closer to.  Tensor work is counted as ISSUED MMA flops — the
+        # FP32-parity algorithm needs three TF32 MMAs per MAC (a_hi b_hi + a_hi b_lo + a_lo b_hi) — against the TF32
+        # GEMM rate cuBLAS sustains on this GPU, measured in this run.  The HBM view stays next to it.
+        t = roofline["tensor"]
+        roofline = dict(roofline, bound="tensor", achieved=t["issued"], peak=t["peak"], unit="TFLOP/s", frac=t["frac_issued"],
+                        peak_source=t["peak_source"],
+                        hbm={"achieved": roofline["achieved"], "peak": roofline["peak"], "unit": "GB/s", "frac": roofline["frac"],
+                             "peak_source": peak_kind},
+                        note="issued = 3 x algorithmic flops (3xTF32 FP32-parity mode); frac_algorithmic = %.3f" % t["frac_algorithmic"])
 
     # ---- e2e arm: public drop-in API, host clips in, adversarial clips + cost log out -----------------
     e2e = None
@@ -533,7 +557,9 @@ def run_b200_arm(args):
                                    "clips x %d frames x 3x%dx%d per GPU, FP32 parity mode" % (clips, FRAMES, SIDE, SIDE),
                        "frames_per_gpu": N, "eps": "16/255", "step_size": STEP_SIZE, "engine": engine_name,
                        "weights": "torchvision random init, seed 0", "l2": "inputs_exceed_l2 (no flush needed)",
-                       "chunk_frames": chunk_frames, "final_cost": float(res.cost[-1]) if len(res.cost) else None},
+                       "chunk_frames": chunk_frames, "final_cost": float(res.cost[-1]) if len(res.cost) else None,
+                       "timed_steps": "CUDA-graph replay of the step" if graph_replayed else "eager launches",
+                       "profiled_ms_per_step": prof_ms_local / K},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(sum(launches.values())),
             "gpu_launches_by_kernel": launches, "roofline": roofline, "roofline_all": roof_all,
             "cpu_baseline": cpu_base, "cudnn_baseline": cudnn_base, "tf32_peak": tf32_meas, "ensemble": ens,
