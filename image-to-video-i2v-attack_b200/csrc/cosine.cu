@@ -44,8 +44,10 @@ __device__ __forceinline__ float cos_grad1(float a, float b, const CosCoef& c) {
     return __fadd_rn(__fsub_rn(g1, e), lo);
 }
 
-template <bool VEC>
-__global__ void __launch_bounds__(kCosThreads, 2)
+// THREADS = 512 with two CTAs per SM (each stashes half an SM's shared memory) or 1024 with ONE CTA per SM that owns the
+// whole 227 KB: same threads and loads in flight per SM, twice the stash per frame slice, half the frames in flight.
+template <bool VEC, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 cosine_loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ grad,
                         float* __restrict__ cos_out, int64_t D, const float* __restrict__ w_dev, float w_host,
                         int relu_mask, int64_t cap, int64_t N, int hint_mode) {
@@ -53,7 +55,7 @@ cosine_loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b
     cg::cluster_group cluster = cg::this_cluster();
     const unsigned S = cluster.num_blocks();
     const unsigned rank = cluster.block_rank();
-    __shared__ CosPartial warp_part[kCosThreads / 32];
+    __shared__ CosPartial warp_part[THREADS / 32];
     __shared__ CosPartial cta_part;
     __shared__ CosCoef coef;
     // L2 hints: what the gradient pass will re-read from L2 (the un-stashed tail of the slice) is loaded evict_last,
@@ -91,17 +93,17 @@ cosine_loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b
         float4* sb = stash + cap;
         int64_t i = lo + threadIdx.x;
         // kUnroll independent 16-byte loads per tensor in flight per thread
-        for (; i + (int64_t)(kUnroll - 1) * kCosThreads < hi; i += (int64_t)kUnroll * kCosThreads) {
+        for (; i + (int64_t)(kUnroll - 1) * THREADS < hi; i += (int64_t)kUnroll * THREADS) {
             float4 av[kUnroll], bv[kUnroll];
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
-                const uint64_t pol = (i + u * kCosThreads - lo < cap) ? pol_stream : pol_keep;
-                av[u] = hints ? ld_hint(a4 + i + u * kCosThreads, pol) : ld_stream(a4 + i + u * kCosThreads);
-                bv[u] = hints ? ld_hint(b4 + i + u * kCosThreads, pol) : ld_stream(b4 + i + u * kCosThreads);
+                const uint64_t pol = (i + u * THREADS - lo < cap) ? pol_stream : pol_keep;
+                av[u] = hints ? ld_hint(a4 + i + u * THREADS, pol) : ld_stream(a4 + i + u * THREADS);
+                bv[u] = hints ? ld_hint(b4 + i + u * THREADS, pol) : ld_stream(b4 + i + u * THREADS);
             }
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
-                const int64_t k = i + u * kCosThreads - lo;
+                const int64_t k = i + u * THREADS - lo;
                 if (k < cap) { sa[k] = av[u]; sb[k] = bv[u]; }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -110,7 +112,7 @@ cosine_loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b
                 }
             }
         }
-        for (; i < hi; i += kCosThreads) {
+        for (; i < hi; i += THREADS) {
             const int64_t k = i - lo;
             const uint64_t pol = (k < cap) ? pol_stream : pol_keep;
             float4 av = hints ? ld_hint(a4 + i, pol) : ld_stream(a4 + i), bv = hints ? ld_hint(b4 + i, pol) : ld_stream(b4 + i);
@@ -122,7 +124,7 @@ cosine_loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b
             }
         }
     } else {
-        for (int64_t i = lo + threadIdx.x; i < hi; i += kCosThreads) {
+        for (int64_t i = lo + threadIdx.x; i < hi; i += THREADS) {
             const float x = af[i], y = bf[i];
             d4[0] = __fmaf_rn(x, y, d4[0]); p4[0] = __fmaf_rn(x, x, p4[0]); q4[0] = __fmaf_rn(y, y, q4[0]);
         }
@@ -141,7 +143,7 @@ cosine_loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b
     if (pending) { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); pending = false; }
     if (threadIdx.x < 32) {
         CosPartial s{0.0, 0.0, 0.0};
-        if (threadIdx.x < kCosThreads / 32) s = warp_part[threadIdx.x];
+        if (threadIdx.x < THREADS / 32) s = warp_part[threadIdx.x];
         s.dot = warp_sum(s.dot); s.aa = warp_sum(s.aa); s.bb = warp_sum(s.bb);
         if (threadIdx.x == 0) cta_part = s;
     }
@@ -182,9 +184,9 @@ cosine_loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b
         // backwards: the un-stashed tail of the slice was read last in pass 1 and is the hottest in L2;
         // each thread revisits exactly the vectors it stashed itself (same i mod 512), so the stash
         // needs no barrier of its own.
-        const int64_t last = lo + ((hi - 1 - lo - threadIdx.x) / kCosThreads) * kCosThreads + threadIdx.x;
+        const int64_t last = lo + ((hi - 1 - lo - threadIdx.x) / THREADS) * THREADS + threadIdx.x;
 #pragma unroll 4
-        for (int64_t i = (hi - lo > (int64_t)threadIdx.x) ? last : lo - 1; i >= lo; i -= kCosThreads) {
+        for (int64_t i = (hi - lo > (int64_t)threadIdx.x) ? last : lo - 1; i >= lo; i -= THREADS) {
             const int64_t k = i - lo;
             float4 av, bv, r;
             if (k < cap) { av = sa[k]; bv = sb[k]; }
@@ -199,7 +201,7 @@ cosine_loss_grad_kernel(const float* __restrict__ a, const float* __restrict__ b
             if (hints) st_hint(g4 + i, r, pol_stream); else st_stream(g4 + i, r);
         }
     } else {
-        for (int64_t i = hi - 1 - threadIdx.x; i >= lo; i -= kCosThreads) {
+        for (int64_t i = hi - 1 - threadIdx.x; i >= lo; i -= THREADS) {
             const float x = af[i];
             const float gval = cos_grad1(x, bf[i], c);
             gf[i] = (relu_mask && !(x > 0.0f)) ? 0.0f : gval;
@@ -291,12 +293,12 @@ static int pick_cluster(int64_t N, int64_t units) {
     return S;
 }
 
-template <bool VEC>
-static int cosine_launch(const float* a, const float* b, float* grad_a, float* cos_out, int64_t N, int64_t D,
+template <bool VEC, int THREADS>
+static int cosine_launch_t(const float* a, const float* b, float* grad_a, float* cos_out, int64_t N, int64_t D,
                          const float* w_dev, float w_host, int relu_mask, cudaStream_t st) {
     static int smem_optin = -1;
     static bool attr_done = false;
-    auto kern = cosine_loss_grad_kernel<VEC>;
+    auto kern = cosine_loss_grad_kernel<VEC, THREADS>;
     if (smem_optin < 0) {
         int dev = 0, v = 0;
         cudaGetDevice(&dev);
@@ -306,8 +308,7 @@ static int cosine_launch(const float* a, const float* b, float* grad_a, float* c
     const int64_t units = VEC ? D / 4 : D;
     // Two CTAs share an SM so that one CTA's load phase overlaps the other's reduce/store phase; each
     // gets half of the shared memory for its stash.  I2V_COS_CTAS_PER_SM=1 gives one CTA the whole SM.
-    int per_sm = 2;
-    if (const char* e = getenv("I2V_COS_CTAS_PER_SM")) { int v = atoi(e); if (v == 1 || v == 2) per_sm = v; }
+    const int per_sm = 1024 / THREADS;
     const int64_t cap_max = VEC ? ((smem_optin - 2048) / per_sm - 1024) / 32 : 0;   // float4 pairs per CTA
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 2048);
@@ -322,7 +323,7 @@ static int cosine_launch(const float* a, const float* b, float* grad_a, float* c
         const int64_t cap = !VEC || grad_a == nullptr ? 0 : (slice <= cap_max ? slice : cap_max);
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)(N * S));   // upper bound; trimmed to the co-resident cluster count below
-        cfg.blockDim = dim3(kCosThreads);
+        cfg.blockDim = dim3(THREADS);
         cfg.dynamicSmemBytes = (size_t)cap * 32;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
@@ -344,6 +345,15 @@ static int cosine_launch(const float* a, const float* b, float* grad_a, float* c
         if (e != cudaSuccess) return cuda_fail(e, "i2v_cosine_loss_grad_f32");
         return I2V_OK;
     }
+}
+
+// $I2V_COS_CTAS_PER_SM = 2 (default): 512-thread CTAs, two per SM; 1: 1024-thread CTAs, one per SM
+template <bool VEC>
+static int cosine_launch(const float* a, const float* b, float* grad_a, float* cos_out, int64_t N, int64_t D,
+                         const float* w_dev, float w_host, int relu_mask, cudaStream_t st) {
+    static const int per_sm = getenv("I2V_COS_CTAS_PER_SM") ? atoi(getenv("I2V_COS_CTAS_PER_SM")) : 2;
+    if (per_sm == 1) return cosine_launch_t<VEC, 1024>(a, b, grad_a, cos_out, N, D, w_dev, w_host, relu_mask, st);
+    return cosine_launch_t<VEC, 512>(a, b, grad_a, cos_out, N, D, w_dev, w_host, relu_mask, st);
 }
 
 extern "C" int i2v_cosine_loss_grad_f32(const float* a, const float* b, float* grad_a, float* cos_out, int64_t N,
