@@ -62,6 +62,8 @@ SIGNATURES = {
     "i2v_conv_stem_fwd_direct_supported": ([_c_p], _c_int),
     "i2v_conv_stem_fwd_direct_scratch_floats": ([_c_p], _c_i64),
     "i2v_conv_stem_fwd_direct_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
+    "i2v_conv_stem_dgrad_direct_supported": ([_c_p], _c_int),
+    "i2v_conv_stem_dgrad_direct_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p], _c_int),
     "i2v_conv_stem_fwd_tc_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_tc_supported": ([_c_p, _c_int], _c_int),
     "i2v_conv_tc_set_trace": ([_c_p, _c_int], _c_int),
@@ -118,7 +120,7 @@ def load():
 # tensors read + written once, 2 x MACs of the convolution).
 LAUNCHES = {}
 PROFILE_EVENTS = None
-_NO_KERNEL = ("i2v_set_adam_arithmetic", "i2v_conv_tc_set_pair_minkit", "i2v_conv_stem_fwd_direct_supported", "i2v_conv_stem_fwd_direct_scratch_floats", "i2v_conv_stem_dgrad_tc_rows", "i2v_device_check", "i2v_std_workspace_doubles", "i2v_ila_workspace_doubles", "i2v_adam_step_table", "i2v_conv_tc_supported", "i2v_conv_stem_supported",
+_NO_KERNEL = ("i2v_set_adam_arithmetic", "i2v_conv_stem_dgrad_direct_supported", "i2v_conv_tc_set_pair_minkit", "i2v_conv_stem_fwd_direct_supported", "i2v_conv_stem_fwd_direct_scratch_floats", "i2v_conv_stem_dgrad_tc_rows", "i2v_device_check", "i2v_std_workspace_doubles", "i2v_ila_workspace_doubles", "i2v_adam_step_table", "i2v_conv_tc_supported", "i2v_conv_stem_supported",
               "i2v_conv_tc_set_trace")
 
 
@@ -438,6 +440,28 @@ def conv_stem_dgrad_tc(desc, dy, wz_hi, wz_lo, z_scratch, dx):
     with _Timed("i2v_conv_stem_dgrad_f32", nb, fl):
         _check(load().i2v_conv_stem_dgrad_tc_f32(ctypes.addressof(desc), _dev(dy), _dev(wz_hi), _dev(wz_lo), _dev(z_scratch),
                                                  _dev(dx), _stream()), "i2v_conv_stem_dgrad_tc_f32")
+
+
+def conv_stem_dgrad_direct_supported(desc):
+    return bool(load().i2v_conv_stem_dgrad_direct_supported(ctypes.addressof(desc)))
+
+
+def conv_stem_dgrad_direct(desc, dy, wd_hi, wd_lo, dx):
+    """First-layer data gradient without scratch (see include/i2v_b200.h); wd_* from stem_direct_dgrad_weights()."""
+    nb, fl = _conv_cost(desc)
+    with _Timed("i2v_conv_stem_dgrad_f32", nb, fl):
+        _check(load().i2v_conv_stem_dgrad_direct_f32(ctypes.addressof(desc), _dev(dy), _dev(wd_hi), _dev(wd_lo), _dev(dx),
+                                                     _stream()), "i2v_conv_stem_dgrad_direct_f32")
+
+
+def stem_direct_dgrad_weights(w_stem):
+    """[(c,r,s) = 147, 64] -> [160, 64]: taps 0..76 | 3 zero rows | taps 77..146 | 10 zero rows (two N = 80 halves that end on
+    (c,r) group boundaries: 11 and 10 groups of 7 taps)."""
+    assert w_stem.shape == (147, 64)
+    out = w_stem.new_zeros(160, 64)
+    out[:77] = w_stem[:77]
+    out[80:150] = w_stem[77:]
+    return out.contiguous()
 
 
 def stem_dgrad_tc_rows(cols):

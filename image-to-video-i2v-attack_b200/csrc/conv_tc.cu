@@ -76,7 +76,7 @@ struct TcArgs {
     // accumulator, [6] epilogue done, [7] split warps done with the tile
     unsigned long long* trace;
     int trace_tiles;
-    int dbg;                     // pair kernel timing experiments ($I2V_TC_PAIR_DBG): bit 0 skips MMA1, bit 1 skips MMA2, bit 2 skips the A split (wrong results)
+    int dbg;                     // pair kernel timing experiments ($I2V_TC_PAIR_DBG): bit 0 skips MMA1, bit 1 skips MMA2, bit 2 skips the A split, bit 3 skips the weight loads (wrong results)
 };
 #define TC_TRACE(slot, tile_no)                                                                          \
     do {                                                                                                   \
@@ -563,7 +563,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                             if ((r | s | cb) == 0) TC_TRACE(0, tno);
                             // (measured: deriving B_lo on the fly in the split warps instead of loading it — 25-33 % fewer TMA
                             // rows per k-step — made every layer 5-15 % SLOWER: the four split warps are the tighter resource)
-                            mbar_arrive_expect_tx(&full_bar[st], TC_A_BYTES + L::B_BYTES * (X3 ? 2 : 1));
+                            const bool no_b = (args.dbg & 8) != 0;          // timing experiment: the weight tiles are not loaded
+                            mbar_arrive_expect_tx(&full_bar[st], TC_A_BYTES + (no_b ? 0u : L::B_BYTES * (X3 ? 2 : 1)));
                             if (IM2COL) tma_load_im2col_4d(&tmA, &full_bar[st], stage_a(st), cb * TC_BK, base_w, base_h, img, (uint16_t)s, (uint16_t)r);
                             else if (args.stem4d) {
                                 // filter row r of a 16 x 8 pixel box: 32 floats (8 padded pixels x 4) per output pixel, rows of
@@ -575,8 +576,10 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                             }
                             else        tma_load_2d(&tmA, &full_bar[st], stage_a(st), cb * TC_BK, (int)m0);
                             const int kcol = ((r * args.taps_w + s) * args.cblocks + cb) * TC_BK;
-                            tma_load_2d(&tmBhi, &full_bar[st], stage_bhi(st), kcol, n0);
-                            if (X3) tma_load_2d(&tmBlo, &full_bar[st], stage_blo(st), kcol, n0);
+                            if (!no_b) {
+                                tma_load_2d(&tmBhi, &full_bar[st], stage_bhi(st), kcol, n0);
+                                if (X3) tma_load_2d(&tmBlo, &full_bar[st], stage_blo(st), kcol, n0);
+                            }
                         }
                 TC_TRACE(1, tno);
             }
@@ -607,6 +610,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     if (X3 && !ALO_TMEM) dal = umma_desc_sw128(smem_u32(stage_alo(st)));
 #pragma unroll
                     for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                        if (args.dbg & 1) continue;                                  // timing experiment: no MMA
                         if (X3) {
                             // [main | cross] += a_hi x [b_hi | b_lo]  (N = 2*BN), then cross += a_lo x b_hi
                             umma_tf32(d0, da + 2 * kk, dbh + 2 * kk, idesc2, (kb | kk) ? 1u : 0u);
@@ -642,7 +646,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     const uint32_t talo = tmem_base + kAloBase + (uint32_t)(it % kAloSlots) * 32u;
 #pragma unroll
                     for (int kk = 0; kk < TC_BK / 8; ++kk)
-                        umma_tf32_ts(d2, talo + 8u * kk, dbh + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
+                        if (!(args.dbg & 2)) umma_tf32_ts(d2, talo + 8u * kk, dbh + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
                     umma_commit(&empty_bar[st]);
                 }
                 umma_commit(&tfull_bar[acc]);
@@ -1441,6 +1445,307 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------
+// First-layer data gradient WITHOUT the Z^T scratch (i2v_conv_stem_dgrad_direct_f32; 7x7 / stride 2 / pad 3, 64 output
+// channels, Q <= 128: ResNet's and DenseNet's stem).  The GEMM + col2im pair above moves 4.85 GB through HBM for 0.98 GB of
+// tensors (ncu: GEMM 823 MB in, 1 998 MB of Z^T out; col2im 1 875 MB in): 1.24 ms per 256 frames.  Here the col2im happens on
+// chip.  A tile is ONE dy row (n, p): 128 TMEM lanes = the row's Q pixels (lanes >= Q are junk and zeroed).  The contraction
+// over the 64 output channels gives Z[q][(c,r,s)] in tensor memory (two N = 80 halves of the 147 padded taps, each half
+// double-buffered against the epilogue; 3xTF32: main += a_hi b_hi, cross += a_hi b_lo + a_lo b_hi, A_lo in a TMEM ring).
+// Epilogue thread q owns image columns 2q and 2q+1: column w receives Z[q'][c][r][s] with 2q' - 3 + s = w, i.e. its own
+// s = 3 / 4, lane q+1's s = 1 / 2, lane q+2's s = 0 and lane q-1's s = 5 / 6 — warp shuffles, plus a 6-float-per-group
+// exchange through shared memory at warp edges.  The sums go into a REGISTER window of the 7 image rows 2p-3 .. 2p+3 that
+// dy row p touches (3 channels x 7 rows x 2 columns per thread); after row p the rows 2p-3 and 2p-2 are complete, are
+// written to dcost/dimage [N,3,H,W] with coalesced float2 stores and the window shifts down by two.  A CTA walks a strip of
+// consecutive dy rows (half an image: 2N strips over the SMs; the second half re-computes three rows), so every dx element
+// is summed in a fixed order (dy rows ascending, taps s ascending): bit-reproducible, no atomics, no scratch.
+// HBM traffic = dy once + dx once.
+// ---------------------------------------------------------------------------------------------
+constexpr int SD_THREADS = 384;          // warp 0 producer, 1 MMA issuer, 2 TMEM allocator, 4-7 A split, 8-11 epilogue
+constexpr int SD_STAGES = 3;             // A stages (one dy row each: two 16 KB k-blocks); the A_lo ring has 2 slots per stage
+constexpr int SD_NH = 80;                // taps per half (77 / 70 real ones): UMMA N
+constexpr uint32_t SD_B_TILE = SD_NH * TC_BK * 4;      // 10 KB: 80 taps x 32 channels
+
+struct StemDirectArgs {
+    float* dx;
+    int N, H, W, P, Q;
+    int units;                           // strips: 2 per image (1 when the image is small)
+    int strips_per_image;
+};
+
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
+
+// strip u -> image, dy rows [pa, pb] it needs and image rows [ha, hb) it writes
+__device__ __forceinline__ void sd_strip(const StemDirectArgs& a, int u, int& img, int& pa, int& pb, int& ha, int& hb) {
+    img = u / a.strips_per_image;
+    const int part = u - img * a.strips_per_image;
+    const int hs = a.strips_per_image == 2 ? ((a.H / 2) & ~1) : a.H;      // even split row
+    ha = part == 0 ? 0 : hs;
+    hb = (part == 0 && a.strips_per_image == 2) ? hs : a.H;
+    pa = ha - 3 > 0 ? (ha - 3 + 1) / 2 : 0;                              // dy rows p with 2p-3 <= h <= 2p+3 for some h in [ha, hb)
+    pb = (hb - 1 + 3) / 2; if (pb > a.P - 1) pb = a.P - 1;
+}
+
+__global__ void __launch_bounds__(SD_THREADS, 1)
+stem_dgrad_direct_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                         const __grid_constant__ CUtensorMap tmBlo, const StemDirectArgs args) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* bhi = smem;                                       // [half][kb] tiles of 10 KB
+    uint8_t* blo = smem + 4 * SD_B_TILE;
+    uint8_t* atiles = smem + 8 * SD_B_TILE;                    // 80 KB = 1024-aligned
+    float* edge = reinterpret_cast<float*>(atiles + (size_t)SD_STAGES * 2 * TC_A_BYTES);   // [2 buffers][4 warps][11 groups][6]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(edge + 2 * 4 * 11 * 6);
+    uint64_t* bfull = bars;
+    uint64_t* afull = bfull + 1;
+    uint64_t* aempty = afull + SD_STAGES;
+    uint64_t* splitb = aempty + SD_STAGES;
+    uint64_t* tfull = splitb + SD_STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto a_tile = [&](int st, int kb) { return atiles + ((size_t)st * 2 + kb) * TC_A_BYTES; };
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA); prefetch_tmap(&tmBhi); prefetch_tmap(&tmBlo);
+        mbar_init(bfull, 1);
+        for (int s = 0; s < SD_STAGES; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); mbar_init(&splitb[s], 128); }
+        for (int h = 0; h < 2; ++h) { mbar_init(&tfull[h], 1); mbar_init(&tempty[h], 128); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // tensor memory: half h: main at 160h, cross at 160h + 80; A_lo ring slot (stage, kb) at 320 + 32 (2 stage + kb)
+    constexpr uint32_t kRing = 320;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // the weights stay resident: [half][kb] x (hi, lo)
+            mbar_arrive_expect_tx(bfull, 8 * SD_B_TILE);
+            for (int h = 0; h < 2; ++h)
+                for (int kb = 0; kb < 2; ++kb) {
+                    tma_load_2d(&tmBhi, bfull, bhi + (size_t)(h * 2 + kb) * SD_B_TILE, kb * TC_BK, h * SD_NH);
+                    tma_load_2d(&tmBlo, bfull, blo + (size_t)(h * 2 + kb) * SD_B_TILE, kb * TC_BK, h * SD_NH);
+                }
+            int t = 0;
+            for (int u = blockIdx.x; u < args.units; u += gridDim.x) {
+                int img, pa, pb, ha, hb;
+                sd_strip(args, u, img, pa, pb, ha, hb);
+                for (int p = pa; p <= pb; ++p, ++t) {
+                    const int st = t % SD_STAGES;
+                    const uint32_t ph = (uint32_t)(t / SD_STAGES) & 1;
+                    mbar_wait(&aempty[st], ph ^ 1);
+                    mbar_arrive_expect_tx(&afull[st], 2 * TC_A_BYTES);
+                    const int m0 = (img * args.P + p) * args.Q;
+                    tma_load_2d(&tmA, &afull[st], a_tile(st, 0), 0, m0);
+                    tma_load_2d(&tmA, &afull[st], a_tile(st, 1), TC_BK, m0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(SD_NH);
+            mbar_wait(bfull, 0);
+            int t = 0;
+            for (int u = blockIdx.x; u < args.units; u += gridDim.x) {
+                int img, pa, pb, ha, hb;
+                sd_strip(args, u, img, pa, pb, ha, hb);
+                for (int p = pa; p <= pb; ++p, ++t) {
+                    const int st = t % SD_STAGES;
+                    const uint32_t ph = (uint32_t)(t / SD_STAGES) & 1;
+                    mbar_wait(&afull[st], ph);
+                    mbar_wait(&splitb[st], ph);
+                    tc_fence_after();
+                    for (int h = 0; h < 2; ++h) {
+                        mbar_wait(&tempty[h], ((uint32_t)t & 1) ^ 1);
+                        tc_fence_after();
+                        const uint32_t dmain = tmem_base + (uint32_t)h * 160u, dcross = dmain + SD_NH;
+                        for (int kb = 0; kb < 2; ++kb) {
+                            const uint64_t da = umma_desc_sw128(smem_u32(a_tile(st, kb)));
+                            const uint64_t dbh = umma_desc_sw128(smem_u32(bhi + (size_t)(h * 2 + kb) * SD_B_TILE));
+                            const uint64_t dbl = umma_desc_sw128(smem_u32(blo + (size_t)(h * 2 + kb) * SD_B_TILE));
+                            const uint32_t talo = tmem_base + kRing + 32u * (uint32_t)(2 * st + kb);
+#pragma unroll
+                            for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                                umma_tf32(dmain, da + 2 * kk, dbh + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
+                                umma_tf32(dcross, da + 2 * kk, dbl + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
+                                umma_tf32_ts(dcross, talo + 8u * kk, dbh + 2 * kk, idesc, 1u);
+                            }
+                        }
+                        umma_commit(&tfull[h]);
+                    }
+                    umma_commit(&aempty[st]);
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // A split: a_lo of this thread's dy pixel (row of the tile), both k-blocks, into the stage's two ring slots
+        const int row = threadIdx.x - 128;
+        const uint32_t swz = (uint32_t)(row & 7);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kRing;
+        int t = 0;
+        for (int u = blockIdx.x; u < args.units; u += gridDim.x) {
+            int img, pa, pb, ha, hb;
+            sd_strip(args, u, img, pa, pb, ha, hb);
+            for (int p = pa; p <= pb; ++p, ++t) {
+                const int st = t % SD_STAGES;
+                const uint32_t ph = (uint32_t)(t / SD_STAGES) & 1;
+                mbar_wait(&afull[st], ph);
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb) {
+                    const uint8_t* arow = a_tile(st, kb) + (size_t)row * 128;
+                    uint32_t lo[32];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 v = *reinterpret_cast<const float4*>(arow + (((uint32_t)c ^ swz) << 4));
+                        lo[4 * c + 0] = __float_as_uint(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u));
+                        lo[4 * c + 1] = __float_as_uint(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
+                        lo[4 * c + 2] = __float_as_uint(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u));
+                        lo[4 * c + 3] = __float_as_uint(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+                    }
+                    tmem_st32(lane_addr + 32u * (uint32_t)(2 * st + kb), lo);
+                }
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                mbar_arrive(&splitb[st]);
+            }
+        }
+    } else if (warp >= 8) {
+        // ===== epilogue: on-chip col2im into a register window, one thread per dy pixel q = two image columns ==============
+        const int ew = warp - 8;                                  // TMEM lane quarter (warps 8..11 -> warp % 4 = 0..3)
+        const int q = ew * 32 + lane;
+        const bool qvalid = q < args.Q;
+        const uint32_t tlane = tmem_base + ((uint32_t)(ew * 32) << 16);
+        float win[3][7][2];                                       // [channel][image row 2p-3+i][column 2q+e]
+        int t = 0, hbuf = 0;
+        for (int u = blockIdx.x; u < args.units; u += gridDim.x) {
+            int img, pa, pb, ha, hb;
+            sd_strip(args, u, img, pa, pb, ha, hb);
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int i = 0; i < 7; ++i) { win[c][i][0] = 0.f; win[c][i][1] = 0.f; }
+            float* dximg = args.dx + (int64_t)img * 3 * args.H * args.W;
+            auto emit = [&](int slot_row_h, const float (&w0)[2], int c) {      // one (channel, image row) pair of this thread
+                if (slot_row_h < ha || slot_row_h >= hb) return;
+                float* o = dximg + ((int64_t)c * args.H + slot_row_h) * args.W + 2 * q;
+                if (2 * q + 1 < args.W) {
+                    if ((args.W & 1) == 0) *reinterpret_cast<float2*>(o) = make_float2(w0[0], w0[1]);
+                    else { o[0] = w0[0]; o[1] = w0[1]; }
+                } else if (2 * q < args.W) o[0] = w0[0];
+            };
+            for (int p = pa; p <= pb; ++p, ++t) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h, hbuf ^= 1) {
+                    constexpr int G0 = 11;                         // half 0: groups (c,r) 0..10 (77 taps), half 1: 11..20 (70 taps)
+                    mbar_wait(&tfull[h], (uint32_t)t & 1);
+                    tc_fence_after();
+                    float z[SD_NH];
+                    {
+                        uint32_t m0[32], c0[32];
+                        tmem_ld32_nowait(tlane + (uint32_t)h * 160u, m0);
+                        tmem_ld32_nowait(tlane + (uint32_t)h * 160u + SD_NH, c0);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) z[i] = __fadd_rn(__uint_as_float(m0[i]), __uint_as_float(c0[i]));
+                        tmem_ld32_nowait(tlane + (uint32_t)h * 160u + 32u, m0);
+                        tmem_ld32_nowait(tlane + (uint32_t)h * 160u + SD_NH + 32u, c0);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) z[32 + i] = __fadd_rn(__uint_as_float(m0[i]), __uint_as_float(c0[i]));
+                        uint32_t m1[16], c1[16];
+                        tmem_ld16_nowait(tlane + (uint32_t)h * 160u + 64u, m1);
+                        tmem_ld16_nowait(tlane + (uint32_t)h * 160u + SD_NH + 64u, c1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) z[64 + i] = __fadd_rn(__uint_as_float(m1[i]), __uint_as_float(c1[i]));
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&tempty[h]);                       // the accumulator half is in registers: the MMA warp may reuse it
+                    if (!qvalid) {
+#pragma unroll
+                        for (int i = 0; i < SD_NH; ++i) z[i] = 0.f;    // lanes beyond the row belong to the next dy row
+                    }
+                    const int ng = h == 0 ? G0 : 21 - G0;
+                    float* eb = edge + (size_t)hbuf * (4 * 11 * 6);
+                    // publish what the neighbouring warps need: lane 0 -> s = 0,1,2; lane 1 -> s = 0; lane 31 -> s = 5,6
+#pragma unroll
+                    for (int g = 0; g < 11; ++g) {
+                        if (g >= ng) break;
+                        float* e = eb + ((size_t)ew * 11 + g) * 6;
+                        if (lane == 0) { e[0] = z[g * 7 + 0]; e[1] = z[g * 7 + 1]; e[2] = z[g * 7 + 2]; }
+                        if (lane == 1) e[3] = z[g * 7 + 0];
+                        if (lane == 31) { e[4] = z[g * 7 + 5]; e[5] = z[g * 7 + 6]; }
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+                    for (int g = 0; g < 11; ++g) {
+                        if (g >= ng) break;
+                        const int gg = h == 0 ? g : g + G0;        // global group = c * 7 + r
+                        const int c = gg / 7, r = gg - c * 7;
+                        const float* zz = z + g * 7;
+                        float v1 = __shfl_down_sync(0xffffffffu, zz[1], 1);
+                        float v2 = __shfl_down_sync(0xffffffffu, zz[2], 1);
+                        float v0 = __shfl_down_sync(0xffffffffu, zz[0], 2);
+                        float v5 = __shfl_up_sync(0xffffffffu, zz[5], 1);
+                        float v6 = __shfl_up_sync(0xffffffffu, zz[6], 1);
+                        const float* en = eb + ((size_t)(ew + 1) * 11 + g) * 6;    // next warp's edge values (ew < 3)
+                        const float* ep = eb + ((size_t)(ew - 1) * 11 + g) * 6;    // previous warp's (ew > 0)
+                        if (lane == 31) { v1 = ew < 3 ? en[1] : 0.f; v2 = ew < 3 ? en[2] : 0.f; v0 = ew < 3 ? en[3] : 0.f; }
+                        if (lane == 30) v0 = ew < 3 ? en[0] : 0.f;
+                        if (lane == 0) { v5 = ew > 0 ? ep[4] : 0.f; v6 = ew > 0 ? ep[5] : 0.f; }
+                        // column 2q: s = 1 (q+1), 3 (q), 5 (q-1); column 2q+1: s = 0 (q+2), 2 (q+1), 4 (q), 6 (q-1)
+                        const float e0 = __fadd_rn(__fadd_rn(v1, zz[3]), v5);
+                        const float e1 = __fadd_rn(__fadd_rn(__fadd_rn(v0, v2), zz[4]), v6);
+#pragma unroll
+                        for (int cc = 0; cc < 3; ++cc)
+#pragma unroll
+                            for (int rr = 0; rr < 7; ++rr)
+                                if (cc == c && rr == r) {
+                                    win[cc][rr][0] = __fadd_rn(win[cc][rr][0], e0);
+                                    win[cc][rr][1] = __fadd_rn(win[cc][rr][1], e1);
+                                }
+                    }
+                }
+                // image rows 2p-3 and 2p-2 are complete
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { emit(2 * p - 3, win[c][0], c); emit(2 * p - 2, win[c][1], c); }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) { win[c][i][0] = win[c][i + 2][0]; win[c][i][1] = win[c][i + 2][1]; }
+                    win[c][5][0] = win[c][5][1] = win[c][6][0] = win[c][6][1] = 0.f;
+                }
+            }
+            // strip done: the window holds image rows 2 pb - 1 .. 2 pb + 3
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int i = 0; i < 5; ++i) emit(2 * pb - 1 + i, win[c][i], c);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host: tensor maps (driver entry points resolved at run time: no link-time libcuda dependency)
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1956,6 +2261,45 @@ extern "C" int i2v_conv_stem_dgrad_tc_f32(const i2v_conv_desc* d, const float* d
         if (int r = stem_col2im_launch(z_scratch, dx + (int64_t)n0 * 3 * d->H * d->W, n, d->H, d->W, d->P, d->Q, d->R, d->stride,
                                        d->pad, as_stream(stream))) return r;
     }
+    return I2V_OK;
+}
+
+// First-layer data gradient without scratch (stem_dgrad_direct_kernel).  wd_hi / wd_lo = [160, 64] K-major: the taps
+// k = (c, r, s) of w_stem in two halves — rows 0..76 = taps 0..76 (groups (c,r) 0..10), 77..79 zero, rows 80..149 = taps
+// 77..146, 150..159 zero — split into hi = w (the tensor core truncates) and lo = w - trunc_tf32(w).
+extern "C" int i2v_conv_stem_dgrad_direct_supported(const i2v_conv_desc* d) {
+    return d && d->Cin == 3 && d->Cout == 64 && d->R == 7 && d->S == 7 && d->stride == 2 && d->pad == 3 && d->Q >= 1 &&
+           d->Q <= TC_BM && d->P >= 1 && d->W <= 2 * d->Q && d->H <= 2 * d->P;
+}
+
+extern "C" int i2v_conv_stem_dgrad_direct_f32(const i2v_conv_desc* d, const float* dy, const float* wd_hi, const float* wd_lo,
+                                              float* dx, i2v_stream_t stream) {
+    I2V_REQUIRE(d && dy && wd_hi && wd_lo && dx, "null pointer");
+    I2V_REQUIRE(i2v_conv_stem_dgrad_direct_supported(d), "shape not supported by the direct first-layer data gradient");
+    I2V_REQUIRE(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(wd_hi) | reinterpret_cast<uintptr_t>(wd_lo) |
+                  reinterpret_cast<uintptr_t>(dx)) & 15) == 0, "all tensors must be 16-byte aligned");
+    if (d->N == 0) return I2V_OK;
+    if (int r = resolve_driver()) return r;
+    const int64_t M = (int64_t)d->N * d->P * d->Q;
+    I2V_REQUIRE(M < (int64_t)0x7fffffff, "too many pixels for one launch");
+    CUtensorMap tmA, tmBhi, tmBlo;
+    if (int r = get_map_2d(&tmA, dy, (int)M, 64, TC_BM)) return r;
+    if (int r = get_map_2d(&tmBhi, wd_hi, 2 * SD_NH, 64, SD_NH)) return r;
+    if (int r = get_map_2d(&tmBlo, wd_lo, 2 * SD_NH, 64, SD_NH)) return r;
+    StemDirectArgs a{};
+    a.dx = dx; a.N = d->N; a.H = d->H; a.W = d->W; a.P = d->P; a.Q = d->Q;
+    a.strips_per_image = d->H >= 32 ? 2 : 1;
+    a.units = d->N * a.strips_per_image;
+    const size_t smem = 1024 + 8 * SD_B_TILE + (size_t)SD_STAGES * 2 * TC_A_BYTES + 2 * 4 * 11 * 6 * sizeof(float) + 256;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(stem_dgrad_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "i2v_conv_stem_dgrad_direct_f32 (shared memory)");
+        attr_done = true;
+    }
+    const int grid = a.units < sm_count() ? a.units : sm_count();
+    stem_dgrad_direct_kernel<<<grid, SD_THREADS, smem, as_stream(stream)>>>(tmA, tmBhi, tmBlo, a);
+    I2V_LAUNCH_CHECK("i2v_conv_stem_dgrad_direct_f32");
     return I2V_OK;
 }
 

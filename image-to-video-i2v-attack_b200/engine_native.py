@@ -74,6 +74,10 @@ class _Conv:
             nz = capi.stem_dgrad_tc_rows(cin * R * S)
             wz = torch.cat([self.w_stem, self.w_stem.new_zeros(nz - cin * R * S, cout)], 0).contiguous()
             self.tc_stem_dgrad = _split_tf32(wz)
+        # first-layer data gradient without the Z^T scratch (7x7 / s2 / p3 stems): [160, 64] taps in two halves
+        self.tc_stem_dgrad_direct = None
+        if x_nchw and cin == 3 and cout == 64 and R == 7 and self.stride == 2 and self.pad == 3:
+            self.tc_stem_dgrad_direct = _split_tf32(capi.stem_direct_dgrad_weights(self.w_stem))
         # EXPERIMENTAL direct first-layer forward ($I2V_STEM_DIRECT=1): [Cout, R*32] K-major, k = r*32 + s*4 + c
         self.tc_stem_direct = None
         if x_nchw and cin == 3 and cout == 64 and R == S and 5 <= S <= 8 and self.stride == 2:
@@ -309,6 +313,8 @@ class NativeEngine:
         self.use_bits = os.environ.get("I2V_NATIVE_BITS", "1") != "0"   # ReLU-backward masks as bits (TMA epilogue)
         self.use_stem_tc = os.environ.get("I2V_NATIVE_STEM_TC", "1") != "0"   # first-layer dgrad as tcgen05 GEMM + col2im
         self._zbuf = None
+        # first-layer data gradient without the Z^T scratch (i2v_conv_stem_dgrad_direct_f32); $I2V_STEM_DGRAD_DIRECT=0: GEMM + col2im
+        self.stem_dgrad_direct = os.environ.get("I2V_STEM_DGRAD_DIRECT", "1") != "0"
         # EXPERIMENTAL: first-layer forward without the im2col patch matrix (i2v_conv_stem_fwd_direct_f32)
         self.stem_direct = os.environ.get("I2V_STEM_DIRECT", "0") == "1"
         self._xpbuf = None
@@ -410,7 +416,12 @@ class NativeEngine:
             capi.conv_fwd_simt(d, x, op.b_fwd, op.bias, residual, y, relu=op.relu, x_nchw=op.x_nchw)
 
     def _conv_dgrad(self, op, d, dy, addend, mask_src, dx, mask_bits=None):
-        if (op.x_nchw and addend is None and mask_src is None and self.use_tc and self.use_stem_tc
+        if (op.x_nchw and addend is None and mask_src is None and self.use_tc and self.use_stem_tc and self.tf32x3
+                and getattr(op, "tc_stem_dgrad_direct", None) is not None and self.stem_dgrad_direct
+                and capi.conv_stem_dgrad_direct_supported(d)):
+            hi, lo, _ = op.tc_stem_dgrad_direct
+            capi.conv_stem_dgrad_direct(d, dy, hi, lo, dx)
+        elif (op.x_nchw and addend is None and mask_src is None and self.use_tc and self.use_stem_tc
                 and op.tc_stem_dgrad is not None and (d.N * d.P * d.Q) % 4 == 0):
             hi, lo, rna = op.tc_stem_dgrad
             nfl = capi.stem_dgrad_tc_scratch_floats(d)

@@ -543,6 +543,35 @@ def test_stem_dgrad_tc(H, W, k, s, p, n, x3):
     assert err <= ((2e-5 + Cout * 2.0 ** -24) if x3 else 4e-3), err
 
 
+@pytest.mark.parametrize("H,W,n", [(224, 224, 5), (64, 64, 3), (32, 32, 2), (16, 16, 3), (63, 61, 2), (224, 200, 1), (8, 8, 1)])
+def test_stem_dgrad_direct(H, W, n):
+    """First-layer data gradient without scratch (one dy row per tile, on-chip col2im in a register window, half-image
+    strips): against float64 autograd with the same error model as test_stem_dgrad_tc, on even / odd sizes, images too small
+    for two strips, widths where the last tile lanes are junk — and twice in a row (deterministic, NaN-prefilled output)."""
+    from i2v_b200.engine_native import _split_tf32
+    g = torch.Generator().manual_seed(3)
+    Cout, k, s, p = 64, 7, 2, 3
+    w = torch.randn(Cout, 3, k, k, generator=g) / (3 * k * k) ** 0.5
+    P, Q = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    dy = torch.randn(n, Cout, P, Q, generator=g)
+    d = capi.ConvDesc(n, H, W, 3, Cout, k, k, s, p, P, Q)
+    assert capi.conv_stem_dgrad_direct_supported(d)
+    w_stem = w.permute(1, 2, 3, 0).reshape(147, Cout).contiguous().to(DEV)
+    hi, lo, _ = _split_tf32(capi.stem_direct_dgrad_weights(w_stem))
+    dyd = dy.permute(0, 2, 3, 1).contiguous().to(DEV)
+    outs = []
+    for _ in range(2):
+        dx = torch.full((n, 3, H, W), float("nan"), device=DEV)
+        capi.conv_stem_dgrad_direct(d, dyd, hi, lo, dx)
+        outs.append(dx)
+    assert torch.equal(outs[0], outs[1])
+    ref64 = torch.nn.grad.conv2d_input((n, 3, H, W), w.double(), dy.double(), s, p)
+    got = outs[0].cpu().double()
+    assert torch.isfinite(got).all()
+    err = (got - ref64).abs().max() / ref64.abs().max()
+    assert err <= (2e-5 + Cout * 2.0 ** -24), err
+
+
 @pytest.mark.parametrize("H,W,k,s,p,n", [(224, 224, 7, 2, 3, 7), (64, 64, 7, 2, 3, 3), (64, 64, 11, 4, 2, 1), (32, 32, 3, 1, 1, 2),
                                          (63, 63, 3, 2, 0, 4)])
 @pytest.mark.parametrize("x3", [True, False])
