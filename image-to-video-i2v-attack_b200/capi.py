@@ -455,13 +455,9 @@ def conv_stem_dgrad_direct(desc, dy, wd_hi, wd_lo, dx):
 
 
 def stem_direct_dgrad_weights(w_stem):
-    """[(c,r,s) = 147, 64] -> [160, 64]: taps 0..76 | 3 zero rows | taps 77..146 | 10 zero rows (two N = 80 halves that end on
-    (c,r) group boundaries: 11 and 10 groups of 7 taps)."""
+    """[(c,r,s) = 147, 64] -> [160, 64]: the taps followed by 13 zero rows (UMMA N = 160)."""
     assert w_stem.shape == (147, 64)
-    out = w_stem.new_zeros(160, 64)
-    out[:77] = w_stem[:77]
-    out[80:150] = w_stem[77:]
-    return out.contiguous()
+    return torch.cat([w_stem, w_stem.new_zeros(13, 64)], 0).contiguous()
 
 
 def stem_dgrad_tc_rows(cols):

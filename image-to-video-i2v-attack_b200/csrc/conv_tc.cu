@@ -1460,16 +1460,18 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // is summed in a fixed order (dy rows ascending, taps s ascending): bit-reproducible, no atomics, no scratch.
 // HBM traffic = dy once + dx once.
 // ---------------------------------------------------------------------------------------------
-constexpr int SD_THREADS = 384;          // warp 0 producer, 1 MMA issuer, 2 TMEM allocator, 4-7 A split, 8-11 epilogue
+constexpr int SD_THREADS = 640;          // warp 0 producer, 1 MMA issuer, 2 TMEM allocator, 4-7 A split, 8-19 epilogue (3 channels x 4 lane quarters)
 constexpr int SD_STAGES = 3;             // A stages (one dy row each: two 16 KB k-blocks); the A_lo ring has 2 slots per stage
-constexpr int SD_NH = 80;                // taps per half (77 / 70 real ones): UMMA N
-constexpr uint32_t SD_B_TILE = SD_NH * TC_BK * 4;      // 10 KB: 80 taps x 32 channels
+constexpr int SD_NZ = 160;               // UMMA N: the 147 taps k = (c,r,s) + 13 zero rows; 2 accumulator stages x 160 + 6 x 32 ring columns = 512
+constexpr int SD_NC = 49;                // taps (columns) per channel: channel c at columns 49c .. 49c+48
+constexpr uint32_t SD_B_TILE = SD_NZ * TC_BK * 4;      // 20 KB: 160 taps x 32 channels
 
 struct StemDirectArgs {
     float* dx;
     int N, H, W, P, Q;
     int units;                           // strips: 2 per image (1 when the image is small)
     int strips_per_image;
+    int dbg;                             // timing experiments ($I2V_STEM_DBG; wrong results): 1 no MMA, 2 no col2im math, 4 no split, 8 no TMEM loads
 };
 
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
@@ -1491,16 +1493,33 @@ __device__ __forceinline__ void sd_strip(const StemDirectArgs& a, int u, int& im
     pb = (hb - 1 + 3) / 2; if (pb > a.P - 1) pb = a.P - 1;
 }
 
+// Measured history of this kernel (256 frames, against 1.11-1.27 ms for the GEMM + col2im pair it replaces):
+//   v1  one issuer, 48 N = 80 instructions per dy row, 4 epilogue warps, per-lane branches around every edge case  2.06 ms
+//   v2  three issuers                                                                                               2.17 ms
+//       (switching every MMA off saved 0.1 ms: never the problem; the epilogue math cost 1.28 ms — ~4000 instructions per row)
+//   v3  branch-free epilogue (broadcast edge loads + selects), two accumulators                                     0.93 ms
+//       (0.40 ms of it still the col2im math of 4 warps at ~0.5 IPC, 0.48 ms everything else)
+//   v4  TWELVE epilogue warps — three per lane quarter, one channel each — share the math; A_lo back in tensor memory       0.64 ms
+//       (math 0.07, TMEM loads 0.10, MMAs 0.08; 0.31 ms is the bare skeleton: with two stages a dy row's TMA round trip is
+//       exposed every other row, and an L2 prefetch six rows ahead changed nothing)
+//   v5  N = 160 (the channels' 49 taps back to back) frees tensor memory for a third A stage                               0.61 ms
+//       (0.42 ms skeleton: with main + cross accumulators of 160 columns each only ONE accumulator stage fits, so every dy
+//       row pays MMA -> commit -> epilogue load -> release -> next MMA in series)
+//   v6  this one: the two cross products accumulate into the SAME accumulator as the main product (K = 64: 24 truncating
+//       accumulations instead of 8, a bias of ~4e-6 relative instead of ~1.5e-6 — both far inside the 2e-5 the parity tests
+//       allow and the ~2e-6 of an FP32 FMA chain), which makes room for TWO accumulator stages: MMAs of row t+1 overlap the
+//       epilogue of row t.  One issuer, fixed order (bit-reproducible).
 __global__ void __launch_bounds__(SD_THREADS, 1)
 stem_dgrad_direct_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                          const __grid_constant__ CUtensorMap tmBlo, const StemDirectArgs args) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* bhi = smem;                                       // [half][kb] tiles of 10 KB
-    uint8_t* blo = smem + 4 * SD_B_TILE;
-    uint8_t* atiles = smem + 8 * SD_B_TILE;                    // 80 KB = 1024-aligned
-    float* edge = reinterpret_cast<float*>(atiles + (size_t)SD_STAGES * 2 * TC_A_BYTES);   // [2 buffers][4 warps][11 groups][6]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(edge + 2 * 4 * 11 * 6);
+    uint8_t* bhi = smem;                                       // [kb] tiles of 20 KB (160 taps x 32 channels)
+    uint8_t* blo = smem + 2 * SD_B_TILE;
+    uint8_t* atiles = smem + 4 * SD_B_TILE;                    // 80 KB = 1024-aligned; per stage: kb0, kb1
+    float* edge = reinterpret_cast<float*>(atiles + (size_t)SD_STAGES * 2 * TC_A_BYTES);   // [3 channels][2 buffers][6 slots][7 groups][6]
+    constexpr int kEdgeSlot = 7 * 6, kEdgeBuf = 6 * kEdgeSlot;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(edge + 3 * 2 * kEdgeBuf);
     uint64_t* bfull = bars;
     uint64_t* afull = bfull + 1;
     uint64_t* aempty = afull + SD_STAGES;
@@ -1512,11 +1531,12 @@ stem_dgrad_direct_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto a_tile = [&](int st, int kb) { return atiles + ((size_t)st * 2 + kb) * TC_A_BYTES; };
 
+    for (int i = threadIdx.x; i < 3 * 2 * kEdgeBuf; i += SD_THREADS) edge[i] = 0.f;     // slots 0 and 5 are never written again
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA); prefetch_tmap(&tmBhi); prefetch_tmap(&tmBlo);
         mbar_init(bfull, 1);
-        for (int s = 0; s < SD_STAGES; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); mbar_init(&splitb[s], 128); }
-        for (int h = 0; h < 2; ++h) { mbar_init(&tfull[h], 1); mbar_init(&tempty[h], 128); }
+        for (int s = 0; s < SD_STAGES; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); mbar_init(&splitb[s], 4); }       // one arrival per warp
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 12); }
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -1526,26 +1546,34 @@ stem_dgrad_direct_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    // tensor memory: half h: main at 160h, cross at 160h + 80; A_lo ring slot (stage, kb) at 320 + 32 (2 stage + kb)
+    const uint32_t tmem_base = *tmem_slot;       // columns: accumulator stage a at 160 a, A_lo ring 320 + 32 (2 stage + kb)
     constexpr uint32_t kRing = 320;
 
     if (warp == 0) {
         if (lane == 0) {
-            // the weights stay resident: [half][kb] x (hi, lo)
-            mbar_arrive_expect_tx(bfull, 8 * SD_B_TILE);
-            for (int h = 0; h < 2; ++h)
-                for (int kb = 0; kb < 2; ++kb) {
-                    tma_load_2d(&tmBhi, bfull, bhi + (size_t)(h * 2 + kb) * SD_B_TILE, kb * TC_BK, h * SD_NH);
-                    tma_load_2d(&tmBlo, bfull, blo + (size_t)(h * 2 + kb) * SD_B_TILE, kb * TC_BK, h * SD_NH);
-                }
+            mbar_arrive_expect_tx(bfull, 4 * SD_B_TILE);          // the weights stay resident
+            for (int kb = 0; kb < 2; ++kb) {
+                tma_load_2d(&tmBhi, bfull, bhi + (size_t)kb * SD_B_TILE, kb * TC_BK, 0);
+                tma_load_2d(&tmBlo, bfull, blo + (size_t)kb * SD_B_TILE, kb * TC_BK, 0);
+            }
             int t = 0;
             for (int u = blockIdx.x; u < args.units; u += gridDim.x) {
                 int img, pa, pb, ha, hb;
                 sd_strip(args, u, img, pa, pb, ha, hb);
+                // Two shared-memory stages cannot hide an HBM round trip per dy row (the A_lo ring in tensor memory caps the
+                // stages at two), so the rows are pulled into L2 a few tiles ahead: the TMA loads below then hit L2.
+                constexpr int kAhead = 6;
+                for (int d = 0; d < kAhead && pa + d <= pb; ++d) {
+                    const int mf = (img * args.P + pa + d) * args.Q;
+                    tma_prefetch_l2_2d(&tmA, 0, mf); tma_prefetch_l2_2d(&tmA, TC_BK, mf);
+                }
                 for (int p = pa; p <= pb; ++p, ++t) {
                     const int st = t % SD_STAGES;
                     const uint32_t ph = (uint32_t)(t / SD_STAGES) & 1;
+                    if (p + kAhead <= pb) {
+                        const int mf = (img * args.P + p + kAhead) * args.Q;
+                        tma_prefetch_l2_2d(&tmA, 0, mf); tma_prefetch_l2_2d(&tmA, TC_BK, mf);
+                    }
                     mbar_wait(&aempty[st], ph ^ 1);
                     mbar_arrive_expect_tx(&afull[st], 2 * TC_A_BYTES);
                     const int m0 = (img * args.P + p) * args.Q;
@@ -1555,8 +1583,9 @@ stem_dgrad_direct_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
         }
     } else if (warp == 1) {
+        // the MMA issuer: acc (+)= a_hi b_hi + a_hi b_lo + a_lo (tensor memory) b_hi, 24 instructions of N = 160 per dy row
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32(SD_NH);
+            constexpr uint32_t idesc = umma_idesc_tf32(SD_NZ);
             mbar_wait(bfull, 0);
             int t = 0;
             for (int u = blockIdx.x; u < args.units; u += gridDim.x) {
@@ -1565,27 +1594,27 @@ stem_dgrad_direct_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 for (int p = pa; p <= pb; ++p, ++t) {
                     const int st = t % SD_STAGES;
                     const uint32_t ph = (uint32_t)(t / SD_STAGES) & 1;
+                    const int acc = t & 1;
                     mbar_wait(&afull[st], ph);
                     mbar_wait(&splitb[st], ph);
+                    mbar_wait(&tempty[acc], ((uint32_t)(t >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    for (int h = 0; h < 2; ++h) {
-                        mbar_wait(&tempty[h], ((uint32_t)t & 1) ^ 1);
-                        tc_fence_after();
-                        const uint32_t dmain = tmem_base + (uint32_t)h * 160u, dcross = dmain + SD_NH;
-                        for (int kb = 0; kb < 2; ++kb) {
-                            const uint64_t da = umma_desc_sw128(smem_u32(a_tile(st, kb)));
-                            const uint64_t dbh = umma_desc_sw128(smem_u32(bhi + (size_t)(h * 2 + kb) * SD_B_TILE));
-                            const uint64_t dbl = umma_desc_sw128(smem_u32(blo + (size_t)(h * 2 + kb) * SD_B_TILE));
-                            const uint32_t talo = tmem_base + kRing + 32u * (uint32_t)(2 * st + kb);
+                    const uint32_t dacc = tmem_base + (uint32_t)acc * SD_NZ;
 #pragma unroll
-                            for (int kk = 0; kk < TC_BK / 8; ++kk) {
-                                umma_tf32(dmain, da + 2 * kk, dbh + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
-                                umma_tf32(dcross, da + 2 * kk, dbl + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
-                                umma_tf32_ts(dcross, talo + 8u * kk, dbh + 2 * kk, idesc, 1u);
-                            }
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const uint64_t da = umma_desc_sw128(smem_u32(a_tile(st, kb)));
+                        const uint64_t dbh = umma_desc_sw128(smem_u32(bhi + (size_t)kb * SD_B_TILE));
+                        const uint64_t dbl = umma_desc_sw128(smem_u32(blo + (size_t)kb * SD_B_TILE));
+                        const uint32_t talo = tmem_base + kRing + 32u * (uint32_t)(2 * st + kb);
+#pragma unroll
+                        for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                            if (args.dbg & 1) continue;
+                            umma_tf32(dacc, da + 2 * kk, dbh + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
+                            umma_tf32(dacc, da + 2 * kk, dbl + 2 * kk, idesc, 1u);
+                            umma_tf32_ts(dacc, talo + 8u * kk, dbh + 2 * kk, idesc, 1u);
                         }
-                        umma_commit(&tfull[h]);
                     }
+                    umma_commit(&tfull[acc]);
                     umma_commit(&aempty[st]);
                 }
             }
@@ -1603,6 +1632,7 @@ stem_dgrad_direct_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 const int st = t % SD_STAGES;
                 const uint32_t ph = (uint32_t)(t / SD_STAGES) & 1;
                 mbar_wait(&afull[st], ph);
+                if (args.dbg & 4) { __syncwarp(); if (lane == 0) mbar_arrive(&splitb[st]); continue; }
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb) {
                     const uint8_t* arow = a_tile(st, kb) + (size_t)row * 128;
@@ -1619,121 +1649,101 @@ stem_dgrad_direct_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 }
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 tc_fence_before();
-                mbar_arrive(&splitb[st]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&splitb[st]);           // one arrival per warp: 128 arrivals per row serialise on the barrier word
             }
         }
     } else if (warp >= 8) {
-        // ===== epilogue: on-chip col2im into a register window, one thread per dy pixel q = two image columns ==============
-        const int ew = warp - 8;                                  // TMEM lane quarter (warps 8..11 -> warp % 4 = 0..3)
+        // ===== epilogue: on-chip col2im; warp = (channel c, lane quarter); thread = dy pixel q = image columns 2q, 2q+1 =====
+        const int c = (warp - 8) >> 2;
+        const int ew = warp & 3;                                  // TMEM lane quarter of this warp
         const int q = ew * 32 + lane;
-        const bool qvalid = q < args.Q;
-        const uint32_t tlane = tmem_base + ((uint32_t)(ew * 32) << 16);
-        float win[3][7][2];                                       // [channel][image row 2p-3+i][column 2q+e]
-        int t = 0, hbuf = 0;
+        const bool v1ok = q + 1 < args.Q, v0ok = q + 2 < args.Q;
+        const bool l31 = lane == 31, l30 = lane == 30, l0 = lane == 0;
+        const uint32_t tlane = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(c * SD_NC);
+        float* ebase = edge + (size_t)c * 2 * kEdgeBuf;
+        float win[7][2];                                          // [image row 2p-3+i][column 2q+e] of channel c
+        int t = 0;
         for (int u = blockIdx.x; u < args.units; u += gridDim.x) {
             int img, pa, pb, ha, hb;
             sd_strip(args, u, img, pa, pb, ha, hb);
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
-#pragma unroll
-                for (int i = 0; i < 7; ++i) { win[c][i][0] = 0.f; win[c][i][1] = 0.f; }
-            float* dximg = args.dx + (int64_t)img * 3 * args.H * args.W;
-            auto emit = [&](int slot_row_h, const float (&w0)[2], int c) {      // one (channel, image row) pair of this thread
-                if (slot_row_h < ha || slot_row_h >= hb) return;
-                float* o = dximg + ((int64_t)c * args.H + slot_row_h) * args.W + 2 * q;
+            for (int i = 0; i < 7; ++i) { win[i][0] = 0.f; win[i][1] = 0.f; }
+            float* dxc = args.dx + ((int64_t)img * 3 + c) * args.H * args.W + 2 * q;
+            auto emit = [&](int h, const float (&w0)[2]) {
+                if (h < ha || h >= hb) return;
+                float* o = dxc + (int64_t)h * args.W;
                 if (2 * q + 1 < args.W) {
                     if ((args.W & 1) == 0) *reinterpret_cast<float2*>(o) = make_float2(w0[0], w0[1]);
                     else { o[0] = w0[0]; o[1] = w0[1]; }
                 } else if (2 * q < args.W) o[0] = w0[0];
             };
             for (int p = pa; p <= pb; ++p, ++t) {
+                const int acc = t & 1;
+                mbar_wait(&tfull[acc], (uint32_t)(t >> 1) & 1);
+                tc_fence_after();
+                const uint32_t tacc = tlane + (uint32_t)acc * SD_NZ;
+                float z[SD_NC];
+                if (args.dbg & 8) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h, hbuf ^= 1) {
-                    constexpr int G0 = 11;                         // half 0: groups (c,r) 0..10 (77 taps), half 1: 11..20 (70 taps)
-                    mbar_wait(&tfull[h], (uint32_t)t & 1);
-                    tc_fence_after();
-                    float z[SD_NH];
-                    {
-                        uint32_t m0[32], c0[32];
-                        tmem_ld32_nowait(tlane + (uint32_t)h * 160u, m0);
-                        tmem_ld32_nowait(tlane + (uint32_t)h * 160u + SD_NH, c0);
-                        tmem_ld_wait();
+                    for (int i = 0; i < SD_NC; ++i) z[i] = 1.f;
+                } else {
+                    uint32_t m0[16], m1[16], m2[16], m3[16];       // taps 0..47 and (last column of a load starting at 33) tap 48
+                    tmem_ld16_nowait(tacc, m0);
+                    tmem_ld16_nowait(tacc + 16u, m1);
+                    tmem_ld16_nowait(tacc + 32u, m2);
+                    tmem_ld16_nowait(tacc + 33u, m3);
+                    tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) z[i] = __fadd_rn(__uint_as_float(m0[i]), __uint_as_float(c0[i]));
-                        tmem_ld32_nowait(tlane + (uint32_t)h * 160u + 32u, m0);
-                        tmem_ld32_nowait(tlane + (uint32_t)h * 160u + SD_NH + 32u, c0);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) z[32 + i] = __fadd_rn(__uint_as_float(m0[i]), __uint_as_float(c0[i]));
-                        uint32_t m1[16], c1[16];
-                        tmem_ld16_nowait(tlane + (uint32_t)h * 160u + 64u, m1);
-                        tmem_ld16_nowait(tlane + (uint32_t)h * 160u + SD_NH + 64u, c1);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) z[64 + i] = __fadd_rn(__uint_as_float(m1[i]), __uint_as_float(c1[i]));
+                    for (int i = 0; i < 16; ++i) {
+                        z[i] = __uint_as_float(m0[i]); z[16 + i] = __uint_as_float(m1[i]); z[32 + i] = __uint_as_float(m2[i]);
                     }
-                    tc_fence_before();
-                    mbar_arrive(&tempty[h]);                       // the accumulator half is in registers: the MMA warp may reuse it
-                    if (!qvalid) {
+                    z[48] = __uint_as_float(m3[15]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);          // this warp's share of the accumulator stage is in registers
+                if (!(args.dbg & 2)) {
+                    float* eb = ebase + (size_t)(t & 1) * kEdgeBuf;
+                    float* mine = eb + (size_t)(ew + 1) * kEdgeSlot;
 #pragma unroll
-                        for (int i = 0; i < SD_NH; ++i) z[i] = 0.f;    // lanes beyond the row belong to the next dy row
+                    for (int r = 0; r < 7; ++r) {                  // publish: lane 0 -> s = 0,1,2; lane 1 -> s = 0; lane 31 -> s = 5,6
+                        if (l0) { mine[r * 6 + 0] = z[r * 7 + 0]; mine[r * 6 + 1] = z[r * 7 + 1]; mine[r * 6 + 2] = z[r * 7 + 2]; }
+                        if (lane == 1) mine[r * 6 + 3] = z[r * 7 + 0];
+                        if (l31) { mine[r * 6 + 4] = z[r * 7 + 5]; mine[r * 6 + 5] = z[r * 7 + 6]; }
                     }
-                    const int ng = h == 0 ? G0 : 21 - G0;
-                    float* eb = edge + (size_t)hbuf * (4 * 11 * 6);
-                    // publish what the neighbouring warps need: lane 0 -> s = 0,1,2; lane 1 -> s = 0; lane 31 -> s = 5,6
+                    asm volatile("bar.sync %0, 128;" :: "r"(1 + c) : "memory");
+                    const float* en = eb + (size_t)(ew + 2) * kEdgeSlot;     // next warp (slot 5 = zeros for the last one)
+                    const float* ep = eb + (size_t)ew * kEdgeSlot;           // previous warp (slot 0 = zeros for the first one)
 #pragma unroll
-                    for (int g = 0; g < 11; ++g) {
-                        if (g >= ng) break;
-                        float* e = eb + ((size_t)ew * 11 + g) * 6;
-                        if (lane == 0) { e[0] = z[g * 7 + 0]; e[1] = z[g * 7 + 1]; e[2] = z[g * 7 + 2]; }
-                        if (lane == 1) e[3] = z[g * 7 + 0];
-                        if (lane == 31) { e[4] = z[g * 7 + 5]; e[5] = z[g * 7 + 6]; }
-                    }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-#pragma unroll
-                    for (int g = 0; g < 11; ++g) {
-                        if (g >= ng) break;
-                        const int gg = h == 0 ? g : g + G0;        // global group = c * 7 + r
-                        const int c = gg / 7, r = gg - c * 7;
-                        const float* zz = z + g * 7;
-                        float v1 = __shfl_down_sync(0xffffffffu, zz[1], 1);
-                        float v2 = __shfl_down_sync(0xffffffffu, zz[2], 1);
-                        float v0 = __shfl_down_sync(0xffffffffu, zz[0], 2);
-                        float v5 = __shfl_up_sync(0xffffffffu, zz[5], 1);
-                        float v6 = __shfl_up_sync(0xffffffffu, zz[6], 1);
-                        const float* en = eb + ((size_t)(ew + 1) * 11 + g) * 6;    // next warp's edge values (ew < 3)
-                        const float* ep = eb + ((size_t)(ew - 1) * 11 + g) * 6;    // previous warp's (ew > 0)
-                        if (lane == 31) { v1 = ew < 3 ? en[1] : 0.f; v2 = ew < 3 ? en[2] : 0.f; v0 = ew < 3 ? en[3] : 0.f; }
-                        if (lane == 30) v0 = ew < 3 ? en[0] : 0.f;
-                        if (lane == 0) { v5 = ew > 0 ? ep[4] : 0.f; v6 = ew > 0 ? ep[5] : 0.f; }
+                    for (int r = 0; r < 7; ++r) {
+                        float v1 = __shfl_down_sync(0xffffffffu, z[r * 7 + 1], 1);
+                        float v2 = __shfl_down_sync(0xffffffffu, z[r * 7 + 2], 1);
+                        float v0 = __shfl_down_sync(0xffffffffu, z[r * 7 + 0], 2);
+                        float v5 = __shfl_up_sync(0xffffffffu, z[r * 7 + 5], 1);
+                        float v6 = __shfl_up_sync(0xffffffffu, z[r * 7 + 6], 1);
+                        const float n0 = en[r * 6 + 0], n1 = en[r * 6 + 1], n2 = en[r * 6 + 2], n3 = en[r * 6 + 3];   // broadcast loads
+                        const float p5 = ep[r * 6 + 4], p6 = ep[r * 6 + 5];
+                        v1 = l31 ? n1 : v1; v2 = l31 ? n2 : v2;
+                        v0 = l31 ? n3 : (l30 ? n0 : v0);
+                        v5 = l0 ? p5 : v5; v6 = l0 ? p6 : v6;
+                        v1 = v1ok ? v1 : 0.f; v2 = v1ok ? v2 : 0.f; v0 = v0ok ? v0 : 0.f;       // q+1 / q+2 beyond the dy row
                         // column 2q: s = 1 (q+1), 3 (q), 5 (q-1); column 2q+1: s = 0 (q+2), 2 (q+1), 4 (q), 6 (q-1)
-                        const float e0 = __fadd_rn(__fadd_rn(v1, zz[3]), v5);
-                        const float e1 = __fadd_rn(__fadd_rn(__fadd_rn(v0, v2), zz[4]), v6);
-#pragma unroll
-                        for (int cc = 0; cc < 3; ++cc)
-#pragma unroll
-                            for (int rr = 0; rr < 7; ++rr)
-                                if (cc == c && rr == r) {
-                                    win[cc][rr][0] = __fadd_rn(win[cc][rr][0], e0);
-                                    win[cc][rr][1] = __fadd_rn(win[cc][rr][1], e1);
-                                }
+                        win[r][0] = __fadd_rn(win[r][0], __fadd_rn(__fadd_rn(v1, z[r * 7 + 3]), v5));
+                        win[r][1] = __fadd_rn(win[r][1], __fadd_rn(__fadd_rn(__fadd_rn(v0, v2), z[r * 7 + 4]), v6));
                     }
+                } else {
+                    win[0][0] += z[0] + z[48];
                 }
-                // image rows 2p-3 and 2p-2 are complete
+                emit(2 * p - 3, win[0]);                           // image rows 2p-3 and 2p-2 are complete
+                emit(2 * p - 2, win[1]);
 #pragma unroll
-                for (int c = 0; c < 3; ++c) { emit(2 * p - 3, win[c][0], c); emit(2 * p - 2, win[c][1], c); }
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-#pragma unroll
-                    for (int i = 0; i < 5; ++i) { win[c][i][0] = win[c][i + 2][0]; win[c][i][1] = win[c][i + 2][1]; }
-                    win[c][5][0] = win[c][5][1] = win[c][6][0] = win[c][6][1] = 0.f;
-                }
+                for (int i = 0; i < 5; ++i) { win[i][0] = win[i + 2][0]; win[i][1] = win[i + 2][1]; }
+                win[5][0] = win[5][1] = win[6][0] = win[6][1] = 0.f;
             }
             // strip done: the window holds image rows 2 pb - 1 .. 2 pb + 3
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
-#pragma unroll
-                for (int i = 0; i < 5; ++i) emit(2 * pb - 1 + i, win[c][i], c);
+            for (int i = 0; i < 5; ++i) emit(2 * pb - 1 + i, win[i]);
         }
     }
 
@@ -2264,9 +2274,8 @@ extern "C" int i2v_conv_stem_dgrad_tc_f32(const i2v_conv_desc* d, const float* d
     return I2V_OK;
 }
 
-// First-layer data gradient without scratch (stem_dgrad_direct_kernel).  wd_hi / wd_lo = [160, 64] K-major: the taps
-// k = (c, r, s) of w_stem in two halves — rows 0..76 = taps 0..76 (groups (c,r) 0..10), 77..79 zero, rows 80..149 = taps
-// 77..146, 150..159 zero — split into hi = w (the tensor core truncates) and lo = w - trunc_tf32(w).
+// First-layer data gradient without scratch (stem_dgrad_direct_kernel).  wd_hi / wd_lo = [160, 64] K-major: the 147 taps
+// k = (c, r, s) of w_stem followed by 13 zero rows — split into hi = w (the tensor core truncates) and lo = w - trunc_tf32(w).
 extern "C" int i2v_conv_stem_dgrad_direct_supported(const i2v_conv_desc* d) {
     return d && d->Cin == 3 && d->Cout == 64 && d->R == 7 && d->S == 7 && d->stride == 2 && d->pad == 3 && d->Q >= 1 &&
            d->Q <= TC_BM && d->P >= 1 && d->W <= 2 * d->Q && d->H <= 2 * d->P;
@@ -2284,13 +2293,15 @@ extern "C" int i2v_conv_stem_dgrad_direct_f32(const i2v_conv_desc* d, const floa
     I2V_REQUIRE(M < (int64_t)0x7fffffff, "too many pixels for one launch");
     CUtensorMap tmA, tmBhi, tmBlo;
     if (int r = get_map_2d(&tmA, dy, (int)M, 64, TC_BM)) return r;
-    if (int r = get_map_2d(&tmBhi, wd_hi, 2 * SD_NH, 64, SD_NH)) return r;
-    if (int r = get_map_2d(&tmBlo, wd_lo, 2 * SD_NH, 64, SD_NH)) return r;
+    if (int r = get_map_2d(&tmBhi, wd_hi, SD_NZ, 64, SD_NZ)) return r;
+    if (int r = get_map_2d(&tmBlo, wd_lo, SD_NZ, 64, SD_NZ)) return r;
     StemDirectArgs a{};
     a.dx = dx; a.N = d->N; a.H = d->H; a.W = d->W; a.P = d->P; a.Q = d->Q;
+    static const int sd_dbg = getenv("I2V_STEM_DBG") ? atoi(getenv("I2V_STEM_DBG")) : 0;
+    a.dbg = sd_dbg;
     a.strips_per_image = d->H >= 32 ? 2 : 1;
     a.units = d->N * a.strips_per_image;
-    const size_t smem = 1024 + 8 * SD_B_TILE + (size_t)SD_STAGES * 2 * TC_A_BYTES + 2 * 4 * 11 * 6 * sizeof(float) + 256;
+    const size_t smem = 1024 + 4 * SD_B_TILE + (size_t)SD_STAGES * 2 * TC_A_BYTES + 3 * 2 * 6 * 42 * sizeof(float) + 256;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(stem_dgrad_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -302,8 +302,8 @@ int     i2v_conv_stem_fwd_direct_f32(const i2v_conv_desc* d, const float* x, con
 /* First-layer data gradient WITHOUT scratch (7x7 / stride 2 / pad 3, Cout = 64, Q <= 128 — ResNet's and DenseNet's stem;
  * image_attacks.py:352 for that layer): one dy row per tile, contraction over the output channels on the tensor cores, the
  * col2im on chip (warp shuffles + a register window of the 7 image rows a dy row touches), dcost/dimage [N,3,H,W] written
- * once.  wd_hi / wd_lo = [160, 64] K-major, taps k = (c,r,s): rows 0..76 = taps 0..76, 77..79 zero, rows 80..149 = taps
- * 77..146, 150..159 zero (hi = w, lo = w - trunc_tf32(w)).                                                       */
+ * once.  wd_hi / wd_lo = [160, 64] K-major: the 147 taps k = (c,r,s) followed by 13 zero rows (hi = w, lo = w -
+ * trunc_tf32(w)).                                                                                                 */
 int i2v_conv_stem_dgrad_direct_supported(const i2v_conv_desc* d);
 int i2v_conv_stem_dgrad_direct_f32(const i2v_conv_desc* d, const float* dy, const float* wd_hi, const float* wd_lo, float* dx,
                                    i2v_stream_t stream);
