@@ -64,6 +64,8 @@ SIGNATURES = {
     "i2v_conv_stem_fwd_direct_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_stem_dgrad_direct_supported": ([_c_p], _c_int),
     "i2v_conv_stem_dgrad_direct_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p], _c_int),
+    "i2v_conv_stem_fwd_rows_supported": ([_c_p], _c_int),
+    "i2v_conv_stem_fwd_rows_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_stem_fwd_tc_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_tc_supported": ([_c_p, _c_int], _c_int),
     "i2v_conv_tc_set_trace": ([_c_p, _c_int], _c_int),
@@ -120,7 +122,7 @@ def load():
 # tensors read + written once, 2 x MACs of the convolution).
 LAUNCHES = {}
 PROFILE_EVENTS = None
-_NO_KERNEL = ("i2v_set_adam_arithmetic", "i2v_conv_stem_dgrad_direct_supported", "i2v_conv_tc_set_pair_minkit", "i2v_conv_stem_fwd_direct_supported", "i2v_conv_stem_fwd_direct_scratch_floats", "i2v_conv_stem_dgrad_tc_rows", "i2v_device_check", "i2v_std_workspace_doubles", "i2v_ila_workspace_doubles", "i2v_adam_step_table", "i2v_conv_tc_supported", "i2v_conv_stem_supported",
+_NO_KERNEL = ("i2v_set_adam_arithmetic", "i2v_conv_stem_fwd_rows_supported", "i2v_conv_stem_dgrad_direct_supported", "i2v_conv_tc_set_pair_minkit", "i2v_conv_stem_fwd_direct_supported", "i2v_conv_stem_fwd_direct_scratch_floats", "i2v_conv_stem_dgrad_tc_rows", "i2v_device_check", "i2v_std_workspace_doubles", "i2v_ila_workspace_doubles", "i2v_adam_step_table", "i2v_conv_tc_supported", "i2v_conv_stem_supported",
               "i2v_conv_tc_set_trace")
 
 
@@ -477,6 +479,18 @@ def conv_stem_fwd_tc(desc, x, wk_hi, wk_lo, bias, col_scratch, y, relu=False):
         _check(load().i2v_conv_stem_fwd_tc_f32(ctypes.addressof(desc), _dev(x), _dev(wk_hi), _dev(wk_lo), _dev(bias),
                                                _dev(col_scratch), _dev(y), EPI_RELU if relu else 0, _stream()),
                "i2v_conv_stem_fwd_tc_f32")
+
+
+def conv_stem_fwd_rows_supported(desc):
+    return bool(load().i2v_conv_stem_fwd_rows_supported(ctypes.addressof(desc)))
+
+
+def conv_stem_fwd_rows(desc, x, wk_hi, wk_lo, bias, y, relu=False):
+    """First-layer forward without the patch matrix: one output row per tile (see include/i2v_b200.h)."""
+    nb, fl = _conv_cost(desc)
+    with _Timed("i2v_conv_stem_fwd_f32", nb, fl):
+        _check(load().i2v_conv_stem_fwd_rows_f32(ctypes.addressof(desc), _dev(x), _dev(wk_hi), _dev(wk_lo), _dev(bias), _dev(y),
+                                                 EPI_RELU if relu else 0, _stream()), "i2v_conv_stem_fwd_rows_f32")
 
 
 def conv_stem_fwd_direct_supported(desc):

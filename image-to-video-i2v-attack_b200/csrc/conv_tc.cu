@@ -1756,6 +1756,228 @@ stem_dgrad_direct_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 }
 
 // ---------------------------------------------------------------------------------------------
+// First-layer FORWARD without the patch matrix (i2v_conv_stem_fwd_rows_f32; 7x7 / stride 2 / pad 3, 64 output channels,
+// Q <= 128, W % 4 == 0).  The im2col + GEMM pair writes a 2 GB patch matrix and reads it back (1.1 ms per 256 frames for
+// 0.98 GB of tensors).  Here a tile is ONE output row (n, p): TMA stages the 7 input rows x 3 channels it needs (zero filled
+// beyond the image: coordinates start at -3), four "assemble" warps (thread = output pixel q) build the 128 x 160 patch tile
+// in shared memory k-block by k-block — A_hi in the swizzled layout the tensor core reads, A_lo into a tensor-memory ring —
+// and the weights [64, 160] (hi | lo) stay resident.  K = 147 taps (c,r,s) + 13 zeros = 5 k-blocks.  [main | cross] +=
+// a_hi [b_hi | b_lo] (N = 128) and cross += a_lo b_hi (N = 64) from one issuer; two accumulator stages; bias + ReLU in the
+// epilogue, output through two swizzled staging slots and TMA stores whose box is exactly the Q rows of the tile.
+// HBM traffic = the image once + the output once.
+// ---------------------------------------------------------------------------------------------
+constexpr int SF_THREADS = 384;          // warp 0 producer, 1 MMA issuer, 2 TMEM allocator, 4-7 assemble, 8-11 epilogue
+constexpr int SF_KB = 5;                 // k-blocks of 32 taps
+constexpr int SF_ASLOTS = 4;             // ring of 16 KB A k-block slots (and of 32-column A_lo slots in tensor memory)
+constexpr int SF_ISTAGES = 2;            // staged input rows
+constexpr uint32_t SF_B_KB = 2 * 64 * TC_BK * 4;      // 16 KB per k-block: [64 x b_hi | 64 x b_lo]
+
+struct StemFwdArgs {
+    const float* bias;
+    int N, H, W, P, Q, relu;
+    int pitch;                           // staged row pitch in floats = TMA box width (>= W + 7: columns -4 .. W+2, multiple of 4)
+    int cstride;                         // floats between the staged channels (7 * pitch rounded up to 128 bytes: TMA destination alignment)
+    int tiles;                           // N * P
+};
+
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+__global__ void __launch_bounds__(SF_THREADS, 1)
+stem_fwd_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBhi,
+                     const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmOut, const StemFwdArgs args) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* bt = smem;                                         // [kb]: b_hi rows then b_lo rows, 16 KB each
+    uint8_t* aslots = smem + SF_KB * SF_B_KB;                   // 80 KB in: 1024-aligned
+    uint8_t* staging = aslots + (size_t)SF_ASLOTS * TC_A_BYTES; // two 16 KB output slots (32 channels each)
+    const uint32_t in_bytes = (uint32_t)(3 * 7 * args.pitch * 4);
+    const uint32_t in_stride = (uint32_t)(3 * args.cstride * 4);
+    float* inrows = reinterpret_cast<float*>(staging + 2 * EPI_SLOT_BYTES);   // [stage][c][r][pitch]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(inrows) + (size_t)SF_ISTAGES * in_stride);
+    uint64_t* bfull = bars;
+    uint64_t* ifull = bfull + 1;             // input rows landed
+    uint64_t* iempty = ifull + SF_ISTAGES;   // the 4 assemble warps are done with them
+    uint64_t* afull = iempty + SF_ISTAGES;   // A k-block assembled (4 warps)
+    uint64_t* aempty = afull + SF_ASLOTS;    // ... consumed by the MMAs
+    uint64_t* tfull = aempty + SF_ASLOTS;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmX); prefetch_tmap(&tmBhi); prefetch_tmap(&tmBlo); prefetch_tmap(&tmOut);
+        mbar_init(bfull, 1);
+        for (int s = 0; s < SF_ISTAGES; ++s) { mbar_init(&ifull[s], 1); mbar_init(&iempty[s], 4); }
+        for (int s = 0; s < SF_ASLOTS; ++s) { mbar_init(&afull[s], 4); mbar_init(&aempty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;   // accumulator stage a: [main 64 | cross 64] at 128 a; A_lo ring at 256 + 32 slot
+    constexpr uint32_t kRing = 256;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bfull, SF_KB * SF_B_KB);
+            for (int kb = 0; kb < SF_KB; ++kb) {
+                tma_load_2d(&tmBhi, bfull, bt + (size_t)kb * SF_B_KB, kb * TC_BK, 0);
+                tma_load_2d(&tmBlo, bfull, bt + (size_t)kb * SF_B_KB + 64 * TC_BK * 4, kb * TC_BK, 0);
+            }
+            int t = 0;
+            for (int tile = blockIdx.x; tile < args.tiles; tile += gridDim.x, ++t) {
+                const int n = tile / args.P, p = tile - n * args.P;
+                const int st = t % SF_ISTAGES;
+                const uint32_t ph = (uint32_t)(t / SF_ISTAGES) & 1;
+                mbar_wait(&iempty[st], ph ^ 1);
+                mbar_arrive_expect_tx(&ifull[st], in_bytes);
+                uint8_t* dst = reinterpret_cast<uint8_t*>(inrows) + (size_t)st * in_stride;
+                for (int c = 0; c < 3; ++c)
+                    // the innermost start coordinate must be 16-byte aligned (-3 floats is an illegal instruction, measured):
+                    // the box starts at column -4, so image column w sits at staged column w + 4
+                    tma_load_3d(&tmX, &ifull[st], dst + (size_t)c * args.cstride * 4, -4, 2 * p - 3, n * 3 + c);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(64), idesc2 = umma_idesc_tf32(128);
+            mbar_wait(bfull, 0);
+            int t = 0, it = 0;
+            for (int tile = blockIdx.x; tile < args.tiles; tile += gridDim.x, ++t) {
+                const int acc = t & 1;
+                mbar_wait(&tempty[acc], ((uint32_t)(t >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + (uint32_t)acc * 128u;
+                for (int kb = 0; kb < SF_KB; ++kb, ++it) {
+                    const int sl = it % SF_ASLOTS;
+                    const uint32_t ph = (uint32_t)(it / SF_ASLOTS) & 1;
+                    mbar_wait(&afull[sl], ph);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_sw128(smem_u32(aslots + (size_t)sl * TC_A_BYTES));
+                    const uint64_t db = umma_desc_sw128(smem_u32(bt + (size_t)kb * SF_B_KB));
+                    const uint32_t talo = tmem_base + kRing + 32u * (uint32_t)sl;
+#pragma unroll
+                    for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                        umma_tf32(d0, da + 2 * kk, db + 2 * kk, idesc2, (kb | kk) ? 1u : 0u);          // [main | cross] += a_hi [b_hi | b_lo]
+                        umma_tf32_ts(d0 + 64u, talo + 8u * kk, db + 2 * kk, idesc, 1u);               // cross += a_lo b_hi
+                    }
+                    umma_commit(&aempty[sl]);
+                }
+                umma_commit(&tfull[acc]);
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===== assemble: thread = output pixel q; patch value k = (c,r,s) is staged[c][r][2q + s] ===========================
+        const int row = threadIdx.x - 128;
+        const int qq = row < args.Q ? row : args.Q - 1;           // junk rows repeat the last pixel (never stored)
+        const uint32_t swz = (uint32_t)(row & 7);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kRing;
+        int t = 0, it = 0;
+        for (int tile = blockIdx.x; tile < args.tiles; tile += gridDim.x, ++t) {
+            const int st = t % SF_ISTAGES;
+            const uint32_t iph = (uint32_t)(t / SF_ISTAGES) & 1;
+            mbar_wait(&ifull[st], iph);
+            const float* in = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(inrows) + (size_t)st * in_stride) + 2 * qq + 1;   // column 2q - 3 + s -> staged 2q + s + 1
+#pragma unroll
+            for (int kb = 0; kb < SF_KB; ++kb, ++it) {
+                const int sl = it % SF_ASLOTS;
+                const uint32_t ph = (uint32_t)(it / SF_ASLOTS) & 1;
+                mbar_wait(&aempty[sl], ph ^ 1);
+                uint8_t* arow = aslots + (size_t)sl * TC_A_BYTES + (size_t)row * 128;
+                uint32_t lo[32];
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    float v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int k = kb * 32 + c4 * 4 + j;        // compile-time after unrolling
+                        if (k < 147) {
+                            const int c = k / 49, rs = k - c * 49, r = rs / 7, s = rs - r * 7;
+                            v[j] = in[c * args.cstride + r * args.pitch + s];
+                        } else v[j] = 0.f;
+                        lo[c4 * 4 + j] = __float_as_uint(v[j] - __uint_as_float(__float_as_uint(v[j]) & 0xFFFFE000u));
+                    }
+                    *reinterpret_cast<float4*>(arow + (((uint32_t)c4 ^ swz) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+                }
+                tmem_st32(lane_addr + 32u * (uint32_t)sl, lo);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                fence_proxy_async();                               // generic-proxy writes of A_hi -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&afull[sl]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&iempty[st]);
+        }
+    } else if (warp >= 8) {
+        // ===== epilogue: thread = output pixel; + bias, ReLU, two swizzled 32-channel slots, TMA store of the Q valid rows =====
+        const int ew = warp - 8;
+        const int row = ew * 32 + lane;
+        const uint32_t swz = (uint32_t)(row & 7);
+        const uint32_t tlane = tmem_base + ((uint32_t)(ew * 32) << 16);
+        const float* __restrict__ gbias = args.bias;
+        int t = 0;
+        for (int tile = blockIdx.x; tile < args.tiles; tile += gridDim.x, ++t) {
+            const int acc = t & 1;
+            mbar_wait(&tfull[acc], (uint32_t)(t >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tacc = tlane + (uint32_t)acc * 128u;
+            float o[64];
+#pragma unroll
+            for (int off = 0; off < 64; off += 16) {
+                uint32_t m0[16], c0[16];
+                tmem_ld16_nowait(tacc + (uint32_t)off, m0);
+                tmem_ld16_nowait(tacc + 64u + (uint32_t)off, c0);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) o[off + i] = __fadd_rn(__uint_as_float(m0[i]), __uint_as_float(c0[i]));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            asm volatile("bar.sync 1, 128;" ::: "memory");          // the previous tile's stores have read the slots (thread 256 waited)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint8_t* srow = staging + (size_t)half * EPI_SLOT_BYTES + (size_t)row * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 bv = gbias ? __ldg(reinterpret_cast<const float4*>(gbias + half * 32) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 v = make_float4(o[half * 32 + 4 * c] + bv.x, o[half * 32 + 4 * c + 1] + bv.y,
+                                           o[half * 32 + 4 * c + 2] + bv.z, o[half * 32 + 4 * c + 3] + bv.w);
+                    if (args.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                    *reinterpret_cast<float4*>(srow + (((uint32_t)c ^ swz) << 4)) = v;
+                }
+            }
+            fence_proxy_async();
+            asm volatile("bar.sync 2, 128;" ::: "memory");
+            if (threadIdx.x == 256) {
+                const int m0 = tile * args.Q;                      // tile = n * P + p: rows (n, p, 0..Q-1) of y [N*P*Q, 64]
+                tma_store_2d(&tmOut, staging, 0, m0);
+                tma_store_2d(&tmOut, staging + EPI_SLOT_BYTES, 32, m0);
+                bulk_commit();
+                bulk_wait_read0();
+            }
+        }
+        if (threadIdx.x == 256) bulk_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host: tensor maps (driver entry points resolved at run time: no link-time libcuda dependency)
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1900,6 +2122,31 @@ static int get_map_im2col(CUtensorMap* out, const float* base, int N, int H, int
     auto it = g_maps.find(key);
     if (it != g_maps.end()) { *out = it->second; return I2V_OK; }
     if (int r = make_map_im2col(out, base, N, H, W, C, lower_w, lower_h, upper_w, upper_h, stride)) return r;
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps.emplace(key, *out);
+    return I2V_OK;
+}
+
+
+// 3-D [planes, H, W] f32 view of an NCHW image batch, box [1, 7, box_w], no swizzle, zero fill outside (negative start
+// coordinates are the convolution's padding)
+static int make_map_planes(CUtensorMap* map, const float* base, uint64_t planes, uint64_t H, uint64_t W, uint32_t box_w, uint32_t box_h) {
+    cuuint64_t dims[3] = {W, H, planes};
+    cuuint64_t strides[2] = {W * sizeof(float), H * W * sizeof(float)};
+    cuuint32_t box[3] = {box_w, box_h, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (planes) failed (%d) planes=%llu H=%llu W=%llu box=%u", (int)r, (unsigned long long)planes, (unsigned long long)H, (unsigned long long)W, box_w); return I2V_ECUDA; }
+    return I2V_OK;
+}
+static int get_map_planes(CUtensorMap* out, const float* base, int planes, int H, int W, int box_w, int box_h) {
+    MapKey key{base, planes, H, W, box_w, box_h, 0, 0, 5};
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return I2V_OK; }
+    if (int r = make_map_planes(out, base, (uint64_t)planes, (uint64_t)H, (uint64_t)W, (uint32_t)box_w, (uint32_t)box_h)) return r;
     if (g_maps.size() > 4096) g_maps.clear();
     g_maps.emplace(key, *out);
     return I2V_OK;
@@ -2311,6 +2558,47 @@ extern "C" int i2v_conv_stem_dgrad_direct_f32(const i2v_conv_desc* d, const floa
     const int grid = a.units < sm_count() ? a.units : sm_count();
     stem_dgrad_direct_kernel<<<grid, SD_THREADS, smem, as_stream(stream)>>>(tmA, tmBhi, tmBlo, a);
     I2V_LAUNCH_CHECK("i2v_conv_stem_dgrad_direct_f32");
+    return I2V_OK;
+}
+
+// First-layer forward without the patch matrix (stem_fwd_rows_kernel).  wk_hi / wk_lo = [64, 160] K-major, k = (c,r,s) + 13
+// zero columns: exactly the operands of i2v_conv_stem_fwd_tc_f32.
+extern "C" int i2v_conv_stem_fwd_rows_supported(const i2v_conv_desc* d) {
+    return d && d->Cin == 3 && d->Cout == 64 && d->R == 7 && d->S == 7 && d->stride == 2 && d->pad == 3 && d->Q >= 1 &&
+           d->Q <= TC_BM && d->P >= 1 && d->W % 4 == 0 && d->W + 10 <= 256 && d->H >= 1;
+}
+
+extern "C" int i2v_conv_stem_fwd_rows_f32(const i2v_conv_desc* d, const float* x, const float* wk_hi, const float* wk_lo,
+                                          const float* bias, float* y, int flags, i2v_stream_t stream) {
+    I2V_REQUIRE(d && x && wk_hi && wk_lo && y, "null pointer");
+    I2V_REQUIRE(i2v_conv_stem_fwd_rows_supported(d), "shape not supported by the row-tile first-layer forward");
+    I2V_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wk_hi) | reinterpret_cast<uintptr_t>(wk_lo) |
+                  reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0, "all tensors must be 16-byte aligned");
+    if (d->N == 0) return I2V_OK;
+    if (int r = resolve_driver()) return r;
+    const int64_t M = (int64_t)d->N * d->P * d->Q;
+    I2V_REQUIRE(M < (int64_t)0x7fffffff, "too many pixels for one launch");
+    const int pitch = (d->W + 7 + 3) / 4 * 4;
+    CUtensorMap tmX, tmBhi, tmBlo, tmOut;
+    if (int r = get_map_planes(&tmX, x, d->N * 3, d->H, d->W, pitch, 7)) return r;
+    if (int r = get_map_2d(&tmBhi, wk_hi, 64, SF_KB * TC_BK, 64)) return r;
+    if (int r = get_map_2d(&tmBlo, wk_lo, 64, SF_KB * TC_BK, 64)) return r;
+    if (int r = get_map_2d(&tmOut, y, (int)M, 64, d->Q)) return r;
+    StemFwdArgs a{};
+    a.bias = bias; a.N = d->N; a.H = d->H; a.W = d->W; a.P = d->P; a.Q = d->Q; a.relu = (flags & I2V_EPI_RELU) ? 1 : 0;
+    a.pitch = pitch; a.tiles = d->N * d->P;
+    a.cstride = (7 * pitch * 4 + 127) / 128 * 32;
+    const size_t in_stride = (size_t)3 * a.cstride * 4;
+    const size_t smem = 1024 + SF_KB * SF_B_KB + (size_t)SF_ASLOTS * TC_A_BYTES + 2 * EPI_SLOT_BYTES + SF_ISTAGES * in_stride + 512;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(stem_fwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "i2v_conv_stem_fwd_rows_f32 (shared memory)");
+        smem_set = smem;
+    }
+    const int grid = a.tiles < sm_count() ? a.tiles : sm_count();
+    stem_fwd_rows_kernel<<<grid, SF_THREADS, smem, as_stream(stream)>>>(tmX, tmBhi, tmBlo, tmOut, a);
+    I2V_LAUNCH_CHECK("i2v_conv_stem_fwd_rows_f32");
     return I2V_OK;
 }
 

@@ -126,6 +126,7 @@ class DenseNetEngine(NativeEngine):
         self.use_stem_tc = os.environ.get("I2V_NATIVE_STEM_TC", "1") != "0"
         self._zbuf = None
         self.stem_dgrad_direct = os.environ.get("I2V_STEM_DGRAD_DIRECT", "1") != "0"
+        self.stem_fwd_rows = os.environ.get("I2V_STEM_FWD_ROWS", "1") != "0"
         self.stem_direct = False
         self._xpbuf = None
         self._cache = {}

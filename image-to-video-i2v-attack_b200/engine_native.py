@@ -315,6 +315,8 @@ class NativeEngine:
         self._zbuf = None
         # first-layer data gradient without the Z^T scratch (i2v_conv_stem_dgrad_direct_f32); $I2V_STEM_DGRAD_DIRECT=0: GEMM + col2im
         self.stem_dgrad_direct = os.environ.get("I2V_STEM_DGRAD_DIRECT", "1") != "0"
+        # first-layer forward without the im2col patch matrix, one output row per tile (i2v_conv_stem_fwd_rows_f32); =0: im2col + GEMM
+        self.stem_fwd_rows = os.environ.get("I2V_STEM_FWD_ROWS", "1") != "0"
         # EXPERIMENTAL: first-layer forward without the im2col patch matrix (i2v_conv_stem_fwd_direct_f32)
         self.stem_direct = os.environ.get("I2V_STEM_DIRECT", "0") == "1"
         self._xpbuf = None
@@ -390,7 +392,11 @@ class NativeEngine:
 
     # ---- forward -------------------------------------------------------------------------------------
     def _conv_fwd(self, op, d, x, y, residual, bits_out=None):
-        if (op.x_nchw and residual is None and self.use_tc and self.use_stem_tc and self.tf32x3 and self.stem_direct
+        if (op.x_nchw and residual is None and self.use_tc and self.use_stem_tc and self.tf32x3 and self.stem_fwd_rows
+                and op.tc_stem_fwd is not None and op.tc_stem_fwd[0].shape == (64, 160) and capi.conv_stem_fwd_rows_supported(d)):
+            hi, lo, _ = op.tc_stem_fwd
+            capi.conv_stem_fwd_rows(d, x, hi, lo, op.bias, y, relu=op.relu)
+        elif (op.x_nchw and residual is None and self.use_tc and self.use_stem_tc and self.tf32x3 and self.stem_direct
                 and op.tc_stem_direct is not None and capi.conv_stem_fwd_direct_supported(d)):
             hi, lo, _ = op.tc_stem_direct
             nfl = capi.stem_fwd_direct_scratch_floats(d)

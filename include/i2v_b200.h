@@ -307,6 +307,13 @@ int     i2v_conv_stem_fwd_direct_f32(const i2v_conv_desc* d, const float* x, con
 int i2v_conv_stem_dgrad_direct_supported(const i2v_conv_desc* d);
 int i2v_conv_stem_dgrad_direct_f32(const i2v_conv_desc* d, const float* dy, const float* wd_hi, const float* wd_lo, float* dx,
                                    i2v_stream_t stream);
+/* First-layer forward WITHOUT the patch matrix (7x7 / stride 2 / pad 3, Cout = 64, Q <= 128, W % 4 == 0; image_attacks.py:334
+ * for that layer): one output row per tile, the 7 x 3 input rows staged by TMA (zero filled outside the image), the
+ * 128 x 160 patch tile assembled on chip, weights resident; bias + ReLU in the epilogue.  wk_hi / wk_lo as for
+ * i2v_conv_stem_fwd_tc_f32: [64, 160] K-major, k = (c,r,s) + 13 zero columns.                                      */
+int i2v_conv_stem_fwd_rows_supported(const i2v_conv_desc* d);
+int i2v_conv_stem_fwd_rows_f32(const i2v_conv_desc* d, const float* x, const float* wk_hi, const float* wk_lo,
+                               const float* bias, float* y, int flags, i2v_stream_t stream);
 int i2v_conv_stem_fwd_tc_f32(const i2v_conv_desc* d, const float* x, const float* wk_hi, const float* wk_lo,
                              const float* bias, float* col_scratch, float* y, int flags, i2v_stream_t stream);
 

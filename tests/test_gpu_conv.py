@@ -543,6 +543,35 @@ def test_stem_dgrad_tc(H, W, k, s, p, n, x3):
     assert err <= ((2e-5 + Cout * 2.0 ** -24) if x3 else 4e-3), err
 
 
+@pytest.mark.parametrize("H,W,n", [(224, 224, 5), (64, 64, 3), (32, 32, 2), (16, 16, 3), (62, 60, 2), (224, 200, 1), (8, 8, 1)])
+def test_stem_fwd_rows(H, W, n):
+    """First-layer forward without the patch matrix (one output row per tile, patch tile assembled on chip from TMA-staged
+    input rows): against the float64 convolution with bias + ReLU, same error model as test_stem_fwd_tc; even sizes, widths
+    whose last tile lanes are junk, tiny images; twice in a row (deterministic, NaN-prefilled output)."""
+    from i2v_b200.engine_native import _split_tf32
+    g = torch.Generator().manual_seed(4)
+    Cout, k, s, p = 64, 7, 2, 3
+    x = torch.randn(n, 3, H, W, generator=g)
+    w = torch.randn(Cout, 3, k, k, generator=g) / (3 * k * k) ** 0.5
+    shift = torch.randn(Cout, generator=g) * 0.1
+    P, Q = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    d = capi.ConvDesc(n, H, W, 3, Cout, k, k, s, p, P, Q)
+    assert capi.conv_stem_fwd_rows_supported(d)
+    wk = torch.cat([w.reshape(Cout, 147), torch.zeros(Cout, 13)], 1).contiguous().to(DEV)
+    hi, lo, _ = _split_tf32(wk)
+    outs = []
+    for _ in range(2):
+        y = torch.full((n, P, Q, Cout), float("nan"), device=DEV)
+        capi.conv_stem_fwd_rows(d, x.to(DEV), hi, lo, shift.to(DEV), y, relu=True)
+        outs.append(y)
+    assert torch.equal(outs[0], outs[1])
+    ref64 = _ref_conv(x, w, torch.ones(Cout), shift, s, p, None, True, torch.float64)
+    got = outs[0].permute(0, 3, 1, 2).cpu().double()
+    assert torch.isfinite(got).all()
+    err = (got - ref64).abs().max() / ref64.abs().max()
+    assert err <= (1e-5 + 3 * k * k * 2.0 ** -24), err
+
+
 @pytest.mark.parametrize("H,W,n", [(224, 224, 5), (64, 64, 3), (32, 32, 2), (16, 16, 3), (63, 61, 2), (224, 200, 1), (8, 8, 1)])
 def test_stem_dgrad_direct(H, W, n):
     """First-layer data gradient without scratch (one dy row per tile, on-chip col2im in a register window, half-image
