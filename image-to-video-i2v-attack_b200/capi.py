@@ -64,6 +64,8 @@ SIGNATURES = {
     "i2v_conv_stem_fwd_direct_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_stem_dgrad_direct_supported": ([_c_p], _c_int),
     "i2v_conv_stem_dgrad_direct_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p], _c_int),
+    "i2v_conv_stem_dgrad_pool_supported": ([_c_p, _c_int, _c_int], _c_int),
+    "i2v_conv_stem_dgrad_pool_f32": ([_c_p, _c_int, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p], _c_int),
     "i2v_conv_stem_fwd_rows_supported": ([_c_p], _c_int),
     "i2v_conv_stem_fwd_rows_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_stem_fwd_tc_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
@@ -122,7 +124,7 @@ def load():
 # tensors read + written once, 2 x MACs of the convolution).
 LAUNCHES = {}
 PROFILE_EVENTS = None
-_NO_KERNEL = ("i2v_set_adam_arithmetic", "i2v_conv_stem_fwd_rows_supported", "i2v_conv_stem_dgrad_direct_supported", "i2v_conv_tc_set_pair_minkit", "i2v_conv_stem_fwd_direct_supported", "i2v_conv_stem_fwd_direct_scratch_floats", "i2v_conv_stem_dgrad_tc_rows", "i2v_device_check", "i2v_std_workspace_doubles", "i2v_ila_workspace_doubles", "i2v_adam_step_table", "i2v_conv_tc_supported", "i2v_conv_stem_supported",
+_NO_KERNEL = ("i2v_set_adam_arithmetic", "i2v_conv_stem_dgrad_pool_supported", "i2v_conv_stem_fwd_rows_supported", "i2v_conv_stem_dgrad_direct_supported", "i2v_conv_tc_set_pair_minkit", "i2v_conv_stem_fwd_direct_supported", "i2v_conv_stem_fwd_direct_scratch_floats", "i2v_conv_stem_dgrad_tc_rows", "i2v_device_check", "i2v_std_workspace_doubles", "i2v_ila_workspace_doubles", "i2v_adam_step_table", "i2v_conv_tc_supported", "i2v_conv_stem_supported",
               "i2v_conv_tc_set_trace")
 
 
@@ -454,6 +456,23 @@ def conv_stem_dgrad_direct(desc, dy, wd_hi, wd_lo, dx):
     with _Timed("i2v_conv_stem_dgrad_f32", nb, fl):
         _check(load().i2v_conv_stem_dgrad_direct_f32(ctypes.addressof(desc), _dev(dy), _dev(wd_hi), _dev(wd_lo), _dev(dx),
                                                      _stream()), "i2v_conv_stem_dgrad_direct_f32")
+
+
+def conv_stem_dgrad_pool_supported(desc, P2, Q2):
+    return bool(load().i2v_conv_stem_dgrad_pool_supported(ctypes.addressof(desc), int(P2), int(Q2)))
+
+
+def conv_stem_dgrad_pool(desc, dy_pooled, argmax, wd_hi, wd_lo, dx):
+    """Max-pool backward (3x3 / stride 2 / pad 1) + first-layer data gradient in one kernel (see include/i2v_b200.h):
+    dy_pooled / argmax = [N, P2, Q2, 64] f32 / u8."""
+    n, P2, Q2, c = dy_pooled.shape
+    assert c == 64 and argmax.shape == dy_pooled.shape and argmax.dtype == torch.uint8
+    nb, fl = _conv_cost(desc)
+    # bytes: the pooled gradient + argmax in, the image gradient out (the stem activation's gradient is never materialised)
+    nb = dy_pooled.numel() * 5 + desc.N * 3 * desc.H * desc.W * 4
+    with _Timed("i2v_conv_stem_dgrad_pool_f32", nb, fl):
+        _check(load().i2v_conv_stem_dgrad_pool_f32(ctypes.addressof(desc), int(P2), int(Q2), _dev(dy_pooled), _dev(argmax, torch.uint8),
+                                                   _dev(wd_hi), _dev(wd_lo), _dev(dx), _stream()), "i2v_conv_stem_dgrad_pool_f32")
 
 
 def stem_direct_dgrad_weights(w_stem):

@@ -39,6 +39,7 @@
 #include <stdlib.h>
 #include <mutex>
 #include <unordered_map>
+#include <type_traits>
 #include "common.cuh"
 
 namespace i2v {
@@ -1472,6 +1473,7 @@ struct StemDirectArgs {
     int units;                           // strips: 2 per image (1 when the image is small)
     int strips_per_image;
     int dbg;                             // timing experiments ($I2V_STEM_DBG; wrong results): 1 no MMA, 2 no col2im math, 4 no split, 8 no TMEM loads
+    int P2, Q2;                          // fused pooling variant: size of the pooled map (3x3 / stride 2 / pad 1 over P x Q)
 };
 
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
@@ -1651,6 +1653,348 @@ stem_dgrad_direct_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&splitb[st]);           // one arrival per warp: 128 arrivals per row serialise on the barrier word
+            }
+        }
+    } else if (warp >= 8) {
+        // ===== epilogue: on-chip col2im; warp = (channel c, lane quarter); thread = dy pixel q = image columns 2q, 2q+1 =====
+        const int c = (warp - 8) >> 2;
+        const int ew = warp & 3;                                  // TMEM lane quarter of this warp
+        const int q = ew * 32 + lane;
+        const bool v1ok = q + 1 < args.Q, v0ok = q + 2 < args.Q;
+        const bool l31 = lane == 31, l30 = lane == 30, l0 = lane == 0;
+        const uint32_t tlane = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(c * SD_NC);
+        float* ebase = edge + (size_t)c * 2 * kEdgeBuf;
+        float win[7][2];                                          // [image row 2p-3+i][column 2q+e] of channel c
+        int t = 0;
+        for (int u = blockIdx.x; u < args.units; u += gridDim.x) {
+            int img, pa, pb, ha, hb;
+            sd_strip(args, u, img, pa, pb, ha, hb);
+#pragma unroll
+            for (int i = 0; i < 7; ++i) { win[i][0] = 0.f; win[i][1] = 0.f; }
+            float* dxc = args.dx + ((int64_t)img * 3 + c) * args.H * args.W + 2 * q;
+            auto emit = [&](int h, const float (&w0)[2]) {
+                if (h < ha || h >= hb) return;
+                float* o = dxc + (int64_t)h * args.W;
+                if (2 * q + 1 < args.W) {
+                    if ((args.W & 1) == 0) *reinterpret_cast<float2*>(o) = make_float2(w0[0], w0[1]);
+                    else { o[0] = w0[0]; o[1] = w0[1]; }
+                } else if (2 * q < args.W) o[0] = w0[0];
+            };
+            for (int p = pa; p <= pb; ++p, ++t) {
+                const int acc = t & 1;
+                mbar_wait(&tfull[acc], (uint32_t)(t >> 1) & 1);
+                tc_fence_after();
+                const uint32_t tacc = tlane + (uint32_t)acc * SD_NZ;
+                float z[SD_NC];
+                if (args.dbg & 8) {
+#pragma unroll
+                    for (int i = 0; i < SD_NC; ++i) z[i] = 1.f;
+                } else {
+                    uint32_t m0[16], m1[16], m2[16], m3[16];       // taps 0..47 and (last column of a load starting at 33) tap 48
+                    tmem_ld16_nowait(tacc, m0);
+                    tmem_ld16_nowait(tacc + 16u, m1);
+                    tmem_ld16_nowait(tacc + 32u, m2);
+                    tmem_ld16_nowait(tacc + 33u, m3);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        z[i] = __uint_as_float(m0[i]); z[16 + i] = __uint_as_float(m1[i]); z[32 + i] = __uint_as_float(m2[i]);
+                    }
+                    z[48] = __uint_as_float(m3[15]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);          // this warp's share of the accumulator stage is in registers
+                if (!(args.dbg & 2)) {
+                    float* eb = ebase + (size_t)(t & 1) * kEdgeBuf;
+                    float* mine = eb + (size_t)(ew + 1) * kEdgeSlot;
+#pragma unroll
+                    for (int r = 0; r < 7; ++r) {                  // publish: lane 0 -> s = 0,1,2; lane 1 -> s = 0; lane 31 -> s = 5,6
+                        if (l0) { mine[r * 6 + 0] = z[r * 7 + 0]; mine[r * 6 + 1] = z[r * 7 + 1]; mine[r * 6 + 2] = z[r * 7 + 2]; }
+                        if (lane == 1) mine[r * 6 + 3] = z[r * 7 + 0];
+                        if (l31) { mine[r * 6 + 4] = z[r * 7 + 5]; mine[r * 6 + 5] = z[r * 7 + 6]; }
+                    }
+                    asm volatile("bar.sync %0, 128;" :: "r"(1 + c) : "memory");
+                    const float* en = eb + (size_t)(ew + 2) * kEdgeSlot;     // next warp (slot 5 = zeros for the last one)
+                    const float* ep = eb + (size_t)ew * kEdgeSlot;           // previous warp (slot 0 = zeros for the first one)
+#pragma unroll
+                    for (int r = 0; r < 7; ++r) {
+                        float v1 = __shfl_down_sync(0xffffffffu, z[r * 7 + 1], 1);
+                        float v2 = __shfl_down_sync(0xffffffffu, z[r * 7 + 2], 1);
+                        float v0 = __shfl_down_sync(0xffffffffu, z[r * 7 + 0], 2);
+                        float v5 = __shfl_up_sync(0xffffffffu, z[r * 7 + 5], 1);
+                        float v6 = __shfl_up_sync(0xffffffffu, z[r * 7 + 6], 1);
+                        const float n0 = en[r * 6 + 0], n1 = en[r * 6 + 1], n2 = en[r * 6 + 2], n3 = en[r * 6 + 3];   // broadcast loads
+                        const float p5 = ep[r * 6 + 4], p6 = ep[r * 6 + 5];
+                        v1 = l31 ? n1 : v1; v2 = l31 ? n2 : v2;
+                        v0 = l31 ? n3 : (l30 ? n0 : v0);
+                        v5 = l0 ? p5 : v5; v6 = l0 ? p6 : v6;
+                        v1 = v1ok ? v1 : 0.f; v2 = v1ok ? v2 : 0.f; v0 = v0ok ? v0 : 0.f;       // q+1 / q+2 beyond the dy row
+                        // column 2q: s = 1 (q+1), 3 (q), 5 (q-1); column 2q+1: s = 0 (q+2), 2 (q+1), 4 (q), 6 (q-1)
+                        win[r][0] = __fadd_rn(win[r][0], __fadd_rn(__fadd_rn(v1, z[r * 7 + 3]), v5));
+                        win[r][1] = __fadd_rn(win[r][1], __fadd_rn(__fadd_rn(__fadd_rn(v0, v2), z[r * 7 + 4]), v6));
+                    }
+                } else {
+                    win[0][0] += z[0] + z[48];
+                }
+                emit(2 * p - 3, win[0]);                           // image rows 2p-3 and 2p-2 are complete
+                emit(2 * p - 2, win[1]);
+#pragma unroll
+                for (int i = 0; i < 5; ++i) { win[i][0] = win[i + 2][0]; win[i][1] = win[i + 2][1]; }
+                win[5][0] = win[5][1] = win[6][0] = win[6][1] = 0.f;
+            }
+            // strip done: the window holds image rows 2 pb - 1 .. 2 pb + 3
+#pragma unroll
+            for (int i = 0; i < 5; ++i) emit(2 * pb - 1 + i, win[i]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+__device__ __forceinline__ void lds128(uint32_t addr, uint32_t (&v)[4]) {
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr));
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// registers -> one TMEM lane per thread, 4 consecutive columns
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+constexpr int SP_AST = 2, SP_PST = 2;      // fused pooling variant: A stages / pooled-row stages
+__host__ __device__ __forceinline__ uint32_t sp_gtile_bytes(int Q2) { return ((uint32_t)Q2 * 128u + 1023u) & ~1023u; }   // SWIZZLE_128B atom
+__host__ __device__ __forceinline__ uint32_t sp_atile_bytes(int Q2) { return ((uint32_t)Q2 * 64u + 1023u) & ~1023u; }    // keeps every tile 1024-aligned
+
+// The same kernel with the max pooling's backward pass fused in front of it (i2v_conv_stem_dgrad_pool_f32): the 822 MB
+// gradient of the stem activation is never written or read.  The producer stages the one or two POOLED gradient rows (and
+// their argmax rows) whose 3x3 / stride-2 / pad-1 windows cover stem row p; the four assemble warps (thread = stem pixel) gather
+// g[c] = sum over the <= 4 covering windows with argmax == this position of the pooled gradient, in the window order of
+// i2v_maxpool_bwd_f32 (bit-identical to running that kernel first), write a_hi into the swizzled A tile and a_lo into the
+// tensor-memory ring.  Everything behind the A tile is the kernel above.
+__global__ void __launch_bounds__(SD_THREADS, 1)
+stem_dgrad_pool_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmAm,
+                       const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, const StemDirectArgs args) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* bhi = smem;                                       // [kb] tiles of 20 KB (160 taps x 32 channels)
+    uint8_t* blo = smem + 2 * SD_B_TILE;
+    uint8_t* atiles = smem + 4 * SD_B_TILE;                    // 80 KB = 1024-aligned; per stage: kb0, kb1
+    constexpr int AST = SP_AST, PST = SP_PST;                  // A stages / pooled-row stages of this variant
+    // pooled rows: per stage and pooled row i in {0, 1}: two SWIZZLE_128B tiles [Q2 pixels][32 channels] f32 (kb = 0, 1), then
+    // per stage and i one SWIZZLE_64B tile [Q2 pixels][64 channels] u8.  A thread (stem pixel q) reads pooled pixels q/2 and
+    // (q+1)/2: 16 different pixels per warp at the same channels — with dense rows that is a 16-way bank conflict; with the
+    // TMA swizzles 8 consecutive pixels land in 8 different 16-byte bank groups (2 wavefronts for 256 bytes: conflict-free).
+    uint8_t* prows = atiles + (size_t)AST * 2 * TC_A_BYTES;
+    const uint32_t gtile = sp_gtile_bytes(args.Q2), atile = sp_atile_bytes(args.Q2);
+    const uint32_t pstage = 4u * gtile + 2u * atile;           // [i][kb] gradient tiles, then [i] argmax tiles
+    float* edge = reinterpret_cast<float*>(prows + (size_t)PST * pstage);   // [3 channels][2 buffers][6 slots][7 groups][6]
+    constexpr int kEdgeSlot = 7 * 6, kEdgeBuf = 6 * kEdgeSlot;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(edge + 3 * 2 * kEdgeBuf);
+    uint64_t* bfull = bars;
+    uint64_t* aempty = bfull + 1;
+    uint64_t* splitb = aempty + AST;
+    uint64_t* tfull = splitb + AST;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* pfull = tempty + 2;                               // pooled rows landed
+    uint64_t* pempty = pfull + PST;                             // ... consumed by the 4 assemble warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pempty + PST);
+    // 64 bytes of argmax = 255 ("dead window"): where the windows that do not exist for a pixel point their argmax loads
+    uint8_t* dead64 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 63) & ~(uintptr_t)63);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto a_tile = [&](int st, int kb) { return atiles + ((size_t)st * 2 + kb) * TC_A_BYTES; };
+
+    for (int i = threadIdx.x; i < 3 * 2 * kEdgeBuf; i += SD_THREADS) edge[i] = 0.f;     // slots 0 and 5 are never written again
+    if (threadIdx.x < 16) reinterpret_cast<uint32_t*>(dead64)[threadIdx.x] = 0xFFFFFFFFu;
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmG); prefetch_tmap(&tmAm); prefetch_tmap(&tmBhi); prefetch_tmap(&tmBlo);
+        for (int s2 = 0; s2 < PST; ++s2) { mbar_init(&pfull[s2], 1); mbar_init(&pempty[s2], 4); }
+        mbar_init(bfull, 1);
+        for (int s = 0; s < AST; ++s) { mbar_init(&aempty[s], 1); mbar_init(&splitb[s], 4); }       // one arrival per warp
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 12); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;       // columns: accumulator stage a at 160 a, A_lo ring 320 + 32 (2 stage + kb)
+    constexpr uint32_t kRing = 320;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bfull, 4 * SD_B_TILE);          // the weights stay resident
+            for (int kb = 0; kb < 2; ++kb) {
+                tma_load_2d(&tmBhi, bfull, bhi + (size_t)kb * SD_B_TILE, kb * TC_BK, 0);
+                tma_load_2d(&tmBlo, bfull, blo + (size_t)kb * SD_B_TILE, kb * TC_BK, 0);
+            }
+            const uint32_t row_tx = (uint32_t)args.Q2 * (64u * 4u + 64u);      // bytes of one pooled row: gradient + argmax
+            int t = 0;
+            for (int u = blockIdx.x; u < args.units; u += gridDim.x) {
+                int img, pa, pb, ha, hb;
+                sd_strip(args, u, img, pa, pb, ha, hb);
+                for (int p = pa; p <= pb; ++p, ++t) {
+                    // stem row p is covered by the pooling windows of pooled rows p/2 (p even) or (p-1)/2 and (p+1)/2 (p odd)
+                    const int ps = t % PST;
+                    const uint32_t ph = (uint32_t)(t / PST) & 1;
+                    const int ra = p >> 1, rb = (p + 1) >> 1;
+                    const int nrows = (rb != ra && rb < args.P2) ? 2 : 1;
+                    mbar_wait(&pempty[ps], ph ^ 1);
+                    mbar_arrive_expect_tx(&pfull[ps], (uint32_t)nrows * row_tx);
+                    uint8_t* gdst = prows + (size_t)ps * pstage;
+                    uint8_t* adst = gdst + 4 * gtile;
+                    for (int i = 0; i < nrows; ++i) {
+                        const int m0 = (img * args.P2 + (i ? rb : ra)) * args.Q2;
+                        tma_load_2d(&tmG, &pfull[ps], gdst + (size_t)(2 * i) * gtile, 0, m0);
+                        tma_load_2d(&tmG, &pfull[ps], gdst + (size_t)(2 * i + 1) * gtile, TC_BK, m0);
+                        tma_load_2d(&tmAm, &pfull[ps], adst + (size_t)i * atile, 0, m0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // the MMA issuer: acc (+)= a_hi b_hi + a_hi b_lo + a_lo (tensor memory) b_hi, 24 instructions of N = 160 per dy row
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(SD_NZ);
+            mbar_wait(bfull, 0);
+            int t = 0;
+            for (int u = blockIdx.x; u < args.units; u += gridDim.x) {
+                int img, pa, pb, ha, hb;
+                sd_strip(args, u, img, pa, pb, ha, hb);
+                for (int p = pa; p <= pb; ++p, ++t) {
+                    const int st = t % AST;
+                    const uint32_t ph = (uint32_t)(t / AST) & 1;
+                    const int acc = t & 1;
+                    mbar_wait(&splitb[st], ph);                  // the assemble warps have built a_hi (shared memory) and a_lo (tensor memory)
+                    mbar_wait(&tempty[acc], ((uint32_t)(t >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t dacc = tmem_base + (uint32_t)acc * SD_NZ;
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const uint64_t da = umma_desc_sw128(smem_u32(a_tile(st, kb)));
+                        const uint64_t dbh = umma_desc_sw128(smem_u32(bhi + (size_t)kb * SD_B_TILE));
+                        const uint64_t dbl = umma_desc_sw128(smem_u32(blo + (size_t)kb * SD_B_TILE));
+                        const uint32_t talo = tmem_base + kRing + 32u * (uint32_t)(2 * st + kb);
+#pragma unroll
+                        for (int kk = 0; kk < TC_BK / 8; ++kk) {
+                            if (args.dbg & 1) continue;
+                            umma_tf32(dacc, da + 2 * kk, dbh + 2 * kk, idesc, (kb | kk) ? 1u : 0u);
+                            umma_tf32(dacc, da + 2 * kk, dbl + 2 * kk, idesc, 1u);
+                            umma_tf32_ts(dacc, talo + 8u * kk, dbh + 2 * kk, idesc, 1u);
+                        }
+                    }
+                    umma_commit(&tfull[acc]);
+                    umma_commit(&aempty[st]);
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===== assemble: thread = stem pixel q; its 64-channel gradient = max-pool backward of the pooled gradient (gather form,
+        // windows in (P', Q') order exactly as i2v_maxpool_bwd_f32; argmax 255 = the forward pass marked the window dead) ======
+        const int row = threadIdx.x - 128;
+        const uint32_t swz = (uint32_t)(row & 7);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kRing;
+        const bool qv = row < args.Q;
+        // pooled columns Q' with 2Q'-1 <= q <= 2Q'+1: window j = 0 is pooled pixel q/2, window j = 1 pooled pixel (q+1)/2 (odd q)
+        const int qa = row >> 1, qb = (row + 1) >> 1;
+        const bool onj[2] = {qv, qv && qb != qa && qb < args.Q2};
+        // Addresses are XOR-composed: a tile base is 1024-aligned and a pixel's record 128 (gradient) / 64 (argmax) bytes, so
+        // base + swizzled chunk + word = (base ^ swizzle bits) ^ (loop bits) — one LOP3 per load inside the loop.  Windows that
+        // do not exist read the 64-byte block of 255s (never a winner) and the first gradient row (never added).
+        uint32_t goff[2], aoff[2];                                  // relative to the stage's gradient / argmax tile of pooled row i
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int qc = j ? qb : qa;
+            goff[j] = onj[j] ? ((uint32_t)qc * 128u) ^ ((uint32_t)(qc & 7) << 4) : 0u;
+            aoff[j] = onj[j] ? ((uint32_t)qc * 64u) ^ ((uint32_t)((qc >> 1) & 3) << 4) : 0u;
+        }
+        const uint32_t dead_addr = smem_u32(dead64);
+        const int wq[2] = {row - (2 * qa - 1), row - (2 * qb - 1)};          // column of this pixel inside the window of qa / qb
+        int t = 0;
+        for (int u = blockIdx.x; u < args.units; u += gridDim.x) {
+            int img, pa, pb, ha, hb;
+            sd_strip(args, u, img, pa, pb, ha, hb);
+            for (int p = pa; p <= pb; ++p, ++t) {
+                const int st = t % AST, ps = t % PST;
+                const uint32_t ph = (uint32_t)(t / AST) & 1, pph = (uint32_t)(t / PST) & 1;
+                const int ra = p >> 1, rb = (p + 1) >> 1;
+                const bool two_p = rb != ra && rb < args.P2;
+                mbar_wait(&pfull[ps], pph);
+                mbar_wait(&aempty[st], ph ^ 1);
+                tc_fence_after();
+                if (args.dbg & 4) { __syncwarp(); if (lane == 0) { mbar_arrive(&splitb[st]); mbar_arrive(&pempty[ps]); } continue; }
+                const uint32_t gsm = smem_u32(prows + (size_t)ps * pstage), asm_ = gsm + 4 * gtile;
+                // NI = pooled rows whose windows cover stem row p (warp-uniform): a compile-time constant per instantiation
+                auto gather = [&](auto ni_tag) {
+                    constexpr int NI = decltype(ni_tag)::value;
+                    uint32_t want[NI][2], aB[NI][2];
+#pragma unroll
+                    for (int i = 0; i < NI; ++i)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            // the window position this pixel has in window (i, j), replicated into the four bytes of a word
+                            want[i][j] = (uint32_t)((p - (2 * (i ? rb : ra) - 1)) * 3 + wq[j]) * 0x01010101u;
+                            aB[i][j] = onj[j] ? asm_ + (uint32_t)i * atile + aoff[j] : dead_addr;
+                        }
+                    // REAL loops over the 16 four-channel chunks of the pixel (2 k-blocks x 8): fully unrolled the body was
+                    // 52 KB of straight-line code run once per row, and 42 % of the assemble warps' stall samples were
+                    // instruction-cache misses (ncu source page); a_lo goes to tensor memory four columns at a time
+#pragma unroll 1
+                    for (int kb = 0; kb < 2; ++kb) {
+                        uint32_t gB[NI][2];
+#pragma unroll
+                        for (int i = 0; i < NI; ++i)
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) gB[i][j] = gsm + (uint32_t)(2 * i + kb) * gtile + goff[j];
+                        const uint32_t arow = smem_u32(a_tile(st, kb)) + (uint32_t)row * 128u;
+                        const uint32_t tcol = lane_addr + 32u * (uint32_t)(2 * st + kb);
+#pragma unroll 2
+                        for (int c4 = 0; c4 < 8; ++c4) {
+                            float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                            for (int i = 0; i < NI; ++i)
+#pragma unroll
+                                for (int j = 0; j < 2; ++j) {
+                                    // x has a zero byte where argmax == this pixel's position; the adds happen in window
+                                    // order under predicates (exact selection; what a window that is off loads is never added)
+                                    const uint32_t x = lds32(aB[i][j] ^ (uint32_t)((kb * 8 + c4) << 2)) ^ want[i][j];
+                                    uint32_t gv[4];
+                                    lds128(gB[i][j] ^ ((uint32_t)c4 << 4), gv);
+                                    if (!(x & 0x000000ffu)) g[0] += __uint_as_float(gv[0]);
+                                    if (!(x & 0x0000ff00u)) g[1] += __uint_as_float(gv[1]);
+                                    if (!(x & 0x00ff0000u)) g[2] += __uint_as_float(gv[2]);
+                                    if (!(x & 0xff000000u)) g[3] += __uint_as_float(gv[3]);
+                                }
+                            uint32_t lo4[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                lo4[j] = __float_as_uint(g[j] - __uint_as_float(__float_as_uint(g[j]) & 0xFFFFE000u));
+                            sts128(arow + (((uint32_t)c4 ^ swz) << 4), g[0], g[1], g[2], g[3]);
+                            tmem_st4(tcol + 4u * (uint32_t)c4, lo4);
+                        }
+                    }
+                };
+                if (two_p) gather(std::integral_constant<int, 2>{}); else gather(std::integral_constant<int, 1>{});
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                if (!(args.dbg & 64)) fence_proxy_async();         // generic-proxy writes of a_hi -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&splitb[st]); mbar_arrive(&pempty[ps]); }
             }
         }
     } else if (warp >= 8) {
@@ -2030,6 +2374,20 @@ static int make_map_2d_plain(CUtensorMap* map, const float* base, uint64_t rows,
     return I2V_OK;
 }
 
+// 2-D row-major [rows, 64] u8 (the pooling's argmax plane), box [box_rows, 64], SWIZZLE_64B: the 16-byte chunk of a 64-byte
+// row is XORed with (row / 2) % 4, so 8 consecutive rows occupy 8 different bank groups
+static int make_map_u8_rows64(CUtensorMap* map, const uint8_t* base, uint64_t rows, uint32_t box_rows) {
+    cuuint64_t dims[2] = {64, rows};
+    cuuint64_t strides[1] = {64};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(base), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (u8 rows) failed (%d) rows=%llu box=%u", (int)r, (unsigned long long)rows, box_rows); return I2V_ECUDA; }
+    return I2V_OK;
+}
+
 // im2col-mode map over an NHWC activation tensor: 32 channels x 128 pixels per load
 // Bounding box of the window corner in source coordinates: [lower, dim - 1 + upper] per axis (w, h).
 // Forward conv: lower = -pad, upper = pad - (filter - 1) (cutlass/conv/collective/detail.hpp
@@ -2100,6 +2458,16 @@ static int get_map_2d_plain(CUtensorMap* out, const float* base, int rows, int c
     auto it = g_maps.find(key);
     if (it != g_maps.end()) { *out = it->second; return I2V_OK; }
     if (int r = make_map_2d_plain(out, base, (uint64_t)rows, (uint64_t)cols, (uint32_t)box_rows, (uint32_t)box_cols)) return r;
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps.emplace(key, *out);
+    return I2V_OK;
+}
+static int get_map_u8_rows64(CUtensorMap* out, const uint8_t* base, int rows, int box_rows) {
+    MapKey key{base, rows, box_rows, 0, 0, 0, 0, 0, 6};
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return I2V_OK; }
+    if (int r = make_map_u8_rows64(out, base, (uint64_t)rows, (uint32_t)box_rows)) return r;
     if (g_maps.size() > 4096) g_maps.clear();
     g_maps.emplace(key, *out);
     return I2V_OK;
@@ -2558,6 +2926,57 @@ extern "C" int i2v_conv_stem_dgrad_direct_f32(const i2v_conv_desc* d, const floa
     const int grid = a.units < sm_count() ? a.units : sm_count();
     stem_dgrad_direct_kernel<<<grid, SD_THREADS, smem, as_stream(stream)>>>(tmA, tmBhi, tmBlo, a);
     I2V_LAUNCH_CHECK("i2v_conv_stem_dgrad_direct_f32");
+    return I2V_OK;
+}
+
+// The same with the 3x3 / stride-2 / pad-1 max pooling's backward pass in front (stem_dgrad_pool_kernel): dy_pooled / argmax =
+// [N, P2, Q2, 64] gradient of the POOLED map and the argmax plane i2v_maxpool_fwd_flags_f32 wrote (mark_dead mode: the stem's
+// ReLU mask is folded into it).  Bit-identical to i2v_maxpool_bwd_f32 followed by i2v_conv_stem_dgrad_direct_f32; the gradient
+// of the stem activation (4x the pooled bytes) never exists.
+static size_t stem_dgrad_pool_smem(int Q2) {
+    return 1024 + 4 * SD_B_TILE + (size_t)SP_AST * 2 * TC_A_BYTES + (size_t)SP_PST * (4 * sp_gtile_bytes(Q2) + 2 * sp_atile_bytes(Q2)) +
+           3 * 2 * 6 * 42 * sizeof(float) + 384;
+}
+
+extern "C" int i2v_conv_stem_dgrad_pool_supported(const i2v_conv_desc* d, int P2, int Q2) {
+    if (!i2v_conv_stem_dgrad_direct_supported(d)) return 0;
+    if (P2 != (d->P - 1) / 2 + 1 || Q2 != (d->Q - 1) / 2 + 1) return 0;          // 3x3 / stride 2 / pad 1, floor mode
+    int dev = 0, optin = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    return stem_dgrad_pool_smem(Q2) <= (size_t)optin;
+}
+
+extern "C" int i2v_conv_stem_dgrad_pool_f32(const i2v_conv_desc* d, int P2, int Q2, const float* dy_pooled, const uint8_t* argmax,
+                                            const float* wd_hi, const float* wd_lo, float* dx, i2v_stream_t stream) {
+    I2V_REQUIRE(d && dy_pooled && argmax && wd_hi && wd_lo && dx, "null pointer");
+    I2V_REQUIRE(i2v_conv_stem_dgrad_pool_supported(d, P2, Q2), "shape not supported by the pooled first-layer data gradient");
+    I2V_REQUIRE(((reinterpret_cast<uintptr_t>(dy_pooled) | reinterpret_cast<uintptr_t>(argmax) | reinterpret_cast<uintptr_t>(wd_hi) |
+                  reinterpret_cast<uintptr_t>(wd_lo) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0, "all tensors must be 16-byte aligned");
+    if (d->N == 0) return I2V_OK;
+    if (int r = resolve_driver()) return r;
+    const int64_t M2 = (int64_t)d->N * P2 * Q2;
+    I2V_REQUIRE(M2 < (int64_t)0x7fffffff, "too many pixels for one launch");
+    CUtensorMap tmG, tmAm, tmBhi, tmBlo;
+    if (int r = get_map_2d(&tmG, dy_pooled, (int)M2, 64, Q2)) return r;
+    if (int r = get_map_u8_rows64(&tmAm, argmax, (int)M2, Q2)) return r;
+    if (int r = get_map_2d(&tmBhi, wd_hi, SD_NZ, 64, SD_NZ)) return r;
+    if (int r = get_map_2d(&tmBlo, wd_lo, SD_NZ, 64, SD_NZ)) return r;
+    StemDirectArgs a{};
+    a.dx = dx; a.N = d->N; a.H = d->H; a.W = d->W; a.P = d->P; a.Q = d->Q; a.P2 = P2; a.Q2 = Q2;
+    a.dbg = getenv("I2V_STEM_DBG") ? atoi(getenv("I2V_STEM_DBG")) : 0;          // timing experiments; re-read per call
+    a.strips_per_image = d->H >= 32 ? 2 : 1;
+    a.units = d->N * a.strips_per_image;
+    const size_t smem = stem_dgrad_pool_smem(Q2);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(stem_dgrad_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "i2v_conv_stem_dgrad_pool_f32 (shared memory)");
+        smem_set = smem;
+    }
+    const int grid = a.units < sm_count() ? a.units : sm_count();
+    stem_dgrad_pool_kernel<<<grid, SD_THREADS, smem, as_stream(stream)>>>(tmG, tmAm, tmBhi, tmBlo, a);
+    I2V_LAUNCH_CHECK("i2v_conv_stem_dgrad_pool_f32");
     return I2V_OK;
 }
 

@@ -126,6 +126,7 @@ class DenseNetEngine(NativeEngine):
         self.use_stem_tc = os.environ.get("I2V_NATIVE_STEM_TC", "1") != "0"
         self._zbuf = None
         self.stem_dgrad_direct = os.environ.get("I2V_STEM_DGRAD_DIRECT", "1") != "0"
+        self.stem_dgrad_pool = os.environ.get("I2V_STEM_DGRAD_POOL", "1") != "0"
         self.stem_fwd_rows = os.environ.get("I2V_STEM_FWD_ROWS", "1") != "0"
         self.stem_direct = False
         self._xpbuf = None
@@ -277,8 +278,16 @@ class DenseNetEngine(NativeEngine):
                 self._conv_dgrad(l.conv1, P["d_" + l.name + ".conv1"], g_u, None, P[l.name + ".t"], g_t)
                 capi.copy_channels(g_t, gcat, 0, 0, l.cin, accumulate=True)
         capi.copy_channels(G[1], P["g_pool"], 0, 0, self.stem.cout)
-        capi.maxpool_bwd(P["g_pool"], P["argmax"], None, P["g_stem"], self.pool.k, self.pool.stride, self.pool.pad)
-        self._conv_dgrad(self.stem, P["d_stem"], P["g_stem"], None, None, gimg)
+        pool = self.pool
+        if (self.stem_dgrad_pool and self.stem_dgrad_direct and self.use_tc and self.use_stem_tc and self.tf32x3
+                and (pool.k, pool.stride, pool.pad) == (3, 2, 1) and not pool.ceil and self.stem.cout == 64
+                and getattr(self.stem, "tc_stem_dgrad_direct", None) is not None
+                and capi.conv_stem_dgrad_pool_supported(P["d_stem"], P["g_pool"].shape[1], P["g_pool"].shape[2])):
+            # pooling backward inside the first layer's data-gradient kernel: g_stem (4x the pooled bytes) is never written
+            self._conv_dgrad(self.stem, P["d_stem"], None, None, None, gimg, pooled=(P["g_pool"], P["argmax"]))
+        else:
+            capi.maxpool_bwd(P["g_pool"], P["argmax"], None, P["g_stem"], pool.k, pool.stride, pool.pad)
+            self._conv_dgrad(self.stem, P["d_stem"], P["g_stem"], None, None, gimg)
         self._last = None
         return gimg
 

@@ -315,6 +315,9 @@ class NativeEngine:
         self._zbuf = None
         # first-layer data gradient without the Z^T scratch (i2v_conv_stem_dgrad_direct_f32); $I2V_STEM_DGRAD_DIRECT=0: GEMM + col2im
         self.stem_dgrad_direct = os.environ.get("I2V_STEM_DGRAD_DIRECT", "1") != "0"
+        # max-pool backward fused into that kernel (i2v_conv_stem_dgrad_pool_f32): the stem activation's gradient never reaches
+        # HBM; $I2V_STEM_DGRAD_POOL=0: i2v_maxpool_bwd_f32 + i2v_conv_stem_dgrad_direct_f32
+        self.stem_dgrad_pool = os.environ.get("I2V_STEM_DGRAD_POOL", "1") != "0"
         # first-layer forward without the im2col patch matrix, one output row per tile (i2v_conv_stem_fwd_rows_f32); =0: im2col + GEMM
         self.stem_fwd_rows = os.environ.get("I2V_STEM_FWD_ROWS", "1") != "0"
         # EXPERIMENTAL: first-layer forward without the im2col patch matrix (i2v_conv_stem_fwd_direct_f32)
@@ -421,8 +424,30 @@ class NativeEngine:
         else:
             capi.conv_fwd_simt(d, x, op.b_fwd, op.bias, residual, y, relu=op.relu, x_nchw=op.x_nchw)
 
-    def _conv_dgrad(self, op, d, dy, addend, mask_src, dx, mask_bits=None):
-        if (op.x_nchw and addend is None and mask_src is None and self.use_tc and self.use_stem_tc and self.tf32x3
+    def _stem_pool_fusable(self, pool, plan):
+        """True when `pool` (a max pooling whose gradient is about to be taken) and the convolution that produced its input
+        can run as ONE kernel (i2v_conv_stem_dgrad_pool_f32): 3x3 / stride 2 / pad 1 over the ReLU output of a 7x7 / stride-2
+        first layer that nothing else consumes."""
+        if not (self.stem_dgrad_pool and self.stem_dgrad_direct and self.use_tc and self.use_stem_tc and self.tf32x3):
+            return False
+        if (pool.k, pool.stride, pool.pad) != (3, 2, 1) or pool.ceil or pool.x not in self.relu_typed or pool.x in self.hook_bufs:
+            return False
+        prod = [o for o in self.ops if o.kind == "conv" and o.y == pool.x]
+        users = [o for o in self.ops if (o.kind == "conv" and (o.x == pool.x or o.residual == pool.x))
+                 or (o.kind == "pool" and o.x == pool.x) or (o.kind not in ("conv", "pool") and pool.x in o.xs)]
+        if len(prod) != 1 or users != [pool]:
+            return False
+        conv = prod[0]
+        if not (conv.x_nchw and conv.residual is None and getattr(conv, "tc_stem_dgrad_direct", None) is not None):
+            return False
+        n, P2, Q2, c = plan["acts"][pool.y].shape
+        return c == 64 and capi.conv_stem_dgrad_pool_supported(plan["descs"][conv.name], P2, Q2)
+
+    def _conv_dgrad(self, op, d, dy, addend, mask_src, dx, mask_bits=None, pooled=None):
+        if pooled is not None:
+            hi, lo, _ = op.tc_stem_dgrad_direct
+            capi.conv_stem_dgrad_pool(d, pooled[0], pooled[1], hi, lo, dx)
+        elif (op.x_nchw and addend is None and mask_src is None and self.use_tc and self.use_stem_tc and self.tf32x3
                 and getattr(op, "tc_stem_dgrad_direct", None) is not None and self.stem_dgrad_direct
                 and capi.conv_stem_dgrad_direct_supported(d)):
             hi, lo, _ = op.tc_stem_dgrad_direct
@@ -539,6 +564,7 @@ class NativeEngine:
             G[b] = g.view_as(acts[b])
             ready.add(b)
         pending = {}          # buffer -> gradient tensor of an identity (residual) contribution not yet merged
+        pooled = {}           # buffer -> (gradient of its pooled map, argmax plane): pooling backward deferred to the producer's dgrad
         last = self.hook_bufs[-1]
         started = False
         for op in reversed(self.ops):
@@ -570,7 +596,8 @@ class NativeEngine:
                         raise RuntimeError("internal: two addends for %s" % op.x)
                 elif op.x in pending:
                     addend = pending.pop(op.x)
-                self._conv_dgrad(op, plan["descs"][op.name], gy, addend, mask, dx, plan["bits"].get(op.x))
+                self._conv_dgrad(op, plan["descs"][op.name], gy, addend, mask, dx, plan["bits"].get(op.x),
+                                 pooled=pooled.pop(op.y, None))
                 ready.add(op.x)
             elif op.kind == "pool":
                 # ReLU-backward mask of the pooled tensor's producer: 1[x[argmax] > 0] = 1[y > 0] was folded into the argmax
@@ -578,6 +605,10 @@ class NativeEngine:
                 # bytes, is never touched in the backward pass).
                 if op.x in pending:
                     raise NotImplementedError("pooling input that is also a residual source")
+                if op.x not in ready and self._stem_pool_fusable(op, plan):
+                    pooled[op.x] = (gy, plan["argmax"][op.y])    # the first layer's data-gradient kernel does the pooling too
+                    ready.add(op.x)
+                    continue
                 capi.maxpool_bwd(gy, plan["argmax"][op.y], None, G[op.x], op.k, op.stride, op.pad,
                                  accumulate=op.x in ready)       # hooked input: K1 wrote its gradient first
                 ready.add(op.x)

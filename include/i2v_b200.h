@@ -307,6 +307,15 @@ int     i2v_conv_stem_fwd_direct_f32(const i2v_conv_desc* d, const float* x, con
 int i2v_conv_stem_dgrad_direct_supported(const i2v_conv_desc* d);
 int i2v_conv_stem_dgrad_direct_f32(const i2v_conv_desc* d, const float* dy, const float* wd_hi, const float* wd_lo, float* dx,
                                    i2v_stream_t stream);
+/* The same with ResNet's / DenseNet's 3x3 / stride-2 / pad-1 max pooling (floor mode) fused in front: dy_pooled and argmax are
+ * the [N, P2, Q2, 64] gradient of the POOLED map and the argmax plane i2v_maxpool_fwd_flags_f32 wrote (mark_dead mode, so the
+ * stem's ReLU-backward mask is already in it).  The rows of the stem activation's gradient are rebuilt on chip from the one or
+ * two pooled rows that cover them, in the window order of i2v_maxpool_bwd_f32: bit-identical to that call followed by
+ * i2v_conv_stem_dgrad_direct_f32, without the 4x larger intermediate ever reaching HBM (image_attacks.py:352 for
+ * model.maxpool + model.conv1).                                                                                    */
+int i2v_conv_stem_dgrad_pool_supported(const i2v_conv_desc* d, int P2, int Q2);
+int i2v_conv_stem_dgrad_pool_f32(const i2v_conv_desc* d, int P2, int Q2, const float* dy_pooled, const uint8_t* argmax,
+                                 const float* wd_hi, const float* wd_lo, float* dx, i2v_stream_t stream);
 /* First-layer forward WITHOUT the patch matrix (7x7 / stride 2 / pad 3, Cout = 64, Q <= 128, W % 4 == 0; image_attacks.py:334
  * for that layer): one output row per tile, the 7 x 3 input rows staged by TMA (zero filled outside the image), the
  * 128 x 160 patch tile assembled on chip, weights resident; bias + ReLU in the epilogue.  wk_hi / wk_lo as for

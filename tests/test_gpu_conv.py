@@ -601,6 +601,42 @@ def test_stem_dgrad_direct(H, W, n):
     assert err <= (2e-5 + Cout * 2.0 ** -24), err
 
 
+@pytest.mark.parametrize("H,W,n", [(224, 224, 5), (112, 112, 3), (64, 64, 3), (32, 32, 2), (16, 16, 3), (63, 61, 2), (60, 58, 2),
+                                   (224, 200, 1), (8, 8, 1)])
+def test_stem_dgrad_pool_fused(H, W, n):
+    """Max-pool backward (3x3 / stride 2 / pad 1, dead windows marked by the forward pass) fused into the first-layer data
+    gradient: BIT-identical to i2v_maxpool_bwd_f32 followed by i2v_conv_stem_dgrad_direct_f32 — the pooling's routing is an
+    exact selection and the window order is the same — on even / odd stem and pooled sizes, with ties and dead windows
+    (the activation is a ReLU output with ~half zeros), twice in a row."""
+    from i2v_b200.engine_native import _split_tf32
+    g = torch.Generator().manual_seed(11)
+    Cout, k, s, p = 64, 7, 2, 3
+    w = torch.randn(Cout, 3, k, k, generator=g) / (3 * k * k) ** 0.5
+    P, Q = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    P2, Q2 = (P - 1) // 2 + 1, (Q - 1) // 2 + 1
+    d = capi.ConvDesc(n, H, W, 3, Cout, k, k, s, p, P, Q)
+    if not capi.conv_stem_dgrad_pool_supported(d, P2, Q2):
+        pytest.skip("pooled rows do not fit in shared memory at this width")
+    act = torch.relu(torch.randn(n, P, Q, Cout, generator=g)).to(DEV)          # the stem's ReLU output, NHWC
+    act[:, : P // 2, : Q // 3] = torch.round(act[:, : P // 2, : Q // 3])      # ties inside windows
+    pooled = torch.empty(n, P2, Q2, Cout, device=DEV)
+    am = torch.empty(n, P2, Q2, Cout, device=DEV, dtype=torch.uint8)
+    capi.maxpool_fwd(act, pooled, am, 3, 2, 1, mark_dead=True)
+    assert int((am == 255).sum()) > 0 or min(P, Q) > 8
+    gp = torch.randn(n, P2, Q2, Cout, generator=g).to(DEV)
+    w_stem = w.permute(1, 2, 3, 0).reshape(147, Cout).contiguous().to(DEV)
+    hi, lo, _ = _split_tf32(capi.stem_direct_dgrad_weights(w_stem))
+    gact = torch.full((n, P, Q, Cout), float("nan"), device=DEV)
+    capi.maxpool_bwd(gp, am, None, gact, 3, 2, 1)
+    ref = torch.full((n, 3, H, W), float("nan"), device=DEV)
+    capi.conv_stem_dgrad_direct(d, gact, hi, lo, ref)
+    for _ in range(2):
+        dx = torch.full((n, 3, H, W), float("nan"), device=DEV)
+        capi.conv_stem_dgrad_pool(d, gp, am, hi, lo, dx)
+        assert torch.isfinite(dx).all()
+        assert torch.equal(dx, ref), float((dx - ref).abs().max())
+
+
 @pytest.mark.parametrize("H,W,k,s,p,n", [(224, 224, 7, 2, 3, 7), (64, 64, 7, 2, 3, 3), (64, 64, 11, 4, 2, 1), (32, 32, 3, 1, 1, 2),
                                          (63, 63, 3, 2, 0, 4)])
 @pytest.mark.parametrize("x3", [True, False])
