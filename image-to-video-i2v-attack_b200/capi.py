@@ -76,6 +76,7 @@ SIGNATURES = {
     "i2v_conv_tc_f32": ([_c_p, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_tc_bits_f32": ([_c_p, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_tc_dgrad_class_f32": ([_c_p, _c_int, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p], _c_int),
+    "i2v_conv_tc_dual_f32": ([_c_p, _c_p, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_maxpool_fwd_f32": ([_c_p, _c_p, _c_p] + [_c_int] * 9 + [_c_p], _c_int),
     "i2v_maxpool_fwd_flags_f32": ([_c_p, _c_p, _c_p] + [_c_int] * 10 + [_c_p], _c_int),
     "i2v_maxpool_bwd_f32": ([_c_p, _c_p, _c_p, _c_p] + [_c_int] * 10 + [_c_p], _c_int),
@@ -574,6 +575,27 @@ def conv_tc(desc, dgrad, src, w_hi, w_lo, bias, residual, mask_src, dst, relu=Fa
                                            _dev(residual), _dev(mask_src), _dev(mask_bits, torch.int32), _dev(dst),
                                            EPI_RELU if relu else 0, _stream()),
                "i2v_conv_tc_f32")
+
+
+def conv_tc_dual(desc, x, t, w_hi, w_lo, bias, dst, relu=True, mask_bits=None):
+    """dst = act(conv1x1_stride_s(x) + conv1x1(t) + bias) as ONE GEMM over K = Cin followed by C2 (see include/i2v_b200.h):
+    desc describes the first convolution (over x), t is [N, P, Q, C2], w_* = [Cout, Cin + C2] K-major."""
+    C2 = t.shape[-1]
+    assert t.shape[:3] == dst.shape[:3] and w_hi.shape == (desc.Cout, desc.Cin + C2)
+    m = desc.N * desc.P * desc.Q
+    # algorithmic bytes: the pixels of x the strided window touches, t, and the output (+ its activity bits)
+    nb = 4 * m * (desc.Cin + C2 + desc.Cout)
+    if mask_bits is not None:
+        nb += 4 * mask_bits.numel()
+    fl = 2.0 * m * desc.Cout * (desc.Cin + C2)
+    detail = None
+    if PROFILE_EVENTS is not None:
+        detail = "fwd %dx%d %d+%d->%d k1s%d dual%s" % (desc.H, desc.W, desc.Cin, C2, desc.Cout, desc.stride,
+                                                     " +bits" if mask_bits is not None else "")
+    with _Timed("i2v_conv_tc_f32", nb, fl, detail):
+        _check(load().i2v_conv_tc_dual_f32(ctypes.addressof(desc), _dev(x), int(C2), _dev(t), _dev(w_hi), _dev(w_lo), _dev(bias),
+                                           _dev(mask_bits, torch.int32), _dev(dst), EPI_RELU if relu else 0, _stream()),
+               "i2v_conv_tc_dual_f32")
 
 
 def conv_tc_dgrad_class(desc, ph, pw, dy, w_hi, w_lo, addend, mask_src, dx):

@@ -67,7 +67,10 @@ struct TcArgs {
     int stride;              // im2col traversal stride of the window corner
     int lower_h, lower_w;    // window corner of (p,q) = (0,0) in source coordinates (= -pad for a forward conv)
     int taps_h, taps_w;      // K = (tap_h, tap_w, channel); TMA im2col offsets = (tap_w, tap_h)
-    int cblocks;             // C / 32
+    int cblocks;             // C / 32 (both sources together when a second one is attached)
+    int a2_cb0;              // > 0: k-steps cb >= a2_cb0 read their A tile from a SECOND, dense [M, C2] tensor through tmRes (1x1
+                             // taps only, no residual): two convolutions that are summed anyway — a bottleneck's downsample
+                             // branch and its last 1x1 — run as ONE GEMM over the concatenated K
     int relu;
     // output row of GEMM row (img,p,q): ((img*out_H + p*out_s + out_h0)*out_W + q*out_s + out_w0); identity when out_s == 0
     int out_s, out_h0, out_w0, out_H, out_W;
@@ -546,7 +549,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     const int p = rem / args.Q, q = rem - p * args.Q;
                     base_h = p * args.stride + args.lower_h;
                     base_w = q * args.stride + args.lower_w;
-                } else if (args.prefetch_tiles > 0) {
+                } else if (args.prefetch_tiles > 0 && args.a2_cb0 == 0) {
                     // the first tiles' prefetches are issued up front, afterwards one tile per tile
                     for (int d = (tno == 0 ? 1 : args.prefetch_tiles); d <= args.prefetch_tiles; ++d) {
                         const int ptile = tile + d * (int)gridDim.x;
@@ -566,7 +569,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                             // rows per k-step — made every layer 5-15 % SLOWER: the four split warps are the tighter resource)
                             const bool no_b = (args.dbg & 8) != 0;          // timing experiment: the weight tiles are not loaded
                             mbar_arrive_expect_tx(&full_bar[st], TC_A_BYTES + (no_b ? 0u : L::B_BYTES * (X3 ? 2 : 1)));
-                            if (IM2COL) tma_load_im2col_4d(&tmA, &full_bar[st], stage_a(st), cb * TC_BK, base_w, base_h, img, (uint16_t)s, (uint16_t)r);
+                            if (args.a2_cb0 > 0 && cb >= args.a2_cb0) tma_load_2d(&tmRes, &full_bar[st], stage_a(st), (cb - args.a2_cb0) * TC_BK, (int)m0);
+                            else if (IM2COL) tma_load_im2col_4d(&tmA, &full_bar[st], stage_a(st), cb * TC_BK, base_w, base_h, img, (uint16_t)s, (uint16_t)r);
                             else if (args.stem4d) {
                                 // filter row r of a 16 x 8 pixel box: 32 floats (8 padded pixels x 4) per output pixel, rows of
                                 // parity r % 2 (tmA even / tmRes odd: the residual map is free, a first layer has none)
@@ -2644,6 +2648,7 @@ struct TcProblem {
     const uint32_t* mask_bits; uint32_t* bits_out;
     int out_transposed, store_cols;     // TMA epilogue: dst = [Cout][M]; only columns < store_cols are written (0 = all)
     int force_dual;                     // take the dual-issuer kernel whatever the tile length (first-layer dgrad GEMM)
+    const float* src2; int C2;          // second A source [M, C2] (K = taps x C followed by C2); see TcArgs::a2_cb0
 };
 
 static int tc_run(const TcProblem& pr, cudaStream_t st) {
@@ -2662,7 +2667,7 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
     static const bool persistent = !(getenv("I2V_TC_PERSISTENT") && atoi(getenv("I2V_TC_PERSISTENT")) == 0);
     int BN = (pr.Cout % 128 == 0 && (!x3 || persistent)) ? 128 : 64;
     if (const char* e = getenv("I2V_TC_BN")) { int v = atoi(e); if ((v == 64 || v == 128) && pr.Cout % v == 0) BN = v; }
-    const int Ktot = pr.taps_h * pr.taps_w * pr.C;
+    const int Ktot = pr.taps_h * pr.taps_w * pr.C + (pr.src2 ? pr.C2 : 0);
 
     // TMA epilogue (v3) whenever the output rows are dense and no f32 mask source is involved; the strided
     // data-gradient classes and callers that pass an f32 mask keep the register/LSU epilogue (v2)
@@ -2685,6 +2690,12 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
         else                   { if (int r = get_map_2d(&tmOut, pr.dst, (int)M, pr.Cout, TC_BM)) return r; }
         if (pr.residual) { if (int r = get_map_2d(&tmRes, pr.residual, (int)M, pr.Cout, TC_BM)) return r; }
     }
+    if (pr.src2) {
+        I2V_REQUIRE(persistent && epi_tma && pr.taps_h == 1 && pr.taps_w == 1 && !pr.residual && !pr.out_transposed && pr.C2 > 0 &&
+                    pr.C2 % 32 == 0 && (reinterpret_cast<uintptr_t>(pr.src2) & 15) == 0,
+                    "a second A source needs 1x1 taps, the TMA epilogue, no residual and C2 % 32 == 0");
+        if (int r = get_map_2d(&tmRes, pr.src2, (int)M, pr.C2, TC_BM)) return r;      // an A-operand map in the residual's seat
+    }
 
     TcArgs a{};
     a.bias = pr.bias; a.residual = pr.residual; a.mask_src = pr.mask_src; a.dst = pr.dst;
@@ -2696,6 +2707,7 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
     a.prefetch_tiles = prefetch_tiles > 0 ? (prefetch_tiles < 8 ? prefetch_tiles : 8) : 0;
     a.M = M; a.Cout = pr.Cout; a.P = pr.P; a.Q = pr.Q; a.stride = pr.stride; a.lower_h = pr.lower_h; a.lower_w = pr.lower_w;
     a.taps_h = pr.taps_h; a.taps_w = pr.taps_w; a.cblocks = pr.C / 32; a.relu = pr.relu;
+    if (pr.src2) { a.a2_cb0 = pr.C / 32; a.cblocks = (pr.C + pr.C2) / 32; }
     a.out_s = pr.out_s; a.out_h0 = pr.out_h0; a.out_w0 = pr.out_w0; a.out_H = pr.out_H; a.out_W = pr.out_W;
     a.trace = g_trace; a.trace_tiles = g_trace_tiles;
     static const int pair_dbg = getenv("I2V_TC_PAIR_DBG") ? atoi(getenv("I2V_TC_PAIR_DBG")) : 0;
@@ -2715,14 +2727,14 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
             // 2; 256->128 dgrad (K = 128) 357 vs 429 us at threshold 4 against 8).  $I2V_TC_ALO_MINKIT overrides.
             // $I2V_TC_ALO_TMEM=0 selects the single-issuer kernel everywhere, =2 the dual-issuer kernel everywhere
             static const int alo_env = getenv("I2V_TC_ALO_TMEM") ? atoi(getenv("I2V_TC_ALO_TMEM")) : 1;
-            const int kit = pr.taps_h * pr.taps_w * (pr.C / 32);
+            const int kit = pr.taps_h * pr.taps_w * (pr.C / 32) + (pr.src2 ? pr.C2 / 32 : 0);
             static const int alo_minkit = getenv("I2V_TC_ALO_MINKIT") ? atoi(getenv("I2V_TC_ALO_MINKIT")) : 4;
             const bool alo = x3 && alo_env != 0 && (BN == 64 || kit >= alo_minkit || alo_env == 2 || pr.force_dual);
             // CTA pairs (tcgen05.mma.cta_group::2, half of the weight rows per CTA): $I2V_TC_PAIR = minimum k-steps per tile
             // from which the pair kernel takes over (0 = never); needs at least two m-tiles
             const int pair_minkit = pair_min_ksteps();
             const bool pair_on = pair_minkit > 0 ? kit >= pair_minkit : (pair_minkit == -1 && pr.residual != nullptr && kit >= 4);
-            if (alo && pair_on && !pr.out_transposed && M > TC_BM) {
+            if (alo && pair_on && !pr.out_transposed && M > TC_BM && !pr.src2) {
                 CUtensorMap hBhi, hBlo;
                 if (int r = get_map_2d(&hBhi, pr.w_hi, pr.Cout, Ktot, BN / 2)) return r;
                 if (int r = get_map_2d(&hBlo, pr.w_lo, pr.Cout, Ktot, BN / 2)) return r;
@@ -2813,6 +2825,27 @@ extern "C" int i2v_conv_tc_bits_f32(const i2v_conv_desc* d, int dgrad, const flo
         pr.lower_h = pr.lower_w = -padp; pr.upper_h = padp - (d->R - 1); pr.upper_w = padp - (d->S - 1);
         pr.mask_bits = mask_bits;
     }
+    return tc_run(pr, as_stream(stream));
+}
+
+// Two 1x1 convolutions whose outputs are added — a bottleneck's downsample branch (d: 1x1, stride s, over x) and its last
+// convolution (1x1 / stride 1 over t [N,P,Q,C2]) — as ONE GEMM: K = Cin followed by C2, w_* = [Cout, Cin + C2] K-major (the two
+// folded weight matrices side by side), bias = the sum of the two.  The downsample output (4 bytes per output element written
+// and read back as the residual) never exists.  Forward only; bits_out as for i2v_conv_tc_bits_f32.
+extern "C" int i2v_conv_tc_dual_f32(const i2v_conv_desc* d, const float* x, int C2, const float* t, const float* w_hi,
+                                    const float* w_lo, const float* bias, uint32_t* bits_out, float* dst, int flags,
+                                    i2v_stream_t stream) {
+    I2V_REQUIRE(d && x && t && w_hi && dst, "null pointer");
+    I2V_REQUIRE(i2v_conv_tc_supported(d, 0) && d->R == 1 && d->S == 1 && d->pad == 0, "the first convolution must be a supported 1x1");
+    I2V_REQUIRE(C2 > 0 && C2 % 32 == 0, "C2 must be a positive multiple of 32");
+    if (d->N == 0) return I2V_OK;
+    TcProblem pr{};
+    pr.src = x; pr.N = d->N; pr.w_hi = w_hi; pr.w_lo = w_lo; pr.bias = bias; pr.dst = dst; pr.relu = (flags & I2V_EPI_RELU) ? 1 : 0;
+    pr.taps_h = pr.taps_w = 1;
+    pr.H = d->H; pr.W = d->W; pr.C = d->Cin; pr.P = d->P; pr.Q = d->Q; pr.Cout = d->Cout; pr.stride = d->stride;
+    pr.lower_h = pr.lower_w = 0; pr.upper_h = pr.upper_w = 0;
+    pr.bits_out = bits_out;
+    pr.src2 = t; pr.C2 = C2;
     return tc_run(pr, as_stream(stream));
 }
 

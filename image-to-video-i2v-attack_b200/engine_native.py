@@ -325,6 +325,27 @@ class NativeEngine:
         self._xpbuf = None
         self._cache = {}
         self.buffer_generation = 0
+        # A bottleneck's downsample branch and its last 1x1 convolution are summed anyway: run them as ONE GEMM over the
+        # concatenated K (i2v_conv_tc_dual_f32) — the downsample output is never written nor read back as a residual.
+        # $I2V_FUSE_DS=0: two launches.
+        self.fuse_ds = os.environ.get("I2V_FUSE_DS", "1") != "0"
+        self.dual = {}                       # name of the last convolution -> (downsample op, hi, lo, rna, bias)
+        for op in self.ops:
+            if op.kind != "conv" or op.residual is None or op.R != 1 or op.stride != 1 or op.pad != 0 or not op.relu:
+                continue
+            r = op.residual
+            prod = [o for o in self.ops if o.kind == "conv" and o.y == r]
+            users = [o for o in self.ops if (o.kind == "conv" and (o.x == r or o.residual == r)) or (o.kind == "pool" and o.x == r)
+                     or (o.kind not in ("conv", "pool") and r in o.xs)]
+            if len(prod) != 1 or users != [op] or r in self.hook_bufs or r in self.relu_typed:
+                continue
+            ds = prod[0]
+            if ds.relu or ds.residual is not None or ds.R != 1 or ds.pad != 0 or ds.x_nchw or ds.cout != op.cout \
+                    or ds.cin % 32 or op.cin % 32:
+                continue
+            self.dual[op.name] = (ds, torch.cat([ds.tc_fwd[0], op.tc_fwd[0]], 1).contiguous(),
+                                  torch.cat([ds.tc_fwd[1], op.tc_fwd[1]], 1).contiguous(),
+                                  torch.cat([ds.tc_fwd[2], op.tc_fwd[2]], 1).contiguous(), (ds.bias + op.bias).contiguous())
 
     @property
     def num_layers(self):
@@ -362,6 +383,7 @@ class NativeEngine:
             return plan
         dims = {"img": (h, w)}
         acts, grads, argmax, descs, bits = {}, {}, {}, {}, {}
+        fused_ds = {}                        # downsample op name -> name of the convolution that absorbs it in this plan
         for op in self.ops:
             if op.kind == "conv":
                 ih, iw = dims[op.x]
@@ -369,6 +391,10 @@ class NativeEngine:
                 dims[op.y] = (oh, ow)
                 d = capi.ConvDesc(n, ih, iw, op.cin, op.cout, op.R, op.R, op.stride, op.pad, oh, ow)
                 descs[op.name] = d
+                if op.name in self.dual and self.fuse_ds and self.use_tc:
+                    ds = self.dual[op.name][0]
+                    if capi.conv_tc_supported(d, 0) and capi.conv_tc_supported(descs[ds.name], 0) and dims[ds.y] == (oh, ow):
+                        fused_ds[ds.name] = op.name
                 # ReLU outputs produced by the tensor-core kernel also leave their activity as BITS ([C/32, M] words):
                 # the data gradients that need 1[activation > 0] then read 1/32 of the bytes (and run the TMA epilogue)
                 if op.relu and self.use_bits and self.use_tc and not op.x_nchw and capi.conv_tc_supported(d, 0):
@@ -382,10 +408,13 @@ class NativeEngine:
             acts[op.y] = torch.empty(n, oh, ow, self.chans[op.y], device=device, dtype=torch.float32)
             if op.kind == "pool":
                 argmax[op.y] = torch.empty(n, oh, ow, self.chans[op.y], device=device, dtype=torch.uint8)
+        for op in self.ops:                  # an absorbed downsample output is never materialised (nor is its gradient: the
+            if op.kind == "conv" and op.name in fused_ds:        # block output's gradient IS the shortcut's)
+                del acts[op.y]
         for name, t in acts.items():
             if name not in self.hook_bufs:
                 grads[name] = torch.empty_like(t)
-        plan = dict(dims=dims, acts=acts, grads=grads, argmax=argmax, descs=descs, bits=bits,
+        plan = dict(dims=dims, acts=acts, grads=grads, argmax=argmax, descs=descs, bits=bits, fused_ds=fused_ds,
                     gimg=torch.empty(n, 3, h, w, device=device, dtype=torch.float32))
         if len(self._cache) > 4:
             self._cache.clear()
@@ -492,11 +521,20 @@ class NativeEngine:
             raise ValueError("expected a contiguous [n,3,H,W] image batch")
         plan = self._plan(n, h, w, img.device)
         acts = plan["acts"]
+        fused_ds = plan["fused_ds"]
         for op in self.ops:
             if op.kind == "conv":
+                if op.name in fused_ds:
+                    continue                                       # runs inside the block's last convolution
                 x = img if op.x == "img" else acts[op.x]
+                bits_out = plan["bits"].get(op.y) if need_grad else None
+                if op.name in self.dual and self.dual[op.name][0].name in fused_ds:
+                    ds, hi, lo, rna, bias = self.dual[op.name]
+                    capi.conv_tc_dual(plan["descs"][ds.name], acts[ds.x], acts[op.x], hi if self.tf32x3 else rna,
+                                      lo if self.tf32x3 else None, bias, acts[op.y], relu=True, mask_bits=bits_out)
+                    continue
                 self._conv_fwd(op, plan["descs"][op.name], x, acts[op.y], acts[op.residual] if op.residual else None,
-                               plan["bits"].get(op.y) if need_grad else None)
+                               bits_out)
             elif op.kind == "pool":
                 # a ReLU output is pooled: windows with nothing > 0 are marked "no winner", which IS the ReLU-backward mask
                 capi.maxpool_fwd(acts[op.x], acts[op.y], plan["argmax"][op.y], op.k, op.stride, op.pad,

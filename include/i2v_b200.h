@@ -326,6 +326,15 @@ int i2v_conv_stem_fwd_rows_f32(const i2v_conv_desc* d, const float* x, const flo
 int i2v_conv_stem_fwd_tc_f32(const i2v_conv_desc* d, const float* x, const float* wk_hi, const float* wk_lo,
                              const float* bias, float* col_scratch, float* y, int flags, i2v_stream_t stream);
 
+/* Two 1x1 convolutions whose outputs are added — a Bottleneck's downsample branch (d: 1x1 / stride s / pad 0 over x) and its
+ * last convolution (1x1 / stride 1 over t [N,P,Q,C2]; torchvision resnet.py Bottleneck.forward `out += identity`, run by
+ * image_attacks.py:334) — as ONE implicit GEMM over K = Cin followed by C2: the k-steps of the second range read their
+ * activation tile from t through a second tensor map.  w_hi / w_lo = [Cout, Cin + C2] K-major (the two BN-folded weight
+ * matrices side by side, TF32 hi / lo split; w_lo = NULL: plain TF32), bias = the sum of the two folded biases.  The
+ * downsample output (written once and read back as the residual otherwise) never exists.  Forward only; bits_out as the
+ * forward mask_bits of i2v_conv_tc_bits_f32.                                                                        */
+int i2v_conv_tc_dual_f32(const i2v_conv_desc* d, const float* x, int C2, const float* t, const float* w_hi, const float* w_lo,
+                         const float* bias, uint32_t* bits_out, float* dst, int flags, i2v_stream_t stream);
 /* Strided data gradient on the tensor cores, one stride-parity class (ph, pw) per call: image rows
  * h = stride*i + ph receive only the taps r = r0 + stride*a, r0 = (ph + pad) mod stride, from dy row
  * i + (ph + pad - r0)/stride - a — a dense stride-1 implicit GEMM over dy whose output rows are scattered

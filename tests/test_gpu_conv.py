@@ -418,6 +418,77 @@ def test_conv_tc_bit_masks(shape, x3):
         assert (got - want).abs().max() <= 2e-6 * want.abs().max()
 
 
+@pytest.mark.parametrize("shape", [(2, 56, 56, 64, 1, 64, 256), (3, 56, 56, 256, 2, 128, 512), (1, 15, 13, 64, 2, 32, 64),
+                                   (5, 9, 9, 32, 1, 96, 128), (2, 28, 28, 512, 2, 256, 1024)])
+@pytest.mark.parametrize("x3", [True, False])
+def test_conv_tc_dual_source(shape, x3):
+    """A bottleneck's downsample branch (1x1 / stride s over x) and its last 1x1 (over t) as ONE GEMM over the concatenated
+    K (second A source through its own tensor map): against float64 with the error model of the single-source launches,
+    against the two-launch path (ds, then conv3 + residual) to rounding, activity bits = 1[y > 0] exactly; ResNet-50's
+    layer1.0 / layer2.0 / layer3.0 shapes, odd sizes under stride 2, ragged last tiles."""
+    N, H, W, C1, s, C2, Cout = shape
+    g = torch.Generator().manual_seed(21)
+    P, Q = (H - 1) // s + 1, (W - 1) // s + 1
+    x = torch.randn(N, C1, H, W, generator=g)
+    t = torch.randn(N, C2, P, Q, generator=g)
+    w1 = torch.randn(Cout, C1, 1, 1, generator=g) / C1 ** 0.5
+    w2 = torch.randn(Cout, C2, 1, 1, generator=g) / C2 ** 0.5
+    sc1, sc2 = torch.rand(Cout, generator=g) + 0.5, torch.rand(Cout, generator=g) + 0.5
+    b1, b2 = torch.randn(Cout, generator=g) * 0.1, torch.randn(Cout, generator=g) * 0.1
+    d1 = capi.ConvDesc(N, H, W, C1, Cout, 1, 1, s, 0, P, Q)
+    d2 = capi.ConvDesc(N, P, Q, C2, Cout, 1, 1, 1, 0, P, Q)
+    _, (h1, l1, r1), _ = _tc_operands(w1, sc1)
+    _, (h2, l2, r2), _ = _tc_operands(w2, sc2)
+    hi, lo, rn = (torch.cat([a, b], 1).contiguous() for a, b in ((h1, h2), (l1, l2), (r1, r2)))
+    lay = lambda v: v.permute(0, 2, 3, 1).contiguous().to(DEV)
+    xd, td = lay(x), lay(t)
+    bias = (b1 + b2).to(DEV)
+    M = N * P * Q
+    y = torch.full((N, P, Q, Cout), float("nan"), device=DEV)
+    bits = torch.zeros(Cout // 32, M, dtype=torch.int32, device=DEV)
+    capi.conv_tc_dual(d1, xd, td, hi if x3 else rn, lo if x3 else None, bias, y, relu=True, mask_bits=bits)
+    assert torch.isfinite(y).all()
+    assert torch.equal(bits, _pack_bits(y > 0))
+    y2 = torch.full_like(y, float("nan"))
+    capi.conv_tc_dual(d1, xd, td, hi if x3 else rn, lo if x3 else None, bias, y2, relu=True)
+    assert torch.equal(y, y2)
+    ref64 = torch.relu(_ref_conv(x, w1, sc1, b1, s, 0, None, False, torch.float64) + _ref_conv(t, w2, sc2, b2, 1, 0, None, False, torch.float64))
+    got = y.permute(0, 3, 1, 2).cpu().double()
+    err = (got - ref64).abs().max() / ref64.abs().max()
+    assert err <= ((1e-5 + (C1 + C2) * 2.0 ** -24) if x3 else 4e-3), err
+    # the two-launch path it replaces
+    sc = torch.full((N, P, Q, Cout), float("nan"), device=DEV)
+    capi.conv_tc(d1, 0, xd, h1 if x3 else r1, l1 if x3 else None, b1.to(DEV), None, None, sc)
+    y3 = torch.full_like(y, float("nan"))
+    capi.conv_tc(d2, 0, td, h2 if x3 else r2, l2 if x3 else None, b2.to(DEV), sc, None, y3, relu=True)
+    assert (y - y3).abs().max() <= (4e-6 if x3 else 4e-3) * y3.abs().max()
+
+
+def test_engine_fused_downsample_matches_two_launches(monkeypatch):
+    """NativeEngine with the downsample branches absorbed into the blocks' last convolutions (default) against the same
+    engine with $I2V_FUSE_DS=0: features and input gradient agree to FP32 rounding; the absorbed buffers are not allocated."""
+    from i2v_b200 import backbones
+    from i2v_b200.engine_native import NativeEngine
+    g = torch.Generator().manual_seed(2)
+    img = torch.randn(3, 3, 64, 64, generator=g).to(DEV)
+    outs = []
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("I2V_FUSE_DS", fuse)
+        model = backbones.get_model("resnet50")
+        eng = NativeEngine(model, "resnet50", 2)
+        feats = eng.features(img, need_grad=True)
+        plan = eng._last
+        assert len(plan["fused_ds"]) == (2 if fuse == "1" else 0)
+        assert all(("l%d.0.sc" % li in plan["acts"]) == (fuse == "0") for li in (1, 2))
+        f0 = feats[0].clone()
+        gin = eng.input_grad([torch.ones_like(f0) / f0.numel()]).clone()
+        outs.append((f0, gin))
+    (fa, ga), (fb, gb) = outs
+    assert (fa - fb).abs().max() <= 1e-5 * fb.abs().max()
+    assert torch.equal(fa > 0, fb > 0) or ((fa > 0) != (fb > 0)).float().mean() < 1e-4
+    assert (ga - gb).abs().max() <= 1e-3 * gb.abs().max()
+
+
 @pytest.mark.parametrize("H,W,k,s,p", [(224, 224, 7, 2, 3), (64, 64, 7, 2, 3), (64, 64, 11, 4, 2), (32, 32, 3, 1, 1),
                                        (64, 64, 3, 2, 0), (37, 53, 7, 2, 3), (31, 45, 3, 2, 0), (50, 70, 11, 4, 2)])
 def test_stem_fwd_and_dgrad(H, W, k, s, p):
