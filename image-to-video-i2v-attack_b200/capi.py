@@ -76,6 +76,7 @@ SIGNATURES = {
     "i2v_conv_tc_f32": ([_c_p, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_tc_bits_f32": ([_c_p, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_tc_dgrad_class_f32": ([_c_p, _c_int, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p], _c_int),
+    "i2v_conv_tc_dgrad_class_bits_f32": ([_c_p, _c_int, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p], _c_int),
     "i2v_conv_tc_dual_f32": ([_c_p, _c_p, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_maxpool_fwd_f32": ([_c_p, _c_p, _c_p] + [_c_int] * 9 + [_c_p], _c_int),
     "i2v_maxpool_fwd_flags_f32": ([_c_p, _c_p, _c_p] + [_c_int] * 10 + [_c_p], _c_int),
@@ -598,16 +599,20 @@ def conv_tc_dual(desc, x, t, w_hi, w_lo, bias, dst, relu=True, mask_bits=None):
                "i2v_conv_tc_dual_f32")
 
 
-def conv_tc_dgrad_class(desc, ph, pw, dy, w_hi, w_lo, addend, mask_src, dx):
-    """One stride-parity class of a strided data gradient on the tensor cores (see include/i2v_b200.h)."""
+def conv_tc_dgrad_class(desc, ph, pw, dy, w_hi, w_lo, addend, mask_src, dx, mask_bits=None):
+    """One stride-parity class of a strided data gradient on the tensor cores (see include/i2v_b200.h); mask_bits (int32
+    [Cin/32, N*H*W]) instead of mask_src selects the TMA epilogue."""
     # one stride-parity class: dy once, 1/stride^2 of dx (+ mask, + addend) and of the taps
     st2 = desc.stride * desc.stride
     nb, fl = _conv_cost(desc)
     nout = desc.N * desc.P * desc.Q * desc.Cout
     nb = 4 * nout + 4 * (dx.numel() // st2) * (1 + (addend is not None) + (mask_src is not None))
+    if mask_bits is not None:
+        nb += 4 * (mask_bits.numel() // st2)
     with _Timed("i2v_conv_tc_dgrad_class_f32", nb, fl / st2):
-        _check(load().i2v_conv_tc_dgrad_class_f32(ctypes.addressof(desc), ph, pw, _dev(dy), _dev(w_hi), _dev(w_lo),
-                                                  _dev(addend), _dev(mask_src), _dev(dx), _stream()),
+        _check(load().i2v_conv_tc_dgrad_class_bits_f32(ctypes.addressof(desc), ph, pw, _dev(dy), _dev(w_hi), _dev(w_lo),
+                                                       _dev(addend), _dev(mask_src), _dev(mask_bits, torch.int32), _dev(dx),
+                                                       _stream()),
                "i2v_conv_tc_dgrad_class_f32")
 
 

@@ -74,6 +74,7 @@ struct TcArgs {
     int relu;
     // output row of GEMM row (img,p,q): ((img*out_H + p*out_s + out_h0)*out_W + q*out_s + out_w0); identity when out_s == 0
     int out_s, out_h0, out_w0, out_H, out_W;
+    int64_t M_out;           // rows of dst (= M unless out_s != 0): plane pitch of mask_bits
     // pipeline trace (debug, i2v_conv_tc_set_trace): CTA 0 stamps clock64() at 8 points of each of its first
     // trace_tiles tiles — [tile][0] producer starts the tile, [1] producer issued its last load, [2] MMA warp owns
     // an accumulator, [3] first operands landed (and split), [4] last MMA issued, [5] epilogue sees the
@@ -139,6 +140,13 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                  :: "l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// im2col-mode STORE (UTMASTG.4D.IM2COL): the 128 pixel rows of the shared-memory tile go to the pixels the map's traversal visits
+// from (w, h, n) on — every elementStride-th pixel of the bounding box, wrapping over rows and images: the scatter of a strided
+// data-gradient class
+__device__ __forceinline__ void tma_store_im2col_4d(const CUtensorMap* map, const void* src, int c, int w, int h, int n) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.im2col_no_offs.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 :: "l"(map), "r"(smem_u32(src)), "r"(c), "r"(w), "r"(h), "r"(n) : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -671,12 +679,25 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 col = n_tile * BN + (g + 2 * (int)(k % SUBS)) * 32;
                 row = m_tile * TC_BM;
             };
+            // strided data-gradient class: tile row m = (img, i, j) of the class grid lives at pixel (i out_s, j out_s) of the
+            // class VIEW of dst (base shifted to the class's first pixel); im2col-mode TMA walks the view with that stride
+            auto view_coords = [&](int row, int& w, int& h, int& n) {
+                const int pq = args.P * args.Q;
+                n = row / pq;
+                const int rem = row - n * pq, i = rem / args.Q;
+                h = i * args.out_s; w = (rem - i * args.Q) * args.out_s;
+            };
             auto refill = [&](int g, uint32_t k) {              // slot k % ns of group g is free: next residual or a plain arrive
                 const uint32_t s = k % ns;
                 if (has_res) {
                     int col, row;
                     coords(g, k, col, row);
                     mbar_arrive_expect_tx(&slot_ready[g * 2 + s], EPI_SLOT_BYTES);
+                    if (args.out_s != 0) {
+                        int w, h, n;
+                        view_coords(row, w, h, n);
+                        tma_load_im2col_4d(&tmRes, &slot_ready[g * 2 + s], staging + ((size_t)g * ns + s) * EPI_SLOT_BYTES, col, w, h, n, 0, 0);
+                    } else
                     tma_load_2d(&tmRes, &slot_ready[g * 2 + s], staging + ((size_t)g * ns + s) * EPI_SLOT_BYTES, col, row);
                 } else {
                     mbar_arrive(&slot_ready[g * 2 + s]);
@@ -702,6 +723,11 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                             const int im = m_tile / per, rem = m_tile - im * per;
                             const int pt = rem / args.stem_tq, qt = rem - pt * args.stem_tq;
                             tma_store_4d(&tmOut, slot, col, qt * 16, pt * 8, im);
+                        }
+                        else if (args.out_s != 0) {
+                            int w, h, n;
+                            view_coords(row, w, h, n);
+                            tma_store_im2col_4d(&tmOut, slot, col, w, h, n);
                         }
                         else if (args.out_transposed) tma_store_2d(&tmOut, slot, row, col);
                         else                          tma_store_2d(&tmOut, slot, col, row);
@@ -795,13 +821,28 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 row = m_tile * TC_BM;
             };
             int col, row;
-            const uint32_t pf = has_res ? (uint32_t)args.prefetch_tiles * SUBS : 0u;   // L2 prefetch distance in sub-tiles
+            auto view_coords = [&](int row_, int& w, int& h, int& n) {       // see the dual-issuer variant's issuer warp
+                const int pq = args.P * args.Q;
+                n = row_ / pq;
+                const int rem = row_ - n * pq, i = rem / args.Q;
+                h = i * args.out_s; w = (rem - i * args.Q) * args.out_s;
+            };
+            auto load_res = [&](uint32_t slot_idx, uint8_t* dst_) {
+                mbar_arrive_expect_tx(&slot_ready[g * 2 + slot_idx], EPI_SLOT_BYTES);
+                if (args.out_s != 0) {
+                    int w, h, n;
+                    view_coords(row, w, h, n);
+                    tma_load_im2col_4d(&tmRes, &slot_ready[g * 2 + slot_idx], dst_, col, w, h, n, 0, 0);
+                } else {
+                    tma_load_2d(&tmRes, &slot_ready[g * 2 + slot_idx], dst_, col, row);
+                }
+            };
+            const uint32_t pf = (has_res && args.out_s == 0) ? (uint32_t)args.prefetch_tiles * SUBS : 0u;   // L2 prefetch distance in sub-tiles
             for (uint32_t k = ns; k < ns + pf && k < total; ++k) { coords(k, col, row); tma_prefetch_l2_2d(&tmRes, col, row); }
             for (uint32_t k = 0; k < ns && k < total; ++k) {    // prime the slots
                 if (has_res) {
                     coords(k, col, row);
-                    mbar_arrive_expect_tx(&slot_ready[g * 2 + k], EPI_SLOT_BYTES);
-                    tma_load_2d(&tmRes, &slot_ready[g * 2 + k], sbase + (size_t)k * EPI_SLOT_BYTES, col, row);
+                    load_res(k, sbase + (size_t)k * EPI_SLOT_BYTES);
                 } else {
                     mbar_arrive(&slot_ready[g * 2 + k]);
                 }
@@ -811,8 +852,13 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 mbar_wait(&out_ready[g * 2 + s], ph);           // the group's 128 threads wrote the slot (and fenced)
                 coords(k, col, row);
                 if (col < args.store_cols) {
-                    if (args.out_transposed) tma_store_2d(&tmOut, sbase + (size_t)s * EPI_SLOT_BYTES, row, col);
-                    else                     tma_store_2d(&tmOut, sbase + (size_t)s * EPI_SLOT_BYTES, col, row);
+                    if (args.out_s != 0) {
+                        int w, h, n;
+                        view_coords(row, w, h, n);
+                        tma_store_im2col_4d(&tmOut, sbase + (size_t)s * EPI_SLOT_BYTES, col, w, h, n);
+                    }
+                    else if (args.out_transposed) tma_store_2d(&tmOut, sbase + (size_t)s * EPI_SLOT_BYTES, row, col);
+                    else                          tma_store_2d(&tmOut, sbase + (size_t)s * EPI_SLOT_BYTES, col, row);
                 }
                 bulk_commit();
                 if (k + ns < total) {
@@ -820,8 +866,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     if (has_res) {
                         if (pf && k + ns + pf < total) { coords(k + ns + pf, col, row); tma_prefetch_l2_2d(&tmRes, col, row); }
                         coords(k + ns, col, row);
-                        mbar_arrive_expect_tx(&slot_ready[g * 2 + s], EPI_SLOT_BYTES);
-                        tma_load_2d(&tmRes, &slot_ready[g * 2 + s], sbase + (size_t)s * EPI_SLOT_BYTES, col, row);
+                        load_res(s, sbase + (size_t)s * EPI_SLOT_BYTES);
                     } else {
                         mbar_arrive(&slot_ready[g * 2 + s]);
                     }
@@ -850,10 +895,18 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const uint32_t aph = (uint32_t)(t / kAcc) & 1;
             const int64_t m = (int64_t)m_tile * TC_BM + row;
             const bool valid = m < args.M;
+            int64_t mo = m;                                      // row of dst: the scattered pixel of a strided class
+            if (args.out_s != 0 && valid && mbits) {
+                const int64_t pq = (int64_t)args.P * args.Q;
+                const int img = (int)(m / pq);
+                const int rem = (int)(m - (int64_t)img * pq);
+                const int p = rem / args.Q, q = rem - p * args.Q;
+                mo = ((int64_t)img * args.out_H + (p * args.out_s + args.out_h0)) * args.out_W + (q * args.out_s + args.out_w0);
+            }
             uint32_t mw[SUBS];
 #pragma unroll
             for (int j = 0; j < SUBS; ++j)
-                mw[j] = (mbits && valid) ? __ldg(mbits + (int64_t)(n0 / 32 + g + 2 * j) * args.M + m) : 0xFFFFFFFFu;
+                mw[j] = (mbits && valid) ? __ldg(mbits + (int64_t)(n0 / 32 + g + 2 * j) * args.M_out + mo) : 0xFFFFFFFFu;
             mbar_wait(&tfull_bar[acc], aph);
             tc_fence_after();
             if (threadIdx.x == 256) TC_TRACE(5, t);
@@ -2410,6 +2463,22 @@ static int make_map_im2col(CUtensorMap* map, const float* base, int N, int H, in
     return I2V_OK;
 }
 
+// im2col-mode map over a VIEW of an NHWC tensor: Hv x Wv pixels starting at `base` (already shifted to the view's first
+// pixel) inside images of Hfull x Wfull pixels; traversal stride `stride`, bounding box = the view.  The epilogue of a strided
+// data-gradient class stores (and reads its addend) through it: tile row (img, i, j) <-> view pixel (i stride, j stride).
+static int make_map_im2col_view(CUtensorMap* map, const float* base, int N, int Hv, int Wv, int C, int Hfull, int Wfull, int stride) {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wv, (cuuint64_t)Hv, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)Wfull * C * 4, (cuuint64_t)Hfull * Wfull * C * 4};
+    int lower[2] = {0, 0};
+    int upper[2] = {0, 0};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    CUresult r = g_encode_im2col(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, lower, upper,
+                                 TC_BK, TC_BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeIm2col (view) failed (%d) N=%d Hv=%d Wv=%d C=%d H=%d W=%d stride=%d", (int)r, N, Hv, Wv, C, Hfull, Wfull, stride); return I2V_ECUDA; }
+    return I2V_OK;
+}
+
 // 4-D tiled map with explicit byte strides (dims / strides innermost first; box = {32, 16, 8, 1} floats x pixels x rows x
 // images, SWIZZLE_128B): the 16 x 8 pixel boxes of the direct first-layer forward.  Strides may OVERLAP the inner extent
 // (the 8-pixel window of output pixel q+1 starts two pixels after that of q).
@@ -2472,6 +2541,16 @@ static int get_map_u8_rows64(CUtensorMap* out, const uint8_t* base, int rows, in
     auto it = g_maps.find(key);
     if (it != g_maps.end()) { *out = it->second; return I2V_OK; }
     if (int r = make_map_u8_rows64(out, base, (uint64_t)rows, (uint32_t)box_rows)) return r;
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps.emplace(key, *out);
+    return I2V_OK;
+}
+static int get_map_im2col_view(CUtensorMap* out, const float* base, int N, int Hv, int Wv, int C, int Hfull, int Wfull, int stride) {
+    MapKey key{base, N, Hv, Wv, C, Hfull, Wfull, stride, 7};
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return I2V_OK; }
+    if (int r = make_map_im2col_view(out, base, N, Hv, Wv, C, Hfull, Wfull, stride)) return r;
     if (g_maps.size() > 4096) g_maps.clear();
     g_maps.emplace(key, *out);
     return I2V_OK;
@@ -2672,7 +2751,9 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
     // TMA epilogue (v3) whenever the output rows are dense and no f32 mask source is involved; the strided
     // data-gradient classes and callers that pass an f32 mask keep the register/LSU epilogue (v2)
     static const bool epi_tma_on = !(getenv("I2V_TC_EPI_TMA") && atoi(getenv("I2V_TC_EPI_TMA")) == 0);
-    const bool epi_tma = persistent && epi_tma_on && pr.out_s == 0 && pr.mask_src == nullptr;
+    // ... since round 2 the strided classes too: their rows scatter through an im2col-mode TMA store ($I2V_TC_CLASS_TMA=0: v2)
+    static const bool class_tma_on = !(getenv("I2V_TC_CLASS_TMA") && atoi(getenv("I2V_TC_CLASS_TMA")) == 0);
+    const bool epi_tma = persistent && epi_tma_on && (pr.out_s == 0 || class_tma_on) && pr.mask_src == nullptr;
     I2V_REQUIRE(epi_tma || (pr.mask_bits == nullptr && pr.bits_out == nullptr),
                 "bit masks need the TMA epilogue (dense output rows, no f32 mask source)");
 
@@ -2685,7 +2766,17 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
     tmOut = tmBhi; tmRes = tmBhi;
     I2V_REQUIRE(!pr.out_transposed || (epi_tma && !pr.residual && !pr.mask_bits && !pr.bits_out && !pr.relu && M % 4 == 0),
                 "transposed output needs the TMA epilogue without residual / masks / ReLU and M % 4 == 0");
-    if (epi_tma) {
+    if (epi_tma && pr.out_s != 0) {
+        // the class's view of dst: first pixel (out_h0, out_w0), every out_s-th pixel from there
+        I2V_REQUIRE(!pr.out_transposed && !pr.bits_out && pr.out_h0 < pr.out_H && pr.out_w0 < pr.out_W, "bad strided output");
+        const int64_t first = ((int64_t)pr.out_h0 * pr.out_W + pr.out_w0) * pr.Cout;
+        if (int r = get_map_im2col_view(&tmOut, pr.dst + first, pr.N, pr.out_H - pr.out_h0, pr.out_W - pr.out_w0, pr.Cout, pr.out_H,
+                                        pr.out_W, pr.out_s)) return r;
+        if (pr.residual) {
+            if (int r = get_map_im2col_view(&tmRes, pr.residual + first, pr.N, pr.out_H - pr.out_h0, pr.out_W - pr.out_w0, pr.Cout,
+                                            pr.out_H, pr.out_W, pr.out_s)) return r;
+        }
+    } else if (epi_tma) {
         if (pr.out_transposed) { if (int r = get_map_2d_plain(&tmOut, pr.dst, pr.Cout, (int)M, 32, TC_BM)) return r; }
         else                   { if (int r = get_map_2d(&tmOut, pr.dst, (int)M, pr.Cout, TC_BM)) return r; }
         if (pr.residual) { if (int r = get_map_2d(&tmRes, pr.residual, (int)M, pr.Cout, TC_BM)) return r; }
@@ -2709,6 +2800,7 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
     a.taps_h = pr.taps_h; a.taps_w = pr.taps_w; a.cblocks = pr.C / 32; a.relu = pr.relu;
     if (pr.src2) { a.a2_cb0 = pr.C / 32; a.cblocks = (pr.C + pr.C2) / 32; }
     a.out_s = pr.out_s; a.out_h0 = pr.out_h0; a.out_w0 = pr.out_w0; a.out_H = pr.out_H; a.out_W = pr.out_W;
+    a.M_out = pr.out_s != 0 ? (int64_t)pr.N * pr.out_H * pr.out_W : M;
     a.trace = g_trace; a.trace_tiles = g_trace_tiles;
     static const int pair_dbg = getenv("I2V_TC_PAIR_DBG") ? atoi(getenv("I2V_TC_PAIR_DBG")) : 0;
     a.dbg = pair_dbg;
@@ -2734,7 +2826,7 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
             // from which the pair kernel takes over (0 = never); needs at least two m-tiles
             const int pair_minkit = pair_min_ksteps();
             const bool pair_on = pair_minkit > 0 ? kit >= pair_minkit : (pair_minkit == -1 && pr.residual != nullptr && kit >= 4);
-            if (alo && pair_on && !pr.out_transposed && M > TC_BM && !pr.src2) {
+            if (alo && pair_on && !pr.out_transposed && M > TC_BM && !pr.src2 && pr.out_s == 0) {
                 CUtensorMap hBhi, hBlo;
                 if (int r = get_map_2d(&hBhi, pr.w_hi, pr.Cout, Ktot, BN / 2)) return r;
                 if (int r = get_map_2d(&hBlo, pr.w_lo, pr.Cout, Ktot, BN / 2)) return r;
@@ -3160,10 +3252,24 @@ extern "C" int i2v_conv_stem_fwd_direct_f32(const i2v_conv_desc* d, const float*
 // scattered with pitch `stride` into dx.  w_* = [Cin, (tap_h, tap_w, co)] with tap_h = A_h-1-a (host: see
 // engine_native._class_weights).  Classes without taps (e.g. the odd rows of a 1x1/s2 conv) receive no gradient
 // from this conv: the call is a no-op for them and the caller owns their contents (addend already in place).
+extern "C" int i2v_conv_tc_dgrad_class_bits_f32(const i2v_conv_desc* d, int ph, int pw, const float* dy, const float* w_hi,
+                                                const float* w_lo, const float* addend, const float* mask_src,
+                                                const uint32_t* mask_bits, float* dx, i2v_stream_t stream);
+
 extern "C" int i2v_conv_tc_dgrad_class_f32(const i2v_conv_desc* d, int ph, int pw, const float* dy, const float* w_hi,
                                            const float* w_lo, const float* addend, const float* mask_src, float* dx,
                                            i2v_stream_t stream) {
+    return i2v_conv_tc_dgrad_class_bits_f32(d, ph, pw, dy, w_hi, w_lo, addend, mask_src, nullptr, dx, stream);
+}
+
+// ... with the ReLU-backward mask as BITS ([Cin/32][N*H*W] words, the forward epilogue's bits_out of the tensor dx belongs to)
+// instead of the f32 activation: with mask_src == NULL the class runs the TMA epilogue (im2col-mode scatter store, addend by
+// im2col-mode load) — no per-thread global access
+extern "C" int i2v_conv_tc_dgrad_class_bits_f32(const i2v_conv_desc* d, int ph, int pw, const float* dy, const float* w_hi,
+                                                const float* w_lo, const float* addend, const float* mask_src,
+                                                const uint32_t* mask_bits, float* dx, i2v_stream_t stream) {
     I2V_REQUIRE(d && dy && dx, "null pointer");
+    I2V_REQUIRE(!(mask_bits && mask_src), "pass either an f32 mask source or a bit mask, not both");
     I2V_REQUIRE(i2v_conv_tc_supported(d, 1), "shape not supported by the tensor-core path");
     const int st = d->stride;
     I2V_REQUIRE(ph >= 0 && ph < st && pw >= 0 && pw < st, "class index out of range");
@@ -3183,7 +3289,7 @@ extern "C" int i2v_conv_tc_dgrad_class_f32(const i2v_conv_desc* d, int ph, int p
     pr.upper_h = pr.lower_h + Hc - d->P; pr.upper_w = pr.lower_w + Wc - d->Q;
     pr.taps_h = Ah; pr.taps_w = Aw;
     pr.w_hi = w_hi; pr.w_lo = w_lo; pr.Cout = d->Cin;
-    pr.bias = nullptr; pr.residual = addend; pr.mask_src = mask_src; pr.dst = dx; pr.relu = 0;
+    pr.bias = nullptr; pr.residual = addend; pr.mask_src = mask_src; pr.mask_bits = mask_bits; pr.dst = dx; pr.relu = 0;
     pr.out_s = st; pr.out_h0 = ph; pr.out_w0 = pw; pr.out_H = d->H; pr.out_W = d->W;
     return tc_run(pr, as_stream(stream));
 }

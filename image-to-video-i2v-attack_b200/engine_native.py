@@ -504,12 +504,16 @@ class NativeEngine:
             # strided: one dense launch per stride-parity class; classes without taps keep what is there
             if addend is None and any(v is None for v in op.tc_dgrad_cls.values()):
                 dx.zero_()
+            if mask_src is not None and mask_bits is not None:
+                mask_src = None                                   # same mask, 1/32 of the bytes — and the TMA epilogue
+            else:
+                mask_bits = None
             for (ph, pw), wt in op.tc_dgrad_cls.items():
                 if wt is None:
                     continue
                 hi, lo, rna = wt
                 capi.conv_tc_dgrad_class(d, ph, pw, dy, hi if self.tf32x3 else rna, lo if self.tf32x3 else None,
-                                         addend, mask_src, dx)
+                                         addend, mask_src, dx, mask_bits=mask_bits)
         else:
             capi.conv_dgrad_simt(d, dy, op.b_dgrad, addend, mask_src, dx, x_nchw=op.x_nchw)
 

@@ -343,6 +343,13 @@ int i2v_conv_tc_dual_f32(const i2v_conv_desc* d, const float* x, int C2, const f
 int i2v_conv_tc_dgrad_class_f32(const i2v_conv_desc* d, int ph, int pw, const float* dy, const float* w_hi,
                                 const float* w_lo, const float* addend, const float* mask_src, float* dx,
                                 i2v_stream_t stream);
+/* The same with the ReLU-backward mask as BITS ([Cin/32][N*H*W] words: the bits_out of the forward launch that produced the
+ * tensor dx is the gradient of) instead of the f32 activation.  With mask_src == NULL the class runs the TMA epilogue: its
+ * rows scatter into dx through an im2col-mode TMA store over the class's strided view of dx (the addend is read the same
+ * way) — no per-thread global access.                                                                              */
+int i2v_conv_tc_dgrad_class_bits_f32(const i2v_conv_desc* d, int ph, int pw, const float* dy, const float* w_hi,
+                                     const float* w_lo, const float* addend, const float* mask_src, const uint32_t* mask_bits,
+                                     float* dx, i2v_stream_t stream);
 
 /* k x k max pooling (stride, -inf padding), NHWC, C % 4 == 0.  argmax[N,P,Q,C] = r*k+s of the FIRST
  * maximum in window scan order (torch.nn.MaxPool2d); backward is the gather form (no atomics) and can

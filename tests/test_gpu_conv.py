@@ -522,8 +522,12 @@ def test_stem_fwd_and_dgrad(H, W, k, s, p):
 @pytest.mark.parametrize("shape", [(2, 56, 56, 128, 128, 3, 2, 1), (2, 56, 56, 256, 512, 1, 2, 0), (3, 28, 28, 256, 256, 3, 2, 1),
                                    (2, 27, 27, 64, 64, 3, 2, 1), (1, 55, 41, 64, 128, 3, 2, 0), (2, 28, 28, 512, 1024, 1, 2, 0)])
 @pytest.mark.parametrize("x3", [True, False])
-def test_conv_tc_strided_dgrad_classes(shape, x3):
-    """Strided data gradient as stride^2 dense tensor-core problems scattered into dx (even/odd sizes, padding 0/1)."""
+@pytest.mark.parametrize("mask", ["f32", "bits", "none"])
+def test_conv_tc_strided_dgrad_classes(shape, x3, mask):
+    """Strided data gradient as stride^2 dense tensor-core problems scattered into dx (even/odd sizes, padding 0/1).
+    mask = f32: the activation as mask source (register epilogue, per-thread scatter); bits / none: the TMA epilogue — rows
+    scatter through an im2col-mode TMA store over the class's strided view of dx, the in-place addend comes in by an
+    im2col-mode load, the mask is one word per row from the [Cin/32][N*H*W] bit planes."""
     from i2v_b200.engine_native import _class_weights
     N, H, W, Cin, Cout, k, s, p = shape
     g = torch.Generator().manual_seed(13)
@@ -538,6 +542,7 @@ def test_conv_tc_strided_dgrad_classes(shape, x3):
     lay = lambda t: t.permute(0, 2, 3, 1).contiguous().to(DEV)
     ref = torch.nn.grad.conv2d_input((N, Cin, H, W), w.double(), dy.double(), s, p)
     tol = (1e-5 + k * k * Cout * 2.0 ** -24) if x3 else 4e-3
+    abits = _pack_bits(lay(act) > 0) if mask == "bits" else None
     for use_add in (False, True):
         dx = lay(addend) if use_add else torch.zeros(N, H, W, Cin, device=DEV)
         for (ph, pw), wt in cls.items():
@@ -545,8 +550,10 @@ def test_conv_tc_strided_dgrad_classes(shape, x3):
                 continue
             hi, lo, rna = wt
             capi.conv_tc_dgrad_class(d, ph, pw, lay(dy), hi if x3 else rna, lo if x3 else None, dx if use_add else None,
-                                     lay(act), dx)
+                                     lay(act) if mask == "f32" else None, dx, mask_bits=abits)
         want = (ref + addend.double()) if use_add else ref
+        if mask == "none":
+            act = torch.ones_like(act)
         # classes with taps are masked by the kernel; classes without taps keep the addend (already masked in real use)
         got = dx.permute(0, 3, 1, 2).cpu().double()
         has = torch.zeros(H, W, dtype=torch.bool)
