@@ -2821,11 +2821,18 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
             static const int alo_env = getenv("I2V_TC_ALO_TMEM") ? atoi(getenv("I2V_TC_ALO_TMEM")) : 1;
             const int kit = pr.taps_h * pr.taps_w * (pr.C / 32) + (pr.src2 ? pr.C2 / 32 : 0);
             static const int alo_minkit = getenv("I2V_TC_ALO_MINKIT") ? atoi(getenv("I2V_TC_ALO_MINKIT")) : 4;
-            const bool alo = x3 && alo_env != 0 && (BN == 64 || kit >= alo_minkit || alo_env == 2 || pr.force_dual);
+            // (a dual-source launch of 4 k-steps — layer1.0's downsample + conv3 — runs 430 us on the single-issuer kernel
+            // with its two accumulator stages against 475 us: threshold 8 there)
+            const bool alo = x3 && alo_env != 0 && (BN == 64 || kit >= (pr.src2 ? 2 * alo_minkit : alo_minkit) || alo_env == 2 || pr.force_dual);
             // CTA pairs (tcgen05.mma.cta_group::2, half of the weight rows per CTA): $I2V_TC_PAIR = minimum k-steps per tile
             // from which the pair kernel takes over (0 = never); needs at least two m-tiles
             const int pair_minkit = pair_min_ksteps();
-            const bool pair_on = pair_minkit > 0 ? kit >= pair_minkit : (pair_minkit == -1 && pr.residual != nullptr && kit >= 4);
+            // default rule (-1), per-shape A/B in situ (gpurun_out/r3h_*): a residual streaming through the epilogue, or a
+            // plain 1x1 with BN = 128 tiles of 4-8 k-steps and at most two n-tiles (56x56 256->128: fwd 320 -> 298 us, dgrad
+            // 432 -> 338 us); the im2col layers and the BN = 64 ones lose on the pair
+            const bool pair_on = pair_minkit > 0 ? kit >= pair_minkit
+                               : (pair_minkit == -1 && kit >= 4 &&
+                                  (pr.residual != nullptr || (!im2col && BN == 128 && kit <= 8 && pr.Cout / BN <= 2)));
             if (alo && pair_on && !pr.out_transposed && M > TC_BM && !pr.src2 && pr.out_s == 0) {
                 CUtensorMap hBhi, hBlo;
                 if (int r = get_map_2d(&hBhi, pr.w_hi, pr.Cout, Ktot, BN / 2)) return r;
