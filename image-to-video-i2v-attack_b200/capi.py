@@ -72,6 +72,7 @@ SIGNATURES = {
     "i2v_conv_tc_supported": ([_c_p, _c_int], _c_int),
     "i2v_conv_tc_set_trace": ([_c_p, _c_int], _c_int),
     "i2v_conv_tc_set_pair_minkit": ([_c_int], _c_int),
+    "i2v_mma_shift_probe": ([_c_int, _c_int, _c_p, _c_p, _c_p, _c_p], _c_int),
     "i2v_mma_probe": ([_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_p, _c_p], _c_int),
     "i2v_conv_tc_f32": ([_c_p, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_tc_bits_f32": ([_c_p, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),

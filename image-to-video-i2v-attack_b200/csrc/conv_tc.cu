@@ -117,6 +117,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (clock64() - t0 > 8000000000LL) { printf("i2v conv_tc: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
     }
 }
+// Role selection.  `if (lane == 0)` leaves the compiler unable to prove that the operands of the uniform-datapath instructions
+// (UTCHMMA, UTMALDG, UTCBAR, SYNCS) are warp-uniform, so it wraps EVERY one of them in a waterfall loop (ELECT + up to seven
+// R2UR.BROADCAST + BRA.U.ANY): ~200 cycles per tcgen05.mma on the issuing thread where an N = 64 / 128 instruction occupies the
+// tensor pipe for 32 / 64.  Behind `elect.sync` the same code is straight-line UTCHMMA (cuobjdump -sass: no BRA.U.ANY).
+// The whole warp must reach elect_one() converged; the warp index goes through a shuffle so that it is uniform by construction.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -263,7 +274,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
     float* bias_s = reinterpret_cast<float*>(tmem_slot + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int64_t m0 = (int64_t)blockIdx.x * TC_BM;
     const int n0 = blockIdx.y * BN;
     const int kiters = args.taps_h * args.taps_w * args.cblocks;
@@ -299,7 +310,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         // ===== TMA producer =====================================================================
-        if (lane == 0) {
+        if (elect_one()) {
             int img = 0, base_h = 0, base_w = 0;
             if (IM2COL) {
                 const int64_t pq = (int64_t)args.P * args.Q;
@@ -326,7 +337,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ===== MMA issuer =======================================================================
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_tf32(BN);
             for (int it = 0; it < kiters; ++it) {
                 const int st = it % stages;
@@ -502,7 +513,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slot_ready + 4);
     float* bias_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 2) + 15) & ~(uintptr_t)15);   // [Cout], 16-byte aligned
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int kiters = args.taps_h * args.taps_w * args.cblocks;
     const int num_tiles = num_m_tiles * num_n_tiles;
 
@@ -543,7 +554,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
     if (warp == 0) {
         // ===== TMA producer: runs ahead across tiles, bounded only by the smem ring ===================
-        if (lane == 0) {
+        if (elect_one()) {
             int it = 0, tno = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tno) {
                 const int m_tile = tile / num_n_tiles, n_tile = tile - m_tile * num_n_tiles;
@@ -599,7 +610,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
     } else if (warp == 1) {
         // ===== MMA issuer ==============================================================================
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_tf32(BN);
             constexpr uint32_t idesc2 = umma_idesc_tf32(2 * BN);
             int it = 0, t = 0;
@@ -640,7 +651,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
     } else if (ALO_TMEM && warp == 2) {
         // ===== second MMA issuer: cross2 += a_lo (tensor memory) x b_hi ===================================
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_tf32(BN);
             int it = 0, t = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
@@ -667,7 +678,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
     } else if (ALO_TMEM && EPI_TMA && warp == 3) {
         // ===== epilogue TMA issuer of BOTH groups (warp 2 issues MMAs here): polls the groups' out_ready barriers ====
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t SUBS = BN / 64;
             const bool has_res = args.residual != nullptr;
             const uint32_t ns = (uint32_t)epi_slots;
@@ -806,7 +817,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
     } else if (EPI_TMA && !ALO_TMEM && (warp == 2 || warp == 3)) {
         // ===== epilogue TMA issuer of group g = warp - 2: output stores and residual loads ================
-        if (lane == 0) {
+        if (elect_one()) {
             const int g = warp - 2;
             constexpr uint32_t SUBS = BN / 64;                  // sub-tiles per tile and group
             const bool has_res = args.residual != nullptr;
@@ -1196,7 +1207,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* slot_ready = out_ready + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slot_ready + 4);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int kiters = args.taps_h * args.taps_w * args.cblocks;
@@ -1236,7 +1247,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     if (warp == 0) {
         // ===== TMA producer (both CTAs): own A tile -> afull (local); own half of the weight rows -> full (leader) =========
-        if (lane == 0) {
+        if (elect_one()) {
             int it = 0, tno = 0;
             for (int pt = pid; pt < num_ptiles; pt += npairs, ++tno) {
                 const int pm = pt / num_n_tiles, n_tile = pt - pm * num_n_tiles;
@@ -1272,7 +1283,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else if (warp == 1) {
         // ===== MMA issuer 1 (leader): [main | cross] halves of both CTAs += a_hi x [b_hi half | b_lo half] ==================
-        if (leader && lane == 0) {
+        if (leader && elect_one()) {
             constexpr uint32_t idesc2 = umma2_idesc_tf32(2 * BN);
             int it = 0, t = 0;
             for (int pt = pid; pt < num_ptiles; pt += npairs, ++t) {
@@ -1303,7 +1314,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else if (warp == 2) {
         // ===== MMA issuer 2 (leader): cross2 += a_lo (tensor memory of each CTA) x b_hi halves ===============================
-        if (leader && lane == 0) {
+        if (leader && elect_one()) {
             constexpr uint32_t idesc = umma2_idesc_tf32(BN);
             int it = 0, t = 0;
             for (int pt = pid; pt < num_ptiles; pt += npairs, ++t) {
@@ -1330,7 +1341,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else if (warp == 3) {
         // ===== epilogue TMA issuer of both groups (per CTA): output stores, residual loads ==================================
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t SUBS = BN / 64;
             const bool has_res = args.residual != nullptr;
             const uint32_t ns = (uint32_t)epi_slots;
@@ -1587,7 +1598,7 @@ stem_dgrad_direct_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     auto a_tile = [&](int st, int kb) { return atiles + ((size_t)st * 2 + kb) * TC_A_BYTES; };
 
     for (int i = threadIdx.x; i < 3 * 2 * kEdgeBuf; i += SD_THREADS) edge[i] = 0.f;     // slots 0 and 5 are never written again
@@ -1609,7 +1620,7 @@ stem_dgrad_direct_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     constexpr uint32_t kRing = 320;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_arrive_expect_tx(bfull, 4 * SD_B_TILE);          // the weights stay resident
             for (int kb = 0; kb < 2; ++kb) {
                 tma_load_2d(&tmBhi, bfull, bhi + (size_t)kb * SD_B_TILE, kb * TC_BK, 0);
@@ -1643,7 +1654,7 @@ stem_dgrad_direct_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
     } else if (warp == 1) {
         // the MMA issuer: acc (+)= a_hi b_hi + a_hi b_lo + a_lo (tensor memory) b_hi, 24 instructions of N = 160 per dy row
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_tf32(SD_NZ);
             mbar_wait(bfull, 0);
             int t = 0;
@@ -1870,7 +1881,7 @@ stem_dgrad_pool_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
     // 64 bytes of argmax = 255 ("dead window"): where the windows that do not exist for a pixel point their argmax loads
     uint8_t* dead64 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 63) & ~(uintptr_t)63);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     auto a_tile = [&](int st, int kb) { return atiles + ((size_t)st * 2 + kb) * TC_A_BYTES; };
 
     for (int i = threadIdx.x; i < 3 * 2 * kEdgeBuf; i += SD_THREADS) edge[i] = 0.f;     // slots 0 and 5 are never written again
@@ -1894,7 +1905,7 @@ stem_dgrad_pool_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
     constexpr uint32_t kRing = 320;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_arrive_expect_tx(bfull, 4 * SD_B_TILE);          // the weights stay resident
             for (int kb = 0; kb < 2; ++kb) {
                 tma_load_2d(&tmBhi, bfull, bhi + (size_t)kb * SD_B_TILE, kb * TC_BK, 0);
@@ -1926,7 +1937,7 @@ stem_dgrad_pool_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
         }
     } else if (warp == 1) {
         // the MMA issuer: acc (+)= a_hi b_hi + a_hi b_lo + a_lo (tensor memory) b_hi, 24 instructions of N = 160 per dy row
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_tf32(SD_NZ);
             mbar_wait(bfull, 0);
             int t = 0;
@@ -2157,6 +2168,312 @@ stem_dgrad_pool_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------
+// 3x3 / stride 1 / pad 1 convolutions with every input patch delivered ONCE ("halo" kernel; 3xTF32, TMA epilogue).
+// The im2col-mode main loop above pulls a 128-pixel x 32-channel tile through L2 for each of the nine filter taps: the same
+// input pixels nine times (3.7 GB of L2 -> shared-memory traffic per 256-frame launch of a 64 -> 64 layer for 0.4 GB of
+// tensors).  Here a tile is R whole output rows of one image laid out on the ZERO-PADDED raster, position j = r (W+2) + q
+// (R (W+2) <= 128: the two padding columns of every row are junk GEMM rows, 3-7 % of the tile), and the activations a
+// 32-channel block of it needs are ONE tiled TMA box {32 ch, W+2, R+2 rows} starting at (-1, p0-1) — out-of-bounds pixels
+// arrive as zeros, which IS the padding.  In that patch the operand of filter tap (r, s) is the SAME 128 rows shifted by
+// r (W+2) + s rows: the tensor core applies the 128-byte swizzle to absolute shared-memory address bits, so a descriptor
+// whose start address is shifted by any number of 128-byte rows reads exactly those rows (tools/mma_shift_probe.py, exact on
+// every shift).  Per 32-channel block: one 30 KB load instead of nine 16 KB ones, and the 3xTF32 split (a_lo = a - tf32(a))
+// is computed once per patch instead of once per tap, into a second patch that the a_lo x b_hi instruction reads.
+//   warp 0: producer — the weight ring (per tap and block: [b_hi | b_lo]) and the two patch slots; the next patch is requested
+//           between weight stages the moment its slot frees
+//   warp 1: a_hi x [b_hi | b_lo] -> [main | cross]                     warp 2: a_lo x b_hi -> cross2
+//   warp 3: TMA stores of the epilogue groups                          warps 4-7: split   warps 8-15: epilogue
+// Epilogue: thread = padded-raster position; valid positions write their 32-column slice into the staging slot at the DENSE
+// row (r W + q), so that one 2-D TMA store of R W rows ships a tile (a second map with fewer rows for an image's last tile).
+// ---------------------------------------------------------------------------------------------
+constexpr int HL_THREADS = 512;
+
+struct HaloArgs {
+    const float* bias;
+    const uint32_t* mask_bits;   // [Cout/32][M] or null (data gradient: ReLU-backward mask of dst)
+    uint32_t* bits_out;          // [Cout/32][M] or null (forward: activity bits of dst)
+    int N, H, W, PW, R, TI;      // padded width W + 2, output rows per tile, tiles per image
+    int CB;                      // Cin / 32
+    int relu;
+    int rows_load;               // (R + 2) * PW rows per patch load
+    uint32_t patch_bytes;        // one patch (raw or lo), multiple of 1024, >= (2 PW + 2 + 128) rows
+    int bstages;
+    int tail_rows;               // H % R: rows of an image's last tile when it is short (0: all tiles full)
+    int dbg;                     // timing experiments ($I2V_TC_HALO_DBG, wrong results): bit 0 skips the main MMAs, bit 1 the a_lo MMAs, bit 2 the split, bit 3 the weight loads
+    int64_t M;                   // N * H * W
+};
+
+template <int BN>
+__global__ void __launch_bounds__(HL_THREADS, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBhi,
+                    const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmOut,
+                    const __grid_constant__ CUtensorMap tmOutTail, const HaloArgs args, const int num_tiles, const int num_n_tiles) {
+    constexpr uint32_t kAccCols = 3 * BN;                       // [main | cross | cross2]
+    constexpr int kAcc = 384 / kAccCols;                        // 2 accumulator stages at BN = 64, 1 at BN = 128
+    constexpr uint32_t kBStage = 2u * BN * 128u;                // [b_hi | b_lo], 32 k-values per row
+    constexpr int SUBS = BN / 64;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t pbytes = args.patch_bytes;
+    const int bstages = args.bstages;
+    uint8_t* patches = smem;                                    // [2 slots][raw | lo]
+    uint8_t* bring = patches + 4 * (size_t)pbytes;
+    uint8_t* staging = bring + (size_t)bstages * kBStage;       // one 16 KB slot per epilogue group
+    uint64_t* pfull = reinterpret_cast<uint64_t*>(staging + 2 * EPI_SLOT_BYTES);
+    uint64_t* pempty = pfull + 2;
+    uint64_t* psplit = pempty + 2;
+    uint64_t* bfull = psplit + 2;
+    uint64_t* bempty = bfull + 8;
+    uint64_t* tfull = bempty + 8;
+    uint64_t* tempty = tfull + 2;
+    uint64_t* out_ready = tempty + 2;
+    uint64_t* slot_ready = out_ready + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slot_ready + 2);
+
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
+    const int CB = args.CB, PW = args.PW;
+    auto patch_raw = [&](int ps) { return patches + (size_t)ps * 2 * pbytes; };
+    auto patch_lo = [&](int ps) { return patches + (size_t)ps * 2 * pbytes + pbytes; };
+    auto bstage = [&](int st) { return bring + (size_t)st * kBStage; };
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmX); prefetch_tmap(&tmBhi); prefetch_tmap(&tmBlo); prefetch_tmap(&tmOut); prefetch_tmap(&tmOutTail);
+        for (int i = 0; i < 2; ++i) { mbar_init(&pfull[i], 1); mbar_init(&pempty[i], 2); mbar_init(&psplit[i], 128); }
+        for (int i = 0; i < bstages; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 2); }
+        for (int i = 0; i < kAcc; ++i) { mbar_init(&tfull[i], 2); mbar_init(&tempty[i], TC2_EPI_THREADS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&out_ready[i], TC2_EPI_THREADS / 2); mbar_init(&slot_ready[i], 1); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile -> (image, first output row, first output channel)
+    auto tile_of = [&](int tile, int& img, int& p0, int& n0, bool& tail) {
+        const int mt = tile / num_n_tiles;
+        n0 = (tile - mt * num_n_tiles) * BN;
+        img = mt / args.TI;
+        const int ti = mt - img * args.TI;
+        p0 = ti * args.R;
+        tail = args.tail_rows != 0 && ti == args.TI - 1;
+    };
+
+    if (warp == 0) {
+        // ===== producer (one elected thread): the weight ring, and the patches (one box per 32-channel block, two slots).  The
+        // patch of block k is requested, blocking, before the weights of block k (the issuers cannot pass block k without it, and its
+        // slot frees on the MMAs of block k - 2, whose weights are already in flight: no deadlock); the patch of block k + 1 is
+        // requested between the weight stages of block k the moment its slot frees (try_wait).
+        if (elect_one()) {
+            int bi = 0, wi = 0;
+            int ptile = blockIdx.x, pcb = 0, pi = 0;             // the next patch to request
+            auto issue_patch = [&]() {
+                int img, p0, n0; bool tail;
+                tile_of(ptile, img, p0, n0, tail);
+                const int ps = pi & 1;
+                mbar_arrive_expect_tx(&pfull[ps], (uint32_t)args.rows_load * 128u);
+                tma_load_4d(&tmX, &pfull[ps], patch_raw(ps), pcb * TC_BK, -1, p0 - 1, img);
+                ++pi;
+                if (++pcb == CB) { pcb = 0; ptile += gridDim.x; }
+            };
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int img, p0, n0; bool tail;
+                tile_of(tile, img, p0, n0, tail);
+                for (int cb = 0; cb < CB; ++cb, ++wi) {
+                    while (pi <= wi && ptile < num_tiles) {
+                        mbar_wait(&pempty[pi & 1], ((uint32_t)(pi >> 1) & 1) ^ 1);
+                        issue_patch();
+                    }
+                    for (int tap = 0; tap < 9; ++tap, ++bi) {
+                        if (pi == wi + 1 && ptile < num_tiles && mbar_try_wait(&pempty[pi & 1], ((uint32_t)(pi >> 1) & 1) ^ 1)) issue_patch();
+                        const int st = bi % bstages;
+                        mbar_wait(&bempty[st], ((uint32_t)(bi / bstages) & 1) ^ 1);
+                        if (args.dbg & 8) { mbar_arrive(&bfull[st]); continue; }
+                        mbar_arrive_expect_tx(&bfull[st], kBStage);
+                        const int kcol = (tap * CB + cb) * TC_BK;
+                        tma_load_2d(&tmBhi, &bfull[st], bstage(st), kcol, n0);
+                        tma_load_2d(&tmBlo, &bfull[st], bstage(st) + (size_t)BN * 128, kcol, n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 || warp == 2) {
+        // ===== MMA issuers: warp 1  [main | cross] += a x [b_hi | b_lo];  warp 2  cross2 += a_lo x b_hi ============
+        if (elect_one()) {
+            const bool lo_issuer = warp == 2;
+            const uint32_t idesc = lo_issuer ? umma_idesc_tf32(BN) : umma_idesc_tf32(2 * BN);
+            int pi = 0, bi = 0, t = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+                const int acc = t % kAcc;
+                mbar_wait(&tempty[acc], ((uint32_t)(t / kAcc) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)acc * kAccCols + (lo_issuer ? 2u * BN : 0u);
+                for (int cb = 0; cb < CB; ++cb, ++pi) {
+                    const int ps = pi & 1;
+                    const uint32_t pph = (uint32_t)(pi >> 1) & 1;
+                    mbar_wait(&pfull[ps], pph);
+                    if (lo_issuer) mbar_wait(&psplit[ps], pph);
+                    tc_fence_after();
+                    const uint32_t abase = smem_u32(lo_issuer ? patch_lo(ps) : patch_raw(ps));
+                    for (int tap = 0; tap < 9; ++tap, ++bi) {
+                        const int st = bi % bstages;
+                        mbar_wait(&bfull[st], (uint32_t)(bi / bstages) & 1);
+                        tc_fence_after();
+                        const int r = tap / 3, sx = tap - 3 * r;
+                        const uint64_t da = umma_desc_sw128(abase + (uint32_t)(r * PW + sx) * 128u);    // the tap = a row shift
+                        const uint64_t db = umma_desc_sw128(smem_u32(bstage(st)));
+                        if (!(args.dbg & (lo_issuer ? 2 : 1))) {
+#pragma unroll
+                            for (int kk = 0; kk < TC_BK / 8; ++kk)
+                                umma_tf32(d, da + 2 * kk, db + 2 * kk, idesc, (cb | tap | kk) ? 1u : 0u);
+                        }
+                        umma_commit(&bempty[st]);
+                    }
+                    umma_commit(&pempty[ps]);
+                }
+                umma_commit(&tfull[acc]);
+            }
+        }
+    } else if (warp == 3) {
+        // ===== epilogue TMA issuer of both groups ===========================================================
+        if (elect_one()) {
+            const uint32_t my_tiles = (uint32_t)((num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
+            const uint32_t total = my_tiles * SUBS;
+            if (total > 0) { mbar_arrive(&slot_ready[0]); mbar_arrive(&slot_ready[1]); }
+            uint32_t kdone[2] = {0, 0};
+            const long long t0 = clock64();
+            while (kdone[0] < total || kdone[1] < total) {
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const uint32_t k = kdone[g];
+                    if (k >= total) continue;
+                    if (!mbar_try_wait(&out_ready[g], k & 1)) continue;
+                    const int tile = (int)blockIdx.x + (int)(k / SUBS) * (int)gridDim.x;
+                    int img, p0, n0; bool tail;
+                    tile_of(tile, img, p0, n0, tail);
+                    const int col = n0 + (g + 2 * (int)(k % SUBS)) * 32;
+                    const int row = (img * args.H + p0) * args.W;
+                    tma_store_2d(tail ? &tmOutTail : &tmOut, staging + (size_t)g * EPI_SLOT_BYTES, col, row);
+                    bulk_commit();
+                    if (k + 1 < total) { bulk_wait_read0(); mbar_arrive(&slot_ready[g]); }
+                    kdone[g] = k + 1;
+                }
+                if (clock64() - t0 > 40000000000LL) { printf("i2v conv3x3_halo: epilogue issuer timeout (block %d)\n", blockIdx.x); __trap(); }
+            }
+            bulk_wait_all();
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===== split: a_lo patch = a - tf32(a), element-wise at the same (swizzled) offsets, once per patch ============
+        const int t128 = threadIdx.x - 128;
+        const int n4 = args.rows_load * 8;
+        int pi = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+            for (int cb = 0; cb < CB; ++cb, ++pi) {
+                const int ps = pi & 1;
+                mbar_wait(&pfull[ps], (uint32_t)(pi >> 1) & 1);
+                const float4* src = reinterpret_cast<const float4*>(patch_raw(ps));
+                float4* dst = reinterpret_cast<float4*>(patch_lo(ps));
+#pragma unroll 4
+                for (int i = (args.dbg & 4) ? n4 : t128; i < n4; i += 128) {
+                    const float4 v = src[i];
+                    float4 o;
+                    o.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                    o.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                    o.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                    o.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                    dst[i] = o;
+                }
+                fence_proxy_async();
+                mbar_arrive(&psplit[ps]);
+            }
+    } else if (warp >= 8) {
+        // ===== epilogue: thread = padded-raster position of the tile =========================================
+        const int g = (warp - 8) >> 2;
+        const int j = (warp & 3) * 32 + lane;
+        const int rr = j / PW, q = j - rr * PW;
+        const float* __restrict__ gbias = args.bias;
+        const uint32_t* __restrict__ mbits = args.mask_bits;
+        uint32_t* __restrict__ obits = args.bits_out;
+        const int jd = rr * args.W + q;                           // dense row of the staging slot
+        uint8_t* srow = staging + (size_t)g * EPI_SLOT_BYTES + (size_t)jd * 128;
+        const uint32_t swz = (uint32_t)(jd & 7);
+        uint32_t k = 0;
+        int t = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+            int img, p0, n0; bool tail;
+            tile_of(tile, img, p0, n0, tail);
+            const int acc = t % kAcc;
+            const int p = p0 + rr;
+            const bool valid = rr < args.R && q < args.W && p < args.H;
+            const int64_t m = ((int64_t)img * args.H + p) * args.W + q;
+            uint32_t mw[SUBS];
+#pragma unroll
+            for (int u = 0; u < SUBS; ++u)
+                mw[u] = (mbits && valid) ? __ldg(mbits + (int64_t)(n0 / 32 + g + 2 * u) * args.M + m) : 0xFFFFFFFFu;
+            mbar_wait(&tfull[acc], (uint32_t)(t / kAcc) & 1);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + (uint32_t)acc * kAccCols + ((uint32_t)((warp & 3) * 32) << 16);
+            uint32_t vals[SUBS][32];
+#pragma unroll
+            for (int u = 0; u < SUBS; ++u) {
+                const int c0 = (g + 2 * u) * 32;
+                uint32_t b[32], c2[32];
+                tmem_ld32_nowait(tacc + (uint32_t)c0, vals[u]);
+                tmem_ld32_nowait(tacc + (uint32_t)(BN + c0), b);
+                tmem_ld32_nowait(tacc + (uint32_t)(2 * BN + c0), c2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {                   // cross + cross2 first (both ~2^-11 of main), then + main
+                    const float x = __fadd_rn(__uint_as_float(b[i]), __uint_as_float(c2[i]));
+                    vals[u][i] = __float_as_uint(__fadd_rn(__uint_as_float(vals[u][i]), x));
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tempty[acc]);                           // accumulator drained: the MMA warps may reuse it
+#pragma unroll
+            for (int u = 0; u < SUBS; ++u, ++k) {
+                const int c0 = (g + 2 * u) * 32;
+                uint32_t (&a)[32] = vals[u];
+                mbar_wait(&slot_ready[g], k & 1);                // the previous store has read the slot
+                if (valid) {
+                    const float4* bs4 = reinterpret_cast<const float4*>(gbias + n0 + c0);
+                    const uint32_t mword = mw[u];
+                    uint32_t oword = 0;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 bv = gbias ? __ldg(bs4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        float4 v = make_float4(__uint_as_float(a[4 * c]) + bv.x, __uint_as_float(a[4 * c + 1]) + bv.y,
+                                               __uint_as_float(a[4 * c + 2]) + bv.z, __uint_as_float(a[4 * c + 3]) + bv.w);
+                        if (args.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+                        if (!((mword >> (4 * c)) & 1u)) v.x = 0.f;
+                        if (!((mword >> (4 * c + 1)) & 1u)) v.y = 0.f;
+                        if (!((mword >> (4 * c + 2)) & 1u)) v.z = 0.f;
+                        if (!((mword >> (4 * c + 3)) & 1u)) v.w = 0.f;
+                        oword |= (v.x > 0.f ? 1u : 0u) << (4 * c) | (v.y > 0.f ? 1u : 0u) << (4 * c + 1) |
+                                 (v.z > 0.f ? 1u : 0u) << (4 * c + 2) | (v.w > 0.f ? 1u : 0u) << (4 * c + 3);
+                        *reinterpret_cast<float4*>(srow + (((uint32_t)c ^ swz) << 4)) = v;
+                    }
+                    if (obits) obits[(int64_t)((n0 + c0) / 32) * args.M + m] = oword;
+                }
+                fence_proxy_async();                             // generic-proxy writes -> visible to the TMA store
+                mbar_arrive(&out_ready[g]);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // First-layer FORWARD without the patch matrix (i2v_conv_stem_fwd_rows_f32; 7x7 / stride 2 / pad 3, 64 output channels,
 // Q <= 128, W % 4 == 0).  The im2col + GEMM pair writes a 2 GB patch matrix and reads it back (1.1 ms per 256 frames for
 // 0.98 GB of tensors).  Here a tile is ONE output row (n, p): TMA stages the 7 input rows x 3 channels it needs (zero filled
@@ -2207,7 +2524,7 @@ stem_fwd_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmX); prefetch_tmap(&tmBhi); prefetch_tmap(&tmBlo); prefetch_tmap(&tmOut);
         mbar_init(bfull, 1);
@@ -2227,7 +2544,7 @@ stem_fwd_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     constexpr uint32_t kRing = 256;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_arrive_expect_tx(bfull, SF_KB * SF_B_KB);
             for (int kb = 0; kb < SF_KB; ++kb) {
                 tma_load_2d(&tmBhi, bfull, bt + (size_t)kb * SF_B_KB, kb * TC_BK, 0);
@@ -2248,7 +2565,7 @@ stem_fwd_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_tf32(64), idesc2 = umma_idesc_tf32(128);
             mbar_wait(bfull, 0);
             int t = 0, it = 0;
@@ -2555,6 +2872,25 @@ static int get_map_im2col_view(CUtensorMap* out, const float* base, int N, int H
     g_maps.emplace(key, *out);
     return I2V_OK;
 }
+// 4-D tiled map over an NHWC tensor, box {32 channels, box_w pixels, box_h rows, 1 image}, SWIZZLE_128B, zeros outside the
+// image (negative start coordinates = the convolution's padding): the input patch of the halo kernel
+static int get_map_nhwc_box(CUtensorMap* out, const float* base, int N, int H, int W, int C, int box_w, int box_h) {
+    MapKey key{base, N, H, W, C, box_w, box_h, 0, 8};
+    std::lock_guard<std::mutex> lk(g_maps_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return I2V_OK; }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+    cuuint32_t box[4] = {TC_BK, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (NHWC box) failed (%d) N=%d H=%d W=%d C=%d box=%dx%d", (int)r, N, H, W, C, box_w, box_h); return I2V_ECUDA; }
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps.emplace(key, *out);
+    return I2V_OK;
+}
 static int get_map_4d(CUtensorMap* out, const float* base, const uint64_t dims[4], const uint64_t strides_bytes[3]) {
     MapKey key{base, (int)dims[1], (int)dims[2], (int)dims[3], (int)(strides_bytes[0]), (int)(strides_bytes[1] & 0x7fffffff),
                (int)(strides_bytes[2] & 0x7fffffff), (int)(((strides_bytes[2] >> 31) << 12) | (dims[0] & 0xfff)), 4};
@@ -2705,6 +3041,57 @@ static int tc_launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmBhi, cons
     return I2V_OK;
 }
 
+// Halo kernel launch (conv3x3_halo_kernel).  Returns I2V_OK after launching, or -1 when the shape does not fit (the caller
+// falls back to the im2col-mode kernel).
+template <int BN>
+static int halo_launch(const float* src, int N, int H, int W, int C, const float* w_hi, const float* w_lo, int Cout,
+                       const float* bias, const uint32_t* mask_bits, uint32_t* bits_out, float* dst, int relu, cudaStream_t st) {
+    const int PW = W + 2;
+    if (PW > TC_BM || C % 32 != 0 || C / 32 > 16 || Cout % BN != 0) return -1;
+    const int R = TC_BM / PW;
+    const int64_t M = (int64_t)N * H * W;
+    HaloArgs a{};
+    a.bias = bias; a.mask_bits = mask_bits; a.bits_out = bits_out;
+    a.N = N; a.H = H; a.W = W; a.PW = PW; a.R = R; a.TI = (H + R - 1) / R; a.CB = C / 32; a.relu = relu;
+    a.rows_load = (R + 2) * PW;
+    a.patch_bytes = (uint32_t)(((2 * PW + 2 + TC_BM) * 128 + 1023) / 1024 * 1024);
+    a.tail_rows = H % R;
+    a.dbg = getenv("I2V_TC_HALO_DBG") ? atoi(getenv("I2V_TC_HALO_DBG")) : 0;
+    a.M = M;
+    static size_t budget = 0;
+    auto kern = conv3x3_halo_kernel<BN>;
+    if (budget == 0) {
+        int dev = 0, optin = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        const size_t b = (size_t)(optin > 0 ? optin : 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b);
+        if (e != cudaSuccess) return cuda_fail(e, "conv3x3 halo: shared memory attribute");
+        budget = b;
+    }
+    const size_t bstage = (size_t)2 * BN * 128;
+    const size_t fixed = 1024 + 4 * (size_t)a.patch_bytes + 2 * EPI_SLOT_BYTES + 512;
+    if (fixed + 2 * bstage > budget) return -1;
+    int bst = (int)((budget - fixed) / bstage);
+    if (bst > 8) bst = 8;
+    a.bstages = bst;
+    CUtensorMap tmX, tmBhi, tmBlo, tmOut, tmTail;
+    if (int r = get_map_nhwc_box(&tmX, src, N, H, W, C, PW, R + 2)) return r;
+    if (int r = get_map_2d(&tmBhi, w_hi, Cout, 9 * C, BN)) return r;
+    if (int r = get_map_2d(&tmBlo, w_lo, Cout, 9 * C, BN)) return r;
+    const int full_rows = (H < R ? H : R) * W;
+    if (int r = get_map_2d(&tmOut, dst, (int)M, Cout, full_rows)) return r;
+    tmTail = tmOut;
+    if (a.tail_rows) { if (int r = get_map_2d(&tmTail, dst, (int)M, Cout, a.tail_rows * W)) return r; }
+    const int num_n_tiles = Cout / BN;
+    const int64_t tiles = (int64_t)N * a.TI * num_n_tiles;
+    if (tiles >= (int64_t)0x7fffffff) return -1;
+    const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+    kern<<<grid, HL_THREADS, fixed + (size_t)bst * bstage, st>>>(tmX, tmBhi, tmBlo, tmOut, tmTail, a, (int)tiles, num_n_tiles);
+    I2V_LAUNCH_CHECK("i2v_conv_tc_f32 (3x3 halo)");
+    return I2V_OK;
+}
+
 // CTA-pair kernel selection ($I2V_TC_PAIR, i2v_conv_tc_set_pair_minkit): n > 0 = every tile of >= n k-steps, 0 = never,
 // -1 (default) = where it was measured to win in the attack step (profiles/r02_pair_kernel.md): convolutions that stream a
 // residual / addend through the epilogue, from 4 k-steps per tile
@@ -2756,6 +3143,21 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
     const bool epi_tma = persistent && epi_tma_on && (pr.out_s == 0 || class_tma_on) && pr.mask_src == nullptr;
     I2V_REQUIRE(epi_tma || (pr.mask_bits == nullptr && pr.bits_out == nullptr),
                 "bit masks need the TMA epilogue (dense output rows, no f32 mask source)");
+
+    // 3x3 / stride 1 / pad 1 in FP32-parity mode: every input patch delivered once (conv3x3_halo_kernel).  $I2V_TC_HALO: 1 = wherever
+    // it fits, 0 = never, default = the 64-channel tiles only, where it was measured to win in the attack step (56x56 64 -> 64:
+    // 345 us against 389 us per 256 frames; at BN = 128 its single accumulator stage loses, 271 us against 233 us)
+    static const int halo_mode = getenv("I2V_TC_HALO") ? atoi(getenv("I2V_TC_HALO")) : -1;
+    const bool halo_on = halo_mode > 0 || (halo_mode < 0 && BN == 64);   // 2 = wherever it fits, always with 64-channel tiles
+    if (halo_on && x3 && epi_tma && pr.taps_h == 3 && pr.taps_w == 3 && pr.stride == 1 && pr.lower_h == -1 && pr.lower_w == -1 &&
+        pr.P == pr.H && pr.Q == pr.W && !pr.residual && !pr.out_transposed && pr.out_s == 0 && !pr.src2 && pr.store_cols == 0 &&
+        (reinterpret_cast<uintptr_t>(pr.bias) & 15) == 0) {
+        const int r = (BN == 128 && halo_mode != 2) ? halo_launch<128>(pr.src, pr.N, pr.H, pr.W, pr.C, pr.w_hi, pr.w_lo, pr.Cout, pr.bias, pr.mask_bits,
+                                                   pr.bits_out, pr.dst, pr.relu, st)
+                                : halo_launch<64>(pr.src, pr.N, pr.H, pr.W, pr.C, pr.w_hi, pr.w_lo, pr.Cout, pr.bias, pr.mask_bits,
+                                                  pr.bits_out, pr.dst, pr.relu, st);
+        if (r != -1) return r;
+    }
 
     CUtensorMap tmA, tmBhi, tmBlo, tmOut, tmRes;
     if (im2col) { if (int r = get_map_im2col(&tmA, pr.src, pr.N, pr.H, pr.W, pr.C, pr.lower_w, pr.lower_h, pr.upper_w, pr.upper_h, pr.stride)) return r; }

@@ -14,6 +14,11 @@ extern "C" {
 int i2v_mma_probe(int N, int accs, int a_tmem, int count, int ctas, int issuers /* 1..3 concurrently issuing warps */,
                   long long* out, i2v_stream_t stream);
 
+/* Debug: D[128 x 64] = A[shift .. shift+127] B^T with a SWIZZLE_128B A descriptor whose start is shifted by `shift_rows`
+ * 128-byte rows (a = [256][32], b = [64][32], out = [128][64] device f32); base_offset_mode 1 also sets the descriptor's
+ * base-offset field to (start >> 7) & 7.  tools/mma_shift_probe.py reports which rows the tensor core actually read.  */
+int i2v_mma_shift_probe(int shift_rows, int base_offset_mode, const float* a, const float* b, float* out, i2v_stream_t stream);
+
 /* Debug: subsequent tensor-core launches make CTA 0 stamp clock64() at 8 pipeline points of each of its first
  * `tiles` tiles into device_buf[tiles][8] (see TcArgs::trace in csrc/conv_tc.cu); NULL switches it off.     */
 int i2v_conv_tc_set_trace(unsigned long long* device_buf, int tiles);

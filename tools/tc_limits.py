@@ -17,10 +17,13 @@ from tc_probe import LAYERS, timeit
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=256)
+    ap.add_argument("--only", default="", help="substring filter on the layer names")
     args = ap.parse_args()
     dev = "cuda"
-    out = {"dbg": int(os.environ.get("I2V_TC_PAIR_DBG", "0")), "pair": os.environ.get("I2V_TC_PAIR", "-1"), "frames": args.frames, "us": {}}
+    out = {"dbg": int(os.environ.get("I2V_TC_PAIR_DBG", "0")), "halo": os.environ.get("I2V_TC_HALO", ""), "halo_dbg": os.environ.get("I2V_TC_HALO_DBG", ""), "pair": os.environ.get("I2V_TC_PAIR", "-1"), "frames": args.frames, "us": {}}
     for name, H, Cin, Cout, k, s, p, cnt in LAYERS:
+        if args.only not in name:
+            continue
         P = (H + 2 * p - k) // s + 1
         g = torch.Generator().manual_seed(1)
         w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
