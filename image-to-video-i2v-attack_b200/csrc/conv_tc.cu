@@ -109,6 +109,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
                  : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// Non-blocking poll: try_wait may SUSPEND the thread up to a system-dependent time limit when the phase is not complete, which
+// a thread that has other work to issue (the epilogue-TMA issuer polling two groups, the producer polling a patch slot between
+// weight stages) cannot afford.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 // Watchdog: ~4 s at 2 GHz.  A protocol bug traps (CUDA error on the host) instead of hanging the box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
@@ -127,6 +136,9 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
     return pred != 0;
 }
+// advance a ring position: `it % stages` / `it / stages` with a run-time divisor cost two emulated integer divisions (~200
+// dependent cycles) per k-step on the single thread that paces the pipeline
+__device__ __forceinline__ void ring_next(int& st, uint32_t& ph, int n) { if (++st == n) { st = 0; ph ^= 1u; } }
 __device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -321,11 +333,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 base_w = q * args.stride + args.lower_w;
             }
             int it = 0;
+            int st = 0; uint32_t ph = 0;               // ring position of k-step `it` (no division in the loop)
             for (int r = 0; r < args.taps_h; ++r)
                 for (int s = 0; s < args.taps_w; ++s)
-                    for (int cb = 0; cb < args.cblocks; ++cb, ++it) {
-                        const int st = it % stages;
-                        const uint32_t ph = (uint32_t)(it / stages) & 1;
+                    for (int cb = 0; cb < args.cblocks; ++cb, ++it, ring_next(st, ph, stages)) {
                         mbar_wait(&empty_bar[st], ph ^ 1);
                         mbar_arrive_expect_tx(&full_bar[st], TC_A_BYTES + L::B_BYTES * (X3 ? 2 : 1));
                         if (IM2COL) tma_load_im2col_4d(&tmA, &full_bar[st], stage_a(st), cb * TC_BK, base_w, base_h, img, (uint16_t)s, (uint16_t)r);
@@ -339,9 +350,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===== MMA issuer =======================================================================
         if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_tf32(BN);
-            for (int it = 0; it < kiters; ++it) {
-                const int st = it % stages;
-                const uint32_t ph = (uint32_t)(it / stages) & 1;
+            int st = 0; uint32_t ph = 0;
+            for (int it = 0; it < kiters; ++it, ring_next(st, ph, stages)) {
                 mbar_wait(&full_bar[st], ph);
                 if (X3) mbar_wait(&split_bar[st], ph);
                 tc_fence_after();
@@ -365,9 +375,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int t = threadIdx.x - 128;           // 0..127
         if (X3) {
             // ===== A split: A_lo = a - trunc_tf32(a), element-wise on the swizzled tile ==============
-            for (int it = 0; it < kiters; ++it) {
-                const int st = it % stages;
-                const uint32_t ph = (uint32_t)(it / stages) & 1;
+            int st = 0; uint32_t ph = 0;
+            for (int it = 0; it < kiters; ++it, ring_next(st, ph, stages)) {
                 mbar_wait(&full_bar[st], ph);
                 const float4* src = reinterpret_cast<const float4*>(stage_a(st));
                 float4* dst = reinterpret_cast<float4*>(stage_alo(st));
@@ -556,6 +565,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         // ===== TMA producer: runs ahead across tiles, bounded only by the smem ring ===================
         if (elect_one()) {
             int it = 0, tno = 0;
+            int st = 0; uint32_t ph = 0;               // ring position of k-step `it` (no division in the loop)
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tno) {
                 const int m_tile = tile / num_n_tiles, n_tile = tile - m_tile * num_n_tiles;
                 const int64_t m0 = (int64_t)m_tile * TC_BM;
@@ -579,9 +589,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 }
                 for (int r = 0; r < args.taps_h; ++r)
                     for (int s = 0; s < args.taps_w; ++s)
-                        for (int cb = 0; cb < args.cblocks; ++cb, ++it) {
-                            const int st = it % stages;
-                            const uint32_t ph = (uint32_t)(it / stages) & 1;
+                        for (int cb = 0; cb < args.cblocks; ++cb, ++it, ring_next(st, ph, stages)) {
                             mbar_wait(&empty_bar[st], ph ^ 1);
                             if ((r | s | cb) == 0) TC_TRACE(0, tno);
                             // (measured: deriving B_lo on the fly in the split warps instead of loading it — 25-33 % fewer TMA
@@ -614,6 +622,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             constexpr uint32_t idesc = umma_idesc_tf32(BN);
             constexpr uint32_t idesc2 = umma_idesc_tf32(2 * BN);
             int it = 0, t = 0;
+            int st = 0; uint32_t ph = 0;               // ring position of k-step `it` (no division in the loop)
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
                 const int acc = t % kAcc;
                 const uint32_t aph = (uint32_t)(t / kAcc) & 1;
@@ -621,9 +630,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 tc_fence_after();
                 TC_TRACE(2, t);
                 const uint32_t d0 = tmem_base + (uint32_t)acc * kAccCols;
-                for (int kb = 0; kb < kiters; ++kb, ++it) {
-                    const int st = it % stages;
-                    const uint32_t ph = (uint32_t)(it / stages) & 1;
+                for (int kb = 0; kb < kiters; ++kb, ++it, ring_next(st, ph, stages)) {
                     mbar_wait(&full_bar[st], ph);
                     if (X3 && !ALO_TMEM) mbar_wait(&split_bar[st], ph);
                     tc_fence_after();
@@ -654,15 +661,14 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_tf32(BN);
             int it = 0, t = 0;
+            int st = 0; uint32_t ph = 0;               // ring position of k-step `it` (no division in the loop)
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
                 const int acc = t % kAcc;
                 const uint32_t aph = (uint32_t)(t / kAcc) & 1;
                 mbar_wait(&tempty_bar[acc], aph ^ 1);
                 tc_fence_after();
                 const uint32_t d2 = tmem_base + (uint32_t)acc * kAccCols + 2u * BN;
-                for (int kb = 0; kb < kiters; ++kb, ++it) {
-                    const int st = it % stages;
-                    const uint32_t ph = (uint32_t)(it / stages) & 1;
+                for (int kb = 0; kb < kiters; ++kb, ++it, ring_next(st, ph, stages)) {
                     mbar_wait(&full_bar[st], ph);               // b_hi landed
                     mbar_wait(&split_bar[st], ph);              // a_lo of this k-step is in its ring slot
                     tc_fence_after();
@@ -724,7 +730,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     const uint32_t k = kdone[g];
                     if (k >= total) continue;
                     const uint32_t s = k % ns, ph = (k / ns) & 1;
-                    if (!mbar_try_wait(&out_ready[g * 2 + s], ph)) continue;
+                    if (!mbar_test_wait(&out_ready[g * 2 + s], ph)) continue;
                     int col, row;
                     coords(g, k, col, row);
                     const uint8_t* slot = staging + ((size_t)g * ns + s) * EPI_SLOT_BYTES;
@@ -759,6 +765,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (X3) {
             const int t128 = threadIdx.x - 128;
             int it = 0, tno = 0;
+            int st = 0; uint32_t ph = 0;               // ring position of k-step `it` (no division in the loop)
             if (ALO_TMEM) {
                 // A_lo goes to TENSOR MEMORY instead of shared memory: thread = tile row (TMEM lane), 32 k-values of its
                 // row read from the swizzled A tile, lo parts written with tcgen05.st into a ring of 32-column slots that
@@ -769,9 +776,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 const uint32_t swz = (uint32_t)(row & 7);
                 const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kAloBase;
                 for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tno) {
-                    for (int kb = 0; kb < kiters; ++kb, ++it) {
-                        const int st = it % stages;
-                        const uint32_t ph = (uint32_t)(it / stages) & 1;
+                    for (int kb = 0; kb < kiters; ++kb, ++it, ring_next(st, ph, stages)) {
                         mbar_wait(&full_bar[st], ph);
                         if (args.dbg & 4) { mbar_arrive(&split_bar[st]); continue; }     // timing experiment: no split work
                         const uint8_t* arow = stage_a(st) + (size_t)row * 128;
@@ -793,9 +798,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 }
             } else {
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tno) {
-                for (int kb = 0; kb < kiters; ++kb, ++it) {
-                    const int st = it % stages;
-                    const uint32_t ph = (uint32_t)(it / stages) & 1;
+                for (int kb = 0; kb < kiters; ++kb, ++it, ring_next(st, ph, stages)) {
                     mbar_wait(&full_bar[st], ph);
                     const float4* src = reinterpret_cast<const float4*>(stage_a(st));
                     float4* dst = reinterpret_cast<float4*>(stage_alo(st));
@@ -1249,6 +1252,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // ===== TMA producer (both CTAs): own A tile -> afull (local); own half of the weight rows -> full (leader) =========
         if (elect_one()) {
             int it = 0, tno = 0;
+            int st = 0; uint32_t ph = 0;               // ring position of k-step `it` (no division in the loop)
             for (int pt = pid; pt < num_ptiles; pt += npairs, ++tno) {
                 const int pm = pt / num_n_tiles, n_tile = pt - pm * num_n_tiles;
                 const int m_tile = 2 * pm + (int)rank;
@@ -1265,9 +1269,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 for (int r = 0; r < args.taps_h; ++r)
                     for (int s = 0; s < args.taps_w; ++s)
-                        for (int cb = 0; cb < args.cblocks; ++cb, ++it) {
-                            const int st = it % stages;
-                            const uint32_t ph = (uint32_t)(it / stages) & 1;
+                        for (int cb = 0; cb < args.cblocks; ++cb, ++it, ring_next(st, ph, stages)) {
                             mbar_wait(&empty_bar[st], ph ^ 1);
                             if ((r | s | cb) == 0) TC_TRACE(0, tno);
                             mbar_arrive_expect_tx(&afull_bar[st], TC_A_BYTES);
@@ -1286,6 +1288,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (leader && elect_one()) {
             constexpr uint32_t idesc2 = umma2_idesc_tf32(2 * BN);
             int it = 0, t = 0;
+            int st = 0; uint32_t ph = 0;               // ring position of k-step `it` (no division in the loop)
             for (int pt = pid; pt < num_ptiles; pt += npairs, ++t) {
                 const int acc = t % kAcc;
                 const uint32_t aph = (uint32_t)(t / kAcc) & 1;
@@ -1293,9 +1296,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 tc_fence_after();
                 TC_TRACE(2, t);
                 const uint32_t d0 = tmem_base + (uint32_t)acc * kAccCols;
-                for (int kb = 0; kb < kiters; ++kb, ++it) {
-                    const int st = it % stages;
-                    const uint32_t ph = (uint32_t)(it / stages) & 1;
+                for (int kb = 0; kb < kiters; ++kb, ++it, ring_next(st, ph, stages)) {
                     mbar_wait_cluster(&full_bar[st], ph);        // the weight rows of both CTAs
                     mbar_wait(&afull_bar[st], ph);               // this CTA's a_hi
                     mbar_wait_cluster(&split_bar[st], ph);       // the peer's a_hi (its split threads saw it land)
@@ -1317,15 +1318,14 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (leader && elect_one()) {
             constexpr uint32_t idesc = umma2_idesc_tf32(BN);
             int it = 0, t = 0;
+            int st = 0; uint32_t ph = 0;               // ring position of k-step `it` (no division in the loop)
             for (int pt = pid; pt < num_ptiles; pt += npairs, ++t) {
                 const int acc = t % kAcc;
                 const uint32_t aph = (uint32_t)(t / kAcc) & 1;
                 mbar_wait_cluster(&tempty_bar[acc], aph ^ 1);
                 tc_fence_after();
                 const uint32_t d2 = tmem_base + (uint32_t)acc * kAccCols + 2u * BN;
-                for (int kb = 0; kb < kiters; ++kb, ++it) {
-                    const int st = it % stages;
-                    const uint32_t ph = (uint32_t)(it / stages) & 1;
+                for (int kb = 0; kb < kiters; ++kb, ++it, ring_next(st, ph, stages)) {
                     mbar_wait_cluster(&full_bar[st], ph);
                     mbar_wait_cluster(&split_bar[st], ph);       // a_lo of both CTAs is in its ring slot
                     tc_fence_after();
@@ -1374,7 +1374,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const uint32_t k = kdone[g];
                     if (k >= total) continue;
                     const uint32_t s = k % ns, ph = (k / ns) & 1;
-                    if (!mbar_try_wait(&out_ready[g * 2 + s], ph)) continue;
+                    if (!mbar_test_wait(&out_ready[g * 2 + s], ph)) continue;
                     int col, row;
                     coords(g, k, col, row);
                     const uint8_t* slot = staging + ((size_t)g * ns + s) * EPI_SLOT_BYTES;
@@ -1396,10 +1396,9 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t swz = (uint32_t)(row & 7);
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kAloBase;
         int it = 0, tno = 0;
+        int st = 0; uint32_t ph = 0;               // ring position of k-step `it` (no division in the loop)
         for (int pt = pid; pt < num_ptiles; pt += npairs, ++tno) {
-            for (int kb = 0; kb < kiters; ++kb, ++it) {
-                const int st = it % stages;
-                const uint32_t ph = (uint32_t)(it / stages) & 1;
+            for (int kb = 0; kb < kiters; ++kb, ++it, ring_next(st, ph, stages)) {
                 mbar_wait(&afull_bar[st], ph);
                 if (args.dbg & 4) { mbar_arrive_leader(&split_bar[st]); continue; }      // timing experiment: no split work
                 const uint8_t* arow = stage_a(st) + (size_t)row * 128;
@@ -2200,16 +2199,22 @@ struct HaloArgs {
     int bstages;
     int tail_rows;               // H % R: rows of an image's last tile when it is short (0: all tiles full)
     int dbg;                     // timing experiments ($I2V_TC_HALO_DBG, wrong results): bit 0 skips the main MMAs, bit 1 the a_lo MMAs, bit 2 the split, bit 3 the weight loads
+    unsigned long long* trace;   // i2v_conv_tc_set_trace: [tile][0] first patch requested, [1] last weight stage requested, [2] issuer owns the
+    int trace_tiles;             // accumulator, [3] first patch landed, [4] last MMA issued, [5] epilogue sees the accumulator, [6] epilogue done, [7] split done
     int64_t M;                   // N * H * W
 };
 
-template <int BN>
+template <int BN, bool DUAL>
 __global__ void __launch_bounds__(HL_THREADS, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBhi,
                     const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmOut,
                     const __grid_constant__ CUtensorMap tmOutTail, const HaloArgs args, const int num_tiles, const int num_n_tiles) {
-    constexpr uint32_t kAccCols = 3 * BN;                       // [main | cross | cross2]
-    constexpr int kAcc = 384 / kAccCols;                        // 2 accumulator stages at BN = 64, 1 at BN = 128
+    // DUAL: two issuers, [main | cross | cross2], 2 accumulator stages at BN = 64 but only 1 at BN = 128.
+    // !DUAL: ONE issuer (behind elect.sync an issuer keeps the tensor pipe fed on its own) adds a_lo x b_hi into `cross` after
+    // a_hi x [b_hi | b_lo]: [main | cross], 2 stages at either width (512 columns at BN = 128).
+    constexpr uint32_t kAccCols = (DUAL ? 3 : 2) * BN;
+    constexpr int kAcc = DUAL ? 384 / kAccCols : 2;
+    constexpr uint32_t kIssuers = DUAL ? 2 : 1;
     constexpr uint32_t kBStage = 2u * BN * 128u;                // [b_hi | b_lo], 32 k-values per row
     constexpr int SUBS = BN / 64;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -2238,9 +2243,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmX); prefetch_tmap(&tmBhi); prefetch_tmap(&tmBlo); prefetch_tmap(&tmOut); prefetch_tmap(&tmOutTail);
-        for (int i = 0; i < 2; ++i) { mbar_init(&pfull[i], 1); mbar_init(&pempty[i], 2); mbar_init(&psplit[i], 128); }
-        for (int i = 0; i < bstages; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 2); }
-        for (int i = 0; i < kAcc; ++i) { mbar_init(&tfull[i], 2); mbar_init(&tempty[i], TC2_EPI_THREADS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&pfull[i], 1); mbar_init(&pempty[i], kIssuers); mbar_init(&psplit[i], 128); }
+        for (int i = 0; i < bstages; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], kIssuers); }
+        for (int i = 0; i < kAcc; ++i) { mbar_init(&tfull[i], kIssuers); mbar_init(&tempty[i], TC2_EPI_THREADS); }
         for (int i = 0; i < 2; ++i) { mbar_init(&out_ready[i], TC2_EPI_THREADS / 2); mbar_init(&slot_ready[i], 1); }
         fence_barrier_init();
     }
@@ -2269,12 +2274,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         // slot frees on the MMAs of block k - 2, whose weights are already in flight: no deadlock); the patch of block k + 1 is
         // requested between the weight stages of block k the moment its slot frees (try_wait).
         if (elect_one()) {
-            int bi = 0, wi = 0;
+            int bi = 0, wi = 0, st = 0;
+            uint32_t ph = 0;
             int ptile = blockIdx.x, pcb = 0, pi = 0;             // the next patch to request
             auto issue_patch = [&]() {
                 int img, p0, n0; bool tail;
                 tile_of(ptile, img, p0, n0, tail);
                 const int ps = pi & 1;
+                if (pcb == 0) TC_TRACE(0, (ptile - (int)blockIdx.x) / (int)gridDim.x);
                 mbar_arrive_expect_tx(&pfull[ps], (uint32_t)args.rows_load * 128u);
                 tma_load_4d(&tmX, &pfull[ps], patch_raw(ps), pcb * TC_BK, -1, p0 - 1, img);
                 ++pi;
@@ -2288,10 +2295,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                         mbar_wait(&pempty[pi & 1], ((uint32_t)(pi >> 1) & 1) ^ 1);
                         issue_patch();
                     }
-                    for (int tap = 0; tap < 9; ++tap, ++bi) {
-                        if (pi == wi + 1 && ptile < num_tiles && mbar_try_wait(&pempty[pi & 1], ((uint32_t)(pi >> 1) & 1) ^ 1)) issue_patch();
-                        const int st = bi % bstages;
-                        mbar_wait(&bempty[st], ((uint32_t)(bi / bstages) & 1) ^ 1);
+                    for (int tap = 0; tap < 9; ++tap, ++bi, ring_next(st, ph, bstages)) {
+                        if (pi == wi + 1 && ptile < num_tiles && mbar_test_wait(&pempty[pi & 1], ((uint32_t)(pi >> 1) & 1) ^ 1)) issue_patch();
+                        mbar_wait(&bempty[st], ph ^ 1);
                         if (args.dbg & 8) { mbar_arrive(&bfull[st]); continue; }
                         mbar_arrive_expect_tx(&bfull[st], kBStage);
                         const int kcol = (tap * CB + cb) * TC_BK;
@@ -2299,29 +2305,77 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                         tma_load_2d(&tmBlo, &bfull[st], bstage(st) + (size_t)BN * 128, kcol, n0);
                     }
                 }
+                TC_TRACE(1, (tile - (int)blockIdx.x) / (int)gridDim.x);
             }
         }
-    } else if (warp == 1 || warp == 2) {
+    } else if (!DUAL && warp == 1) {
+        // ===== the MMA issuer: [main | cross] += a x [b_hi | b_lo], then cross += a_lo x b_hi =================
+        if (elect_one()) {
+            constexpr uint32_t idesc2 = umma_idesc_tf32(2 * BN), idesc1 = umma_idesc_tf32(BN);
+            int pi = 0, bi = 0, t = 0, st = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
+                const int acc = t % kAcc;
+                mbar_wait(&tempty[acc], ((uint32_t)(t / kAcc) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)acc * kAccCols;
+                TC_TRACE(2, t);
+                for (int cb = 0; cb < CB; ++cb, ++pi) {
+                    const int ps = pi & 1;
+                    const uint32_t pph = (uint32_t)(pi >> 1) & 1;
+                    mbar_wait(&pfull[ps], pph);
+                    tc_fence_after();
+                    if (cb == 0) TC_TRACE(3, t);
+                    const uint32_t araw = smem_u32(patch_raw(ps)), alo = smem_u32(patch_lo(ps));
+                    for (int tap = 0; tap < 9; ++tap, ++bi, ring_next(st, ph, bstages)) {
+                        mbar_wait(&bfull[st], ph);
+                        tc_fence_after();
+                        const int r = tap / 3, sx = tap - 3 * r;
+                        const uint32_t shift = (uint32_t)(r * PW + sx) * 128u;                          // the tap = a row shift
+                        const uint64_t da = umma_desc_sw128(araw + shift), dl = umma_desc_sw128(alo + shift);
+                        const uint64_t db = umma_desc_sw128(smem_u32(bstage(st)));
+                        if (!(args.dbg & 1)) {
+#pragma unroll
+                            for (int kk = 0; kk < TC_BK / 8; ++kk)
+                                umma_tf32(d, da + 2 * kk, db + 2 * kk, idesc2, (cb | tap | kk) ? 1u : 0u);
+                        }
+                        if (tap == 0) { mbar_wait(&psplit[ps], pph); tc_fence_after(); }
+                        if (!(args.dbg & 2)) {
+#pragma unroll
+                            for (int kk = 0; kk < TC_BK / 8; ++kk)
+                                umma_tf32(d + BN, dl + 2 * kk, db + 2 * kk, idesc1, 1u);
+                        }
+                        if (args.dbg & 16) mbar_arrive(&bempty[st]); else umma_commit(&bempty[st]);
+                    }
+                    umma_commit(&pempty[ps]);
+                }
+                TC_TRACE(4, t);
+                umma_commit(&tfull[acc]);
+            }
+        }
+    } else if (DUAL && (warp == 1 || warp == 2)) {
         // ===== MMA issuers: warp 1  [main | cross] += a x [b_hi | b_lo];  warp 2  cross2 += a_lo x b_hi ============
         if (elect_one()) {
             const bool lo_issuer = warp == 2;
             const uint32_t idesc = lo_issuer ? umma_idesc_tf32(BN) : umma_idesc_tf32(2 * BN);
-            int pi = 0, bi = 0, t = 0;
+            int pi = 0, bi = 0, t = 0, st = 0;
+            uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
                 const int acc = t % kAcc;
                 mbar_wait(&tempty[acc], ((uint32_t)(t / kAcc) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d = tmem_base + (uint32_t)acc * kAccCols + (lo_issuer ? 2u * BN : 0u);
+                if (!lo_issuer) TC_TRACE(2, t);
                 for (int cb = 0; cb < CB; ++cb, ++pi) {
                     const int ps = pi & 1;
                     const uint32_t pph = (uint32_t)(pi >> 1) & 1;
                     mbar_wait(&pfull[ps], pph);
                     if (lo_issuer) mbar_wait(&psplit[ps], pph);
                     tc_fence_after();
+                    if (!lo_issuer && cb == 0) TC_TRACE(3, t);
                     const uint32_t abase = smem_u32(lo_issuer ? patch_lo(ps) : patch_raw(ps));
-                    for (int tap = 0; tap < 9; ++tap, ++bi) {
-                        const int st = bi % bstages;
-                        mbar_wait(&bfull[st], (uint32_t)(bi / bstages) & 1);
+                    for (int tap = 0; tap < 9; ++tap, ++bi, ring_next(st, ph, bstages)) {
+                        mbar_wait(&bfull[st], ph);
                         tc_fence_after();
                         const int r = tap / 3, sx = tap - 3 * r;
                         const uint64_t da = umma_desc_sw128(abase + (uint32_t)(r * PW + sx) * 128u);    // the tap = a row shift
@@ -2335,6 +2389,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     }
                     umma_commit(&pempty[ps]);
                 }
+                if (!lo_issuer) TC_TRACE(4, t);
                 umma_commit(&tfull[acc]);
             }
         }
@@ -2351,7 +2406,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 for (int g = 0; g < 2; ++g) {
                     const uint32_t k = kdone[g];
                     if (k >= total) continue;
-                    if (!mbar_try_wait(&out_ready[g], k & 1)) continue;
+                    if (!((args.dbg & 32) ? mbar_try_wait(&out_ready[g], k & 1) : mbar_test_wait(&out_ready[g], k & 1))) continue;
                     const int tile = (int)blockIdx.x + (int)(k / SUBS) * (int)gridDim.x;
                     int img, p0, n0; bool tail;
                     tile_of(tile, img, p0, n0, tail);
@@ -2370,8 +2425,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         // ===== split: a_lo patch = a - tf32(a), element-wise at the same (swizzled) offsets, once per patch ============
         const int t128 = threadIdx.x - 128;
         const int n4 = args.rows_load * 8;
-        int pi = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+        int pi = 0, t = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t)
             for (int cb = 0; cb < CB; ++cb, ++pi) {
                 const int ps = pi & 1;
                 mbar_wait(&pfull[ps], (uint32_t)(pi >> 1) & 1);
@@ -2389,6 +2444,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 }
                 fence_proxy_async();
                 mbar_arrive(&psplit[ps]);
+                if (t128 == 0 && cb == CB - 1) TC_TRACE(7, t);
             }
     } else if (warp >= 8) {
         // ===== epilogue: thread = padded-raster position of the tile =========================================
@@ -2416,20 +2472,29 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 mw[u] = (mbits && valid) ? __ldg(mbits + (int64_t)(n0 / 32 + g + 2 * u) * args.M + m) : 0xFFFFFFFFu;
             mbar_wait(&tfull[acc], (uint32_t)(t / kAcc) & 1);
             tc_fence_after();
+            if (threadIdx.x == 256) TC_TRACE(5, t);
             const uint32_t tacc = tmem_base + (uint32_t)acc * kAccCols + ((uint32_t)((warp & 3) * 32) << 16);
             uint32_t vals[SUBS][32];
 #pragma unroll
             for (int u = 0; u < SUBS; ++u) {
                 const int c0 = (g + 2 * u) * 32;
-                uint32_t b[32], c2[32];
+                uint32_t b[32];
                 tmem_ld32_nowait(tacc + (uint32_t)c0, vals[u]);
                 tmem_ld32_nowait(tacc + (uint32_t)(BN + c0), b);
-                tmem_ld32_nowait(tacc + (uint32_t)(2 * BN + c0), c2);
-                tmem_ld_wait();
+                if (DUAL) {
+                    uint32_t c2[32];
+                    tmem_ld32_nowait(tacc + (uint32_t)(2 * BN + c0), c2);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {                   // cross + cross2 first (both ~2^-11 of main), then + main
-                    const float x = __fadd_rn(__uint_as_float(b[i]), __uint_as_float(c2[i]));
-                    vals[u][i] = __float_as_uint(__fadd_rn(__uint_as_float(vals[u][i]), x));
+                    for (int i = 0; i < 32; ++i) {               // cross + cross2 first (both ~2^-11 of main), then + main
+                        const float x = __fadd_rn(__uint_as_float(b[i]), __uint_as_float(c2[i]));
+                        vals[u][i] = __float_as_uint(__fadd_rn(__uint_as_float(vals[u][i]), x));
+                    }
+                } else {
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        vals[u][i] = __float_as_uint(__fadd_rn(__uint_as_float(vals[u][i]), __uint_as_float(b[i])));
                 }
             }
             tc_fence_before();
@@ -2462,6 +2527,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 fence_proxy_async();                             // generic-proxy writes -> visible to the TMA store
                 mbar_arrive(&out_ready[g]);
             }
+            if (threadIdx.x == 256) TC_TRACE(6, t);
         }
     }
 
@@ -3041,9 +3107,11 @@ static int tc_launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmBhi, cons
     return I2V_OK;
 }
 
+static unsigned long long* g_trace = nullptr;
+static int g_trace_tiles = 0;
 // Halo kernel launch (conv3x3_halo_kernel).  Returns I2V_OK after launching, or -1 when the shape does not fit (the caller
 // falls back to the im2col-mode kernel).
-template <int BN>
+template <int BN, bool DUAL>
 static int halo_launch(const float* src, int N, int H, int W, int C, const float* w_hi, const float* w_lo, int Cout,
                        const float* bias, const uint32_t* mask_bits, uint32_t* bits_out, float* dst, int relu, cudaStream_t st) {
     const int PW = W + 2;
@@ -3057,9 +3125,10 @@ static int halo_launch(const float* src, int N, int H, int W, int C, const float
     a.patch_bytes = (uint32_t)(((2 * PW + 2 + TC_BM) * 128 + 1023) / 1024 * 1024);
     a.tail_rows = H % R;
     a.dbg = getenv("I2V_TC_HALO_DBG") ? atoi(getenv("I2V_TC_HALO_DBG")) : 0;
+    a.trace = g_trace; a.trace_tiles = g_trace_tiles;
     a.M = M;
     static size_t budget = 0;
-    auto kern = conv3x3_halo_kernel<BN>;
+    auto kern = conv3x3_halo_kernel<BN, DUAL>;
     if (budget == 0) {
         int dev = 0, optin = 0;
         cudaGetDevice(&dev);
@@ -3074,6 +3143,7 @@ static int halo_launch(const float* src, int N, int H, int W, int C, const float
     if (fixed + 2 * bstage > budget) return -1;
     int bst = (int)((budget - fixed) / bstage);
     if (bst > 8) bst = 8;
+    if (getenv("I2V_TC_HALO_BSTAGES") && atoi(getenv("I2V_TC_HALO_BSTAGES")) >= 1 && atoi(getenv("I2V_TC_HALO_BSTAGES")) < bst) bst = atoi(getenv("I2V_TC_HALO_BSTAGES"));
     a.bstages = bst;
     CUtensorMap tmX, tmBhi, tmBlo, tmOut, tmTail;
     if (int r = get_map_nhwc_box(&tmX, src, N, H, W, C, PW, R + 2)) return r;
@@ -3101,8 +3171,6 @@ static int pair_min_ksteps() {
     return g_pair_minkit;
 }
 
-static unsigned long long* g_trace = nullptr;
-static int g_trace_tiles = 0;
 
 // Common driver: `src` [N,H,W,C] is the gathered tensor, GEMM rows are the (img,p,q) grid, K = taps x C.
 struct TcProblem {
@@ -3146,16 +3214,22 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
 
     // 3x3 / stride 1 / pad 1 in FP32-parity mode: every input patch delivered once (conv3x3_halo_kernel).  $I2V_TC_HALO: 1 = wherever
     // it fits, 0 = never, default = the 64-channel tiles only, where it was measured to win in the attack step (56x56 64 -> 64:
-    // 345 us against 389 us per 256 frames; at BN = 128 its single accumulator stage loses, 271 us against 233 us)
+    // 325 us against 382 us per 256 frames = 88 % of the measured TF32 GEMM rate counting issued MMAs; at BN = 128 its single
+    // accumulator stage and two-stage weight ring lose, 255 us against 233 us)
     static const int halo_mode = getenv("I2V_TC_HALO") ? atoi(getenv("I2V_TC_HALO")) : -1;
     const bool halo_on = halo_mode > 0 || (halo_mode < 0 && BN == 64);   // 2 = wherever it fits, always with 64-channel tiles
     if (halo_on && x3 && epi_tma && pr.taps_h == 3 && pr.taps_w == 3 && pr.stride == 1 && pr.lower_h == -1 && pr.lower_w == -1 &&
         pr.P == pr.H && pr.Q == pr.W && !pr.residual && !pr.out_transposed && pr.out_s == 0 && !pr.src2 && pr.store_cols == 0 &&
         (reinterpret_cast<uintptr_t>(pr.bias) & 15) == 0) {
-        const int r = (BN == 128 && halo_mode != 2) ? halo_launch<128>(pr.src, pr.N, pr.H, pr.W, pr.C, pr.w_hi, pr.w_lo, pr.Cout, pr.bias, pr.mask_bits,
-                                                   pr.bits_out, pr.dst, pr.relu, st)
-                                : halo_launch<64>(pr.src, pr.N, pr.H, pr.W, pr.C, pr.w_hi, pr.w_lo, pr.Cout, pr.bias, pr.mask_bits,
-                                                  pr.bits_out, pr.dst, pr.relu, st);
+        // two issuers and three accumulators (1 stage at BN = 128); $I2V_TC_HALO_DUAL=0: one issuer, two stages (measured slower:
+        // 339 against 294 us at 56x56 64->64)
+        static const bool halo_dual = !(getenv("I2V_TC_HALO_DUAL") && atoi(getenv("I2V_TC_HALO_DUAL")) == 0);
+        const bool wide = BN == 128 && halo_mode != 2;
+#define I2V_HALO_CALL(bn, dual) halo_launch<bn, dual>(pr.src, pr.N, pr.H, pr.W, pr.C, pr.w_hi, pr.w_lo, pr.Cout, pr.bias, pr.mask_bits, \
+                                                       pr.bits_out, pr.dst, pr.relu, st)
+        const int r = wide ? (halo_dual ? I2V_HALO_CALL(128, true) : I2V_HALO_CALL(128, false))
+                           : (halo_dual ? I2V_HALO_CALL(64, true) : I2V_HALO_CALL(64, false));
+#undef I2V_HALO_CALL
         if (r != -1) return r;
     }
 
