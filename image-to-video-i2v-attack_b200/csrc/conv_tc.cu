@@ -2550,7 +2550,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 // epilogue, output through two swizzled staging slots and TMA stores whose box is exactly the Q rows of the tile.
 // HBM traffic = the image once + the output once.
 // ---------------------------------------------------------------------------------------------
-constexpr int SF_THREADS = 384;          // warp 0 producer, 1 MMA issuer, 2 TMEM allocator, 4-7 assemble, 8-11 epilogue
+constexpr int SF_THREADS = 512;          // warp 0 producer, 1 MMA issuer, 2 TMEM allocator, 4-7 and 12-15 assemble (alternate k-blocks), 8-11 epilogue
 constexpr int SF_KB = 5;                 // k-blocks of 32 taps
 constexpr int SF_ASLOTS = 4;             // ring of 16 KB A k-block slots (and of 32-column A_lo slots in tensor memory)
 constexpr int SF_ISTAGES = 2;            // staged input rows
@@ -2594,7 +2594,7 @@ stem_fwd_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmX); prefetch_tmap(&tmBhi); prefetch_tmap(&tmBlo); prefetch_tmap(&tmOut);
         mbar_init(bfull, 1);
-        for (int s = 0; s < SF_ISTAGES; ++s) { mbar_init(&ifull[s], 1); mbar_init(&iempty[s], 4); }
+        for (int s = 0; s < SF_ISTAGES; ++s) { mbar_init(&ifull[s], 1); mbar_init(&iempty[s], 8); }
         for (int s = 0; s < SF_ASLOTS; ++s) { mbar_init(&afull[s], 4); mbar_init(&aempty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
         fence_barrier_init();
@@ -2658,9 +2658,13 @@ stem_fwd_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 umma_commit(&tfull[acc]);
             }
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if ((warp >= 4 && warp < 8) || warp >= 12) {
         // ===== assemble: thread = output pixel q; patch value k = (c,r,s) is staged[c][r][2q + s] ===========================
-        const int row = threadIdx.x - 128;
+        // Two groups of four warps (one warp per TMEM lane quarter each) take alternate k-blocks: an assemble warp's k-block is a
+        // chain of dependent latencies (32 LDS, the split, 8 STS.128, tcgen05.st + wait, two fences, the arrive), and with one
+        // group that chain, not the tensor pipe, set the 2.8 us per output row.
+        const int group = warp >= 12 ? 1 : 0;
+        const int row = (warp & 3) * 32 + lane;
         const int qq = row < args.Q ? row : args.Q - 1;           // junk rows repeat the last pixel (never stored)
         const uint32_t swz = (uint32_t)(row & 7);
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kRing;
@@ -2672,6 +2676,7 @@ stem_fwd_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             const float* in = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(inrows) + (size_t)st * in_stride) + 2 * qq + 1;   // column 2q - 3 + s -> staged 2q + s + 1
 #pragma unroll
             for (int kb = 0; kb < SF_KB; ++kb, ++it) {
+                if ((it & 1) != group) continue;
                 const int sl = it % SF_ASLOTS;
                 const uint32_t ph = (uint32_t)(it / SF_ASLOTS) & 1;
                 mbar_wait(&aempty[sl], ph ^ 1);
