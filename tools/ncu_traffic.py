@@ -10,7 +10,10 @@ import json
 import re
 import sys
 
-FAMILY = [("conv_tc_persist_kernel", "i2v_conv_tc_f32"), ("conv_tc_kernel", "i2v_conv_tc_f32"),
+FAMILY = [("stem_fwd_rows_kernel", "i2v_conv_stem_fwd_f32"), ("stem_dgrad_pool_kernel", "i2v_conv_stem_dgrad_pool_f32"),
+          ("stem_dgrad_direct_kernel", "i2v_conv_stem_dgrad_f32"),
+          ("conv_tc_persist_kernel", "i2v_conv_tc_f32"), ("conv_tc_pair_kernel", "i2v_conv_tc_f32"),
+          ("conv3x3_halo_kernel", "i2v_conv_tc_f32"), ("conv_tc_kernel", "i2v_conv_tc_f32"),
           # (the first-layer entry points are composites — im2col / col2im pass + a conv_tc_persist GEMM whose launches
           # cannot be told apart from the other convolutions' by name — so they get no per-launch traffic figure)
           ("maxpool_fwd", "i2v_maxpool_fwd_f32"), ("maxpool_bwd", "i2v_maxpool_bwd_f32"),
