@@ -72,6 +72,7 @@ SIGNATURES = {
     "i2v_conv_tc_supported": ([_c_p, _c_int], _c_int),
     "i2v_conv_tc_set_trace": ([_c_p, _c_int], _c_int),
     "i2v_conv_tc_set_pair_minkit": ([_c_int], _c_int),
+    "i2v_conv_tc_set_halo_mode": ([_c_int], _c_int),
     "i2v_mma_shift_probe": ([_c_int, _c_int, _c_p, _c_p, _c_p, _c_p], _c_int),
     "i2v_mma_probe": ([_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_p, _c_p], _c_int),
     "i2v_conv_tc_f32": ([_c_p, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
@@ -127,7 +128,7 @@ def load():
 # tensors read + written once, 2 x MACs of the convolution).
 LAUNCHES = {}
 PROFILE_EVENTS = None
-_NO_KERNEL = ("i2v_set_adam_arithmetic", "i2v_conv_stem_dgrad_pool_supported", "i2v_conv_stem_fwd_rows_supported", "i2v_conv_stem_dgrad_direct_supported", "i2v_conv_tc_set_pair_minkit", "i2v_conv_stem_fwd_direct_supported", "i2v_conv_stem_fwd_direct_scratch_floats", "i2v_conv_stem_dgrad_tc_rows", "i2v_device_check", "i2v_std_workspace_doubles", "i2v_ila_workspace_doubles", "i2v_adam_step_table", "i2v_conv_tc_supported", "i2v_conv_stem_supported",
+_NO_KERNEL = ("i2v_set_adam_arithmetic", "i2v_conv_stem_dgrad_pool_supported", "i2v_conv_stem_fwd_rows_supported", "i2v_conv_stem_dgrad_direct_supported", "i2v_conv_tc_set_pair_minkit", "i2v_conv_tc_set_halo_mode", "i2v_conv_stem_fwd_direct_supported", "i2v_conv_stem_fwd_direct_scratch_floats", "i2v_conv_stem_dgrad_tc_rows", "i2v_device_check", "i2v_std_workspace_doubles", "i2v_ila_workspace_doubles", "i2v_adam_step_table", "i2v_conv_tc_supported", "i2v_conv_stem_supported",
               "i2v_conv_tc_set_trace")
 
 
@@ -553,6 +554,11 @@ def conv_tc_set_trace(buf, tiles=0):
 def conv_tc_set_pair_minkit(min_ksteps):
     """Tiles of >= min_ksteps k-steps run on the CTA-pair (cta_group::2) kernel; 0 = never."""
     _check(load().i2v_conv_tc_set_pair_minkit(int(min_ksteps)), "i2v_conv_tc_set_pair_minkit")
+
+
+def conv_tc_set_halo_mode(mode):
+    """Which 3x3 / s1 / p1 convolutions run on the patch-once kernel: 1 wherever it fits, 0 never, -1 the default rule."""
+    _check(load().i2v_conv_tc_set_halo_mode(int(mode)), "i2v_conv_tc_set_halo_mode")
 
 
 def conv_tc_supported(desc, dgrad):

@@ -3171,6 +3171,7 @@ static int halo_launch(const float* src, int N, int H, int W, int C, const float
 // -1 (default) = where it was measured to win in the attack step (profiles/r02_pair_kernel.md): convolutions that stream a
 // residual / addend through the epilogue, from 4 k-steps per tile
 static int g_pair_minkit = -2;
+static int g_halo_mode = -2;        // $I2V_TC_HALO / i2v_conv_tc_set_halo_mode; see tc_run
 static int pair_min_ksteps() {
     if (g_pair_minkit == -2) g_pair_minkit = getenv("I2V_TC_PAIR") ? atoi(getenv("I2V_TC_PAIR")) : -1;
     return g_pair_minkit;
@@ -3221,7 +3222,8 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
     // it fits, 0 = never, default = the 64-channel tiles only, where it was measured to win in the attack step (56x56 64 -> 64:
     // 325 us against 382 us per 256 frames = 88 % of the measured TF32 GEMM rate counting issued MMAs; at BN = 128 its single
     // accumulator stage and two-stage weight ring lose, 255 us against 233 us)
-    static const int halo_mode = getenv("I2V_TC_HALO") ? atoi(getenv("I2V_TC_HALO")) : -1;
+    if (g_halo_mode == -2) g_halo_mode = getenv("I2V_TC_HALO") ? atoi(getenv("I2V_TC_HALO")) : -1;
+    const int halo_mode = g_halo_mode;
     const bool halo_on = halo_mode > 0 || (halo_mode < 0 && BN == 64);   // 2 = wherever it fits, always with 64-channel tiles
     if (halo_on && x3 && epi_tma && pr.taps_h == 3 && pr.taps_w == 3 && pr.stride == 1 && pr.lower_h == -1 && pr.lower_w == -1 &&
         pr.P == pr.H && pr.Q == pr.W && !pr.residual && !pr.out_transposed && pr.out_s == 0 && !pr.src2 && pr.store_cols == 0 &&
@@ -3363,6 +3365,11 @@ using namespace i2v;
 
 extern "C" int i2v_conv_tc_set_pair_minkit(int min_ksteps) {
     g_pair_minkit = min_ksteps < -1 ? -1 : min_ksteps;
+    return I2V_OK;
+}
+
+extern "C" int i2v_conv_tc_set_halo_mode(int mode) {
+    g_halo_mode = mode < -1 ? -1 : mode;
     return I2V_OK;
 }
 

@@ -29,6 +29,11 @@ int i2v_conv_tc_set_trace(unsigned long long* device_buf, int tiles);
  * k-steps — where the pair was measured to win in the attack step.  Initial value: $I2V_TC_PAIR.                  */
 int i2v_conv_tc_set_pair_minkit(int min_ksteps);
 
+/* Tuning: which 3x3 / stride-1 / pad-1 convolutions of the 3xTF32 / TMA-epilogue configuration run on the patch-once kernel
+ * (csrc/conv_tc.cu: conv3x3_halo_kernel): 1 = wherever it fits, 2 = likewise but always with 64-channel tiles, 0 = never,
+ * -1 (the default) = the 64-channel tiles only, where it was measured to win.  Initial value: $I2V_TC_HALO.            */
+int i2v_conv_tc_set_halo_mode(int mode);
+
 #ifdef __cplusplus
 }
 #endif

@@ -310,6 +310,78 @@ def test_conv_tc_pair_kernel_is_bit_identical(shape, pair_kernel):
         assert torch.isfinite(out[1][3]).all() and torch.equal(out[0][3], out[1][3])
 
 
+HALO_SHAPES = [
+    #  N  H   W   Cin  Cout
+    (2, 56, 56, 64, 64),       # the layer it runs for: two output rows per tile (58-pixel padded rows), 28 tiles per image
+    (2, 28, 28, 128, 128),     # four rows per tile, BN = 128: one accumulator stage, two weight stages
+    (3, 14, 14, 256, 64),      # eight rows per tile, H % R != 0: a short last tile per image through the second store map
+    (2, 7, 9, 64, 128),        # H < R: one short tile per image
+    (1, 57, 31, 64, 192),      # odd sizes, three n-tiles of 64
+    (2, 20, 126, 64, 64),      # the widest row that fits a tile (W + 2 = 128): one row per tile
+    (5, 3, 3, 512, 64),        # 16 channel blocks per tile
+]
+
+
+@pytest.mark.parametrize("shape", HALO_SHAPES)
+@pytest.mark.parametrize("mode", [1, 2])
+def test_conv3x3_halo_kernel(shape, mode):
+    """The patch-once 3x3 kernel (conv3x3_halo_kernel: padded-raster tiles, the nine taps as row-shifted descriptor views of
+    one TMA box) against the im2col-mode kernel on the same operands — same 3xTF32 products, a different accumulation order
+    (taps inside a channel block instead of channel blocks inside a tap), so equal to within the accumulation bound — and both
+    against float64: forward (+bias, ReLU, activity bits out) and data gradient (+ReLU-backward bit mask).  mode 2 forces
+    64-channel tiles (two accumulator stages) where mode 1 would pick 128."""
+    N, H, W, Cin, Cout = shape
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(N, H, W, Cin, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    scale = torch.rand(Cout, generator=g) + 0.5
+    bias = torch.randn(Cout, generator=g) * 0.1
+    d = capi.ConvDesc(N, H, W, Cin, Cout, 3, 3, 1, 1, H, W)
+    ws, (fh, fl, fr), (dh, dl, dr) = _tc_operands(w, scale)
+    dy = torch.randn(N, H, W, Cout, generator=g)
+    mb = torch.randint(-2 ** 31, 2 ** 31 - 1, (Cin // 32, N * H * W), generator=g, dtype=torch.int64).to(torch.int32)
+    xd, dyd, mbd, bd = x.to(DEV), dy.to(DEV), mb.to(DEV), bias.to(DEV)
+    out = {}
+    try:
+        for m in (0, mode):
+            capi.conv_tc_set_halo_mode(m)
+            y = torch.full((N, H, W, Cout), float("nan"), device=DEV)
+            bits = torch.zeros(Cout // 32, N * H * W, device=DEV, dtype=torch.int32)
+            capi.conv_tc(d, 0, xd, fh, fl, bd, None, None, y, relu=True, mask_bits=bits)
+            dx = None
+            if capi.conv_tc_supported(d, 1):
+                dx = torch.full((N, H, W, Cin), float("nan"), device=DEV)
+                capi.conv_tc(d, 1, dyd, dh, dl, None, None, None, dx, mask_bits=mbd)
+            out[m] = (y, bits, dx)
+    finally:
+        capi.conv_tc_set_halo_mode(int(os.environ.get("I2V_TC_HALO", "-1")))
+    K = 9 * Cin
+    y64 = torch.relu(torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), ws.double(), bias.double(), padding=1))
+    y64 = y64.permute(0, 2, 3, 1)
+    tol = (1e-5 + K * 2.0 ** -24) * float(y64.abs().max())
+    for m in out:
+        y = out[m][0].cpu().double()
+        assert torch.isfinite(y).all()
+        assert float((y - y64).abs().max()) <= tol, (m, float((y - y64).abs().max()), tol)
+    assert float((out[0][0] - out[mode][0]).abs().max()) <= tol
+    # activity bits: the same function of the kernel's own output in both kernels
+    for m in out:
+        y, bits = out[m][0], out[m][1]
+        want = (y.reshape(-1, Cout // 32, 32) > 0).to(torch.int64)
+        words = (want << torch.arange(32, device=DEV).view(1, 1, 32)).sum(-1)                       # [M, Cout/32]
+        words = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32).t().contiguous()
+        assert torch.equal(words, bits), m
+    if out[0][2] is not None:
+        keep = ((mb.view(Cin // 32, -1, 1) >> torch.arange(32).view(1, 1, 32)) & 1).permute(1, 0, 2).reshape(N, H, W, Cin)
+        wd = ws.double()
+        dx64 = torch.nn.functional.conv_transpose2d(dy.permute(0, 3, 1, 2).double(), wd, padding=1).permute(0, 2, 3, 1) * keep
+        told = (1e-5 + 9 * Cout * 2.0 ** -24) * float(dx64.abs().max())
+        for m in out:
+            dx = out[m][2].cpu().double()
+            assert torch.isfinite(dx).all()
+            assert float((dx - dx64).abs().max()) <= told, (m, float((dx - dx64).abs().max()), told)
+
+
 @pytest.mark.parametrize("shape", TC_SHAPES)
 @pytest.mark.parametrize("x3", [True, False])
 def test_conv_tc_fwd_and_dgrad(shape, x3):
