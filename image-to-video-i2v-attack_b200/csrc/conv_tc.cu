@@ -81,6 +81,8 @@ struct TcArgs {
     // accumulator, [6] epilogue done, [7] split warps done with the tile
     unsigned long long* trace;
     int trace_tiles;
+    int b_resident;              // persistent kernel: the n-tile's whole weight block [kiters][b_hi | b_lo] is loaded ONCE per CTA and stays in
+                                 // shared memory (every tile of a CTA has the same n-tile when gridDim % num_n_tiles == 0); the ring carries A only
     int dbg;                     // pair kernel timing experiments ($I2V_TC_PAIR_DBG): bit 0 skips MMA1, bit 1 skips MMA2, bit 2 skips the A split, bit 3 skips the weight loads (wrong results)
 };
 #define TC_TRACE(slot, tile_no)                                                                          \
@@ -507,8 +509,14 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     constexpr uint32_t kStageBytes = ALO_TMEM ? L::STAGE_BYTES - TC_A_BYTES : L::STAGE_BYTES;   // no A_lo tile in smem
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // resident weights (args.b_resident): the ring stages shrink to the A tile(s), the n-tile's weights follow the ring
+    const bool bres_on = args.b_resident != 0;
+    const uint32_t stage_bytes = bres_on ? kStageBytes - (X3 ? 2u : 1u) * L::B_BYTES : kStageBytes;
+    const uint32_t bres_kb = (X3 ? 2u : 1u) * L::B_BYTES;       // per k-step: [b_hi | b_lo]
+    const uint32_t bres_bytes = bres_on ? (uint32_t)(args.taps_h * args.taps_w * args.cblocks) * bres_kb : 0u;
     uint8_t* tiles = smem;
-    uint8_t* staging = smem + (size_t)stages * kStageBytes;     // stage sizes are multiples of 1024: stays swizzle-aligned
+    uint8_t* bres = smem + (size_t)stages * stage_bytes;
+    uint8_t* staging = bres + bres_bytes;                       // stage sizes are multiples of 1024: stays swizzle-aligned
     // staging: epi_slots (1 or 2) slots of 16 KB per epilogue group.  K-heavy layers without a residual take ONE slot
     // per group so that a third 64 KB pipeline stage fits (3xTF32, BN = 128): with two stages the tensor pipe idled
     // ~45 % of the time waiting for the next k-step's operands (measured 53 % active on the 3x3 128->128 layers)
@@ -519,17 +527,20 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     uint64_t* tempty_bar = tfull_bar + kAcc;
     uint64_t* out_ready = tempty_bar + kAcc;                    // [group][slot]
     uint64_t* slot_ready = out_ready + 4;                       // [group][slot]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slot_ready + 4);
+    uint64_t* bres_full = slot_ready + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_full + 1);
     float* bias_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 2) + 15) & ~(uintptr_t)15);   // [Cout], 16-byte aligned
 
     const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
     const int kiters = args.taps_h * args.taps_w * args.cblocks;
     const int num_tiles = num_m_tiles * num_n_tiles;
 
-    auto stage_a = [&](int s) { return tiles + (size_t)s * kStageBytes; };
-    auto stage_alo = [&](int s) { return tiles + (size_t)s * kStageBytes + TC_A_BYTES; };
-    auto stage_bhi = [&](int s) { return tiles + (size_t)s * kStageBytes + TC_A_BYTES * ((X3 && !ALO_TMEM) ? 2 : 1); };
+    auto stage_a = [&](int s) { return tiles + (size_t)s * stage_bytes; };
+    auto stage_alo = [&](int s) { return tiles + (size_t)s * stage_bytes + TC_A_BYTES; };
+    auto stage_bhi = [&](int s) { return tiles + (size_t)s * stage_bytes + TC_A_BYTES * ((X3 && !ALO_TMEM) ? 2 : 1); };
     auto stage_blo = [&](int s) { return stage_bhi(s) + L::B_BYTES; };
+    // weights of k-step kb: the ring stage, or the resident block
+    auto b_of = [&](int s, int kb) { return bres_on ? bres + (size_t)kb * bres_kb : stage_bhi(s); };
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA); prefetch_tmap(&tmBhi);
@@ -547,6 +558,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             mbar_init(&out_ready[i], TC2_EPI_THREADS / 2);
             mbar_init(&slot_ready[i], 1);
         }
+        mbar_init(bres_full, 1);
         if (EPI_TMA) { prefetch_tmap(&tmOut); prefetch_tmap(&tmRes); }
         fence_barrier_init();
     }
@@ -566,6 +578,14 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         if (elect_one()) {
             int it = 0, tno = 0;
             int st = 0; uint32_t ph = 0;               // ring position of k-step `it` (no division in the loop)
+            if (bres_on && (int)blockIdx.x < num_tiles) {
+                const int n0r = ((int)blockIdx.x % num_n_tiles) * BN;      // the n-tile of every tile of this CTA
+                mbar_arrive_expect_tx(bres_full, bres_bytes);
+                for (int kb = 0; kb < kiters; ++kb) {
+                    tma_load_2d(&tmBhi, bres_full, bres + (size_t)kb * bres_kb, kb * TC_BK, n0r);
+                    if (X3) tma_load_2d(&tmBlo, bres_full, bres + (size_t)kb * bres_kb + L::B_BYTES, kb * TC_BK, n0r);
+                }
+            }
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tno) {
                 const int m_tile = tile / num_n_tiles, n_tile = tile - m_tile * num_n_tiles;
                 const int64_t m0 = (int64_t)m_tile * TC_BM;
@@ -594,7 +614,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                             if ((r | s | cb) == 0) TC_TRACE(0, tno);
                             // (measured: deriving B_lo on the fly in the split warps instead of loading it — 25-33 % fewer TMA
                             // rows per k-step — made every layer 5-15 % SLOWER: the four split warps are the tighter resource)
-                            const bool no_b = (args.dbg & 8) != 0;          // timing experiment: the weight tiles are not loaded
+                            const bool no_b = (args.dbg & 8) != 0 || bres_on;   // resident weights (or the timing experiment): no weight loads
                             mbar_arrive_expect_tx(&full_bar[st], TC_A_BYTES + (no_b ? 0u : L::B_BYTES * (X3 ? 2 : 1)));
                             if (args.a2_cb0 > 0 && cb >= args.a2_cb0) tma_load_2d(&tmRes, &full_bar[st], stage_a(st), (cb - args.a2_cb0) * TC_BK, (int)m0);
                             else if (IM2COL) tma_load_im2col_4d(&tmA, &full_bar[st], stage_a(st), cb * TC_BK, base_w, base_h, img, (uint16_t)s, (uint16_t)r);
@@ -623,6 +643,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             constexpr uint32_t idesc2 = umma_idesc_tf32(2 * BN);
             int it = 0, t = 0;
             int st = 0; uint32_t ph = 0;               // ring position of k-step `it` (no division in the loop)
+            if (bres_on && (int)blockIdx.x < num_tiles) { mbar_wait(bres_full, 0); tc_fence_after(); }
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
                 const int acc = t % kAcc;
                 const uint32_t aph = (uint32_t)(t / kAcc) & 1;
@@ -636,7 +657,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     tc_fence_after();
                     if (kb == 0) TC_TRACE(3, t);
                     const uint64_t da = umma_desc_sw128(smem_u32(stage_a(st)));
-                    const uint64_t dbh = umma_desc_sw128(smem_u32(stage_bhi(st)));
+                    const uint64_t dbh = umma_desc_sw128(smem_u32(b_of(st, kb)));
                     uint64_t dal = 0;
                     if (X3 && !ALO_TMEM) dal = umma_desc_sw128(smem_u32(stage_alo(st)));
 #pragma unroll
@@ -662,6 +683,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             constexpr uint32_t idesc = umma_idesc_tf32(BN);
             int it = 0, t = 0;
             int st = 0; uint32_t ph = 0;               // ring position of k-step `it` (no division in the loop)
+            if (bres_on && (int)blockIdx.x < num_tiles) { mbar_wait(bres_full, 0); tc_fence_after(); }
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
                 const int acc = t % kAcc;
                 const uint32_t aph = (uint32_t)(t / kAcc) & 1;
@@ -672,7 +694,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     mbar_wait(&full_bar[st], ph);               // b_hi landed
                     mbar_wait(&split_bar[st], ph);              // a_lo of this k-step is in its ring slot
                     tc_fence_after();
-                    const uint64_t dbh = umma_desc_sw128(smem_u32(stage_bhi(st)));
+                    const uint64_t dbh = umma_desc_sw128(smem_u32(b_of(st, kb)));
                     const uint32_t talo = tmem_base + kAloBase + (uint32_t)(it % kAloSlots) * 32u;
 #pragma unroll
                     for (int kk = 0; kk < TC_BK / 8; ++kk)
@@ -3070,8 +3092,27 @@ static int tc_launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmBhi, c
     const int num_m_tiles = (int)((args.M + TC_BM - 1) / TC_BM), num_n_tiles = args.Cout / BN;
     const int64_t tiles = (int64_t)num_m_tiles * num_n_tiles;
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-    kern<<<grid, TC2_THREADS, fixed + (size_t)stages * kStageBytes, st>>>(tmA, tmBhi, tmBlo, tmOut, tmRes, args, stages,
-                                                                         num_m_tiles, num_n_tiles, slots);
+    // Resident weights ($I2V_TC_BRES=0: off): when the n-tile's whole weight block fits beside >= 3 A stages and every tile of a
+    // CTA has the same n-tile (grid % num_n_tiles == 0), it is loaded once per CTA instead of once per tile — the 1x1 layers with
+    // K <= 128 (BN = 128) / K <= 256 (BN = 64) re-fetched 2-3x the bytes of their A tiles from L2 as weights.
+    static const bool bres_env = !(getenv("I2V_TC_BRES") && atoi(getenv("I2V_TC_BRES")) == 0);
+    TcArgs a2 = args;
+    size_t smem_bytes = fixed + (size_t)stages * kStageBytes;
+    // (measured in the attack step: 1-2 % on each of these layers — 56x56 256->64 +res 358 -> 353 us, 64->256 207 -> 203 us —
+    // except the two-k-step BN = 64 launches, 100 -> 107 us, which keep the ring)
+    if (bres_env && X3 && !IM2COL && grid % num_n_tiles == 0 && tiles >= 4 * (int64_t)grid && (BN == 128 || kiters >= 3)) {
+        constexpr size_t kStageA = kStageBytes - 2 * (size_t)L::B_BYTES;
+        const size_t bres = (size_t)kiters * 2 * L::B_BYTES;
+        if (fixed + bres + 3 * kStageA <= budget) {
+            int sa = (int)((budget - fixed - bres) / kStageA);
+            if (sa > 8) sa = 8;
+            if (ALO_TMEM && sa > 4) sa = 4;
+            a2.b_resident = 1;
+            stages = sa;
+            smem_bytes = fixed + bres + (size_t)sa * kStageA;
+        }
+    }
+    kern<<<grid, TC2_THREADS, smem_bytes, st>>>(tmA, tmBhi, tmBlo, tmOut, tmRes, a2, stages, num_m_tiles, num_n_tiles, slots);
     I2V_LAUNCH_CHECK("i2v_conv_tc_f32 (persistent)");
     return I2V_OK;
 }
@@ -3206,6 +3247,11 @@ static int tc_run(const TcProblem& pr, cudaStream_t st) {
     // CTAs are co-resident; plain TF32 has room for BN=128.  I2V_TC_BN=64|128 overrides for experiments.
     static const bool persistent = !(getenv("I2V_TC_PERSISTENT") && atoi(getenv("I2V_TC_PERSISTENT")) == 0);
     int BN = (pr.Cout % 128 == 0 && (!x3 || persistent)) ? 128 : 64;
+    // dual-source launches of <= $I2V_TC_DUAL_BN64 (default 4) k-steps: 64-channel tiles keep TWO accumulator stages with two
+    // issuers (three accumulators of 128 columns leave one), so the epilogue overlaps the next tile's main loop
+    // (layer1.0, 64 + 64 -> 256: 393 -> 352 us per 256 frames)
+    static const int dual_bn64 = getenv("I2V_TC_DUAL_BN64") ? atoi(getenv("I2V_TC_DUAL_BN64")) : 4;
+    if (pr.src2 && x3 && persistent && pr.taps_h * pr.taps_w * (pr.C / 32) + pr.C2 / 32 <= dual_bn64) BN = 64;
     if (const char* e = getenv("I2V_TC_BN")) { int v = atoi(e); if ((v == 64 || v == 128) && pr.Cout % v == 0) BN = v; }
     const int Ktot = pr.taps_h * pr.taps_w * pr.C + (pr.src2 ? pr.C2 : 0);
 

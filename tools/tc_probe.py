@@ -23,6 +23,7 @@ LAYERS = [  # name, H, Cin, Cout, k, s, p, count(fwd)
     ("l2.conv3(128->512,1x1)+res", 28, 128, 512, 1, 1, 0, 4),
     ("l2.conv1(512->128,1x1)", 28, 512, 128, 1, 1, 0, 3),
     ("l2.conv2(128->128,3x3)", 28, 128, 128, 3, 1, 1, 3),
+    ("syn(128->256,1x1)@56", 56, 128, 256, 1, 1, 0, 0),      # the K of the dual-source launch (64 + 64 -> 256) from one source
 ]
 
 
