@@ -69,3 +69,35 @@ def test_product_never_imports_oracle():
     for f in os.listdir(os.path.join(pkg, "csrc")):
         src = open(os.path.join(pkg, "csrc", f)).read()
         assert not re.search(r"#include\s*[\"<][^\">]*oracle", src), f
+
+
+def _sass(obj):
+    import shutil
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.isfile(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    return subprocess.check_output([cuobjdump, "-sass", obj]).decode(errors="replace")
+
+
+def test_tensor_core_kernels_are_tcgen05_tma_without_waterfall_loops(lib):
+    """SASS of the tensor-core convolution object (sm_100a, cross-compiled here): the contraction is tcgen05 (UTCHMMA, also
+    the cta_group::2 form), operands and results move by TMA (UTMALDG incl. im2col mode, UTMASTG), accumulators are read
+    from tensor memory (LDTM) — and no uniform-datapath instruction sits in a compiler-generated waterfall loop
+    (ELECT + R2UR.BROADCAST + BRA.U.ANY): that is what `if (lane == 0)` role selection produced, ~200 cycles per tcgen05.mma
+    on the issuing thread; the roles are selected with elect.sync instead."""
+    obj = os.path.join(ROOT, "image-to-video-i2v-attack_b200", "build", "conv_tc.o")
+    assert os.path.isfile(obj)
+    sass = _sass(obj)
+    count = lambda pat: len(re.findall(pat, sass))
+    assert count(r"\bUTCHMMA\b") > 100
+    assert count(r"UTCHMMA\.2CTA") > 0
+    assert count(r"\bUTMALDG\.") > 50 and count(r"UTMALDG\.4D\.IM2COL") > 0
+    assert count(r"\bUTMASTG\.") > 10
+    assert count(r"\bLDTM\b") + count(r"\bLDTM\.") > 50
+    assert count(r"BRA\.U\.ANY") == 0, "a waterfall loop is back around a uniform-datapath instruction"
+    # the mainloops of the kernels the attack step runs have no emulated integer division per k-step: the only I2F.RP /
+    # MUFU.RCP sequences left are per tile (tile -> image / row coordinates)
+    for kern in ("conv3x3_halo_kernelILi64ELb1", ):
+        body = re.search(r"Function : \S*%s.*?(?=Function : |\Z)" % kern, sass, flags=re.S)
+        assert body is not None, kern
+        assert len(re.findall(r"BRA\.U\.ANY", body.group(0))) == 0
