@@ -68,6 +68,8 @@ SIGNATURES = {
     "i2v_conv_stem_dgrad_pool_f32": ([_c_p, _c_int, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p], _c_int),
     "i2v_conv_stem_fwd_rows_supported": ([_c_p], _c_int),
     "i2v_conv_stem_fwd_rows_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
+    "i2v_conv_stem_fwd_pool_supported": ([_c_p, _c_int, _c_int], _c_int),
+    "i2v_conv_stem_fwd_pool_f32": ([_c_p, _c_int, _c_int, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_stem_fwd_tc_f32": ([_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_int, _c_p], _c_int),
     "i2v_conv_tc_supported": ([_c_p, _c_int], _c_int),
     "i2v_conv_tc_set_trace": ([_c_p, _c_int], _c_int),
@@ -128,7 +130,7 @@ def load():
 # tensors read + written once, 2 x MACs of the convolution).
 LAUNCHES = {}
 PROFILE_EVENTS = None
-_NO_KERNEL = ("i2v_set_adam_arithmetic", "i2v_conv_stem_dgrad_pool_supported", "i2v_conv_stem_fwd_rows_supported", "i2v_conv_stem_dgrad_direct_supported", "i2v_conv_tc_set_pair_minkit", "i2v_conv_tc_set_halo_mode", "i2v_conv_stem_fwd_direct_supported", "i2v_conv_stem_fwd_direct_scratch_floats", "i2v_conv_stem_dgrad_tc_rows", "i2v_device_check", "i2v_std_workspace_doubles", "i2v_ila_workspace_doubles", "i2v_adam_step_table", "i2v_conv_tc_supported", "i2v_conv_stem_supported",
+_NO_KERNEL = ("i2v_set_adam_arithmetic", "i2v_conv_stem_dgrad_pool_supported", "i2v_conv_stem_fwd_rows_supported", "i2v_conv_stem_fwd_pool_supported", "i2v_conv_stem_dgrad_direct_supported", "i2v_conv_tc_set_pair_minkit", "i2v_conv_tc_set_halo_mode", "i2v_conv_stem_fwd_direct_supported", "i2v_conv_stem_fwd_direct_scratch_floats", "i2v_conv_stem_dgrad_tc_rows", "i2v_device_check", "i2v_std_workspace_doubles", "i2v_ila_workspace_doubles", "i2v_adam_step_table", "i2v_conv_tc_supported", "i2v_conv_stem_supported",
               "i2v_conv_tc_set_trace")
 
 
@@ -514,6 +516,22 @@ def conv_stem_fwd_rows(desc, x, wk_hi, wk_lo, bias, y, relu=False):
     with _Timed("i2v_conv_stem_fwd_f32", nb, fl):
         _check(load().i2v_conv_stem_fwd_rows_f32(ctypes.addressof(desc), _dev(x), _dev(wk_hi), _dev(wk_lo), _dev(bias), _dev(y),
                                                  EPI_RELU if relu else 0, _stream()), "i2v_conv_stem_fwd_rows_f32")
+
+
+def conv_stem_fwd_pool_supported(desc, P2, Q2):
+    return bool(load().i2v_conv_stem_fwd_pool_supported(ctypes.addressof(desc), int(P2), int(Q2)))
+
+
+def conv_stem_fwd_pool(desc, x, wk_hi, wk_lo, bias, pooled, argmax, relu=True, mark_dead=True):
+    """First-layer forward with the 3x3 / stride-2 / pad-1 max pooling fused into its epilogue (see include/i2v_b200.h)."""
+    _, fl = _conv_cost(desc)
+    nb = 4 * x.numel() + 5 * pooled.numel()          # the image once, the pooled tensor and its argmax plane once
+    P2, Q2 = pooled.shape[1], pooled.shape[2]
+    with _Timed("i2v_conv_stem_fwd_pool_f32", nb, fl):
+        _check(load().i2v_conv_stem_fwd_pool_f32(ctypes.addressof(desc), int(P2), int(Q2), _dev(x), _dev(wk_hi), _dev(wk_lo),
+                                                 _dev(bias), _dev(pooled), _dev(argmax, torch.uint8),
+                                                 (EPI_RELU if relu else 0) | (4 if mark_dead else 0), _stream()),
+               "i2v_conv_stem_fwd_pool_f32")
 
 
 def conv_stem_fwd_direct_supported(desc):

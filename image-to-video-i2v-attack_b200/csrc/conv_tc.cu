@@ -2584,13 +2584,48 @@ struct StemFwdArgs {
     int pitch;                           // staged row pitch in floats = TMA box width (>= W + 7: columns -4 .. W+2, multiple of 4)
     int cstride;                         // floats between the staged channels (7 * pitch rounded up to 128 bytes: TMA destination alignment)
     int tiles;                           // N * P
+    // fused 3x3 / stride-2 / pad-1 max pooling (stem_fwd_rows_kernel<true>): the CTA walks UNITS = (image, strip of S pooled rows),
+    // conv rows 2 i0 - 1 .. 2 i1 - 1 of a strip in order, and the stem activation never leaves the chip
+    float* pooled;                       // [N, P2, Q2, 64]
+    uint8_t* argmax;                     // [N, P2, Q2, 64] window position r * 3 + s of the winner, 255 = no winner (mark_dead)
+    int P2, Q2, S, U, units, mark_dead;
 };
+
+// the rows (image n, conv row p) a CTA computes, in order; t counts them
+struct SfIter { int t, n, p, i0, i1, u, pend; };
+__device__ __forceinline__ void sf_unit(const StemFwdArgs& a, SfIter& it) {
+    it.n = it.u / a.U;
+    const int k = it.u - it.n * a.U;
+    it.i0 = k * a.S;
+    it.i1 = it.i0 + a.S < a.P2 ? it.i0 + a.S : a.P2;
+    it.p = it.i0 > 0 ? 2 * it.i0 - 1 : 0;          // the lead-in row 2 i0 - 1 is row r = 0 of pooled row i0
+    it.pend = 2 * it.i1 - 1;
+}
+template <bool POOL>
+__device__ __forceinline__ bool sf_begin(const StemFwdArgs& a, SfIter& it) {
+    it.t = 0; it.u = blockIdx.x; it.i0 = it.i1 = 0; it.pend = 0;
+    if (!POOL) { if (it.u >= a.tiles) return false; it.n = it.u / a.P; it.p = it.u - it.n * a.P; return true; }
+    if (it.u >= a.units) return false;
+    sf_unit(a, it);
+    return true;
+}
+template <bool POOL>
+__device__ __forceinline__ bool sf_next(const StemFwdArgs& a, SfIter& it) {
+    ++it.t;
+    if (!POOL) { it.u += gridDim.x; if (it.u >= a.tiles) return false; it.n = it.u / a.P; it.p = it.u - it.n * a.P; return true; }
+    if (it.p < it.pend) { ++it.p; return true; }
+    it.u += gridDim.x;
+    if (it.u >= a.units) return false;
+    sf_unit(a, it);
+    return true;
+}
 
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
+template <bool POOL>
 __global__ void __launch_bounds__(SF_THREADS, 1)
 stem_fwd_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBhi,
                      const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmOut, const StemFwdArgs args) {
@@ -2638,9 +2673,9 @@ stem_fwd_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                 tma_load_2d(&tmBhi, bfull, bt + (size_t)kb * SF_B_KB, kb * TC_BK, 0);
                 tma_load_2d(&tmBlo, bfull, bt + (size_t)kb * SF_B_KB + 64 * TC_BK * 4, kb * TC_BK, 0);
             }
-            int t = 0;
-            for (int tile = blockIdx.x; tile < args.tiles; tile += gridDim.x, ++t) {
-                const int n = tile / args.P, p = tile - n * args.P;
+            SfIter ri;
+            for (bool more = sf_begin<POOL>(args, ri); more; more = sf_next<POOL>(args, ri)) {
+                const int n = ri.n, p = ri.p, t = ri.t;
                 const int st = t % SF_ISTAGES;
                 const uint32_t ph = (uint32_t)(t / SF_ISTAGES) & 1;
                 mbar_wait(&iempty[st], ph ^ 1);
@@ -2656,8 +2691,10 @@ stem_fwd_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_tf32(64), idesc2 = umma_idesc_tf32(128);
             mbar_wait(bfull, 0);
-            int t = 0, it = 0;
-            for (int tile = blockIdx.x; tile < args.tiles; tile += gridDim.x, ++t) {
+            int it = 0;
+            SfIter ri;
+            for (bool more = sf_begin<POOL>(args, ri); more; more = sf_next<POOL>(args, ri)) {
+                const int t = ri.t;
                 const int acc = t & 1;
                 mbar_wait(&tempty[acc], ((uint32_t)(t >> 1) & 1) ^ 1);
                 tc_fence_after();
@@ -2690,8 +2727,10 @@ stem_fwd_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         const int qq = row < args.Q ? row : args.Q - 1;           // junk rows repeat the last pixel (never stored)
         const uint32_t swz = (uint32_t)(row & 7);
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kRing;
-        int t = 0, it = 0;
-        for (int tile = blockIdx.x; tile < args.tiles; tile += gridDim.x, ++t) {
+        int it = 0;
+        SfIter ri;
+        for (bool more = sf_begin<POOL>(args, ri); more; more = sf_next<POOL>(args, ri)) {
+            const int t = ri.t;
             const int st = t % SF_ISTAGES;
             const uint32_t iph = (uint32_t)(t / SF_ISTAGES) & 1;
             mbar_wait(&ifull[st], iph);
@@ -2735,8 +2774,18 @@ stem_fwd_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         const uint32_t swz = (uint32_t)(row & 7);
         const uint32_t tlane = tmem_base + ((uint32_t)(ew * 32) << 16);
         const float* __restrict__ gbias = args.bias;
-        int t = 0;
-        for (int tile = blockIdx.x; tile < args.tiles; tile += gridDim.x, ++t) {
+        // fused pooling: thread = (pooled column pj, channel half ph_) keeps the running window maximum of 32 channels in registers
+        const int et = threadIdx.x - 256;
+        const int pj = et >> 1, ph_ = et & 1;
+        float pacc[32];
+        uint32_t pidx[8];                                           // window positions, one byte per channel
+#pragma unroll
+        for (int c = 0; c < 32; ++c) pacc[c] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) pidx[c] = 0u;
+        SfIter ri;
+        for (bool more = sf_begin<POOL>(args, ri); more; more = sf_next<POOL>(args, ri)) {
+            const int t = ri.t;
             const int acc = t & 1;
             mbar_wait(&tfull[acc], (uint32_t)(t >> 1) & 1);
             tc_fence_after();
@@ -2767,17 +2816,82 @@ stem_fwd_rows_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                     *reinterpret_cast<float4*>(srow + (((uint32_t)c ^ swz) << 4)) = v;
                 }
             }
-            fence_proxy_async();
+            if (!POOL) fence_proxy_async();
             asm volatile("bar.sync 2, 128;" ::: "memory");
-            if (threadIdx.x == 256) {
-                const int m0 = tile * args.Q;                      // tile = n * P + p: rows (n, p, 0..Q-1) of y [N*P*Q, 64]
-                tma_store_2d(&tmOut, staging, 0, m0);
-                tma_store_2d(&tmOut, staging + EPI_SLOT_BYTES, 32, m0);
-                bulk_commit();
-                bulk_wait_read0();
+            if (!POOL) {
+                if (threadIdx.x == 256) {
+                    const int m0 = (ri.n * args.P + ri.p) * args.Q;    // rows (n, p, 0..Q-1) of y [N*P*Q, 64]
+                    tma_store_2d(&tmOut, staging, 0, m0);
+                    tma_store_2d(&tmOut, staging + EPI_SLOT_BYTES, 32, m0);
+                    bulk_commit();
+                    bulk_wait_read0();
+                }
+            } else if (pj < args.Q2) {
+                // ---- max pooling of the row that now sits in the staging slots, separably and in i2v_maxpool_fwd_f32's window order
+                // (first maximum in (r, s) order wins: strict > for every later candidate; columns / rows outside the image are
+                // skipped).  Horizontal: pixels 2 pj - 1, 2 pj, 2 pj + 1 of this row.
+                const int p = ri.p;
+                const uint8_t* slot = staging + (size_t)ph_ * EPI_SLOT_BYTES;
+                const int x0 = 2 * pj - 1, x1 = 2 * pj, x2 = 2 * pj + 1;
+                const bool v0 = x0 >= 0, v2 = x2 < args.Q;
+                const uint8_t* r0 = slot + (size_t)(v0 ? x0 : x1) * 128;
+                const uint8_t* r1 = slot + (size_t)x1 * 128;
+                const uint8_t* r2 = slot + (size_t)(v2 ? x2 : x1) * 128;
+                const uint32_t z0 = (uint32_t)((v0 ? x0 : x1) & 7), z1 = (uint32_t)(x1 & 7), z2 = (uint32_t)((v2 ? x2 : x1) & 7);
+                // Vertical: an even row p = 2i is row r = 1 of pooled row i; an odd row p = 2i + 1 is row r = 2 of pooled row i (which
+                // it completes) and row r = 0 of pooled row i + 1.  Horizontal and vertical steps are fused per group of four
+                // channels, so only the running maxima (32 registers) and their packed positions (8) live across rows.
+                const bool odd = (p & 1) != 0;
+                const bool first = p == 0;                           // row -1 does not exist: row 0 opens the window
+                const int i = (p - 1) >> 1;
+                const bool emit = odd && i >= ri.i0;                 // (a strip's lead-in row completes a pooled row of another unit)
+                const uint32_t rbase = odd ? 6u : 3u;
+                const int64_t o0 = ((((int64_t)ri.n * args.P2 + (emit ? i : 0)) * args.Q2 + pj) * 64 + ph_ * 32);
+                float4* py = reinterpret_cast<float4*>(args.pooled + o0);
+                uint32_t ow[8];
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 a0 = *reinterpret_cast<const float4*>(r0 + (((uint32_t)c4 ^ z0) << 4));
+                    const float4 a1 = *reinterpret_cast<const float4*>(r1 + (((uint32_t)c4 ^ z1) << 4));
+                    const float4 a2 = *reinterpret_cast<const float4*>(r2 + (((uint32_t)c4 ^ z2) << 4));
+                    const float w0[4] = {a0.x, a0.y, a0.z, a0.w}, w1[4] = {a1.x, a1.y, a1.z, a1.w}, w2[4] = {a2.x, a2.y, a2.z, a2.w};
+                    const uint32_t oldw = pidx[c4];
+                    uint32_t keepw = 0u, outw = 0u;
+                    float o4[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int c = 4 * c4 + k;
+                        // horizontal, first maximum in s order: s = 0 keeps ties against s = 1, s = 2 needs strictly more
+                        float b = w1[k];
+                        uint32_t sidx = 1u;
+                        const bool t0 = v0 && !(b > w0[k]);
+                        b = t0 ? w0[k] : b; sidx = t0 ? 0u : sidx;
+                        const bool t2 = v2 && (w2[k] > b);
+                        b = t2 ? w2[k] : b; sidx = t2 ? 2u : sidx;
+                        const uint32_t old = (oldw >> (8 * k)) & 0xffu;
+                        // vertical against the running maximum of rows r < this one
+                        const bool take = first || b > pacc[c];
+                        const float best = (take && !(odd && !emit)) ? b : pacc[c];
+                        uint32_t bi = take ? rbase + sidx : old;
+                        if (args.mark_dead && !(best > 0.f)) bi = 255u;
+                        o4[k] = best;
+                        outw |= bi << (8 * k);
+                        // state for the next row: an odd row restarts the window with itself as r = 0
+                        pacc[c] = odd ? b : (take ? b : pacc[c]);
+                        keepw |= (odd ? sidx : (take ? 3u + sidx : old)) << (8 * k);
+                    }
+                    pidx[c4] = keepw;
+                    ow[c4] = outw;
+                    if (emit) py[c4] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+                }
+                if (emit) {
+                    uint4* pa = reinterpret_cast<uint4*>(args.argmax + o0);
+                    pa[0] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    pa[1] = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+                }
             }
         }
-        if (threadIdx.x == 256) bulk_wait_all();
+        if (!POOL && threadIdx.x == 256) bulk_wait_all();
     }
 
     tc_fence_before();
@@ -3677,13 +3791,67 @@ extern "C" int i2v_conv_stem_fwd_rows_f32(const i2v_conv_desc* d, const float* x
     const size_t smem = 1024 + SF_KB * SF_B_KB + (size_t)SF_ASLOTS * TC_A_BYTES + 2 * EPI_SLOT_BYTES + SF_ISTAGES * in_stride + 512;
     static size_t smem_set = 0;
     if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(stem_fwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(stem_fwd_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(e, "i2v_conv_stem_fwd_rows_f32 (shared memory)");
         smem_set = smem;
     }
     const int grid = a.tiles < sm_count() ? a.tiles : sm_count();
-    stem_fwd_rows_kernel<<<grid, SF_THREADS, smem, as_stream(stream)>>>(tmX, tmBhi, tmBlo, tmOut, a);
+    stem_fwd_rows_kernel<false><<<grid, SF_THREADS, smem, as_stream(stream)>>>(tmX, tmBhi, tmBlo, tmOut, a);
     I2V_LAUNCH_CHECK("i2v_conv_stem_fwd_rows_f32");
+    return I2V_OK;
+}
+
+// The same with the 3x3 / stride-2 / pad-1 max pooling behind it fused into the epilogue (stem_fwd_rows_kernel<true>): pooled
+// [N, P2, Q2, 64] and its argmax plane come out, the 4x larger stem activation is never written or read back.  A CTA walks
+// strips of S pooled rows of one image (conv rows 2 i0 - 1 .. 2 i1 - 1 in order: one lead-in row per strip is computed twice);
+// S is chosen for the best product of wave fill and (2S) / (2S + 1).
+extern "C" int i2v_conv_stem_fwd_pool_supported(const i2v_conv_desc* d, int P2, int Q2) {
+    return i2v_conv_stem_fwd_rows_supported(d) && d->P % 2 == 0 && d->Q % 2 == 0 && P2 == d->P / 2 && Q2 == d->Q / 2;
+}
+
+extern "C" int i2v_conv_stem_fwd_pool_f32(const i2v_conv_desc* d, int P2, int Q2, const float* x, const float* wk_hi,
+                                          const float* wk_lo, const float* bias, float* pooled, uint8_t* argmax, int flags,
+                                          i2v_stream_t stream) {
+    I2V_REQUIRE(d && x && wk_hi && wk_lo && pooled && argmax, "null pointer");
+    I2V_REQUIRE(i2v_conv_stem_fwd_pool_supported(d, P2, Q2), "shape not supported by the first-layer forward with fused pooling");
+    I2V_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wk_hi) | reinterpret_cast<uintptr_t>(wk_lo) |
+                  reinterpret_cast<uintptr_t>(pooled) | reinterpret_cast<uintptr_t>(argmax) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0,
+                "all tensors must be 16-byte aligned");
+    if (d->N == 0) return I2V_OK;
+    if (int r = resolve_driver()) return r;
+    I2V_REQUIRE((int64_t)d->N * d->P * d->Q < (int64_t)0x7fffffff, "too many pixels for one launch");
+    const int pitch = (d->W + 7 + 3) / 4 * 4;
+    CUtensorMap tmX, tmBhi, tmBlo;
+    if (int r = get_map_planes(&tmX, x, d->N * 3, d->H, d->W, pitch, 7)) return r;
+    if (int r = get_map_2d(&tmBhi, wk_hi, 64, SF_KB * TC_BK, 64)) return r;
+    if (int r = get_map_2d(&tmBlo, wk_lo, 64, SF_KB * TC_BK, 64)) return r;
+    StemFwdArgs a{};
+    a.bias = bias; a.N = d->N; a.H = d->H; a.W = d->W; a.P = d->P; a.Q = d->Q; a.relu = (flags & I2V_EPI_RELU) ? 1 : 0;
+    a.pitch = pitch; a.tiles = d->N * d->P;
+    a.cstride = (7 * pitch * 4 + 127) / 128 * 32;
+    a.pooled = pooled; a.argmax = argmax; a.P2 = P2; a.Q2 = Q2; a.mark_dead = (flags & 4) ? 1 : 0;
+    const int sms = sm_count();
+    double best = -1.0;
+    for (int S = 1; S <= P2; ++S) {
+        const int U = (P2 + S - 1) / S;
+        const int64_t units = (int64_t)d->N * U;
+        const int64_t waves = (units + sms - 1) / sms;
+        // rows computed per image: 2 P2 + (U - 1) lead-in rows; fill of the last wave
+        const double eff = ((double)units / (double)(waves * sms)) * (2.0 * P2 / (2.0 * P2 + U - 1));
+        if (eff > best + 1e-9) { best = eff; a.S = S; a.U = U; }
+    }
+    a.units = d->N * a.U;
+    const size_t in_stride = (size_t)3 * a.cstride * 4;
+    const size_t smem = 1024 + SF_KB * SF_B_KB + (size_t)SF_ASLOTS * TC_A_BYTES + 2 * EPI_SLOT_BYTES + SF_ISTAGES * in_stride + 512;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(stem_fwd_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "i2v_conv_stem_fwd_pool_f32 (shared memory)");
+        smem_set = smem;
+    }
+    const int grid = a.units < sms ? a.units : sms;
+    stem_fwd_rows_kernel<true><<<grid, SF_THREADS, smem, as_stream(stream)>>>(tmX, tmBhi, tmBlo, tmBhi, a);
+    I2V_LAUNCH_CHECK("i2v_conv_stem_fwd_pool_f32");
     return I2V_OK;
 }
 

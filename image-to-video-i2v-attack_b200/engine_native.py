@@ -318,6 +318,11 @@ class NativeEngine:
         # max-pool backward fused into that kernel (i2v_conv_stem_dgrad_pool_f32): the stem activation's gradient never reaches
         # HBM; $I2V_STEM_DGRAD_POOL=0: i2v_maxpool_bwd_f32 + i2v_conv_stem_dgrad_direct_f32
         self.stem_dgrad_pool = os.environ.get("I2V_STEM_DGRAD_POOL", "1") != "0"
+        # max pooling fused into the first-layer forward's epilogue (i2v_conv_stem_fwd_pool_f32): the stem activation is never
+        # written.  Bit-identical, but OFF by default on numbers: the pooling runs in the four epilogue warps, in series with the
+        # TMEM drain of the next row, and the fused kernel takes 970 us per 256 frames against 441 + 264 us for the two launches
+        # (profiles/r02_stem_fwd_pool_fused.txt); $I2V_STEM_FWD_POOL=1 enables it
+        self.stem_fwd_pool = os.environ.get("I2V_STEM_FWD_POOL", "0") == "1"
         # first-layer forward without the im2col patch matrix, one output row per tile (i2v_conv_stem_fwd_rows_f32); =0: im2col + GEMM
         self.stem_fwd_rows = os.environ.get("I2V_STEM_FWD_ROWS", "1") != "0"
         # EXPERIMENTAL: first-layer forward without the im2col patch matrix (i2v_conv_stem_fwd_direct_f32)
@@ -472,6 +477,25 @@ class NativeEngine:
         n, P2, Q2, c = plan["acts"][pool.y].shape
         return c == 64 and capi.conv_stem_dgrad_pool_supported(plan["descs"][conv.name], P2, Q2)
 
+    def _stem_pool_fwd(self, plan):
+        """{stem conv name: pool op} when the first layer and the max pooling behind it run as ONE forward kernel
+        (i2v_conv_stem_fwd_pool_f32): the conditions of `_stem_pool_fusable` for the backward fusion — which must be on, the stem
+        activation does not exist for a separate pooling backward's producer — plus the row-tile forward kernel's."""
+        if "stem_pool_fwd" in plan:
+            return plan["stem_pool_fwd"]
+        out = {}
+        if self.stem_fwd_pool and self.stem_fwd_rows:
+            for pool in self.ops:
+                if pool.kind != "pool" or not self._stem_pool_fusable(pool, plan):
+                    continue
+                conv = [o for o in self.ops if o.kind == "conv" and o.y == pool.x][0]
+                n, P2, Q2, c = plan["acts"][pool.y].shape
+                if (conv.relu and conv.tc_stem_fwd is not None and conv.tc_stem_fwd[0].shape == (64, 160)
+                        and capi.conv_stem_fwd_pool_supported(plan["descs"][conv.name], P2, Q2)):
+                    out[conv.name] = pool
+        plan["stem_pool_fwd"] = out
+        return out
+
     def _conv_dgrad(self, op, d, dy, addend, mask_src, dx, mask_bits=None, pooled=None):
         if pooled is not None:
             hi, lo, _ = op.tc_stem_dgrad_direct
@@ -526,11 +550,22 @@ class NativeEngine:
         plan = self._plan(n, h, w, img.device)
         acts = plan["acts"]
         fused_ds = plan["fused_ds"]
+        stem_pool = self._stem_pool_fwd(plan)
+        pooled_by_stem = set()
+        self._stem_act_stale = None
         for op in self.ops:
             if op.kind == "conv":
                 if op.name in fused_ds:
                     continue                                       # runs inside the block's last convolution
                 x = img if op.x == "img" else acts[op.x]
+                if op.name in stem_pool:
+                    pool = stem_pool[op.name]
+                    hi, lo, _ = op.tc_stem_fwd
+                    capi.conv_stem_fwd_pool(plan["descs"][op.name], x, hi, lo, op.bias, acts[pool.y], plan["argmax"][pool.y],
+                                            relu=True, mark_dead=True)
+                    pooled_by_stem.add(id(pool))
+                    self._stem_act_stale = (op, x)                 # acts[op.y] was not written (relu_masks recomputes it on demand)
+                    continue
                 bits_out = plan["bits"].get(op.y) if need_grad else None
                 if op.name in self.dual and self.dual[op.name][0].name in fused_ds:
                     ds, hi, lo, rna, bias = self.dual[op.name]
@@ -540,6 +575,8 @@ class NativeEngine:
                 self._conv_fwd(op, plan["descs"][op.name], x, acts[op.y], acts[op.residual] if op.residual else None,
                                bits_out)
             elif op.kind == "pool":
+                if id(op) in pooled_by_stem:
+                    continue                                       # ran inside the first layer's epilogue
                 # a ReLU output is pooled: windows with nothing > 0 are marked "no winner", which IS the ReLU-backward mask
                 capi.maxpool_fwd(acts[op.x], acts[op.y], plan["argmax"][op.y], op.k, op.stride, op.pad,
                                  mark_dead=op.x in self.relu_typed)
@@ -559,6 +596,11 @@ class NativeEngine:
         order, as [n,C,h,w] bool tensors — the decisions the backward pass uses; None for a ReLU the truncated
         graph does not execute.  For parity tests only (forces a sync)."""
         acts = self._last_fwd["acts"]
+        if getattr(self, "_stem_act_stale", None) is not None:      # the fused forward never wrote the stem activation
+            op, x = self._stem_act_stale
+            hi, lo, _ = op.tc_stem_fwd
+            capi.conv_stem_fwd_rows(self._last_fwd["descs"][op.name], x, hi, lo, op.bias, acts[op.y], relu=op.relu)
+            self._stem_act_stale = None
         out = []
         for op in self.ops:
             if op.kind == "conv" and op.relu:

@@ -323,6 +323,14 @@ int i2v_conv_stem_dgrad_pool_f32(const i2v_conv_desc* d, int P2, int Q2, const f
 int i2v_conv_stem_fwd_rows_supported(const i2v_conv_desc* d);
 int i2v_conv_stem_fwd_rows_f32(const i2v_conv_desc* d, const float* x, const float* wk_hi, const float* wk_lo,
                                const float* bias, float* y, int flags, i2v_stream_t stream);
+/* The same with the 3x3 / stride-2 / pad-1 max pooling behind it (torchvision resnet.py: conv1 -> bn1 -> relu -> maxpool, run by
+ * image_attacks.py:334) fused into the epilogue: pooled [N, P2, Q2, 64] and its argmax plane (window position r*3+s, first
+ * maximum in window order; 255 = no element > 0 when flags has I2V_POOL_MARK_DEAD) come out, bit-identical to
+ * i2v_conv_stem_fwd_rows_f32 followed by i2v_maxpool_fwd_flags_f32; the 4x larger stem activation never reaches HBM.
+ * P and Q even, P2 = P/2, Q2 = Q/2.  flags: I2V_EPI_RELU | I2V_POOL_MARK_DEAD.                                       */
+int i2v_conv_stem_fwd_pool_supported(const i2v_conv_desc* d, int P2, int Q2);
+int i2v_conv_stem_fwd_pool_f32(const i2v_conv_desc* d, int P2, int Q2, const float* x, const float* wk_hi, const float* wk_lo,
+                               const float* bias, float* pooled, uint8_t* argmax, int flags, i2v_stream_t stream);
 int i2v_conv_stem_fwd_tc_f32(const i2v_conv_desc* d, const float* x, const float* wk_hi, const float* wk_lo,
                              const float* bias, float* col_scratch, float* y, int flags, i2v_stream_t stream);
 

@@ -722,6 +722,41 @@ def test_stem_fwd_rows(H, W, n):
     assert err <= (1e-5 + 3 * k * k * 2.0 ** -24), err
 
 
+@pytest.mark.parametrize("H,W,n", [(224, 224, 5), (224, 224, 150), (64, 64, 3), (32, 32, 2), (16, 16, 3), (224, 200, 1), (8, 8, 1),
+                                   (112, 112, 33), (40, 244, 2)])
+@pytest.mark.parametrize("mark_dead", [True, False])
+def test_stem_fwd_pool_fused(H, W, n, mark_dead):
+    """First-layer forward with the 3x3 / stride-2 / pad-1 max pooling fused into its epilogue (strips of pooled rows per CTA,
+    running window maxima in registers, first maximum in window order wins): pooled tensor AND argmax plane bit-identical to
+    i2v_conv_stem_fwd_rows_f32 followed by i2v_maxpool_fwd_f32 — many strips per CTA (150 frames), fewer units than SMs,
+    widths with junk tile lanes, one-pooled-row images; a negative bias makes dead windows common."""
+    from i2v_b200.engine_native import _split_tf32
+    g = torch.Generator().manual_seed(21)
+    Cout, k, s, p = 64, 7, 2, 3
+    x = torch.randn(n, 3, H, W, generator=g).to(DEV)
+    w = torch.randn(Cout, 3, k, k, generator=g) / (3 * k * k) ** 0.5
+    shift = (torch.randn(Cout, generator=g) * 0.3 - 0.4).to(DEV)
+    P, Q = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    P2, Q2 = (P + 2 - 3) // 2 + 1, (Q + 2 - 3) // 2 + 1
+    d = capi.ConvDesc(n, H, W, 3, Cout, k, k, s, p, P, Q)
+    assert capi.conv_stem_fwd_pool_supported(d, P2, Q2)
+    wk = torch.cat([w.reshape(Cout, 147), torch.zeros(Cout, 13)], 1).contiguous().to(DEV)
+    hi, lo, _ = _split_tf32(wk)
+    y = torch.empty(n, P, Q, Cout, device=DEV)
+    capi.conv_stem_fwd_rows(d, x, hi, lo, shift, y, relu=True)
+    want = torch.empty(n, P2, Q2, Cout, device=DEV)
+    want_am = torch.empty(n, P2, Q2, Cout, device=DEV, dtype=torch.uint8)
+    capi.maxpool_fwd(y, want, want_am, 3, 2, 1, mark_dead=mark_dead)
+    for _ in range(2):
+        got = torch.full((n, P2, Q2, Cout), float("nan"), device=DEV)
+        got_am = torch.full((n, P2, Q2, Cout), 77, device=DEV, dtype=torch.uint8)
+        capi.conv_stem_fwd_pool(d, x, hi, lo, shift, got, got_am, relu=True, mark_dead=mark_dead)
+        assert torch.equal(got.view(torch.int32), want.view(torch.int32))
+        assert torch.equal(got_am, want_am)
+    if mark_dead:
+        assert int((want_am == 255).sum()) > 0
+
+
 @pytest.mark.parametrize("H,W,n", [(224, 224, 5), (64, 64, 3), (32, 32, 2), (16, 16, 3), (63, 61, 2), (224, 200, 1), (8, 8, 1)])
 def test_stem_dgrad_direct(H, W, n):
     """First-layer data gradient without scratch (one dy row per tile, on-chip col2im in a register window, half-image

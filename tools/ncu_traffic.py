@@ -10,7 +10,7 @@ import json
 import re
 import sys
 
-FAMILY = [("stem_fwd_rows_kernel", "i2v_conv_stem_fwd_f32"), ("stem_dgrad_pool_kernel", "i2v_conv_stem_dgrad_pool_f32"),
+FAMILY = [("stem_fwd_rows_kernel<(bool)1>", "i2v_conv_stem_fwd_pool_f32"), ("stem_fwd_rows_kernel", "i2v_conv_stem_fwd_f32"), ("stem_dgrad_pool_kernel", "i2v_conv_stem_dgrad_pool_f32"),
           ("stem_dgrad_direct_kernel", "i2v_conv_stem_dgrad_f32"),
           ("conv_tc_persist_kernel", "i2v_conv_tc_f32"), ("conv_tc_pair_kernel", "i2v_conv_tc_f32"),
           ("conv3x3_halo_kernel", "i2v_conv_tc_f32"), ("conv_tc_kernel", "i2v_conv_tc_f32"),
