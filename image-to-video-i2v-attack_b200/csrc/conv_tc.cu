@@ -3284,7 +3284,8 @@ static int halo_launch(const float* src, int N, int H, int W, int C, const float
     a.rows_load = (R + 2) * PW;
     a.patch_bytes = (uint32_t)(((2 * PW + 2 + TC_BM) * 128 + 1023) / 1024 * 1024);
     a.tail_rows = H % R;
-    a.dbg = getenv("I2V_TC_HALO_DBG") ? atoi(getenv("I2V_TC_HALO_DBG")) : 0;
+    static const int halo_dbg = getenv("I2V_TC_HALO_DBG") ? atoi(getenv("I2V_TC_HALO_DBG")) : 0;
+    a.dbg = halo_dbg;
     a.trace = g_trace; a.trace_tiles = g_trace_tiles;
     a.M = M;
     static size_t budget = 0;
@@ -3303,7 +3304,8 @@ static int halo_launch(const float* src, int N, int H, int W, int C, const float
     if (fixed + 2 * bstage > budget) return -1;
     int bst = (int)((budget - fixed) / bstage);
     if (bst > 8) bst = 8;
-    if (getenv("I2V_TC_HALO_BSTAGES") && atoi(getenv("I2V_TC_HALO_BSTAGES")) >= 1 && atoi(getenv("I2V_TC_HALO_BSTAGES")) < bst) bst = atoi(getenv("I2V_TC_HALO_BSTAGES"));
+    static const int bst_env = getenv("I2V_TC_HALO_BSTAGES") ? atoi(getenv("I2V_TC_HALO_BSTAGES")) : 0;     // ring-depth experiments
+    if (bst_env >= 1 && bst_env < bst) bst = bst_env;
     a.bstages = bst;
     CUtensorMap tmX, tmBhi, tmBlo, tmOut, tmTail;
     if (int r = get_map_nhwc_box(&tmX, src, N, H, W, C, PW, R + 2)) return r;
