@@ -23,7 +23,7 @@
 // rewrite each landed A tile into a second shared-memory buffer (element-wise, so the swizzle pattern is
 // preserved).  X3 = false is plain TF32 (one MMA per K-slice), the mode cuDNN uses with allow_tf32.
 //
-// Two kernels live in this file:
+// Kernels in this file (conv3x3_halo_kernel, the CTA-pair kernel and the first-layer kernels are described next to their code):
 //   conv_tc_kernel          (v1) one tile per CTA, 256 threads: warp 0 TMA producer, warp 1 MMA issuer + TMEM allocator,
 //                           warps 4..7 A-split during the main loop, then the epilogue (TMEM -> registers -> 128-bit stores).
 //                           Kept as the simple reference implementation ($I2V_TC_PERSISTENT=0).
@@ -489,6 +489,10 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // ALO_TMEM = the DUAL-ISSUER variant.  Measured (tools/mma_probe.py, profiles/r01_mma_issue_probe.txt): ONE thread
     // issues a tcgen05.mma every ~200 cycles whatever its width (N = 64..256, floor N/2 cycles), while several issuing
     // warps proceed concurrently at that same rate each — the 3xTF32 main loop (8 MMAs per k-step) was issue-bound.
+    // (End of round 2: those 200 cycles were the compiler's waterfall loop around every UTCHMMA of an `if (lane == 0)` role and
+    // the ring's integer divisions — see elect_one() / ring_next() above.  With both gone two issuers still win, because each
+    // keeps its own accumulators and the two instruction streams overlap in the tensor pipe; the A/B is in
+    // profiles/r02_dispatch_ab_per_shape.txt.)
     // So the two MMAs of a k-slice go to two issuers with DISJOINT accumulators: warp 1 issues a_hi x [b_hi | b_lo]
     // (main | cross), warp 2 issues a_lo x b_hi with A_lo read from tensor memory into a third accumulator (cross2);
     // the epilogue adds the three.  TMEM: kAcc stages of [main | cross | cross2] in 384 columns + a 4-slot A_lo ring.
