@@ -30,8 +30,13 @@ for _ in range(K):
     run.step()
 mark("%d steps" % K)
 res = run.finish(); mark("finish (clone, cost log D2H)")
-out_host.copy_(res.adv, non_blocking=True); mark("d2h")
+if os.environ.get("D2H_SPLIT"):
+    adv_c = res.adv.contiguous(); mark("permuting copy on the device")
+    out_host.copy_(adv_c, non_blocking=True); mark("d2h (contiguous source)")
+else:
+    out_host.copy_(res.adv, non_blocking=True); mark("d2h")
 torch.cuda.synchronize()
+mark("sync")
 out = {}
 for (n0, e0, t0), (n1, e1, t1) in zip(marks, marks[1:]):
     out[n1] = {"gpu_ms": round(e0.elapsed_time(e1), 2), "host_ms": round(1e3 * (t1 - t0), 2)}
