@@ -141,6 +141,13 @@ __device__ __forceinline__ bool elect_one() {
 // advance a ring position: `it % stages` / `it / stages` with a run-time divisor cost two emulated integer divisions (~200
 // dependent cycles) per k-step on the single thread that paces the pipeline
 __device__ __forceinline__ void ring_next(int& st, uint32_t& ph, int n) { if (++st == n) { st = 0; ph ^= 1u; } }
+// tile / num_n_tiles for the n-tile counts that occur (1, 2, 4, 8: shifts; anything else: the emulated division) — every role
+// derives its tile coordinates once per tile or sub-tile, the epilogue threads among them
+__device__ __forceinline__ int div_ntiles(int tile, int nn) {
+    if (nn == 1) return tile;
+    if ((nn & (nn - 1)) == 0) return tile >> (31 - __clz(nn));
+    return tile / nn;
+}
 __device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -591,7 +598,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 }
             }
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tno) {
-                const int m_tile = tile / num_n_tiles, n_tile = tile - m_tile * num_n_tiles;
+                const int m_tile = div_ntiles(tile, num_n_tiles), n_tile = tile - m_tile * num_n_tiles;
                 const int64_t m0 = (int64_t)m_tile * TC_BM;
                 const int n0 = n_tile * BN;
                 int img = 0, base_h = 0, base_w = 0;
@@ -607,7 +614,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     for (int d = (tno == 0 ? 1 : args.prefetch_tiles); d <= args.prefetch_tiles; ++d) {
                         const int ptile = tile + d * (int)gridDim.x;
                         if (ptile >= num_tiles) break;
-                        const int pm = ptile / num_n_tiles;
+                        const int pm = div_ntiles(ptile, num_n_tiles);
                         for (int cb = 0; cb < args.cblocks; ++cb) tma_prefetch_l2_2d(&tmA, cb * TC_BK, pm * TC_BM);
                     }
                 }
@@ -718,7 +725,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const uint32_t total = my_tiles * SUBS;
             auto coords = [&](int g, uint32_t k, int& col, int& row) {
                 const int tile = (int)blockIdx.x + (int)(k / SUBS) * (int)gridDim.x;
-                const int m_tile = tile / num_n_tiles, n_tile = tile - m_tile * num_n_tiles;
+                const int m_tile = div_ntiles(tile, num_n_tiles), n_tile = tile - m_tile * num_n_tiles;
                 col = n_tile * BN + (g + 2 * (int)(k % SUBS)) * 32;
                 row = m_tile * TC_BM;
             };
@@ -731,7 +738,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 h = i * args.out_s; w = (rem - i * args.Q) * args.out_s;
             };
             auto refill = [&](int g, uint32_t k) {              // slot k % ns of group g is free: next residual or a plain arrive
-                const uint32_t s = k % ns;
+                const uint32_t s = k & (ns - 1);
                 if (has_res) {
                     int col, row;
                     coords(g, k, col, row);
@@ -755,7 +762,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 for (int g = 0; g < 2; ++g) {
                     const uint32_t k = kdone[g];
                     if (k >= total) continue;
-                    const uint32_t s = k % ns, ph = (k / ns) & 1;
+                    const uint32_t s = k & (ns - 1), ph = (k >> (ns - 1)) & 1;      // ns is 1 or 2: no division
                     if (!mbar_test_wait(&out_ready[g * 2 + s], ph)) continue;
                     int col, row;
                     coords(g, k, col, row);
@@ -856,7 +863,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const uint32_t total = my_tiles * SUBS;
             auto coords = [&](uint32_t k, int& col, int& row) {
                 const int tile = (int)blockIdx.x + (int)(k / SUBS) * (int)gridDim.x;
-                const int m_tile = tile / num_n_tiles, n_tile = tile - m_tile * num_n_tiles;
+                const int m_tile = div_ntiles(tile, num_n_tiles), n_tile = tile - m_tile * num_n_tiles;
                 col = n_tile * BN + (g + 2 * (int)(k % SUBS)) * 32;
                 row = m_tile * TC_BM;
             };
@@ -888,7 +895,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 }
             }
             for (uint32_t k = 0; k < total; ++k) {
-                const uint32_t s = k % ns, ph = (k / ns) & 1;
+                const uint32_t s = k & (ns - 1), ph = (k >> (ns - 1)) & 1;      // ns is 1 or 2: no division
                 mbar_wait(&out_ready[g * 2 + s], ph);           // the group's 128 threads wrote the slot (and fenced)
                 coords(k, col, row);
                 if (col < args.store_cols) {
@@ -929,7 +936,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         uint32_t k = 0;
         int t = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
-            const int m_tile = tile / num_n_tiles, n_tile = tile - m_tile * num_n_tiles;
+            const int m_tile = div_ntiles(tile, num_n_tiles), n_tile = tile - m_tile * num_n_tiles;
             const int n0 = n_tile * BN;
             const int acc = t % kAcc;
             const uint32_t aph = (uint32_t)(t / kAcc) & 1;
@@ -982,7 +989,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             for (int j = 0; j < SUBS; ++j, ++k) {
                 const int c0 = (g + 2 * j) * 32;
                 uint32_t (&a)[32] = vals[j];
-                const uint32_t s = k % ns, ph = (k / ns) & 1;
+                const uint32_t s = k & (ns - 1), ph = (k >> (ns - 1)) & 1;      // ns is 1 or 2: no division
                 mbar_wait(&slot_ready[g * 2 + s], ph);          // residual landed / previous store has read the slot
                 uint8_t* srow = sbase + (size_t)s * EPI_SLOT_BYTES;
                 const float4* bs4 = reinterpret_cast<const float4*>(gbias + n0 + c0);   // warp-uniform: one broadcast per load
@@ -1028,7 +1035,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const float* __restrict__ masks = args.mask_src;
         int t = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++t) {
-            const int m_tile = tile / num_n_tiles, n_tile = tile - m_tile * num_n_tiles;
+            const int m_tile = div_ntiles(tile, num_n_tiles), n_tile = tile - m_tile * num_n_tiles;
             const int n0 = n_tile * BN;
             const int acc = t % kAcc;
             const uint32_t aph = (uint32_t)(t / kAcc) & 1;
@@ -1280,7 +1287,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int it = 0, tno = 0;
             int st = 0; uint32_t ph = 0;               // ring position of k-step `it` (no division in the loop)
             for (int pt = pid; pt < num_ptiles; pt += npairs, ++tno) {
-                const int pm = pt / num_n_tiles, n_tile = pt - pm * num_n_tiles;
+                const int pm = div_ntiles(pt, num_n_tiles), n_tile = pt - pm * num_n_tiles;
                 const int m_tile = 2 * pm + (int)rank;
                 const int64_t m0 = (int64_t)m_tile * TC_BM;
                 const int n0 = n_tile * BN + (int)rank * H;
@@ -1375,12 +1382,12 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t total = my_tiles * SUBS;
             auto coords = [&](int g, uint32_t k, int& col, int& row) {
                 const int pt = pid + (int)(k / SUBS) * npairs;
-                const int pm = pt / num_n_tiles, n_tile = pt - pm * num_n_tiles;
+                const int pm = div_ntiles(pt, num_n_tiles), n_tile = pt - pm * num_n_tiles;
                 col = n_tile * BN + (g + 2 * (int)(k % SUBS)) * 32;
                 row = (2 * pm + (int)rank) * TC_BM;
             };
             auto refill = [&](int g, uint32_t k) {
-                const uint32_t s = k % ns;
+                const uint32_t s = k & (ns - 1);
                 if (has_res) {
                     int col, row;
                     coords(g, k, col, row);
@@ -1399,7 +1406,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int g = 0; g < 2; ++g) {
                     const uint32_t k = kdone[g];
                     if (k >= total) continue;
-                    const uint32_t s = k % ns, ph = (k / ns) & 1;
+                    const uint32_t s = k & (ns - 1), ph = (k >> (ns - 1)) & 1;      // ns is 1 or 2: no division
                     if (!mbar_test_wait(&out_ready[g * 2 + s], ph)) continue;
                     int col, row;
                     coords(g, k, col, row);
@@ -1459,7 +1466,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t k = 0;
         int t = 0;
         for (int pt = pid; pt < num_ptiles; pt += npairs, ++t) {
-            const int pm = pt / num_n_tiles, n_tile = pt - pm * num_n_tiles;
+            const int pm = div_ntiles(pt, num_n_tiles), n_tile = pt - pm * num_n_tiles;
             const int m_tile = 2 * pm + (int)rank;
             const int n0 = n_tile * BN;
             const int acc = t % kAcc;
@@ -1500,7 +1507,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < SUBS; ++j, ++k) {
                 const int c0 = (g + 2 * j) * 32;
                 uint32_t (&a)[32] = vals[j];
-                const uint32_t s = k % ns, ph = (k / ns) & 1;
+                const uint32_t s = k & (ns - 1), ph = (k >> (ns - 1)) & 1;      // ns is 1 or 2: no division
                 mbar_wait(&slot_ready[g * 2 + s], ph);
                 uint8_t* srow = sbase + (size_t)s * EPI_SLOT_BYTES;
                 const float4* bs4 = reinterpret_cast<const float4*>(gbias + n0 + c0);
@@ -2286,7 +2293,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 
     // tile -> (image, first output row, first output channel)
     auto tile_of = [&](int tile, int& img, int& p0, int& n0, bool& tail) {
-        const int mt = tile / num_n_tiles;
+        const int mt = div_ntiles(tile, num_n_tiles);
         n0 = (tile - mt * num_n_tiles) * BN;
         img = mt / args.TI;
         const int ti = mt - img * args.TI;
